@@ -1,0 +1,440 @@
+// selection_filter.cu -- Filter for fixed-width (and dictionary-index) columns, the
+// filter-output-size pre-pass, and mask -> take-indices.
+//
+// Replaces:
+//   GetFilterOutputSize / GetBitmapFilterOutputSize   kernels/vector_selection_filter_internal.cc:62-114
+//   PrimitiveFilterExec + PrimitiveFilterImpl<W>      :158-510
+//   DictionaryFilterExec (filters the index column)   :871-881
+//   GetTakeIndices (bitmap filter -> uint16/uint32 indices)
+//                                                     kernels/vector_selection_take_internal.cc:62-305
+// Semantics kept (FilterOptions, compute/api_vector.h:37-51): DROP keeps rows whose mask
+// slot is valid and true; EMIT_NULL additionally keeps rows whose mask slot is null and
+// emits a null there; output validity = values validity AND mask validity compacted
+// alongside; the output carries a validity bitmap iff values or mask may have nulls.
+//
+// B200 design (three launches, all HBM streaming, no atomics on the data path):
+//   1. filter_count_kernel : one warp per 4096-row tile popcounts the selection words
+//      (mask data &/| mask validity) -> per-tile counts.           reads bitmaps only
+//   2. tile_scan_kernel    : exclusive scan of the tile counts (one CTA). tiny
+//   3. filter_compact_kernel<W>: one CTA per tile.  Warp 0 rebuilds the tile's 64
+//      selection words and their prefix popcounts in shared memory; then every lane
+//      streams its rows with 16-byte coalesced loads (skipped when none of its rows is
+//      selected), and stores survivors at base + prefix + popc(lower bits): ranks are
+//      dense and monotonic across a warp, so each store instruction writes one
+//      contiguous span.  Validity bits are compacted into a shared-memory bitmap and
+//      flushed with plain word stores (atomicOr only on the two boundary words).
+// Algorithmic bytes/row (int64, values nullable, mask non-null, s=0.5): 12.3125
+// (SURVEY section 8d); passes 1+2 re-read only the bitmaps (+0.25 B/row).
+#include "bitmap.h"
+#include "common.cuh"
+#include "context.h"
+
+namespace b2 {
+
+constexpr int kTileRows = 4096;  // rows per compaction tile = 64 bitmap words
+constexpr int kTileWords = kTileRows / 64;
+
+struct FilterBitmaps {
+  BitmapReader mask_data, mask_valid, values_valid;
+  int emit_null;
+  // selection word: DROP = data & valid ; EMIT_NULL = data | ~valid
+  __device__ __forceinline__ uint64_t sel(int64_t w) const {
+    uint64_t d = mask_data.word(w);
+    if (!mask_valid.present()) return d;
+    uint64_t v = mask_valid.word(w);
+    if (!emit_null) return d & v;
+    // ~v must not leak past nbits: build the in-range mask from an all-ones reader
+    int64_t rem = mask_data.nbits - (w << 6);
+    uint64_t in_range = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1ull));
+    return (d | ~v) & in_range;
+  }
+  // validity of the selected rows before compaction
+  __device__ __forceinline__ uint64_t out_valid(int64_t w) const {
+    return values_valid.word(w) & mask_valid.word(w);
+  }
+};
+
+// ---- pass 1: per-tile selected counts (+ total valid-and-selected) ----
+__global__ void __launch_bounds__(kBlock) filter_count_kernel(FilterBitmaps fb, int64_t n_tiles,
+                                                              uint32_t* tile_counts,
+                                                              int64_t* total_valid, bool want_valid) {
+  const unsigned lane = lane_id();
+  int64_t valid_local = 0;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < n_tiles;
+       tile += (int64_t)gridDim.x * kWarpsPerBlock) {
+    int64_t w0 = tile * kTileWords + 2 * lane;
+    uint64_t s0 = fb.sel(w0), s1 = fb.sel(w0 + 1);
+    int c = __popcll(s0) + __popcll(s1);
+    if (want_valid) valid_local += __popcll(s0 & fb.out_valid(w0)) + __popcll(s1 & fb.out_valid(w0 + 1));
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) tile_counts[tile] = static_cast<uint32_t>(c);
+  }
+  if (want_valid) {
+    int64_t s = block_sum<kBlock>(valid_local);
+    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(total_valid), (unsigned long long)s);
+  }
+}
+
+// ---- pass 2: exclusive scan of tile counts -> int64 offsets[n_tiles + 1] ----
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* counts, int64_t n_tiles,
+                                                         int64_t* offsets, int64_t* total) {
+  __shared__ int64_t warp_tot[32];
+  const int t = threadIdx.x;
+  int64_t per = (n_tiles + 1023) / 1024;
+  int64_t lo = t * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+  int64_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += counts[i];
+  // block exclusive scan of `sum`
+  int64_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int64_t w = warp_tot[t];
+    int64_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += v;
+    }
+    warp_tot[t] = wi - w;  // exclusive
+    if (t == 31) {
+      offsets[n_tiles] = wi;
+      if (total) *total = wi;
+    }
+  }
+  __syncthreads();
+  int64_t run = incl - sum + warp_tot[t >> 5];
+  for (int64_t i = lo; i < hi; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+}
+
+// ---- pass 3: compaction ----
+template <int W>
+struct RowBytes;
+template <> struct RowBytes<1> { using type = uint8_t; };
+template <> struct RowBytes<2> { using type = uint16_t; };
+template <> struct RowBytes<4> { using type = uint32_t; };
+template <> struct RowBytes<8> { using type = uint64_t; };
+template <> struct RowBytes<16> { using type = uint4; };
+
+template <typename T>
+__device__ __forceinline__ T iota_value(int64_t x) {
+  return static_cast<T>(x);
+}
+template <>
+__device__ __forceinline__ uint4 iota_value<uint4>(int64_t x) {
+  return make_uint4(static_cast<unsigned>(x), static_cast<unsigned>(x >> 32), 0u, 0u);
+}
+
+struct FilterArgs {
+  FilterBitmaps fb;
+  const void* values;  // already advanced by offset * W
+  void* out;
+  uint32_t* out_validity;  // zero-initialised, or NULL
+  const int64_t* tile_offsets;
+  int64_t n;
+  bool vec_ok;
+};
+
+// IOTA: the "value" of row r is r itself (GetTakeIndices); W = index width
+template <int W, bool HAS_VALID, bool IOTA>
+__global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
+  using T = typename RowBytes<W>::type;
+  constexpr int R = 16 / W;                      // rows per lane per 16-byte load
+  constexpr int kPassRows = kBlock * R;          // rows per CTA pass
+  constexpr int kPasses = kTileRows / kPassRows; // W=8: 8, W=4: 4, W=1: 1
+  static_assert(kPasses >= 1, "tile too small");
+  __shared__ uint64_t s_sel[kTileWords];
+  __shared__ uint64_t s_ov[kTileWords];
+  __shared__ uint32_t s_prefix[kTileWords];
+  __shared__ uint32_t s_bits[kTileRows / 32 + 2];
+
+  const int64_t tile = blockIdx.x;
+  const int64_t row0 = tile * kTileRows;
+  const int64_t out_base = a.tile_offsets[tile];
+  const unsigned lane = lane_id();
+
+  if (threadIdx.x < 32) {
+    int64_t w0 = tile * kTileWords + 2 * lane;
+    uint64_t s0 = a.fb.sel(w0), s1 = a.fb.sel(w0 + 1);
+    int c0 = __popcll(s0), c1 = __popcll(s1);
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int excl = incl - c0 - c1;
+    s_sel[2 * lane] = s0;
+    s_sel[2 * lane + 1] = s1;
+    s_prefix[2 * lane] = excl;
+    s_prefix[2 * lane + 1] = excl + c0;
+    if (HAS_VALID) {
+      s_ov[2 * lane] = a.fb.out_valid(w0);
+      s_ov[2 * lane + 1] = a.fb.out_valid(w0 + 1);
+    }
+  }
+  if (HAS_VALID) {
+    for (int i = threadIdx.x; i < kTileRows / 32 + 2; i += kBlock) s_bits[i] = 0;
+  }
+  __syncthreads();
+
+  T* out = static_cast<T*>(a.out) + out_base;
+  const T* vals = static_cast<const T*>(a.values);
+  const unsigned bit_base = static_cast<unsigned>(out_base & 31);
+
+  // phase A: issue every pass's 16-byte load before the first dependent store so
+  // kPasses requests per lane are in flight (guide, Guideline 7)
+  uint4 raw[kPasses];
+  unsigned pbits[kPasses];
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = p * kPassRows + threadIdx.x * R;  // row within tile, multiple of R
+    const uint64_t selw = s_sel[r >> 6];
+    pbits[p] = static_cast<unsigned>(selw >> (r & 63)) & ((1u << R) - 1u);
+    const int64_t grow = row0 + r;
+    if (!IOTA && pbits[p] != 0) {
+      if (a.vec_ok && grow + R <= a.n) {
+        raw[p] = __ldcs(reinterpret_cast<const uint4*>(vals + grow));
+      } else {
+        T tmp[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) tmp[k] = ((pbits[p] >> k) & 1) ? vals[grow + k] : T{};
+        memcpy(&raw[p], tmp, 16);
+      }
+    }
+  }
+  // phase B: scatter survivors; ranks are dense and ascending across the warp
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const unsigned bits = pbits[p];
+    if (bits == 0) continue;
+    const int r = p * kPassRows + threadIdx.x * R;
+    const uint64_t selw = s_sel[r >> 6];
+    const unsigned rank = s_prefix[r >> 6] + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+    T v[R];
+    if (IOTA) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = iota_value<T>(row0 + r + k);
+    } else {
+      memcpy(v, &raw[p], 16);
+    }
+    unsigned j = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if ((bits >> k) & 1) {
+        out[rank + j] = v[k];
+        ++j;
+      }
+    }
+    if (HAS_VALID) {
+      const unsigned vb = static_cast<unsigned>(s_ov[r >> 6] >> (r & 63)) & ((1u << R) - 1u);
+      unsigned cb = 0;
+      j = 0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if ((bits >> k) & 1) {
+          cb |= ((vb >> k) & 1u) << j;
+          ++j;
+        }
+      }
+      if (cb) {
+        const unsigned q = bit_base + rank;
+        atomicOr(&s_bits[q >> 5], cb << (q & 31));
+        if ((q & 31) + j > 32) atomicOr(&s_bits[(q >> 5) + 1], cb >> (32 - (q & 31)));
+      }
+    }
+  }
+  if (HAS_VALID) {
+    __syncthreads();
+    const unsigned count = static_cast<unsigned>(a.tile_offsets[tile + 1] - out_base);
+    const unsigned q_end = bit_base + count;  // bits [bit_base, q_end) belong to this tile
+    uint32_t* gw = a.out_validity + (out_base >> 5);
+    for (unsigned i = threadIdx.x; i * 32 < q_end; i += kBlock) {
+      uint32_t wv = s_bits[i];
+      bool full = (i * 32 >= bit_base) && ((i + 1) * 32 <= q_end);
+      if (full) gw[i] = wv;
+      else if (wv) atomicOr(&gw[i], wv);
+    }
+  }
+}
+
+static int64_t tiles_for(int64_t n) { return (n + kTileRows - 1) / kTileRows; }
+
+// passes 1+2; returns device tile offsets (caller frees), output length and selected-valid count
+static int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_valid,
+                       Temp* offsets, int64_t* out_length, int64_t* out_valid, cudaStream_t s) {
+  int64_t n_tiles = tiles_for(n);
+  Temp counts(ctx, s);
+  B2_RETURN_NOT_OK(counts.alloc(n_tiles * sizeof(uint32_t)));
+  B2_RETURN_NOT_OK(offsets->alloc((n_tiles + 1) * sizeof(int64_t)));
+  ScalarSlot slot(ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  int grid = grid_for(n_tiles, kWarpsPerBlock, kSMs * 8);
+  filter_count_kernel<<<grid, kBlock, 0, s>>>(fb, n_tiles, counts.as<uint32_t>(), slot.dev() + 1,
+                                              want_valid);
+  B2_LAUNCHED();
+  tile_scan_kernel<<<1, 1024, 0, s>>>(counts.as<uint32_t>(), n_tiles, offsets->as<int64_t>(),
+                                      slot.dev());
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  *out_length = slot.host()[0];
+  *out_valid = slot.host()[1];
+  return B2_OK;
+}
+
+static int check_mask(const B2Array* mask) {
+  if (!mask) return set_error(B2_INVALID, "filter: null mask");
+  if (mask->type != B2_BOOL) return set_error(B2_TYPE_ERROR, "filter mask must be a boolean array");
+  if (mask->length < 0 || mask->offset < 0) return set_error(B2_INVALID, "negative length/offset");
+  return B2_OK;
+}
+
+static FilterBitmaps make_bitmaps(const B2Array* values, const B2Array* mask, int null_selection) {
+  FilterBitmaps fb;
+  fb.mask_data = BitmapReader(mask->data, mask->offset, mask->length);
+  fb.mask_valid = BitmapReader(mask->null_count == 0 ? nullptr : mask->validity, mask->offset, mask->length);
+  fb.values_valid = values ? BitmapReader(values->null_count == 0 ? nullptr : values->validity,
+                                          values->offset, values->length)
+                           : BitmapReader(nullptr, 0, mask->length);
+  fb.emit_null = null_selection == 1;
+  return fb;
+}
+
+template <bool IOTA>
+static int launch_compact(int width, bool has_valid, const FilterArgs& a, int64_t n_tiles, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>(n_tiles));
+#define B2_FC(W)                                                                          \
+  case W:                                                                                 \
+    if (has_valid) filter_compact_kernel<W, true, IOTA><<<grid, kBlock, 0, s>>>(a);       \
+    else filter_compact_kernel<W, false, IOTA><<<grid, kBlock, 0, s>>>(a);                \
+    break;
+  switch (width) {
+    B2_FC(1) B2_FC(2) B2_FC(4) B2_FC(8) B2_FC(16)
+    default: return set_error(B2_NOT_IMPLEMENTED, "filter: unsupported byte width %d", width);
+  }
+#undef B2_FC
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+int filter_binary(B2Context* ctx, const B2Array* values, const B2Array* mask, int null_selection,
+                  B2Array* out, cudaStream_t s);  // selection_binary.cu
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_filter_output_size(B2Context* ctx, const B2Array* mask, int null_selection,
+                                     int64_t* out_length, void* stream) {
+  if (!ctx || !out_length) return set_error(B2_INVALID, "b2_filter_output_size: null argument");
+  B2_RETURN_NOT_OK(check_mask(mask));
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  *out_length = 0;
+  if (mask->length == 0) return B2_OK;
+  FilterBitmaps fb = make_bitmaps(nullptr, mask, null_selection);
+  Temp offsets(ctx, s);
+  int64_t valid;
+  return filter_plan(ctx, fb, mask->length, false, &offsets, out_length, &valid, s);
+}
+
+extern "C" int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* mask,
+                         int null_selection, B2Array* out, void* stream) {
+  if (!ctx || !values || !out) return set_error(B2_INVALID, "b2_filter: null argument");
+  B2_RETURN_NOT_OK(check_mask(mask));
+  if (values->length != mask->length)
+    return set_error(B2_INVALID, "Filter inputs must all be the same length");
+  if (null_selection != 0 && null_selection != 1) return set_error(B2_INVALID, "bad null_selection");
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  if (type_is_binary_like(values->type)) return filter_binary(ctx, values, mask, null_selection, out, s);
+  int width = values->type == B2_FIXED_SIZE_BINARY ? values->byte_width : type_width(values->type);
+  if (width != 1 && width != 2 && width != 4 && width != 8 && width != 16)
+    return set_error(B2_NOT_IMPLEMENTED, "filter: unsupported value type id %d (width %d)", values->type, width);
+  const int64_t n = values->length;
+  const bool has_valid = (values->null_count != 0 && values->validity) ||
+                         (mask->null_count != 0 && mask->validity);
+  if (n == 0) {
+    fill_out(out, values->type, 0, 0, nullptr, nullptr);
+    out->byte_width = values->byte_width;
+    return B2_OK;
+  }
+  FilterBitmaps fb = make_bitmaps(values, mask, null_selection);
+  Temp offsets(ctx, s);
+  int64_t out_len = 0, out_valid = 0;
+  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));
+
+  Temp data(ctx, s), bits(ctx, s);
+  B2_RETURN_NOT_OK(data.alloc(static_cast<size_t>(out_len) * width));
+  if (has_valid) {
+    B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(out_len)));
+    B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(out_len), s));
+  }
+  if (out_len > 0) {
+    FilterArgs a;
+    a.fb = fb;
+    a.values = static_cast<const char*>(values->data) + values->offset * width;
+    a.out = data.ptr;
+    a.out_validity = bits.as<uint32_t>();
+    a.tile_offsets = offsets.as<int64_t>();
+    a.n = n;
+    a.vec_ok = aligned_to(a.values, 16);
+    B2_RETURN_NOT_OK(launch_compact<false>(width, has_valid, a, tiles_for(n), s));
+  }
+  int64_t null_count = has_valid ? out_len - out_valid : 0;
+  fill_out(out, values->type, out_len, null_count, has_valid ? bits.release() : nullptr, data.release());
+  out->byte_width = values->byte_width;
+  return B2_OK;
+}
+
+extern "C" int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_selection,
+                                 B2Array* out, void* stream) {
+  if (!ctx || !out) return set_error(B2_INVALID, "b2_filter_indices: null argument");
+  B2_RETURN_NOT_OK(check_mask(mask));
+  // vector_selection_take_internal.cc:262-271
+  if (mask->length > 0xffffffffll)
+    return set_error(B2_NOT_IMPLEMENTED, "Filter length exceeds UINT32_MAX, consider a different strategy for selecting elements");
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = mask->length;
+  const int out_type = n <= 0xffff ? B2_UINT16 : B2_UINT32;  // :298-305
+  const int width = n <= 0xffff ? 2 : 4;
+  if (n == 0) {
+    fill_out(out, out_type, 0, 0, nullptr, nullptr);
+    return B2_OK;
+  }
+  const bool has_valid = null_selection == 1 && mask->null_count != 0 && mask->validity;
+  FilterBitmaps fb = make_bitmaps(nullptr, mask, null_selection);
+  Temp offsets(ctx, s);
+  int64_t out_len = 0, out_valid = 0;
+  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));
+  Temp data(ctx, s), bits(ctx, s);
+  B2_RETURN_NOT_OK(data.alloc(static_cast<size_t>(out_len) * width));
+  if (has_valid) {
+    B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(out_len)));
+    B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(out_len), s));
+  }
+  if (out_len > 0) {
+    FilterArgs a;
+    a.fb = fb;
+    a.values = nullptr;
+    a.out = data.ptr;
+    a.out_validity = bits.as<uint32_t>();
+    a.tile_offsets = offsets.as<int64_t>();
+    a.n = n;
+    a.vec_ok = false;
+    B2_RETURN_NOT_OK(launch_compact<true>(width, has_valid, a, tiles_for(n), s));
+  }
+  int64_t null_count = has_valid ? out_len - out_valid : 0;
+  fill_out(out, out_type, out_len, null_count, (has_valid && null_count) ? bits.release() : nullptr,
+           data.release());
+  return B2_OK;
+}

@@ -1,0 +1,285 @@
+// selection_take.cu -- Take (gather) for fixed-width and dictionary-index columns.
+//
+// Replaces:
+//   FixedWidthTakeExec + FixedWidthTakeImpl      kernels/vector_selection_take_internal.cc:336-468
+//   Gather<..>::Execute / GatherBaseCRTP::ExecuteWithNulls   kernels/gather_internal.h:84-251
+//   CheckIndexBounds                             util/int_util.cc:452-560 (IndexError)
+//   DictionaryTake (takes the index column)      kernels/vector_selection_take_internal.cc:488-497
+// Semantics kept: out[i] = values[idx[i]]; out valid = idx valid AND values valid at
+// idx[i]; signed index types are bounds-checked then reinterpreted as unsigned; null
+// indices are never dereferenced and produce a zero-filled null slot; with boundscheck
+// the first out-of-range VALID index raises IndexError("Index <v> out of bounds").
+//
+// B200 design: one streaming pass.  Each lane loads V consecutive indices with one
+// 16-byte coalesced load per unroll step (U steps issued back to back => U*V independent
+// gathers in flight per lane, the only way to cover random-access DRAM latency), gathers
+// values and validity bits, stores V results with one vector store, and the warp packs
+// its 32*V validity bits into V words with redux.sync.  The gather itself is sector-
+// granular (32 B fetched per 8 B element for random indices): algorithmic bytes/row are
+// idx + 2*W + 2/8 (24.25 for int64 idx / float64) but DRAM traffic
+// for uniformly random indices is ~idx + 32 + W.
+#include <type_traits>
+
+#include "bitmap.h"
+#include "elementwise.cuh"
+
+namespace b2 {
+
+template <int W>
+struct TakeBytes;
+template <> struct TakeBytes<1> { using type = uint8_t; };
+template <> struct TakeBytes<2> { using type = uint16_t; };
+template <> struct TakeBytes<4> { using type = uint32_t; };
+template <> struct TakeBytes<8> { using type = uint64_t; };
+template <> struct TakeBytes<16> { using type = uint4; };
+
+template <typename T>
+__device__ __forceinline__ T zero_value() {
+  return T{};
+}
+template <>
+__device__ __forceinline__ uint4 zero_value<uint4>() {
+  return make_uint4(0, 0, 0, 0);
+}
+
+struct TakeArgs {
+  const void* values;  // advanced by offset * W
+  BitmapReader values_valid;
+  int64_t values_length;
+  const void* indices;  // advanced by offset * sizeof(Idx)
+  BitmapReader idx_valid;
+  int64_t n;
+  void* out;
+  uint32_t* out_validity;  // NULL when no validity is produced
+  int64_t* valid_count;    // device counter (popcount of out validity)
+  unsigned long long* first_bad;  // device, ~0 initially
+  bool vec_ok;
+};
+
+// pack each lane's V bits (bit k = element lane*V+k) into V warp-wide words;
+// lane j < V returns word j
+template <int V>
+__device__ __forceinline__ unsigned warp_pack_bits(unsigned m, unsigned lane) {
+  const unsigned my_word = (lane * V) >> 5;
+  const unsigned shifted = m << ((lane * V) & 31);
+  unsigned mine = 0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    unsigned w = __reduce_or_sync(0xffffffffu, my_word == j ? shifted : 0u);
+    if (lane == j) mine = w;
+  }
+  return mine;
+}
+
+template <int W, typename Idx, bool HAS_VALID>
+__global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
+  using T = typename TakeBytes<W>::type;
+  constexpr int V = 16 / (sizeof(Idx) > W ? sizeof(Idx) : W);
+  constexpr int UU = kUnroll;
+  constexpr int64_t kWarpTile = 32 * V * UU;
+  constexpr int64_t kTile = kWarpTile * kWarpsPerBlock;
+  const unsigned lane = lane_id();
+  const T* __restrict__ vals = static_cast<const T*>(a.values);
+  const Idx* __restrict__ idx = static_cast<const Idx*>(a.indices);
+  T* __restrict__ out = static_cast<T*>(a.out);
+  const uint64_t vlen = static_cast<uint64_t>(a.values_length);
+  int64_t valid_local = 0;
+
+  for (int64_t tile = (int64_t)blockIdx.x * kTile; tile < a.n; tile += (int64_t)gridDim.x * kTile) {
+    int64_t wb = tile + (int64_t)(threadIdx.x >> 5) * kWarpTile;
+    if (wb >= a.n) continue;
+    if (a.vec_ok && wb + kWarpTile <= a.n) {
+      Vec<Idx, V> ix[UU];
+      unsigned ivalid[UU];
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        int64_t i0 = wb + u * 32 * V + lane * V;
+        ix[u] = load_vec<Idx, V>(idx + i0);
+        // i0 is a multiple of V and V divides 64: the V bits never straddle a word
+        ivalid[u] = HAS_VALID ? static_cast<unsigned>(a.idx_valid.word(i0 >> 6) >> (i0 & 63)) & ((1u << V) - 1u)
+                              : ((1u << V) - 1u);
+      }
+      Vec<T, V> g[UU];
+      unsigned gvalid[UU];
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        gvalid[u] = 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          // signed -> unsigned reinterpretation after the bounds check (gather_internal.h)
+          uint64_t j = static_cast<uint64_t>(static_cast<int64_t>(ix[u].v[k]));
+          if (std::is_unsigned<Idx>::value) j = static_cast<uint64_t>(ix[u].v[k]);
+          bool iv = (ivalid[u] >> k) & 1;
+          bool inb = j < vlen;
+          if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(wb + u * 32 * V + lane * V + k));
+          if (iv && inb) {
+            g[u].v[k] = __ldg(vals + j);
+            if (HAS_VALID) gvalid[u] |= (a.values_valid.bit(static_cast<int64_t>(j)) ? 1u : 0u) << k;
+          } else {
+            g[u].v[k] = zero_value<T>();
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        int64_t i0 = wb + u * 32 * V + lane * V;
+        store_vec<T, V>(out + i0, g[u]);
+        if (HAS_VALID) {
+          unsigned w = warp_pack_bits<V>(gvalid[u], lane);
+          if (lane < V) {
+            a.out_validity[((wb + u * 32 * V) >> 5) + lane] = w;
+            valid_local += __popc(w);
+          }
+        }
+      }
+    } else {
+      int64_t end = wb + kWarpTile < a.n ? wb + kWarpTile : a.n;
+      for (int64_t base = wb; base < end; base += 32) {
+        int64_t i = base + lane;
+        bool ov = false;
+        if (i < end) {
+          bool iv = HAS_VALID ? a.idx_valid.bit(i) : true;
+          Idx raw = idx[i];
+          uint64_t j = std::is_unsigned<Idx>::value ? static_cast<uint64_t>(raw)
+                                                    : static_cast<uint64_t>(static_cast<int64_t>(raw));
+          bool inb = j < vlen;
+          if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(i));
+          if (iv && inb) {
+            out[i] = __ldg(vals + j);
+            ov = HAS_VALID ? a.values_valid.bit(static_cast<int64_t>(j)) : true;
+          } else {
+            out[i] = zero_value<T>();
+          }
+        }
+        if (HAS_VALID) {
+          unsigned w = __ballot_sync(0xffffffffu, ov);
+          if (lane == 0) {
+            a.out_validity[base >> 5] = w;
+            valid_local += __popc(w);
+          }
+        }
+      }
+    }
+  }
+  if (HAS_VALID) {
+    int64_t s = block_sum<kBlock>(valid_local);
+    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(a.valid_count), (unsigned long long)s);
+  }
+}
+
+template <int W, typename Idx>
+static int launch_take(const TakeArgs& a, bool has_valid, cudaStream_t s) {
+  constexpr int V = 16 / (sizeof(Idx) > W ? sizeof(Idx) : W);
+  constexpr int64_t kTile = (int64_t)32 * V * kUnroll * kWarpsPerBlock;
+  int grid = grid_for(a.n, kTile, kSMs * 8 * 16);
+  if (has_valid) take_kernel<W, Idx, true><<<grid, kBlock, 0, s>>>(a);
+  else take_kernel<W, Idx, false><<<grid, kBlock, 0, s>>>(a);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+template <int W>
+static int launch_take_w(int idx_type, const TakeArgs& a, bool has_valid, cudaStream_t s) {
+  switch (idx_type) {
+    case B2_INT8: return launch_take<W, int8_t>(a, has_valid, s);
+    case B2_UINT8: return launch_take<W, uint8_t>(a, has_valid, s);
+    case B2_INT16: return launch_take<W, int16_t>(a, has_valid, s);
+    case B2_UINT16: return launch_take<W, uint16_t>(a, has_valid, s);
+    case B2_INT32: return launch_take<W, int32_t>(a, has_valid, s);
+    case B2_UINT32: return launch_take<W, uint32_t>(a, has_valid, s);
+    case B2_INT64: return launch_take<W, int64_t>(a, has_valid, s);
+    case B2_UINT64: return launch_take<W, uint64_t>(a, has_valid, s);
+    default: return set_error(B2_TYPE_ERROR, "take: indices must be an integer array (type id %d)", idx_type);
+  }
+}
+
+int take_binary(B2Context* ctx, const B2Array* values, const B2Array* indices, int boundscheck,
+                B2Array* out, cudaStream_t s);  // selection_binary.cu
+
+// Reads the offending index back for the IndexError message (util/int_util.cc:554-555)
+int index_error(const B2Array* indices, uint64_t row, cudaStream_t s) {
+  int iw = type_width(indices->type);
+  uint64_t raw = 0;
+  B2_CUDA(cudaMemcpyAsync(&raw, static_cast<const char*>(indices->data) + (indices->offset + row) * iw, iw,
+                          cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  bool is_signed = indices->type == B2_INT8 || indices->type == B2_INT16 || indices->type == B2_INT32 ||
+                   indices->type == B2_INT64;
+  if (is_signed) {
+    int64_t v = iw == 1 ? (int8_t)raw : iw == 2 ? (int16_t)raw : iw == 4 ? (int32_t)raw : (int64_t)raw;
+    return set_error(B2_INDEX_ERROR, "Index %lld out of bounds", (long long)v);
+  }
+  return set_error(B2_INDEX_ERROR, "Index %llu out of bounds", (unsigned long long)raw);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* indices, int boundscheck,
+                       B2Array* out, void* stream) {
+  if (!ctx || !values || !indices || !out) return set_error(B2_INVALID, "b2_take: null argument");
+  if (values->length < 0 || indices->length < 0 || values->offset < 0 || indices->offset < 0)
+    return set_error(B2_INVALID, "negative length/offset");
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  if (type_is_binary_like(values->type)) return take_binary(ctx, values, indices, boundscheck, out, s);
+  int width = values->type == B2_FIXED_SIZE_BINARY ? values->byte_width : type_width(values->type);
+  if (width != 1 && width != 2 && width != 4 && width != 8 && width != 16)
+    return set_error(B2_NOT_IMPLEMENTED, "take: unsupported value type id %d (width %d)", values->type, width);
+  int iw = type_width(indices->type);
+  if (iw == 0 || indices->type == B2_FLOAT || indices->type == B2_DOUBLE || indices->type == B2_HALF_FLOAT)
+    return set_error(B2_TYPE_ERROR, "take: indices must be an integer array (type id %d)", indices->type);
+  const int64_t n = indices->length;
+  if (n == 0) {
+    fill_out(out, values->type, 0, 0, nullptr, nullptr);
+    out->byte_width = values->byte_width;
+    return B2_OK;
+  }
+  const bool has_valid = (values->null_count != 0 && values->validity) ||
+                         (indices->null_count != 0 && indices->validity);
+  Temp data(ctx, s), bits(ctx, s);
+  B2_RETURN_NOT_OK(data.alloc(static_cast<size_t>(n) * width));
+  size_t bit_bytes = bitmap_alloc_bytes(n);
+  if (has_valid) {
+    B2_RETURN_NOT_OK(bits.alloc(bit_bytes));
+    size_t tail = bit_bytes >= 24 ? bit_bytes - 24 : 0;
+    B2_CUDA(cudaMemsetAsync(static_cast<char*>(bits.ptr) + tail, 0, bit_bytes - tail, s));
+  }
+  ScalarSlot slot(ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  B2_CUDA(cudaMemsetAsync(slot.dev() + 1, 0xff, 8, s));
+  TakeArgs a;
+  a.values = static_cast<const char*>(values->data) + values->offset * width;
+  a.values_valid = BitmapReader(values->null_count == 0 ? nullptr : values->validity, values->offset, values->length);
+  a.values_length = values->length;
+  a.indices = static_cast<const char*>(indices->data) + indices->offset * iw;
+  a.idx_valid = BitmapReader(indices->null_count == 0 ? nullptr : indices->validity, indices->offset, n);
+  a.n = n;
+  a.out = data.ptr;
+  a.out_validity = bits.as<uint32_t>();
+  a.valid_count = slot.dev();
+  a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 1);
+  a.vec_ok = aligned_to(a.indices, 16) && aligned_to(a.out, 16);
+  int st;
+  switch (width) {
+    case 1: st = launch_take_w<1>(indices->type, a, has_valid, s); break;
+    case 2: st = launch_take_w<2>(indices->type, a, has_valid, s); break;
+    case 4: st = launch_take_w<4>(indices->type, a, has_valid, s); break;
+    case 8: st = launch_take_w<8>(indices->type, a, has_valid, s); break;
+    default: st = launch_take_w<16>(indices->type, a, has_valid, s); break;
+  }
+  if (st != B2_OK) return st;
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  uint64_t bad = static_cast<uint64_t>(slot.host()[1]);
+  if (bad != ~0ull) {
+    // without boundscheck the reference's behaviour is undefined; we still refuse to
+    // return garbage silently
+    return index_error(indices, bad, s);
+  }
+  int64_t null_count = has_valid ? n - slot.host()[0] : 0;
+  fill_out(out, values->type, n, null_count, (has_valid && null_count) ? bits.release() : nullptr, data.release());
+  out->byte_width = values->byte_width;
+  (void)boundscheck;
+  return B2_OK;
+}

@@ -1,0 +1,322 @@
+/*
+ * arrow_b200.h -- C-ABI of the B200-native execution layer for arrow::compute's
+ * ExecBatch hot path (Filter/Take, Cast, arithmetic/compare, SortIndices,
+ * Grouper + hash aggregates).
+ *
+ * This is the drop-in boundary: every entry point below replaces one reference
+ * kernel entry (an ArrayKernelExec, a Grouper method or a HashAggregateKernel
+ * callback) and takes exactly the information the reference passes through an
+ * ArraySpan (cpp/src/arrow/array/data.h:525-690): validity bitmap, data buffer(s),
+ * length, offset, null_count, type id -- but with DEVICE addresses.  No torch, no
+ * arrow C++ type appears in a signature; the C++ host plugin (arrow_b200/cpp) and
+ * the Python ctypes mirror (arrow_b200/_cabi.py) both bind these symbols.
+ *
+ * Conventions
+ *  - every function returns a B2Status (0 = OK); b2_last_error() gives the message
+ *    for the calling thread.  Status codes map 1:1 to arrow::StatusCode
+ *    (cpp/src/arrow/status.h:86-110) so the trampolines can rebuild the same Status.
+ *  - all pointers inside B2Array are device pointers valid on ctx's device.
+ *  - validity bitmaps and boolean data are LSB-first bit-packed
+ *    (cpp/src/arrow/util/bit_util.h), addressed with `offset` in bits.
+ *  - outputs are allocated through the context's allocator (built-in pool, or the
+ *    callbacks the host installs with b2_context_set_allocator so memory stays in
+ *    the host-side MemoryManager pool); ownership passes to the caller, who
+ *    releases with b2_free().
+ *  - calls are stream-ordered on `stream` (a cudaStream_t passed as void*; NULL =
+ *    the context's own non-blocking stream).  Calls that return a length or a null
+ *    count synchronise that stream once before returning (the one unavoidable
+ *    read-back).
+ */
+#ifndef ARROW_B200_H
+#define ARROW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_API __attribute__((visibility("default")))
+
+/* ---- status codes: values follow arrow::StatusCode (status.h:86-110) ---- */
+typedef enum B2Status {
+  B2_OK = 0,
+  B2_OUT_OF_MEMORY = 1,
+  B2_KEY_ERROR = 2,
+  B2_TYPE_ERROR = 3,
+  B2_INVALID = 4,
+  B2_IO_ERROR = 5,
+  B2_CAPACITY_ERROR = 6,
+  B2_INDEX_ERROR = 7,
+  B2_CANCELLED = 8,
+  B2_UNKNOWN_ERROR = 9,
+  B2_NOT_IMPLEMENTED = 10,
+  B2_CUDA_ERROR = 100
+} B2Status;
+
+/* ---- type ids: values follow arrow::Type::type (type_fwd.h:328-460) ---- */
+typedef enum B2Type {
+  B2_NA = 0,
+  B2_BOOL = 1,
+  B2_UINT8 = 2,
+  B2_INT8 = 3,
+  B2_UINT16 = 4,
+  B2_INT16 = 5,
+  B2_UINT32 = 6,
+  B2_INT32 = 7,
+  B2_UINT64 = 8,
+  B2_INT64 = 9,
+  B2_HALF_FLOAT = 10,
+  B2_FLOAT = 11,
+  B2_DOUBLE = 12,
+  B2_STRING = 13,
+  B2_BINARY = 14,
+  B2_FIXED_SIZE_BINARY = 15,
+  B2_LARGE_STRING = 34,
+  B2_LARGE_BINARY = 35
+} B2Type;
+
+/* One ArraySpan with device addresses (array/data.h:525-690).
+ *   fixed width : data  = values                       (data2 unused)
+ *   bool        : data  = bit-packed values
+ *   (large_)utf8/binary : data = int32/int64 offsets (length+1 entries, indexed
+ *                 from `offset`), data2 = character bytes
+ * byte_width is only read for B2_FIXED_SIZE_BINARY. */
+typedef struct B2Array {
+  const void* validity; /* NULL = no nulls */
+  const void* data;
+  const void* data2;
+  int64_t length;
+  int64_t offset;
+  int64_t null_count; /* -1 = unknown (kUnknownNullCount) */
+  int32_t type;       /* B2Type */
+  int32_t byte_width;
+} B2Array;
+
+/* A Scalar operand (scalar.h): value bits in `bits` (little-endian, low bytes),
+ * is_valid = 0 for a null scalar. */
+typedef struct B2Scalar {
+  uint64_t bits;
+  int32_t type;
+  int32_t is_valid;
+} B2Scalar;
+
+/* Binary-kernel operand: an array or a scalar (exec.h:275-330 ExecValue). */
+typedef struct B2Value {
+  const B2Array* array;   /* non-NULL => array operand */
+  const B2Scalar* scalar; /* used when array == NULL */
+} B2Value;
+
+typedef struct B2Context B2Context;
+
+/* ---------------------------------------------------------------------------
+ * Context, device pool, streams.
+ * Replaces: arrow::cuda::CudaContext / CudaMemoryManager allocation path
+ * (cpp/src/arrow/gpu/cuda_context.cc:110-121 = one cuMemAlloc per buffer) with a
+ * size-binned caching pool.
+ * ------------------------------------------------------------------------- */
+typedef void* (*B2AllocFn)(size_t nbytes, void* stream, void* user);
+typedef void (*B2FreeFn)(void* ptr, size_t nbytes, void* stream, void* user);
+
+B2_API int b2_context_create(int device, B2Context** out);
+B2_API void b2_context_destroy(B2Context* ctx);
+B2_API int b2_context_device(const B2Context* ctx);
+B2_API void* b2_context_stream(const B2Context* ctx);
+B2_API int b2_context_set_allocator(B2Context* ctx, B2AllocFn alloc, B2FreeFn free_fn,
+                                    void* user);
+B2_API int b2_alloc(B2Context* ctx, size_t nbytes, void** out);
+B2_API int b2_free(B2Context* ctx, void* ptr);
+B2_API int b2_pool_stats(const B2Context* ctx, int64_t* bytes_in_use,
+                         int64_t* bytes_reserved, int64_t* max_in_use);
+B2_API int b2_pool_trim(B2Context* ctx);
+B2_API int b2_sync(B2Context* ctx, void* stream);
+B2_API int b2_memcpy_h2d(B2Context* ctx, void* dst, const void* src, size_t n, void* stream);
+B2_API int b2_memcpy_d2h(B2Context* ctx, void* dst, const void* src, size_t n, void* stream);
+B2_API int b2_memset(B2Context* ctx, void* dst, int byte, size_t n, void* stream);
+/* pinned host staging (CudaHostBuffer, cuda_memory.h:113) */
+B2_API int b2_host_alloc(size_t nbytes, void** out);
+B2_API int b2_host_free(void* ptr);
+
+B2_API const char* b2_last_error(void);
+B2_API const char* b2_version(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim) */
+B2_API int64_t b2_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Bitmap utilities.  Replaces internal::CopyBitmap / BitmapAnd / CountSetBits
+ * (cpp/src/arrow/util/bitmap_ops.cc) as used by NullPropagator
+ * (cpp/src/arrow/compute/exec.cc:527-686).
+ * ------------------------------------------------------------------------- */
+/* number of set bits in bits[offset, offset+length) */
+B2_API int b2_bitmap_count(B2Context* ctx, const void* bits, int64_t offset, int64_t length,
+                           int64_t* out_count, void* stream);
+/* dst[dst_offset..] = src[src_offset..]; dst must be a fresh buffer, padding zeroed */
+B2_API int b2_bitmap_copy(B2Context* ctx, const void* src, int64_t src_offset, int64_t length,
+                          void* dst, void* stream);
+/* dst = a & b (either may be NULL = all ones); returns popcount if out_count != NULL */
+B2_API int b2_bitmap_and(B2Context* ctx, const void* a, int64_t a_offset, const void* b,
+                         int64_t b_offset, int64_t length, void* dst, int64_t* out_count,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Cast.  Replaces CastNumberToNumberUnsafe + the safety checks
+ * (kernels/scalar_cast_internal.cc:41-53,155; kernels/scalar_cast_numeric.cc:45-279).
+ * out is allocated by the callee (data + validity copy at offset 0).
+ * ------------------------------------------------------------------------- */
+typedef struct B2CastOptions { /* compute/cast.h CastOptions */
+  int32_t to_type;
+  int32_t allow_int_overflow;
+  int32_t allow_float_truncate;
+  int32_t reserved;
+} B2CastOptions;
+B2_API int b2_cast_numeric(B2Context* ctx, const B2Array* in, const B2CastOptions* options,
+                           B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Arithmetic.  Replaces ScalarBinary<..>::{ArrayArray,ArrayScalar,ScalarArray}
+ * with the Add/Subtract/Multiply(+Checked)/Divide op functors
+ * (kernels/codegen_internal.h:813-976, kernels/base_arithmetic_internal.h:44-330).
+ * Both operands must already have the same (dispatched) type, as after
+ * ArithmeticFunction::DispatchBest (kernels/scalar_arithmetic.cc:734-781).
+ * ------------------------------------------------------------------------- */
+typedef enum B2ArithOp {
+  B2_ADD = 0,
+  B2_SUBTRACT = 1,
+  B2_MULTIPLY = 2,
+  B2_DIVIDE = 3,
+  B2_ADD_CHECKED = 16,
+  B2_SUBTRACT_CHECKED = 17,
+  B2_MULTIPLY_CHECKED = 18,
+  B2_DIVIDE_CHECKED = 19
+} B2ArithOp;
+B2_API int b2_binary_arith(B2Context* ctx, int op, const B2Value* left, const B2Value* right,
+                           B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Compare -> bit-packed boolean.  Replaces CompareKernel::Exec
+ * (kernels/scalar_compare.cc:164-303).  less/less_equal are the flipped
+ * greater/greater_equal exactly as MakeFlippedCompare does (:910).
+ * ------------------------------------------------------------------------- */
+typedef enum B2CompareOp {
+  B2_EQUAL = 0,
+  B2_NOT_EQUAL = 1,
+  B2_GREATER = 2,
+  B2_GREATER_EQUAL = 3,
+  B2_LESS = 4,
+  B2_LESS_EQUAL = 5
+} B2CompareOp;
+B2_API int b2_compare(B2Context* ctx, int op, const B2Value* left, const B2Value* right,
+                      B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Filter.  Replaces PrimitiveFilterExec / BinaryFilterExec /
+ * DictionaryFilterExec (kernels/vector_selection_filter_internal.cc:445-510,
+ * 806-856,871-881) and GetFilterOutputSize (:62-114).
+ * null_selection: 0 = DROP, 1 = EMIT_NULL (compute/api_vector.h:37-51).
+ * mask is a B2_BOOL array.
+ * ------------------------------------------------------------------------- */
+B2_API int b2_filter_output_size(B2Context* ctx, const B2Array* mask, int null_selection,
+                                 int64_t* out_length, void* stream);
+B2_API int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* mask,
+                     int null_selection, B2Array* out, void* stream);
+/* mask -> selection indices (GetTakeIndices, vector_selection_take_internal.cc:62-305);
+ * out type is B2_UINT32 if mask length <= UINT32_MAX else error as the reference. */
+B2_API int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_selection,
+                             B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Take.  Replaces FixedWidthTakeExec / Gather / VarBinaryTakeExec / DictionaryTake
+ * (kernels/vector_selection_take_internal.cc:336-497, kernels/gather_internal.h:84-251)
+ * and CheckIndexBounds (util/int_util.cc:452-560).
+ * ------------------------------------------------------------------------- */
+B2_API int b2_take(B2Context* ctx, const B2Array* values, const B2Array* indices,
+                   int boundscheck, B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * SortIndices.  Replaces ArraySortIndices::Exec + ArrayCompareSorter /
+ * ArrayCountSorter (kernels/vector_array_sort.cc:144-446,524-540) and
+ * PartitionNullsAndNans (kernels/vector_sort_internal.h:113-305).
+ * order: 0 = Ascending, 1 = Descending; null_placement: 0 = AtStart, 1 = AtEnd
+ * (compute/ordering.h:30-44).  out: B2_UINT64, length = values.length, no nulls.
+ * ------------------------------------------------------------------------- */
+B2_API int b2_sort_indices(B2Context* ctx, const B2Array* values, int order,
+                           int null_placement, B2Array* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Grouper.  Replaces Grouper::{Make,Consume,Lookup,GetUniques,num_groups,Reset}
+ * (compute/row/grouper.h:104-196; GrouperFastImpl row/grouper.cc:555-963) for
+ * fixed-width key columns (1..n_keys columns, each 1/2/4/8 bytes wide).
+ * Group ids are dense uint32 assigned in first-occurrence row order.
+ * ------------------------------------------------------------------------- */
+typedef struct B2Grouper B2Grouper;
+B2_API int b2_grouper_create(B2Context* ctx, const int32_t* key_types, int n_keys,
+                             B2Grouper** out);
+B2_API void b2_grouper_destroy(B2Grouper* g);
+/* keys: n_keys arrays of equal length; out_ids: B2_UINT32 array, no nulls */
+B2_API int b2_grouper_consume(B2Grouper* g, const B2Array* keys, B2Array* out_ids,
+                              void* stream);
+/* as consume but never inserts; unknown keys give null ids */
+B2_API int b2_grouper_lookup(B2Grouper* g, const B2Array* keys, B2Array* out_ids,
+                             void* stream);
+B2_API int b2_grouper_num_groups(const B2Grouper* g, uint32_t* out);
+/* out_keys: n_keys arrays, each num_groups long, in group-id order */
+B2_API int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream);
+B2_API int b2_grouper_reset(B2Grouper* g);
+
+/* ---------------------------------------------------------------------------
+ * Hash aggregates.  Replaces the HashAggregateKernel contract
+ * {init,resize,consume,merge,finalize} (compute/kernel.h:720-769) for
+ * GroupedSumImpl / GroupedCountImpl / GroupedCountAllImpl / GroupedMeanImpl /
+ * GroupedMinMaxImpl (kernels/hash_aggregate_numeric.cc:44-295,330-,
+ * kernels/hash_aggregate.cc:61-272).
+ * ------------------------------------------------------------------------- */
+typedef enum B2HashAggKind {
+  B2_HASH_SUM = 0,
+  B2_HASH_COUNT = 1,
+  B2_HASH_COUNT_ALL = 2,
+  B2_HASH_MEAN = 3,
+  B2_HASH_MIN = 4,
+  B2_HASH_MAX = 5,
+  B2_HASH_PRODUCT = 6
+} B2HashAggKind;
+typedef struct B2HashAggOptions {
+  int32_t skip_nulls;  /* ScalarAggregateOptions (api_aggregate.h:48-50), default 1 */
+  uint32_t min_count;  /* default 1 */
+  int32_t count_mode;  /* CountOptions: 0 ONLY_VALID, 1 ONLY_NULL, 2 ALL (api_aggregate.h:64-78) */
+  int32_t reserved;
+} B2HashAggOptions;
+typedef struct B2HashAgg B2HashAgg;
+B2_API int b2_hashagg_create(B2Context* ctx, int kind, int32_t value_type,
+                             const B2HashAggOptions* options, B2HashAgg** out);
+B2_API void b2_hashagg_destroy(B2HashAgg* a);
+B2_API int b2_hashagg_resize(B2HashAgg* a, int64_t num_groups, void* stream);
+/* values may be NULL for count_all; ids: B2_UINT32 array of the same length */
+B2_API int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids,
+                              void* stream);
+/* state[mapping[i]] (+)= other.state[i]; mapping: B2_UINT32, length = other groups */
+B2_API int b2_hashagg_merge(B2HashAgg* a, B2HashAgg* other, const B2Array* group_id_mapping,
+                            void* stream);
+B2_API int b2_hashagg_finalize(B2HashAgg* a, B2Array* out, void* stream);
+B2_API int32_t b2_hashagg_out_type(const B2HashAgg* a);
+
+/* Fused group-by for the Acero aggregate node (acero/groupby_aggregate_node.cc:210-253
+ * Consume = grouper->Consume + kernel->consume per aggregate): one pass over
+ * (key, value) rows updating an on-device table, no uint32 id column materialised.
+ * Semantically identical to b2_grouper_consume followed by b2_hashagg_consume of a
+ * sum and a count(ONLY_VALID) aggregator over the same value column. */
+typedef struct B2GroupBySumCount B2GroupBySumCount;
+B2_API int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_type,
+                                      int64_t expected_groups, B2GroupBySumCount** out);
+B2_API void b2_groupby_sumcount_destroy(B2GroupBySumCount* g);
+B2_API int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys,
+                                       const B2Array* values, void* stream);
+/* out_keys / out_sums / out_counts: num_groups long, first-occurrence order */
+B2_API int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys,
+                                        B2Array* out_sums, B2Array* out_counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROW_B200_H */
