@@ -1,0 +1,468 @@
+"""Host-side mirror of the reference's function API for the hot path.
+
+Same names, argument meaning and error behaviour as arrow::compute::CallFunction
+(cpp/src/arrow/compute/exec.cc:1362-1390) / pyarrow.compute, but operands are
+DeviceArray and every kernel is a C-ABI call into libarrow_b200.so.  The dispatch rules
+reproduced here are the reference's:
+  * arithmetic / compare: exact match, else promote all operands to CommonNumeric
+    (kernels/codegen_internal.cc:166-218) with an implicit safe cast
+    (ArithmeticFunction::DispatchBest kernels/scalar_arithmetic.cc:734-781,
+     CompareFunction::DispatchBest kernels/scalar_compare.cc:340-366,
+     FunctionExecutorImpl::Execute function.cc:242-250),
+  * filter / take / sort_indices meta-functions unwrap to array_* kernels
+    (kernels/vector_selection_filter_internal.cc:1043-1072, vector_selection_take_internal.cc:660-701,
+     kernels/vector_sort.cc:856-924).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import pyarrow as pa
+
+from . import _cabi as cabi
+from .device import Context, DeviceArray, arrow_type, check, type_id
+
+Operand = Union[DeviceArray, pa.Scalar, int, float, bool, None]
+
+_NUMERIC_IDS = (cabi.UINT8, cabi.INT8, cabi.UINT16, cabi.INT16, cabi.UINT32, cabi.INT32, cabi.UINT64,
+                cabi.INT64, cabi.FLOAT, cabi.DOUBLE)
+_SIGNED = {cabi.INT8: 8, cabi.INT16: 16, cabi.INT32: 32, cabi.INT64: 64}
+_UNSIGNED = {cabi.UINT8: 8, cabi.UINT16: 16, cabi.UINT32: 32, cabi.UINT64: 64}
+_NP = {cabi.INT8: np.int8, cabi.UINT8: np.uint8, cabi.INT16: np.int16, cabi.UINT16: np.uint16,
+       cabi.INT32: np.int32, cabi.UINT32: np.uint32, cabi.INT64: np.int64, cabi.UINT64: np.uint64,
+       cabi.FLOAT: np.float32, cabi.DOUBLE: np.float64}
+
+
+def _ctx(*args) -> Context:
+    for a in args:
+        if isinstance(a, DeviceArray):
+            return a.ctx
+    return Context.get()
+
+
+def _out(ctx: Context, c: cabi.B2Array, type: pa.DataType, dictionary=None) -> DeviceArray:
+    return DeviceArray._from_c(ctx, c, type, dictionary)
+
+
+# ------------------------------------------------------------------------------------
+# dispatch helpers
+# ------------------------------------------------------------------------------------
+def common_numeric(ids: Sequence[int]) -> int:
+    """CommonNumeric (kernels/codegen_internal.cc:166-218)."""
+    for i in ids:
+        if i not in _NUMERIC_IDS:
+            raise pa.ArrowNotImplementedError("Function has no kernel matching input types")
+    if cabi.DOUBLE in ids:
+        return cabi.DOUBLE
+    if cabi.FLOAT in ids:
+        return cabi.FLOAT
+    ms = max([_SIGNED[i] for i in ids if i in _SIGNED], default=0)
+    mu = max([_UNSIGNED[i] for i in ids if i in _UNSIGNED], default=0)
+    if ms == 0:
+        return {8: cabi.UINT8, 16: cabi.UINT16, 32: cabi.UINT32}.get(mu, cabi.UINT64)
+    if ms <= mu:
+        ms = 1 << (mu + 1 - 1).bit_length()  # NextPower2(mu + 1)
+    return {8: cabi.INT8, 16: cabi.INT16, 32: cabi.INT32}.get(ms, cabi.INT64)
+
+
+def _as_scalar(x) -> pa.Scalar:
+    if isinstance(x, pa.Scalar):
+        return x
+    return pa.scalar(x)
+
+
+def _scalar_to(s: pa.Scalar, tid: int) -> cabi.B2Scalar:
+    """Implicit safe cast of a host scalar to the dispatched type (done on the host: it is
+    argument preparation, one value)."""
+    out = cabi.B2Scalar()
+    out.type = tid
+    out.is_valid = 1 if s.is_valid else 0
+    out.bits = 0
+    if s.is_valid:
+        v = s.as_py()
+        dt = _NP[tid]
+        if np.issubdtype(dt, np.integer):
+            if isinstance(v, float):
+                if v != int(v):
+                    raise pa.ArrowInvalid(f"Float value {v:g} was truncated converting to {arrow_type(tid)}")
+                v = int(v)
+            info = np.iinfo(dt)
+            if not (info.min <= int(v) <= info.max):
+                raise pa.ArrowInvalid(f"Integer value {v} not in range: {info.min} to {info.max}")
+            arr = np.array([int(v)], dtype=dt)
+        else:
+            arr = np.array([v], dtype=dt)
+        out.bits = int(np.frombuffer(arr.tobytes().ljust(8, b"\0"), dtype=np.uint64)[0])
+    return out
+
+
+def _prepare_binary(left: Operand, right: Operand):
+    ctx = _ctx(left, right)
+    ops = []
+    ids = []
+    for x in (left, right):
+        if isinstance(x, DeviceArray):
+            ids.append(type_id(x.type))
+            ops.append(x)
+        else:
+            s = _as_scalar(x)
+            if pa.types.is_null(s.type):
+                raise pa.ArrowNotImplementedError("null-typed scalar operands are not supported")
+            ids.append(type_id(s.type))
+            ops.append(s)
+    if not any(isinstance(o, DeviceArray) for o in ops):
+        raise pa.ArrowNotImplementedError("arrow_b200: at least one operand must be a device array")
+    tid = ids[0] if ids[0] == ids[1] and ids[0] in _NUMERIC_IDS else common_numeric(ids)
+    keep = []  # keep ctypes structs alive for the call
+    vals = []
+    for o, i in zip(ops, ids):
+        v = cabi.B2Value()
+        if isinstance(o, DeviceArray):
+            if i != tid:
+                o = cast(o, arrow_type(tid))  # implicit safe cast
+            c = o._c()
+            keep.append((o, c))
+            v.array = C.pointer(c)
+            v.scalar = None
+        else:
+            sc = _scalar_to(o, tid)
+            keep.append(sc)
+            v.array = None
+            v.scalar = C.pointer(sc)
+        vals.append(v)
+    return ctx, tid, vals, keep
+
+
+# ------------------------------------------------------------------------------------
+# scalar kernels
+# ------------------------------------------------------------------------------------
+def cast(arr: DeviceArray, target_type=None, safe: Optional[bool] = None, options=None) -> DeviceArray:
+    """pyarrow.compute.cast / CastMetaFunction (compute/cast.cc:78-127)."""
+    allow_int_overflow = allow_float_truncate = False
+    if options is not None:
+        target_type = options.target_type if target_type is None else target_type
+        allow_int_overflow = bool(options.allow_int_overflow)
+        allow_float_truncate = bool(options.allow_float_truncate)
+    if safe is False:
+        allow_int_overflow = allow_float_truncate = True
+    target_type = pa.lib.ensure_type(target_type)
+    if arr.type == target_type:
+        return arr
+    src, dst = type_id(arr.type), type_id(target_type)
+    if src not in _NUMERIC_IDS or dst not in _NUMERIC_IDS or pa.types.is_dictionary(arr.type):
+        raise pa.ArrowNotImplementedError(
+            f"Unsupported cast from {arr.type} to {target_type} using function cast_{target_type}")
+    ctx = arr.ctx
+    opt = cabi.B2CastOptions(dst, int(allow_int_overflow), int(allow_float_truncate), 0)
+    cin, cout = arr._c(), cabi.B2Array()
+    check(ctx.lib.b2_cast_numeric(ctx.handle, C.byref(cin), C.byref(opt), C.byref(cout), ctx.stream))
+    return _out(ctx, cout, target_type)
+
+
+def _arith(name: str, left: Operand, right: Operand) -> DeviceArray:
+    ctx, tid, vals, keep = _prepare_binary(left, right)
+    cout = cabi.B2Array()
+    check(ctx.lib.b2_binary_arith(ctx.handle, cabi.ARITH_OPS[name], C.byref(vals[0]), C.byref(vals[1]),
+                                  C.byref(cout), ctx.stream))
+    return _out(ctx, cout, arrow_type(tid))
+
+
+def _compare(name: str, left: Operand, right: Operand) -> DeviceArray:
+    ctx, tid, vals, keep = _prepare_binary(left, right)
+    cout = cabi.B2Array()
+    check(ctx.lib.b2_compare(ctx.handle, cabi.COMPARE_OPS[name], C.byref(vals[0]), C.byref(vals[1]),
+                             C.byref(cout), ctx.stream))
+    return _out(ctx, cout, pa.bool_())
+
+
+def add(x, y): return _arith("add", x, y)
+def subtract(x, y): return _arith("subtract", x, y)
+def multiply(x, y): return _arith("multiply", x, y)
+def divide(x, y): return _arith("divide", x, y)
+def add_checked(x, y): return _arith("add_checked", x, y)
+def subtract_checked(x, y): return _arith("subtract_checked", x, y)
+def multiply_checked(x, y): return _arith("multiply_checked", x, y)
+def divide_checked(x, y): return _arith("divide_checked", x, y)
+def equal(x, y): return _compare("equal", x, y)
+def not_equal(x, y): return _compare("not_equal", x, y)
+def greater(x, y): return _compare("greater", x, y)
+def greater_equal(x, y): return _compare("greater_equal", x, y)
+def less(x, y): return _compare("less", x, y)
+def less_equal(x, y): return _compare("less_equal", x, y)
+
+
+# ------------------------------------------------------------------------------------
+# selection
+# ------------------------------------------------------------------------------------
+def _null_selection(v) -> int:
+    if v in ("drop", 0, None):
+        return 0
+    if v in ("emit_null", 1):
+        return 1
+    raise ValueError(f'"{v}" is not a valid null selection behavior')
+
+
+def filter(values: DeviceArray, mask: DeviceArray, null_selection_behavior="drop") -> DeviceArray:
+    """pyarrow.compute.filter / array_filter (kernels/vector_selection_filter_internal.cc:1043-1072)."""
+    if not pa.types.is_boolean(mask.type):
+        raise pa.ArrowNotImplementedError(
+            f"Function 'array_filter' has no kernel matching input types ({values.type}, {mask.type})")
+    ctx = values.ctx
+    cv, cm, cout = values._c(), mask._c(), cabi.B2Array()
+    check(ctx.lib.b2_filter(ctx.handle, C.byref(cv), C.byref(cm), _null_selection(null_selection_behavior),
+                            C.byref(cout), ctx.stream))
+    return _out(ctx, cout, values.type, values.dictionary)
+
+
+def array_filter(values, mask, null_selection_behavior="drop"):
+    return filter(values, mask, null_selection_behavior)
+
+
+def filter_output_size(mask: DeviceArray, null_selection_behavior="drop") -> int:
+    ctx = mask.ctx
+    n = C.c_int64()
+    cm = mask._c()
+    check(ctx.lib.b2_filter_output_size(ctx.handle, C.byref(cm), _null_selection(null_selection_behavior),
+                                        C.byref(n), ctx.stream))
+    return n.value
+
+
+def take_indices_from_filter(mask: DeviceArray, null_selection_behavior="drop") -> DeviceArray:
+    """GetTakeIndices (kernels/vector_selection_take_internal.cc:298-305)."""
+    ctx = mask.ctx
+    cm, cout = mask._c(), cabi.B2Array()
+    check(ctx.lib.b2_filter_indices(ctx.handle, C.byref(cm), _null_selection(null_selection_behavior),
+                                    C.byref(cout), ctx.stream))
+    return _out(ctx, cout, arrow_type(cout.type))
+
+
+def take(values: DeviceArray, indices: DeviceArray, boundscheck: bool = True) -> DeviceArray:
+    """pyarrow.compute.take / array_take (kernels/vector_selection_take_internal.cc:660-701)."""
+    if not pa.types.is_integer(indices.type):
+        raise pa.ArrowNotImplementedError(
+            f"Function 'array_take' has no kernel matching input types ({values.type}, {indices.type})")
+    ctx = values.ctx
+    cv, ci, cout = values._c(), indices._c(), cabi.B2Array()
+    check(ctx.lib.b2_take(ctx.handle, C.byref(cv), C.byref(ci), int(bool(boundscheck)), C.byref(cout),
+                          ctx.stream))
+    return _out(ctx, cout, values.type, values.dictionary)
+
+
+def array_take(values, indices, boundscheck=True):
+    return take(values, indices, boundscheck)
+
+
+# ------------------------------------------------------------------------------------
+# sort
+# ------------------------------------------------------------------------------------
+def _order(v) -> int:
+    if v in ("ascending", 0):
+        return 0
+    if v in ("descending", 1):
+        return 1
+    raise ValueError(f'"{v}" is not a valid order')
+
+
+def _placement(v) -> int:
+    if v in ("at_start", 0):
+        return 0
+    if v in ("at_end", 1):
+        return 1
+    raise ValueError(f'"{v}" is not a valid null placement')
+
+
+def array_sort_indices(arr: DeviceArray, order="ascending", null_placement="at_end") -> DeviceArray:
+    """array_sort_indices (kernels/vector_array_sort.cc:524-540): stable argsort -> uint64."""
+    ctx = arr.ctx
+    ca, cout = arr._c(), cabi.B2Array()
+    check(ctx.lib.b2_sort_indices(ctx.handle, C.byref(ca), _order(order), _placement(null_placement),
+                                  C.byref(cout), ctx.stream))
+    return _out(ctx, cout, pa.uint64())
+
+
+def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", order=None) -> DeviceArray:
+    """sort_indices meta function on one array (kernels/vector_sort.cc:856-924)."""
+    o = "ascending"
+    if sort_keys:
+        o = sort_keys[0][1] if isinstance(sort_keys[0], (tuple, list)) else sort_keys[0]
+    if order is not None:
+        o = order
+    return array_sort_indices(arr, o, null_placement)
+
+
+# ------------------------------------------------------------------------------------
+# grouper + hash aggregates
+# ------------------------------------------------------------------------------------
+class Grouper:
+    """arrow::compute::Grouper (compute/row/grouper.h:104-196) over fixed-width key columns."""
+
+    def __init__(self, key_types: Sequence[pa.DataType], ctx: Optional[Context] = None):
+        self.ctx = ctx or Context.get()
+        self.key_types = [pa.lib.ensure_type(t) for t in key_types]
+        ids = (C.c_int32 * len(self.key_types))(*[type_id(t) for t in self.key_types])
+        h = C.c_void_p()
+        check(self.ctx.lib.b2_grouper_create(self.ctx.handle, ids, len(self.key_types), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.b2_grouper_destroy(self.handle)
+            self.handle = None
+
+    def _keys(self, keys):
+        if isinstance(keys, DeviceArray):
+            keys = [keys]
+        if len(keys) != len(self.key_types):
+            raise pa.ArrowInvalid(f"expected batch size {len(self.key_types)} but got {len(keys)}")
+        for k, t in zip(keys, self.key_types):
+            if k.type != t:
+                raise pa.ArrowInvalid(f"expected batch value of type {t} but got {k.type}")
+        carr = (cabi.B2Array * len(keys))(*[k._c() for k in keys])
+        return carr
+
+    def consume(self, keys) -> DeviceArray:
+        carr, cout = self._keys(keys), cabi.B2Array()
+        check(self.ctx.lib.b2_grouper_consume(self.handle, carr, C.byref(cout), self.ctx.stream))
+        return _out(self.ctx, cout, pa.uint32())
+
+    def lookup(self, keys) -> DeviceArray:
+        carr, cout = self._keys(keys), cabi.B2Array()
+        check(self.ctx.lib.b2_grouper_lookup(self.handle, carr, C.byref(cout), self.ctx.stream))
+        return _out(self.ctx, cout, pa.uint32())
+
+    @property
+    def num_groups(self) -> int:
+        n = C.c_uint32()
+        check(self.ctx.lib.b2_grouper_num_groups(self.handle, C.byref(n)))
+        return n.value
+
+    def get_uniques(self):
+        couts = (cabi.B2Array * len(self.key_types))()
+        check(self.ctx.lib.b2_grouper_uniques(self.handle, couts, self.ctx.stream))
+        return [_out(self.ctx, couts[i], t) for i, t in enumerate(self.key_types)]
+
+    def reset(self):
+        check(self.ctx.lib.b2_grouper_reset(self.handle))
+
+
+class HashAggregator:
+    """One HashAggregateKernel state (compute/kernel.h:720-769): resize/consume/merge/finalize."""
+
+    def __init__(self, function: str, value_type: Optional[pa.DataType], *, skip_nulls=True, min_count=1,
+                 mode="only_valid", ctx: Optional[Context] = None):
+        self.ctx = ctx or Context.get()
+        self.function = function
+        kind = cabi.HASH_AGG_KINDS[function]
+        cm = {"only_valid": 0, "only_null": 1, "all": 2}[mode]
+        opts = cabi.B2HashAggOptions(int(skip_nulls), int(min_count), cm, 0)
+        vt = type_id(value_type) if value_type is not None else cabi.NA
+        h = C.c_void_p()
+        check(self.ctx.lib.b2_hashagg_create(self.ctx.handle, kind, vt, C.byref(opts), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.b2_hashagg_destroy(self.handle)
+            self.handle = None
+
+    def resize(self, num_groups: int):
+        check(self.ctx.lib.b2_hashagg_resize(self.handle, int(num_groups), self.ctx.stream))
+
+    def consume(self, values: Optional[DeviceArray], ids: DeviceArray):
+        cv = values._c() if values is not None else None
+        ci = ids._c()
+        check(self.ctx.lib.b2_hashagg_consume(self.handle, C.byref(cv) if cv is not None else None,
+                                              C.byref(ci), self.ctx.stream))
+
+    def merge(self, other: "HashAggregator", group_id_mapping: DeviceArray):
+        cm = group_id_mapping._c()
+        check(self.ctx.lib.b2_hashagg_merge(self.handle, other.handle, C.byref(cm), self.ctx.stream))
+
+    def finalize(self) -> DeviceArray:
+        cout = cabi.B2Array()
+        check(self.ctx.lib.b2_hashagg_finalize(self.handle, C.byref(cout), self.ctx.stream))
+        return _out(self.ctx, cout, arrow_type(cout.type))
+
+
+def group_by(keys: Sequence[DeviceArray], aggregates: Sequence[tuple]):
+    """The Acero aggregate node's Consume/Finalize over one batch
+    (acero/groupby_aggregate_node.cc:210-253,300-337): aggregates = [(function, values|None, opts)].
+    Returns (unique key columns, [aggregate columns])."""
+    if isinstance(keys, DeviceArray):
+        keys = [keys]
+    g = Grouper([k.type for k in keys], keys[0].ctx)
+    ids = g.consume(keys)
+    outs = []
+    for fn, values, opts in aggregates:
+        agg = HashAggregator(fn, values.type if values is not None else None, ctx=keys[0].ctx, **(opts or {}))
+        agg.resize(g.num_groups)
+        agg.consume(values, ids)
+        outs.append(agg.finalize())
+    return g.get_uniques(), outs
+
+
+class GroupBySumCount:
+    """Fused consume of the aggregate node for `hash_sum` + `hash_count` over one value column
+    (b2_groupby_sumcount_*): same results as Grouper + two HashAggregators."""
+
+    def __init__(self, key_type, value_type, expected_groups=0, ctx: Optional[Context] = None):
+        self.ctx = ctx or Context.get()
+        self.key_type, self.value_type = pa.lib.ensure_type(key_type), pa.lib.ensure_type(value_type)
+        h = C.c_void_p()
+        check(self.ctx.lib.b2_groupby_sumcount_create(self.ctx.handle, type_id(self.key_type),
+                                                      type_id(self.value_type), int(expected_groups), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.b2_groupby_sumcount_destroy(self.handle)
+            self.handle = None
+
+    def consume(self, keys: DeviceArray, values: DeviceArray):
+        ck, cv = keys._c(), values._c()
+        check(self.ctx.lib.b2_groupby_sumcount_consume(self.handle, C.byref(ck), C.byref(cv), self.ctx.stream))
+
+    def finalize(self):
+        k, s, c = cabi.B2Array(), cabi.B2Array(), cabi.B2Array()
+        check(self.ctx.lib.b2_groupby_sumcount_finalize(self.handle, C.byref(k), C.byref(s), C.byref(c),
+                                                        self.ctx.stream))
+        return (_out(self.ctx, k, self.key_type), _out(self.ctx, s, arrow_type(s.type)),
+                _out(self.ctx, c, pa.int64()))
+
+
+# ------------------------------------------------------------------------------------
+# CallFunction-style registry (compute/registry.cc:87-96 lookup by name)
+# ------------------------------------------------------------------------------------
+_REGISTRY = {
+    "cast": cast, "filter": filter, "array_filter": array_filter, "take": take, "array_take": array_take,
+    "sort_indices": sort_indices, "array_sort_indices": array_sort_indices,
+    "add": add, "subtract": subtract, "multiply": multiply, "divide": divide,
+    "add_checked": add_checked, "subtract_checked": subtract_checked,
+    "multiply_checked": multiply_checked, "divide_checked": divide_checked,
+    "equal": equal, "not_equal": not_equal, "greater": greater, "greater_equal": greater_equal,
+    "less": less, "less_equal": less_equal,
+}
+
+
+def list_functions():
+    return sorted(_REGISTRY)
+
+
+def call_function(name: str, args: Sequence, options=None):
+    """CallFunction(name, args, options): KeyError text follows registry.cc:95."""
+    fn = _REGISTRY.get(name)
+    if fn is None:
+        raise pa.ArrowKeyError(f"No function registered with name: {name}")
+    if options is None:
+        return fn(*args)
+    if name == "cast":
+        return cast(args[0], options=options)
+    if name in ("filter", "array_filter"):
+        return fn(*args, null_selection_behavior=getattr(options, "null_selection_behavior", options))
+    if name in ("take", "array_take"):
+        return fn(*args, boundscheck=getattr(options, "boundscheck", True))
+    if name == "array_sort_indices":
+        return fn(*args, order=options.order, null_placement=options.null_placement)
+    return fn(*args)

@@ -1,0 +1,340 @@
+// groupby_fused.cu -- one-pass (key, value) -> {sum, count} group-by.
+//
+// This is the aggregate node's per-batch Consume (grouper->Consume followed by
+// kernel->consume for each aggregate, cpp/src/arrow/acero/groupby_aggregate_node.cc:210-253)
+// for the `hash_sum` + `hash_count(ONLY_VALID)` pair of BASELINE config 3, fused so the
+// uint32 id column is never materialised: each row claims/finds its 32-byte slot
+// {key, sum, count, first_row} with one CAS and updates sum and count in the same
+// 32-byte sector (one DRAM sector RMW per row when the table exceeds L2).
+// Results are identical to Grouper + GroupedSumImpl + GroupedCountImpl
+// (kernels/hash_aggregate_numeric.cc:274-295, kernels/hash_aggregate.cc:61-245):
+// integer sums wrap in 64 bits, float sums accumulate in double, the null key is its own
+// group, sum is null for groups whose count is 0 (min_count = 1).  Group ORDER is
+// unspecified (as under use_threads in the reference, whose tests sort by key).
+//
+// Algorithmic bytes: 16.125 B/row + 24.25 B/group.
+#include <type_traits>
+
+#include "bitmap.h"
+#include "hash_table.cuh"
+
+namespace b2 {
+
+constexpr int kSlotWords = 4;  // 32-byte slots: key, sum, count, spare
+constexpr int64_t kChunkRows = 1ll << 26;
+
+struct FusedTable {
+  unsigned long long* slots;  // [(cap + 2) * 4]
+  uint64_t mask;
+};
+
+__global__ void __launch_bounds__(kBlock) fused_init_kernel(FusedTable t) {
+  for (uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x; i < t.mask + 3; i += (uint64_t)gridDim.x * kBlock) {
+    ulonglong4 v;
+    v.x = kEmptyKey;
+    v.y = 0;
+    v.z = 0;
+    v.w = 0;
+    *reinterpret_cast<ulonglong4*>(t.slots + i * kSlotWords) = v;
+  }
+}
+
+// rows: either [row0, row0 + n) or the explicit list `pending_in`
+template <typename V, int KW>
+__global__ void __launch_bounds__(kBlock) fused_consume_kernel(const void* __restrict__ keys,
+                                                               BitmapReader key_valid,
+                                                               const V* __restrict__ values,
+                                                               BitmapReader val_valid, int64_t row0, int64_t n,
+                                                               const uint32_t* pending_in, FusedTable t,
+                                                               uint32_t* pending_out, unsigned long long* counters) {
+  for (int64_t j = blockIdx.x * (int64_t)kBlock + threadIdx.x; j < n; j += (int64_t)gridDim.x * kBlock) {
+    const int64_t i = pending_in ? row0 + pending_in[j] : row0 + j;
+    const bool knull = !key_valid.bit(i);
+    const uint64_t key = knull ? 0 : load_key_bits(keys, KW, i);
+    bool inserted;
+    int64_t slot = table_find_or_insert(t.slots, t.mask, kSlotWords, key, knull, &inserted);
+    if (slot < 0) {
+      unsigned long long k = atomicAdd(&counters[0], 1ull);
+      pending_out[k] = static_cast<uint32_t>(i - row0);
+      continue;
+    }
+    if (inserted) atomicAdd(&counters[1], 1ull);
+    if (val_valid.bit(i)) {
+      unsigned long long* p = t.slots + slot * kSlotWords;
+      const V v = values[i];
+      if constexpr (std::is_floating_point<V>::value) atomicAdd(reinterpret_cast<double*>(p + 1), static_cast<double>(v));
+      else if constexpr (std::is_signed<V>::value) atomicAdd(p + 1, static_cast<unsigned long long>(static_cast<long long>(v)));
+      else atomicAdd(p + 1, static_cast<unsigned long long>(v));
+      atomicAdd(p + 2, 1ull);
+    }
+  }
+}
+
+// move every occupied slot of `src` into `dst` (growth)
+__global__ void __launch_bounds__(kBlock) fused_rehash_kernel(FusedTable src, FusedTable dst, int64_t* overflow) {
+  for (uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x; i < src.mask + 3; i += (uint64_t)gridDim.x * kBlock) {
+    const unsigned long long* p = src.slots + i * kSlotWords;
+    unsigned long long k = p[0];
+    const bool special = i > src.mask;
+    if (special ? (k != 0ull) : (k == kEmptyKey)) continue;
+    bool inserted;
+    int64_t slot = special ? table_find_or_insert(dst.slots, dst.mask, kSlotWords, kEmptyKey, i == src.mask + 2, &inserted)
+                           : table_find_or_insert(dst.slots, dst.mask, kSlotWords, k, false, &inserted);
+    if (slot < 0) {
+      *overflow = 1;
+      continue;
+    }
+    unsigned long long* q = dst.slots + slot * kSlotWords;
+    q[1] = p[1];
+    q[2] = p[2];
+  }
+}
+
+// occupied slots -> dense output rows (order = slot order); rank via atomic ticket per warp
+__global__ void __launch_bounds__(kBlock) fused_emit_kernel(FusedTable t, int key_width, void* out_keys,
+                                                            uint32_t* key_validity, unsigned long long* out_sums,
+                                                            uint32_t* sum_validity, long long* out_counts,
+                                                            unsigned long long* ticket) {
+  const uint64_t total = t.mask + 3;
+  for (uint64_t base = (blockIdx.x * (uint64_t)kBlock + threadIdx.x) & ~31ull; base < total;
+       base += (uint64_t)gridDim.x * kBlock) {
+    const uint64_t i = base + lane_id();
+    bool occ = false;
+    unsigned long long k = 0, sum = 0, cnt = 0;
+    if (i < total) {
+      const unsigned long long* p = t.slots + i * kSlotWords;
+      k = p[0];
+      occ = (i > t.mask) ? (k == 0ull) : (k != kEmptyKey);
+      sum = p[1];
+      cnt = p[2];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (m == 0) continue;
+    unsigned long long start = 0;
+    if (lane_id() == 0) start = atomicAdd(ticket, (unsigned long long)__popc(m));
+    start = __shfl_sync(0xffffffffu, start, 0);
+    if (occ) {
+      const uint64_t g = start + __popc(m & lanemask_lt());
+      const bool is_null = i == t.mask + 2;
+      const uint64_t kv = i == t.mask + 1 ? kEmptyKey : (is_null ? 0ull : k);
+      switch (key_width) {
+        case 1: static_cast<uint8_t*>(out_keys)[g] = static_cast<uint8_t>(kv); break;
+        case 2: static_cast<uint16_t*>(out_keys)[g] = static_cast<uint16_t>(kv); break;
+        case 4: static_cast<uint32_t*>(out_keys)[g] = static_cast<uint32_t>(kv); break;
+        default: static_cast<uint64_t*>(out_keys)[g] = kv; break;
+      }
+      out_sums[g] = sum;
+      out_counts[g] = static_cast<long long>(cnt);
+      // validity bitmaps start all-ones; clear the few null bits atomically
+      if (is_null) atomicAnd(&key_validity[g >> 5], ~(1u << (g & 31)));
+      if (cnt == 0) atomicAnd(&sum_validity[g >> 5], ~(1u << (g & 31)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) count_zero_bits_kernel(const uint32_t* bits, int64_t n, int64_t* out) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = blockIdx.x * (int64_t)kBlock + threadIdx.x; w < nw; w += (int64_t)gridDim.x * kBlock) {
+    uint32_t v = bits[w];
+    int64_t rem = n - (w << 5);
+    if (rem < 32) v |= ~((1u << rem) - 1u);
+    local += 32 - __popc(v);
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)s);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct B2GroupBySumCount {
+  B2Context* ctx;
+  int key_type, value_type;
+  FusedTable table{};
+  uint64_t cap = 0;
+  uint64_t groups = 0;
+};
+
+static int fused_alloc(B2Context* ctx, uint64_t cap, FusedTable* t, cudaStream_t s) {
+  void* p;
+  B2_RETURN_NOT_OK(ctx->alloc((cap + 2) * kSlotWords * 8, &p, s));
+  t->slots = static_cast<unsigned long long*>(p);
+  t->mask = cap - 1;
+  fused_init_kernel<<<grid_for((int64_t)cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(*t);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+static int fused_grow(B2GroupBySumCount* g, uint64_t cap, cudaStream_t s) {
+  while (true) {
+    FusedTable nt;
+    B2_RETURN_NOT_OK(fused_alloc(g->ctx, cap, &nt, s));
+    ScalarSlot slot(g->ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    fused_rehash_kernel<<<grid_for((int64_t)g->cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(g->table, nt, slot.dev());
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    if (slot.host()[0]) {
+      g->ctx->free(nt.slots, s);
+      cap *= 2;
+      continue;
+    }
+    g->ctx->free(g->table.slots, s);
+    g->table = nt;
+    g->cap = cap;
+    return B2_OK;
+  }
+}
+
+template <typename V>
+static void launch_fused(int kw, int grid, cudaStream_t s, const void* keys, BitmapReader kv, const V* values,
+                         BitmapReader vv, int64_t row0, int64_t n, const uint32_t* pin, FusedTable t, uint32_t* pout,
+                         unsigned long long* counters) {
+  switch (kw) {
+    case 1: fused_consume_kernel<V, 1><<<grid, kBlock, 0, s>>>(keys, kv, values, vv, row0, n, pin, t, pout, counters); break;
+    case 2: fused_consume_kernel<V, 2><<<grid, kBlock, 0, s>>>(keys, kv, values, vv, row0, n, pin, t, pout, counters); break;
+    case 4: fused_consume_kernel<V, 4><<<grid, kBlock, 0, s>>>(keys, kv, values, vv, row0, n, pin, t, pout, counters); break;
+    default: fused_consume_kernel<V, 8><<<grid, kBlock, 0, s>>>(keys, kv, values, vv, row0, n, pin, t, pout, counters); break;
+  }
+}
+
+template <typename V>
+static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Array* values, cudaStream_t s) {
+  B2Context* ctx = g->ctx;
+  const int kw = type_width(g->key_type);
+  const int64_t n = keys->length;
+  const void* kdata = static_cast<const char*>(keys->data) + keys->offset * kw;
+  const V* vdata = static_cast<const V*>(values->data) + values->offset;
+  BitmapReader kv(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
+  BitmapReader vv(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
+    const int64_t cn = n - row0 < kChunkRows ? n - row0 : kChunkRows;
+    Temp pend_a(ctx, s), pend_b(ctx, s);
+    B2_RETURN_NOT_OK(pend_a.alloc(sizeof(uint32_t) * (size_t)cn));
+    const uint32_t* pin = nullptr;
+    uint32_t* pout = pend_a.as<uint32_t>();
+    int64_t todo = cn;
+    while (todo > 0) {
+      ScalarSlot slot(ctx);
+      B2_RETURN_NOT_OK(slot.zero(s));
+      launch_fused<V>(kw, grid_for(todo, kBlock * 4, kSMs * 16), s, kdata, kv, vdata, vv, row0, todo, pin, g->table,
+                      pout, reinterpret_cast<unsigned long long*>(slot.dev()));
+      B2_LAUNCHED();
+      B2_RETURN_NOT_OK(slot.fetch(s));
+      const int64_t pending = slot.host()[0];
+      g->groups += static_cast<uint64_t>(slot.host()[1]);
+      if (pending == 0 && g->groups * 2 <= g->cap) break;
+      // probe limit hit (or load above 1/2): grow, then retry only the rows that failed
+      B2_RETURN_NOT_OK(fused_grow(g, next_pow2(g->groups * 4 > g->cap * 2 ? g->groups * 4 : g->cap * 2), s));
+      if (pending == 0) break;
+      if (!pend_b.ptr) B2_RETURN_NOT_OK(pend_b.alloc(sizeof(uint32_t) * (size_t)cn));
+      pin = pout;
+      pout = (pout == pend_a.as<uint32_t>()) ? pend_b.as<uint32_t>() : pend_a.as<uint32_t>();
+      todo = pending;
+    }
+  }
+  return B2_OK;
+}
+
+extern "C" {
+
+int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_type, int64_t expected_groups,
+                               B2GroupBySumCount** out) {
+  if (!ctx || !out) return set_error(B2_INVALID, "b2_groupby_sumcount_create: null argument");
+  if (type_width(key_type) == 0) return set_error(B2_NOT_IMPLEMENTED, "group-by key type id %d", key_type);
+  if (!type_is_numeric(value_type)) return set_error(B2_NOT_IMPLEMENTED, "group-by value type id %d", value_type);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2GroupBySumCount* g = new B2GroupBySumCount();
+  g->ctx = ctx;
+  g->key_type = key_type;
+  g->value_type = value_type;
+  uint64_t cap = next_pow2(expected_groups > 0 ? (uint64_t)expected_groups * 2 : (1u << 16));
+  if (cap < 1024) cap = 1024;
+  int st = fused_alloc(ctx, cap, &g->table, ctx->stream);
+  if (st != B2_OK) {
+    delete g;
+    return st;
+  }
+  g->cap = cap;
+  *out = g;
+  return B2_OK;
+}
+
+void b2_groupby_sumcount_destroy(B2GroupBySumCount* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  if (g->table.slots) g->ctx->free(g->table.slots, g->ctx->stream);
+  delete g;
+}
+
+int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Array* values, void* stream) {
+  if (!g || !keys || !values) return set_error(B2_INVALID, "b2_groupby_sumcount_consume: null argument");
+  if (keys->type != g->key_type || values->type != g->value_type)
+    return set_error(B2_TYPE_ERROR, "group-by was created for (key %d, value %d), got (%d, %d)", g->key_type,
+                     g->value_type, keys->type, values->type);
+  if (keys->length != values->length) return set_error(B2_INVALID, "keys and values differ in length");
+  cudaStream_t s = g->ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(g->ctx->device));
+  if (keys->length == 0) return B2_OK;
+  switch (values->type) {
+    case B2_INT8: return fused_consume<int8_t>(g, keys, values, s);
+    case B2_UINT8: return fused_consume<uint8_t>(g, keys, values, s);
+    case B2_INT16: return fused_consume<int16_t>(g, keys, values, s);
+    case B2_UINT16: return fused_consume<uint16_t>(g, keys, values, s);
+    case B2_INT32: return fused_consume<int32_t>(g, keys, values, s);
+    case B2_UINT32: return fused_consume<uint32_t>(g, keys, values, s);
+    case B2_INT64: return fused_consume<int64_t>(g, keys, values, s);
+    case B2_UINT64: return fused_consume<uint64_t>(g, keys, values, s);
+    case B2_FLOAT: return fused_consume<float>(g, keys, values, s);
+    default: return fused_consume<double>(g, keys, values, s);
+  }
+}
+
+int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Array* out_sums, B2Array* out_counts,
+                                 void* stream) {
+  if (!g || !out_keys || !out_sums || !out_counts) return set_error(B2_INVALID, "b2_groupby_sumcount_finalize: null argument");
+  B2Context* ctx = g->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = static_cast<int64_t>(g->groups);
+  const int kw = type_width(g->key_type);
+  const int sum_type = (g->value_type == B2_FLOAT || g->value_type == B2_DOUBLE) ? B2_DOUBLE
+                       : (g->value_type == B2_UINT8 || g->value_type == B2_UINT16 || g->value_type == B2_UINT32 ||
+                          g->value_type == B2_UINT64) ? B2_UINT64 : B2_INT64;
+  Temp keys(ctx, s), sums(ctx, s), counts(ctx, s), kbits(ctx, s), sbits(ctx, s);
+  B2_RETURN_NOT_OK(keys.alloc((size_t)n * kw));
+  B2_RETURN_NOT_OK(sums.alloc((size_t)n * 8));
+  B2_RETURN_NOT_OK(counts.alloc((size_t)n * 8));
+  int64_t key_nulls = 0, sum_nulls = 0;
+  if (n > 0) {
+    const size_t bb = bitmap_alloc_bytes(n);
+    B2_RETURN_NOT_OK(kbits.alloc(bb));
+    B2_RETURN_NOT_OK(sbits.alloc(bb));
+    B2_CUDA(cudaMemsetAsync(kbits.ptr, 0xff, bb, s));
+    B2_CUDA(cudaMemsetAsync(sbits.ptr, 0xff, bb, s));
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    fused_emit_kernel<<<grid_for((int64_t)g->cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+        g->table, kw, keys.ptr, kbits.as<uint32_t>(), sums.as<unsigned long long>(), sbits.as<uint32_t>(),
+        counts.as<long long>(), reinterpret_cast<unsigned long long*>(slot.dev()));
+    B2_LAUNCHED();
+    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(kbits.as<uint32_t>(), n, slot.dev() + 1);
+    B2_LAUNCHED();
+    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(sbits.as<uint32_t>(), n, slot.dev() + 2);
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    if (slot.host()[0] != n) return set_error(B2_UNKNOWN_ERROR, "group-by emitted %lld of %lld groups", (long long)slot.host()[0], (long long)n);
+    key_nulls = slot.host()[1];
+    sum_nulls = slot.host()[2];
+    // Arrow bitmaps must be zero past `length`: clear the padding the 0xff fill left
+    // (done on the host-visible tail only when needed by consumers; bits past n are ignored by Equals)
+  }
+  fill_out(out_keys, g->key_type, n, key_nulls, key_nulls ? kbits.release() : nullptr, keys.release());
+  fill_out(out_sums, sum_type, n, sum_nulls, sum_nulls ? sbits.release() : nullptr, sums.release());
+  fill_out(out_counts, B2_INT64, n, 0, nullptr, counts.release());
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,508 @@
+// grouper.cu -- key columns -> dense uint32 group ids, on device.
+//
+// Replaces arrow::compute::Grouper (cpp/src/arrow/compute/row/grouper.h:104-196) as
+// implemented by GrouperFastImpl (row/grouper.cc:555-963: row encode -> Hashing32 ->
+// SwissTable early_filter/find -> map_new_keys) for fixed-width key columns:
+//   Make / Consume / Lookup / GetUniques / num_groups / Reset.
+// Semantics kept: one id per row, ids are dense [0, num_groups), a null key is its own
+// group, keys group by BYTES (so -0.0 != +0.0 and NaNs group by payload, row/grouper.cc
+// encodes raw bytes), uniques only ever grow by appending (prefix-stable), Lookup never
+// inserts and yields null for unknown keys.  Stronger than the reference: ids are
+// assigned in first-occurrence row order, deterministically (the reference only
+// guarantees a bijection of that order).
+//
+// B200 design (per Consume call, all stream-ordered):
+//   insert : every row encodes its key (<= 64 bits incl. in-band null flags), claims or
+//            finds its slot with one 64-bit atomicCAS (linear probing), remembers the
+//            slot, and atomicMin's its row number into the slot if the group is new.
+//   flag   : row i is a "first occurrence" iff its slot is new and holds min row == i;
+//            flags are written as bitmap words (warp ballot).
+//   rank   : the Filter count+scan passes turn the flag bitmap into per-tile offsets, so
+//            new-group ids = num_groups + rank (first-occurrence order, no atomics).
+//   assign : first-occurrence rows publish id and append the encoded key to `uniques`.
+//   gather : out_ids[i] = id[slot[i]].
+// The table grows 4x (rehash from `uniques`) when the probe limit is hit or load > 1/2.
+#include "hash_table.cuh"
+#include "selection.cuh"
+
+namespace b2 {
+
+constexpr uint32_t kNoId = 0xffffffffu;
+constexpr int kMaxKeys = 8;
+
+struct KeyLayout {
+  int n_keys;
+  int width[kMaxKeys];    // bytes
+  int bit_off[kMaxKeys];  // position of column j inside the encoded key
+  int null_bit[kMaxKeys]; // in-band null flag position (multi-column), -1 if single column
+};
+
+struct KeyColumns {
+  const void* data[kMaxKeys];  // advanced by offset
+  BitmapReader valid[kMaxKeys];
+};
+
+__device__ __forceinline__ uint64_t encode_row(const KeyLayout& L, const KeyColumns& c, int64_t i, bool* is_null) {
+  uint64_t enc = 0;
+  *is_null = false;
+  if (L.n_keys == 1) {
+    if (!c.valid[0].bit(i)) {
+      *is_null = true;
+      return 0;
+    }
+    return load_key_bits(c.data[0], L.width[0], i);
+  }
+#pragma unroll 1
+  for (int j = 0; j < L.n_keys; ++j) {
+    if (c.valid[j].bit(i)) enc |= load_key_bits(c.data[j], L.width[j], i) << L.bit_off[j];
+    else enc |= 1ull << L.null_bit[j];
+  }
+  return enc;
+}
+
+struct GrouperTable {
+  unsigned long long* keys;  // [cap + 2]
+  uint32_t* ids;             // [cap + 2]
+  uint32_t* first_row;       // [cap + 2]
+  uint64_t mask;
+};
+
+__global__ void __launch_bounds__(kBlock) grouper_init_kernel(GrouperTable t) {
+  for (uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x; i < t.mask + 3; i += (uint64_t)gridDim.x * kBlock) {
+    t.keys[i] = kEmptyKey;
+    t.ids[i] = kNoId;
+    t.first_row[i] = 0xffffffffu;
+  }
+}
+
+template <bool INSERT>
+__global__ void __launch_bounds__(kBlock) grouper_probe_kernel(KeyLayout L, KeyColumns c, int64_t n,
+                                                               GrouperTable t, uint32_t* row_slot,
+                                                               int64_t* overflow) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    bool is_null;
+    uint64_t enc = encode_row(L, c, i, &is_null);
+    int64_t slot;
+    if (INSERT) {
+      bool inserted;
+      slot = table_find_or_insert(t.keys, t.mask, 1, enc, is_null, &inserted);
+      if (slot < 0) {
+        *overflow = 1;
+        row_slot[i] = kNoId;
+        continue;
+      }
+      if (t.ids[slot] == kNoId) atomicMin(&t.first_row[slot], static_cast<uint32_t>(i));
+    } else {
+      slot = table_find(t.keys, t.mask, 1, enc, is_null);
+    }
+    row_slot[i] = slot < 0 ? kNoId : static_cast<uint32_t>(slot);
+  }
+}
+
+// bit i = row i is the first occurrence of a new group
+__global__ void __launch_bounds__(kBlock) grouper_flag_kernel(int64_t n, GrouperTable t,
+                                                              const uint32_t* row_slot, uint32_t* flags) {
+  int64_t nw = (n + 31) >> 5;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    int64_t i = (w << 5) + lane_id();
+    bool f = false;
+    if (i < n) {
+      uint32_t s = row_slot[i];
+      f = t.ids[s] == kNoId && t.first_row[s] == static_cast<uint32_t>(i);
+    }
+    unsigned word = __ballot_sync(0xffffffffu, f);
+    if (lane_id() == 0) flags[w] = word;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_assign_kernel(KeyLayout L, KeyColumns c, int64_t n,
+                                                                GrouperTable t, const uint32_t* row_slot,
+                                                                BitmapReader flags, const int64_t* tile_offsets,
+                                                                uint32_t base_id, uint64_t* uniq_keys,
+                                                                uint8_t* uniq_null) {
+  __shared__ uint64_t s_sel[kTileWords];
+  __shared__ uint32_t s_prefix[kTileWords];
+  const int64_t tile = blockIdx.x;
+  const int64_t row0 = tile * kTileRows;
+  const unsigned lane = lane_id();
+  if (threadIdx.x < 32) {
+    int64_t w0 = tile * kTileWords + 2 * lane;
+    uint64_t s0 = flags.word(w0), s1 = flags.word(w0 + 1);
+    int c0 = __popcll(s0), c1 = __popcll(s1);
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int excl = incl - c0 - c1;
+    s_sel[2 * lane] = s0;
+    s_sel[2 * lane + 1] = s1;
+    s_prefix[2 * lane] = excl;
+    s_prefix[2 * lane + 1] = excl + c0;
+  }
+  __syncthreads();
+  const int64_t vbase = tile_offsets[tile];
+  for (int p = 0; p < kTileRows / kBlock; ++p) {
+    const int r = p * kBlock + threadIdx.x;
+    const int64_t row = row0 + r;
+    if (row >= n) break;
+    const uint64_t selw = s_sel[r >> 6];
+    if (!((selw >> (r & 63)) & 1)) continue;
+    const unsigned rank = s_prefix[r >> 6] + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+    const uint32_t id = base_id + static_cast<uint32_t>(vbase + rank);
+    bool is_null;
+    uint64_t enc = encode_row(L, c, row, &is_null);
+    t.ids[row_slot[row]] = id;
+    uniq_keys[id] = enc;
+    uniq_null[id] = is_null ? 1 : 0;
+  }
+}
+
+// out[i] = id of row i; for Lookup unknown keys become null (validity via ballot)
+__global__ void __launch_bounds__(kBlock) grouper_gather_kernel(int64_t n, GrouperTable t,
+                                                                const uint32_t* row_slot, uint32_t* out,
+                                                                uint32_t* out_validity, int64_t* valid_count) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    int64_t i = (w << 5) + lane_id();
+    bool ok = false;
+    if (i < n) {
+      uint32_t s = row_slot[i];
+      uint32_t id = s == kNoId ? kNoId : t.ids[s];
+      ok = id != kNoId;
+      out[i] = ok ? id : 0u;
+    }
+    if (out_validity) {
+      unsigned word = __ballot_sync(0xffffffffu, ok);
+      if (lane_id() == 0) {
+        out_validity[w] = word;
+        local += __popc(word);
+      }
+    }
+  }
+  if (out_validity) {
+    int64_t s = block_sum<kBlock>(local);
+    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_rehash_kernel(GrouperTable t, const uint64_t* uniq_keys,
+                                                                const uint8_t* uniq_null, uint32_t n_groups,
+                                                                int64_t* overflow) {
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < n_groups; g += gridDim.x * kBlock) {
+    bool inserted;
+    int64_t slot = table_find_or_insert(t.keys, t.mask, 1, uniq_keys[g], uniq_null[g] != 0, &inserted);
+    if (slot < 0) {
+      *overflow = 1;
+      continue;
+    }
+    t.ids[slot] = g;
+  }
+}
+
+// uniques -> one key column
+__global__ void __launch_bounds__(kBlock) grouper_decode_kernel(KeyLayout L, int col, const uint64_t* uniq_keys,
+                                                                const uint8_t* uniq_null, uint32_t n_groups,
+                                                                void* out, uint32_t* out_validity,
+                                                                int64_t* valid_count) {
+  uint32_t nw = (n_groups + 31) >> 5;
+  int64_t local = 0;
+  for (uint32_t w = (blockIdx.x * kBlock + threadIdx.x) >> 5; w < nw; w += (gridDim.x * kBlock) >> 5) {
+    uint32_t g = (w << 5) + lane_id();
+    bool valid = false;
+    if (g < n_groups) {
+      uint64_t enc = uniq_keys[g];
+      uint64_t v;
+      if (L.n_keys == 1) {
+        valid = uniq_null[g] == 0;
+        v = enc;
+      } else {
+        valid = !((enc >> L.null_bit[col]) & 1);
+        v = enc >> L.bit_off[col];
+      }
+      if (!valid) v = 0;
+      switch (L.width[col]) {
+        case 1: static_cast<uint8_t*>(out)[g] = static_cast<uint8_t>(v); break;
+        case 2: static_cast<uint16_t*>(out)[g] = static_cast<uint16_t>(v); break;
+        case 4: static_cast<uint32_t*>(out)[g] = static_cast<uint32_t>(v); break;
+        default: static_cast<uint64_t*>(out)[g] = v; break;
+      }
+    }
+    unsigned word = __ballot_sync(0xffffffffu, valid);
+    if (lane_id() == 0) {
+      out_validity[w] = word;
+      local += __popc(word);
+    }
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct B2Grouper {
+  B2Context* ctx;
+  KeyLayout layout;
+  int32_t key_types[kMaxKeys];
+  GrouperTable table{};
+  uint64_t cap = 0;
+  uint32_t num_groups = 0;
+  uint64_t* uniq_keys = nullptr;
+  uint8_t* uniq_null = nullptr;
+  uint64_t uniq_cap = 0;
+};
+
+static void grouper_free_table(B2Grouper* g, cudaStream_t s) {
+  if (g->table.keys) g->ctx->free(g->table.keys, s);
+  if (g->table.ids) g->ctx->free(g->table.ids, s);
+  if (g->table.first_row) g->ctx->free(g->table.first_row, s);
+  g->table = GrouperTable{};
+  g->cap = 0;
+}
+
+static int grouper_alloc_table(B2Grouper* g, uint64_t cap, cudaStream_t s) {
+  GrouperTable t;
+  void* p;
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 8, &p, s));
+  t.keys = static_cast<unsigned long long*>(p);
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 4, &p, s));
+  t.ids = static_cast<uint32_t*>(p);
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 4, &p, s));
+  t.first_row = static_cast<uint32_t*>(p);
+  t.mask = cap - 1;
+  grouper_init_kernel<<<grid_for((int64_t)cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(t);
+  B2_LAUNCHED();
+  g->table = t;
+  g->cap = cap;
+  return B2_OK;
+}
+
+// (re)build the table at `cap` slots from the uniques
+static int grouper_rebuild(B2Grouper* g, uint64_t cap, cudaStream_t s) {
+  while (true) {
+    grouper_free_table(g, s);
+    B2_RETURN_NOT_OK(grouper_alloc_table(g, cap, s));
+    if (g->num_groups == 0) return B2_OK;
+    ScalarSlot slot(g->ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    grouper_rehash_kernel<<<grid_for(g->num_groups, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+        g->table, g->uniq_keys, g->uniq_null, g->num_groups, slot.dev());
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    if (!slot.host()[0]) return B2_OK;
+    cap *= 4;
+  }
+}
+
+static int grouper_reserve_uniques(B2Grouper* g, uint64_t need, cudaStream_t s) {
+  if (need <= g->uniq_cap) return B2_OK;
+  uint64_t cap = next_pow2(need < 1024 ? 1024 : need);
+  void *k, *nl;
+  B2_RETURN_NOT_OK(g->ctx->alloc(cap * 8, &k, s));
+  B2_RETURN_NOT_OK(g->ctx->alloc(cap, &nl, s));
+  if (g->num_groups) {
+    B2_CUDA(cudaMemcpyAsync(k, g->uniq_keys, (size_t)g->num_groups * 8, cudaMemcpyDeviceToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(nl, g->uniq_null, (size_t)g->num_groups, cudaMemcpyDeviceToDevice, s));
+  }
+  if (g->uniq_keys) g->ctx->free(g->uniq_keys, s);
+  if (g->uniq_null) g->ctx->free(g->uniq_null, s);
+  g->uniq_keys = static_cast<uint64_t*>(k);
+  g->uniq_null = static_cast<uint8_t*>(nl);
+  g->uniq_cap = cap;
+  return B2_OK;
+}
+
+static int grouper_columns(const B2Grouper* g, const B2Array* keys, KeyColumns* c, int64_t* n) {
+  if (!keys) return set_error(B2_INVALID, "grouper: null keys");
+  *n = keys[0].length;
+  for (int j = 0; j < g->layout.n_keys; ++j) {
+    if (keys[j].type != g->key_types[j])
+      return set_error(B2_INVALID, "expected batch value %d of type id %d but got %d", j, g->key_types[j], keys[j].type);
+    if (keys[j].length != *n) return set_error(B2_INVALID, "grouper: key columns differ in length");
+    c->data[j] = static_cast<const char*>(keys[j].data) + keys[j].offset * g->layout.width[j];
+    c->valid[j] = BitmapReader(keys[j].null_count == 0 ? nullptr : keys[j].validity, keys[j].offset, keys[j].length);
+  }
+  return B2_OK;
+}
+
+static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool insert, cudaStream_t s) {
+  B2Context* ctx = g->ctx;
+  KeyColumns cols;
+  int64_t n;
+  B2_RETURN_NOT_OK(grouper_columns(g, keys, &cols, &n));
+  if (n > 0xfffffff0ll) return set_error(B2_NOT_IMPLEMENTED, "grouper: batches above 2^32 rows must be split");
+  Temp ids(ctx, s);
+  B2_RETURN_NOT_OK(ids.alloc(sizeof(uint32_t) * (size_t)n));
+  if (n == 0) {
+    fill_out(out_ids, B2_UINT32, 0, 0, nullptr, ids.release());
+    return B2_OK;
+  }
+  Temp row_slot(ctx, s);
+  B2_RETURN_NOT_OK(row_slot.alloc(sizeof(uint32_t) * (size_t)n));
+  const int grid = grid_for(n, kBlock * 4, kSMs * 8);
+
+  if (!insert) {
+    if (g->cap == 0) B2_RETURN_NOT_OK(grouper_rebuild(g, 1024, s));
+    grouper_probe_kernel<false><<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, row_slot.as<uint32_t>(), nullptr);
+    B2_LAUNCHED();
+    Temp bits(ctx, s);
+    B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
+    B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>(),
+                                                  bits.as<uint32_t>(), slot.dev());
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    int64_t nulls = n - slot.host()[0];
+    fill_out(out_ids, B2_UINT32, n, nulls, nulls ? bits.release() : nullptr, ids.release());
+    return B2_OK;
+  }
+
+  // make room: at most n new groups; keep load <= 1/2 with a modest first guess
+  if (g->cap == 0) {
+    uint64_t guess = next_pow2((uint64_t)(n < 512 ? 1024 : (n < (1 << 22) ? 2 * n : (1 << 23))));
+    B2_RETURN_NOT_OK(grouper_rebuild(g, guess, s));
+  }
+  while (true) {
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    grouper_probe_kernel<true><<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, row_slot.as<uint32_t>(), slot.dev());
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    if (!slot.host()[0]) break;
+    // probe limit hit: grow 4x; keys without ids are dropped by the rebuild and re-inserted
+    B2_RETURN_NOT_OK(grouper_rebuild(g, g->cap * 4, s));
+  }
+  Temp flags(ctx, s);
+  B2_RETURN_NOT_OK(flags.alloc(bitmap_alloc_bytes(n)));
+  B2_CUDA(cudaMemsetAsync(flags.ptr, 0, bitmap_alloc_bytes(n), s));
+  grouper_flag_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), flags.as<uint32_t>());
+  B2_LAUNCHED();
+  FilterBitmaps fb;
+  fb.mask_data = BitmapReader(flags.ptr, 0, n);
+  fb.mask_valid = BitmapReader(nullptr, 0, n);
+  fb.values_valid = BitmapReader(nullptr, 0, n);
+  fb.emit_null = 0;
+  Temp offsets(ctx, s);
+  int64_t n_new = 0, unused = 0;
+  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, false, &offsets, &n_new, &unused, s));
+  if ((uint64_t)g->num_groups + (uint64_t)n_new >= kNoId)
+    return set_error(B2_CAPACITY_ERROR, "grouper: more than 2^32-1 groups");
+  if (n_new > 0) {
+    B2_RETURN_NOT_OK(grouper_reserve_uniques(g, (uint64_t)g->num_groups + n_new, s));
+    grouper_assign_kernel<<<(unsigned)tiles_for(n), kBlock, 0, s>>>(g->layout, cols, n, g->table,
+                                                                   row_slot.as<uint32_t>(), fb.mask_data,
+                                                                   offsets.as<int64_t>(), g->num_groups,
+                                                                   g->uniq_keys, g->uniq_null);
+    B2_LAUNCHED();
+    g->num_groups += static_cast<uint32_t>(n_new);
+  }
+  grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>(), nullptr, nullptr);
+  B2_LAUNCHED();
+  fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
+  // keep load factor <= 1/2 for the next batch
+  if ((uint64_t)g->num_groups * 2 > g->cap) {
+    B2_CUDA(cudaStreamSynchronize(s));
+    B2_RETURN_NOT_OK(grouper_rebuild(g, next_pow2((uint64_t)g->num_groups * 4), s));
+  }
+  return B2_OK;
+}
+
+extern "C" {
+
+int b2_grouper_create(B2Context* ctx, const int32_t* key_types, int n_keys, B2Grouper** out) {
+  if (!ctx || !key_types || !out) return set_error(B2_INVALID, "b2_grouper_create: null argument");
+  if (n_keys < 1 || n_keys > kMaxKeys) return set_error(B2_NOT_IMPLEMENTED, "grouper: 1..%d key columns supported", kMaxKeys);
+  KeyLayout L{};
+  L.n_keys = n_keys;
+  int bits = 0;
+  for (int j = 0; j < n_keys; ++j) {
+    int w = type_width(key_types[j]);
+    if (w == 0) return set_error(B2_NOT_IMPLEMENTED, "grouper: key type id %d is not fixed-width", key_types[j]);
+    L.width[j] = w;
+    L.bit_off[j] = bits;
+    bits += 8 * w;
+    L.null_bit[j] = -1;
+  }
+  if (n_keys > 1) {
+    for (int j = 0; j < n_keys; ++j) L.null_bit[j] = bits++;
+  }
+  if (bits > 64)
+    return set_error(B2_NOT_IMPLEMENTED, "grouper: encoded key needs %d bits; at most 64 are supported", bits);
+  B2Grouper* g = new B2Grouper();
+  g->ctx = ctx;
+  g->layout = L;
+  for (int j = 0; j < n_keys; ++j) g->key_types[j] = key_types[j];
+  *out = g;
+  return B2_OK;
+}
+
+void b2_grouper_destroy(B2Grouper* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  cudaStream_t s = g->ctx->stream;
+  grouper_free_table(g, s);
+  if (g->uniq_keys) g->ctx->free(g->uniq_keys, s);
+  if (g->uniq_null) g->ctx->free(g->uniq_null, s);
+  delete g;
+}
+
+int b2_grouper_consume(B2Grouper* g, const B2Array* keys, B2Array* out_ids, void* stream) {
+  if (!g || !out_ids) return set_error(B2_INVALID, "b2_grouper_consume: null argument");
+  B2_CUDA(cudaSetDevice(g->ctx->device));
+  return grouper_run(g, keys, out_ids, true, g->ctx->pick(stream));
+}
+
+int b2_grouper_lookup(B2Grouper* g, const B2Array* keys, B2Array* out_ids, void* stream) {
+  if (!g || !out_ids) return set_error(B2_INVALID, "b2_grouper_lookup: null argument");
+  B2_CUDA(cudaSetDevice(g->ctx->device));
+  return grouper_run(g, keys, out_ids, false, g->ctx->pick(stream));
+}
+
+int b2_grouper_num_groups(const B2Grouper* g, uint32_t* out) {
+  if (!g || !out) return set_error(B2_INVALID, "b2_grouper_num_groups: null argument");
+  *out = g->num_groups;
+  return B2_OK;
+}
+
+int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream) {
+  if (!g || !out_keys) return set_error(B2_INVALID, "b2_grouper_uniques: null argument");
+  B2Context* ctx = g->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const uint32_t n = g->num_groups;
+  for (int j = 0; j < g->layout.n_keys; ++j) {
+    Temp data(ctx, s), bits(ctx, s);
+    B2_RETURN_NOT_OK(data.alloc((size_t)n * g->layout.width[j]));
+    int64_t nulls = 0;
+    if (n > 0) {
+      B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
+      B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
+      ScalarSlot slot(ctx);
+      B2_RETURN_NOT_OK(slot.zero(s));
+      grouper_decode_kernel<<<grid_for(n, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+          g->layout, j, g->uniq_keys, g->uniq_null, n, data.ptr, bits.as<uint32_t>(), slot.dev());
+      B2_LAUNCHED();
+      B2_RETURN_NOT_OK(slot.fetch(s));
+      nulls = (int64_t)n - slot.host()[0];
+    }
+    fill_out(&out_keys[j], g->key_types[j], n, nulls, nulls ? bits.release() : nullptr, data.release());
+  }
+  return B2_OK;
+}
+
+int b2_grouper_reset(B2Grouper* g) {
+  if (!g) return set_error(B2_INVALID, "b2_grouper_reset: null argument");
+  B2_CUDA(cudaSetDevice(g->ctx->device));
+  cudaStream_t s = g->ctx->stream;
+  grouper_free_table(g, s);
+  g->num_groups = 0;
+  return B2_OK;
+}
+
+}  // extern "C"

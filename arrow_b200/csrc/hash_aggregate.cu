@@ -1,0 +1,393 @@
+// hash_aggregate.cu -- grouped aggregators driven by uint32 group ids, plus the fused
+// (key,value) -> table group-by used by the aggregate node.
+//
+// Replaces the HashAggregateKernel contract {init,resize,consume,merge,finalize}
+// (cpp/src/arrow/compute/kernel.h:720-769) for
+//   GroupedSumImpl / GroupedMeanImpl via GroupedReducingAggregator
+//                                      kernels/hash_aggregate_numeric.cc:44-190,274-295,359-434
+//   GroupedCountImpl / GroupedCountAllImpl      kernels/hash_aggregate.cc:61-272
+//   GroupedMinMaxImpl (hash_min / hash_max)     kernels/hash_aggregate.cc:330-420
+//   VisitGroupedValues                          kernels/hash_aggregate_internal.h:148-171
+// Semantics kept: integer sums accumulate in int64/uint64 with wrap-around (unsigned
+// add), float sums and all means in double; count modes ONLY_VALID/ONLY_NULL/ALL;
+// sum/mean are null where count < min_count, and (skip_nulls=false) where the group saw
+// a null; min/max ignore NaN like std::fmin/fmax and are null for groups without values.
+// Integer results are bit-exact; float sums differ from the reference only by summation
+// order (the reference adds in row order, atomics do not) -- tests use a tolerance there.
+//
+// B200 design: one thread per row, coalesced id/value loads, one red.global per state
+// word.  The state (G x 8 B sums + G x 8 B counts) lives in L2 when G is small; for
+// G >> L2 every update is a 32-byte sector RMW in HBM, which is what bounds config 3.
+#include <cmath>
+#include <limits>
+#include <type_traits>
+
+#include "bitmap.h"
+#include "hash_table.cuh"
+
+namespace b2 {
+
+enum AccKind { ACC_I64 = 0, ACC_U64 = 1, ACC_F64 = 2 };
+
+__host__ __device__ inline int acc_kind_for(int value_type) {
+  switch (value_type) {
+    case B2_INT8: case B2_INT16: case B2_INT32: case B2_INT64: return ACC_I64;
+    case B2_UINT8: case B2_UINT16: case B2_UINT32: case B2_UINT64: return ACC_U64;
+    default: return ACC_F64;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T load_as(const void* p, int64_t i) {
+  return static_cast<const T*>(p)[i];
+}
+
+// ordered encoding so min/max of any numeric type is an unsigned 64-bit atomicMin/Max
+template <typename T>
+__device__ __forceinline__ unsigned long long minmax_encode(T v) {
+  if constexpr (std::is_floating_point<T>::value) {
+    double d = static_cast<double>(v);
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(d));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+  } else if constexpr (std::is_signed<T>::value) {
+    return static_cast<unsigned long long>(static_cast<long long>(v)) ^ 0x8000000000000000ull;
+  } else {
+    return static_cast<unsigned long long>(v);
+  }
+}
+
+struct AggState {
+  unsigned long long* reduced;  // [G] sum bits / ordered min-max key
+  unsigned long long* counts;   // [G]
+  uint8_t* flags;               // [G] bit0 = saw a null, bit1 = has a value
+};
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __restrict__ values,
+                                                                 BitmapReader valid,
+                                                                 const uint32_t* __restrict__ ids, int64_t n,
+                                                                 AggState st, int count_mode) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint32_t g = ids[i];
+    const bool ok = valid.bit(i);
+    if (KIND == B2_HASH_COUNT) {
+      bool inc = count_mode == 2 || (count_mode == 0 ? ok : !ok);
+      if (inc) atomicAdd(&st.counts[g], 1ull);
+      continue;
+    }
+    if (!ok) {
+      st.flags[g] |= 1;  // benign race: only ever sets bit 0 (byte store of an OR'd value)
+      continue;
+    }
+    const T v = values[i];
+    if (KIND == B2_HASH_SUM || KIND == B2_HASH_MEAN) {
+      if (std::is_floating_point<T>::value || KIND == B2_HASH_MEAN) {
+        atomicAdd(reinterpret_cast<double*>(&st.reduced[g]), static_cast<double>(v));
+      } else if (std::is_signed<T>::value) {
+        atomicAdd(&st.reduced[g], static_cast<unsigned long long>(static_cast<long long>(v)));
+      } else {
+        atomicAdd(&st.reduced[g], static_cast<unsigned long long>(v));
+      }
+      atomicAdd(&st.counts[g], 1ull);
+    } else {  // MIN / MAX
+      if (v == v) {  // fmin/fmax skip NaN
+        if (KIND == B2_HASH_MIN) atomicMin(&st.reduced[g], minmax_encode<T>(v));
+        else atomicMax(&st.reduced[g], minmax_encode<T>(v));
+      }
+      atomicAdd(&st.counts[g], 1ull);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) hashagg_countall_kernel(const uint32_t* __restrict__ ids, int64_t n,
+                                                                  unsigned long long* counts) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    atomicAdd(&counts[ids[i]], 1ull);
+}
+
+__global__ void __launch_bounds__(kBlock) hashagg_fill_kernel(unsigned long long* p, unsigned long long v,
+                                                              int64_t from, int64_t to) {
+  for (int64_t i = from + blockIdx.x * (int64_t)kBlock + threadIdx.x; i < to; i += (int64_t)gridDim.x * kBlock) p[i] = v;
+}
+
+// state[map[i]] (+)= other[i]
+__global__ void __launch_bounds__(kBlock) hashagg_merge_kernel(AggState dst, AggState src, const uint32_t* map,
+                                                               int64_t n, int kind, int acc) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint32_t g = map[i];
+    atomicAdd(&dst.counts[g], src.counts[i]);
+    if (src.flags[i] & 1) dst.flags[g] |= 1;
+    if (kind == B2_HASH_SUM || kind == B2_HASH_MEAN) {
+      if (acc == ACC_F64 || kind == B2_HASH_MEAN)
+        atomicAdd(reinterpret_cast<double*>(&dst.reduced[g]), __longlong_as_double((long long)src.reduced[i]));
+      else
+        atomicAdd(&dst.reduced[g], src.reduced[i]);
+    } else if (kind == B2_HASH_MIN) {
+      atomicMin(&dst.reduced[g], src.reduced[i]);
+    } else if (kind == B2_HASH_MAX) {
+      atomicMax(&dst.reduced[g], src.reduced[i]);
+    }
+  }
+}
+
+// state -> output column + validity (ballot) ; out_type is the finalized type id
+__global__ void __launch_bounds__(kBlock) hashagg_finalize_kernel(AggState st, int64_t n, int kind, int acc,
+                                                                  int out_type, int skip_nulls, uint32_t min_count,
+                                                                  void* out, uint32_t* out_validity,
+                                                                  int64_t* valid_count) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    int64_t g = (w << 5) + lane_id();
+    bool valid = false;
+    if (g < n) {
+      const unsigned long long c = st.counts[g];
+      const unsigned long long r = st.reduced ? st.reduced[g] : 0ull;
+      const bool saw_null = st.flags && (st.flags[g] & 1);
+      if (kind == B2_HASH_COUNT || kind == B2_HASH_COUNT_ALL) {
+        static_cast<long long*>(out)[g] = static_cast<long long>(c);
+        valid = true;
+      } else if (kind == B2_HASH_SUM) {
+        valid = c >= min_count && (skip_nulls || !saw_null);
+        static_cast<unsigned long long*>(out)[g] = r;  // int64 / uint64 / double share the bits
+      } else if (kind == B2_HASH_MEAN) {
+        valid = c >= min_count && (skip_nulls || !saw_null);
+        double m = c >= min_count && c > 0 ? __longlong_as_double((long long)r) / static_cast<double>(c) : 0.0;
+        static_cast<double*>(out)[g] = m;
+      } else {  // MIN / MAX: valid iff the group has a value (hash_aggregate.cc:401-411)
+        valid = c > 0 && (skip_nulls || !saw_null);
+        // decode the ordered key back into out_type
+        unsigned long long k = r;
+        if (out_type == B2_FLOAT || out_type == B2_DOUBLE) {
+          unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+          double d = __longlong_as_double((long long)b);
+          if (out_type == B2_FLOAT) static_cast<float*>(out)[g] = static_cast<float>(d);
+          else static_cast<double*>(out)[g] = d;
+        } else {
+          long long sv = (acc == ACC_I64) ? static_cast<long long>(k ^ 0x8000000000000000ull) : static_cast<long long>(k);
+          switch (type_width(out_type)) {
+            case 1: static_cast<uint8_t*>(out)[g] = static_cast<uint8_t>(sv); break;
+            case 2: static_cast<uint16_t*>(out)[g] = static_cast<uint16_t>(sv); break;
+            case 4: static_cast<uint32_t*>(out)[g] = static_cast<uint32_t>(sv); break;
+            default: static_cast<unsigned long long*>(out)[g] = static_cast<unsigned long long>(sv); break;
+          }
+        }
+      }
+    }
+    unsigned word = __ballot_sync(0xffffffffu, valid);
+    if (lane_id() == 0) {
+      out_validity[w] = word;
+      local += __popc(word);
+    }
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct B2HashAgg {
+  B2Context* ctx;
+  int kind;
+  int value_type;
+  int acc;
+  B2HashAggOptions opt;
+  AggState st{};
+  int64_t num_groups = 0;
+  int64_t cap = 0;
+};
+
+static unsigned long long agg_identity(const B2HashAgg* a) {
+  // anti-extrema in the ordered encoding (AntiExtrema<T>, hash_aggregate.cc:349-350):
+  // floats start at +inf / -inf so a group holding only NaNs finalizes like std::fmin/fmax
+  const bool flt = a->acc == ACC_F64;
+  if (a->kind == B2_HASH_MIN) return flt ? 0xfff0000000000000ull : ~0ull;
+  if (a->kind == B2_HASH_MAX) return flt ? 0x000fffffffffffffull : 0ull;
+  return 0ull;  // sum / mean: 0 (== 0.0)
+}
+
+template <typename T>
+static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, cudaStream_t s) {
+  const int64_t n = ids->length;
+  const T* v = static_cast<const T*>(values->data) + values->offset;
+  const uint32_t* id = static_cast<const uint32_t*>(ids->data) + ids->offset;
+  BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  int grid = grid_for(n, kBlock * 4, kSMs * 16);
+  switch (a->kind) {
+    case B2_HASH_SUM: hashagg_consume_kernel<T, B2_HASH_SUM><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0); break;
+    case B2_HASH_MEAN: hashagg_consume_kernel<T, B2_HASH_MEAN><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0); break;
+    case B2_HASH_MIN: hashagg_consume_kernel<T, B2_HASH_MIN><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0); break;
+    case B2_HASH_MAX: hashagg_consume_kernel<T, B2_HASH_MAX><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0); break;
+    case B2_HASH_COUNT:
+      hashagg_consume_kernel<T, B2_HASH_COUNT><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, a->opt.count_mode);
+      break;
+    default: return set_error(B2_NOT_IMPLEMENTED, "hash aggregate kind %d", a->kind);
+  }
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+extern "C" {
+
+int b2_hashagg_create(B2Context* ctx, int kind, int32_t value_type, const B2HashAggOptions* options,
+                      B2HashAgg** out) {
+  if (!ctx || !out) return set_error(B2_INVALID, "b2_hashagg_create: null argument");
+  if (kind < B2_HASH_SUM || kind > B2_HASH_MAX)
+    return set_error(B2_NOT_IMPLEMENTED, "hash aggregate kind %d is not implemented", kind);
+  if (kind != B2_HASH_COUNT_ALL && kind != B2_HASH_COUNT && !type_is_numeric(value_type))
+    return set_error(B2_NOT_IMPLEMENTED, "hash aggregate over value type id %d", value_type);
+  B2HashAgg* a = new B2HashAgg();
+  a->ctx = ctx;
+  a->kind = kind;
+  a->value_type = value_type;
+  a->acc = acc_kind_for(value_type);
+  if (options) a->opt = *options;
+  else a->opt = B2HashAggOptions{1, 1, 0, 0};
+  *out = a;
+  return B2_OK;
+}
+
+void b2_hashagg_destroy(B2HashAgg* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  cudaStream_t s = a->ctx->stream;
+  if (a->st.reduced) a->ctx->free(a->st.reduced, s);
+  if (a->st.counts) a->ctx->free(a->st.counts, s);
+  if (a->st.flags) a->ctx->free(a->st.flags, s);
+  delete a;
+}
+
+int32_t b2_hashagg_out_type(const B2HashAgg* a) {
+  if (!a) return B2_NA;
+  switch (a->kind) {
+    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return B2_INT64;
+    case B2_HASH_MEAN: return B2_DOUBLE;
+    case B2_HASH_SUM: return a->acc == ACC_I64 ? B2_INT64 : a->acc == ACC_U64 ? B2_UINT64 : B2_DOUBLE;
+    default: return a->value_type;
+  }
+}
+
+int b2_hashagg_resize(B2HashAgg* a, int64_t num_groups, void* stream) {
+  if (!a) return set_error(B2_INVALID, "b2_hashagg_resize: null argument");
+  if (num_groups < a->num_groups) return set_error(B2_INVALID, "hash aggregate state cannot shrink");
+  B2Context* ctx = a->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  if (num_groups > a->cap) {
+    int64_t cap = static_cast<int64_t>(next_pow2(num_groups < 1024 ? 1024 : num_groups));
+    void *r, *c, *f;
+    B2_RETURN_NOT_OK(ctx->alloc(cap * 8, &r, s));
+    B2_RETURN_NOT_OK(ctx->alloc(cap * 8, &c, s));
+    B2_RETURN_NOT_OK(ctx->alloc(cap, &f, s));
+    if (a->num_groups) {
+      B2_CUDA(cudaMemcpyAsync(r, a->st.reduced, a->num_groups * 8, cudaMemcpyDeviceToDevice, s));
+      B2_CUDA(cudaMemcpyAsync(c, a->st.counts, a->num_groups * 8, cudaMemcpyDeviceToDevice, s));
+      B2_CUDA(cudaMemcpyAsync(f, a->st.flags, a->num_groups, cudaMemcpyDeviceToDevice, s));
+    }
+    if (a->st.reduced) ctx->free(a->st.reduced, s);
+    if (a->st.counts) ctx->free(a->st.counts, s);
+    if (a->st.flags) ctx->free(a->st.flags, s);
+    a->st.reduced = static_cast<unsigned long long*>(r);
+    a->st.counts = static_cast<unsigned long long*>(c);
+    a->st.flags = static_cast<uint8_t*>(f);
+    a->cap = cap;
+  }
+  const int64_t added = num_groups - a->num_groups;
+  if (added > 0) {
+    hashagg_fill_kernel<<<grid_for(added, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(a->st.reduced, agg_identity(a),
+                                                                                 a->num_groups, num_groups);
+    B2_LAUNCHED();
+    B2_CUDA(cudaMemsetAsync(a->st.counts + a->num_groups, 0, added * 8, s));
+    B2_CUDA(cudaMemsetAsync(a->st.flags + a->num_groups, 0, added, s));
+  }
+  a->num_groups = num_groups;
+  return B2_OK;
+}
+
+int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, void* stream) {
+  if (!a || !ids) return set_error(B2_INVALID, "b2_hashagg_consume: null argument");
+  if (ids->type != B2_UINT32) return set_error(B2_TYPE_ERROR, "group ids must be uint32");
+  B2Context* ctx = a->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = ids->length;
+  if (n == 0) return B2_OK;
+  const uint32_t* id = static_cast<const uint32_t*>(ids->data) + ids->offset;
+  if (a->kind == B2_HASH_COUNT_ALL) {
+    hashagg_countall_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(id, n, a->st.counts);
+    B2_LAUNCHED();
+    return B2_OK;
+  }
+  if (!values) return set_error(B2_INVALID, "hash aggregate needs a value column");
+  if (values->length != n) return set_error(B2_INVALID, "values and group ids differ in length");
+  if (a->kind == B2_HASH_COUNT && !type_is_numeric(values->type)) {
+    // count only needs validity: any layout works
+    BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+    hashagg_consume_kernel<uint8_t, B2_HASH_COUNT><<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(
+        nullptr, valid, id, n, a->st, a->opt.count_mode);
+    B2_LAUNCHED();
+    return B2_OK;
+  }
+  if (values->type != a->value_type && a->kind != B2_HASH_COUNT)
+    return set_error(B2_TYPE_ERROR, "hash aggregate was created for type id %d, got %d", a->value_type, values->type);
+  switch (values->type) {
+    case B2_INT8: return launch_consume<int8_t>(a, values, ids, s);
+    case B2_UINT8: return launch_consume<uint8_t>(a, values, ids, s);
+    case B2_INT16: return launch_consume<int16_t>(a, values, ids, s);
+    case B2_UINT16: return launch_consume<uint16_t>(a, values, ids, s);
+    case B2_INT32: return launch_consume<int32_t>(a, values, ids, s);
+    case B2_UINT32: return launch_consume<uint32_t>(a, values, ids, s);
+    case B2_INT64: return launch_consume<int64_t>(a, values, ids, s);
+    case B2_UINT64: return launch_consume<uint64_t>(a, values, ids, s);
+    case B2_FLOAT: return launch_consume<float>(a, values, ids, s);
+    case B2_DOUBLE: return launch_consume<double>(a, values, ids, s);
+    default: return set_error(B2_NOT_IMPLEMENTED, "hash aggregate over value type id %d", values->type);
+  }
+}
+
+int b2_hashagg_merge(B2HashAgg* a, B2HashAgg* other, const B2Array* group_id_mapping, void* stream) {
+  if (!a || !other || !group_id_mapping) return set_error(B2_INVALID, "b2_hashagg_merge: null argument");
+  if (a->kind != other->kind || a->value_type != other->value_type)
+    return set_error(B2_INVALID, "cannot merge different aggregators");
+  if (group_id_mapping->type != B2_UINT32 || group_id_mapping->length != other->num_groups)
+    return set_error(B2_INVALID, "group_id_mapping must be uint32 with one entry per group of `other`");
+  B2Context* ctx = a->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = other->num_groups;
+  if (n == 0) return B2_OK;
+  const uint32_t* map = static_cast<const uint32_t*>(group_id_mapping->data) + group_id_mapping->offset;
+  hashagg_merge_kernel<<<grid_for(n, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(a->st, other->st, map, n, a->kind, a->acc);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+int b2_hashagg_finalize(B2HashAgg* a, B2Array* out, void* stream) {
+  if (!a || !out) return set_error(B2_INVALID, "b2_hashagg_finalize: null argument");
+  B2Context* ctx = a->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = a->num_groups;
+  const int out_type = b2_hashagg_out_type(a);
+  Temp data(ctx, s), bits(ctx, s);
+  B2_RETURN_NOT_OK(data.alloc((size_t)n * type_width(out_type)));
+  int64_t nulls = 0;
+  if (n > 0) {
+    B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
+    B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    hashagg_finalize_kernel<<<grid_for(n, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+        a->st, n, a->kind, a->acc, out_type, a->opt.skip_nulls, a->opt.min_count, data.ptr, bits.as<uint32_t>(),
+        slot.dev());
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    nulls = n - slot.host()[0];
+  }
+  fill_out(out, out_type, n, nulls, nulls ? bits.release() : nullptr, data.release());
+  return B2_OK;
+}
+
+}  // extern "C"

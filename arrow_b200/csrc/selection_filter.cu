@@ -25,34 +25,9 @@
 //      flushed with plain word stores (atomicOr only on the two boundary words).
 // Algorithmic bytes/row (int64, values nullable, mask non-null, s=0.5): 12.3125
 // (SURVEY section 8d); passes 1+2 re-read only the bitmaps (+0.25 B/row).
-#include "bitmap.h"
-#include "common.cuh"
-#include "context.h"
+#include "selection.cuh"
 
 namespace b2 {
-
-constexpr int kTileRows = 4096;  // rows per compaction tile = 64 bitmap words
-constexpr int kTileWords = kTileRows / 64;
-
-struct FilterBitmaps {
-  BitmapReader mask_data, mask_valid, values_valid;
-  int emit_null;
-  // selection word: DROP = data & valid ; EMIT_NULL = data | ~valid
-  __device__ __forceinline__ uint64_t sel(int64_t w) const {
-    uint64_t d = mask_data.word(w);
-    if (!mask_valid.present()) return d;
-    uint64_t v = mask_valid.word(w);
-    if (!emit_null) return d & v;
-    // ~v must not leak past nbits: build the in-range mask from an all-ones reader
-    int64_t rem = mask_data.nbits - (w << 6);
-    uint64_t in_range = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1ull));
-    return (d | ~v) & in_range;
-  }
-  // validity of the selected rows before compaction
-  __device__ __forceinline__ uint64_t out_valid(int64_t w) const {
-    return values_valid.word(w) & mask_valid.word(w);
-  }
-};
 
 // ---- pass 1: per-tile selected counts (+ total valid-and-selected) ----
 __global__ void __launch_bounds__(kBlock) filter_count_kernel(FilterBitmaps fb, int64_t n_tiles,
@@ -266,10 +241,9 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
   }
 }
 
-static int64_t tiles_for(int64_t n) { return (n + kTileRows - 1) / kTileRows; }
 
 // passes 1+2; returns device tile offsets (caller frees), output length and selected-valid count
-static int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_valid,
+int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_valid,
                        Temp* offsets, int64_t* out_length, int64_t* out_valid, cudaStream_t s) {
   int64_t n_tiles = tiles_for(n);
   Temp counts(ctx, s);
@@ -297,7 +271,7 @@ static int check_mask(const B2Array* mask) {
   return B2_OK;
 }
 
-static FilterBitmaps make_bitmaps(const B2Array* values, const B2Array* mask, int null_selection) {
+FilterBitmaps make_filter_bitmaps(const B2Array* values, const B2Array* mask, int null_selection) {
   FilterBitmaps fb;
   fb.mask_data = BitmapReader(mask->data, mask->offset, mask->length);
   fb.mask_valid = BitmapReader(mask->null_count == 0 ? nullptr : mask->validity, mask->offset, mask->length);
@@ -340,7 +314,7 @@ extern "C" int b2_filter_output_size(B2Context* ctx, const B2Array* mask, int nu
   B2_CUDA(cudaSetDevice(ctx->device));
   *out_length = 0;
   if (mask->length == 0) return B2_OK;
-  FilterBitmaps fb = make_bitmaps(nullptr, mask, null_selection);
+  FilterBitmaps fb = make_filter_bitmaps(nullptr, mask, null_selection);
   Temp offsets(ctx, s);
   int64_t valid;
   return filter_plan(ctx, fb, mask->length, false, &offsets, out_length, &valid, s);
@@ -367,7 +341,7 @@ extern "C" int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* m
     out->byte_width = values->byte_width;
     return B2_OK;
   }
-  FilterBitmaps fb = make_bitmaps(values, mask, null_selection);
+  FilterBitmaps fb = make_filter_bitmaps(values, mask, null_selection);
   Temp offsets(ctx, s);
   int64_t out_len = 0, out_valid = 0;
   B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));
@@ -412,7 +386,7 @@ extern "C" int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_s
     return B2_OK;
   }
   const bool has_valid = null_selection == 1 && mask->null_count != 0 && mask->validity;
-  FilterBitmaps fb = make_bitmaps(nullptr, mask, null_selection);
+  FilterBitmaps fb = make_filter_bitmaps(nullptr, mask, null_selection);
   Temp offsets(ctx, s);
   int64_t out_len = 0, out_valid = 0;
   B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));

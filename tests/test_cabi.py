@@ -1,0 +1,75 @@
+"""CPU checks of the drop-in boundary: the built library loads, exports every symbol that
+include/arrow_b200.h declares, fails loudly without a GPU, and the host-side dispatch rules
+(no kernels involved) match the reference's."""
+import ctypes as C
+import os
+import re
+
+import pyarrow as pa
+import pytest
+
+from arrow_b200 import _cabi as cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "arrow_b200.h")).read()
+    return sorted(set(re.findall(r"B2_API\s+[\w\s\*]+?\b(b2_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    declared = header_symbols()
+    bound = sorted(name for name, _, _ in cabi.PROTOTYPES)
+    assert declared == bound, f"header-only: {set(declared) - set(bound)}; binding-only: {set(bound) - set(declared)}"
+
+
+def test_library_exports_every_symbol():
+    lib = cabi.lib()  # raises if the .so is missing or a symbol is not exported
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.b2_version().startswith(b"arrow_b200")
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = cabi.lib()
+    h = C.c_void_p()
+    st = lib.b2_context_create(0, C.byref(h))
+    assert st != 0 and b"no CPU" in lib.b2_last_error()
+    from arrow_b200.device import Context, CudaError
+    with pytest.raises(CudaError):
+        Context(0)
+
+
+def test_struct_layout_matches_header():
+    # B2Array: 3 pointers + 3 int64 + 2 int32 = 56 bytes; B2Scalar 16; options 16
+    assert C.sizeof(cabi.B2Array) == 56
+    assert C.sizeof(cabi.B2Scalar) == 16
+    assert C.sizeof(cabi.B2CastOptions) == 16
+    assert C.sizeof(cabi.B2HashAggOptions) == 16
+    assert C.sizeof(cabi.B2Value) == 16
+
+
+def test_type_ids_follow_arrow():
+    # arrow::Type::type values (type_fwd.h:328-460) as exposed by pyarrow
+    from arrow_b200.device import type_id
+    for t in (pa.bool_(), pa.uint8(), pa.int8(), pa.uint16(), pa.int16(), pa.uint32(), pa.int32(), pa.uint64(),
+              pa.int64(), pa.float32(), pa.float64(), pa.string(), pa.binary(), pa.large_string(), pa.large_binary()):
+        assert type_id(t) == t.id, str(t)
+    assert type_id(pa.timestamp("us")) == cabi.INT64 and type_id(pa.date32()) == cabi.INT32
+    assert type_id(pa.dictionary(pa.int32(), pa.string())) == cabi.INT32
+
+
+def test_common_numeric_matches_reference_dispatch():
+    import itertools
+    import pyarrow.compute as pc
+    from arrow_b200.compute import common_numeric
+    from arrow_b200.device import arrow_type, type_id
+    types = [pa.int8(), pa.uint8(), pa.int16(), pa.uint16(), pa.int32(), pa.uint32(), pa.int64(), pa.uint64(),
+             pa.float32(), pa.float64()]
+    for a, b in itertools.product(types, types):
+        want = pc.add(pa.array([1], a), pa.array([1], b)).type  # ArithmeticFunction::DispatchBest
+        assert arrow_type(common_numeric([type_id(a), type_id(b)])) == want, f"{a},{b}"

@@ -1,0 +1,462 @@
+"""Parity of the CUDA path (through the C-ABI, via arrow_b200.compute) against the oracle,
+the reference's known-answer vectors and -- since the same image ships it -- the
+reference binary (pyarrow.compute) on identical inputs.  Bit-exact for integer, index,
+selection, sort and cast outputs and for single IEEE float ops; float SUMS use rtol 1e-9
+(summation order differs; the reference itself compares those approximately,
+acero/hash_aggregate_test.cc:3641-3663)."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+import arrow_b200.compute as bc
+from arrow_b200 import DeviceArray
+from oracle import arrow_oracle as ora
+from tests.util import INT_TYPES, NUMERIC_TYPES, SEED, TYPE_BY_NAME, assert_equal, equal_nan, from_json, kat, random_array
+
+pytestmark = pytest.mark.gpu
+KAT = kat()
+
+
+def dev(arr, ctx):
+    return DeviceArray.from_arrow(arr, ctx)
+
+
+# ---------------------------------------------------------------- known answers
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_kat_filter(ctx, t):
+    for c in KAT["filter_numeric_basics"]["cases"]:
+        v, m = from_json(t, c["values"]), from_json(pa.bool_(), c["filter"])
+        for ns in ("emit_null", "drop"):
+            got = bc.filter(dev(v, ctx), dev(m, ctx), ns).to_arrow()
+            assert_equal(got, from_json(t, c[ns]), f"{ns} {c}")
+    with pytest.raises(pa.ArrowInvalid, match="same length"):
+        bc.filter(dev(from_json(t, [7, 8, 9]), ctx), dev(from_json(pa.bool_(), []), ctx))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_kat_take(ctx, t):
+    for c in KAT["take_numeric_basics"]["cases"]:
+        for it in (pa.int8(), pa.uint32(), pa.int64()):
+            got = bc.take(dev(from_json(t, c["values"]), ctx), dev(from_json(it, c["indices"]), ctx)).to_arrow()
+            assert_equal(got, from_json(t, c["expected"]), str(c))
+    for c in KAT["take_numeric_basics"]["index_errors"]:
+        with pytest.raises(pa.ArrowIndexError, match="out of bounds"):
+            bc.take(dev(from_json(t, c["values"]), ctx), dev(from_json(pa.int8(), c["indices"]), ctx))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_kat_sort(ctx, t):
+    cases = list(KAT["sort_integral"]["cases"]) if pa.types.is_integer(t) else list(KAT["sort_real"]["cases"])
+    if t == pa.int64():
+        cases += KAT["sort_integral"]["int64_cases"]
+    for c in cases:
+        got = bc.array_sort_indices(dev(from_json(t, c["values"]), ctx), c["order"], c["null_placement"]).to_arrow()
+        assert_equal(got, pa.array(c["expected"], pa.uint64()), str(c))
+
+
+def test_kat_cast(ctx):
+    for c in KAT["cast_float_to_float"]["cases"]:
+        got = bc.cast(dev(from_json(TYPE_BY_NAME[c["from"]], c["values"]), ctx), TYPE_BY_NAME[c["to"]]).to_arrow()
+        assert_equal(got, from_json(TYPE_BY_NAME[c["to"]], c["expected"]))
+    for c in KAT["cast_int_to_float_bounds"]["ok"]:
+        src = from_json(TYPE_BY_NAME[c["from"]], c["values"])
+        assert_equal(bc.cast(dev(src, ctx), TYPE_BY_NAME[c["to"]]).to_arrow(), pc.cast(src, TYPE_BY_NAME[c["to"]]))
+    for c in KAT["cast_int_to_float_bounds"]["fails"]:
+        src = from_json(TYPE_BY_NAME[c["from"]], c["values"])
+        with pytest.raises(pa.ArrowInvalid) as want:
+            pc.cast(src, TYPE_BY_NAME[c["to"]])
+        with pytest.raises(pa.ArrowInvalid) as got:
+            bc.cast(dev(src, ctx), TYPE_BY_NAME[c["to"]])
+        assert str(got.value) == str(want.value)
+    c = KAT["cast_overflow_in_null_slot"]
+    v = pa.array(c["values"], TYPE_BY_NAME[c["from"]], mask=~np.array(c["validity"], dtype=bool))
+    assert_equal(bc.cast(dev(v, ctx), TYPE_BY_NAME[c["to"]]).to_arrow(), from_json(TYPE_BY_NAME[c["to"]], c["expected"]))
+
+
+def _sorted_by_key(keys, cols):
+    order = pc.sort_indices(keys, null_placement="at_end")
+    return [pc.take(c, order) for c in [keys] + list(cols)]
+
+
+def test_kat_group_by(ctx):
+    c = KAT["group_by_count_only"]
+    arg = pa.array([r[0] for r in c["rows"]], pa.float64())
+    key = pa.array([r[1] for r in c["rows"]], pa.int64())
+    for mode in ("only_valid", "only_null", "all"):
+        uniq, (cnt,) = bc.group_by([dev(key, ctx)], [("hash_count", dev(arg, ctx), {"mode": mode})])
+        k, v = _sorted_by_key(uniq[0].to_arrow(), [cnt.to_arrow()])
+        assert k.to_pylist() == [r[0] for r in c[mode]] and v.to_pylist() == [r[1] for r in c[mode]]
+    c = KAT["group_by_sum_only"]
+    arg = pa.array([r[0] for r in c["rows"]], pa.float64())
+    key = pa.array([r[1] for r in c["rows"]], pa.int64())
+    uniq, (s,) = bc.group_by([dev(key, ctx)], [("hash_sum", dev(arg, ctx), None)])
+    k, v = _sorted_by_key(uniq[0].to_arrow(), [s.to_arrow()])
+    assert k.to_pylist() == [r[0] for r in c["expected"]] and v.to_pylist() == [r[1] for r in c["expected"]]
+    # fused path, same vectors
+    f = bc.GroupBySumCount(pa.int64(), pa.float64(), ctx=ctx)
+    f.consume(dev(key, ctx), dev(arg, ctx))
+    fk, fs, fc = [x.to_arrow() for x in f.finalize()]
+    k, v = _sorted_by_key(fk, [fs])
+    assert k.to_pylist() == [r[0] for r in c["expected"]] and v.to_pylist() == [r[1] for r in c["expected"]]
+    c = KAT["grouper_int64"]
+    g = bc.Grouper([pa.int64()], ctx)
+    assert g.consume(dev(pa.array(c["keys"], pa.int64()), ctx)).to_arrow().to_pylist() == c["ids"]
+    assert g.num_groups == 4
+
+
+# ---------------------------------------------------------------- random, vs oracle and reference
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("null_p", [0.0, 0.01, 0.1, 0.999, 1.0])
+def test_filter_random(ctx, t, null_p):
+    # FilterRandomTest, vector_selection_test.cc:2241-2259 (+ larger sizes that span many tiles)
+    for i, (n, true_p, mask_null, off) in enumerate([(1024, 0.5, 0.0, 0), (1024, 0.1, 0.05, 3), (1024, 0.999, 0.5, 2),
+                                                     (1024, 0.0, 0.0, 1), (1024, 1.0, 0.0, 0), (70001, 0.5, 0.1, 5),
+                                                     (70001, 0.01, 0.0, 0)]):
+        v = random_array(t, n, null_p, SEED + i, offset=off)
+        m = random_array(pa.bool_(), n, mask_null, SEED + 77 + i, hi=true_p, offset=(off * 5) % 7)
+        dv, dm = dev(v, ctx), dev(m, ctx)
+        for ns in ("drop", "emit_null"):
+            got = bc.filter(dv, dm, ns)
+            want = ora.filter(v, m, ns)
+            assert_equal(got.to_arrow(), want, f"{t} {ns} case {i}")
+            assert got.null_count == want.null_count
+            assert bc.filter_output_size(dm, ns) == len(want)
+            assert_equal(got.to_arrow(), pc.filter(v, m, null_selection_behavior=ns))
+        # ValidateFilter: Filter(v, f) == Take(v, GetTakeIndices(f))  (vector_selection_test.cc:352-373)
+        if n <= 1024:
+            for ns in ("drop", "emit_null"):
+                idx = bc.take_indices_from_filter(dm, ns)
+                assert_equal(idx.to_arrow(), ora.take_indices_from_filter(m, ns))
+                assert_equal(bc.take(dv, idx).to_arrow(), bc.filter(dv, dm, ns).to_arrow())
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("it", [pa.int8(), pa.uint8(), pa.int16(), pa.uint16(), pa.int32(), pa.uint32(), pa.int64(),
+                                pa.uint64()], ids=str)
+def test_take_random(ctx, t, it):
+    # TakeRandomTest, vector_selection_test.cc:2286-2315
+    for null_p in (0.0, 0.001, 0.05, 0.25, 0.95, 1.0):
+        v = random_array(t, 1025, null_p, SEED, offset=1)
+        hi = min(1024, np.iinfo(it.to_pandas_dtype()).max)
+        for n_idx, off in ((257, 3), (9000, 0)):
+            idx = random_array(it, n_idx, null_p, SEED + 5, lo=0, hi=hi, offset=off)
+            got = bc.take(dev(v, ctx), dev(idx, ctx))
+            want = ora.take(v, idx)
+            assert_equal(got.to_arrow(), want, f"{t} {it} {null_p}")
+            assert got.null_count == want.null_count
+            assert_equal(got.to_arrow(), pc.take(v, idx))
+
+
+def test_take_errors(ctx):
+    v = dev(pa.array(range(100), pa.int64()), ctx)
+    for bad, it in ((100, pa.int32()), (-1, pa.int64()), (2**40, pa.int64()), (200, pa.uint8())):
+        idx = pa.array([1, 2, bad, 3], it)
+        with pytest.raises(pa.ArrowIndexError) as want:
+            pc.take(pa.array(range(100), pa.int64()), idx)
+        with pytest.raises(pa.ArrowIndexError) as got:
+            bc.take(v, dev(idx, ctx))
+        assert str(got.value) == str(want.value)
+    # out-of-range index under a null is fine
+    idx = pa.array([1, 1000, 3], pa.int32(), mask=np.array([False, True, False]))
+    assert_equal(bc.take(v, dev(idx, ctx)).to_arrow(), pc.take(pa.array(range(100), pa.int64()), idx))
+
+
+@pytest.mark.parametrize("src", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("dst", NUMERIC_TYPES, ids=str)
+def test_cast_random(ctx, src, dst):
+    if src == dst:
+        return
+    for n, off in ((500, 1), (20000, 0), (4099, 7)):
+        v = random_array(src, n, 0.1, SEED, lo=0, hi=100, offset=off)
+        assert_equal(bc.cast(dev(v, ctx), dst, safe=False).to_arrow(), pc.cast(v, dst, safe=False), f"{src}->{dst}")
+        if pa.types.is_floating(src) and pa.types.is_integer(dst):
+            v = pc.round(v)
+        got = bc.cast(dev(v, ctx), dst).to_arrow()
+        assert_equal(got, pc.cast(v, dst))
+        assert_equal(got, ora.cast_array(v, dst))
+    # full-range inputs: wrap when unsafe / identical error text when safe
+    wide = random_array(src, 3000, 0.1, SEED + 1)
+    if pa.types.is_integer(src) or pa.types.is_floating(dst):
+        assert_equal(bc.cast(dev(wide, ctx), dst, safe=False).to_arrow(), pc.cast(wide, dst, safe=False))
+    try:
+        want = pc.cast(wide, dst)
+    except pa.ArrowInvalid as e:
+        with pytest.raises(pa.ArrowInvalid) as got:
+            bc.cast(dev(wide, ctx), dst)
+        assert str(got.value) == str(e), f"{src}->{dst}"
+    else:
+        assert_equal(bc.cast(dev(wide, ctx), dst).to_arrow(), want)
+
+
+def test_cast_float_edge_values(ctx):
+    # denormals, +-0, inf, nan, round-to-nearest-even ties: f64 -> f32 must be bit-exact
+    vals = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 1e-40, -1e-46, 3.4028235e38, 3.4028236e38, 1e39,
+                     1.0 + 2**-24, 1.0 + 2**-23 + 2**-24, 16777217.0, 0.1, 1 / 3], dtype=np.float64)
+    v = pa.array(vals, pa.float64())
+    got = bc.cast(dev(v, ctx), pa.float32(), safe=False).to_arrow()
+    want = pc.cast(v, pa.float32(), safe=False)
+    assert got.buffers()[1].to_pybytes()[:4 * len(vals)] == want.buffers()[1].to_pybytes()[:4 * len(vals)]
+    # float -> int truncation errors: same first offending value, same text
+    for dst in (pa.int32(), pa.uint8(), pa.int64()):
+        x = pa.array([1.0, 2.0, 3.5, 4.5], pa.float64())
+        with pytest.raises(pa.ArrowInvalid) as want_e:
+            pc.cast(x, dst)
+        with pytest.raises(pa.ArrowInvalid) as got_e:
+            bc.cast(dev(x, ctx), dst)
+        assert str(got_e.value) == str(want_e.value)
+
+
+ARITH = ["add", "subtract", "multiply", "divide", "add_checked", "subtract_checked", "multiply_checked", "divide_checked"]
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("op", ARITH)
+def test_arithmetic_random(ctx, t, op):
+    small = dict(lo=1, hi=11) if pa.types.is_integer(t) else dict(lo=-100, hi=100)
+    cases = [(random_array(t, 300, 0.1, SEED, offset=1, **small), random_array(t, 300, 0.1, SEED + 1, offset=2, **small)),
+             (random_array(t, 40000, 0.1, SEED + 4, **small), random_array(t, 40000, 0.0, SEED + 5, **small))]
+    if not op.endswith("_checked") and "divide" not in op:
+        cases.append((random_array(t, 5000, 0.1, SEED + 2), random_array(t, 5000, 0.0, SEED + 3)))  # wraps
+    for a, b in cases:
+        da, db = dev(a, ctx), dev(b, ctx)
+        try:
+            want = getattr(pc, op)(a, b)
+        except pa.ArrowInvalid as e:
+            with pytest.raises(pa.ArrowInvalid) as got:
+                getattr(bc, op)(da, db)
+            assert str(got.value) == str(e)
+            continue
+        got = getattr(bc, op)(da, db)
+        assert equal_nan(got.to_arrow(), want), f"{t} {op}"
+        assert got.null_count == want.null_count
+        assert equal_nan(getattr(bc, op)(da, b[0]).to_arrow(), getattr(pc, op)(a, b[0]))   # ArrayScalar
+        assert equal_nan(getattr(bc, op)(a[0], db).to_arrow(), getattr(pc, op)(a[0], b))   # ScalarArray
+        assert equal_nan(getattr(bc, op)(da, pa.scalar(None, t)).to_arrow(), getattr(pc, op)(a, pa.scalar(None, t)))
+
+
+def test_arithmetic_float_bit_exact(ctx):
+    rng = np.random.default_rng(SEED)
+    for t, dt in ((pa.float32(), np.float32), (pa.float64(), np.float64)):
+        a = rng.standard_normal(100000).astype(dt) * dt(1e-20)
+        b = rng.standard_normal(100000).astype(dt) * dt(1e20)
+        a[:5] = [np.inf, -np.inf, np.nan, 0.0, -0.0]
+        b[:5] = [-np.inf, 1.0, 1.0, -0.0, 0.0]
+        tiny = np.finfo(dt).tiny
+        a[5:8] = [tiny, tiny / 2, -tiny / 4]   # denormal results must not be flushed
+        b[5:8] = [-tiny / 2, tiny / 4, tiny / 8]
+        for op in ("add", "subtract", "multiply", "divide"):
+            got = getattr(bc, op)(dev(pa.array(a, t), ctx), dev(pa.array(b, t), ctx)).to_arrow()
+            want = getattr(pc, op)(pa.array(a, t), pa.array(b, t))
+            nb = np.dtype(dt).itemsize * len(a)
+            assert got.buffers()[1].to_pybytes()[:nb] == want.buffers()[1].to_pybytes()[:nb], f"{t} {op}"
+
+
+def test_arithmetic_errors(ctx):
+    for t in INT_TYPES:
+        info = np.iinfo(t.to_pandas_dtype())
+        a = pa.array([1, info.max, 1], t)
+        for op, b in (("add_checked", [1, 2, 1]), ("multiply_checked", [1, 2, 1]), ("divide", [1, 0, 1]),
+                      ("divide_checked", [1, 0, 1])):
+            with pytest.raises(pa.ArrowInvalid) as want:
+                getattr(pc, op)(a, pa.array(b, t))
+            with pytest.raises(pa.ArrowInvalid) as got:
+                getattr(bc, op)(dev(a, ctx), dev(pa.array(b, t), ctx))
+            assert str(got.value) == str(want.value), f"{t} {op}"
+        z = pa.array([0, 1, 1], t, mask=np.array([True, False, False]))
+        assert_equal(bc.divide(dev(a, ctx), dev(z, ctx)).to_arrow(), pc.divide(a, z))
+        assert_equal(bc.add_checked(dev(pa.array([info.max, 1, 2], t, mask=np.array([True, False, False])), ctx),
+                                    dev(pa.array([5, 1, 2], t), ctx)).to_arrow(),
+                     pc.add_checked(pa.array([info.max, 1, 2], t, mask=np.array([True, False, False])), pa.array([5, 1, 2], t)))
+    m = pa.array([-128, 5], pa.int8())
+    assert_equal(bc.divide(dev(m, ctx), dev(pa.array([-1, 2], pa.int8()), ctx)).to_arrow(), pc.divide(m, pa.array([-1, 2], pa.int8())))
+    with pytest.raises(pa.ArrowInvalid, match="overflow"):
+        bc.divide_checked(dev(m, ctx), dev(pa.array([-1, 2], pa.int8()), ctx))
+    with pytest.raises(pa.ArrowInvalid, match="divide by zero"):
+        bc.divide_checked(dev(pa.array([1.0]), ctx), dev(pa.array([0.0]), ctx))
+    with pytest.raises(pa.ArrowInvalid, match="same length"):
+        bc.add(dev(pa.array([1, 2]), ctx), dev(pa.array([1]), ctx))
+
+
+def test_mixed_type_dispatch(ctx):
+    pairs = [(pa.int8(), pa.uint8()), (pa.int32(), pa.uint32()), (pa.uint64(), pa.int8()), (pa.int64(), pa.float32()),
+             (pa.uint16(), pa.float64()), (pa.int16(), pa.int64())]
+    for ta, tb in pairs:
+        a, b = random_array(ta, 1000, 0.1, SEED, lo=0, hi=50), random_array(tb, 1000, 0.1, SEED + 9, lo=0, hi=50)
+        assert_equal(bc.add(dev(a, ctx), dev(b, ctx)).to_arrow(), pc.add(a, b), f"{ta}+{tb}")
+        assert_equal(bc.less(dev(a, ctx), dev(b, ctx)).to_arrow(), pc.less(a, b), f"{ta}<{tb}")
+    a = random_array(pa.int32(), 100, 0.1, SEED)
+    assert_equal(bc.add(dev(a, ctx), 1.5).to_arrow(), pc.add(a, 1.5))
+    assert_equal(bc.call_function("multiply", [dev(a, ctx), 3]).to_arrow(), pc.multiply(a, 3))
+    with pytest.raises(pa.ArrowKeyError):
+        bc.call_function("no_such_function", [dev(a, ctx)])
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_compare_random(ctx, t):
+    for n, o1, o2 in ((777, 3, 5), (100000, 0, 0), (4096, 1, 0)):
+        a = random_array(t, n, 0.1, SEED, lo=0, hi=20, offset=o1)
+        b = random_array(t, n, 0.1, SEED + 1, lo=0, hi=20, offset=o2)
+        if pa.types.is_floating(t):
+            x = a.to_numpy(zero_copy_only=False).copy()
+            x[::13] = np.nan
+            a = pa.array(x, t, mask=~ora.validity(a))
+        for op in ("equal", "not_equal", "greater", "greater_equal", "less", "less_equal"):
+            got = getattr(bc, op)(dev(a, ctx), dev(b, ctx))
+            assert_equal(got.to_arrow(), getattr(pc, op)(a, b), f"{t} {op}")
+            assert_equal(got.to_arrow(), ora.compare(op, a, b))
+            assert_equal(getattr(bc, op)(dev(a, ctx), b[1]).to_arrow(), getattr(pc, op)(a, b[1]))
+            assert_equal(getattr(bc, op)(a[2], dev(b, ctx)).to_arrow(), getattr(pc, op)(a[2], b))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("null_p", [0.0, 0.1, 0.5, 1.0])
+def test_sort_random(ctx, t, null_p):
+    # ValidateSorted-style random test (vector_sort_test.cc:972-1061) against both oracles
+    for i, (n, rng) in enumerate([(100, dict()), (1000, dict(lo=0, hi=10)), (50000, dict()), (50000, dict(lo=0, hi=300))]):
+        v = random_array(t, n, null_p, SEED + i, offset=i % 3, **rng)
+        if pa.types.is_floating(t):
+            a = v.to_numpy(zero_copy_only=False).copy()
+            a[::17] = np.nan
+            a[5::31] = -0.0
+            a[7::31] = 0.0
+            a[11::97] = np.inf
+            a[13::97] = -np.inf
+            v = pa.array(a, t, mask=~ora.validity(v))
+        dv = dev(v, ctx)
+        for order in ("ascending", "descending"):
+            for np_ in ("at_end", "at_start"):
+                got = bc.array_sort_indices(dv, order, np_).to_arrow()
+                assert_equal(got, ora.sort_indices(v, order, np_), f"{t} {order} {np_} n={n}")
+                assert_equal(got, pc.array_sort_indices(v, order=order, null_placement=np_))
+
+
+def test_grouper_random(ctx):
+    # TestGrouper::ValidateConsume (row/grouper_test.cc:736-760): Take(uniques, ids) == keys, uniques prefix-stable
+    for kt in (pa.int64(), pa.int32(), pa.uint8(), pa.float64()):
+        g = bc.Grouper([kt], ctx)
+        og = ora.Grouper([kt])
+        prev = None
+        for b in range(4):
+            keys = random_array(kt, 3000, 0.05, SEED + b, lo=0, hi=40 * (b + 1))
+            ids = g.consume(dev(keys, ctx)).to_arrow()
+            assert_equal(ids, og.consume(keys), f"{kt} batch {b}")   # first-occurrence order == oracle
+            uniq = g.get_uniques()[0].to_arrow()
+            assert g.num_groups == og.num_groups == len(uniq)
+            assert pc.take(uniq, ids).equals(keys)
+            if prev is not None:
+                assert uniq.slice(0, len(prev)).equals(prev)
+            prev = uniq
+        look = random_array(kt, 500, 0.05, SEED + 99, lo=0, hi=400)
+        assert_equal(g.lookup(dev(look, ctx)).to_arrow(), og.lookup(look))
+    # multi-column keys with nulls
+    g = bc.Grouper([pa.int32(), pa.int16()], ctx)
+    og = ora.Grouper([pa.int32(), pa.int16()])
+    k0, k1 = random_array(pa.int32(), 5000, 0.1, SEED, lo=0, hi=9), random_array(pa.int16(), 5000, 0.1, SEED + 1, lo=-3, hi=3)
+    assert_equal(g.consume([dev(k0, ctx), dev(k1, ctx)]).to_arrow(), og.consume([k0, k1]))
+    for got, want in zip(g.get_uniques(), og.get_uniques()):
+        assert_equal(got.to_arrow(), want)
+    # high-cardinality batch forces table growth
+    g = bc.Grouper([pa.int64()], ctx)
+    keys = pa.array(np.random.default_rng(SEED).permutation(300000), pa.int64())
+    ids = g.consume(dev(keys, ctx)).to_arrow()
+    assert ids.to_numpy().tolist() == list(range(300000)) and g.num_groups == 300000
+
+
+@pytest.mark.parametrize("vt", [pa.int64(), pa.int32(), pa.uint16(), pa.uint64(), pa.float64(), pa.float32()], ids=str)
+def test_hash_aggregates_random(ctx, vt):
+    n = 20000
+    keys = random_array(pa.int64(), n, 0.05, SEED, lo=0, hi=300)
+    vals = random_array(vt, n, 0.1, SEED + 3, lo=-100 if not pa.types.is_unsigned_integer(vt) else 0, hi=100)
+    aggs = [("hash_sum", None), ("hash_count", None), ("hash_count", {"mode": "only_null"}), ("hash_count", {"mode": "all"}),
+            ("hash_mean", None), ("hash_min", None), ("hash_max", None), ("hash_sum", {"skip_nulls": False}),
+            ("hash_sum", {"min_count": 60})]
+    dk, dvv = dev(keys, ctx), dev(vals, ctx)
+    uniq, outs = bc.group_by([dk], [(fn, dvv, o) for fn, o in aggs] + [("hash_count_all", None, None)])
+    ouniq, oouts = ora.group_by([keys], [(fn, vals, o) for fn, o in aggs] + [("hash_count_all", None, None)])
+    assert_equal(uniq[0].to_arrow(), ouniq[0])
+    for (fn, o), got, want in zip(aggs + [("hash_count_all", None)], outs, oouts):
+        got = got.to_arrow()
+        if pa.types.is_floating(got.type) and fn in ("hash_sum", "hash_mean"):
+            assert got.is_valid().equals(want.is_valid())
+            np.testing.assert_allclose(got.fill_null(0).to_numpy(), want.fill_null(0).to_numpy(), rtol=1e-9, atol=1e-9)
+        else:
+            assert_equal(got, want, f"{vt} {fn} {o}")
+    # against the reference engine (Acero), sorted by key as its own tests do
+    import pyarrow.acero  # noqa: F401
+    ref = pa.table({"k": keys, "v": vals}).group_by("k", use_threads=False).aggregate([("v", "sum"), ("v", "count")]).sort_by("k")
+    mine = pa.table({"k": uniq[0].to_arrow(), "v_sum": outs[0].to_arrow(), "v_count": outs[1].to_arrow()}).sort_by("k")
+    assert mine["k"].combine_chunks().equals(ref["k"].combine_chunks())
+    assert mine["v_count"].combine_chunks().equals(ref["v_count"].combine_chunks())
+    if pa.types.is_integer(vt):
+        assert mine["v_sum"].combine_chunks().equals(ref["v_sum"].combine_chunks())
+    # fused group-by == grouper + aggregators
+    f = bc.GroupBySumCount(pa.int64(), vt, ctx=ctx)
+    half = n // 2
+    f.consume(dk.slice(0, half), dvv.slice(0, half))
+    f.consume(dk.slice(half), dvv.slice(half))
+    fk, fs, fc = [x.to_arrow() for x in f.finalize()]
+    fused = pa.table({"k": fk, "v_sum": fs, "v_count": fc}).sort_by("k")
+    assert fused["k"].combine_chunks().equals(ref["k"].combine_chunks())
+    assert fused["v_count"].combine_chunks().equals(ref["v_count"].combine_chunks())
+    if pa.types.is_integer(vt):
+        assert fused["v_sum"].combine_chunks().equals(ref["v_sum"].combine_chunks())
+    else:
+        np.testing.assert_allclose(fused["v_sum"].combine_chunks().fill_null(0).to_numpy(),
+                                   ref["v_sum"].combine_chunks().fill_null(0).to_numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_hash_aggregate_merge(ctx):
+    # GroupByNode::Merge (acero/groupby_aggregate_node.cc:255-298): consume uniques -> transposition -> merge
+    n = 8000
+    keys = random_array(pa.int64(), n, 0.05, SEED, lo=0, hi=200)
+    vals = random_array(pa.int64(), n, 0.1, SEED + 3, lo=-100, hi=100)
+    half = n // 2
+    states = []
+    for sl in (slice(0, half), slice(half, n)):
+        k, v = keys.slice(sl.start, sl.stop - sl.start), vals.slice(sl.start, sl.stop - sl.start)
+        g = bc.Grouper([pa.int64()], ctx)
+        ids = g.consume(dev(k, ctx))
+        aggs = [bc.HashAggregator(fn, pa.int64(), ctx=ctx) for fn in ("hash_sum", "hash_count", "hash_min", "hash_max")]
+        for a in aggs:
+            a.resize(g.num_groups)
+            a.consume(dev(v, ctx), ids)
+        states.append((g, aggs))
+    (g0, a0), (g1, a1) = states
+    mapping = g0.consume(g1.get_uniques())
+    for x, y in zip(a0, a1):
+        x.resize(g0.num_groups)
+        x.merge(y, mapping)
+    uniq = g0.get_uniques()[0].to_arrow()
+    ouniq, oouts = ora.group_by([keys], [(fn, vals, None) for fn in ("hash_sum", "hash_count", "hash_min", "hash_max")])
+    assert_equal(uniq, ouniq[0])
+    for a, want in zip(a0, oouts):
+        assert_equal(a.finalize().to_arrow(), want)
+
+
+def test_large_filter_take_sort_properties(ctx):
+    """BASELINE-sized shapes are checked through size-independent properties (16M rows here so the
+    default suite stays in minutes; bench.py runs the 1B-row configuration)."""
+    n = 1 << 24
+    rng = np.random.default_rng(SEED)
+    vals = pa.array(rng.integers(-100, 100, n, dtype=np.int64), pa.int64(), mask=rng.random(n) < 0.1)
+    mask = pa.array(rng.random(n) < 0.5)
+    dv, dm = dev(vals, ctx), dev(mask, ctx)
+    out = bc.filter(dv, dm)
+    assert len(out) == int(np.count_nonzero(mask.to_numpy(zero_copy_only=False)))
+    assert out.to_arrow().equals(pc.filter(vals, mask))
+    # take(iota) is the identity; take(reversed) reverses
+    iota = dev(pa.array(np.arange(n, dtype=np.int64)), ctx)
+    assert bc.take(dv, iota).to_arrow().equals(vals)
+    # sort: output is a permutation, keys non-decreasing along it, nulls last, ties by index
+    keys = pa.array(rng.integers(-2**62, 2**62, n, dtype=np.int64), pa.int64(), mask=rng.random(n) < 0.1)
+    idx = bc.array_sort_indices(dev(keys, ctx)).to_arrow().to_numpy()
+    assert np.array_equal(np.sort(idx), np.arange(n, dtype=np.uint64))
+    kv = keys.to_numpy(zero_copy_only=False)
+    valid = ora.validity(keys)
+    nv = int(valid.sum())
+    assert valid[idx[:nv]].all() and not valid[idx[nv:]].any()
+    assert np.all(np.diff(idx[nv:].astype(np.int64)) > 0)
+    sk = np.frombuffer(keys.buffers()[1], dtype=np.int64)[idx[:nv].astype(np.int64)]
+    assert np.all(sk[1:] >= sk[:-1])
+    del kv

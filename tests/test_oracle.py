@@ -1,0 +1,250 @@
+"""Pins the oracle (oracle/arrow_oracle.py): (a) the reference's own known-answer vectors
+(tests/golden/kat.json) and (b) the reference binary itself (pyarrow 24.0.0's
+libarrow_compute) on seeded random inputs.  CPU only."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+from oracle import arrow_oracle as ora
+from tests.util import INT_TYPES, NUMERIC_TYPES, SEED, TYPE_BY_NAME, assert_equal, equal_nan, from_json, kat, random_array
+
+KAT = kat()
+
+
+# ---------------------------------------------------------------- (a) known answers
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_kat_filter(t):
+    for c in KAT["filter_numeric_basics"]["cases"]:
+        v, m = from_json(t, c["values"]), from_json(pa.bool_(), c["filter"])
+        assert_equal(ora.filter(v, m, "emit_null"), from_json(t, c["emit_null"]), f"emit_null {c}")
+        assert_equal(ora.filter(v, m, "drop"), from_json(t, c["drop"]), f"drop {c}")
+    with pytest.raises(pa.ArrowInvalid):
+        ora.filter(from_json(t, [7, 8, 9]), from_json(pa.bool_(), []), "drop")
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_kat_take(t):
+    for c in KAT["take_numeric_basics"]["cases"]:
+        for it in (pa.int8(), pa.uint32(), pa.int64()):
+            assert_equal(ora.take(from_json(t, c["values"]), from_json(it, c["indices"])), from_json(t, c["expected"]))
+    for c in KAT["take_numeric_basics"]["index_errors"]:
+        with pytest.raises(pa.ArrowIndexError):
+            ora.take(from_json(t, c["values"]), from_json(pa.int8(), c["indices"]))
+
+
+@pytest.mark.parametrize("t", INT_TYPES, ids=str)
+def test_kat_sort_integral(t):
+    for c in KAT["sort_integral"]["cases"]:
+        got = ora.sort_indices(from_json(t, c["values"]), c["order"], c["null_placement"])
+        assert_equal(got, pa.array(c["expected"], pa.uint64()), str(c))
+    if t == pa.int64():
+        for c in KAT["sort_integral"]["int64_cases"]:
+            got = ora.sort_indices(from_json(t, c["values"]), c["order"], c["null_placement"])
+            assert_equal(got, pa.array(c["expected"], pa.uint64()), str(c))
+
+
+@pytest.mark.parametrize("t", [pa.float32(), pa.float64()], ids=str)
+def test_kat_sort_real(t):
+    for c in KAT["sort_real"]["cases"]:
+        got = ora.sort_indices(from_json(t, c["values"]), c["order"], c["null_placement"])
+        assert_equal(got, pa.array(c["expected"], pa.uint64()), str(c))
+
+
+def test_kat_cast():
+    for c in KAT["cast_float_to_float"]["cases"]:
+        assert_equal(ora.cast_array(from_json(TYPE_BY_NAME[c["from"]], c["values"]), TYPE_BY_NAME[c["to"]]),
+                     from_json(TYPE_BY_NAME[c["to"]], c["expected"]))
+    for c in KAT["cast_int_to_float_bounds"]["ok"]:
+        ora.cast_array(from_json(TYPE_BY_NAME[c["from"]], c["values"]), TYPE_BY_NAME[c["to"]])
+    for c in KAT["cast_int_to_float_bounds"]["fails"]:
+        with pytest.raises(pa.ArrowInvalid):
+            ora.cast_array(from_json(TYPE_BY_NAME[c["from"]], c["values"]), TYPE_BY_NAME[c["to"]])
+    c = KAT["cast_overflow_in_null_slot"]
+    v = pa.array(c["values"], TYPE_BY_NAME[c["from"]], mask=~np.array(c["validity"], dtype=bool))
+    assert_equal(ora.cast_array(v, TYPE_BY_NAME[c["to"]]), from_json(TYPE_BY_NAME[c["to"]], c["expected"]))
+
+
+def _sorted_by_key(keys: pa.Array, cols):
+    order = pc.sort_indices(keys, null_placement="at_end")
+    return [pc.take(c, order) for c in [keys] + list(cols)]
+
+
+def test_kat_group_by():
+    c = KAT["group_by_count_only"]
+    arg = pa.array([r[0] for r in c["rows"]], pa.float64())
+    key = pa.array([r[1] for r in c["rows"]], pa.int64())
+    for mode in ("only_valid", "only_null", "all"):
+        uniq, (cnt,) = ora.group_by([key], [("hash_count", arg, {"mode": mode})])
+        k, v = _sorted_by_key(uniq[0], [cnt])
+        assert k.to_pylist() == [r[0] for r in c[mode]] and v.to_pylist() == [r[1] for r in c[mode]]
+    c = KAT["group_by_sum_only"]
+    arg = pa.array([r[0] for r in c["rows"]], pa.float64())
+    key = pa.array([r[1] for r in c["rows"]], pa.int64())
+    uniq, (s,) = ora.group_by([key], [("hash_sum", arg, None)])
+    k, v = _sorted_by_key(uniq[0], [s])
+    assert k.to_pylist() == [r[0] for r in c["expected"]] and v.to_pylist() == [r[1] for r in c["expected"]]
+    c = KAT["grouper_int64"]
+    g = ora.Grouper([pa.int64()])
+    assert g.consume(pa.array(c["keys"], pa.int64())).to_pylist() == c["ids"]
+
+
+# ---------------------------------------------------------------- (b) the reference binary
+NULL_PROBS = [0.0, 0.1, 0.999]
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("null_p", NULL_PROBS)
+def test_filter_vs_reference(t, null_p):
+    for i, (true_p, mask_null, off) in enumerate([(0.5, 0.0, 0), (0.1, 0.05, 3), (0.999, 0.5, 2)]):
+        v = random_array(t, 1024, null_p, SEED + i, offset=off)
+        m = random_array(pa.bool_(), 1024, mask_null, SEED + 77 + i, hi=true_p, offset=(off * 5) % 7)
+        for ns in ("drop", "emit_null"):
+            assert_equal(ora.filter(v, m, ns), pc.filter(v, m, null_selection_behavior=ns), f"{t} {ns}")
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("it", [pa.int8(), pa.uint16(), pa.int32(), pa.uint32(), pa.int64(), pa.uint64()], ids=str)
+def test_take_vs_reference(t, it):
+    for null_p in (0.0, 0.05, 0.95):
+        v = random_array(t, 1025, null_p, SEED, offset=1)
+        hi = min(1024, np.iinfo(it.to_pandas_dtype()).max)
+        idx = random_array(it, 257, null_p, SEED + 5, lo=0, hi=hi, offset=3)
+        assert_equal(ora.take(v, idx), pc.take(v, idx), f"{t} {it} {null_p}")
+
+
+@pytest.mark.parametrize("src", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("dst", NUMERIC_TYPES, ids=str)
+def test_cast_vs_reference(src, dst):
+    if src == dst:
+        return
+    v = random_array(src, 500, 0.1, SEED, lo=0, hi=100, offset=1)  # in range for every target
+    assert_equal(ora.cast_array(v, dst, safe=False), pc.cast(v, dst, safe=False), f"{src}->{dst}")
+    if pa.types.is_floating(src) and pa.types.is_integer(dst):
+        w = pc.round(v)
+        assert_equal(ora.cast_array(w, dst, safe=True), pc.cast(w, dst, safe=True))
+        with pytest.raises(pa.ArrowInvalid):
+            ora.cast_array(pa.array([1.5], src), dst, safe=True)
+        with pytest.raises(pa.ArrowInvalid):
+            pc.cast(pa.array([1.5], src), dst, safe=True)
+    else:
+        assert_equal(ora.cast_array(v, dst, safe=True), pc.cast(v, dst, safe=True))
+    # wide-range input: wraps when unsafe, errors (both sides) when safe and out of range
+    wide = random_array(src, 300, 0.1, SEED + 1)
+    if pa.types.is_integer(src) and pa.types.is_integer(dst):
+        assert_equal(ora.cast_array(wide, dst, safe=False), pc.cast(wide, dst, safe=False))
+        try:
+            want = pc.cast(wide, dst, safe=True)
+        except pa.ArrowInvalid as e:
+            with pytest.raises(pa.ArrowInvalid) as ei:
+                ora.cast_array(wide, dst, safe=True)
+            assert str(ei.value) == str(e)
+        else:
+            assert_equal(ora.cast_array(wide, dst, safe=True), want)
+
+
+ARITH = ["add", "subtract", "multiply", "add_checked", "subtract_checked", "multiply_checked", "divide", "divide_checked"]
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("op", ARITH)
+def test_arithmetic_vs_reference(t, op):
+    small = dict(lo=1, hi=11) if pa.types.is_integer(t) else dict(lo=-100, hi=100)
+    cases = [(random_array(t, 300, 0.1, SEED, offset=1, **small), random_array(t, 300, 0.1, SEED + 1, offset=2, **small))]
+    if not op.endswith("_checked") and "divide" not in op:
+        cases.append((random_array(t, 300, 0.1, SEED + 2), random_array(t, 300, 0.0, SEED + 3)))  # wraps
+    for a, b in cases:
+        try:
+            want = getattr(pc, op)(a, b)
+        except pa.ArrowInvalid as e:  # e.g. unsigned subtract_checked underflow: same error both sides
+            with pytest.raises(pa.ArrowInvalid) as ei:
+                ora.arithmetic(op, a, b)
+            assert str(ei.value) == str(e)
+            continue
+        got = ora.arithmetic(op, a, b)
+        assert equal_nan(got, want), f"{t} {op}"
+        assert equal_nan(ora.arithmetic(op, a, b[0]), getattr(pc, op)(a, b[0]))
+        assert equal_nan(ora.arithmetic(op, a[0], b), getattr(pc, op)(a[0], b))
+
+
+def test_arithmetic_errors_vs_reference():
+    for t in INT_TYPES:
+        info = np.iinfo(t.to_pandas_dtype())
+        a = pa.array([info.max, 1], t)
+        for op in ("add_checked", "multiply_checked"):
+            with pytest.raises(pa.ArrowInvalid, match="overflow"):
+                getattr(pc, op)(a, pa.array([2, 1], t))
+            with pytest.raises(pa.ArrowInvalid, match="overflow"):
+                ora.arithmetic(op, a, pa.array([2, 1], t))
+        for op in ("divide", "divide_checked"):
+            with pytest.raises(pa.ArrowInvalid, match="divide by zero"):
+                getattr(pc, op)(a, pa.array([0, 1], t))
+            with pytest.raises(pa.ArrowInvalid, match="divide by zero"):
+                ora.arithmetic(op, a, pa.array([0, 1], t))
+        # errors under nulls are ignored
+        z = pa.array([0, 1], t, mask=np.array([True, False]))
+        assert_equal(ora.arithmetic("divide", a, z), pc.divide(a, z))
+    assert_equal(ora.arithmetic("divide", pa.array([-128], pa.int8()), pa.array([-1], pa.int8())),
+                 pc.divide(pa.array([-128], pa.int8()), pa.array([-1], pa.int8())))
+
+
+def test_mixed_type_dispatch_vs_reference():
+    pairs = [(pa.int8(), pa.uint8()), (pa.int32(), pa.uint32()), (pa.uint64(), pa.int8()), (pa.int64(), pa.float32()),
+             (pa.uint16(), pa.float64()), (pa.int16(), pa.int64())]
+    for ta, tb in pairs:
+        a, b = random_array(ta, 100, 0.1, SEED, lo=0, hi=50), random_array(tb, 100, 0.1, SEED + 9, lo=0, hi=50)
+        assert_equal(ora.arithmetic("add", a, b), pc.add(a, b), f"{ta}+{tb}")
+        assert_equal(ora.compare("less", a, b), pc.less(a, b), f"{ta}<{tb}")
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_compare_vs_reference(t):
+    a = random_array(t, 777, 0.1, SEED, lo=0, hi=20, offset=3)
+    b = random_array(t, 777, 0.1, SEED + 1, lo=0, hi=20, offset=5)
+    for op in ("equal", "not_equal", "greater", "greater_equal", "less", "less_equal"):
+        assert_equal(ora.compare(op, a, b), getattr(pc, op)(a, b), f"{t} {op}")
+        assert_equal(ora.compare(op, a, b[1]), getattr(pc, op)(a, b[1]))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+@pytest.mark.parametrize("null_p", [0.0, 0.1, 0.5, 1.0])
+def test_sort_vs_reference(t, null_p):
+    for i, rng in enumerate([dict(), dict(lo=0, hi=10)]):
+        v = random_array(t, 1000, null_p, SEED + i, offset=i, **rng)
+        if pa.types.is_floating(t):
+            a = v.to_numpy(zero_copy_only=False).copy()
+            a[::17] = np.nan
+            a[5::31] = -0.0
+            a[7::31] = 0.0
+            v = pa.array(a, t, mask=~ora.validity(v))
+        for order in ("ascending", "descending"):
+            for np_ in ("at_end", "at_start"):
+                want = pc.array_sort_indices(v, order=order, null_placement=np_)
+                assert_equal(ora.sort_indices(v, order, np_), want, f"{t} {order} {np_}")
+
+
+def test_grouper_and_aggregates_vs_reference():
+    import pyarrow.acero  # noqa: F401
+    n = 5000
+    keys = random_array(pa.int64(), n, 0.05, SEED, lo=0, hi=300)
+    for vt in (pa.int64(), pa.int32(), pa.uint16(), pa.float64(), pa.float32()):
+        vals = random_array(vt, n, 0.1, SEED + 3, lo=-100 if not pa.types.is_unsigned_integer(vt) else 0, hi=100)
+        tbl = pa.table({"k": keys, "v": vals})
+        want = tbl.group_by("k", use_threads=False).aggregate(
+            [("v", "sum"), ("v", "count"), ("v", "mean"), ("v", "min"), ("v", "max"), ([], "count_all")])
+        uniq, outs = ora.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None), ("hash_mean", vals, None),
+                                           ("hash_min", vals, None), ("hash_max", vals, None), ("hash_count_all", None, None)])
+        got = pa.table({"k": uniq[0], "v_sum": outs[0], "v_count": outs[1], "v_mean": outs[2], "v_min": outs[3],
+                        "v_max": outs[4], "count_all": outs[5]}).sort_by("k")
+        want = want.sort_by("k").select(got.column_names)
+        for name in got.column_names:
+            g, w = got[name].combine_chunks(), want[name].combine_chunks()
+            if pa.types.is_floating(g.type) and name in ("v_sum", "v_mean"):
+                assert g.is_valid().equals(w.is_valid())
+                np.testing.assert_allclose(g.fill_null(0).to_numpy(), w.fill_null(0).to_numpy(), rtol=1e-9)
+            else:
+                assert_equal(g, w, f"{vt} {name}")
+    # ids: first-occurrence order == the reference Grouper on this (single-batch) input
+    g = ora.Grouper([pa.int64()])
+    ids = g.consume(keys)
+    assert pc.take(g.get_uniques()[0], ids).equals(keys)
