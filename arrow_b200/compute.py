@@ -86,7 +86,7 @@ def _scalar_to(s: pa.Scalar, tid: int) -> cabi.B2Scalar:
         if np.issubdtype(dt, np.integer):
             if isinstance(v, float):
                 if v != int(v):
-                    raise pa.ArrowInvalid(f"Float value {v:g} was truncated converting to {arrow_type(tid)}")
+                    raise pa.ArrowInvalid(f"Float value {v:f} was truncated converting to {arrow_type(tid)}")
                 v = int(v)
             info = np.iinfo(dt)
             if not (info.min <= int(v) <= info.max):

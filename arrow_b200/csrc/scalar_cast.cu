@@ -27,10 +27,10 @@ namespace b2 {
 // We reproduce that so `safe=false` casts agree bit-for-bit on the same inputs.
 template <typename F>
 __device__ __forceinline__ int32_t x86_cvtt32(F x) {
-  return (x > static_cast<F>(-2147483904.0) && x < static_cast<F>(2147483648.0) &&
-          static_cast<double>(x) > -2147483649.0)
-             ? static_cast<int32_t>(x)
-             : std::numeric_limits<int32_t>::min();
+  // fits iff trunc(x) is in [-2^31, 2^31): compare in double so -2147483648.9 still fits
+  const double d = static_cast<double>(x);
+  return (d > -2147483649.0 && d < 2147483648.0) ? static_cast<int32_t>(x)
+                                                 : std::numeric_limits<int32_t>::min();
 }
 template <typename F>
 __device__ __forceinline__ int64_t x86_cvtt64(F x) {
@@ -137,8 +137,8 @@ const char* type_name(int t) {
 template <typename T>
 static std::string to_chars(T v) {
   if constexpr (std::is_floating_point<T>::value) {
-    char b[64];
-    snprintf(b, sizeof(b), "%g", static_cast<double>(v));  // operator<< default formatting
+    char b[512];
+    snprintf(b, sizeof(b), "%f", static_cast<double>(v));  // the reference formats with std::to_string
     return b;
   } else if constexpr (std::is_signed<T>::value) {
     return std::to_string(static_cast<long long>(v));

@@ -207,7 +207,7 @@ def cast(arr: pa.Array, to: pa.DataType, safe: bool = True) -> pa.Array:
                 bad = valid & (~inr | (out.astype(src) != v))
                 if bad.any():
                     x = v[np.nonzero(bad)[0][0]]
-                    raise pa.ArrowInvalid(f"Float value {x:g} was truncated converting to {to}")
+                    raise pa.ArrowInvalid(f"Float value {x:f} was truncated converting to {to}")
             return make_array(to, out, valid), (inr | ~valid)
         out = v.astype(dst)
     if safe and si and di:

@@ -248,3 +248,36 @@ def test_grouper_and_aggregates_vs_reference():
     g = ora.Grouper([pa.int64()])
     ids = g.consume(keys)
     assert pc.take(g.get_uniques()[0], ids).equals(keys)
+
+
+STRING_TYPES = [pa.string(), pa.large_string(), pa.binary(), pa.large_binary()]
+
+
+@pytest.mark.parametrize("t", STRING_TYPES, ids=str)
+def test_binary_filter_take_vs_reference(t):
+    # string KATs of vector_selection_test.cc:670-698 / 1661-1676 shape + random (0-32 byte strings)
+    v = pa.array(["a", "b", "c"], pa.string()).cast(t)
+    assert_equal(ora.filter(v, pa.array([False, True, False])), v.slice(1, 1))
+    m = pa.array([None, True, False])
+    assert_equal(ora.filter(v, m, "emit_null"), pc.filter(v, m, null_selection_behavior="emit_null"))
+    assert_equal(ora.take(v, pa.array([2, None, 0, 0], pa.int8())), pc.take(v, pa.array([2, None, 0, 0], pa.int8())))
+    for null_p in (0.0, 0.1, 0.9):
+        vals = random_array(t, 1500, null_p, SEED, offset=3)
+        mask = random_array(pa.bool_(), 1500, 0.05, SEED + 1, hi=0.5, offset=2)
+        for ns in ("drop", "emit_null"):
+            assert_equal(ora.filter(vals, mask, ns), pc.filter(vals, mask, null_selection_behavior=ns), f"{t} {ns}")
+        idx = random_array(pa.int32(), 700, null_p, SEED + 2, lo=0, hi=1499, offset=1)
+        assert_equal(ora.take(vals, idx), pc.take(vals, idx))
+    with pytest.raises(pa.ArrowIndexError):
+        ora.take(v, pa.array([0, 3], pa.int32()))
+
+
+def test_dictionary_filter_take_vs_reference():
+    # TakeDictionary / FilterDictionary (vector_selection_test.cc:1678-1683): indices move, dictionary passes through
+    d = pa.DictionaryArray.from_arrays(random_array(pa.int32(), 2000, 0.1, SEED, lo=0, hi=9),
+                                       pa.array([f"v{i}" for i in range(10)]))
+    mask = random_array(pa.bool_(), 2000, 0.05, SEED + 1, hi=0.5)
+    for ns in ("drop", "emit_null"):
+        assert_equal(ora.filter(d, mask, ns), pc.filter(d, mask, null_selection_behavior=ns))
+    idx = random_array(pa.int64(), 500, 0.1, SEED + 2, lo=0, hi=1999)
+    assert_equal(ora.take(d, idx), pc.take(d, idx))
