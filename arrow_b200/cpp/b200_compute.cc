@@ -1,0 +1,634 @@
+// b200_compute.cc -- kernel trampolines and function registration (see b200_compute.h).
+//
+// Every trampoline has the reference's kernel entry signature
+//   Status exec(KernelContext*, const ExecSpan&, ExecResult*)          compute/kernel.h:556
+// and registers with null_handling = COMPUTED_NO_PREALLOCATE and
+// mem_allocation = NO_PREALLOCATE, because the stock executor cannot see device bitmaps
+// (ArraySpan::SetBuffer stores Buffer::data() == nullptr for device buffers,
+// array/data.h:578-582, and SetSlice then resets null_count, :680-690): validity is
+// computed on device and null_count is always set explicitly.  Device addresses are read
+// through BufferSpan::owner -> Buffer::address().
+#include "b200_compute.h"
+
+#include <arrow/compute/cast.h>
+#include <arrow/compute/registry.h>
+#include <arrow/util/checked_cast.h>
+
+#include <map>
+#include <mutex>
+
+namespace arrow_b200 {
+
+namespace cp = arrow::compute;
+using arrow::ArrayData;
+using arrow::ArraySpan;
+using arrow::DataType;
+using arrow::Datum;
+using arrow::Result;
+using arrow::Status;
+using arrow::Type;
+using arrow::TypeHolder;
+using arrow::internal::checked_cast;
+
+// ------------------------------------------------------------------------------------------
+// type mapping and (de)marshalling
+// ------------------------------------------------------------------------------------------
+static Result<int> B2TypeId(const DataType& t) {
+  switch (t.id()) {
+    case Type::BOOL: return B2_BOOL;
+    case Type::UINT8: return B2_UINT8;
+    case Type::INT8: return B2_INT8;
+    case Type::UINT16: return B2_UINT16;
+    case Type::INT16: return B2_INT16;
+    case Type::UINT32: return B2_UINT32;
+    case Type::INT32: case Type::DATE32: case Type::TIME32: return B2_INT32;
+    case Type::UINT64: return B2_UINT64;
+    case Type::INT64: case Type::DATE64: case Type::TIME64: case Type::TIMESTAMP: case Type::DURATION: return B2_INT64;
+    case Type::FLOAT: return B2_FLOAT;
+    case Type::DOUBLE: return B2_DOUBLE;
+    case Type::STRING: return B2_STRING;
+    case Type::BINARY: return B2_BINARY;
+    case Type::LARGE_STRING: return B2_LARGE_STRING;
+    case Type::LARGE_BINARY: return B2_LARGE_BINARY;
+    case Type::FIXED_SIZE_BINARY: return B2_FIXED_SIZE_BINARY;
+    case Type::DICTIONARY: return B2TypeId(*checked_cast<const arrow::DictionaryType&>(t).index_type());
+    default: return Status::NotImplemented("arrow_b200: type ", t.ToString(), " is not supported on device");
+  }
+}
+
+static const void* Addr(const arrow::BufferSpan& b) {
+  return b.owner && *b.owner ? reinterpret_cast<const void*>((*b.owner)->address()) : nullptr;
+}
+static const void* Addr(const std::shared_ptr<arrow::Buffer>& b) {
+  return b ? reinterpret_cast<const void*>(b->address()) : nullptr;
+}
+
+Status SpanToB2(const ArraySpan& span, B2Array* out) {
+  ARROW_ASSIGN_OR_RAISE(int tid, B2TypeId(*span.type));
+  out->validity = Addr(span.buffers[0]);
+  out->data = Addr(span.buffers[1]);
+  out->data2 = Addr(span.buffers[2]);
+  out->length = span.length;
+  out->offset = span.offset;
+  // never trust span.null_count for device data (SetSlice resets it): unknown unless no bitmap
+  out->null_count = out->validity ? -1 : 0;
+  out->type = tid;
+  out->byte_width = span.type->id() == Type::FIXED_SIZE_BINARY ? span.type->byte_width() : 0;
+  return Status::OK();
+}
+
+Status DataToB2(const ArrayData& data, B2Array* out) {
+  ARROW_ASSIGN_OR_RAISE(int tid, B2TypeId(*data.type));
+  out->validity = data.buffers.size() > 0 ? Addr(data.buffers[0]) : nullptr;
+  out->data = data.buffers.size() > 1 ? Addr(data.buffers[1]) : nullptr;
+  out->data2 = data.buffers.size() > 2 ? Addr(data.buffers[2]) : nullptr;
+  out->length = data.length;
+  out->offset = data.offset;
+  out->null_count = out->validity ? data.null_count.load() : 0;
+  out->type = tid;
+  out->byte_width = data.type->id() == Type::FIXED_SIZE_BINARY ? data.type->byte_width() : 0;
+  return Status::OK();
+}
+
+static int64_t DataBytes(const B2Array& o) {
+  switch (o.type) {
+    case B2_BOOL: return (o.length + 7) / 8;
+    case B2_STRING: case B2_BINARY: return 4 * (o.length + 1);
+    case B2_LARGE_STRING: case B2_LARGE_BINARY: return 8 * (o.length + 1);
+    case B2_FIXED_SIZE_BINARY: return o.length * o.byte_width;
+    case B2_UINT8: case B2_INT8: return o.length;
+    case B2_UINT16: case B2_INT16: return 2 * o.length;
+    case B2_UINT32: case B2_INT32: case B2_FLOAT: return 4 * o.length;
+    default: return 8 * o.length;
+  }
+}
+
+std::shared_ptr<ArrayData> AdoptOutput(Runtime* rt, const B2Array& o, std::shared_ptr<DataType> type,
+                                       std::shared_ptr<ArrayData> dictionary) {
+  auto out = std::make_shared<ArrayData>(std::move(type), o.length, o.null_count, o.offset);
+  out->buffers.push_back(rt->mm()->Adopt(o.validity, (o.length + 7) / 8));
+  out->buffers.push_back(rt->mm()->Adopt(o.data, DataBytes(o)));
+  const bool binary = o.type == B2_STRING || o.type == B2_BINARY || o.type == B2_LARGE_STRING || o.type == B2_LARGE_BINARY;
+  if (binary) out->buffers.push_back(rt->mm()->Adopt(o.data2, 0));
+  out->dictionary = std::move(dictionary);
+  return out;
+}
+
+static void MoveInto(std::shared_ptr<ArrayData> produced, cp::ExecResult* out) {
+  // keep the ArrayData object the executor handed us (it already carries the output type)
+  ArrayData* dst = out->array_data().get();
+  dst->length = produced->length;
+  dst->null_count = produced->null_count.load();
+  dst->offset = produced->offset;
+  dst->buffers = std::move(produced->buffers);
+  dst->dictionary = std::move(produced->dictionary);
+}
+
+static bool AnyOnDevice(const std::vector<Datum>& args) {
+  for (const auto& a : args) {
+    if (a.is_array() && IsOnDevice(*a.array())) return true;
+    if (a.is_chunked_array())
+      for (const auto& c : a.chunked_array()->chunks())
+        if (IsOnDevice(*c->data())) return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// runtime singleton
+// ------------------------------------------------------------------------------------------
+Result<Runtime*> Runtime::Get(int device) {
+  static std::mutex mu;
+  static std::map<int, std::unique_ptr<Runtime>> instances;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = instances.find(device);
+  if (it != instances.end()) return it->second.get();
+  auto rt = std::unique_ptr<Runtime>(new Runtime());
+  ARROW_ASSIGN_OR_RAISE(rt->device_, B200Device::Make(device));
+  rt->mm_ = rt->device_->default_memory_manager();
+  rt->registry_ = cp::FunctionRegistry::Make(cp::GetFunctionRegistry());
+  ARROW_RETURN_NOT_OK(RegisterFunctions(rt->registry_.get(), rt.get()));
+  Runtime* raw = rt.get();
+  instances[device] = std::move(rt);
+  return raw;
+}
+
+// per-kernel immutable data: which runtime, which op
+struct KernelData : public cp::KernelState {
+  KernelData(Runtime* r, int o) : rt(r), op(o) {}
+  Runtime* rt;
+  int op;
+};
+static const KernelData& DataOf(cp::KernelContext* ctx) { return checked_cast<const KernelData&>(*ctx->kernel()->data); }
+
+template <typename Options>
+struct OptionsState : public cp::KernelState {
+  explicit OptionsState(Options o) : options(std::move(o)) {}
+  Options options;
+  static Result<std::unique_ptr<cp::KernelState>> Init(cp::KernelContext*, const cp::KernelInitArgs& args) {
+    if (auto o = static_cast<const Options*>(args.options)) return std::make_unique<OptionsState>(*o);
+    return std::make_unique<OptionsState>(Options::Defaults());
+  }
+  static const Options& Get(cp::KernelContext* ctx) { return checked_cast<const OptionsState&>(*ctx->state()).options; }
+};
+
+// ------------------------------------------------------------------------------------------
+// a function that forwards host arguments to the parent registry's stock function
+// ------------------------------------------------------------------------------------------
+template <typename Base>
+class Forwarding : public Base {
+ public:
+  using Base::Base;
+  Result<Datum> Execute(const std::vector<Datum>& args, const cp::FunctionOptions* options,
+                        cp::ExecContext* ctx) const override {
+    if (!AnyOnDevice(args)) {
+      ARROW_ASSIGN_OR_RAISE(auto parent, cp::GetFunctionRegistry()->GetFunction(this->name()));
+      cp::ExecContext host_ctx(ctx ? ctx->memory_pool() : arrow::default_memory_pool(), ctx ? ctx->executor() : nullptr,
+                               cp::GetFunctionRegistry());
+      return parent->Execute(args, options, &host_ctx);
+    }
+    return Base::Execute(args, options, ctx);
+  }
+};
+
+static const cp::FunctionDoc kDoc{"B200 device kernel", "Runs on the GPU through libarrow_b200 (see include/arrow_b200.h).", {}};
+static cp::FunctionDoc DocFor(std::vector<std::string> arg_names, const char* options_class = "", bool required = false) {
+  cp::FunctionDoc d = kDoc;
+  d.arg_names = std::move(arg_names);
+  d.options_class = options_class;
+  d.options_required = required;
+  return d;
+}
+
+static const std::vector<std::shared_ptr<DataType>>& NumericTypes() {
+  static std::vector<std::shared_ptr<DataType>> t = {arrow::int8(),  arrow::uint8(),  arrow::int16(),   arrow::uint16(),
+                                                     arrow::int32(), arrow::uint32(), arrow::int64(),   arrow::uint64(),
+                                                     arrow::float32(), arrow::float64()};
+  return t;
+}
+
+// CommonNumeric (compute/kernels/codegen_internal.cc:166-218)
+static std::shared_ptr<DataType> CommonNumeric(const std::vector<TypeHolder>& types) {
+  for (const auto& t : types)
+    if (!arrow::is_floating(t.id()) && !arrow::is_integer(t.id())) return nullptr;
+  for (const auto& t : types)
+    if (t.id() == Type::HALF_FLOAT) return nullptr;
+  for (const auto& t : types)
+    if (t.id() == Type::DOUBLE) return arrow::float64();
+  for (const auto& t : types)
+    if (t.id() == Type::FLOAT) return arrow::float32();
+  int max_s = 0, max_u = 0;
+  for (const auto& t : types) {
+    int& m = arrow::is_signed_integer(t.id()) ? max_s : max_u;
+    m = std::max(arrow::bit_width(t.id()), m);
+  }
+  if (max_s == 0) {
+    if (max_u >= 64) return arrow::uint64();
+    if (max_u == 32) return arrow::uint32();
+    if (max_u == 16) return arrow::uint16();
+    return arrow::uint8();
+  }
+  if (max_s <= max_u) {
+    int v = max_u + 1, p = 1;
+    while (p < v) p <<= 1;
+    max_s = p;
+  }
+  if (max_s >= 64) return arrow::int64();
+  if (max_s == 32) return arrow::int32();
+  if (max_s == 16) return arrow::int16();
+  return arrow::int8();
+}
+
+// ------------------------------------------------------------------------------------------
+// arithmetic + compare (ScalarBinary applicators, codegen_internal.h:813-976)
+// ------------------------------------------------------------------------------------------
+struct BinaryOperand {
+  B2Array array;
+  B2Scalar scalar;
+  B2Value value;
+};
+
+static Status MakeOperand(const cp::ExecValue& v, BinaryOperand* o) {
+  if (v.is_array()) {
+    ARROW_RETURN_NOT_OK(SpanToB2(v.array, &o->array));
+    o->value.array = &o->array;
+    o->value.scalar = nullptr;
+  } else {
+    ARROW_ASSIGN_OR_RAISE(int tid, B2TypeId(*v.scalar->type));
+    o->scalar.type = tid;
+    o->scalar.is_valid = v.scalar->is_valid;
+    o->scalar.bits = 0;
+    if (v.scalar->is_valid) {
+      auto view = checked_cast<const arrow::internal::PrimitiveScalarBase&>(*v.scalar).view();
+      memcpy(&o->scalar.bits, view.data(), std::min<size_t>(8, view.size()));
+    }
+    o->value.array = nullptr;
+    o->value.scalar = &o->scalar;
+  }
+  return Status::OK();
+}
+
+static Status ArithExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  BinaryOperand l, r;
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[0], &l));
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[1], &r));
+  B2Array o;
+  B200_RETURN_NOT_OK(b2_binary_arith(kd.rt->context(), kd.op, &l.value, &r.value, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, out->type()->GetSharedPtr()), out);
+  return Status::OK();
+}
+
+static Status CompareExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  BinaryOperand l, r;
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[0], &l));
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[1], &r));
+  B2Array o;
+  B200_RETURN_NOT_OK(b2_compare(kd.rt->context(), kd.op, &l.value, &r.value, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, arrow::boolean()), out);
+  return Status::OK();
+}
+
+// ArithmeticFunction / CompareFunction dispatch: exact, else promote to CommonNumeric
+// (kernels/scalar_arithmetic.cc:734-781, kernels/scalar_compare.cc:340-366)
+class NumericBinaryFunction : public Forwarding<cp::ScalarFunction> {
+ public:
+  using Forwarding<cp::ScalarFunction>::Forwarding;
+  Result<const cp::Kernel*> DispatchBest(std::vector<TypeHolder>* values) const override {
+    auto exact = DispatchExact(*values);
+    if (exact.ok()) return exact;
+    if (auto common = CommonNumeric(*values)) {
+      for (auto& v : *values) v = common;
+      return DispatchExact(*values);
+    }
+    return exact;
+  }
+};
+
+static Status AddBinaryFunction(cp::FunctionRegistry* reg, Runtime* rt, const std::string& name, int op, bool compare) {
+  auto fn = std::make_shared<NumericBinaryFunction>(name, cp::Arity::Binary(), DocFor({"x", "y"}));
+  for (const auto& ty : NumericTypes()) {
+    cp::ScalarKernel k({cp::InputType(ty), cp::InputType(ty)}, compare ? cp::OutputType(arrow::boolean()) : cp::OutputType(ty),
+                       compare ? CompareExec : ArithExec);
+    k.null_handling = cp::NullHandling::COMPUTED_NO_PREALLOCATE;
+    k.mem_allocation = cp::MemAllocation::NO_PREALLOCATE;
+    k.can_write_into_slices = false;
+    k.data = std::make_shared<KernelData>(rt, op);
+    ARROW_RETURN_NOT_OK(fn->AddKernel(std::move(k)));
+  }
+  return reg->AddFunction(std::move(fn), /*allow_overwrite=*/true);
+}
+
+// ------------------------------------------------------------------------------------------
+// cast: a MetaFunction like the reference's CastMetaFunction (compute/cast.cc:78-127)
+// ------------------------------------------------------------------------------------------
+class CastFunction : public cp::MetaFunction {
+ public:
+  explicit CastFunction(Runtime* rt) : cp::MetaFunction("cast", cp::Arity::Unary(), DocFor({"input"}, "CastOptions", true)), rt_(rt) {}
+  Result<Datum> ExecuteImpl(const std::vector<Datum>& args, const cp::FunctionOptions* options,
+                            cp::ExecContext* ctx) const override {
+    if (!AnyOnDevice(args)) {
+      ARROW_ASSIGN_OR_RAISE(auto parent, cp::GetFunctionRegistry()->GetFunction("cast"));
+      return parent->Execute(args, options, ctx);
+    }
+    auto opts = static_cast<const cp::CastOptions*>(options);
+    if (!opts || !opts->to_type.type) return Status::Invalid("Cast requires that options.to_type has been set");
+    if (!args[0].is_array()) return Status::NotImplemented("arrow_b200 cast: only Array inputs (chunks are cast one by one by the caller)");
+    const ArrayData& in = *args[0].array();
+    if (in.type->Equals(*opts->to_type.type)) return args[0];
+    B2Array bin, bout;
+    ARROW_RETURN_NOT_OK(DataToB2(in, &bin));
+    ARROW_ASSIGN_OR_RAISE(int to, B2TypeId(*opts->to_type.type));
+    B2CastOptions co{to, opts->allow_int_overflow, opts->allow_float_truncate, 0};
+    int st = b2_cast_numeric(rt_->context(), &bin, &co, &bout, nullptr);
+    if (st == B2_NOT_IMPLEMENTED)
+      return Status::NotImplemented("Unsupported cast from ", in.type->ToString(), " to ", opts->to_type.type->ToString(),
+                                    " using function cast_", opts->to_type.type->name());
+    B200_RETURN_NOT_OK(st);
+    return Datum(AdoptOutput(rt_, bout, opts->to_type.GetSharedPtr()));
+  }
+
+ private:
+  Runtime* rt_;
+};
+
+// ------------------------------------------------------------------------------------------
+// selection + sort vector kernels
+// ------------------------------------------------------------------------------------------
+static Result<TypeHolder> FirstType(cp::KernelContext*, const std::vector<TypeHolder>& types) { return types.front(); }
+
+static std::shared_ptr<ArrayData> DictionaryOf(const ArraySpan& span) {
+  return span.type->id() == Type::DICTIONARY ? span.dictionary().ToArrayData() : nullptr;
+}
+
+static Status FilterExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  const auto& opts = OptionsState<cp::FilterOptions>::Get(ctx);
+  if (batch[0].array.length != batch[1].array.length) return Status::Invalid("Filter inputs must all be the same length");
+  B2Array v, m, o;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[1].array, &m));
+  B200_RETURN_NOT_OK(b2_filter(kd.rt->context(), &v, &m, opts.null_selection_behavior == cp::FilterOptions::EMIT_NULL ? 1 : 0, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, batch[0].type()->GetSharedPtr(), DictionaryOf(batch[0].array)), out);
+  return Status::OK();
+}
+
+static Status TakeExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  const auto& opts = OptionsState<cp::TakeOptions>::Get(ctx);
+  B2Array v, i, o;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[1].array, &i));
+  B200_RETURN_NOT_OK(b2_take(kd.rt->context(), &v, &i, opts.boundscheck, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, batch[0].type()->GetSharedPtr(), DictionaryOf(batch[0].array)), out);
+  return Status::OK();
+}
+
+static Status SortExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  const auto& opts = OptionsState<cp::ArraySortOptions>::Get(ctx);
+  B2Array v, o;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  B200_RETURN_NOT_OK(b2_sort_indices(kd.rt->context(), &v, opts.order == cp::SortOrder::Descending ? 1 : 0,
+                                     opts.null_placement == cp::NullPlacement::AtEnd ? 1 : 0, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, arrow::uint64()), out);
+  return Status::OK();
+}
+
+static cp::VectorKernel MakeVectorKernel(Runtime* rt, std::vector<cp::InputType> in, cp::OutputType out, cp::ArrayKernelExec exec,
+                                         cp::KernelInit init) {
+  cp::VectorKernel k(std::move(in), std::move(out), exec, std::move(init));
+  k.null_handling = cp::NullHandling::COMPUTED_NO_PREALLOCATE;
+  k.mem_allocation = cp::MemAllocation::NO_PREALLOCATE;
+  k.can_write_into_slices = false;
+  k.can_execute_chunkwise = false;  // as array_take / array_sort_indices in the reference
+  k.output_chunked = false;
+  k.data = std::make_shared<KernelData>(rt, 0);
+  return k;
+}
+
+static Status AddSelectionFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
+  static const cp::FilterOptions kFilterDefaults = cp::FilterOptions::Defaults();
+  static const cp::TakeOptions kTakeDefaults = cp::TakeOptions::Defaults();
+  static const cp::ArraySortOptions kSortDefaults = cp::ArraySortOptions::Defaults();
+  auto filter = std::make_shared<Forwarding<cp::VectorFunction>>("array_filter", cp::Arity::Binary(),
+                                                                 DocFor({"array", "selection_filter"}, "FilterOptions"), &kFilterDefaults);
+  ARROW_RETURN_NOT_OK(filter->AddKernel(MakeVectorKernel(rt, {cp::InputType::Any(), cp::InputType(arrow::boolean())},
+                                                         cp::OutputType(FirstType), FilterExec, OptionsState<cp::FilterOptions>::Init)));
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(filter), true));
+
+  auto take = std::make_shared<Forwarding<cp::VectorFunction>>("array_take", cp::Arity::Binary(),
+                                                               DocFor({"array", "indices"}, "TakeOptions"), &kTakeDefaults);
+  for (const auto& it : arrow::IntTypes()) {
+    ARROW_RETURN_NOT_OK(take->AddKernel(MakeVectorKernel(rt, {cp::InputType::Any(), cp::InputType(it)}, cp::OutputType(FirstType),
+                                                         TakeExec, OptionsState<cp::TakeOptions>::Init)));
+  }
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(take), true));
+
+  auto sort = std::make_shared<Forwarding<cp::VectorFunction>>("array_sort_indices", cp::Arity::Unary(),
+                                                               DocFor({"array"}, "ArraySortOptions"), &kSortDefaults);
+  for (const auto& ty : NumericTypes()) {
+    ARROW_RETURN_NOT_OK(sort->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(arrow::uint64()), SortExec,
+                                                         OptionsState<cp::ArraySortOptions>::Init)));
+  }
+  return reg->AddFunction(std::move(sort), true);
+}
+
+// ------------------------------------------------------------------------------------------
+// hash aggregates: the HashAggregateKernel contract (compute/kernel.h:720-769)
+// ------------------------------------------------------------------------------------------
+struct HashAggState : public cp::KernelState {
+  ~HashAggState() override {
+    if (agg) b2_hashagg_destroy(agg);
+  }
+  Runtime* rt = nullptr;
+  B2HashAgg* agg = nullptr;
+  std::shared_ptr<DataType> out_type;
+};
+
+struct HashAggKernelData : public cp::KernelState {
+  HashAggKernelData(Runtime* r, int k) : rt(r), kind(k) {}
+  Runtime* rt;
+  int kind;
+};
+
+static std::shared_ptr<DataType> HashAggOutType(int kind, const DataType& in) {
+  switch (kind) {
+    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return arrow::int64();
+    case B2_HASH_MEAN: return arrow::float64();
+    case B2_HASH_SUM:
+      if (arrow::is_signed_integer(in.id())) return arrow::int64();
+      if (arrow::is_unsigned_integer(in.id())) return arrow::uint64();
+      return arrow::float64();
+    default: return in.GetSharedPtr();
+  }
+}
+
+static Result<std::unique_ptr<cp::KernelState>> HashAggInit(cp::KernelContext* ctx, const cp::KernelInitArgs& args) {
+  const auto& kd = checked_cast<const HashAggKernelData&>(*args.kernel->data);
+  auto st = std::make_unique<HashAggState>();
+  st->rt = kd.rt;
+  B2HashAggOptions o{1, 1, 0, 0};
+  if (kd.kind == B2_HASH_COUNT) {
+    if (auto co = static_cast<const cp::CountOptions*>(args.options))
+      o.count_mode = co->mode == cp::CountOptions::ONLY_VALID ? 0 : co->mode == cp::CountOptions::ONLY_NULL ? 1 : 2;
+  } else if (kd.kind != B2_HASH_COUNT_ALL) {
+    if (auto so = static_cast<const cp::ScalarAggregateOptions*>(args.options)) {
+      o.skip_nulls = so->skip_nulls;
+      o.min_count = so->min_count;
+    }
+  }
+  int vt = B2_NA;
+  const DataType* in_type = nullptr;
+  if (kd.kind != B2_HASH_COUNT_ALL) {
+    in_type = args.inputs[0].type;
+    ARROW_ASSIGN_OR_RAISE(vt, B2TypeId(*in_type));
+  }
+  B200_RETURN_NOT_OK(b2_hashagg_create(kd.rt->context(), kd.kind, vt, &o, &st->agg));
+  st->out_type = in_type ? HashAggOutType(kd.kind, *in_type) : arrow::int64();
+  return st;
+}
+
+static HashAggState* AggOf(cp::KernelContext* ctx) { return checked_cast<HashAggState*>(ctx->state()); }
+
+static Status HashAggResize(cp::KernelContext* ctx, int64_t num_groups) {
+  B200_RETURN_NOT_OK(b2_hashagg_resize(AggOf(ctx)->agg, num_groups, nullptr));
+  return Status::OK();
+}
+static Status HashAggConsume(cp::KernelContext* ctx, const cp::ExecSpan& batch) {
+  B2Array v, ids;
+  const bool count_all = batch.num_values() == 1;
+  if (!count_all) ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[count_all ? 0 : 1].array, &ids));
+  B200_RETURN_NOT_OK(b2_hashagg_consume(AggOf(ctx)->agg, count_all ? nullptr : &v, &ids, nullptr));
+  return Status::OK();
+}
+static Status HashAggMerge(cp::KernelContext* ctx, cp::KernelState&& other, const ArrayData& mapping) {
+  B2Array m;
+  ARROW_RETURN_NOT_OK(DataToB2(mapping, &m));
+  B200_RETURN_NOT_OK(b2_hashagg_merge(AggOf(ctx)->agg, checked_cast<HashAggState&>(other).agg, &m, nullptr));
+  return Status::OK();
+}
+static Status HashAggFinalize(cp::KernelContext* ctx, Datum* out) {
+  HashAggState* st = AggOf(ctx);
+  B2Array o;
+  B200_RETURN_NOT_OK(b2_hashagg_finalize(st->agg, &o, nullptr));
+  *out = Datum(AdoptOutput(st->rt, o, st->out_type));
+  return Status::OK();
+}
+
+static Status AddHashAggregate(cp::FunctionRegistry* reg, Runtime* rt, const std::string& name, int kind) {
+  static const cp::ScalarAggregateOptions kAggDefaults = cp::ScalarAggregateOptions::Defaults();
+  static const cp::CountOptions kCountDefaults = cp::CountOptions::Defaults();
+  const cp::FunctionOptions* defaults = kind == B2_HASH_COUNT ? static_cast<const cp::FunctionOptions*>(&kCountDefaults)
+                                        : kind == B2_HASH_COUNT_ALL ? nullptr : &kAggDefaults;
+  auto fn = std::make_shared<cp::HashAggregateFunction>(
+      name, kind == B2_HASH_COUNT_ALL ? cp::Arity::Unary() : cp::Arity::Binary(),
+      kind == B2_HASH_COUNT_ALL ? DocFor({"group_id_array"})
+                                : DocFor({"array", "group_id_array"}, kind == B2_HASH_COUNT ? "CountOptions" : "ScalarAggregateOptions"),
+      defaults);
+  auto out_resolver = [kind](cp::KernelContext* ctx, const std::vector<TypeHolder>& types) -> Result<TypeHolder> {
+    if (kind == B2_HASH_COUNT_ALL) return TypeHolder(arrow::int64());
+    return TypeHolder(HashAggOutType(kind, *types[0].type));
+  };
+  auto add = [&](std::vector<cp::InputType> in) {
+    cp::HashAggregateKernel k(cp::KernelSignature::Make(std::move(in), cp::OutputType(out_resolver)), HashAggInit, HashAggResize,
+                              HashAggConsume, HashAggMerge, HashAggFinalize, /*ordered=*/false);
+    k.data = std::make_shared<HashAggKernelData>(rt, kind);
+    return fn->AddKernel(std::move(k));
+  };
+  if (kind == B2_HASH_COUNT_ALL) {
+    ARROW_RETURN_NOT_OK(add({cp::InputType(arrow::uint32())}));
+  } else if (kind == B2_HASH_COUNT) {
+    ARROW_RETURN_NOT_OK(add({cp::InputType::Any(), cp::InputType(arrow::uint32())}));
+  } else {
+    for (const auto& ty : NumericTypes()) ARROW_RETURN_NOT_OK(add({cp::InputType(ty), cp::InputType(arrow::uint32())}));
+  }
+  return reg->AddFunction(std::move(fn), true);
+}
+
+// ------------------------------------------------------------------------------------------
+// Grouper
+// ------------------------------------------------------------------------------------------
+class DeviceGrouper : public cp::Grouper {
+ public:
+  DeviceGrouper(Runtime* rt, std::vector<TypeHolder> key_types, B2Grouper* g)
+      : rt_(rt), key_types_(std::move(key_types)), g_(g) {}
+  ~DeviceGrouper() override { b2_grouper_destroy(g_); }
+
+  Status Reset() override {
+    B200_RETURN_NOT_OK(b2_grouper_reset(g_));
+    return Status::OK();
+  }
+  Result<Datum> Consume(const cp::ExecSpan& batch, int64_t offset, int64_t length) override { return Run(batch, offset, length, true); }
+  Result<Datum> Lookup(const cp::ExecSpan& batch, int64_t offset, int64_t length) override { return Run(batch, offset, length, false); }
+  Status Populate(const cp::ExecSpan& batch, int64_t offset, int64_t length) override { return Run(batch, offset, length, true).status(); }
+  uint32_t num_groups() const override {
+    uint32_t n = 0;
+    b2_grouper_num_groups(g_, &n);
+    return n;
+  }
+  Result<cp::ExecBatch> GetUniques() override {
+    std::vector<B2Array> outs(key_types_.size());
+    B200_RETURN_NOT_OK(b2_grouper_uniques(g_, outs.data(), nullptr));
+    cp::ExecBatch batch({}, num_groups());
+    for (size_t i = 0; i < outs.size(); ++i) batch.values.emplace_back(AdoptOutput(rt_, outs[i], key_types_[i].GetSharedPtr()));
+    return batch;
+  }
+
+ private:
+  Result<Datum> Run(const cp::ExecSpan& batch, int64_t offset, int64_t length, bool insert) {
+    if (static_cast<size_t>(batch.num_values()) != key_types_.size())
+      return Status::Invalid("expected batch size ", key_types_.size(), " but got ", batch.num_values());
+    if (offset < 0 || offset > batch.length) return Status::Invalid("invalid grouper consume offset: ", offset);
+    if (length < 0) length = batch.length - offset;
+    std::vector<B2Array> keys(key_types_.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (!batch[i].is_array()) return Status::NotImplemented("arrow_b200 grouper: scalar key columns");
+      if (!batch[i].type()->Equals(*key_types_[i].type))
+        return Status::Invalid("expected batch value ", i, " of type ", key_types_[i].type->ToString(), " but got ", batch[i].type()->ToString());
+      ARROW_RETURN_NOT_OK(SpanToB2(batch[i].array, &keys[i]));
+      keys[i].offset += offset;
+      keys[i].length = length;
+    }
+    B2Array ids;
+    B200_RETURN_NOT_OK((insert ? b2_grouper_consume : b2_grouper_lookup)(g_, keys.data(), &ids, nullptr));
+    return Datum(AdoptOutput(rt_, ids, arrow::uint32()));
+  }
+  Runtime* rt_;
+  std::vector<TypeHolder> key_types_;
+  B2Grouper* g_;
+};
+
+Result<std::unique_ptr<cp::Grouper>> MakeGrouper(const std::vector<TypeHolder>& key_types, Runtime* rt) {
+  std::vector<int32_t> ids;
+  for (const auto& t : key_types) {
+    ARROW_ASSIGN_OR_RAISE(int id, B2TypeId(*t.type));
+    ids.push_back(id);
+  }
+  B2Grouper* g = nullptr;
+  B200_RETURN_NOT_OK(b2_grouper_create(rt->context(), ids.data(), static_cast<int>(ids.size()), &g));
+  return std::unique_ptr<cp::Grouper>(new DeviceGrouper(rt, key_types, g));
+}
+
+// ------------------------------------------------------------------------------------------
+Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
+  const std::pair<const char*, int> arith[] = {{"add", B2_ADD}, {"subtract", B2_SUBTRACT}, {"multiply", B2_MULTIPLY},
+                                               {"divide", B2_DIVIDE}, {"add_checked", B2_ADD_CHECKED},
+                                               {"subtract_checked", B2_SUBTRACT_CHECKED},
+                                               {"multiply_checked", B2_MULTIPLY_CHECKED}, {"divide_checked", B2_DIVIDE_CHECKED}};
+  for (const auto& a : arith) ARROW_RETURN_NOT_OK(AddBinaryFunction(reg, rt, a.first, a.second, false));
+  const std::pair<const char*, int> cmp[] = {{"equal", B2_EQUAL}, {"not_equal", B2_NOT_EQUAL}, {"greater", B2_GREATER},
+                                             {"greater_equal", B2_GREATER_EQUAL}, {"less", B2_LESS}, {"less_equal", B2_LESS_EQUAL}};
+  for (const auto& c : cmp) ARROW_RETURN_NOT_OK(AddBinaryFunction(reg, rt, c.first, c.second, true));
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<CastFunction>(rt), true));
+  ARROW_RETURN_NOT_OK(AddSelectionFunctions(reg, rt));
+  const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},
+                                              {"hash_count_all", B2_HASH_COUNT_ALL}, {"hash_mean", B2_HASH_MEAN},
+                                              {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX}};
+  for (const auto& a : aggs) ARROW_RETURN_NOT_OK(AddHashAggregate(reg, rt, a.first, a.second));
+  return Status::OK();
+}
+
+}  // namespace arrow_b200

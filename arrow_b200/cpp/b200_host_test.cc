@@ -1,0 +1,294 @@
+// b200_host_test.cc -- parity of the C++ drop-in against the reference itself: the same
+// ExecBatch inputs go through arrow::compute::CallFunction twice, once with the default
+// (CPU) registry of the installed reference binary and once with the nested B200 registry
+// on device copies, and the results must be Equal (bit-exact for integer / selection /
+// sort outputs and single IEEE float ops).  Mirrors the reference's own helpers
+// CheckScalar / AssertFilter / AssertSortIndices (compute/kernels/test_util_internal.h).
+// Prints one line per check and exits non-zero on the first failure.
+#include <arrow/api.h>
+#include <arrow/compute/api.h>
+#include <arrow/compute/initialize.h>
+#include <arrow/compute/row/grouper.h>
+
+#include <iostream>
+#include <random>
+
+#include "b200_compute.h"
+
+namespace cp = arrow::compute;
+using arrow::Datum;
+using arrow::Result;
+using arrow::Status;
+
+static int g_checks = 0;
+
+#define CHECK_OK(expr)                                                                  \
+  do {                                                                                  \
+    auto _st = (expr);                                                                  \
+    if (!_st.ok()) {                                                                    \
+      std::cout << "FAIL " << __LINE__ << ": " << _st.ToString() << std::endl;          \
+      std::exit(1);                                                                     \
+    }                                                                                   \
+  } while (0)
+
+template <typename T>
+T Unwrap(Result<T> r, int line) {
+  if (!r.ok()) {
+    std::cout << "FAIL " << line << ": " << r.status().ToString() << std::endl;
+    std::exit(1);
+  }
+  return std::move(r).ValueUnsafe();
+}
+#define UNWRAP(expr) Unwrap((expr), __LINE__)
+
+// ---- seeded random arrays (kSeed = 0x0ff1ce, compute/kernels/test_util_internal.h:135) ----
+template <typename ArrowType>
+std::shared_ptr<arrow::Array> RandomNumeric(int64_t n, double null_p, uint64_t seed, double lo, double hi) {
+  using C = typename ArrowType::c_type;
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> val(lo, hi), u(0, 1);
+  typename arrow::TypeTraits<ArrowType>::BuilderType b;
+  for (int64_t i = 0; i < n; ++i) {
+    if (u(rng) < null_p) CHECK_OK(b.AppendNull());
+    else CHECK_OK(b.Append(static_cast<C>(val(rng))));
+  }
+  return UNWRAP(b.Finish());
+}
+
+std::shared_ptr<arrow::Array> RandomBool(int64_t n, double true_p, double null_p, uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> u(0, 1);
+  arrow::BooleanBuilder b;
+  for (int64_t i = 0; i < n; ++i) {
+    if (u(rng) < null_p) CHECK_OK(b.AppendNull());
+    else CHECK_OK(b.Append(u(rng) < true_p));
+  }
+  return UNWRAP(b.Finish());
+}
+
+std::shared_ptr<arrow::Array> RandomStrings(int64_t n, double null_p, uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> u(0, 1);
+  std::uniform_int_distribution<int> len(0, 32), ch('a', 'z');
+  arrow::StringBuilder b;
+  for (int64_t i = 0; i < n; ++i) {
+    if (u(rng) < null_p) {
+      CHECK_OK(b.AppendNull());
+    } else {
+      std::string s(len(rng), ' ');
+      for (auto& c : s) c = static_cast<char>(ch(rng));
+      CHECK_OK(b.Append(s));
+    }
+  }
+  return UNWRAP(b.Finish());
+}
+
+struct Harness {
+  arrow_b200::Runtime* rt;
+  cp::ExecContext cpu_ctx;
+  cp::ExecContext gpu_ctx;
+  explicit Harness(arrow_b200::Runtime* r)
+      : rt(r), cpu_ctx(arrow::default_memory_pool()), gpu_ctx(arrow::default_memory_pool(), nullptr, r->registry()) {}
+
+  Datum Dev(const Datum& d) {
+    if (!d.is_array()) return d;
+    return Datum(UNWRAP(arrow_b200::ToDevice(*d.array(), rt->memory_manager())));
+  }
+  std::shared_ptr<arrow::Array> Host(const Datum& d) {
+    if (d.is_scalar()) return UNWRAP(arrow::MakeArrayFromScalar(*d.scalar(), 1));
+    return arrow::MakeArray(UNWRAP(arrow_b200::ToHost(*d.array())));
+  }
+
+  // same call, both registries; device result must Equal the reference's
+  void Check(const std::string& what, const std::string& fn, std::vector<Datum> args, const cp::FunctionOptions* opts = nullptr) {
+    auto want = cp::CallFunction(fn, args, opts, &cpu_ctx);
+    std::vector<Datum> dargs;
+    for (auto& a : args) dargs.push_back(Dev(a));
+    auto got = cp::CallFunction(fn, dargs, opts, &gpu_ctx);
+    ++g_checks;
+    if (!want.ok() || !got.ok()) {
+      if (want.ok() != got.ok() || want.status().code() != got.status().code() ||
+          want.status().message() != got.status().message()) {
+        std::cout << "FAIL " << what << ": reference -> " << want.status().ToString() << " ; device -> " << got.status().ToString() << std::endl;
+        std::exit(1);
+      }
+      std::cout << "OK   " << what << " (same error: " << want.status().message() << ")" << std::endl;
+      return;
+    }
+    if (got->is_array() && !arrow_b200::IsOnDevice(*got->array()) && got->length() > 0) {
+      std::cout << "FAIL " << what << ": result is not on the device (CPU path was taken)" << std::endl;
+      std::exit(1);
+    }
+    auto w = want->is_chunked_array() ? UNWRAP(arrow::Concatenate(want->chunked_array()->chunks())) : Host(*want);
+    auto g = Host(*got);
+    auto vst = g->ValidateFull();
+    if (!vst.ok() || !g->Equals(*w, arrow::EqualOptions::Defaults().nans_equal(true))) {
+      std::cout << "FAIL " << what << ": arrays differ " << vst.ToString() << "\n  want: " << w->ToString().substr(0, 400)
+                << "\n  got:  " << g->ToString().substr(0, 400) << std::endl;
+      std::exit(1);
+    }
+    std::cout << "OK   " << what << " (" << g->length() << " rows, " << g->null_count() << " nulls)" << std::endl;
+  }
+};
+
+int main() {
+  CHECK_OK(cp::Initialize());
+  auto rt_r = arrow_b200::Runtime::Get(0);
+  if (!rt_r.ok()) {
+    std::cout << "FAIL runtime: " << rt_r.status().ToString() << std::endl;
+    return 1;
+  }
+  Harness h(*rt_r);
+  const int64_t n = 100003;
+
+  auto i64a = RandomNumeric<arrow::Int64Type>(n, 0.1, 0x0ff1ce, -100, 100);
+  auto i64b = RandomNumeric<arrow::Int64Type>(n, 0.1, 0x0ff1cf, 1, 100);
+  auto i32 = RandomNumeric<arrow::Int32Type>(n, 0.1, 0x0ff1d0, -1000, 1000);
+  auto u8 = RandomNumeric<arrow::UInt8Type>(n, 0.0, 0x0ff1d1, 0, 255);
+  auto f32a = RandomNumeric<arrow::FloatType>(n, 0.1, 0x0ff1d2, 0, 1e6);
+  auto f32b = RandomNumeric<arrow::FloatType>(n, 0.1, 0x0ff1d3, 0, 1e6);
+  auto f64 = RandomNumeric<arrow::DoubleType>(n, 0.1, 0x0ff1d4, 0, 1e6);
+  auto mask = RandomBool(n, 0.5, 0.05, 0x0ff1d5);
+  auto idx = RandomNumeric<arrow::Int64Type>(n, 0.05, 0x0ff1d6, 0, n - 1);
+  auto idx32 = RandomNumeric<arrow::Int32Type>(n / 3, 0.0, 0x0ff1d7, 0, n - 1);
+  auto strs = RandomStrings(20000, 0.1, 0x0ff1d8);
+
+  // ---- arithmetic / compare through CallFunction: exact dispatch, implicit casts, scalars ----
+  for (const char* fn : {"add", "subtract", "multiply", "divide", "add_checked", "subtract_checked", "multiply_checked"}) {
+    h.Check(std::string(fn) + "(int64,int64)", fn, {i64a, i64b});
+    h.Check(std::string(fn) + "(float32,float32)", fn, {f32a, f32b});
+  }
+  h.Check("add(int32,int64) implicit cast", "add", {i32, i64a});
+  h.Check("add(uint8,int32) implicit cast", "add", {u8, i32});
+  h.Check("multiply(int64,float32) implicit cast", "multiply", {i64a, f32a});
+  h.Check("add(int64,scalar)", "add", {i64a, Datum(int64_t(7))});
+  h.Check("subtract(scalar,float32)", "subtract", {Datum(1.5f), f32a});
+  h.Check("add(sliced,sliced)", "add", {i64a->Slice(3, 5000), i64b->Slice(77, 5000)});
+  h.Check("divide by zero error", "divide", {i64a, UNWRAP(cp::Subtract(i64b, i64b, cp::ArithmeticOptions(), &h.cpu_ctx))});
+  {
+    arrow::Int64Builder b;
+    CHECK_OK(b.AppendValues({1, std::numeric_limits<int64_t>::max(), 3}));
+    auto big = UNWRAP(b.Finish());
+    h.Check("add_checked overflow error", "add_checked", {big, big});
+  }
+  for (const char* fn : {"equal", "not_equal", "greater", "greater_equal", "less", "less_equal"}) {
+    h.Check(std::string(fn) + "(int64,int64)", fn, {i64a, i64b});
+    h.Check(std::string(fn) + "(float32,scalar)", fn, {f32a, Datum(5e5f)});
+  }
+  h.Check("less(int32,int64) implicit cast", "less", {i32, i64a});
+
+  // ---- cast ----
+  auto cast_to = [&](const std::shared_ptr<arrow::DataType>& t, bool safe) {
+    return safe ? cp::CastOptions::Safe(t) : cp::CastOptions::Unsafe(t);
+  };
+  {
+    auto o = cast_to(arrow::float32(), true);
+    h.Check("cast(float64->float32)", "cast", {f64}, &o);
+    o = cast_to(arrow::int32(), true);
+    h.Check("cast(int64->int32) safe", "cast", {i64a}, &o);
+    h.Check("cast(float64->int32) truncation error", "cast", {f64}, &o);
+    o = cast_to(arrow::int32(), false);
+    h.Check("cast(float64->int32) unsafe", "cast", {f64}, &o);
+    o = cast_to(arrow::int8(), true);
+    h.Check("cast(int32->int8) range error", "cast", {i32}, &o);
+    o = cast_to(arrow::float64(), true);
+    h.Check("cast(int64->float64)", "cast", {i64a}, &o);
+  }
+
+  // ---- filter / take (meta functions of the parent registry route into our array_* kernels) ----
+  for (auto ns : {cp::FilterOptions::DROP, cp::FilterOptions::EMIT_NULL}) {
+    cp::FilterOptions o(ns);
+    const std::string tag = ns == cp::FilterOptions::DROP ? " DROP" : " EMIT_NULL";
+    h.Check("filter(int64)" + tag, "filter", {i64a, mask}, &o);
+    h.Check("filter(float32)" + tag, "filter", {f32a, mask}, &o);
+    h.Check("filter(uint8)" + tag, "filter", {u8, mask}, &o);
+    h.Check("filter(utf8)" + tag, "filter", {strs, mask->Slice(0, strs->length())}, &o);
+    h.Check("array_filter(sliced int64)" + tag, "array_filter", {i64a->Slice(5, 40000), mask->Slice(9, 40000)}, &o);
+  }
+  h.Check("filter length mismatch error", "filter", {i64a, mask->Slice(0, 10)});
+  h.Check("take(int64, int64 idx)", "take", {i64a, idx});
+  h.Check("take(float64, int32 idx)", "take", {f64, idx32});
+  h.Check("take(utf8, int32 idx)", "take", {strs, UNWRAP(cp::Cast(*RandomNumeric<arrow::Int32Type>(5000, 0.1, 9, 0, 19999), arrow::int32()))});
+  {
+    arrow::Int32Builder b;
+    CHECK_OK(b.AppendValues({0, 5, static_cast<int32_t>(n), 1}));
+    h.Check("take out of bounds error", "take", {i64a, UNWRAP(b.Finish())});
+  }
+
+  // ---- sort_indices ----
+  for (auto order : {cp::SortOrder::Ascending, cp::SortOrder::Descending}) {
+    for (auto np : {cp::NullPlacement::AtEnd, cp::NullPlacement::AtStart}) {
+      cp::ArraySortOptions o(order, np);
+      const std::string tag = std::string(order == cp::SortOrder::Ascending ? " asc" : " desc") + (np == cp::NullPlacement::AtEnd ? " at_end" : " at_start");
+      h.Check("array_sort_indices(int64)" + tag, "array_sort_indices", {i64a}, &o);
+      h.Check("array_sort_indices(float32)" + tag, "array_sort_indices", {f32a}, &o);
+      cp::SortOptions so({cp::SortKey("not-used", order)}, np);
+      h.Check("sort_indices(int32)" + tag, "sort_indices", {i32}, &so);
+    }
+  }
+
+  // ---- Grouper: TestGrouper::ValidateConsume (row/grouper_test.cc:736-760) ----
+  {
+    auto keys = RandomNumeric<arrow::Int64Type>(50000, 0.05, 77, 0, 500);
+    auto ref = UNWRAP(cp::Grouper::Make({arrow::int64()}, &h.cpu_ctx));
+    auto dev = UNWRAP(arrow_b200::MakeGrouper({arrow::int64()}, h.rt));
+    cp::ExecBatch hb({keys}, keys->length());
+    cp::ExecBatch db({h.Dev(keys)}, keys->length());
+    auto ref_ids = UNWRAP(ref->Consume(cp::ExecSpan(hb)));
+    auto dev_ids = UNWRAP(dev->Consume(cp::ExecSpan(db)));
+    auto dev_ids_h = h.Host(dev_ids);
+    auto uniq = UNWRAP(dev->GetUniques());
+    auto uniq_h = h.Host(uniq.values[0]);
+    auto taken = UNWRAP(cp::Take(uniq_h, dev_ids_h, cp::TakeOptions::Defaults(), &h.cpu_ctx));
+    ++g_checks;
+    if (dev->num_groups() != ref->num_groups() || !taken.make_array()->Equals(*keys)) {
+      std::cout << "FAIL grouper: groups " << dev->num_groups() << " vs " << ref->num_groups() << std::endl;
+      return 1;
+    }
+    std::cout << "OK   grouper consume/uniques (" << dev->num_groups() << " groups, Take(uniques, ids) == keys)" << std::endl;
+
+    // ---- hash aggregate kernels driven exactly as acero/aggregate_internal.cc:67-123 does ----
+    auto vals = RandomNumeric<arrow::Int64Type>(50000, 0.1, 78, -100, 100);
+    for (const char* fn : {"hash_sum", "hash_count", "hash_min", "hash_max", "hash_mean"}) {
+      auto run = [&](cp::ExecContext* ctx, const Datum& v, const Datum& ids, uint32_t groups) -> Datum {
+        auto function = UNWRAP(ctx->func_registry()->GetFunction(fn));
+        auto kernel = static_cast<const cp::HashAggregateKernel*>(UNWRAP(function->DispatchExact({arrow::int64(), arrow::uint32()})));
+        cp::KernelContext kctx(ctx, kernel);
+        std::vector<arrow::TypeHolder> in_types = {arrow::int64(), arrow::uint32()};
+        auto state = UNWRAP(kernel->init(&kctx, cp::KernelInitArgs{kernel, in_types, function->default_options()}));
+        kctx.SetState(state.get());
+        CHECK_OK(kernel->resize(&kctx, groups));
+        cp::ExecBatch b({v, ids}, v.length());
+        CHECK_OK(kernel->consume(&kctx, cp::ExecSpan(b)));
+        Datum out;
+        CHECK_OK(kernel->finalize(&kctx, &out));
+        return out;
+      };
+      // the reference consumes the DEVICE grouper's ids (ids differ between groupers only by a bijection)
+      auto want = run(&h.cpu_ctx, vals, dev_ids_h, dev->num_groups());
+      auto got = run(&h.gpu_ctx, h.Dev(vals), dev_ids, dev->num_groups());
+      ++g_checks;
+      auto g = h.Host(got);
+      bool ok = std::string(fn) == "hash_mean" ? g->ApproxEquals(*want.make_array()) : g->Equals(*want.make_array());
+      if (!ok) {
+        std::cout << "FAIL " << fn << "\n  want " << want.make_array()->ToString().substr(0, 300) << "\n  got " << g->ToString().substr(0, 300) << std::endl;
+        return 1;
+      }
+      std::cout << "OK   " << fn << "(int64) via HashAggregateKernel init/resize/consume/finalize" << std::endl;
+    }
+    (void)ref_ids;
+  }
+
+  // ---- host arguments fall through to the stock CPU functions of the parent registry ----
+  {
+    auto out = UNWRAP(cp::CallFunction("add", {i64a, i64b}, nullptr, &h.gpu_ctx));
+    ++g_checks;
+    if (arrow_b200::IsOnDevice(*out.array()) || !out.make_array()->Equals(*UNWRAP(cp::CallFunction("add", {i64a, i64b}, nullptr, &h.cpu_ctx)).make_array())) {
+      std::cout << "FAIL host passthrough" << std::endl;
+      return 1;
+    }
+    std::cout << "OK   host arrays pass through to the parent registry" << std::endl;
+  }
+  std::cout << "PASS " << g_checks << " checks; " << b2_launch_count() << " kernels launched by libarrow_b200.so" << std::endl;
+  return 0;
+}

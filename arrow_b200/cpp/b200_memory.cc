@@ -1,0 +1,159 @@
+// b200_memory.cc -- see b200_memory.h
+#include "b200_memory.h"
+
+#include <arrow/io/interfaces.h>
+#include <arrow/util/logging.h>
+
+namespace arrow_b200 {
+
+using arrow::Result;
+using arrow::Status;
+
+Status StatusFromB2(int code) {
+  const char* msg = b2_last_error();
+  switch (code) {
+    case B2_OUT_OF_MEMORY: return Status::OutOfMemory(msg);
+    case B2_KEY_ERROR: return Status::KeyError(msg);
+    case B2_TYPE_ERROR: return Status::TypeError(msg);
+    case B2_INVALID: return Status::Invalid(msg);
+    case B2_IO_ERROR: return Status::IOError(msg);
+    case B2_CAPACITY_ERROR: return Status::CapacityError(msg);
+    case B2_INDEX_ERROR: return Status::IndexError(msg);
+    case B2_NOT_IMPLEMENTED: return Status::NotImplemented(msg);
+    default: return Status::UnknownError(msg);
+  }
+}
+
+namespace {
+
+// A pool-owned device buffer: freed back into the libarrow_b200 pool on destruction,
+// as CudaBuffer frees through its context (cuda_memory.cc).
+class B200Buffer : public arrow::MutableBuffer {
+ public:
+  B200Buffer(uint8_t* ptr, int64_t size, std::shared_ptr<arrow::MemoryManager> mm, B2Context* ctx)
+      : arrow::MutableBuffer(ptr, size, std::move(mm)), ctx_(ctx), ptr_(ptr) {}
+  ~B200Buffer() override {
+    if (ptr_) b2_free(ctx_, ptr_);
+  }
+
+ private:
+  B2Context* ctx_;
+  void* ptr_;
+};
+
+}  // namespace
+
+Result<std::shared_ptr<B200Device>> B200Device::Make(int device_number) {
+  B2Context* ctx = nullptr;
+  B200_RETURN_NOT_OK(b2_context_create(device_number, &ctx));
+  return std::shared_ptr<B200Device>(new B200Device(device_number, ctx));
+}
+
+B200Device::~B200Device() { b2_context_destroy(ctx_); }
+
+std::string B200Device::ToString() const { return "B200Device(device " + std::to_string(device_number_) + ")"; }
+
+bool B200Device::Equals(const arrow::Device& other) const {
+  if (other.type_name() != type_name()) return false;
+  return static_cast<const B200Device&>(other).device_number_ == device_number_;
+}
+
+std::shared_ptr<arrow::MemoryManager> B200Device::default_memory_manager() {
+  auto mm = mm_.lock();
+  if (!mm) {
+    mm = std::make_shared<B200MemoryManager>(shared_from_this());
+    mm_ = mm;
+  }
+  return mm;
+}
+
+Result<std::shared_ptr<arrow::io::RandomAccessFile>> B200MemoryManager::GetBufferReader(std::shared_ptr<arrow::Buffer>) {
+  return Status::NotImplemented("B200MemoryManager::GetBufferReader");
+}
+Result<std::shared_ptr<arrow::io::OutputStream>> B200MemoryManager::GetBufferWriter(std::shared_ptr<arrow::Buffer>) {
+  return Status::NotImplemented("B200MemoryManager::GetBufferWriter");
+}
+
+Result<std::unique_ptr<arrow::Buffer>> B200MemoryManager::AllocateBuffer(int64_t size) {
+  void* p = nullptr;
+  B200_RETURN_NOT_OK(b2_alloc(context(), static_cast<size_t>(size > 0 ? size : 1), &p));
+  return std::unique_ptr<arrow::Buffer>(new B200Buffer(static_cast<uint8_t*>(p), size, shared_from_this(), context()));
+}
+
+std::shared_ptr<arrow::Buffer> B200MemoryManager::Adopt(const void* ptr, int64_t size) {
+  if (!ptr) return nullptr;
+  return std::make_shared<B200Buffer>(static_cast<uint8_t*>(const_cast<void*>(ptr)), size, shared_from_this(), context());
+}
+
+Result<std::shared_ptr<arrow::Buffer>> B200MemoryManager::CopyBufferFrom(const std::shared_ptr<arrow::Buffer>& buf,
+                                                                        const std::shared_ptr<arrow::MemoryManager>& from) {
+  ARROW_ASSIGN_OR_RAISE(auto out, CopyNonOwnedFrom(*buf, from));
+  return std::shared_ptr<arrow::Buffer>(std::move(out));
+}
+
+Result<std::unique_ptr<arrow::Buffer>> B200MemoryManager::CopyNonOwnedFrom(const arrow::Buffer& buf,
+                                                                          const std::shared_ptr<arrow::MemoryManager>& from) {
+  if (!from->is_cpu()) return nullptr;  // unsupported source: let arrow try other routes
+  ARROW_ASSIGN_OR_RAISE(auto out, AllocateBuffer(buf.size()));
+  B200_RETURN_NOT_OK(b2_memcpy_h2d(context(), reinterpret_cast<void*>(out->address()), buf.data(),
+                                   static_cast<size_t>(buf.size()), nullptr));
+  B200_RETURN_NOT_OK(b2_sync(context(), nullptr));
+  return out;
+}
+
+Result<std::shared_ptr<arrow::Buffer>> B200MemoryManager::CopyBufferTo(const std::shared_ptr<arrow::Buffer>& buf,
+                                                                      const std::shared_ptr<arrow::MemoryManager>& to) {
+  ARROW_ASSIGN_OR_RAISE(auto out, CopyNonOwnedTo(*buf, to));
+  return std::shared_ptr<arrow::Buffer>(std::move(out));
+}
+
+Result<std::unique_ptr<arrow::Buffer>> B200MemoryManager::CopyNonOwnedTo(const arrow::Buffer& buf,
+                                                                        const std::shared_ptr<arrow::MemoryManager>& to) {
+  if (!to->is_cpu()) return nullptr;
+  ARROW_ASSIGN_OR_RAISE(auto out, to->AllocateBuffer(buf.size()));
+  B200_RETURN_NOT_OK(b2_memcpy_d2h(context(), out->mutable_data(), reinterpret_cast<const void*>(buf.address()),
+                                   static_cast<size_t>(buf.size()), nullptr));
+  B200_RETURN_NOT_OK(b2_sync(context(), nullptr));
+  return out;
+}
+
+bool IsOnDevice(const arrow::ArrayData& data) {
+  for (const auto& b : data.buffers)
+    if (b && !b->is_cpu()) return true;
+  if (data.dictionary && IsOnDevice(*data.dictionary)) return true;
+  return false;
+}
+
+namespace {
+Result<std::shared_ptr<arrow::ArrayData>> CopyData(const arrow::ArrayData& in, const std::shared_ptr<arrow::MemoryManager>& to) {
+  auto out = std::make_shared<arrow::ArrayData>(in.type, in.length, in.null_count.load(), in.offset);
+  out->buffers.resize(in.buffers.size());
+  for (size_t i = 0; i < in.buffers.size(); ++i) {
+    if (in.buffers[i]) {
+      ARROW_ASSIGN_OR_RAISE(out->buffers[i], arrow::MemoryManager::CopyBuffer(in.buffers[i], to));
+    }
+  }
+  for (const auto& child : in.child_data) {
+    ARROW_ASSIGN_OR_RAISE(auto c, CopyData(*child, to));
+    out->child_data.push_back(std::move(c));
+  }
+  if (in.dictionary) {
+    ARROW_ASSIGN_OR_RAISE(out->dictionary, CopyData(*in.dictionary, to));
+  }
+  return out;
+}
+}  // namespace
+
+Result<std::shared_ptr<arrow::ArrayData>> ToDevice(const arrow::ArrayData& host, const std::shared_ptr<arrow::MemoryManager>& mm) {
+  // a device array must carry an explicit null_count: ArrayData::GetNullCount would
+  // dereference a null bitmap pointer (array/data.cc:214-226)
+  ARROW_ASSIGN_OR_RAISE(auto out, CopyData(host, mm));
+  out->null_count = host.GetNullCount();
+  return out;
+}
+
+Result<std::shared_ptr<arrow::ArrayData>> ToHost(const arrow::ArrayData& device) {
+  return CopyData(device, arrow::default_cpu_memory_manager());
+}
+
+}  // namespace arrow_b200
