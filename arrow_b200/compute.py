@@ -209,6 +209,8 @@ def filter(values: DeviceArray, mask: DeviceArray, null_selection_behavior="drop
     if not pa.types.is_boolean(mask.type):
         raise pa.ArrowNotImplementedError(
             f"Function 'array_filter' has no kernel matching input types ({values.type}, {mask.type})")
+    if len(values) != len(mask):  # raised by the reference's VectorExecutor before the kernel runs
+        raise pa.ArrowInvalid("Arguments for execution of vector kernel function 'array_filter' must all be the same length")
     ctx = values.ctx
     cv, cm, cout = values._c(), mask._c(), cabi.B2Array()
     check(ctx.lib.b2_filter(ctx.handle, C.byref(cv), C.byref(cm), _null_selection(null_selection_behavior),

@@ -109,7 +109,11 @@ std::shared_ptr<ArrayData> AdoptOutput(Runtime* rt, const B2Array& o, std::share
   out->buffers.push_back(rt->mm()->Adopt(o.validity, (o.length + 7) / 8));
   out->buffers.push_back(rt->mm()->Adopt(o.data, DataBytes(o)));
   const bool binary = o.type == B2_STRING || o.type == B2_BINARY || o.type == B2_LARGE_STRING || o.type == B2_LARGE_BINARY;
-  if (binary) out->buffers.push_back(rt->mm()->Adopt(o.data2, 0));
+  if (binary) {
+    int64_t nbytes = 0;
+    b2_binary_data_size(rt->context(), &o, &nbytes, nullptr);  // outputs start at offset 0: size = last offset
+    out->buffers.push_back(rt->mm()->Adopt(o.data2, nbytes));
+  }
   out->dictionary = std::move(dictionary);
   return out;
 }
@@ -365,7 +369,9 @@ static std::shared_ptr<ArrayData> DictionaryOf(const ArraySpan& span) {
 static Status FilterExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
   const KernelData& kd = DataOf(ctx);
   const auto& opts = OptionsState<cp::FilterOptions>::Get(ctx);
-  if (batch[0].array.length != batch[1].array.length) return Status::Invalid("Filter inputs must all be the same length");
+  // the stock VectorExecutor raises this for mismatched array arguments (exec.cc CheckAllArrayOrScalar/InferBatchLength)
+  if (batch[0].array.length != batch[1].array.length)
+    return Status::Invalid("Arguments for execution of vector kernel function 'array_filter' must all be the same length");
   B2Array v, m, o;
   ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
   ARROW_RETURN_NOT_OK(SpanToB2(batch[1].array, &m));

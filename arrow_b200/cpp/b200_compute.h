@@ -58,3 +58,9 @@ std::shared_ptr<arrow::ArrayData> AdoptOutput(Runtime* rt, const B2Array& o, std
                                               std::shared_ptr<arrow::ArrayData> dictionary = nullptr);
 
 }  // namespace arrow_b200
+
+namespace arrow_b200 {
+// Adds the "b200_aggregate" / "b200_filter" / "b200_order_by" ExecNode factories to Acero's
+// default ExecFactoryRegistry (b200_acero.cc).
+arrow::Status RegisterAceroNodes();
+}  // namespace arrow_b200

@@ -9,6 +9,9 @@
 #include <arrow/compute/api.h>
 #include <arrow/compute/initialize.h>
 #include <arrow/compute/row/grouper.h>
+#include <arrow/acero/exec_plan.h>
+#include <arrow/acero/options.h>
+#include <arrow/table.h>
 
 #include <iostream>
 #include <random>
@@ -288,6 +291,63 @@ int main() {
       return 1;
     }
     std::cout << "OK   host arrays pass through to the parent registry" << std::endl;
+  }
+  // ---- Acero: the same Declarations with the stock node names and with the b200_ factories ----
+  {
+    namespace ac = arrow::acero;
+    CHECK_OK(arrow_b200::RegisterAceroNodes());
+    const int64_t rows = 200000;
+    auto k = RandomNumeric<arrow::Int64Type>(rows, 0.02, 91, 0, 1000);
+    auto v = RandomNumeric<arrow::Int64Type>(rows, 0.1, 92, -100, 100);
+    auto w = RandomNumeric<arrow::DoubleType>(rows, 0.1, 93, 0, 100);
+    auto table = arrow::Table::Make(arrow::schema({arrow::field("k", arrow::int64()), arrow::field("v", arrow::int64()),
+                                                   arrow::field("w", arrow::float64())}), {k, v, w});
+    auto sorted = [&](std::shared_ptr<arrow::Table> t, const std::string& key) {
+      auto idx = UNWRAP(cp::SortIndices(Datum(t), cp::SortOptions({cp::SortKey(key)}), &h.cpu_ctx));
+      return UNWRAP(cp::Take(Datum(t), Datum(idx), cp::TakeOptions::Defaults(), &h.cpu_ctx)).table()->CombineChunks().ValueOrDie();
+    };
+    auto run = [&](const std::string& factory, std::shared_ptr<ac::ExecNodeOptions> opts) {
+      ac::Declaration plan = ac::Declaration::Sequence({{"table_source", ac::TableSourceNodeOptions(table, 1 << 15)},
+                                                        {factory, std::move(opts)}});
+      return UNWRAP(ac::DeclarationToTable(std::move(plan), /*use_threads=*/false));
+    };
+    // aggregate: hash_sum + hash_count + hash_min + hash_count_all by k (rows sorted by key, as the reference's tests do)
+    std::vector<cp::Aggregate> aggs = {{"hash_sum", nullptr, "v", "v_sum"}, {"hash_count", nullptr, "v", "v_count"},
+                                       {"hash_min", nullptr, "w", "w_min"}, {"hash_count_all", "n"}};
+    auto want = sorted(run("aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs, std::vector<arrow::FieldRef>{"k"})), "k");
+    auto got = sorted(run("b200_aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs, std::vector<arrow::FieldRef>{"k"})), "k");
+    ++g_checks;
+    auto got_sel = UNWRAP(got->SelectColumns({0, 1, 2, 3, 4}));
+    auto want_sel = UNWRAP(want->SelectColumns({UNWRAP(arrow::FieldRef("k").FindOne(*want->schema())).indices()[0],
+                                                UNWRAP(arrow::FieldRef("v_sum").FindOne(*want->schema())).indices()[0],
+                                                UNWRAP(arrow::FieldRef("v_count").FindOne(*want->schema())).indices()[0],
+                                                UNWRAP(arrow::FieldRef("w_min").FindOne(*want->schema())).indices()[0],
+                                                UNWRAP(arrow::FieldRef("n").FindOne(*want->schema())).indices()[0]}));
+    if (!got_sel->Equals(*want_sel)) {
+      std::cout << "FAIL b200_aggregate\n want " << want_sel->ToString().substr(0, 600) << "\n got " << got_sel->ToString().substr(0, 600) << std::endl;
+      return 1;
+    }
+    std::cout << "OK   b200_aggregate == aggregate (" << got->num_rows() << " groups over " << rows << " rows in 32Ki-row batches)" << std::endl;
+    // filter: the predicate is an Expression bound against the nested registry
+    auto pred = cp::greater(cp::call("add", {cp::field_ref("v"), cp::field_ref("k")}), cp::literal(int64_t(400)));
+    auto fwant = run("filter", std::make_shared<ac::FilterNodeOptions>(pred));
+    auto fgot = run("b200_filter", std::make_shared<ac::FilterNodeOptions>(pred));
+    ++g_checks;
+    if (!fgot->CombineChunks().ValueOrDie()->Equals(*fwant->CombineChunks().ValueOrDie())) {
+      std::cout << "FAIL b200_filter rows " << fgot->num_rows() << " vs " << fwant->num_rows() << std::endl;
+      return 1;
+    }
+    std::cout << "OK   b200_filter == filter (" << fgot->num_rows() << " rows kept; predicate greater(add(v,k),400) ran on device)" << std::endl;
+    // order_by
+    cp::Ordering ord({cp::SortKey("v", cp::SortOrder::Descending)}, cp::NullPlacement::AtStart);
+    auto owant = run("order_by", std::make_shared<ac::OrderByNodeOptions>(ord));
+    auto ogot = run("b200_order_by", std::make_shared<ac::OrderByNodeOptions>(ord));
+    ++g_checks;
+    if (!ogot->CombineChunks().ValueOrDie()->Equals(*owant->CombineChunks().ValueOrDie())) {
+      std::cout << "FAIL b200_order_by" << std::endl;
+      return 1;
+    }
+    std::cout << "OK   b200_order_by == order_by (stable, descending, nulls first)" << std::endl;
   }
   std::cout << "PASS " << g_checks << " checks; " << b2_launch_count() << " kernels launched by libarrow_b200.so" << std::endl;
   return 0;

@@ -80,6 +80,16 @@ struct BitmapReader {
     int64_t a = bit0 + i;
     return (__ldg(reinterpret_cast<const uint8_t*>(base) + (a >> 3)) >> (a & 7)) & 1;
   }
+  // random-access variant: the byte load carries an L2 cache policy (see l2_policy_*)
+  __device__ __forceinline__ bool bit_hint(int64_t i, uint64_t policy) const {
+    if (base == nullptr) return true;
+    int64_t a = bit0 + i;
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;"
+                 : "=r"(v)
+                 : "l"(reinterpret_cast<const uint8_t*>(base) + (a >> 3)), "l"(policy));
+    return (v >> (a & 7)) & 1;
+  }
 };
 
 __host__ __device__ inline int64_t bitmap_bytes(int64_t nbits) { return (nbits + 7) >> 3; }
@@ -119,6 +129,55 @@ __device__ __forceinline__ T ld_stream(const T* p) {
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) {
   __stcs(p, v);
+}
+
+// ---------------------------------------------------------------------------
+// L2 residency hints for random-access kernels (gather, hash tables): the big,
+// touched-once structure is loaded evict-first and the small hot one (a validity
+// bitmap, a hash-table slot array) evict-last, so the 126 MB L2 keeps the latter.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ld_hint_u8(const uint8_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T ld_hint(const T* p, uint64_t pol) {
+  T out;
+  if constexpr (sizeof(T) == 1) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    uint8_t b = static_cast<uint8_t>(v);
+    memcpy(&out, &b, 1);
+  } else if constexpr (sizeof(T) == 2) {
+    uint16_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    memcpy(&out, &v, 2);
+  } else if constexpr (sizeof(T) == 4) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    memcpy(&out, &v, 4);
+  } else if constexpr (sizeof(T) == 8) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    memcpy(&out, &v, 8);
+  } else {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    memcpy(&out, &v, 16);
+  }
+  return out;
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
   T* __restrict__ out = static_cast<T*>(a.out);
   const uint64_t vlen = static_cast<uint64_t>(a.values_length);
   int64_t valid_local = 0;
+  // values are touched once per gather (evict-first); the validity bitmap is 1/64 of their
+  // size and hit by every row: keep it resident in L2 (evict-last)
+  const uint64_t pol_values = l2_policy_evict_first();
+  const uint64_t pol_bitmap = l2_policy_evict_last();
 
   for (int64_t tile = (int64_t)blockIdx.x * kTile; tile < a.n; tile += (int64_t)gridDim.x * kTile) {
     int64_t wb = tile + (int64_t)(threadIdx.x >> 5) * kWarpTile;
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
           bool inb = j < vlen;
           if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(wb + u * 32 * V + lane * V + k));
           if (iv && inb) {
-            g[u].v[k] = __ldg(vals + j);
-            if (HAS_VALID) gvalid[u] |= (a.values_valid.bit(static_cast<int64_t>(j)) ? 1u : 0u) << k;
+            g[u].v[k] = ld_hint<T>(vals + j, pol_values);
+            if (HAS_VALID) gvalid[u] |= (a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) ? 1u : 0u) << k;
           } else {
             g[u].v[k] = zero_value<T>();
           }
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
           bool inb = j < vlen;
           if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(i));
           if (iv && inb) {
-            out[i] = __ldg(vals + j);
-            ov = HAS_VALID ? a.values_valid.bit(static_cast<int64_t>(j)) : true;
+            out[i] = ld_hint<T>(vals + j, pol_values);
+            ov = HAS_VALID ? a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) : true;
           } else {
             out[i] = zero_value<T>();
           }
@@ -215,6 +219,23 @@ int index_error(const B2Array* indices, uint64_t row, cudaStream_t s) {
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_binary_data_size(B2Context* ctx, const B2Array* array, int64_t* out_bytes, void* stream) {
+  if (!ctx || !array || !out_bytes) return set_error(B2_INVALID, "b2_binary_data_size: null argument");
+  if (!type_is_binary_like(array->type)) return set_error(B2_TYPE_ERROR, "b2_binary_data_size: not a binary-like array");
+  *out_bytes = 0;
+  if (array->length == 0 || !array->data) return B2_OK;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int ow = offset_width(array->type);
+  int64_t first = 0, last = 0;
+  const char* base = static_cast<const char*>(array->data);
+  B2_CUDA(cudaMemcpyAsync(&first, base + array->offset * ow, ow, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaMemcpyAsync(&last, base + (array->offset + array->length) * ow, ow, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  *out_bytes = last - first;  // little-endian: the low `ow` bytes were filled
+  return B2_OK;
+}
 
 extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* indices, int boundscheck,
                        B2Array* out, void* stream) {

@@ -61,6 +61,14 @@ int main() {
       printf("%llu,16,%d,0,%.3f,%.1f\n", (unsigned long long)((mask + 1) * 8 >> 20), mem, t16, n / t16 / 1e6);
     }
   }
+  // L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes), 8 GB table
+  for (size_t gran : {32, 64, 128}) {
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    uint64_t m = (1ull << 30) - 1;
+    float t = run<8>(vals, nullptr, out, n, m, 0, 148 * 16);
+    printf("# l2_fetch_granularity req=%zu got=%zu : %.3f ms, %.1f Ggathers/s\n", gran, got, t, n / t / 1e6);
+  }
   // 8 GB table, but consecutive groups of gathers confined to a window (what a partition pass would give)
   uint64_t mask = (1ull << 30) - 1;
   for (int wshift = 22; wshift <= 28; wshift += 2) {

@@ -234,6 +234,11 @@ B2_API int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_selec
 B2_API int b2_take(B2Context* ctx, const B2Array* values, const B2Array* indices,
                    int boundscheck, B2Array* out, void* stream);
 
+/* Bytes of character data a (large_)utf8/binary array spans: offsets[offset+length] -
+ * offsets[offset] (one D2H read).  Lets the host size the data buffer of an output the
+ * way BufferSpan::size does (array/data.h:525-532). */
+B2_API int b2_binary_data_size(B2Context* ctx, const B2Array* array, int64_t* out_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * SortIndices.  Replaces ArraySortIndices::Exec + ArrayCompareSorter /
  * ArrayCountSorter (kernels/vector_array_sort.cc:144-446,524-540) and
