@@ -1,0 +1,131 @@
+// partition.cu -- destination ids for the one exchange step of the multi-GPU hash-aggregate
+// and SortIndices (the reference has no distributed path, its per-thread
+// analogue is GroupByNode::Merge, acero/groupby_aggregate_node.cc:255-298).
+//
+//   b2_hash_partition  : id[i] = hash64(key[i]) % n_parts   (null keys -> partition 0); the same
+//                        hash64 the Grouper table uses, so one owner sees every duplicate of a key.
+//   b2_range_partition : id[i] = #splitters whose ordered key is <= ordered_key(value[i])
+//                        (upper bound), in the same total order SortIndices uses (sign-flipped
+//                        ints, IEEE total order with -0 == +0, NaN last, bitwise NOT for
+//                        Descending); null rows get id = n_splitters + 1 (they do not move).
+// Both are streaming HBM-bound passes: read W B/row, write 4 B/row.
+#include <type_traits>
+
+#include "bitmap.h"
+#include "hash_table.cuh"
+
+namespace b2 {
+
+__global__ void __launch_bounds__(kBlock) hash_partition_kernel(const void* keys, int width, BitmapReader valid, int64_t n,
+                                                                uint32_t n_parts, uint32_t* out) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    uint32_t p = 0;
+    if (valid.bit(i)) p = static_cast<uint32_t>(hash64(load_key_bits(keys, width, i)) % n_parts);
+    out[i] = p;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ uint64_t total_order_key(T v, bool descending) {
+  uint64_t k;
+  if constexpr (std::is_floating_point<T>::value) {
+    if (v != v) return ~0ull;  // NaNs after every value in either order (they are "null-like")
+    double d = static_cast<double>(v);
+    if (d == 0.0) d = 0.0;
+    uint64_t b = static_cast<uint64_t>(__double_as_longlong(d));
+    k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    if (descending) k = ~k;
+    return k;
+  } else if constexpr (std::is_signed<T>::value) {
+    k = static_cast<uint64_t>(static_cast<int64_t>(v)) ^ 0x8000000000000000ull;
+  } else {
+    k = static_cast<uint64_t>(v);
+  }
+  return descending ? ~k : k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) range_partition_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
+                                                                 const T* __restrict__ splitters, int n_split, bool descending,
+                                                                 uint32_t* __restrict__ out) {
+  __shared__ uint64_t s_split[64];
+  if (threadIdx.x < n_split) s_split[threadIdx.x] = total_order_key<T>(splitters[threadIdx.x], descending);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    uint32_t p = static_cast<uint32_t>(n_split) + 1;
+    if (valid.bit(i)) {
+      const uint64_t k = total_order_key<T>(values[i], descending);
+      p = 0;
+      for (int j = 0; j < n_split; ++j) p += (s_split[j] <= k) ? 1u : 0u;
+    }
+    out[i] = p;
+  }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_hash_partition(B2Context* ctx, const B2Array* keys, int n_parts, B2Array* out_ids, void* stream) {
+  if (!ctx || !keys || !out_ids) return set_error(B2_INVALID, "b2_hash_partition: null argument");
+  if (n_parts < 1) return set_error(B2_INVALID, "n_parts must be >= 1");
+  const int w = type_width(keys->type);
+  if (w == 0) return set_error(B2_NOT_IMPLEMENTED, "b2_hash_partition: key type id %d", keys->type);
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = keys->length;
+  Temp ids(ctx, s);
+  B2_RETURN_NOT_OK(ids.alloc(sizeof(uint32_t) * (size_t)n));
+  if (n > 0) {
+    BitmapReader valid(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
+    hash_partition_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(
+        static_cast<const char*>(keys->data) + keys->offset * w, w, valid, n, (uint32_t)n_parts, ids.as<uint32_t>());
+    B2_LAUNCHED();
+  }
+  fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
+  return B2_OK;
+}
+
+template <typename T>
+static int run_range(const B2Array* values, const B2Array* splitters, int order, uint32_t* out, cudaStream_t s) {
+  const int64_t n = values->length;
+  BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  range_partition_kernel<T><<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(
+      static_cast<const T*>(values->data) + values->offset, valid, n,
+      static_cast<const T*>(splitters->data) + splitters->offset, (int)splitters->length, order == 1, out);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+extern "C" int b2_range_partition(B2Context* ctx, const B2Array* values, const B2Array* splitters, int order,
+                                  B2Array* out_ids, void* stream) {
+  if (!ctx || !values || !splitters || !out_ids) return set_error(B2_INVALID, "b2_range_partition: null argument");
+  if (values->type != splitters->type) return set_error(B2_TYPE_ERROR, "splitters must have the values' type");
+  if (splitters->length > 63) return set_error(B2_INVALID, "at most 63 splitters");
+  if (splitters->null_count > 0) return set_error(B2_INVALID, "splitters must not contain nulls");
+  if (!type_is_numeric(values->type)) return set_error(B2_NOT_IMPLEMENTED, "b2_range_partition: type id %d", values->type);
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = values->length;
+  Temp ids(ctx, s);
+  B2_RETURN_NOT_OK(ids.alloc(sizeof(uint32_t) * (size_t)n));
+  if (n > 0) {
+    int st;
+    uint32_t* o = ids.as<uint32_t>();
+    switch (values->type) {
+      case B2_INT8: st = run_range<int8_t>(values, splitters, order, o, s); break;
+      case B2_UINT8: st = run_range<uint8_t>(values, splitters, order, o, s); break;
+      case B2_INT16: st = run_range<int16_t>(values, splitters, order, o, s); break;
+      case B2_UINT16: st = run_range<uint16_t>(values, splitters, order, o, s); break;
+      case B2_INT32: st = run_range<int32_t>(values, splitters, order, o, s); break;
+      case B2_UINT32: st = run_range<uint32_t>(values, splitters, order, o, s); break;
+      case B2_INT64: st = run_range<int64_t>(values, splitters, order, o, s); break;
+      case B2_UINT64: st = run_range<uint64_t>(values, splitters, order, o, s); break;
+      case B2_FLOAT: st = run_range<float>(values, splitters, order, o, s); break;
+      default: st = run_range<double>(values, splitters, order, o, s); break;
+    }
+    if (st != B2_OK) return st;
+  }
+  fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
+  return B2_OK;
+}

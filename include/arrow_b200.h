@@ -321,6 +321,19 @@ B2_API int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys
 B2_API int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys,
                                         B2Array* out_sums, B2Array* out_counts, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Multi-GPU exchange helpers (no reference counterpart: the reference is single-process;
+ * its per-thread analogue is GroupByNode::Merge, acero/groupby_aggregate_node.cc:255-298).
+ * out_ids: B2_UINT32, one destination id per row.
+ *   hash : id = hash64(key) % n_parts, null keys -> 0          (hash-aggregate shuffle)
+ *   range: id = #splitters <= value in SortIndices' total order; nulls -> n_splitters + 1
+ *          (SortIndices shuffle; order as in b2_sort_indices)
+ * ------------------------------------------------------------------------- */
+B2_API int b2_hash_partition(B2Context* ctx, const B2Array* keys, int n_parts, B2Array* out_ids,
+                             void* stream);
+B2_API int b2_range_partition(B2Context* ctx, const B2Array* values, const B2Array* splitters,
+                              int order, B2Array* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
