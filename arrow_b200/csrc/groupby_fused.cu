@@ -209,6 +209,7 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
   const V* vdata = static_cast<const V*>(values->data) + values->offset;
   BitmapReader kv(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
   BitmapReader vv(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  if (!g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
   for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
     const int64_t cn = n - row0 < kChunkRows ? n - row0 : kChunkRows;
     Temp pend_a(ctx, s), pend_b(ctx, s);
@@ -252,11 +253,8 @@ int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_t
   g->value_type = value_type;
   uint64_t cap = next_pow2(expected_groups > 0 ? (uint64_t)expected_groups * 2 : (1u << 16));
   if (cap < 1024) cap = 1024;
-  int st = fused_alloc(ctx, cap, &g->table, ctx->stream);
-  if (st != B2_OK) {
-    delete g;
-    return st;
-  }
+  // the table is allocated and initialised lazily on the first consume, on the CALLER's stream:
+  // an init kernel queued on the context stream would race with a consume on another stream
   g->cap = cap;
   *out = g;
   return B2_OK;
@@ -298,6 +296,7 @@ int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Arra
   B2Context* ctx = g->ctx;
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
+  if (!g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
   const int64_t n = static_cast<int64_t>(g->groups);
   const int kw = type_width(g->key_type);
   const int sum_type = (g->value_type == B2_FLOAT || g->value_type == B2_DOUBLE) ? B2_DOUBLE

@@ -301,6 +301,8 @@ static int launch_compact(int width, bool has_valid, const FilterArgs& a, int64_
 
 int filter_binary(B2Context* ctx, const B2Array* values, const B2Array* mask, int null_selection,
                   B2Array* out, cudaStream_t s);  // selection_binary.cu
+int filter_bool(B2Context* ctx, const B2Array* values, const B2Array* mask, int null_selection, B2Array* out,
+                cudaStream_t s);  // selection_bool.cu
 
 }  // namespace b2
 
@@ -330,6 +332,7 @@ extern "C" int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* m
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
   if (type_is_binary_like(values->type)) return filter_binary(ctx, values, mask, null_selection, out, s);
+  if (values->type == B2_BOOL) return filter_bool(ctx, values, mask, null_selection, out, s);
   int width = values->type == B2_FIXED_SIZE_BINARY ? values->byte_width : type_width(values->type);
   if (width != 1 && width != 2 && width != 4 && width != 8 && width != 16)
     return set_error(B2_NOT_IMPLEMENTED, "filter: unsupported value type id %d (width %d)", values->type, width);

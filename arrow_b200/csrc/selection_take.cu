@@ -197,6 +197,7 @@ static int launch_take_w(int idx_type, const TakeArgs& a, bool has_valid, cudaSt
   }
 }
 
+int take_bool(B2Context* ctx, const B2Array* values, const B2Array* indices, B2Array* out, cudaStream_t s);  // selection_bool.cu
 int take_binary(B2Context* ctx, const B2Array* values, const B2Array* indices, int boundscheck,
                 B2Array* out, cudaStream_t s);  // selection_binary.cu
 
@@ -245,6 +246,7 @@ extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* ind
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
   if (type_is_binary_like(values->type)) return take_binary(ctx, values, indices, boundscheck, out, s);
+  if (values->type == B2_BOOL) return take_bool(ctx, values, indices, out, s);
   int width = values->type == B2_FIXED_SIZE_BINARY ? values->byte_width : type_width(values->type);
   if (width != 1 && width != 2 && width != 4 && width != 8 && width != 16)
     return set_error(B2_NOT_IMPLEMENTED, "take: unsupported value type id %d (width %d)", values->type, width);
