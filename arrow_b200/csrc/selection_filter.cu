@@ -16,13 +16,15 @@
 //   1. filter_count_kernel : one warp per 4096-row tile popcounts the selection words
 //      (mask data &/| mask validity) -> per-tile counts.           reads bitmaps only
 //   2. tile_scan_kernel    : exclusive scan of the tile counts (one CTA). tiny
-//   3. filter_compact_kernel<W>: one CTA per tile.  Warp 0 rebuilds the tile's 64
-//      selection words and their prefix popcounts in shared memory; then every lane
-//      streams its rows with 16-byte coalesced loads (skipped when none of its rows is
-//      selected), and stores survivors at base + prefix + popc(lower bits): ranks are
-//      dense and monotonic across a warp, so each store instruction writes one
-//      contiguous span.  Validity bits are compacted into a shared-memory bitmap and
-//      flushed with plain word stores (atomicOr only on the two boundary words).
+//   3. filter_compact_kernel<W>: one CTA per tile.  Dense tiles issue all their 16-byte
+//      coalesced value loads first (they need every sector anyway) so the loads overlap
+//      the bitmap round trip; every WARP then rebuilds the tile's 64 selection words and
+//      prefix popcounts in registers (no shared memory, no barrier on the data path) and
+//      stores survivors at base + prefix + popc(lower bits): ranks are dense and
+//      monotonic across a warp, so each store instruction writes one contiguous span.
+//      Sparse tiles load only lanes holding a survivor.  Validity bits are compacted into
+//      a shared-memory bitmap and flushed with plain word stores (atomicOr only on the
+//      two boundary words).
 // Algorithmic bytes/row (int64, values nullable, mask non-null, s=0.5): 12.3125
 // (SURVEY section 8d); passes 1+2 re-read only the bitmaps (+0.25 B/row).
 #include "selection.cuh"
@@ -126,80 +128,82 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
   constexpr int kPassRows = kBlock * R;          // rows per CTA pass
   constexpr int kPasses = kTileRows / kPassRows; // W=8: 8, W=4: 4, W=1: 1
   static_assert(kPasses >= 1, "tile too small");
-  __shared__ uint64_t s_sel[kTileWords];
-  __shared__ uint64_t s_ov[kTileWords];
-  __shared__ uint32_t s_prefix[kTileWords];
-  __shared__ uint32_t s_bits[kTileRows / 32 + 2];
+  __shared__ uint32_t s_bits[HAS_VALID ? kTileRows / 32 + 2 : 1];
 
   const int64_t tile = blockIdx.x;
   const int64_t row0 = tile * kTileRows;
   const int64_t out_base = a.tile_offsets[tile];
+  const unsigned tile_count = static_cast<unsigned>(a.tile_offsets[tile + 1] - out_base);
+  if (tile_count == 0) return;  // nothing selected in this tile (uniform for the CTA)
   const unsigned lane = lane_id();
+  const T* vals = static_cast<const T*>(a.values);
 
-  if (threadIdx.x < 32) {
-    int64_t w0 = tile * kTileWords + 2 * lane;
-    uint64_t s0 = a.fb.sel(w0), s1 = a.fb.sel(w0 + 1);
-    int c0 = __popcll(s0), c1 = __popcll(s1);
-    int incl = c0 + c1;
+  // Dense tiles (>= 1/8 of the rows survive) need every 32-byte sector anyway: issue all value
+  // loads NOW, before the selection words are known, so they overlap the bitmap round trip.
+  // Sparse tiles load only the lanes that hold a survivor (after the selection is known).
+  const bool dense = !IOTA && a.vec_ok && tile_count >= kTileRows / 8 && row0 + kTileRows <= a.n;
+  uint4 raw[kPasses];
+  if (dense) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int excl = incl - c0 - c1;
-    s_sel[2 * lane] = s0;
-    s_sel[2 * lane + 1] = s1;
-    s_prefix[2 * lane] = excl;
-    s_prefix[2 * lane + 1] = excl + c0;
-    if (HAS_VALID) {
-      s_ov[2 * lane] = a.fb.out_valid(w0);
-      s_ov[2 * lane + 1] = a.fb.out_valid(w0 + 1);
-    }
+    for (int p = 0; p < kPasses; ++p)
+      raw[p] = __ldcs(reinterpret_cast<const uint4*>(vals + row0 + p * kPassRows + threadIdx.x * R));
   }
+
+  // Every warp rebuilds the tile's 64 selection words and their exclusive prefix popcounts in
+  // registers (lane l owns words 2l, 2l+1): no shared memory, no CTA barrier on the data path;
+  // the 7 redundant bitmap reads per tile hit L1/L2.
+  const int64_t w0 = tile * kTileWords + 2 * lane;
+  const uint64_t s0 = a.fb.sel(w0), s1 = a.fb.sel(w0 + 1);
+  uint64_t ov0 = 0, ov1 = 0;
   if (HAS_VALID) {
+    ov0 = a.fb.out_valid(w0);
+    ov1 = a.fb.out_valid(w0 + 1);
     for (int i = threadIdx.x; i < kTileRows / 32 + 2; i += kBlock) s_bits[i] = 0;
   }
-  __syncthreads();
+  const int c0 = __popcll(s0), c1 = __popcll(s1);
+  int incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned pre0 = incl - c0 - c1, pre1 = pre0 + c0;
+  if (HAS_VALID) __syncthreads();  // s_bits zeroed before any atomicOr
 
   T* out = static_cast<T*>(a.out) + out_base;
-  const T* vals = static_cast<const T*>(a.values);
   const unsigned bit_base = static_cast<unsigned>(out_base & 31);
 
-  // phase A: issue every pass's 16-byte load before the first dependent store so
-  // kPasses requests per lane are in flight (guide, Guideline 7)
-  uint4 raw[kPasses];
-  unsigned pbits[kPasses];
 #pragma unroll
   for (int p = 0; p < kPasses; ++p) {
     const int r = p * kPassRows + threadIdx.x * R;  // row within tile, multiple of R
-    const uint64_t selw = s_sel[r >> 6];
-    pbits[p] = static_cast<unsigned>(selw >> (r & 63)) & ((1u << R) - 1u);
-    const int64_t grow = row0 + r;
-    if (!IOTA && pbits[p] != 0) {
-      if (a.vec_ok && grow + R <= a.n) {
-        raw[p] = __ldcs(reinterpret_cast<const uint4*>(vals + grow));
-      } else {
-        T tmp[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) tmp[k] = ((pbits[p] >> k) & 1) ? vals[grow + k] : T{};
-        memcpy(&raw[p], tmp, 16);
-      }
+    const int wi = r >> 6;                          // selection word of this lane's rows
+    // fetch word wi and its prefix from the lane that owns it (wi is warp-uniform up to R | 64)
+    const int src = wi >> 1;
+    const uint64_t sa = __shfl_sync(0xffffffffu, s0, src), sb = __shfl_sync(0xffffffffu, s1, src);
+    const unsigned pa = __shfl_sync(0xffffffffu, pre0, src), pb = __shfl_sync(0xffffffffu, pre1, src);
+    const uint64_t selw = (wi & 1) ? sb : sa;
+    const unsigned bits = static_cast<unsigned>(selw >> (r & 63)) & ((1u << R) - 1u);
+    uint64_t ovw = 0;
+    if (HAS_VALID) {
+      const uint64_t oa = __shfl_sync(0xffffffffu, ov0, src), ob = __shfl_sync(0xffffffffu, ov1, src);
+      ovw = (wi & 1) ? ob : oa;
     }
-  }
-  // phase B: scatter survivors; ranks are dense and ascending across the warp
-#pragma unroll
-  for (int p = 0; p < kPasses; ++p) {
-    const unsigned bits = pbits[p];
     if (bits == 0) continue;
-    const int r = p * kPassRows + threadIdx.x * R;
-    const uint64_t selw = s_sel[r >> 6];
-    const unsigned rank = s_prefix[r >> 6] + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+    const unsigned rank = ((wi & 1) ? pb : pa) + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+    const int64_t grow = row0 + r;
     T v[R];
     if (IOTA) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) v[k] = iota_value<T>(row0 + r + k);
-    } else {
+      for (int k = 0; k < R; ++k) v[k] = iota_value<T>(grow + k);
+    } else if (dense) {
       memcpy(v, &raw[p], 16);
+    } else if (a.vec_ok && grow + R <= a.n) {
+      uint4 x = __ldcs(reinterpret_cast<const uint4*>(vals + grow));
+      memcpy(v, &x, 16);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if ((bits >> k) & 1) v[k] = vals[grow + k];
     }
     unsigned j = 0;
 #pragma unroll
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
       }
     }
     if (HAS_VALID) {
-      const unsigned vb = static_cast<unsigned>(s_ov[r >> 6] >> (r & 63)) & ((1u << R) - 1u);
+      const unsigned vb = static_cast<unsigned>(ovw >> (r & 63)) & ((1u << R) - 1u);
       unsigned cb = 0;
       j = 0;
 #pragma unroll
@@ -229,8 +233,7 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
   }
   if (HAS_VALID) {
     __syncthreads();
-    const unsigned count = static_cast<unsigned>(a.tile_offsets[tile + 1] - out_base);
-    const unsigned q_end = bit_base + count;  // bits [bit_base, q_end) belong to this tile
+    const unsigned q_end = bit_base + tile_count;  // bits [bit_base, q_end) belong to this tile
     uint32_t* gw = a.out_validity + (out_base >> 5);
     for (unsigned i = threadIdx.x; i * 32 < q_end; i += kBlock) {
       uint32_t wv = s_bits[i];
