@@ -132,11 +132,12 @@ class Context:
     def trim(self) -> None:
         check(self.lib.b2_pool_trim(self.handle))
 
-    def h2d(self, dst_ptr: int, src_ptr: int, n: int) -> None:
-        check(self.lib.b2_memcpy_h2d(self.handle, dst_ptr, src_ptr, n, self.stream))
+    def h2d(self, dst_ptr: int, src_ptr: int, n: int, stream: Optional[int] = None) -> None:
+        """async host->device copy on `stream` (default: the context's current stream)"""
+        check(self.lib.b2_memcpy_h2d(self.handle, dst_ptr, src_ptr, n, self.stream if stream is None else stream))
 
-    def d2h(self, dst_ptr: int, src_ptr: int, n: int) -> None:
-        check(self.lib.b2_memcpy_d2h(self.handle, dst_ptr, src_ptr, n, self.stream))
+    def d2h(self, dst_ptr: int, src_ptr: int, n: int, stream: Optional[int] = None) -> None:
+        check(self.lib.b2_memcpy_d2h(self.handle, dst_ptr, src_ptr, n, self.stream if stream is None else stream))
 
 
 class DeviceBuffer:

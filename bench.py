@@ -293,18 +293,49 @@ def run_gpu(args):
     h2d_bytes = 8 * m + bm + 8 * m + 4 * m + bm
     d2h_bytes = 4 * m + bm
 
+    # The e2e leg is chunked the way the reference chunks: `indices` / `other` travel as K chunks (a
+    # ChunkedArray argument to take/add, each chunk one CallFunction-equivalent call), so the H2D copy of
+    # chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap on three streams.  `values`
+    # (the gathered column) must be fully resident before the first chunk is gathered.
+    K = max(1, args.e2e_chunks)
+    copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+    bounds = [min(m, (m * k // K) // 64 * 64) for k in range(K)] + [m]
+
     def e2e_step():
-        for hb, db in ((h_values, d_values), (h_vvalid, d_vvalid), (h_idx, d_idx), (h_other, d_other), (h_ovalid, d_ovalid)):
-            ctx.h2d(db.ptr, hb.ptr, hb.size)
+        ci, co, cs = copy_in.cuda_stream, copy_out.cuda_stream, stream.cuda_stream
+        ctx.h2d(d_values.ptr, h_values.ptr, h_values.size, ci)
+        ctx.h2d(d_vvalid.ptr, h_vvalid.ptr, h_vvalid.size, ci)
+        ev_vals = torch.cuda.Event()
+        ev_vals.record(copy_in)
+        ready = []
+        for k in range(K):
+            lo, hi = bounds[k], bounds[k + 1]
+            ctx.h2d(d_idx.ptr + 8 * lo, h_idx.ptr + 8 * lo, 8 * (hi - lo), ci)
+            ctx.h2d(d_other.ptr + 4 * lo, h_other.ptr + 4 * lo, 4 * (hi - lo), ci)
+            ctx.h2d(d_ovalid.ptr + lo // 8, h_ovalid.ptr + lo // 8, (hi - lo + 7) // 8, ci)
+            e = torch.cuda.Event()
+            e.record(copy_in)
+            ready.append(e)
         v = DeviceArray.from_pointers(ctx, pa.float64(), m, d_values.ptr, validity_ptr=d_vvalid.ptr, null_count=-1)
-        i = DeviceArray.from_pointers(ctx, pa.int64(), m, d_idx.ptr)
-        o = DeviceArray.from_pointers(ctx, pa.float32(), m, d_other.ptr, validity_ptr=d_ovalid.ptr, null_count=-1)
-        r = pipeline(v, i, o)
-        ctx.d2h(h_out.ptr, r.buffers[1].ptr, 4 * m)
-        if r.buffers[0] is not None:
-            ctx.d2h(h_outvalid.ptr, r.buffers[0].ptr, bm)
-        ctx.sync()
-        return r.null_count
+        stream.wait_event(ev_vals)
+        keep, nulls = [], 0
+        for k in range(K):
+            lo, hi = bounds[k], bounds[k + 1]
+            stream.wait_event(ready[k])
+            i = DeviceArray.from_pointers(ctx, pa.int64(), hi - lo, d_idx.ptr + 8 * lo)
+            o = DeviceArray.from_pointers(ctx, pa.float32(), hi - lo, d_other.ptr + 4 * lo, validity_ptr=d_ovalid.ptr + lo // 8,
+                                          null_count=-1)
+            r = pipeline(v, i, o)          # three C-ABI calls on `stream`
+            done = torch.cuda.Event()
+            done.record(stream)
+            copy_out.wait_event(done)
+            ctx.d2h(h_out.ptr + 4 * lo, r.buffers[1].ptr, 4 * (hi - lo), co)
+            if r.buffers[0] is not None:   # chunk validity lands at its own (byte aligned: lo % 64 == 0) position
+                ctx.d2h(h_outvalid.ptr + lo // 8, r.buffers[0].ptr, (hi - lo + 7) // 8, co)
+            keep.append(r)                 # buffers stay alive until the D2H stream drains
+            nulls += r.null_count
+        copy_out.synchronize()
+        return nulls
 
     e2e_step()
     sync_all()
@@ -360,7 +391,7 @@ def run_gpu(args):
         "cpu_baseline": {"value": cpu_rate, "unit": "rows/s", "cores": cores, "kind": "reference",
                          "sample": f"{args.cpu_sample_rows} rows x 2 steps of the same pipeline, pyarrow 24.0.0 libarrow_compute, {cores} row-range threads"},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "rows_per_gpu": m, "ms_per_step": e2e_ms},
+                "rows_per_gpu": m, "ms_per_step": e2e_ms, "chunks": K},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -377,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU for the host-buffer leg (0 = same as --rows)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the indices/other columns in the host-buffer leg")
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 25)
     args = ap.parse_args()
     if args.warmup < 3:
