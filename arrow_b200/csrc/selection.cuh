@@ -36,8 +36,9 @@ inline int64_t tiles_for(int64_t n) { return (n + kTileRows - 1) / kTileRows; }
 
 // passes 1+2: per-tile exclusive output offsets (int64[n_tiles+1], device), the output
 // length and -- when want_valid -- the number of selected rows whose output is valid.
+// chunk_rel (optional): uint16 survivors before each 512-row chunk, relative to its tile.
 int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_valid, Temp* offsets,
-                int64_t* out_length, int64_t* out_valid, cudaStream_t s);
+                int64_t* out_length, int64_t* out_valid, cudaStream_t s, Temp* chunk_rel = nullptr);
 
 FilterBitmaps make_filter_bitmaps(const B2Array* values, const B2Array* mask, int null_selection);
 

@@ -92,6 +92,78 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* counts,
   }
 }
 
+// ---- passes 1+2 fused: per-tile counts with a chained scan (decoupled look-back) ----
+// One warp per tile; tiles are claimed through an atomic ticket, so the warp owning tile t-1
+// is always running or done (no residency assumption): tile t publishes its count, then looks
+// back over up to 32 predecessor cells per step (one per lane) until it meets one that already
+// carries an inclusive prefix.  cell = flag(2 bits) << 62 | value.  Removes the single-CTA scan.
+constexpr unsigned long long kCellAgg = 1ull << 62, kCellIncl = 2ull << 62, kCellMask = (1ull << 62) - 1ull;
+
+__global__ void __launch_bounds__(kBlock) filter_count_scan_kernel(FilterBitmaps fb, int64_t n_tiles,
+                                                                   unsigned long long* cells, int64_t* offsets,
+                                                                   uint16_t* chunk_rel, int64_t* totals, bool want_valid) {
+  const unsigned lane = lane_id();
+  int64_t valid_local = 0;
+  volatile unsigned long long* vc = cells;
+  unsigned long long* ticket = cells + n_tiles;  // zero-initialised with the cells
+  while (true) {
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1ull);
+    const int64_t tile = static_cast<int64_t>(__shfl_sync(0xffffffffu, tk, 0));
+    if (tile >= n_tiles) break;
+    int64_t w0 = tile * kTileWords + 2 * lane;
+    uint64_t s0 = fb.sel(w0), s1 = fb.sel(w0 + 1);
+    int c = __popcll(s0) + __popcll(s1);
+    if (want_valid) valid_local += __popcll(s0 & fb.out_valid(w0)) + __popcll(s1 & fb.out_valid(w0 + 1));
+    const unsigned long long count = static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, c));
+    if (lane == 0) vc[tile] = (tile == 0 ? kCellIncl : kCellAgg) | count;
+    if (chunk_rel) {
+      // survivors before each 512-row chunk of the tile (lane 4k owns the first word of chunk k)
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if ((lane & 3) == 0) chunk_rel[tile * 8 + (lane >> 2)] = static_cast<uint16_t>(incl - c);
+    }
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      int64_t back = tile - 1;  // newest cell not yet folded in
+      while (true) {
+        const int64_t t = back - lane;
+        unsigned long long cell = 0;
+        if (t >= 0) {
+          do {
+            cell = vc[t];
+          } while ((cell >> 62) == 0);
+        }
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, t >= 0 && (cell >> 62) == 2);
+        // lanes up to (and including) the first inclusive cell contribute
+        const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+        unsigned long long part = (t >= 0 && (int)lane <= first) ? (cell & kCellMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (incl_mask || back - 32 < 0) break;
+        back -= 32;
+      }
+      if (lane == 0) vc[tile] = kCellIncl | (excl + count);
+    }
+    if (lane == 0) {
+      offsets[tile] = static_cast<int64_t>(excl);
+      if (tile == n_tiles - 1) {
+        offsets[n_tiles] = static_cast<int64_t>(excl + count);
+        totals[0] = static_cast<int64_t>(excl + count);
+      }
+    }
+  }
+  if (want_valid) {
+    int64_t s = block_sum<kBlock>(valid_local);
+    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(totals + 1), (unsigned long long)s);
+  }
+}
+
 // ---- pass 3: compaction ----
 template <int W>
 struct RowBytes;
@@ -116,80 +188,110 @@ struct FilterArgs {
   void* out;
   uint32_t* out_validity;  // zero-initialised, or NULL
   const int64_t* tile_offsets;
+  const uint16_t* chunk_rel;  // survivors before each 512-row chunk, relative to its tile
   int64_t n;
   bool vec_ok;
 };
 
+// 32-bit software PEXT (Hacker's Delight 7-4): bits of x selected by m, packed to the right
+__device__ __forceinline__ uint32_t pext32(uint32_t x, uint32_t m) {
+  x &= m;
+  uint32_t mk = ~m << 1;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    uint32_t mp = mk ^ (mk << 1);
+    mp ^= mp << 2;
+    mp ^= mp << 4;
+    mp ^= mp << 8;
+    mp ^= mp << 16;
+    const uint32_t mv = mp & m;
+    m = (m ^ mv) | (mv >> (1 << i));
+    const uint32_t t = x & mv;
+    x = (x ^ t) | (t >> (1 << i));
+    mk &= ~mp;
+  }
+  return x;
+}
+
+constexpr int kChunkRows = 512;  // rows per warp: 16 selection words of 32 bits
+
+// One WARP compacts one 512-row chunk (a CTA = 8 chunks = one 4096-row tile), fully
+// autonomously: no shared memory, no barrier.
+//   * lanes 0..15 each build one 32-bit selection word of the chunk (+ its output-validity
+//     word) and an exclusive prefix popcount over the 16 words (one warp scan);
+//   * per pass a lane fetches the word and prefix covering its R rows with two 32-bit
+//     shuffles, ranks its survivors with a popcount and stores them -- ranks are dense and
+//     ascending across the warp, so each store instruction writes one contiguous span;
+//   * validity: the same 16 lanes compress their 32 validity bits with a software PEXT and
+//     OR them into the (zeroed) output bitmap -- 2 RED.OR per 32 rows, off the data path.
+// Dense chunks (>= 1/8 survivors) issue all 16-byte value loads before anything else.
 // IOTA: the "value" of row r is r itself (GetTakeIndices); W = index width
 template <int W, bool HAS_VALID, bool IOTA>
 __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
   using T = typename RowBytes<W>::type;
-  constexpr int R = 16 / W;                      // rows per lane per 16-byte load
-  constexpr int kPassRows = kBlock * R;          // rows per CTA pass
-  constexpr int kPasses = kTileRows / kPassRows; // W=8: 8, W=4: 4, W=1: 1
-  static_assert(kPasses >= 1, "tile too small");
-  __shared__ uint32_t s_bits[HAS_VALID ? kTileRows / 32 + 2 : 1];
-
-  const int64_t tile = blockIdx.x;
-  const int64_t row0 = tile * kTileRows;
-  const int64_t out_base = a.tile_offsets[tile];
-  const unsigned tile_count = static_cast<unsigned>(a.tile_offsets[tile + 1] - out_base);
-  if (tile_count == 0) return;  // nothing selected in this tile (uniform for the CTA)
+  constexpr int R = 16 / W;                    // rows per lane per 16-byte load
+  constexpr int kPasses = kChunkRows / (32 * R);  // W=8: 8, W=4: 4, W=1: 1, W=16: 16
   const unsigned lane = lane_id();
+  const int64_t tile = blockIdx.x;
+  const int64_t chunk = tile * (kTileRows / kChunkRows) + (threadIdx.x >> 5);
+  const int64_t row0 = chunk * kChunkRows;
+  if (row0 >= a.n) return;
+  const int64_t tile_base = a.tile_offsets[tile];
+  const unsigned rel = a.chunk_rel[chunk];
+  const unsigned next_rel = ((threadIdx.x >> 5) == kTileRows / kChunkRows - 1)
+                                ? static_cast<unsigned>(a.tile_offsets[tile + 1] - tile_base)
+                                : a.chunk_rel[chunk + 1];
+  const unsigned chunk_count = next_rel - rel;
+  if (chunk_count == 0) return;
+  const int64_t out_base = tile_base + rel;
   const T* vals = static_cast<const T*>(a.values);
 
-  // Dense tiles (>= 1/8 of the rows survive) need every 32-byte sector anyway: issue all value
-  // loads NOW, before the selection words are known, so they overlap the bitmap round trip.
-  // Sparse tiles load only the lanes that hold a survivor (after the selection is known).
-  const bool dense = !IOTA && a.vec_ok && tile_count >= kTileRows / 8 && row0 + kTileRows <= a.n;
+  const bool dense = !IOTA && a.vec_ok && chunk_count >= kChunkRows / 8 && row0 + kChunkRows <= a.n;
   uint4 raw[kPasses];
   if (dense) {
 #pragma unroll
-    for (int p = 0; p < kPasses; ++p)
-      raw[p] = __ldcs(reinterpret_cast<const uint4*>(vals + row0 + p * kPassRows + threadIdx.x * R));
+    for (int p = 0; p < kPasses; ++p) raw[p] = __ldcs(reinterpret_cast<const uint4*>(vals + row0 + p * 32 * R + lane * R));
   }
 
-  // Every warp rebuilds the tile's 64 selection words and their exclusive prefix popcounts in
-  // registers (lane l owns words 2l, 2l+1): no shared memory, no CTA barrier on the data path;
-  // the 7 redundant bitmap reads per tile hit L1/L2.
-  const int64_t w0 = tile * kTileWords + 2 * lane;
-  const uint64_t s0 = a.fb.sel(w0), s1 = a.fb.sel(w0 + 1);
-  uint64_t ov0 = 0, ov1 = 0;
-  if (HAS_VALID) {
-    ov0 = a.fb.out_valid(w0);
-    ov1 = a.fb.out_valid(w0 + 1);
-    for (int i = threadIdx.x; i < kTileRows / 32 + 2; i += kBlock) s_bits[i] = 0;
+  // selection / validity words of this chunk (lanes 0..15) and their exclusive prefix
+  uint32_t sel = 0, ov = 0;
+  if (lane < 16) {
+    const int64_t w64 = (row0 >> 6) + (lane >> 1);
+    const uint64_t s64 = a.fb.sel(w64);
+    sel = static_cast<uint32_t>((lane & 1) ? (s64 >> 32) : s64);
+    if (HAS_VALID) {
+      const uint64_t o64 = a.fb.out_valid(w64);
+      ov = static_cast<uint32_t>((lane & 1) ? (o64 >> 32) : o64);
+    }
   }
-  const int c0 = __popcll(s0), c1 = __popcll(s1);
-  int incl = c0 + c1;
+  const int c = __popc(sel);
+  int incl = c;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
+  for (int o = 1; o < 16; o <<= 1) {
     int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
-  const unsigned pre0 = incl - c0 - c1, pre1 = pre0 + c0;
-  if (HAS_VALID) __syncthreads();  // s_bits zeroed before any atomicOr
+  const unsigned pre = incl - c;
+
+  if (HAS_VALID && c) {
+    const uint32_t bits = pext32(ov, sel);
+    const uint64_t q = static_cast<uint64_t>(out_base) + pre;  // absolute output bit position
+    uint32_t* w = a.out_validity + (q >> 5);
+    const unsigned sh = static_cast<unsigned>(q & 31);
+    if (bits << sh) atomicOr(w, bits << sh);
+    if (sh + c > 32 && (bits >> (32 - sh))) atomicOr(w + 1, bits >> (32 - sh));
+  }
 
   T* out = static_cast<T*>(a.out) + out_base;
-  const unsigned bit_base = static_cast<unsigned>(out_base & 31);
-
 #pragma unroll
   for (int p = 0; p < kPasses; ++p) {
-    const int r = p * kPassRows + threadIdx.x * R;  // row within tile, multiple of R
-    const int wi = r >> 6;                          // selection word of this lane's rows
-    // fetch word wi and its prefix from the lane that owns it (wi is warp-uniform up to R | 64)
-    const int src = wi >> 1;
-    const uint64_t sa = __shfl_sync(0xffffffffu, s0, src), sb = __shfl_sync(0xffffffffu, s1, src);
-    const unsigned pa = __shfl_sync(0xffffffffu, pre0, src), pb = __shfl_sync(0xffffffffu, pre1, src);
-    const uint64_t selw = (wi & 1) ? sb : sa;
-    const unsigned bits = static_cast<unsigned>(selw >> (r & 63)) & ((1u << R) - 1u);
-    uint64_t ovw = 0;
-    if (HAS_VALID) {
-      const uint64_t oa = __shfl_sync(0xffffffffu, ov0, src), ob = __shfl_sync(0xffffffffu, ov1, src);
-      ovw = (wi & 1) ? ob : oa;
-    }
+    const int r = p * 32 * R + lane * R;  // row within chunk
+    const uint32_t wsel = __shfl_sync(0xffffffffu, sel, r >> 5);
+    const unsigned wpre = __shfl_sync(0xffffffffu, pre, r >> 5);
+    const unsigned sh = r & 31;
+    const unsigned bits = (wsel >> sh) & ((1u << R) - 1u);
     if (bits == 0) continue;
-    const unsigned rank = ((wi & 1) ? pb : pa) + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+    const unsigned rank = wpre + __popc(wsel & ((1u << sh) - 1u));
     const int64_t grow = row0 + r;
     T v[R];
     if (IOTA) {
@@ -213,53 +315,24 @@ __global__ void __launch_bounds__(kBlock) filter_compact_kernel(FilterArgs a) {
         ++j;
       }
     }
-    if (HAS_VALID) {
-      const unsigned vb = static_cast<unsigned>(ovw >> (r & 63)) & ((1u << R) - 1u);
-      unsigned cb = 0;
-      j = 0;
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        if ((bits >> k) & 1) {
-          cb |= ((vb >> k) & 1u) << j;
-          ++j;
-        }
-      }
-      if (cb) {
-        const unsigned q = bit_base + rank;
-        atomicOr(&s_bits[q >> 5], cb << (q & 31));
-        if ((q & 31) + j > 32) atomicOr(&s_bits[(q >> 5) + 1], cb >> (32 - (q & 31)));
-      }
-    }
-  }
-  if (HAS_VALID) {
-    __syncthreads();
-    const unsigned q_end = bit_base + tile_count;  // bits [bit_base, q_end) belong to this tile
-    uint32_t* gw = a.out_validity + (out_base >> 5);
-    for (unsigned i = threadIdx.x; i * 32 < q_end; i += kBlock) {
-      uint32_t wv = s_bits[i];
-      bool full = (i * 32 >= bit_base) && ((i + 1) * 32 <= q_end);
-      if (full) gw[i] = wv;
-      else if (wv) atomicOr(&gw[i], wv);
-    }
   }
 }
 
-
-// passes 1+2; returns device tile offsets (caller frees), output length and selected-valid count
+// passes 1+2 (one kernel): device tile offsets (caller frees), output length, selected-valid count
 int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_valid,
-                       Temp* offsets, int64_t* out_length, int64_t* out_valid, cudaStream_t s) {
+                Temp* offsets, int64_t* out_length, int64_t* out_valid, cudaStream_t s, Temp* chunk_rel) {
   int64_t n_tiles = tiles_for(n);
-  Temp counts(ctx, s);
-  B2_RETURN_NOT_OK(counts.alloc(n_tiles * sizeof(uint32_t)));
+  Temp cells(ctx, s);
+  B2_RETURN_NOT_OK(cells.alloc((n_tiles + 1) * sizeof(unsigned long long)));  // + the ticket
   B2_RETURN_NOT_OK(offsets->alloc((n_tiles + 1) * sizeof(int64_t)));
+  B2_CUDA(cudaMemsetAsync(cells.ptr, 0, (n_tiles + 1) * sizeof(unsigned long long), s));
+  if (chunk_rel) B2_RETURN_NOT_OK(chunk_rel->alloc(n_tiles * 8 * sizeof(uint16_t)));
   ScalarSlot slot(ctx);
   B2_RETURN_NOT_OK(slot.zero(s));
-  int grid = grid_for(n_tiles, kWarpsPerBlock, kSMs * 8);
-  filter_count_kernel<<<grid, kBlock, 0, s>>>(fb, n_tiles, counts.as<uint32_t>(), slot.dev() + 1,
-                                              want_valid);
-  B2_LAUNCHED();
-  tile_scan_kernel<<<1, 1024, 0, s>>>(counts.as<uint32_t>(), n_tiles, offsets->as<int64_t>(),
-                                      slot.dev());
+  int grid = grid_for(n_tiles, kWarpsPerBlock, ctx->sm_count * 8);
+  filter_count_scan_kernel<<<grid, kBlock, 0, s>>>(fb, n_tiles, cells.as<unsigned long long>(),
+                                                   offsets->as<int64_t>(), chunk_rel ? chunk_rel->as<uint16_t>() : nullptr,
+                                                   slot.dev(), want_valid);
   B2_LAUNCHED();
   B2_RETURN_NOT_OK(slot.fetch(s));
   *out_length = slot.host()[0];
@@ -350,7 +423,8 @@ extern "C" int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* m
   FilterBitmaps fb = make_filter_bitmaps(values, mask, null_selection);
   Temp offsets(ctx, s);
   int64_t out_len = 0, out_valid = 0;
-  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));
+  Temp chunk_rel(ctx, s);
+  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s, &chunk_rel));
 
   Temp data(ctx, s), bits(ctx, s);
   B2_RETURN_NOT_OK(data.alloc(static_cast<size_t>(out_len) * width));
@@ -365,6 +439,7 @@ extern "C" int b2_filter(B2Context* ctx, const B2Array* values, const B2Array* m
     a.out = data.ptr;
     a.out_validity = bits.as<uint32_t>();
     a.tile_offsets = offsets.as<int64_t>();
+    a.chunk_rel = chunk_rel.as<uint16_t>();
     a.n = n;
     a.vec_ok = aligned_to(a.values, 16);
     B2_RETURN_NOT_OK(launch_compact<false>(width, has_valid, a, tiles_for(n), s));
@@ -395,7 +470,8 @@ extern "C" int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_s
   FilterBitmaps fb = make_filter_bitmaps(nullptr, mask, null_selection);
   Temp offsets(ctx, s);
   int64_t out_len = 0, out_valid = 0;
-  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s));
+  Temp chunk_rel(ctx, s);
+  B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, has_valid, &offsets, &out_len, &out_valid, s, &chunk_rel));
   Temp data(ctx, s), bits(ctx, s);
   B2_RETURN_NOT_OK(data.alloc(static_cast<size_t>(out_len) * width));
   if (has_valid) {
@@ -409,6 +485,7 @@ extern "C" int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_s
     a.out = data.ptr;
     a.out_validity = bits.as<uint32_t>();
     a.tile_offsets = offsets.as<int64_t>();
+    a.chunk_rel = chunk_rel.as<uint16_t>();
     a.n = n;
     a.vec_ok = false;
     B2_RETURN_NOT_OK(launch_compact<true>(width, has_valid, a, tiles_for(n), s));

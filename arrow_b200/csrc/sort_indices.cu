@@ -36,9 +36,9 @@ namespace b2 {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u;
 
@@ -201,27 +201,33 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_kernel(OnesweepArgs<K> 
   extern __shared__ __align__(16) uint8_t smem[];
   K* s_keys = reinterpret_cast<K*>(smem);
   uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
-  uint32_t* s_cnt = s_idx + kSortTile;        // [warps][256]
+  uint32_t* s_cnt = s_idx + kSortTile;            // [warps][256]
   uint32_t* s_bin = s_cnt + kSortWarps * kRadix;  // [256] local exclusive bin offsets
-  uint32_t* s_gbase = s_bin + kRadix;         // [256] global base - local bin offset
+  uint32_t* s_gbase = s_bin + kRadix;             // [256] global base - local bin offset
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_warp_tot[kSortWarps];
+  __shared__ uint32_t s_warp_tot[kRadix / 32];
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-#pragma unroll
-  for (int i = 0; i < kSortWarps; ++i) s_cnt[i * kRadix + tid] = 0;
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) s_cnt[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * kSortTile;
   const uint32_t tile_n = (a.n - base) < (uint32_t)kSortTile ? (a.n - base) : (uint32_t)kSortTile;
 
-  // warp-striped load: item j of lane l is element warp*512 + j*32 + l of the tile
+  // warp-striped loads of keys AND indices up front: item j of lane l is element
+  // warp*(32*ITEMS) + j*32 + l of the tile; 2*ITEMS independent requests per lane in flight
   K key[kSortItems];
+  uint32_t idxv[kSortItems];
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
-    uint32_t i = warp * (32 * kSortItems) + j * 32 + lane;
+    const uint32_t i = warp * (32 * kSortItems) + j * 32 + lane;
     key[j] = i < tile_n ? __ldcs(a.keys_in + base + i) : ~K(0);
+  }
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint32_t i = warp * (32 * kSortItems) + j * 32 + lane;
+    idxv[j] = (i < tile_n && a.idx_in) ? __ldcs(a.idx_in + base + i) : base + i;
   }
   // rank within the warp's segment, in element order (=> stable)
   uint32_t* wc = s_cnt + warp * kRadix;
@@ -243,66 +249,61 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_kernel(OnesweepArgs<K> 
   }
   __syncthreads();
 
-  // thread d owns digit d: exclusive scan over warps, tile count, look-back
-  uint32_t run = 0;
+  // threads 0..255 each own one digit: exclusive scan over warps, tile count, look-back
+  uint32_t run = 0, count = 0, incl = 0;
+  if (tid < kRadix) {
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) {
-    uint32_t c = s_cnt[w * kRadix + tid];
-    s_cnt[w * kRadix + tid] = run;
-    run += c;
-  }
-  uint32_t count = run;
-  if (tid == kRadix - 1) count -= (kSortTile - tile_n);  // padding keys are all-ones
-  volatile uint32_t* lb = a.lookback;
-  if (tile == 0) lb[tid] = kFlagIncl | count;
-  else lb[(size_t)tile * kRadix + tid] = kFlagAgg | count;
-
-  // block exclusive scan of `run` (padding included: it only occupies the tail of bin 255)
-  uint32_t incl = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp_tot[warp] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-#pragma unroll
-  for (int w = 0; w < kSortWarps; ++w)
-    if (w < (int)warp) woff += s_warp_tot[w];
-  const uint32_t bin_off = woff + incl - run;
-  s_bin[tid] = bin_off;
-
-  uint32_t excl = 0;
-  if (tile > 0) {
-    int64_t t = (int64_t)tile - 1;
-    while (true) {
-      uint32_t cell = lb[(size_t)t * kRadix + tid];
-      if ((cell >> 30) == 0) continue;  // predecessor not published yet
-      excl += cell & kValMask;
-      if ((cell >> 30) == 2) break;
-      --t;
+    for (int w = 0; w < kSortWarps; ++w) {
+      uint32_t c = s_cnt[w * kRadix + tid];
+      s_cnt[w * kRadix + tid] = run;
+      run += c;
     }
-    lb[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
+    count = run;
+    if (tid == kRadix - 1) count -= (kSortTile - tile_n);  // padding keys are all-ones
+    volatile uint32_t* lb = a.lookback;
+    if (tile == 0) lb[tid] = kFlagIncl | count;
+    else lb[(size_t)tile * kRadix + tid] = kFlagAgg | count;
+    // block exclusive scan of `run` over the 256 digits (padding only occupies the tail of bin 255)
+    incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
   }
-  s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
+  __syncthreads();
+  if (tid < kRadix) {
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kRadix / 32; ++w)
+      if (w < (int)warp) woff += s_warp_tot[w];
+    const uint32_t bin_off = woff + incl - run;
+    s_bin[tid] = bin_off;
+    uint32_t excl = 0;
+    if (tile > 0) {
+      volatile uint32_t* lb = a.lookback;
+      int64_t t = (int64_t)tile - 1;
+      while (true) {
+        uint32_t cell = lb[(size_t)t * kRadix + tid];
+        if ((cell >> 30) == 0) continue;  // predecessor not published yet
+        excl += cell & kValMask;
+        if ((cell >> 30) == 2) break;
+        --t;
+      }
+      lb[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
+    }
+    s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
+  }
   __syncthreads();
 
-  // stage keys in digit order
+  // stage keys and indices in digit order
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const unsigned digit = static_cast<unsigned>(key[j] >> a.shift) & (kRadix - 1);
     const uint32_t pos = s_bin[digit] + wc[digit] + rank[j];
     s_keys[pos] = key[j];
-    rank[j] = static_cast<uint16_t>(pos);
-  }
-  // stage indices the same way
-#pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
-    uint32_t i = warp * (32 * kSortItems) + j * 32 + lane;
-    uint32_t v = 0;
-    if (i < tile_n) v = a.idx_in ? __ldcs(a.idx_in + base + i) : base + i;
-    s_idx[rank[j]] = v;
+    s_idx[pos] = idxv[j];
   }
   __syncthreads();
   // contiguous runs out
