@@ -17,6 +17,7 @@
 
 #include "bitmap.h"
 #include "hash_table.cuh"
+#include "groupby_partitioned.cuh"
 
 namespace b2 {
 
@@ -155,7 +156,12 @@ struct B2GroupBySumCount {
   FusedTable table{};
   uint64_t cap = 0;
   uint64_t groups = 0;
+  int64_t hint = 0;  // expected number of groups (0 = unknown); refined after every chunk
 };
+
+constexpr int64_t kPartMinRows = 1ll << 21;  // below this the plain atomic path is cheaper than 5 launches
+template <typename V>
+static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, const B2Array* values, cudaStream_t s);
 
 static int fused_alloc(B2Context* ctx, uint64_t cap, FusedTable* t, cudaStream_t s) {
   void* p;
@@ -209,6 +215,7 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
   const V* vdata = static_cast<const V*>(values->data) + values->offset;
   BitmapReader kv(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
   BitmapReader vv(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  if (n >= kPartMinRows) return fused_consume_partitioned<V>(g, keys, values, s);
   if (!g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
   for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
     const int64_t cn = n - row0 < kChunkRows ? n - row0 : kChunkRows;
@@ -239,6 +246,121 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
   return B2_OK;
 }
 
+// ---- partitioned path (groupby_partitioned.cuh) -------------------------------------------------
+
+template <typename V, int KW>
+static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, cudaStream_t s,
+                                 unsigned long long* d_counters) {
+  B2Context* ctx = g->ctx;
+  constexpr bool kFloat = std::is_floating_point<V>::value;
+  FusedTableRef tref{g->table.slots, g->table.mask};
+  const int pre_grid = ctx->sm_count * 4;
+  if (passes == 0) {
+    preagg_kernel<true, kFloat, V, KW><<<pre_grid, kBlock, 0, s>>>(raw, Tuples{}, cn, tref, d_counters);
+    B2_LAUNCHED();
+    return B2_OK;
+  }
+  Temp hist(ctx, s), dbase(ctx, s), lookback(ctx, s);
+  Temp ka(ctx, s), va(ctx, s), fa(ctx, s), kb(ctx, s), vb(ctx, s), fb(ctx, s);
+  B2_RETURN_NOT_OK(hist.alloc(sizeof(unsigned long long) * 2 * kPartRadix));
+  B2_RETURN_NOT_OK(dbase.alloc(sizeof(uint32_t) * 2 * kPartRadix));
+  B2_CUDA(cudaMemsetAsync(hist.ptr, 0, sizeof(unsigned long long) * 2 * kPartRadix, s));
+  part_hist_kernel<KW><<<grid_for(cn, kBlock * 16, ctx->sm_count * 8), kBlock, 0, s>>>(raw, cn, passes, hist.as<unsigned long long>());
+  B2_LAUNCHED();
+  part_scan_kernel<<<passes, kPartRadix, 0, s>>>(hist.as<unsigned long long>(), dbase.as<uint32_t>());
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(ka.alloc(8 * (size_t)cn));
+  B2_RETURN_NOT_OK(va.alloc(8 * (size_t)cn));
+  B2_RETURN_NOT_OK(fa.alloc((size_t)cn));
+  if (passes > 1) {
+    B2_RETURN_NOT_OK(kb.alloc(8 * (size_t)cn));
+    B2_RETURN_NOT_OK(vb.alloc(8 * (size_t)cn));
+    B2_RETURN_NOT_OK(fb.alloc((size_t)cn));
+  }
+  const uint32_t n_tiles = (uint32_t)((cn + kPartTile - 1) / kPartTile);
+  const size_t lb_bytes = (size_t)n_tiles * kPartRadix * sizeof(uint32_t) + 256;
+  B2_RETURN_NOT_OK(lookback.alloc(lb_bytes));
+  constexpr size_t smem = part_smem_bytes();
+  PartArgs a;
+  a.raw = raw;
+  a.n = (uint32_t)cn;
+  a.lookback = lookback.as<uint32_t>();
+  a.ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles * kPartRadix * sizeof(uint32_t));
+  // pass 1: user columns -> tuples A, ordered by hash bits 0..7
+  B2_CUDA(cudaMemsetAsync(lookback.ptr, 0, lb_bytes, s));
+  a.in = Tuples{};
+  a.out = Tuples{ka.as<unsigned long long>(), va.as<unsigned long long>(), fa.as<uint8_t>()};
+  a.shift = 0;
+  a.digit_base = dbase.as<uint32_t>();
+  B2_CUDA(cudaFuncSetAttribute(part_pass_kernel<true, V, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  part_pass_kernel<true, V, KW><<<n_tiles, kPartThreads, smem, s>>>(a);
+  B2_LAUNCHED();
+  Tuples sorted = a.out;
+  if (passes > 1) {  // pass 2: A -> B, ordered by (hash bits 8..15, hash bits 0..7)
+    B2_CUDA(cudaMemsetAsync(lookback.ptr, 0, lb_bytes, s));
+    a.in = a.out;
+    a.out = Tuples{kb.as<unsigned long long>(), vb.as<unsigned long long>(), fb.as<uint8_t>()};
+    a.shift = 8;
+    a.digit_base = dbase.as<uint32_t>() + kPartRadix;
+    B2_CUDA(cudaFuncSetAttribute(part_pass_kernel<false, int64_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    part_pass_kernel<false, int64_t, 8><<<n_tiles, kPartThreads, smem, s>>>(a);
+    B2_LAUNCHED();
+    sorted = a.out;
+  }
+  preagg_kernel<false, kFloat, int64_t, 8><<<pre_grid, kBlock, 0, s>>>(RawColumns{}, sorted, cn, tref, d_counters);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
+template <typename V>
+static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, const B2Array* values, cudaStream_t s) {
+  B2Context* ctx = g->ctx;
+  const int kw = type_width(g->key_type);
+  const int64_t n = keys->length;
+  RawColumns raw;
+  raw.keys = static_cast<const char*>(keys->data) + keys->offset * kw;
+  raw.values = static_cast<const V*>(values->data) + values->offset;
+  raw.key_valid = BitmapReader(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
+  raw.val_valid = BitmapReader(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  if (!g->table.slots) {
+    // room for the hinted groups plus one full chunk of never-seen keys at load <= 1/2
+    uint64_t want = next_pow2(2 * ((uint64_t)(g->hint > 0 ? g->hint : 0) + (uint64_t)(n < kChunkRows ? n : kChunkRows)));
+    if (want > g->cap) g->cap = want;
+    B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
+  }
+  for (int64_t row0 = 0; row0 < n;) {
+    // capacity guarantee: a chunk can add at most `cn` groups, keep groups + cn <= cap / 2
+    int64_t headroom = (int64_t)(g->cap / 2) - (int64_t)g->groups;
+    const int64_t remaining = n - row0;
+    if (headroom < (remaining < (1 << 22) ? remaining : (1 << 22))) {
+      B2_RETURN_NOT_OK(fused_grow(g, next_pow2(2 * (g->groups + (uint64_t)(remaining < kChunkRows ? remaining : kChunkRows))), s));
+      headroom = (int64_t)(g->cap / 2) - (int64_t)g->groups;
+    }
+    int64_t cn = remaining < kChunkRows ? remaining : kChunkRows;
+    if (cn > headroom) cn = headroom;
+    const int64_t est = g->hint > 0 ? g->hint : (g->groups > 0 ? (int64_t)g->groups : (1ll << 40));
+    const int passes = est <= 1500 ? 0 : (est <= 400000 ? 1 : 2);
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    raw.row0 = row0;
+    unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
+    int st;
+    switch (kw) {
+      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc); break;
+      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc); break;
+      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc); break;
+      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc); break;
+    }
+    if (st != B2_OK) return st;
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    if (slot.host()[0] != 0) return set_error(B2_UNKNOWN_ERROR, "group-by table overflow (%lld entries lost)", (long long)slot.host()[0]);
+    g->groups += static_cast<uint64_t>(slot.host()[1]);
+    if (g->hint <= 0 || (int64_t)g->groups > g->hint) g->hint = (int64_t)g->groups;  // measured cardinality
+    row0 += cn;
+  }
+  return B2_OK;
+}
+
 extern "C" {
 
 int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_type, int64_t expected_groups,
@@ -256,6 +378,7 @@ int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_t
   // the table is allocated and initialised lazily on the first consume, on the CALLER's stream:
   // an init kernel queued on the context stream would race with a consume on another stream
   g->cap = cap;
+  g->hint = expected_groups;
   *out = g;
   return B2_OK;
 }
