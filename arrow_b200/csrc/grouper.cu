@@ -60,18 +60,19 @@ __device__ __forceinline__ uint64_t encode_row(const KeyLayout& L, const KeyColu
   return enc;
 }
 
+// 16-byte slots {key, id, first_row}: the probe, the id read and the first-occurrence atomicMin of
+// a row all land in ONE 32-byte sector (three separate arrays cost three random DRAM accesses).
 struct GrouperTable {
-  unsigned long long* keys;  // [cap + 2]
-  uint32_t* ids;             // [cap + 2]
-  uint32_t* first_row;       // [cap + 2]
+  unsigned long long* slots;  // [(cap + 2) * 2]: word 0 = key, word 1 = {id, first_row}
   uint64_t mask;
+  __host__ __device__ uint32_t* id_ptr(uint64_t slot) const { return reinterpret_cast<uint32_t*>(slots + slot * 2 + 1); }
+  __host__ __device__ uint32_t* first_row_ptr(uint64_t slot) const { return id_ptr(slot) + 1; }
 };
 
 __global__ void __launch_bounds__(kBlock) grouper_init_kernel(GrouperTable t) {
   for (uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x; i < t.mask + 3; i += (uint64_t)gridDim.x * kBlock) {
-    t.keys[i] = kEmptyKey;
-    t.ids[i] = kNoId;
-    t.first_row[i] = 0xffffffffu;
+    t.slots[i * 2] = kEmptyKey;
+    t.slots[i * 2 + 1] = ~0ull;  // id = kNoId, first_row = 0xffffffff
   }
 }
 
@@ -85,15 +86,15 @@ __global__ void __launch_bounds__(kBlock) grouper_probe_kernel(KeyLayout L, KeyC
     int64_t slot;
     if (INSERT) {
       bool inserted;
-      slot = table_find_or_insert(t.keys, t.mask, 1, enc, is_null, &inserted);
+      slot = table_find_or_insert(t.slots, t.mask, 2, enc, is_null, &inserted);
       if (slot < 0) {
         *overflow = 1;
         row_slot[i] = kNoId;
         continue;
       }
-      if (t.ids[slot] == kNoId) atomicMin(&t.first_row[slot], static_cast<uint32_t>(i));
+      if (*t.id_ptr(slot) == kNoId) atomicMin(t.first_row_ptr(slot), static_cast<uint32_t>(i));
     } else {
-      slot = table_find(t.keys, t.mask, 1, enc, is_null);
+      slot = table_find(t.slots, t.mask, 2, enc, is_null);
     }
     row_slot[i] = slot < 0 ? kNoId : static_cast<uint32_t>(slot);
   }
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kBlock) grouper_flag_kernel(int64_t n, Grouper
     bool f = false;
     if (i < n) {
       uint32_t s = row_slot[i];
-      f = t.ids[s] == kNoId && t.first_row[s] == static_cast<uint32_t>(i);
+      f = *t.id_ptr(s) == kNoId && *t.first_row_ptr(s) == static_cast<uint32_t>(i);
     }
     unsigned word = __ballot_sync(0xffffffffu, f);
     if (lane_id() == 0) flags[w] = word;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kBlock) grouper_assign_kernel(KeyLayout L, Key
     const uint32_t id = base_id + static_cast<uint32_t>(vbase + rank);
     bool is_null;
     uint64_t enc = encode_row(L, c, row, &is_null);
-    t.ids[row_slot[row]] = id;
+    *t.id_ptr(row_slot[row]) = id;
     uniq_keys[id] = enc;
     uniq_null[id] = is_null ? 1 : 0;
   }
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kBlock) grouper_gather_kernel(int64_t n, Group
     bool ok = false;
     if (i < n) {
       uint32_t s = row_slot[i];
-      uint32_t id = s == kNoId ? kNoId : t.ids[s];
+      uint32_t id = s == kNoId ? kNoId : *t.id_ptr(s);
       ok = id != kNoId;
       out[i] = ok ? id : 0u;
     }
@@ -193,12 +194,12 @@ __global__ void __launch_bounds__(kBlock) grouper_rehash_kernel(GrouperTable t, 
                                                                 int64_t* overflow) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < n_groups; g += gridDim.x * kBlock) {
     bool inserted;
-    int64_t slot = table_find_or_insert(t.keys, t.mask, 1, uniq_keys[g], uniq_null[g] != 0, &inserted);
+    int64_t slot = table_find_or_insert(t.slots, t.mask, 2, uniq_keys[g], uniq_null[g] != 0, &inserted);
     if (slot < 0) {
       *overflow = 1;
       continue;
     }
-    t.ids[slot] = g;
+    *t.id_ptr(slot) = g;
   }
 }
 
@@ -257,9 +258,7 @@ struct B2Grouper {
 };
 
 static void grouper_free_table(B2Grouper* g, cudaStream_t s) {
-  if (g->table.keys) g->ctx->free(g->table.keys, s);
-  if (g->table.ids) g->ctx->free(g->table.ids, s);
-  if (g->table.first_row) g->ctx->free(g->table.first_row, s);
+  if (g->table.slots) g->ctx->free(g->table.slots, s);
   g->table = GrouperTable{};
   g->cap = 0;
 }
@@ -267,12 +266,8 @@ static void grouper_free_table(B2Grouper* g, cudaStream_t s) {
 static int grouper_alloc_table(B2Grouper* g, uint64_t cap, cudaStream_t s) {
   GrouperTable t;
   void* p;
-  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 8, &p, s));
-  t.keys = static_cast<unsigned long long*>(p);
-  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 4, &p, s));
-  t.ids = static_cast<uint32_t*>(p);
-  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 4, &p, s));
-  t.first_row = static_cast<uint32_t*>(p);
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 2) * 16, &p, s));
+  t.slots = static_cast<unsigned long long*>(p);
   t.mask = cap - 1;
   grouper_init_kernel<<<grid_for((int64_t)cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(t);
   B2_LAUNCHED();
