@@ -250,10 +250,10 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
 
 template <typename V, int KW>
 static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, cudaStream_t s,
-                                 unsigned long long* d_counters) {
+                                 unsigned long long* d_counters, unsigned long long* ovf_pairs, unsigned int* ovf_counts) {
   B2Context* ctx = g->ctx;
   constexpr bool kFloat = std::is_floating_point<V>::value;
-  FusedTableRef tref{g->table.slots, g->table.mask};
+  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts};
   const int pre_grid = ctx->sm_count * 4;
   if (passes == 0) {
     preagg_kernel<true, kFloat, V, KW><<<pre_grid, kBlock, 0, s>>>(raw, Tuples{}, cn, tref, d_counters);
@@ -323,38 +323,56 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
   raw.key_valid = BitmapReader(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
   raw.val_valid = BitmapReader(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
   if (!g->table.slots) {
-    // room for the hinted groups plus one full chunk of never-seen keys at load <= 1/2
-    uint64_t want = next_pow2(2 * ((uint64_t)(g->hint > 0 ? g->hint : 0) + (uint64_t)(n < kChunkRows ? n : kChunkRows)));
+    uint64_t want = next_pow2(2 * (uint64_t)(g->hint > (1 << 19) ? g->hint : (1 << 19)));
     if (want > g->cap) g->cap = want;
     B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
   }
+  constexpr bool kFloat = std::is_floating_point<V>::value;
   for (int64_t row0 = 0; row0 < n;) {
-    // capacity guarantee: a chunk can add at most `cn` groups, keep groups + cn <= cap / 2
-    int64_t headroom = (int64_t)(g->cap / 2) - (int64_t)g->groups;
     const int64_t remaining = n - row0;
-    if (headroom < (remaining < (1 << 22) ? remaining : (1 << 22))) {
-      B2_RETURN_NOT_OK(fused_grow(g, next_pow2(2 * (g->groups + (uint64_t)(remaining < kChunkRows ? remaining : kChunkRows))), s));
-      headroom = (int64_t)(g->cap / 2) - (int64_t)g->groups;
-    }
-    int64_t cn = remaining < kChunkRows ? remaining : kChunkRows;
-    if (cn > headroom) cn = headroom;
+    const int64_t cn = remaining < kChunkRows ? remaining : kChunkRows;
     const int64_t est = g->hint > 0 ? g->hint : (g->groups > 0 ? (int64_t)g->groups : (1ll << 40));
     const int passes = est <= 1500 ? 0 : (est <= 400000 ? 1 : 2);
+    // parking space for entries that hit the probe limit (worst case: every row of the chunk)
+    Temp ovf_pairs(ctx, s), ovf_counts(ctx, s);
+    B2_RETURN_NOT_OK(ovf_pairs.alloc(16 * (size_t)cn));
+    B2_RETURN_NOT_OK(ovf_counts.alloc(4 * (size_t)cn));
     ScalarSlot slot(ctx);
     B2_RETURN_NOT_OK(slot.zero(s));
     raw.row0 = row0;
     unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
     int st;
     switch (kw) {
-      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc); break;
-      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc); break;
-      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc); break;
-      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc); break;
+      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
+      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
+      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
+      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
     }
     if (st != B2_OK) return st;
     B2_RETURN_NOT_OK(slot.fetch(s));
-    if (slot.host()[0] != 0) return set_error(B2_UNKNOWN_ERROR, "group-by table overflow (%lld entries lost)", (long long)slot.host()[0]);
+    int64_t parked = slot.host()[0];
     g->groups += static_cast<uint64_t>(slot.host()[1]);
+    while (parked > 0) {
+      // the table filled up inside this chunk: grow it and replay the parked (key, sum, count) entries
+      B2_RETURN_NOT_OK(fused_grow(g, next_pow2(4 * (g->groups + (uint64_t)parked)), s));
+      Temp p2(ctx, s), c2(ctx, s);
+      B2_RETURN_NOT_OK(p2.alloc(16 * (size_t)parked));
+      B2_RETURN_NOT_OK(c2.alloc(4 * (size_t)parked));
+      FusedTableRef tref{g->table.slots, g->table.mask, p2.as<unsigned long long>(), c2.as<unsigned int>()};
+      B2_RETURN_NOT_OK(slot.zero(s));
+      replay_overflow_kernel<kFloat><<<grid_for(parked, kBlock * 4, ctx->sm_count * 8), kBlock, 0, s>>>(
+          tref, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), parked, dc);
+      B2_LAUNCHED();
+      B2_RETURN_NOT_OK(slot.fetch(s));
+      g->groups += static_cast<uint64_t>(slot.host()[1]);
+      const int64_t again = slot.host()[0];
+      if (again > 0) {  // (only if the grown table is somehow still too small) keep the remainder parked
+        B2_CUDA(cudaMemcpyAsync(ovf_pairs.ptr, p2.ptr, 16 * (size_t)again, cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(cudaMemcpyAsync(ovf_counts.ptr, c2.ptr, 4 * (size_t)again, cudaMemcpyDeviceToDevice, s));
+      }
+      parked = again;
+    }
+    if (g->groups * 2 > g->cap) B2_RETURN_NOT_OK(fused_grow(g, next_pow2(g->groups * 4), s));
     if (g->hint <= 0 || (int64_t)g->groups > g->hint) g->hint = (int64_t)g->groups;  // measured cardinality
     row0 += cn;
   }

@@ -102,7 +102,7 @@ struct PartArgs {
 };
 
 constexpr size_t part_smem_bytes() {
-  return kPartTile * 8 * 2 + kPartTile + kPartWarps * kPartRadix * 4 + 2 * kPartRadix * 4;
+  return kPartTile * 8 * 2 + kPartTile + 3 * kPartRadix * 4;
 }
 
 template <bool FIRST, typename V, int KW>
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
   unsigned long long* s_vals = s_keys + kPartTile;
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_vals + kPartTile);  // [warps][256]
-  uint32_t* s_bin = s_cnt + kPartWarps * kPartRadix;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_vals + kPartTile);  // [256] rows per bin in this tile
+  uint32_t* s_bin = s_cnt + kPartRadix;
   uint32_t* s_gbase = s_bin + kPartRadix;
   uint8_t* s_flags = reinterpret_cast<uint8_t*>(s_gbase + kPartRadix);
   __shared__ uint32_t s_tile;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-  for (int i = tid; i < kPartWarps * kPartRadix; i += kPartThreads) s_cnt[i] = 0;
+  for (int i = tid; i < kPartRadix; i += kPartThreads) s_cnt[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * kPartTile;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
     const uint32_t i = warp * (32 * kPartItems) + j * 32 + lane;
     key[j] = ~0ull;
     val[j] = 0;
-    flg[j] = 4u;  // padding marker: sorts into bin 255 behind every real row
+    flg[j] = 4u;  // padding marker
     if (i < tile_n) {
       if (FIRST) {
         const int64_t r = a.raw.row0 + base + i;
@@ -150,40 +150,24 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
       }
     }
   }
-  uint32_t* wc = s_cnt + warp * kPartRadix;
-  uint16_t rank[kPartItems];
+  // Rank inside the tile's bin with ONE returning shared-memory atomic per row
+  // (ATOMS.ADD.u32: 0.17 cycles/lane/SM measured, vs 1.83 for MATCH.ANY -- profiles/smem_probe_r01.txt).
+  // The order of rows inside a partition is irrelevant for grouping, so no stable ranking is needed.
+  uint32_t rank[kPartItems];
   unsigned dig[kPartItems];
-  const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int j = 0; j < kPartItems; ++j) {
-    dig[j] = (flg[j] & 4u) ? (kPartRadix - 1) : part_digit(key[j], flg[j], a.shift);
-    // padding must rank after real rows of bin 255: it does, padding rows are the last elements of the tile
-    const unsigned peers = __match_any_sync(0xffffffffu, dig[j]);
-    const int leader = __ffs(peers) - 1;
-    unsigned prev = 0;
-    if ((int)lane == leader) {
-      prev = wc[dig[j]];
-      wc[dig[j]] = prev + __popc(peers);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, leader);
-    rank[j] = static_cast<uint16_t>(prev + __popc(peers & lt));
-    __syncwarp();
+    dig[j] = part_digit(key[j], flg[j], a.shift);
+    rank[j] = (flg[j] & 4u) ? 0u : atomicAdd(&s_cnt[dig[j]], 1u);  // padding rows are neither counted nor staged
   }
   __syncthreads();
 
-  uint32_t run = 0, count = 0, incl = 0;
+  uint32_t run = 0, incl = 0;
   if (tid < kPartRadix) {
-#pragma unroll
-    for (int w = 0; w < kPartWarps; ++w) {
-      uint32_t c = s_cnt[w * kPartRadix + tid];
-      s_cnt[w * kPartRadix + tid] = run;
-      run += c;
-    }
-    count = run;
-    if (tid == kPartRadix - 1) count -= (kPartTile - tile_n);
+    run = s_cnt[tid];
     volatile uint32_t* lb = a.lookback;
-    if (tile == 0) lb[tid] = kPFlagIncl | count;
-    else lb[(size_t)tile * kPartRadix + tid] = kPFlagAgg | count;
+    if (tile == 0) lb[tid] = kPFlagIncl | run;
+    else lb[(size_t)tile * kPartRadix + tid] = kPFlagAgg | run;
     incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -211,14 +195,15 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
         if ((cell >> 30) == 2) break;
         --t;
       }
-      lb[(size_t)tile * kPartRadix + tid] = kPFlagIncl | (excl + count);
+      lb[(size_t)tile * kPartRadix + tid] = kPFlagIncl | (excl + run);
     }
     s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kPartItems; ++j) {
-    const uint32_t pos = s_bin[dig[j]] + wc[dig[j]] + rank[j];
+    if (flg[j] & 4u) continue;
+    const uint32_t pos = s_bin[dig[j]] + rank[j];
     s_keys[pos] = key[j];
     s_vals[pos] = val[j];
     s_flags[pos] = static_cast<uint8_t>(flg[j]);
@@ -246,6 +231,10 @@ constexpr int kPreProbe = 48;
 struct FusedTableRef {
   unsigned long long* slots;
   uint64_t mask;
+  // entries that met a full neighbourhood (probe limit) are parked here and replayed by the host
+  // after it has grown the table: {key, sum bits} pairs + {count | key_null << 31}
+  unsigned long long* ovf_pairs;
+  unsigned int* ovf_counts;
 };
 
 template <bool IS_FLOAT>
@@ -254,7 +243,10 @@ __device__ __forceinline__ void global_accumulate(const FusedTableRef& t, unsign
   bool inserted;
   int64_t slot = table_find_or_insert(t.slots, t.mask, 4, key, key_null, &inserted);
   if (slot < 0) {
-    atomicAdd(&counters[0], 1ull);  // capacity guarantee violated: reported as an error by the host
+    const unsigned long long i = atomicAdd(&counters[0], 1ull);
+    t.ovf_pairs[2 * i] = key;
+    t.ovf_pairs[2 * i + 1] = sum_bits;
+    t.ovf_counts[i] = count | (key_null ? 0x80000000u : 0u);
     return;
   }
   if (inserted) atomicAdd(&counters[1], 1ull);
@@ -270,6 +262,9 @@ template <bool RAW, bool IS_FLOAT, typename V, int KW>
 __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples in, int64_t n, FusedTableRef table,
                                                         unsigned long long* counters) {
   __shared__ unsigned long long s_keys[kPreSlots + 2];  // +2: the empty-pattern key and the null key
+  // integer sums live as (lo, hi) 32-bit halves updated with two native ATOMS.ADD.u32 and an explicit
+  // carry: a 64-bit shared atomicAdd is a CAS loop on this part (0.64 cycles/lane spread, 40 when
+  // contended on one key -- profiles/smem_probe_r01.txt); doubles keep the CAS-based atomicAdd
   __shared__ unsigned long long s_sums[kPreSlots + 2];
   __shared__ unsigned int s_counts[kPreSlots + 2];
   __shared__ uint8_t s_used[kPreSlots + 2];  // slot touched (a group can exist with count 0)
@@ -329,8 +324,15 @@ __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples i
       }
       s_used[slot] = 1;
       if (f & 1u) {
-        if (IS_FLOAT) atomicAdd(reinterpret_cast<double*>(&s_sums[slot]), __longlong_as_double((long long)vb));
-        else atomicAdd(&s_sums[slot], vb);
+        if (IS_FLOAT) {
+          atomicAdd(reinterpret_cast<double*>(&s_sums[slot]), __longlong_as_double((long long)vb));
+        } else {
+          unsigned int* half = reinterpret_cast<unsigned int*>(&s_sums[slot]);  // little endian: [0] = lo, [1] = hi
+          const unsigned int lo = static_cast<unsigned int>(vb), hi = static_cast<unsigned int>(vb >> 32);
+          const unsigned int old = atomicAdd(half, lo);
+          const unsigned int carry = (old + lo) < old ? 1u : 0u;
+          if (hi + carry) atomicAdd(half + 1, hi + carry);
+        }
         atomicAdd(&s_counts[slot], 1u);
       }
     }
@@ -344,6 +346,14 @@ __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples i
     }
     __syncthreads();
   }
+}
+
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(kBlock) replay_overflow_kernel(FusedTableRef table, const unsigned long long* pairs,
+                                                                 const unsigned int* counts, int64_t n,
+                                                                 unsigned long long* counters) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    global_accumulate<IS_FLOAT>(table, pairs[2 * i], (counts[i] >> 31) != 0, pairs[2 * i + 1], counts[i] & 0x7fffffffu, counters);
 }
 
 }  // namespace b2
