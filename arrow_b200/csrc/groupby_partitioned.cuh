@@ -26,10 +26,10 @@
 
 namespace b2 {
 
-constexpr int kPartThreads = 512;
+constexpr int kPartThreads = 256;
 constexpr int kPartWarps = kPartThreads / 32;
 constexpr int kPartItems = 8;
-constexpr int kPartTile = kPartThreads * kPartItems;  // 4096 rows per tile
+constexpr int kPartTile = kPartThreads * kPartItems;  // 2048 rows per tile: 35 KB smem, 4 CTAs/SM
 constexpr int kPartRadix = 256;
 constexpr uint32_t kPFlagAgg = 1u << 30, kPFlagIncl = 2u << 30, kPValMask = (1u << 30) - 1u;
 
@@ -106,7 +106,7 @@ constexpr size_t part_smem_bytes() {
 }
 
 template <bool FIRST, typename V, int KW>
-__global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) {
+__global__ void __launch_bounds__(kPartThreads, 4) part_pass_kernel(PartArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
   unsigned long long* s_vals = s_keys + kPartTile;
@@ -279,61 +279,78 @@ __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples i
     __syncthreads();
     const int64_t lo = slice * kPreSlice;
     const int64_t hi = lo + kPreSlice < n ? lo + kPreSlice : n;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kBlock) {
-      unsigned long long k, vb = 0;
-      unsigned f;
-      if (RAW) {
-        const int64_t r = raw.row0 + i;
-        f = raw.key_valid.bit(r) ? 0u : 2u;
-        k = f ? 0ull : load_key_bits(raw.keys, KW, r);
-        if (raw.val_valid.bit(r)) {
-          f |= 1u;
-          vb = value_bits<V>(static_cast<const V*>(raw.values)[r]);
-        }
-      } else {
-        k = __ldcs(in.keys + i);
-        vb = __ldcs(in.vals + i);
-        f = in.flags[i];
-      }
-      int slot = -1;
-      if (f & 2u) {
-        slot = kPreSlots + 1;
-      } else if (k == kEmptyKey) {
-        slot = kPreSlots;
-      } else {
-        unsigned s = static_cast<unsigned>(hash64(k) >> 20) & (kPreSlots - 1);
-        for (int probe = 0; probe < kPreProbe; ++probe) {
-          unsigned long long cur = s_keys[s];
-          if (cur == k) {
-            slot = s;
-            break;
+    constexpr int kBatch = 8;  // rows loaded per thread before the dependent shared-memory work
+    for (int64_t b0 = lo; b0 < hi; b0 += (int64_t)kBatch * kBlock) {
+      unsigned long long kk[kBatch], vv[kBatch];
+      unsigned ff[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int64_t i = b0 + u * kBlock + threadIdx.x;
+        kk[u] = 0;
+        vv[u] = 0;
+        ff[u] = 8u;  // 8 = no row
+        if (i < hi) {
+          if (RAW) {
+            const int64_t r = raw.row0 + i;
+            unsigned f = raw.key_valid.bit(r) ? 0u : 2u;
+            kk[u] = f ? 0ull : load_key_bits(raw.keys, KW, r);
+            if (raw.val_valid.bit(r)) {
+              f |= 1u;
+              vv[u] = value_bits<V>(static_cast<const V*>(raw.values)[r]);
+            }
+            ff[u] = f;
+          } else {
+            kk[u] = __ldcs(in.keys + i);
+            vv[u] = __ldcs(in.vals + i);
+            ff[u] = in.flags[i];
           }
-          if (cur == kEmptyKey) {
-            unsigned long long old = atomicCAS(&s_keys[s], (unsigned long long)kEmptyKey, k);
-            if (old == kEmptyKey || old == k) {
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned f = ff[u];
+        if (f & 8u) continue;
+        const unsigned long long k = kk[u], vb = vv[u];
+        int slot = -1;
+        if (f & 2u) {
+          slot = kPreSlots + 1;
+        } else if (k == kEmptyKey) {
+          slot = kPreSlots;
+        } else {
+          unsigned s = static_cast<unsigned>(hash64(k) >> 20) & (kPreSlots - 1);
+          for (int probe = 0; probe < kPreProbe; ++probe) {
+            unsigned long long cur = s_keys[s];
+            if (cur == k) {
               slot = s;
               break;
             }
+            if (cur == kEmptyKey) {
+              unsigned long long old = atomicCAS(&s_keys[s], (unsigned long long)kEmptyKey, k);
+              if (old == kEmptyKey || old == k) {
+                slot = s;
+                break;
+              }
+            }
+            s = (s + 1) & (kPreSlots - 1);
           }
-          s = (s + 1) & (kPreSlots - 1);
         }
-      }
-      if (slot < 0) {  // slice holds too many distinct keys: spill this row to the global table
-        global_accumulate<IS_FLOAT>(table, k, false, vb, (f & 1u) ? 1u : 0u, counters);
-        continue;
-      }
-      s_used[slot] = 1;
-      if (f & 1u) {
-        if (IS_FLOAT) {
-          atomicAdd(reinterpret_cast<double*>(&s_sums[slot]), __longlong_as_double((long long)vb));
-        } else {
-          unsigned int* half = reinterpret_cast<unsigned int*>(&s_sums[slot]);  // little endian: [0] = lo, [1] = hi
-          const unsigned int lo = static_cast<unsigned int>(vb), hi = static_cast<unsigned int>(vb >> 32);
-          const unsigned int old = atomicAdd(half, lo);
-          const unsigned int carry = (old + lo) < old ? 1u : 0u;
-          if (hi + carry) atomicAdd(half + 1, hi + carry);
+        if (slot < 0) {  // slice holds too many distinct keys: spill this row to the global table
+          global_accumulate<IS_FLOAT>(table, k, false, vb, (f & 1u) ? 1u : 0u, counters);
+          continue;
         }
-        atomicAdd(&s_counts[slot], 1u);
+        s_used[slot] = 1;
+        if (f & 1u) {
+          if (IS_FLOAT) {
+            atomicAdd(reinterpret_cast<double*>(&s_sums[slot]), __longlong_as_double((long long)vb));
+          } else {
+            unsigned int* half = reinterpret_cast<unsigned int*>(&s_sums[slot]);  // little endian: [0] = lo, [1] = hi
+            const unsigned int lo32 = static_cast<unsigned int>(vb), hi32 = static_cast<unsigned int>(vb >> 32);
+            const unsigned int old = atomicAdd(half, lo32);
+            const unsigned int carry = (old + lo32) < old ? 1u : 0u;
+            if (hi32 + carry) atomicAdd(half + 1, hi32 + carry);
+          }
+          atomicAdd(&s_counts[slot], 1u);
+        }
       }
     }
     __syncthreads();
