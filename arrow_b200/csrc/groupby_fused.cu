@@ -157,6 +157,7 @@ struct B2GroupBySumCount {
   uint64_t cap = 0;
   uint64_t groups = 0;
   int64_t hint = 0;  // expected number of groups (0 = unknown); refined after every chunk
+  bool hint_given = false;
 };
 
 constexpr int64_t kPartMinRows = 1ll << 21;  // below this the plain atomic path is cheaper than 5 launches
@@ -250,10 +251,11 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
 
 template <typename V, int KW>
 static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, cudaStream_t s,
-                                 unsigned long long* d_counters, unsigned long long* ovf_pairs, unsigned int* ovf_counts) {
+                                 unsigned long long* d_counters, unsigned long long* ovf_pairs, unsigned int* ovf_counts,
+                                 uint64_t ovf_cap) {
   B2Context* ctx = g->ctx;
   constexpr bool kFloat = std::is_floating_point<V>::value;
-  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts};
+  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts, ovf_cap};
   const int pre_grid = ctx->sm_count * 4;
   if (passes == 0) {
     preagg_kernel<true, kFloat, V, KW><<<pre_grid, kBlock, 0, s>>>(raw, Tuples{}, cn, tref, d_counters);
@@ -328,28 +330,43 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
   }
   constexpr bool kFloat = std::is_floating_point<V>::value;
+  // Chunking.  Pre-aggregation pays off in proportion to how often a key repeats INSIDE one chunk, so
+  // chunks should be as large as memory allows (tuples: 2 x 17 B/row).  Entries that hit a full table
+  // are parked and replayed after growth; the parking area holds min(chunk, 64M) entries, so without a
+  // cardinality hint chunks stay at 64M rows (worst case fully parkable), while a caller that passes
+  // expected_groups gets one chunk of up to 2^30 rows and a capacity error only if the true cardinality
+  // exceeds the hint by more than the table slack + 64M groups inside a single chunk.
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const int64_t mem_rows = static_cast<int64_t>((free_b + (size_t)(ctx->bytes_reserved - ctx->bytes_in_use)) / 48);
+  int64_t max_chunk = g->hint_given ? ((1ll << 30) - kPartTile) : kChunkRows;
+  if (max_chunk > mem_rows) max_chunk = mem_rows > kChunkRows ? mem_rows / kPartTile * kPartTile : kChunkRows;
   for (int64_t row0 = 0; row0 < n;) {
     const int64_t remaining = n - row0;
-    const int64_t cn = remaining < kChunkRows ? remaining : kChunkRows;
+    const int64_t cn = remaining < max_chunk ? remaining : max_chunk;
+    const uint64_t ovf_cap = static_cast<uint64_t>(cn < kChunkRows ? cn : kChunkRows);
     const int64_t est = g->hint > 0 ? g->hint : (g->groups > 0 ? (int64_t)g->groups : (1ll << 40));
     const int passes = est <= 1500 ? 0 : (est <= 400000 ? 1 : 2);
     // parking space for entries that hit the probe limit (worst case: every row of the chunk)
     Temp ovf_pairs(ctx, s), ovf_counts(ctx, s);
-    B2_RETURN_NOT_OK(ovf_pairs.alloc(16 * (size_t)cn));
-    B2_RETURN_NOT_OK(ovf_counts.alloc(4 * (size_t)cn));
+    B2_RETURN_NOT_OK(ovf_pairs.alloc(16 * (size_t)ovf_cap));
+    B2_RETURN_NOT_OK(ovf_counts.alloc(4 * (size_t)ovf_cap));
     ScalarSlot slot(ctx);
     B2_RETURN_NOT_OK(slot.zero(s));
     raw.row0 = row0;
     unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
     int st;
     switch (kw) {
-      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
-      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
-      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
-      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>()); break;
+      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
     }
     if (st != B2_OK) return st;
     B2_RETURN_NOT_OK(slot.fetch(s));
+    if (slot.host()[2] != 0)
+      return set_error(B2_CAPACITY_ERROR, "group-by: %lld more groups than the table sized from expected_groups=%lld can absorb in one batch; "
+                       "pass a larger expected_groups (or 0 to let the table grow chunk by chunk)", (long long)slot.host()[2], (long long)g->hint);
     int64_t parked = slot.host()[0];
     g->groups += static_cast<uint64_t>(slot.host()[1]);
     while (parked > 0) {
@@ -358,7 +375,7 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
       Temp p2(ctx, s), c2(ctx, s);
       B2_RETURN_NOT_OK(p2.alloc(16 * (size_t)parked));
       B2_RETURN_NOT_OK(c2.alloc(4 * (size_t)parked));
-      FusedTableRef tref{g->table.slots, g->table.mask, p2.as<unsigned long long>(), c2.as<unsigned int>()};
+      FusedTableRef tref{g->table.slots, g->table.mask, p2.as<unsigned long long>(), c2.as<unsigned int>(), (uint64_t)parked};
       B2_RETURN_NOT_OK(slot.zero(s));
       replay_overflow_kernel<kFloat><<<grid_for(parked, kBlock * 4, ctx->sm_count * 8), kBlock, 0, s>>>(
           tref, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), parked, dc);
@@ -397,6 +414,7 @@ int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_t
   // an init kernel queued on the context stream would race with a consume on another stream
   g->cap = cap;
   g->hint = expected_groups;
+  g->hint_given = expected_groups > 0;
   *out = g;
   return B2_OK;
 }

@@ -26,10 +26,10 @@
 
 namespace b2 {
 
-constexpr int kPartThreads = 256;
+constexpr int kPartThreads = 512;
 constexpr int kPartWarps = kPartThreads / 32;
 constexpr int kPartItems = 8;
-constexpr int kPartTile = kPartThreads * kPartItems;  // 2048 rows per tile: 35 KB smem, 4 CTAs/SM
+constexpr int kPartTile = kPartThreads * kPartItems;  // 4096 rows per tile (2048 measured 20 % slower: shorter write runs, 2x look-back)
 constexpr int kPartRadix = 256;
 constexpr uint32_t kPFlagAgg = 1u << 30, kPFlagIncl = 2u << 30, kPValMask = (1u << 30) - 1u;
 
@@ -106,7 +106,7 @@ constexpr size_t part_smem_bytes() {
 }
 
 template <bool FIRST, typename V, int KW>
-__global__ void __launch_bounds__(kPartThreads, 4) part_pass_kernel(PartArgs a) {
+__global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem);
   unsigned long long* s_vals = s_keys + kPartTile;
@@ -235,6 +235,7 @@ struct FusedTableRef {
   // after it has grown the table: {key, sum bits} pairs + {count | key_null << 31}
   unsigned long long* ovf_pairs;
   unsigned int* ovf_counts;
+  unsigned long long ovf_cap;  // entries the parking area can hold; counters[2] counts what did not fit
 };
 
 template <bool IS_FLOAT>
@@ -244,9 +245,13 @@ __device__ __forceinline__ void global_accumulate(const FusedTableRef& t, unsign
   int64_t slot = table_find_or_insert(t.slots, t.mask, 4, key, key_null, &inserted);
   if (slot < 0) {
     const unsigned long long i = atomicAdd(&counters[0], 1ull);
-    t.ovf_pairs[2 * i] = key;
-    t.ovf_pairs[2 * i + 1] = sum_bits;
-    t.ovf_counts[i] = count | (key_null ? 0x80000000u : 0u);
+    if (i < t.ovf_cap) {
+      t.ovf_pairs[2 * i] = key;
+      t.ovf_pairs[2 * i + 1] = sum_bits;
+      t.ovf_counts[i] = count | (key_null ? 0x80000000u : 0u);
+    } else {
+      atomicAdd(&counters[2], 1ull);  // reported by the host as a capacity error
+    }
     return;
   }
   if (inserted) atomicAdd(&counters[1], 1ull);

@@ -36,10 +36,10 @@ namespace b2 {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 8;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per tile: 4 CTAs/SM
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile (2048 measured 16 % slower)
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u;
 
 // ---- ordered keys ----------------------------------------------------------------------

@@ -311,6 +311,11 @@ B2_API int32_t b2_hashagg_out_type(const B2HashAgg* a);
  * (key, value) rows updating an on-device table, no uint32 id column materialised.
  * Semantically identical to b2_grouper_consume followed by b2_hashagg_consume of a
  * sum and a count(ONLY_VALID) aggregator over the same value column. */
+/* expected_groups: cardinality hint (like reserving a builder).  0 = unknown: the table grows batch by
+ * batch and large batches are processed in 64M-row chunks.  > 0: the table is sized for it and a batch is
+ * processed in one chunk (fastest: rows of a key meet in shared memory); if the true number of groups
+ * exceeds the hint by more than the table slack + 64M inside one batch, consume fails with
+ * B2_CAPACITY_ERROR (nothing is silently dropped). */
 typedef struct B2GroupBySumCount B2GroupBySumCount;
 B2_API int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_type,
                                       int64_t expected_groups, B2GroupBySumCount** out);
