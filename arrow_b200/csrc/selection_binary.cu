@@ -117,36 +117,18 @@ __device__ __forceinline__ void copy_tile_bytes(const uint8_t* __restrict__ src,
     }
     return lo;
   };
-  // Each thread fills 64 contiguous output bytes (four aligned 16-byte stores): ONE binary search
-  // per 64 bytes, then it walks the rows with the current row's end and (source - output) delta held
-  // in registers, touching shared memory again only when it crosses into the next row.  (The first
-  // version searched and re-read the row table per byte: ~60 LDS per 16 bytes made the kernel
-  // shared-memory-pipe bound at 1.7 TB/s -- LDS costs 0.17 cycles/lane/SM, profiles/smem_probe_r01.txt.)
-  constexpr int kChunksPerThread = 4;
-  const int64_t n_groups = (body_chunks + kChunksPerThread - 1) / kChunksPerThread;
-  for (int64_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
-    const int64_t c0 = g * kChunksPerThread;
-    uint32_t pos = static_cast<uint32_t>(head + (c0 << 4));
+  for (int64_t c = threadIdx.x; c < body_chunks; c += blockDim.x) {
+    uint32_t pos = static_cast<uint32_t>(head + (c << 4));
     int j = find_row(pos);
-    uint32_t next = s_out[j + 1];
-    int64_t delta = static_cast<int64_t>(s_src[j]) - static_cast<int64_t>(s_out[j]);
+    uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < kChunksPerThread; ++c) {
-      if (c0 + c >= body_chunks) break;
-      uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int b = 0; b < 16; ++b) {
-        while (pos >= next) {  // skips empty strings; sentinel s_out[n_rows] = tile_bytes > pos
-          ++j;
-          next = s_out[j + 1];
-          delta = static_cast<int64_t>(s_src[j]) - static_cast<int64_t>(s_out[j]);
-        }
-        const uint32_t byte = src[delta + pos];
-        w[b >> 2] |= byte << ((b & 3) * 8);
-        ++pos;
-      }
-      *reinterpret_cast<uint4*>(d0 + head + ((c0 + c) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int b = 0; b < 16; ++b) {
+      while (pos >= s_out[j + 1]) ++j;  // skips empty strings; sentinel s_out[n_rows] = tile_bytes > pos
+      uint32_t byte = src[static_cast<int64_t>(s_src[j]) + (pos - s_out[j])];
+      w[b >> 2] |= byte << ((b & 3) * 8);
+      ++pos;
     }
+    *reinterpret_cast<uint4*>(d0 + head + (c << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   // head + tail bytes (< 32 per tile)
   const int64_t edge = head + (tile_bytes - tail_start);
