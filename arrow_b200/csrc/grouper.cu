@@ -76,43 +76,119 @@ __global__ void __launch_bounds__(kBlock) grouper_init_kernel(GrouperTable t) {
   }
 }
 
-template <bool INSERT>
-__global__ void __launch_bounds__(kBlock) grouper_probe_kernel(KeyLayout L, KeyColumns c, int64_t n,
-                                                               GrouperTable t, uint32_t* row_slot,
-                                                               int64_t* overflow) {
+constexpr uint32_t kResolved = 0xfffffffeu;  // row_slot marker: the id was already written by the probe
+
+// Consume probe: find or claim the slot of every row.  A row of a group that already has an
+// id (seen in an earlier batch) writes its id right away; a row of a group that is new in this
+// batch remembers its slot for the gather pass and lowers the slot's first_row to its own row
+// number (the atomicMin is skipped when a smaller row got there first, which is the common case
+// because rows are visited in ascending order).  Stops early once the table overflowed.
+__global__ void __launch_bounds__(kBlock) grouper_insert_kernel(KeyLayout L, KeyColumns c, int64_t n,
+                                                                GrouperTable t, uint32_t* row_slot,
+                                                                uint32_t* out_ids, int64_t* overflow) {
+  const volatile int64_t* ovf = overflow;
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    if (*ovf) return;
     bool is_null;
     uint64_t enc = encode_row(L, c, i, &is_null);
-    int64_t slot;
-    if (INSERT) {
+    int64_t slot = -1;
+    unsigned long long w1 = ~0ull;
+    if (is_null || enc == kEmptyKey) {
       bool inserted;
       slot = table_find_or_insert(t.slots, t.mask, 2, enc, is_null, &inserted);
-      if (slot < 0) {
-        *overflow = 1;
-        row_slot[i] = kNoId;
-        continue;
-      }
-      if (*t.id_ptr(slot) == kNoId) atomicMin(t.first_row_ptr(slot), static_cast<uint32_t>(i));
+      w1 = *reinterpret_cast<volatile unsigned long long*>(t.slots + slot * 2 + 1);
     } else {
-      slot = table_find(t.slots, t.mask, 2, enc, is_null);
+      // one 16-byte load per probe brings the key and {id, first_row} together
+      uint64_t sl = hash64(enc) & t.mask;
+      for (int probe = 0; probe < kMaxProbe; ++probe) {
+        unsigned long long* p = t.slots + sl * 2;
+        unsigned long long k, v;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(v) : "l"(p) : "memory");
+        if (k == kEmptyKey) {
+          k = atomicCAS(p, (unsigned long long)kEmptyKey, (unsigned long long)enc);
+          if (k == kEmptyKey) {  // claimed: a fresh slot has no id and no first row yet
+            slot = static_cast<int64_t>(sl);
+            break;
+          }
+          if (k == enc) v = *reinterpret_cast<volatile unsigned long long*>(p + 1);
+        }
+        if (k == enc) {
+          slot = static_cast<int64_t>(sl);
+          w1 = v;
+          break;
+        }
+        sl = (sl + 1) & t.mask;
+      }
     }
-    row_slot[i] = slot < 0 ? kNoId : static_cast<uint32_t>(slot);
+    if (slot < 0) {
+      *overflow = 1;
+      return;
+    }
+    const uint32_t id = static_cast<uint32_t>(w1), first_row = static_cast<uint32_t>(w1 >> 32);
+    if (id != kNoId) {
+      out_ids[i] = id;
+      row_slot[i] = kResolved;
+    } else {
+      if (first_row > static_cast<uint32_t>(i)) atomicMin(t.first_row_ptr(slot), static_cast<uint32_t>(i));
+      row_slot[i] = static_cast<uint32_t>(slot);
+    }
   }
 }
 
-// bit i = row i is the first occurrence of a new group
-__global__ void __launch_bounds__(kBlock) grouper_flag_kernel(int64_t n, GrouperTable t,
-                                                              const uint32_t* row_slot, uint32_t* flags) {
+// Lookup: never inserts; unknown keys become null (validity via ballot)
+__global__ void __launch_bounds__(kBlock) grouper_lookup_kernel(KeyLayout L, KeyColumns c, int64_t n,
+                                                                GrouperTable t, uint32_t* out,
+                                                                uint32_t* out_validity, int64_t* valid_count) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    int64_t i = (w << 5) + lane_id();
+    bool ok = false;
+    if (i < n) {
+      bool is_null;
+      uint64_t enc = encode_row(L, c, i, &is_null);
+      int64_t slot = table_find(t.slots, t.mask, 2, enc, is_null);
+      uint32_t id = slot < 0 ? kNoId : *t.id_ptr(slot);
+      ok = id != kNoId;
+      out[i] = ok ? id : 0u;
+    }
+    unsigned word = __ballot_sync(0xffffffffu, ok);
+    if (lane_id() == 0) {
+      out_validity[w] = word;
+      local += __popc(word);
+    }
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+}
+
+// bit i = row i is the first occurrence of a new group.  Two ways to build the bitmap:
+//   by rows  : every unresolved row re-reads its slot (one random access per row);
+//   by slots : one streaming pass over the table sets bit first_row of every slot that
+//              has no id yet -- cheaper whenever the table is not much larger than the batch.
+__global__ void __launch_bounds__(kBlock) grouper_flag_rows_kernel(int64_t n, GrouperTable t,
+                                                                   const uint32_t* row_slot, uint32_t* flags) {
   int64_t nw = (n + 31) >> 5;
   for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
     int64_t i = (w << 5) + lane_id();
     bool f = false;
     if (i < n) {
       uint32_t s = row_slot[i];
-      f = *t.id_ptr(s) == kNoId && *t.first_row_ptr(s) == static_cast<uint32_t>(i);
+      if (s != kResolved) {
+        const unsigned long long w1 = t.slots[(uint64_t)s * 2 + 1];
+        f = static_cast<uint32_t>(w1) == kNoId && static_cast<uint32_t>(w1 >> 32) == static_cast<uint32_t>(i);
+      }
     }
     unsigned word = __ballot_sync(0xffffffffu, f);
     if (lane_id() == 0) flags[w] = word;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_flag_slots_kernel(GrouperTable t, uint32_t* flags) {
+  for (uint64_t s = blockIdx.x * (uint64_t)kBlock + threadIdx.x; s < t.mask + 3; s += (uint64_t)gridDim.x * kBlock) {
+    const unsigned long long w1 = __ldcs(t.slots + s * 2 + 1);
+    const uint32_t id = static_cast<uint32_t>(w1), first_row = static_cast<uint32_t>(w1 >> 32);
+    if (id == kNoId && first_row != 0xffffffffu) atomicOr(flags + (first_row >> 5), 1u << (first_row & 31));
   }
 }
 
@@ -160,32 +236,25 @@ __global__ void __launch_bounds__(kBlock) grouper_assign_kernel(KeyLayout L, Key
   }
 }
 
-// out[i] = id of row i; for Lookup unknown keys become null (validity via ballot)
+// out[i] = id of row i for the rows the probe left unresolved (groups new in this batch)
 __global__ void __launch_bounds__(kBlock) grouper_gather_kernel(int64_t n, GrouperTable t,
-                                                                const uint32_t* row_slot, uint32_t* out,
-                                                                uint32_t* out_validity, int64_t* valid_count) {
-  int64_t nw = (n + 31) >> 5;
-  int64_t local = 0;
-  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
-    int64_t i = (w << 5) + lane_id();
-    bool ok = false;
-    if (i < n) {
-      uint32_t s = row_slot[i];
-      uint32_t id = s == kNoId ? kNoId : *t.id_ptr(s);
-      ok = id != kNoId;
-      out[i] = ok ? id : 0u;
+                                                                const uint32_t* __restrict__ row_slot,
+                                                                uint32_t* __restrict__ out) {
+  constexpr int kPer = 4;
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t i0 = blockIdx.x * (int64_t)kBlock + threadIdx.x; i0 < n; i0 += stride * kPer) {
+    uint32_t s[kPer], id[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int64_t i = i0 + k * stride;
+      s[k] = i < n ? __ldcs(row_slot + i) : kResolved;
     }
-    if (out_validity) {
-      unsigned word = __ballot_sync(0xffffffffu, ok);
-      if (lane_id() == 0) {
-        out_validity[w] = word;
-        local += __popc(word);
-      }
-    }
-  }
-  if (out_validity) {
-    int64_t s = block_sum<kBlock>(local);
-    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (s[k] != kResolved) id[k] = *t.id_ptr(s[k]);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (s[k] != kResolved) out[i0 + k * stride] = id[k];
   }
 }
 
@@ -342,15 +411,13 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
 
   if (!insert) {
     if (g->cap == 0) B2_RETURN_NOT_OK(grouper_rebuild(g, 1024, s));
-    grouper_probe_kernel<false><<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, row_slot.as<uint32_t>(), nullptr);
-    B2_LAUNCHED();
     Temp bits(ctx, s);
     B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
     B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
     ScalarSlot slot(ctx);
     B2_RETURN_NOT_OK(slot.zero(s));
-    grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>(),
-                                                  bits.as<uint32_t>(), slot.dev());
+    grouper_lookup_kernel<<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, ids.as<uint32_t>(), bits.as<uint32_t>(),
+                                                  slot.dev());
     B2_LAUNCHED();
     B2_RETURN_NOT_OK(slot.fetch(s));
     int64_t nulls = n - slot.host()[0];
@@ -366,7 +433,8 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
   while (true) {
     ScalarSlot slot(ctx);
     B2_RETURN_NOT_OK(slot.zero(s));
-    grouper_probe_kernel<true><<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, row_slot.as<uint32_t>(), slot.dev());
+    grouper_insert_kernel<<<grid, kBlock, 0, s>>>(g->layout, cols, n, g->table, row_slot.as<uint32_t>(),
+                                                  ids.as<uint32_t>(), slot.dev());
     B2_LAUNCHED();
     B2_RETURN_NOT_OK(slot.fetch(s));
     if (!slot.host()[0]) break;
@@ -376,7 +444,12 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
   Temp flags(ctx, s);
   B2_RETURN_NOT_OK(flags.alloc(bitmap_alloc_bytes(n)));
   B2_CUDA(cudaMemsetAsync(flags.ptr, 0, bitmap_alloc_bytes(n), s));
-  grouper_flag_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), flags.as<uint32_t>());
+  if (g->cap <= (uint64_t)n) {
+    grouper_flag_slots_kernel<<<grid_for((int64_t)g->cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(g->table,
+                                                                                                    flags.as<uint32_t>());
+  } else {
+    grouper_flag_rows_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), flags.as<uint32_t>());
+  }
   B2_LAUNCHED();
   FilterBitmaps fb;
   fb.mask_data = BitmapReader(flags.ptr, 0, n);
@@ -397,8 +470,10 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
     B2_LAUNCHED();
     g->num_groups += static_cast<uint32_t>(n_new);
   }
-  grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>(), nullptr, nullptr);
-  B2_LAUNCHED();
+  if (n_new > 0) {  // otherwise the probe resolved every row
+    grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>());
+    B2_LAUNCHED();
+  }
   fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
   // keep load factor <= 1/2 for the next batch
   if ((uint64_t)g->num_groups * 2 > g->cap) {

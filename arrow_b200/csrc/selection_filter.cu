@@ -12,124 +12,95 @@
 // emits a null there; output validity = values validity AND mask validity compacted
 // alongside; the output carries a validity bitmap iff values or mask may have nulls.
 //
-// B200 design (three launches, all HBM streaming, no atomics on the data path):
-//   1. filter_count_kernel : one warp per 4096-row tile popcounts the selection words
-//      (mask data &/| mask validity) -> per-tile counts.           reads bitmaps only
-//   2. tile_scan_kernel    : exclusive scan of the tile counts (one CTA). tiny
-//   3. filter_compact_kernel<W>: one CTA per tile.  Dense tiles issue all their 16-byte
-//      coalesced value loads first (they need every sector anyway) so the loads overlap
-//      the bitmap round trip; every WARP then rebuilds the tile's 64 selection words and
-//      prefix popcounts in registers (no shared memory, no barrier on the data path) and
-//      stores survivors at base + prefix + popc(lower bits): ranks are dense and
+// B200 design (two launches, HBM streaming):
+//   1. filter_count_scan_kernel : one warp per 4096-row tile popcounts the selection words
+//      (mask data &/| mask validity), publishes the count and resolves its exclusive prefix
+//      with a chained scan (decoupled look-back over atomic-ticket ordered tiles); also emits
+//      the survivors-before-chunk table (uint16 per 512 rows).      reads bitmaps only
+//   2. filter_compact_kernel<W> : one WARP per 512-row chunk, no shared memory, no barrier.
+//      Dense chunks issue all their 16-byte coalesced value loads first (they need every
+//      sector anyway) so the loads overlap the bitmap round trip; lanes 0..15 rebuild the
+//      chunk's 32-bit selection words and prefix popcounts in registers and every lane
+//      stores its survivors at base + prefix + popc(lower bits): ranks are dense and
 //      monotonic across a warp, so each store instruction writes one contiguous span.
-//      Sparse tiles load only lanes holding a survivor.  Validity bits are compacted into
-//      a shared-memory bitmap and flushed with plain word stores (atomicOr only on the
-//      two boundary words).
+//      Sparse chunks load only lanes holding a survivor.  Validity bits are compacted with
+//      a software PEXT and OR-ed into the zeroed output bitmap (2 RED per 32 rows).
 // Algorithmic bytes/row (int64, values nullable, mask non-null, s=0.5): 12.3125
-// (SURVEY section 8d); passes 1+2 re-read only the bitmaps (+0.25 B/row).
+// (SURVEY section 8d); pass 1 re-reads only the bitmaps (+0.25 B/row).
 #include "selection.cuh"
 
 namespace b2 {
 
-// ---- pass 1: per-tile selected counts (+ total valid-and-selected) ----
-__global__ void __launch_bounds__(kBlock) filter_count_kernel(FilterBitmaps fb, int64_t n_tiles,
-                                                              uint32_t* tile_counts,
-                                                              int64_t* total_valid, bool want_valid) {
-  const unsigned lane = lane_id();
-  int64_t valid_local = 0;
-  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < n_tiles;
-       tile += (int64_t)gridDim.x * kWarpsPerBlock) {
-    int64_t w0 = tile * kTileWords + 2 * lane;
-    uint64_t s0 = fb.sel(w0), s1 = fb.sel(w0 + 1);
-    int c = __popcll(s0) + __popcll(s1);
-    if (want_valid) valid_local += __popcll(s0 & fb.out_valid(w0)) + __popcll(s1 & fb.out_valid(w0 + 1));
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) tile_counts[tile] = static_cast<uint32_t>(c);
-  }
-  if (want_valid) {
-    int64_t s = block_sum<kBlock>(valid_local);
-    if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(total_valid), (unsigned long long)s);
-  }
-}
-
-// ---- pass 2: exclusive scan of tile counts -> int64 offsets[n_tiles + 1] ----
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* counts, int64_t n_tiles,
-                                                         int64_t* offsets, int64_t* total) {
-  __shared__ int64_t warp_tot[32];
-  const int t = threadIdx.x;
-  int64_t per = (n_tiles + 1023) / 1024;
-  int64_t lo = t * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
-  int64_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += counts[i];
-  // block exclusive scan of `sum`
-  int64_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((t & 31) >= o) incl += v;
-  }
-  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
-  __syncthreads();
-  if (t < 32) {
-    int64_t w = warp_tot[t];
-    int64_t wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (t >= o) wi += v;
-    }
-    warp_tot[t] = wi - w;  // exclusive
-    if (t == 31) {
-      offsets[n_tiles] = wi;
-      if (total) *total = wi;
-    }
-  }
-  __syncthreads();
-  int64_t run = incl - sum + warp_tot[t >> 5];
-  for (int64_t i = lo; i < hi; ++i) {
-    offsets[i] = run;
-    run += counts[i];
-  }
-}
-
 // ---- passes 1+2 fused: per-tile counts with a chained scan (decoupled look-back) ----
-// One warp per tile; tiles are claimed through an atomic ticket, so the warp owning tile t-1
-// is always running or done (no residency assumption): tile t publishes its count, then looks
-// back over up to 32 predecessor cells per step (one per lane) until it meets one that already
-// carries an inclusive prefix.  cell = flag(2 bits) << 62 | value.  Removes the single-CTA scan.
+// One warp owns a SPAN of kSpanTiles consecutive tiles; a CTA claims 8 consecutive spans with one
+// atomic ticket, so the owners of all earlier spans are running or done (no residency
+// assumption) and the single ticket address sees n_tiles/32 atomics, not n_tiles.  A span
+// publishes its survivor count, then looks back over up to 32 predecessor cells per step (one
+// per lane) until it meets one that already carries an inclusive prefix.
+// cell = flag(2 bits) << 62 | value.
 constexpr unsigned long long kCellAgg = 1ull << 62, kCellIncl = 2ull << 62, kCellMask = (1ull << 62) - 1ull;
+constexpr int kSpanTiles = 4;
 
 __global__ void __launch_bounds__(kBlock) filter_count_scan_kernel(FilterBitmaps fb, int64_t n_tiles,
                                                                    unsigned long long* cells, int64_t* offsets,
                                                                    uint16_t* chunk_rel, int64_t* totals, bool want_valid) {
-  const unsigned lane = lane_id();
+  __shared__ unsigned long long s_ticket;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const int64_t n_spans = (n_tiles + kSpanTiles - 1) / kSpanTiles;
   int64_t valid_local = 0;
   volatile unsigned long long* vc = cells;
-  unsigned long long* ticket = cells + n_tiles;  // zero-initialised with the cells
+  unsigned long long* ticket = cells + n_spans;  // zero-initialised with the cells
   while (true) {
-    unsigned long long tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, 1ull);
-    const int64_t tile = static_cast<int64_t>(__shfl_sync(0xffffffffu, tk, 0));
-    if (tile >= n_tiles) break;
-    int64_t w0 = tile * kTileWords + 2 * lane;
-    uint64_t s0 = fb.sel(w0), s1 = fb.sel(w0 + 1);
-    int c = __popcll(s0) + __popcll(s1);
-    if (want_valid) valid_local += __popcll(s0 & fb.out_valid(w0)) + __popcll(s1 & fb.out_valid(w0 + 1));
-    const unsigned long long count = static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, c));
-    if (lane == 0) vc[tile] = (tile == 0 ? kCellIncl : kCellAgg) | count;
-    if (chunk_rel) {
-      // survivors before each 512-row chunk of the tile (lane 4k owns the first word of chunk k)
-      int incl = c;
+    __syncthreads();  // previous round's readers of s_ticket are done
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const int64_t span = static_cast<int64_t>(s_ticket) * kWarpsPerBlock + warp;
+    if (static_cast<int64_t>(s_ticket) * kWarpsPerBlock >= n_spans) break;  // uniform across the CTA
+    if (span >= n_spans) continue;
+    const int64_t tile0 = span * kSpanTiles;
+    int c[kSpanTiles];
+    uint64_t w[kSpanTiles][2];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+    for (int k = 0; k < kSpanTiles; ++k) {
+      const int64_t w0 = (tile0 + k) * kTileWords + 2 * lane;
+      const bool in = tile0 + k < n_tiles;
+      w[k][0] = in ? fb.sel(w0) : 0ull;
+      w[k][1] = in ? fb.sel(w0 + 1) : 0ull;
+      c[k] = __popcll(w[k][0]) + __popcll(w[k][1]);
+    }
+    if (want_valid) {
+#pragma unroll
+      for (int k = 0; k < kSpanTiles; ++k) {
+        if (tile0 + k >= n_tiles) break;
+        const int64_t w0 = (tile0 + k) * kTileWords + 2 * lane;
+        valid_local += __popcll(w[k][0] & fb.out_valid(w0)) + __popcll(w[k][1] & fb.out_valid(w0 + 1));
       }
-      if ((lane & 3) == 0) chunk_rel[tile * 8 + (lane >> 2)] = static_cast<uint16_t>(incl - c);
+    }
+    unsigned tile_count[kSpanTiles];
+    unsigned long long count = 0;
+#pragma unroll
+    for (int k = 0; k < kSpanTiles; ++k) {
+      tile_count[k] = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(c[k]));
+      count += tile_count[k];
+    }
+    if (lane == 0) vc[span] = (span == 0 ? kCellIncl : kCellAgg) | count;
+    if (chunk_rel) {
+      // survivors before each 512-row chunk of a tile (lane 4j owns the first word of chunk j)
+#pragma unroll
+      for (int k = 0; k < kSpanTiles; ++k) {
+        int incl = c[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if ((lane & 3) == 0 && tile0 + k < n_tiles)
+          chunk_rel[(tile0 + k) * 8 + (lane >> 2)] = static_cast<uint16_t>(incl - c[k]);
+      }
     }
     unsigned long long excl = 0;
-    if (tile > 0) {
-      int64_t back = tile - 1;  // newest cell not yet folded in
+    if (span > 0) {
+      int64_t back = span - 1;  // newest cell not yet folded in
       while (true) {
         const int64_t t = back - lane;
         unsigned long long cell = 0;
@@ -148,11 +119,16 @@ __global__ void __launch_bounds__(kBlock) filter_count_scan_kernel(FilterBitmaps
         if (incl_mask || back - 32 < 0) break;
         back -= 32;
       }
-      if (lane == 0) vc[tile] = kCellIncl | (excl + count);
+      if (lane == 0) vc[span] = kCellIncl | (excl + count);
     }
     if (lane == 0) {
-      offsets[tile] = static_cast<int64_t>(excl);
-      if (tile == n_tiles - 1) {
+      unsigned long long run = excl;
+#pragma unroll
+      for (int k = 0; k < kSpanTiles; ++k) {
+        if (tile0 + k < n_tiles) offsets[tile0 + k] = static_cast<int64_t>(run);
+        run += tile_count[k];
+      }
+      if (span == n_spans - 1) {
         offsets[n_tiles] = static_cast<int64_t>(excl + count);
         totals[0] = static_cast<int64_t>(excl + count);
       }
@@ -329,7 +305,7 @@ int filter_plan(B2Context* ctx, const FilterBitmaps& fb, int64_t n, bool want_va
   if (chunk_rel) B2_RETURN_NOT_OK(chunk_rel->alloc(n_tiles * 8 * sizeof(uint16_t)));
   ScalarSlot slot(ctx);
   B2_RETURN_NOT_OK(slot.zero(s));
-  int grid = grid_for(n_tiles, kWarpsPerBlock, ctx->sm_count * 8);
+  int grid = grid_for(n_tiles, kWarpsPerBlock * kSpanTiles, ctx->sm_count * 8);
   filter_count_scan_kernel<<<grid, kBlock, 0, s>>>(fb, n_tiles, cells.as<unsigned long long>(),
                                                    offsets->as<int64_t>(), chunk_rel ? chunk_rel->as<uint16_t>() : nullptr,
                                                    slot.dev(), want_valid);
