@@ -1,6 +1,6 @@
 #!/bin/bash
 # per-kernel device times of the non-headline configs (filter / group-by / sort / utf8) at full size
-K='filter_|tile_scan|onesweep|radix_|sort_prepare|fused_|grouper_|hashagg_|take_|widen_|count_zero|bitmap_and'
+K='part_|preagg_|replay_|filter_|tile_scan|onesweep|radix_|sort_prepare|fused_|grouper_|hashagg_|take_|widen_|count_zero|bitmap_and'
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -c 600 --csv \
     --log-file gpurun_out/launches_configs.csv python bench_configs.py --reps 1 --only ${1:-c1,c3,c4,c5} > gpurun_out/configs_under_ncu.log 2>&1
 python - <<'PY'
