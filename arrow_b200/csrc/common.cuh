@@ -215,4 +215,32 @@ inline int grid_for(int64_t work_items, int64_t items_per_block, int max_waves_b
   return static_cast<int>(b);
 }
 
+// Decoupled look-back over one column of a [tile][stride] table of 32-bit cells
+// (bits 31:30 = 0 not published / 1 tile aggregate / 2 inclusive prefix, bits 29:0 = count):
+// returns the exclusive prefix of `tile`.  Four predecessor cells are requested per step so
+// the walk costs one L2 round trip per four tiles instead of one per tile.
+__device__ __forceinline__ uint32_t lookback_exclusive(const volatile uint32_t* col, int64_t tile, size_t stride) {
+  uint32_t excl = 0;
+  int64_t t = tile - 1;
+  while (t >= 0) {
+    uint32_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (t - k >= 0) ? col[static_cast<size_t>(t - k) * stride] : (2u << 30);
+    bool done = false;
+    int used = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t f = c[k] >> 30;
+      if (!done && used == k && f != 0) {
+        excl += c[k] & 0x3fffffffu;
+        ++used;
+        done = f == 2;
+      }
+    }
+    if (done) break;
+    t -= used;  // poll again from the first cell that was not published yet
+  }
+  return excl;
+}
+
 }  // namespace b2

@@ -153,12 +153,12 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
   // Rank inside the tile's bin with ONE returning shared-memory atomic per row
   // (ATOMS.ADD.u32: 0.17 cycles/lane/SM measured, vs 1.83 for MATCH.ANY -- profiles/smem_probe_r01.txt).
   // The order of rows inside a partition is irrelevant for grouping, so no stable ranking is needed.
-  uint32_t rank[kPartItems];
-  unsigned dig[kPartItems];
+  uint32_t rank_dig[kPartItems];  // rank inside the bin | digit << 16 (one register per row)
 #pragma unroll
   for (int j = 0; j < kPartItems; ++j) {
-    dig[j] = part_digit(key[j], flg[j], a.shift);
-    rank[j] = (flg[j] & 4u) ? 0u : atomicAdd(&s_cnt[dig[j]], 1u);  // padding rows are neither counted nor staged
+    const unsigned d = part_digit(key[j], flg[j], a.shift);
+    const uint32_t r = (flg[j] & 4u) ? 0u : atomicAdd(&s_cnt[d], 1u);  // padding rows are neither counted nor staged
+    rank_dig[j] = r | (d << 16);
   }
   __syncthreads();
 
@@ -177,36 +177,33 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
     if (lane == 31) s_warp_tot[warp] = incl;
   }
   __syncthreads();
+  uint32_t bin_off = 0;
   if (tid < kPartRadix) {
     uint32_t woff = 0;
 #pragma unroll
     for (int w = 0; w < kPartRadix / 32; ++w)
       if (w < (int)warp) woff += s_warp_tot[w];
-    const uint32_t bin_off = woff + incl - run;
+    bin_off = woff + incl - run;
     s_bin[tid] = bin_off;
-    uint32_t excl = 0;
-    if (tile > 0) {
-      volatile uint32_t* lb = a.lookback;
-      int64_t t = (int64_t)tile - 1;
-      while (true) {
-        uint32_t cell = lb[(size_t)t * kPartRadix + tid];
-        if ((cell >> 30) == 0) continue;
-        excl += cell & kPValMask;
-        if ((cell >> 30) == 2) break;
-        --t;
-      }
-      lb[(size_t)tile * kPartRadix + tid] = kPFlagIncl | (excl + run);
-    }
-    s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
   __syncthreads();
+  // stage the tile in bin order first: it needs only tile-local offsets, and it gives the
+  // predecessors time to publish before the look-back below has to wait for them
 #pragma unroll
   for (int j = 0; j < kPartItems; ++j) {
     if (flg[j] & 4u) continue;
-    const uint32_t pos = s_bin[dig[j]] + rank[j];
+    const uint32_t pos = s_bin[rank_dig[j] >> 16] + (rank_dig[j] & 0xffffu);
     s_keys[pos] = key[j];
     s_vals[pos] = val[j];
     s_flags[pos] = static_cast<uint8_t>(flg[j]);
+  }
+  if (tid < kPartRadix) {
+    uint32_t excl = 0;
+    if (tile > 0) {
+      excl = lookback_exclusive(a.lookback + tid, tile, kPartRadix);
+      reinterpret_cast<volatile uint32_t*>(a.lookback)[(size_t)tile * kPartRadix + tid] = kPFlagIncl | (excl + run);
+    }
+    s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
   __syncthreads();
 #pragma unroll

@@ -284,37 +284,33 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_kernel(OnesweepArgs<K> 
     if (lane == 31) s_warp_tot[warp] = incl;
   }
   __syncthreads();
+  uint32_t bin_off = 0;
   if (tid < kRadix) {
     uint32_t woff = 0;
 #pragma unroll
     for (int w = 0; w < kRadix / 32; ++w)
       if (w < (int)warp) woff += s_warp_tot[w];
-    const uint32_t bin_off = woff + incl - run;
+    bin_off = woff + incl - run;
     s_bin[tid] = bin_off;
-    uint32_t excl = 0;
-    if (tile > 0) {
-      volatile uint32_t* lb = a.lookback;
-      int64_t t = (int64_t)tile - 1;
-      while (true) {
-        uint32_t cell = lb[(size_t)t * kRadix + tid];
-        if ((cell >> 30) == 0) continue;  // predecessor not published yet
-        excl += cell & kValMask;
-        if ((cell >> 30) == 2) break;
-        --t;
-      }
-      lb[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
-    }
-    s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
   __syncthreads();
 
-  // stage keys and indices in digit order
+  // stage keys and indices in digit order first: it needs only tile-local offsets, and it gives
+  // the predecessors time to publish before the look-back below has to wait for them
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const unsigned digit = static_cast<unsigned>(key[j] >> a.shift) & (kRadix - 1);
     const uint32_t pos = s_bin[digit] + wc[digit] + rank[j];
     s_keys[pos] = key[j];
     s_idx[pos] = idxv[j];
+  }
+  if (tid < kRadix) {
+    uint32_t excl = 0;
+    if (tile > 0) {
+      excl = lookback_exclusive(a.lookback + tid, tile, kRadix);
+      reinterpret_cast<volatile uint32_t*>(a.lookback)[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
+    }
+    s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
   __syncthreads();
   // contiguous runs out
