@@ -11,15 +11,16 @@
 // (vector_selection_internal.cc:519-523).
 //
 // B200 design (per call): sizes pass -> tile scan -> copy pass.
-//   sizes: one CTA per tile; every thread owns a run of consecutive rows, reads their
-//          offsets and sums the kept lengths (block reduce) -> bytes per tile.
+//   sizes: one CTA per 4096-row tile; each warp walks 512 rows 32 at a time (coalesced
+//          offset loads), sums the kept lengths -> bytes per tile.
 //   scan : exclusive scan of the per-tile byte counts (single CTA, tiny).
-//   copy : the same CTA walk rebuilds per-row output offsets with one block scan, writes
-//          the new offsets coalesced, stages (output offset, source offset) of the tile's
-//          kept rows in shared memory, and then EVERY thread copies 16-byte chunks of the
-//          tile's contiguous output range: a binary search finds the row a chunk starts
-//          in, bytes are gathered from the (L1/L2-resident) sources and written with one
-//          aligned 16-byte store -- writes are fully coalesced regardless of string length.
+//   copy : the same walk with a warp scan per step rebuilds per-row output offsets, stages
+//          (output offset, source offset) of the tile's kept rows in shared memory and writes
+//          the new offsets coalesced; then EVERY thread produces 16-byte chunks of the tile's
+//          contiguous output range: a coarse index + short binary search finds the row a
+//          chunk starts in, each overlapping row segment is fetched with aligned 8-byte loads
+//          and funnel-shifted into place, and the chunk leaves with one aligned 16-byte
+//          store -- writes are fully coalesced regardless of string length.
 // Algorithmic bytes/row (offset width o, mean length L, selectivity s): o + L + bitmaps
 // read, s*(o + L + 1/8) written (utf8 Filter o=8, L=16, s=0.5: 36.3 B/row).
 #include <type_traits>
@@ -29,7 +30,6 @@
 namespace b2 {
 
 constexpr int kBinThreads = 256;
-constexpr int kFilterRowsPerThread = kTileRows / kBinThreads;  // 16 consecutive rows
 constexpr int kTakeTile = 2048;
 constexpr int kTakeRowsPerThread = kTakeTile / kBinThreads;  // 8 consecutive indices
 
@@ -108,8 +108,21 @@ __device__ __forceinline__ void copy_tile_bytes(const uint8_t* __restrict__ src,
   if (head > tile_bytes) head = tile_bytes;
   const int64_t body_chunks = (tile_bytes - head) >> 4;
   const int64_t tail_start = head + (body_chunks << 4);
-  auto find_row = [&](uint32_t pos) {
-    int lo = 0, hi = n_rows;  // largest j with s_out[j] <= pos
+  // coarse index: s_coarse[k] = the row that covers output byte k << g (g >= 6 chosen so the
+  // table has <= 512 entries), so a chunk's row is found by a binary search over the handful of
+  // rows between two table entries instead of over the whole tile (12 dependent LDS steps)
+  __shared__ uint16_t s_coarse[513];
+  int g = 6;
+  while ((tile_bytes >> g) >= 512) ++g;
+  for (int j = threadIdx.x; j < n_rows; j += blockDim.x) {
+    const uint32_t a = s_out[j], b = s_out[j + 1];
+    for (uint32_t k = (a + (1u << g) - 1u) >> g; (static_cast<uint64_t>(k) << g) < b; ++k) s_coarse[k] = static_cast<uint16_t>(j);
+  }
+  __syncthreads();
+  auto find_row = [&](uint32_t pos) {  // largest j with s_out[j] <= pos
+    const uint32_t k = pos >> g;
+    int lo = s_coarse[k];
+    int hi = ((static_cast<int64_t>(k + 1) << g) < tile_bytes) ? s_coarse[k + 1] + 1 : n_rows;
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
       if (s_out[mid] <= pos) lo = mid;
@@ -131,38 +144,56 @@ __device__ __forceinline__ void copy_tile_bytes(const uint8_t* __restrict__ src,
       unsigned long long lo = 0, hi = 0;
       unsigned filled = 0;
       while (filled < 16) {
-        while (pos >= s_out[j + 1]) ++j;  // skips empty strings; sentinel s_out[n_rows] = tile_bytes > pos
-        const unsigned avail = s_out[j + 1] - pos;
-        const unsigned len = avail < 16u - filled ? avail : 16u - filled;
-        const uint8_t* p = src + static_cast<int64_t>(s_src[j]) + (pos - s_out[j]);
-        const unsigned long long* q = reinterpret_cast<const unsigned long long*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(7));
-        const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) & 7) * 8;
-        const unsigned long long w0 = __ldg(q);
-        const unsigned long long w1 = (sh + len * 8 > 64) ? __ldg(q + 1) : 0ull;
-        const unsigned long long w2 = (sh + len * 8 > 128) ? __ldg(q + 2) : 0ull;
-        unsigned long long vlo = w0, vhi = w1;
-        if (sh) {
-          vlo = (w0 >> sh) | (w1 << (64 - sh));
-          vhi = (w1 >> sh) | (w2 << (64 - sh));
+        // describe up to two row segments first (shared memory only), then issue the loads of
+        // both, then merge: twice the loads in flight per thread on this latency-bound loop
+        const unsigned long long* q[2];
+        unsigned sh[2], len[2] = {0, 0}, at[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (filled < 16) {
+            while (pos >= s_out[j + 1]) ++j;  // skips empty strings; sentinel s_out[n_rows] = tile_bytes > pos
+            const unsigned avail = s_out[j + 1] - pos;
+            len[g] = avail < 16u - filled ? avail : 16u - filled;
+            const uint8_t* p = src + static_cast<int64_t>(s_src[j]) + (pos - s_out[j]);
+            q[g] = reinterpret_cast<const unsigned long long*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(7));
+            sh[g] = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+            at[g] = filled;
+            filled += len[g];
+            pos += len[g];
+          }
         }
-        if (len < 8) {
-          vlo &= (1ull << (len * 8)) - 1ull;
-          vhi = 0;
-        } else if (len < 16) {
-          vhi &= (1ull << ((len - 8) * 8)) - 1ull;  // len == 8 -> 0
+        unsigned long long w[2][3];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          w[g][0] = len[g] ? __ldg(q[g]) : 0ull;
+          w[g][1] = (len[g] && sh[g] + len[g] * 8 > 64) ? __ldg(q[g] + 1) : 0ull;
+          w[g][2] = (len[g] && sh[g] + len[g] * 8 > 128) ? __ldg(q[g] + 2) : 0ull;
         }
-        if (filled == 0) {
-          lo = vlo;
-          hi = vhi;
-        } else if (filled < 8) {
-          const unsigned s8 = filled * 8;
-          lo |= vlo << s8;
-          hi |= (vhi << s8) | (vlo >> (64 - s8));
-        } else {
-          hi |= vlo << ((filled - 8) * 8);  // filled >= 8 -> len <= 8 -> vhi == 0
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (!len[g]) continue;
+          unsigned long long vlo = w[g][0], vhi = w[g][1];
+          if (sh[g]) {
+            vlo = (w[g][0] >> sh[g]) | (w[g][1] << (64 - sh[g]));
+            vhi = (w[g][1] >> sh[g]) | (w[g][2] << (64 - sh[g]));
+          }
+          if (len[g] < 8) {
+            vlo &= (1ull << (len[g] * 8)) - 1ull;
+            vhi = 0;
+          } else if (len[g] < 16) {
+            vhi &= (1ull << ((len[g] - 8) * 8)) - 1ull;  // len == 8 -> 0
+          }
+          if (at[g] == 0) {
+            lo = vlo;
+            hi = vhi;
+          } else if (at[g] < 8) {
+            const unsigned s8 = at[g] * 8;
+            lo |= vlo << s8;
+            hi |= (vhi << s8) | (vlo >> (64 - s8));
+          } else {
+            hi |= vlo << ((at[g] - 8) * 8);  // at >= 8 -> len <= 8 -> vhi == 0
+          }
         }
-        filled += len;
-        pos += len;
       }
       *reinterpret_cast<uint4*>(d0 + head + (c << 4)) =
           make_uint4(static_cast<uint32_t>(lo), static_cast<uint32_t>(lo >> 32), static_cast<uint32_t>(hi),
@@ -238,69 +269,72 @@ __global__ void __launch_bounds__(kBinThreads) filter_binary_kernel(BinFilterArg
     for (int i = threadIdx.x; i < kTileRows / 32 + 2; i += kBinThreads) s_bits[i] = 0;
   __syncthreads();
 
-  // this thread's 16 consecutive rows
-  const int r = threadIdx.x * kFilterRowsPerThread;
-  const uint64_t selw = s_sel[r >> 6];
-  const unsigned bits = static_cast<unsigned>(selw >> (r & 63)) & 0xffffu;
-  const unsigned vbits = static_cast<unsigned>(s_ov[r >> 6] >> (r & 63)) & 0xffffu;
-  const unsigned keep = bits & vbits;  // rows whose bytes are copied
-  int64_t local = 0;
-  uint32_t len[kFilterRowsPerThread];
-  OffT first_off = 0;
-  if (bits) {
+  // Every warp walks its 512 rows 32 at a time, so the offset loads are coalesced (a thread
+  // owning 16 consecutive rows made every LDG touch 32 different lines: the L1 tag stage, not
+  // HBM, bounded the kernel).  Per step: lengths of the kept rows, a warp scan for their
+  // warp-relative output offsets, and -- in the copy pass -- (offset, source) staged at the
+  // row's rank among the tile's kept rows.
+  const unsigned warp = threadIdx.x >> 5;
+  constexpr int kWarps = kBinThreads / 32;
+  constexpr int kRowsPerWarp = kTileRows / kWarps;  // 512
+  __shared__ int64_t s_wtot[kWarps];
+  const int64_t out_row_base = COPY ? a.tile_rows[tile] : 0;
+  const OffT tile_src0 = a.offsets[row0];
+  int64_t wrun = 0;  // bytes of this warp's kept rows so far (uniform across the warp)
+#pragma unroll 4
+  for (int it = 0; it < kRowsPerWarp / 32; ++it) {
+    const int r = warp * kRowsPerWarp + it * 32 + lane;
     const int64_t g = row0 + r;
-    OffT prev = a.offsets[g];
-    first_off = prev;
+    const uint64_t selw = s_sel[r >> 6];
+    const bool sel = (selw >> (r & 63)) & 1;
+    const bool ov = (s_ov[r >> 6] >> (r & 63)) & 1;
+    OffT o0 = 0, o1 = 0;
+    if (g < a.n) {
+      o0 = a.offsets[g];
+      o1 = a.offsets[g + 1];
+    }
+    const uint32_t len = (sel && ov) ? static_cast<uint32_t>(o1 - o0) : 0u;
+    uint32_t incl = len;
 #pragma unroll
-    for (int k = 0; k < kFilterRowsPerThread; ++k) {
-      len[k] = 0;
-      if (g + k < a.n) {
-        OffT next = a.offsets[g + k + 1];
-        if ((keep >> k) & 1) len[k] = static_cast<uint32_t>(next - prev);
-        prev = next;
-        local += len[k];
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (COPY && sel) {
+      const unsigned j = s_prefix[r >> 6] + __popcll(selw & ((1ull << (r & 63)) - 1ull));
+      s_out[j] = static_cast<uint32_t>(wrun) + incl - len;
+      s_src[j] = static_cast<uint32_t>(o0 - tile_src0);
+      if (HAS_VALID && ov) {
+        const unsigned q = static_cast<unsigned>(out_row_base & 31) + j;
+        atomicOr(&s_bits[q >> 5], 1u << (q & 31));
       }
     }
+    wrun += __shfl_sync(0xffffffffu, incl, 31);
   }
-  int64_t total;
-  const int64_t excl = block_excl_scan(local, &total);
+  if (lane == 0) s_wtot[warp] = wrun;
+  __syncthreads();
+  int64_t total = 0, wbase[kWarps];
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    wbase[w] = total;
+    total += s_wtot[w];
+  }
   if (!COPY) {
     if (threadIdx.x == 0) a.tile_bytes[tile] = total;
     return;
   }
-  const int64_t out_row_base = a.tile_rows[tile];
   const int64_t byte_base = a.tile_bytes[tile];
-  const OffT tile_src0 = a.offsets[row0];
-  const unsigned rank0 = s_prefix[r >> 6] + __popcll(selw & ((1ull << (r & 63)) - 1ull));
-  if (bits) {
-    unsigned j = rank0;
-    uint32_t run = static_cast<uint32_t>(excl);
-    OffT src = first_off;
-    const int64_t g = row0 + r;
-    unsigned cb = 0, nsel = 0;
-#pragma unroll
-    for (int k = 0; k < kFilterRowsPerThread; ++k) {
-      if (g + k < a.n) {
-        OffT next = a.offsets[g + k + 1];
-        if ((bits >> k) & 1) {
-          s_out[j] = run;
-          s_src[j] = static_cast<uint32_t>(src - tile_src0);
-          a.out_offsets[out_row_base + j] = static_cast<OffT>(byte_base + run);
-          run += len[k];
-          cb |= ((vbits >> k) & 1u) << nsel;
-          ++nsel;
-          ++j;
-        }
-        src = next;
-      }
-    }
-    if (HAS_VALID && cb) {
-      const unsigned q = static_cast<unsigned>(out_row_base & 31) + rank0;
-      atomicOr(&s_bits[q >> 5], cb << (q & 31));
-      if ((q & 31) + nsel > 32) atomicOr(&s_bits[(q >> 5) + 1], cb >> (32 - (q & 31)));
-    }
-  }
   const int n_rows = static_cast<int>(a.tile_rows[tile + 1] - out_row_base);
+  // second half: add the warp bases and write the new offsets, coalesced
+  for (int j = threadIdx.x; j < n_rows; j += kBinThreads) {
+    int64_t base = 0;
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w)
+      if (s_prefix[w * (kRowsPerWarp / 64)] <= static_cast<uint32_t>(j)) base = wbase[w];
+    const uint32_t v = s_out[j] + static_cast<uint32_t>(base);
+    s_out[j] = v;
+    a.out_offsets[out_row_base + j] = static_cast<OffT>(byte_base + v);
+  }
   if (threadIdx.x == 0) {
     s_out[n_rows] = static_cast<uint32_t>(total);
     if (tile == gridDim.x - 1) a.out_offsets[out_row_base + n_rows] = static_cast<OffT>(byte_base + total);
