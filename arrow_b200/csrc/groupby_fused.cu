@@ -250,22 +250,15 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
 // ---- partitioned path (groupby_partitioned.cuh) -------------------------------------------------
 
 template <typename V, int KW>
-static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, int64_t est_groups,
-                                 cudaStream_t s,
+static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, cudaStream_t s,
                                  unsigned long long* d_counters, unsigned long long* ovf_pairs, unsigned int* ovf_counts,
                                  uint64_t ovf_cap) {
   B2Context* ctx = g->ctx;
   constexpr bool kFloat = std::is_floating_point<V>::value;
   FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts, ovf_cap};
   const int pre_grid = ctx->sm_count * 4;
-  // rows per pre-aggregation slice: every slice ends with a flush of its distinct keys into the global
-  // table (random DRAM atomics the CTA has to wait for), so slices should be as long as the 2048-slot
-  // shared table allows -- about 1000 distinct keys, i.e. 1000 * rows / groups rows of hash-ordered tuples
-  int64_t slice_rows = est_groups > 0 ? 1000 * cn / est_groups : kPreSliceMin;
-  slice_rows = slice_rows < kPreSliceMin ? kPreSliceMin : (slice_rows > kPreSliceMax ? kPreSliceMax : slice_rows);
-  slice_rows = slice_rows / 2048 * 2048;
   if (passes == 0) {
-    preagg_kernel<true, kFloat, V, KW><<<pre_grid, kBlock, 0, s>>>(raw, Tuples{}, cn, (int)slice_rows, tref, d_counters);
+    preagg_kernel<true, kFloat, V, KW><<<pre_grid, kBlock, 0, s>>>(raw, Tuples{}, cn, tref, d_counters);
     B2_LAUNCHED();
     return B2_OK;
   }
@@ -316,8 +309,7 @@ static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, in
     B2_LAUNCHED();
     sorted = a.out;
   }
-  preagg_kernel<false, kFloat, int64_t, 8><<<pre_grid, kBlock, 0, s>>>(RawColumns{}, sorted, cn, (int)slice_rows, tref,
-                                                                       d_counters);
+  preagg_kernel<false, kFloat, int64_t, 8><<<pre_grid, kBlock, 0, s>>>(RawColumns{}, sorted, cn, tref, d_counters);
   B2_LAUNCHED();
   return B2_OK;
 }
@@ -365,10 +357,10 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
     int st;
     switch (kw) {
-      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, est, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, est, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, est, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, est, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
     }
     if (st != B2_OK) return st;
     B2_RETURN_NOT_OK(slot.fetch(s));

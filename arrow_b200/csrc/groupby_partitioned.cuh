@@ -11,7 +11,7 @@
 //                          look-back, smem-staged contiguous writes) move (key, value, flags)
 //                          tuples so that rows with equal hash digits become contiguous --
 //                          256 or 65536 partitions, i.e. ~G/65536 distinct keys per partition;
-//   3. preagg_kernel     : each CTA streams 8K..64K-row slices of the partitioned tuples through
+//   3. preagg_kernel     : each CTA streams 8192-row slices of the partitioned tuples through
 //                          a 2048-slot shared-memory table (smem CAS + smem atomicAdd), then
 //                          flushes the few distinct (key, sum, count) entries it found into
 //                          the global table -- G x few global atomics instead of 3 per row.
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_pass_kernel(PartArgs a) 
 
 // ---- pre-aggregation in shared memory, flush to the global table ----
 constexpr int kPreSlots = 2048;
-constexpr int kPreSliceMin = 8192, kPreSliceMax = 65536;  // rows per CTA iteration (chosen by the host)
+constexpr int kPreSlice = 8192;  // rows per CTA iteration
 constexpr int kPreProbe = 48;
 
 struct FusedTableRef {
@@ -261,8 +261,8 @@ __device__ __forceinline__ void global_accumulate(const FusedTableRef& t, unsign
 }
 
 template <bool RAW, bool IS_FLOAT, typename V, int KW>
-__global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples in, int64_t n, int slice_rows,
-                                                        FusedTableRef table, unsigned long long* counters) {
+__global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples in, int64_t n, FusedTableRef table,
+                                                        unsigned long long* counters) {
   __shared__ unsigned long long s_keys[kPreSlots + 2];  // +2: the empty-pattern key and the null key
   // integer sums live as (lo, hi) 32-bit halves updated with two native ATOMS.ADD.u32 and an explicit
   // carry: a 64-bit shared atomicAdd is a CAS loop on this part (0.64 cycles/lane spread, 40 when
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples i
   __shared__ unsigned long long s_sums[kPreSlots + 2];
   __shared__ unsigned int s_counts[kPreSlots + 2];
   __shared__ uint8_t s_used[kPreSlots + 2];  // slot touched (a group can exist with count 0)
-  const int64_t n_slices = (n + slice_rows - 1) / slice_rows;
+  const int64_t n_slices = (n + kPreSlice - 1) / kPreSlice;
   for (int64_t slice = blockIdx.x; slice < n_slices; slice += gridDim.x) {
     for (int i = threadIdx.x; i < kPreSlots + 2; i += kBlock) {
       s_keys[i] = kEmptyKey;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(kBlock) preagg_kernel(RawColumns raw, Tuples i
       s_used[i] = 0;
     }
     __syncthreads();
-    const int64_t lo = slice * slice_rows;
-    const int64_t hi = lo + slice_rows < n ? lo + slice_rows : n;
+    const int64_t lo = slice * kPreSlice;
+    const int64_t hi = lo + kPreSlice < n ? lo + kPreSlice : n;
     constexpr int kBatch = 8;  // rows loaded per thread before the dependent shared-memory work
     for (int64_t b0 = lo; b0 < hi; b0 += (int64_t)kBatch * kBlock) {
       unsigned long long kk[kBatch], vv[kBatch];
