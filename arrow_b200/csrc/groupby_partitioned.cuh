@@ -7,7 +7,7 @@
 // in SHARED memory instead:
 //   1. part_hist_kernel  : histogram of the low hash digits of every key (one read of the keys)
 //   2. part_pass_kernel  : 1 or 2 LSD radix passes on hash64(key) digits (the SortIndices
-//                          onesweep machinery: ticketed tiles, match-any ranking, decoupled
+//                          onesweep machinery: ticketed tiles, smem-atomic ranking, decoupled
 //                          look-back, smem-staged contiguous writes) move (key, value, flags)
 //                          tuples so that rows with equal hash digits become contiguous --
 //                          256 or 65536 partitions, i.e. ~G/65536 distinct keys per partition;

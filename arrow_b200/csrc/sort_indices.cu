@@ -18,13 +18,16 @@
 //              flip with -0.0 canonicalised for floats, NaN -> all-ones (AtEnd) or 0
 //              (AtStart), bitwise NOT for Descending (ties stay in index order).
 //   histogram: one read of the keys builds all digit histograms in shared memory.
-//   onesweep : per 8-bit digit ONE kernel -- tiles are claimed through an atomic ticket,
-//              ranked with warp match-any into per-warp digit counters, the tile's 256
-//              digit counts are published and the exclusive prefix over earlier tiles is
-//              fetched with decoupled look-back (no global scan pass); keys and indices
-//              are staged in shared memory in digit order so global writes are
-//              contiguous runs.  Passes whose digit is constant are skipped; the last
-//              executed pass writes the uint64 result directly.
+//   onesweep : per 8-bit digit ONE kernel -- 4096-key tiles (256 threads x 16 keys, 3 CTAs
+//              per SM) are claimed through an atomic ticket and ranked stably into
+//              per-warp digit counters (lanes with equal digits meet through a per-warp
+//              shared-memory mask table: ATOMS.OR + LDS, 10x cheaper than MATCH.ANY on this
+//              part); the tile's 256 digit counts are published, keys and indices are
+//              staged in shared memory in digit order, and only then the exclusive prefix
+//              over earlier tiles is fetched with a 4-deep prefetching decoupled look-back
+//              (no global scan pass), so global writes are contiguous runs.  Passes whose
+//              digit is constant are skipped; indices stay uint32 until the last executed
+//              pass, which writes the uint64 result directly.
 // Traffic per executed pass: read (K+4) + write (K+4) bytes per row (K = key bytes).
 // Algorithmic bytes: 16.125 B/row for int64 + validity.
 #include <cmath>

@@ -77,3 +77,27 @@ def test_dictionary_filter_take(ctx):
         idx = random_array(pa.int64(), 5000, 0.1, SEED + 2, lo=0, hi=19999)
         assert_equal(bc.take(dd, dev(idx, ctx)).to_arrow(), pc.take(d, idx))
         assert_equal(bc.take(dd, dev(idx, ctx)).to_arrow(), ora.take(d, idx))
+
+
+@pytest.mark.parametrize("shift", [1, 3, 5])
+def test_binary_filter_unaligned_data_buffer(ctx, shift):
+    """A byte buffer that does not start on an 8-byte boundary takes the byte-wise copy
+    path instead of the aligned-word path; both must agree with the reference."""
+    t = pa.large_string()
+    n = 20000
+    vals = random_array(t, n, 0.1, SEED + shift, lo=0, hi=40)
+    mask = random_array(pa.bool_(), n, 0.05, SEED + 9, hi=0.5)
+    aligned = dev(vals, ctx)
+    data = np.frombuffer(vals.buffers()[2], dtype=np.uint8)
+    raw = ctx.alloc(len(data) + 16)
+    host = np.ascontiguousarray(data)
+    ctx.h2d(raw.ptr + shift, host.ctypes.data, len(host))
+    ctx.sync()
+    moved = DeviceArray.from_pointers(ctx, t, n, aligned.buffers[1].ptr, validity_ptr=aligned.buffers[0].ptr,
+                                      null_count=vals.null_count, data2_ptr=raw.ptr + shift, keepalive=(aligned, raw))
+    for ns in ("drop", "emit_null"):
+        want = pc.filter(vals, mask, null_selection_behavior=ns)
+        assert_equal(bc.filter(moved, dev(mask, ctx), ns).to_arrow(), want, ns)
+        assert_equal(bc.filter(aligned, dev(mask, ctx), ns).to_arrow(), want, ns)
+    idx = random_array(pa.int32(), 5000, 0.05, SEED + 2, lo=0, hi=n - 1)
+    assert_equal(bc.take(moved, dev(idx, ctx)).to_arrow(), pc.take(vals, idx))
