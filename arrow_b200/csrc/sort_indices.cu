@@ -195,8 +195,8 @@ struct OnesweepArgs {
 
 template <typename K>
 constexpr size_t onesweep_smem() {
-  return kSortTile * sizeof(K) + kSortTile * sizeof(uint32_t) + 2 * kSortWarps * kRadix * sizeof(uint32_t) +
-         2 * kRadix * sizeof(uint32_t);
+  return kSortTile * sizeof(K) + kSortTile * sizeof(uint32_t) + kSortWarps * kRadix * sizeof(uint32_t) +
+         kRadix * sizeof(uint32_t);
 }
 
 template <typename K, bool LAST>
@@ -204,19 +204,14 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
   extern __shared__ __align__(16) uint8_t smem[];
   K* s_keys = reinterpret_cast<K*>(smem);
   uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
-  uint32_t* s_cnt = s_idx + kSortTile;            // [warps][256]
-  uint32_t* s_bin = s_cnt + kSortWarps * kRadix;  // [256] local exclusive bin offsets
-  uint32_t* s_gbase = s_bin + kRadix;             // [256] global base - local bin offset
-  uint32_t* s_match = s_gbase + kRadix;           // [warps][256] lane masks of the item being ranked
+  uint32_t* s_cnt = s_idx + kSortTile;              // [warps][256] counts, then tile-local offsets
+  uint32_t* s_gbase = s_cnt + kSortWarps * kRadix;  // [256] global base - local bin offset
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_warp_tot[kRadix / 32];
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) {
-    s_cnt[i] = 0;
-    s_match[i] = 0;
-  }
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) s_cnt[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * kSortTile;
@@ -236,30 +231,33 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
     const uint32_t i = warp * (32 * kSortItems) + j * 32 + lane;
     idxv[j] = (i < tile_n && a.idx_in) ? __ldcs(a.idx_in + base + i) : base + i;
   }
-  // rank within the warp's segment, in element order (=> stable)
-  // Lanes holding the same digit find each other through a per-warp mask table in shared memory
-  // (atomicOr of the lane bit, read back the mask) instead of MATCH.ANY: measured on this part
-  // MATCH.ANY costs 1.83 cycles/lane/SM, ATOMS.OR 0.15 and LDS 0.17 (profiles/smem_probe_r01.txt),
-  // and the ranking step -- not HBM -- was what bounded the pass.
+  // rank within the warp's segment, in element order (=> stable).  Lanes holding the same digit
+  // find each other with 8 ballots (one per digit bit) -- registers only; the kernel is bound by
+  // shared-memory wavefronts (ncu: 51 % short-scoreboard + MIO stalls, 58 % of the wavefronts
+  // bank conflicts of random digits), and MATCH.ANY costs 1.83 cycles/lane on this part
+  // (profiles/smem_probe_r01.txt).  Only the lowest lane of a group touches the warp's counter.
   uint32_t* wc = s_cnt + warp * kRadix;
-  uint32_t* wm = s_match + warp * kRadix;
   uint16_t rank[kSortItems];
   const unsigned lt = lanemask_lt();
-  const unsigned lane_bit = 1u << lane;
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const unsigned digit = static_cast<unsigned>(key[j] >> a.shift) & (kRadix - 1);
-    atomicOr(&wm[digit], lane_bit);
-    __syncwarp();
-    const unsigned peers = wm[digit];
-    const unsigned prev = wc[digit];
-    __syncwarp();
-    if ((peers & lt) == 0) {  // lowest lane of the group: bump the counter, clear the mask for the next item
-      wc[digit] = prev + __popc(peers);
-      wm[digit] = 0;
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+      const bool bit = (digit >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
     }
+    const int leader = __ffs(peers) - 1;
+    unsigned prev = 0;
+    if ((int)lane == leader) {
+      prev = wc[digit];
+      wc[digit] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, leader);
     rank[j] = static_cast<uint16_t>(prev + __popc(peers & lt));
-    __syncwarp();
+    __syncwarp();  // the next item's leader may be another lane reading the counter just written
   }
   __syncthreads();
 
@@ -294,7 +292,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
     for (int w = 0; w < kRadix / 32; ++w)
       if (w < (int)warp) woff += s_warp_tot[w];
     bin_off = woff + incl - run;
-    s_bin[tid] = bin_off;
+    // fold the digit's tile-local start into the per-warp offsets: one lookup per key when staging
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) s_cnt[w * kRadix + tid] += bin_off;
   }
   __syncthreads();
 
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const unsigned digit = static_cast<unsigned>(key[j] >> a.shift) & (kRadix - 1);
-    const uint32_t pos = s_bin[digit] + wc[digit] + rank[j];
+    const uint32_t pos = wc[digit] + rank[j];
     s_keys[pos] = key[j];
     s_idx[pos] = idxv[j];
   }
