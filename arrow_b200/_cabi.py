@@ -112,6 +112,7 @@ PROTOTYPES = [
     ("b2_grouper_num_groups", C.c_int, [_P, C.POINTER(C.c_uint32)]),
     ("b2_grouper_uniques", C.c_int, [_P, _A, _P]),
     ("b2_grouper_reset", C.c_int, [_P]),
+    ("b2_vector_hash", C.c_int, [_P, _A, C.c_int, _A, _A, _A, _P]),
     ("b2_hashagg_create", C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(B2HashAggOptions), C.POINTER(_P)]),
     ("b2_hashagg_destroy", None, [_P]),
     ("b2_hashagg_resize", C.c_int, [_P, C.c_int64, _P]),

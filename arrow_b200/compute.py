@@ -295,6 +295,50 @@ def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", orde
 
 
 # ------------------------------------------------------------------------------------
+# unique / value_counts / dictionary_encode (kernels/vector_hash.cc:782-830)
+# ------------------------------------------------------------------------------------
+def _null_encoding(v) -> int:
+    if v in ("mask", 0):
+        return 0
+    if v in ("encode", 1):
+        return 1
+    raise ValueError(f'"{v}" is not a valid null encoding behavior')
+
+
+def _vector_hash(arr: DeviceArray, null_encoding: int, want_indices: bool, want_counts: bool):
+    ctx = arr.ctx
+    ca, ci, cd, cc = arr._c(), cabi.B2Array(), cabi.B2Array(), cabi.B2Array()
+    check(ctx.lib.b2_vector_hash(ctx.handle, C.byref(ca), null_encoding, C.byref(ci) if want_indices else None,
+                                 C.byref(cd), C.byref(cc) if want_counts else None, ctx.stream))
+    dictionary = _out(ctx, cd, arr.type)
+    indices = _out(ctx, ci, pa.dictionary(pa.int32(), arr.type), dictionary) if want_indices else None
+    counts = _out(ctx, cc, pa.int64()) if want_counts else None
+    return indices, dictionary, counts
+
+
+def unique(arr: DeviceArray) -> DeviceArray:
+    """unique: distinct values in first-occurrence order, null included (vector_hash.cc:65-97,791)."""
+    return _vector_hash(arr, 1, False, False)[1]
+
+
+def value_counts(arr: DeviceArray):
+    """value_counts: (values, counts) = the two fields of the reference's struct result
+    (vector_hash.cc:101-168,634,807); `to_struct` below assembles the StructArray on the host."""
+    _, values, counts = _vector_hash(arr, 1, False, True)
+    return values, counts
+
+
+def value_counts_to_struct(values: DeviceArray, counts: DeviceArray) -> pa.StructArray:
+    return pa.StructArray.from_arrays([values.to_arrow(), counts.to_arrow()], names=["values", "counts"])
+
+
+def dictionary_encode(arr: DeviceArray, null_encoding="mask") -> DeviceArray:
+    """dictionary_encode: int32 indices + dictionary (vector_hash.cc:173-232,826;
+    DictionaryEncodeOptions api_vector.h:66-82)."""
+    return _vector_hash(arr, _null_encoding(null_encoding), True, False)[0]
+
+
+# ------------------------------------------------------------------------------------
 # grouper + hash aggregates
 # ------------------------------------------------------------------------------------
 class Grouper:
@@ -445,6 +489,7 @@ _REGISTRY = {
     "multiply_checked": multiply_checked, "divide_checked": divide_checked,
     "equal": equal, "not_equal": not_equal, "greater": greater, "greater_equal": greater_equal,
     "less": less, "less_equal": less_equal,
+    "unique": unique, "value_counts": value_counts, "dictionary_encode": dictionary_encode,
 }
 
 
@@ -467,4 +512,6 @@ def call_function(name: str, args: Sequence, options=None):
         return fn(*args, boundscheck=getattr(options, "boundscheck", True))
     if name == "array_sort_indices":
         return fn(*args, order=options.order, null_placement=options.null_placement)
+    if name == "dictionary_encode":
+        return fn(*args, null_encoding=getattr(options, "null_encoding", options))
     return fn(*args)

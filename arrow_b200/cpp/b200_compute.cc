@@ -125,6 +125,7 @@ static void MoveInto(std::shared_ptr<ArrayData> produced, cp::ExecResult* out) {
   dst->null_count = produced->null_count.load();
   dst->offset = produced->offset;
   dst->buffers = std::move(produced->buffers);
+  dst->child_data = std::move(produced->child_data);
   dst->dictionary = std::move(produced->dictionary);
 }
 
@@ -442,6 +443,67 @@ static Status AddSelectionFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
 }
 
 // ------------------------------------------------------------------------------------------
+// unique / value_counts / dictionary_encode (compute/kernels/vector_hash.cc:782-830)
+// ------------------------------------------------------------------------------------------
+static Status UniqueExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  B2Array v, d;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  B200_RETURN_NOT_OK(b2_vector_hash(kd.rt->context(), &v, /*ENCODE*/ 1, nullptr, &d, nullptr, nullptr));
+  MoveInto(AdoptOutput(kd.rt, d, batch[0].type()->GetSharedPtr()), out);
+  return Status::OK();
+}
+
+static Status ValueCountsExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  B2Array v, d, c;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  B200_RETURN_NOT_OK(b2_vector_hash(kd.rt->context(), &v, /*ENCODE*/ 1, nullptr, &d, &c, nullptr));
+  // struct<values, counts> with no top-level validity (vector_hash.cc:634)
+  auto produced = std::make_shared<ArrayData>(out->type()->GetSharedPtr(), d.length, 0);
+  produced->buffers.push_back(nullptr);
+  produced->child_data.push_back(AdoptOutput(kd.rt, d, batch[0].type()->GetSharedPtr()));
+  produced->child_data.push_back(AdoptOutput(kd.rt, c, arrow::int64()));
+  MoveInto(std::move(produced), out);
+  return Status::OK();
+}
+
+static Status DictEncodeExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  const auto& opts = OptionsState<cp::DictionaryEncodeOptions>::Get(ctx);
+  B2Array v, i, d;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  const int mode = opts.null_encoding_behavior == cp::DictionaryEncodeOptions::ENCODE ? 1 : 0;
+  B200_RETURN_NOT_OK(b2_vector_hash(kd.rt->context(), &v, mode, &i, &d, nullptr, nullptr));
+  MoveInto(AdoptOutput(kd.rt, i, out->type()->GetSharedPtr(), AdoptOutput(kd.rt, d, batch[0].type()->GetSharedPtr())), out);
+  return Status::OK();
+}
+
+static Result<TypeHolder> ValueCountsType(cp::KernelContext*, const std::vector<TypeHolder>& types) {
+  return TypeHolder(arrow::struct_({arrow::field("values", types[0].GetSharedPtr()), arrow::field("counts", arrow::int64())}));
+}
+static Result<TypeHolder> DictEncodeType(cp::KernelContext*, const std::vector<TypeHolder>& types) {
+  return TypeHolder(arrow::dictionary(arrow::int32(), types[0].GetSharedPtr()));
+}
+
+static Status AddHashFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
+  static const cp::DictionaryEncodeOptions kDictDefaults = cp::DictionaryEncodeOptions::Defaults();
+  auto unique = std::make_shared<Forwarding<cp::VectorFunction>>("unique", cp::Arity::Unary(), DocFor({"array"}, ""), nullptr);
+  auto counts = std::make_shared<Forwarding<cp::VectorFunction>>("value_counts", cp::Arity::Unary(), DocFor({"array"}, ""), nullptr);
+  auto encode = std::make_shared<Forwarding<cp::VectorFunction>>("dictionary_encode", cp::Arity::Unary(),
+                                                                 DocFor({"array"}, "DictionaryEncodeOptions"), &kDictDefaults);
+  for (const auto& ty : NumericTypes()) {
+    ARROW_RETURN_NOT_OK(unique->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(FirstType), UniqueExec, nullptr)));
+    ARROW_RETURN_NOT_OK(counts->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(ValueCountsType), ValueCountsExec, nullptr)));
+    ARROW_RETURN_NOT_OK(encode->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(DictEncodeType), DictEncodeExec,
+                                                           OptionsState<cp::DictionaryEncodeOptions>::Init)));
+  }
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(unique), true));
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(counts), true));
+  return reg->AddFunction(std::move(encode), true);
+}
+
+// ------------------------------------------------------------------------------------------
 // hash aggregates: the HashAggregateKernel contract (compute/kernel.h:720-769)
 // ------------------------------------------------------------------------------------------
 struct HashAggState : public cp::KernelState {
@@ -630,6 +692,7 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   for (const auto& c : cmp) ARROW_RETURN_NOT_OK(AddBinaryFunction(reg, rt, c.first, c.second, true));
   ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<CastFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddSelectionFunctions(reg, rt));
+  ARROW_RETURN_NOT_OK(AddHashFunctions(reg, rt));
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},
                                               {"hash_count_all", B2_HASH_COUNT_ALL}, {"hash_mean", B2_HASH_MEAN},
                                               {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX}};

@@ -230,6 +230,22 @@ int main() {
     }
   }
 
+  // ---- unique / value_counts / dictionary_encode (kernels/vector_hash_test.cc:159-250) ----
+  {
+    auto k64 = RandomNumeric<arrow::Int64Type>(60000, 0.05, 91, -300, 300);
+    auto k16 = RandomNumeric<arrow::UInt16Type>(60000, 0.0, 92, 0, 2000);
+    auto kf = RandomNumeric<arrow::Int32Type>(5000, 0.3, 93, 0, 40);
+    auto kf64 = UNWRAP(cp::Cast(*kf, arrow::float64()));
+    for (const auto& a : {k64, k16, kf64, k64->Slice(7, 1000)}) {
+      const std::string tag = "(" + a->type()->ToString() + ", " + std::to_string(a->length()) + " rows)";
+      h.Check("unique" + tag, "unique", {a});
+      h.Check("value_counts" + tag, "value_counts", {a});
+      cp::DictionaryEncodeOptions mask(cp::DictionaryEncodeOptions::MASK), encode(cp::DictionaryEncodeOptions::ENCODE);
+      h.Check("dictionary_encode MASK" + tag, "dictionary_encode", {a}, &mask);
+      h.Check("dictionary_encode ENCODE" + tag, "dictionary_encode", {a}, &encode);
+    }
+  }
+
   // ---- Grouper: TestGrouper::ValidateConsume (row/grouper_test.cc:736-760) ----
   {
     auto keys = RandomNumeric<arrow::Int64Type>(50000, 0.05, 77, 0, 500);

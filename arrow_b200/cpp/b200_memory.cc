@@ -120,6 +120,8 @@ Result<std::unique_ptr<arrow::Buffer>> B200MemoryManager::CopyNonOwnedTo(const a
 bool IsOnDevice(const arrow::ArrayData& data) {
   for (const auto& b : data.buffers)
     if (b && !b->is_cpu()) return true;
+  for (const auto& c : data.child_data)
+    if (c && IsOnDevice(*c)) return true;
   if (data.dictionary && IsOnDevice(*data.dictionary)) return true;
   return false;
 }

@@ -3,6 +3,7 @@
   c1  Filter(int64, bool mask)            1B rows, values null_p 0.1, mask non-null, s = 0.5
   c3  group-by sum+count, int64 key/value 1B rows, 10M groups (fused table and Grouper+aggregators)
   c4  SortIndices int64 + validity        1B rows (wide range) and narrow range [0, 4095]
+  f1  dictionary_encode / value_counts of an int64 column (1M distinct values), 500M rows
   c5  large_utf8 Filter                   500M strings, 0-32 B, null_p 0.1, s = 0.5  (+ dictionary Take)
   cmp compare int64 -> bool               1B rows
 Each prints one JSON line: rows/s, algorithmic GB/s (SURVEY.md section 8d byte model) and the
@@ -53,7 +54,7 @@ def report(name, n, ms, alg_bytes, extra=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_000_000_000)
-    ap.add_argument("--only", default="c1,cmp,c3,c4,c5")
+    ap.add_argument("--only", default="c1,cmp,c3,c4,c5,f1")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -156,6 +157,20 @@ def main():
         take_idx = DeviceArray.from_pointers(ctx, pa.int64(), m, take_idx_t.data_ptr())
         ms = timed(stream, lambda: bc.take(col, take_idx), args.reps, warmup=1)
         report("c5 dictionary take (int32 index column, random int64 idx)", m, ms, m * (8 + 4 + 4))
+        del col, take_idx, dict_idx_t, take_idx_t
+
+    if "f1" in only:
+        # produce config 5's dictionary column on the device
+        m = n // 2
+        distinct = 1_000_000
+        keys_t = torch.randint(0, distinct, (m,), dtype=torch.int64, device="cuda", generator=gen)
+        kvalid_t, k_nulls = make_validity(torch, m, gen)
+        col = DeviceArray.from_pointers(ctx, pa.int64(), m, keys_t.data_ptr(), validity_ptr=kvalid_t.data_ptr(), null_count=k_nulls)
+        ms = timed(stream, lambda: bc.dictionary_encode(col), args.reps, warmup=1)
+        nd = len(bc.unique(col))
+        report("f1 dictionary_encode int64 (1M distinct, null_p 0.1)", m, ms, m * (8 + 0.125 + 4 + 0.125) + nd * 8, {"dictionary": nd})
+        ms = timed(stream, lambda: bc.value_counts(col), args.reps, warmup=1)
+        report("f1 value_counts int64 (1M distinct, null_p 0.1)", m, ms, m * (8 + 0.125) + nd * 16, {"dictionary": nd})
 
 
 if __name__ == "__main__":

@@ -271,6 +271,23 @@ B2_API int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream);
 B2_API int b2_grouper_reset(B2Grouper* g);
 
 /* ---------------------------------------------------------------------------
+ * unique / value_counts / dictionary_encode over one fixed-width column.
+ * Replaces UniqueAction / ValueCountsAction / DictEncodeAction + RegularHashKernel
+ * (compute/kernels/vector_hash.cc:65-235,236-470; registration :782-830;
+ * DictionaryEncodeOptions compute/api_vector.h:66-82).
+ *   out_dictionary : the distinct values in first-occurrence order (required)
+ *   out_indices    : int32 index of every row into the dictionary, or NULL if not wanted
+ *   out_counts     : int64 occurrences of every dictionary entry, or NULL if not wanted
+ *   null_encoding  : 0 = MASK  (null rows -> null index; no null in the dictionary)
+ *                    1 = ENCODE (null is a dictionary entry; what unique / value_counts use)
+ * unique = (ENCODE, NULL, &d, NULL); value_counts = (ENCODE, NULL, &d, &c);
+ * dictionary_encode = (mode, &i, &d, NULL).
+ * ------------------------------------------------------------------------- */
+B2_API int b2_vector_hash(B2Context* ctx, const B2Array* values, int null_encoding,
+                          B2Array* out_indices, B2Array* out_dictionary, B2Array* out_counts,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------
  * Hash aggregates.  Replaces the HashAggregateKernel contract
  * {init,resize,consume,merge,finalize} (compute/kernel.h:720-769) for
  * GroupedSumImpl / GroupedCountImpl / GroupedCountAllImpl / GroupedMeanImpl /

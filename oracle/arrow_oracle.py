@@ -421,6 +421,48 @@ class Grouper:
 
 
 # ---------------------------------------------------------------------------------------
+# unique / value_counts / dictionary_encode   (kernels/vector_hash.cc:65-235, 782-830)
+# The memo table hands out indices in first-occurrence order (RegularHashKernel::DoAppend,
+# vector_hash.cc:300-340); UniqueAction and ValueCountsAction encode null as a value,
+# DictEncodeAction only with DictionaryEncodeOptions::ENCODE (api_vector.h:66-82).
+# ---------------------------------------------------------------------------------------
+def _memo(arr: pa.Array, encode_nulls: bool):
+    v, valid = values(arr), validity(arr)
+    raw = v.view(np.uint8).reshape(len(v), -1) if len(v) else np.zeros((0, 1), np.uint8)
+    table, order, idx = {}, [], np.zeros(len(v), dtype=np.int32)
+    for i in range(len(v)):
+        if not valid[i] and not encode_nulls:
+            continue
+        key = raw[i].tobytes() if valid[i] else None
+        g = table.get(key)
+        if g is None:
+            g = table[key] = len(order)
+            order.append(i)
+        idx[i] = g
+    order = np.array(order, dtype=np.int64)
+    uniq_valid = valid[order] if len(order) else np.zeros(0, bool)
+    uniq = make_array(arr.type, v[order] if len(order) else v[:0], uniq_valid)
+    return idx, uniq
+
+
+def unique(arr: pa.Array) -> pa.Array:
+    return _memo(arr, True)[1]
+
+
+def value_counts(arr: pa.Array) -> pa.StructArray:
+    idx, uniq = _memo(arr, True)
+    counts = np.bincount(idx, minlength=len(uniq)).astype(np.int64)
+    return pa.StructArray.from_arrays([uniq, make_array(pa.int64(), counts)], names=["values", "counts"])
+
+
+def dictionary_encode(arr: pa.Array, null_encoding: str = "mask") -> pa.DictionaryArray:
+    encode = null_encoding == "encode"
+    idx, uniq = _memo(arr, encode)
+    idx_valid = None if encode else validity(arr)
+    return pa.DictionaryArray.from_arrays(make_array(pa.int32(), idx, idx_valid), uniq)
+
+
+# ---------------------------------------------------------------------------------------
 # Hash aggregates   (kernels/hash_aggregate_numeric.cc:44-434, kernels/hash_aggregate.cc:61-420)
 # ---------------------------------------------------------------------------------------
 def _sum_type(t):

@@ -467,3 +467,41 @@ def test_large_filter_take_sort_properties(ctx):
     sk = np.frombuffer(keys.buffers()[1], dtype=np.int64)[idx[:nv].astype(np.int64)]
     assert np.all(sk[1:] >= sk[:-1])
     del kv
+
+
+# ---------------------------------------------------------------- unique / value_counts / dictionary_encode
+def test_kat_vector_hash(ctx):
+    from tests.test_oracle import VECTOR_HASH_KAT
+    for t in (pa.int8(), pa.uint16(), pa.int32(), pa.int64(), pa.float32(), pa.float64()):
+        for vals, want in VECTOR_HASH_KAT["unique"]:
+            assert_equal(bc.unique(dev(pa.array(vals, t), ctx)).to_arrow(), pa.array(want, t))
+        for vals, uniq, counts in VECTOR_HASH_KAT["value_counts"]:
+            v, c = bc.value_counts(dev(pa.array(vals, t), ctx))
+            assert_equal(v.to_arrow(), pa.array(uniq, t))
+            assert_equal(c.to_arrow(), pa.array(counts, pa.int64()))
+        for vals, dictionary, idx in VECTOR_HASH_KAT["dictionary_encode"]:
+            got = bc.dictionary_encode(dev(pa.array(vals, t), ctx)).to_arrow()
+            assert got.equals(pa.DictionaryArray.from_arrays(pa.array(idx, pa.int32()), pa.array(dictionary, t)))
+        for empty in (pa.array([], t), pa.array([None, None], t)):
+            assert_equal(bc.unique(dev(empty, ctx)).to_arrow(), pc.unique(empty))
+            assert bc.dictionary_encode(dev(empty, ctx)).to_arrow().equals(pc.dictionary_encode(empty))
+            assert bc.dictionary_encode(dev(empty, ctx), "encode").to_arrow().equals(pc.dictionary_encode(empty, "encode"))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_vector_hash_random(ctx, t):
+    for n, hi, null_p in ((1, 3, 0.0), (300, 7, 0.2), (70000, 100, 0.05), (70000, 5000, 0.0), (3000, 3000, 1.0),
+                          (300000, 120, 0.01)):
+        a = random_array(t, n, null_p, SEED + n, lo=0, hi=hi, offset=3)
+        d = dev(a, ctx)
+        assert_equal(bc.unique(d).to_arrow(), pc.unique(a), f"unique {t} {n}")
+        assert_equal(bc.unique(d).to_arrow(), ora.unique(a))
+        v, c = bc.value_counts(d)
+        assert bc.value_counts_to_struct(v, c).equals(pc.value_counts(a)), f"value_counts {t} {n}"
+        for mode in ("mask", "encode"):
+            got = bc.dictionary_encode(d, mode).to_arrow()
+            assert got.equals(pc.dictionary_encode(a, null_encoding=mode)), f"dictionary_encode {t} {n} {mode}"
+            assert got.equals(ora.dictionary_encode(a, mode))
+    assert bc.call_function("unique", [dev(pa.array([3, 3, 1], t), ctx)]).to_arrow().equals(pa.array([3, 1], t))
+    with pytest.raises(pa.ArrowNotImplementedError):
+        bc.unique(dev(pa.array(["a", "b"]), ctx))

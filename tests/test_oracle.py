@@ -281,3 +281,37 @@ def test_dictionary_filter_take_vs_reference():
         assert_equal(ora.filter(d, mask, ns), pc.filter(d, mask, null_selection_behavior=ns))
     idx = random_array(pa.int64(), 500, 0.1, SEED + 2, lo=0, hi=1999)
     assert_equal(ora.take(d, idx), pc.take(d, idx))
+
+
+# KATs transcribed from the reference's own tests (compute/kernels/vector_hash_test.cc):
+# TestHashKernelPrimitive Unique :177-180, ValueCounts :209-212, DictEncode :242-244.
+VECTOR_HASH_KAT = {
+    "unique": [([2, None, 2, 1], [2, None, 1]), ([None, None, 3, 1], [None, 3, 1])],
+    "value_counts": [([2, None, 2, 1, 2, 3, None], [2, None, 1, 3], [3, 2, 1, 1])],
+    "dictionary_encode": [([2, None, 2, 1, 2, 3], [2, 1, 3], [0, None, 0, 1, 0, 2])],
+}
+
+
+def test_kat_vector_hash():
+    for t in (pa.int8(), pa.uint16(), pa.int32(), pa.int64(), pa.float32(), pa.float64()):
+        for vals, want in VECTOR_HASH_KAT["unique"]:
+            assert_equal(ora.unique(pa.array(vals, t)), pa.array(want, t))
+        for vals, uniq, counts in VECTOR_HASH_KAT["value_counts"]:
+            assert ora.value_counts(pa.array(vals, t)).equals(pa.StructArray.from_arrays(
+                [pa.array(uniq, t), pa.array(counts, pa.int64())], names=["values", "counts"]))
+        for vals, dictionary, idx in VECTOR_HASH_KAT["dictionary_encode"]:
+            assert ora.dictionary_encode(pa.array(vals, t)).equals(
+                pa.DictionaryArray.from_arrays(pa.array(idx, pa.int32()), pa.array(dictionary, t)))
+        for empty in (pa.array([], t), pa.array([None, None], t)):
+            assert_equal(ora.unique(empty), pc.unique(empty))
+            assert ora.dictionary_encode(empty).equals(pc.dictionary_encode(empty))
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_vector_hash_vs_reference(t):
+    for n, hi, null_p in ((1, 3, 0.0), (300, 7, 0.2), (5000, 100, 0.05), (5000, 100, 0.0), (2000, 2000, 1.0)):
+        a = random_array(t, n, null_p, SEED + n, lo=0, hi=hi, offset=3)
+        assert_equal(ora.unique(a), pc.unique(a))
+        assert ora.value_counts(a).equals(pc.value_counts(a))
+        for mode in ("mask", "encode"):
+            assert ora.dictionary_encode(a, mode).equals(pc.dictionary_encode(a, null_encoding=mode)), (t, n, mode)
