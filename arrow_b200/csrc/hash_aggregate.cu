@@ -62,21 +62,43 @@ struct AggState {
   uint8_t* flags;               // [G] bit0 = saw a null, bit1 = has a value
 };
 
+// counts[g] += 1 for the lanes with inc: lanes of a warp holding the same group are merged first
+// (MATCH.ANY, one atomic per distinct group per warp) so a hot group does not serialise on one address
+__device__ __forceinline__ void count_merged(unsigned long long* counts, uint32_t g, bool inc) {
+  const unsigned live = __ballot_sync(0xffffffffu, inc);
+  if (inc) {
+    const unsigned peers = __match_any_sync(live, g);
+    if ((peers & lanemask_lt()) == 0) atomicAdd(&counts[g], static_cast<unsigned long long>(__popc(peers)));
+  }
+}
+
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __restrict__ values,
                                                                  BitmapReader valid,
                                                                  const uint32_t* __restrict__ ids, int64_t n,
                                                                  AggState st, int count_mode, uint32_t g_lo,
                                                                  uint32_t g_hi) {
+  if (KIND == B2_HASH_COUNT) {
+    // a few hot groups would serialise their atomics on one L2 address: merge equal ids inside the warp first
+    const unsigned lane = lane_id();
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t base = blockIdx.x * (int64_t)kBlock + (threadIdx.x & ~31u); base < n; base += stride) {
+      const int64_t i = base + lane;
+      bool inc = false;
+      uint32_t g = 0;
+      if (i < n) {
+        g = __ldcs(ids + i);
+        const bool ok = valid.bit(i);
+        inc = g >= g_lo && g < g_hi && (count_mode == 2 || (count_mode == 0 ? ok : !ok));
+      }
+      count_merged(st.counts, g, inc);
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
     const uint32_t g = __ldcs(ids + i);
     if (g < g_lo || g >= g_hi) continue;  // another band's group (see launch_consume)
     const bool ok = valid.bit(i);
-    if (KIND == B2_HASH_COUNT) {
-      bool inc = count_mode == 2 || (count_mode == 0 ? ok : !ok);
-      if (inc) atomicAdd(&st.counts[g], 1ull);
-      continue;
-    }
     if (!ok) {
       st.flags[g] |= 1;  // benign race: only ever sets bit 0 (byte store of an OR'd value)
       continue;
@@ -103,8 +125,12 @@ __global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __rest
 
 __global__ void __launch_bounds__(kBlock) hashagg_countall_kernel(const uint32_t* __restrict__ ids, int64_t n,
                                                                   unsigned long long* counts) {
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
-    atomicAdd(&counts[ids[i]], 1ull);
+  const unsigned lane = lane_id();
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t base = blockIdx.x * (int64_t)kBlock + (threadIdx.x & ~31u); base < n; base += stride) {
+    const int64_t i = base + lane;
+    count_merged(counts, i < n ? __ldcs(ids + i) : 0u, i < n);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) hashagg_fill_kernel(unsigned long long* p, unsigned long long v,

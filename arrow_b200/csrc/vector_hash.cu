@@ -45,10 +45,23 @@ __global__ void __launch_bounds__(kBlock) remap_ids_kernel(const uint32_t* __res
   }
 }
 
+// counts[id] += 1 per row.  Lanes of a warp holding the same id are merged first (MATCH.ANY, one
+// atomic per distinct id per warp): a hot value -- e.g. the null entry of a column with 10 % nulls --
+// would otherwise serialise tens of millions of atomics on one L2 address (50 ms per 500M rows).
 __global__ void __launch_bounds__(kBlock) count_ids_kernel(const uint32_t* __restrict__ ids, int64_t n,
                                                            unsigned long long* counts) {
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
-    atomicAdd(&counts[__ldcs(ids + i)], 1ull);
+  const unsigned lane = lane_id();
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t base = blockIdx.x * (int64_t)kBlock + (threadIdx.x & ~31u); base < n; base += stride) {
+    const int64_t i = base + lane;
+    const bool in = i < n;
+    const uint32_t g = in ? __ldcs(ids + i) : 0u;
+    const unsigned live = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const unsigned peers = __match_any_sync(live, g);
+      if ((peers & lanemask_lt()) == 0) atomicAdd(&counts[g], static_cast<unsigned long long>(__popc(peers)));
+    }
+  }
 }
 
 }  // namespace b2
