@@ -52,6 +52,19 @@ class B2HashAggOptions(C.Structure):
     ]
 
 
+class B2ReduceResult(C.Structure):
+    _fields_ = [
+        ("count", C.c_int64),
+        ("null_count", C.c_int64),
+        ("sum_bits", C.c_uint64),
+        ("min_bits", C.c_uint64),
+        ("max_bits", C.c_uint64),
+        ("dsum_bits", C.c_uint64),
+        ("acc_type", C.c_int32),
+        ("value_type", C.c_int32),
+    ]
+
+
 # status codes (arrow::StatusCode values)
 OK, OUT_OF_MEMORY, KEY_ERROR, TYPE_ERROR, INVALID, IO_ERROR, CAPACITY_ERROR, INDEX_ERROR = range(8)
 NOT_IMPLEMENTED = 10
@@ -113,6 +126,7 @@ PROTOTYPES = [
     ("b2_grouper_uniques", C.c_int, [_P, _A, _P]),
     ("b2_grouper_reset", C.c_int, [_P]),
     ("b2_vector_hash", C.c_int, [_P, _A, C.c_int, _A, _A, _A, _P]),
+    ("b2_reduce", C.c_int, [_P, _A, C.POINTER(B2ReduceResult), _P]),
     ("b2_hashagg_create", C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(B2HashAggOptions), C.POINTER(_P)]),
     ("b2_hashagg_destroy", None, [_P]),
     ("b2_hashagg_resize", C.c_int, [_P, C.c_int64, _P]),

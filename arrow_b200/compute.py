@@ -15,6 +15,7 @@ reproduced here are the reference's:
 """
 from __future__ import annotations
 
+import builtins
 import ctypes as C
 from typing import Optional, Sequence, Union
 
@@ -58,8 +59,8 @@ def common_numeric(ids: Sequence[int]) -> int:
         return cabi.DOUBLE
     if cabi.FLOAT in ids:
         return cabi.FLOAT
-    ms = max([_SIGNED[i] for i in ids if i in _SIGNED], default=0)
-    mu = max([_UNSIGNED[i] for i in ids if i in _UNSIGNED], default=0)
+    ms = builtins.max([_SIGNED[i] for i in ids if i in _SIGNED], default=0)
+    mu = builtins.max([_UNSIGNED[i] for i in ids if i in _UNSIGNED], default=0)
     if ms == 0:
         return {8: cabi.UINT8, 16: cabi.UINT16, 32: cabi.UINT32}.get(mu, cabi.UINT64)
     if ms <= mu:
@@ -295,6 +296,85 @@ def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", orde
 
 
 # ------------------------------------------------------------------------------------
+# ungrouped aggregates (kernels/aggregate_basic.cc, aggregate_basic.inc.cc)
+# ------------------------------------------------------------------------------------
+def _reduce(arr: DeviceArray) -> "cabi.B2ReduceResult":
+    ctx = arr.ctx
+    ca, r = arr._c(), cabi.B2ReduceResult()
+    check(ctx.lib.b2_reduce(ctx.handle, C.byref(ca), C.byref(r), ctx.stream))
+    return r
+
+
+def _from_bits(bits: int, t: pa.DataType):
+    raw = np.array([bits], dtype=np.uint64)
+    if pa.types.is_floating(t):
+        return raw.view(np.float64)[0]
+    return raw.view(np.int64)[0] if pa.types.is_signed_integer(t) else raw[0]
+
+
+def _acc_type(t: pa.DataType) -> pa.DataType:
+    if pa.types.is_floating(t):
+        return pa.float64()
+    return pa.int64() if pa.types.is_signed_integer(t) else pa.uint64()
+
+
+def sum(arr: DeviceArray, skip_nulls: bool = True, min_count: int = 1) -> pa.Scalar:  # noqa: A001
+    """sum (SumImpl::Finalize, aggregate_basic.inc.cc:95-103): null if a null was seen and
+    !skip_nulls, or fewer than min_count valid values; accumulator = int64 / uint64 / double."""
+    r, out_t = _reduce(arr), _acc_type(arr.type)
+    if (not skip_nulls and r.null_count > 0) or r.count < min_count:
+        return pa.scalar(None, out_t)
+    return pa.scalar(_from_bits(r.sum_bits, out_t).item(), out_t)
+
+
+def mean(arr: DeviceArray, skip_nulls: bool = True, min_count: int = 1) -> pa.Scalar:
+    """mean (MeanImpl, aggregate_basic.inc.cc:263-283): the sum is accumulated in double, then / count."""
+    r = _reduce(arr)
+    if (not skip_nulls and r.null_count > 0) or r.count < min_count:
+        return pa.scalar(None, pa.float64())
+    with np.errstate(invalid="ignore", divide="ignore"):  # no valid value and min_count == 0: 0/0 = NaN like the reference
+        return pa.scalar(float(_from_bits(r.dsum_bits, pa.float64()) / np.float64(r.count)), pa.float64())
+
+
+def min_max(arr: DeviceArray, skip_nulls: bool = True, min_count: int = 1) -> pa.Scalar:
+    """min_max (MinMaxImpl::Finalize, aggregate_basic.inc.cc:834-853): struct<min, max> of the input
+    type; min_count is at least 1 (:783)."""
+    r, t = _reduce(arr), arr.type
+    st = pa.struct([("min", t), ("max", t)])
+    if (r.null_count > 0 and not skip_nulls) or r.count < builtins.max(1, min_count):
+        return pa.scalar({"min": None, "max": None}, st)
+    wide = _acc_type(t)
+    lo, hi = _from_bits(r.min_bits, wide), _from_bits(r.max_bits, wide)
+    nt = np.dtype(t.to_pandas_dtype()).type
+    return pa.scalar({"min": nt(lo).item(), "max": nt(hi).item()}, st)
+
+
+def min(arr: DeviceArray, skip_nulls: bool = True, min_count: int = 1) -> pa.Scalar:  # noqa: A001
+    return min_max(arr, skip_nulls, min_count)["min"]
+
+
+def max(arr: DeviceArray, skip_nulls: bool = True, min_count: int = 1) -> pa.Scalar:  # noqa: A001
+    return min_max(arr, skip_nulls, min_count)["max"]
+
+
+def count(arr: DeviceArray, mode: str = "only_valid") -> pa.Scalar:
+    """count (CountImpl, aggregate_basic.cc:98-130; CountOptions api_aggregate.h:64-78)."""
+    ctx = arr.ctx
+    nulls = arr.null_count
+    if nulls < 0:  # unknown after slicing: count the validity bits on the device
+        out = C.c_int64()
+        check(ctx.lib.b2_bitmap_count(ctx.handle, arr.buffers[0].ptr, arr.offset, arr.length, C.byref(out), ctx.stream))
+        nulls = arr.length - out.value
+    if mode == "only_valid":
+        return pa.scalar(arr.length - nulls, pa.int64())
+    if mode == "only_null":
+        return pa.scalar(nulls, pa.int64())
+    if mode == "all":
+        return pa.scalar(arr.length, pa.int64())
+    raise ValueError(f'"{mode}" is not a valid count mode')
+
+
+# ------------------------------------------------------------------------------------
 # unique / value_counts / dictionary_encode (kernels/vector_hash.cc:782-830)
 # ------------------------------------------------------------------------------------
 def _null_encoding(v) -> int:
@@ -490,6 +570,7 @@ _REGISTRY = {
     "equal": equal, "not_equal": not_equal, "greater": greater, "greater_equal": greater_equal,
     "less": less, "less_equal": less_equal,
     "unique": unique, "value_counts": value_counts, "dictionary_encode": dictionary_encode,
+    "sum": sum, "mean": mean, "min_max": min_max, "min": min, "max": max, "count": count,
 }
 
 
@@ -514,4 +595,8 @@ def call_function(name: str, args: Sequence, options=None):
         return fn(*args, order=options.order, null_placement=options.null_placement)
     if name == "dictionary_encode":
         return fn(*args, null_encoding=getattr(options, "null_encoding", options))
+    if name in ("sum", "mean", "min_max", "min", "max"):
+        return fn(*args, skip_nulls=options.skip_nulls, min_count=options.min_count)
+    if name == "count":
+        return fn(*args, mode=getattr(options, "mode", options))
     return fn(*args)

@@ -1,0 +1,223 @@
+// scalar_aggregate.cu -- ungrouped sum / mean / min_max / count of one numeric column.
+//
+// Replaces (the ungrouped half):
+//   SumImpl / MeanImpl            kernels/aggregate_basic.inc.cc:49-107,227-290
+//   MinMaxState / MinMaxImpl      kernels/aggregate_basic.inc.cc:657-701,776-860
+//   CountImpl                     kernels/aggregate_basic.cc:98-130
+//   SumArray (pairwise summation) kernels/aggregate_internal.h
+// One pass computes everything those kernels keep as state -- valid count, sum in the
+// reference's accumulator type (int64 / uint64 / double, FindAccumulatorType), min and max --
+// and the host side applies ScalarAggregateOptions{skip_nulls, min_count} exactly like the
+// reference's Finalize.  Integer sums wrap like the reference's unsigned accumulation; float
+// sums are accumulated in double per thread and combined in a fixed tree order, so the result
+// is deterministic but may differ from the reference's pairwise order in the last bits
+// (tests use rtol 1e-12).  Float min/max ignore NaNs (std::fmin/fmax) and are NaN when every
+// value is NaN, as MinMaxState's quiet_NaN identity gives.
+//
+// B200 design: HBM streaming, W + 1/8 bytes read per row, nothing written.
+// Each warp walks 32-row groups (coalesced loads, one 32-bit validity word per group, four
+// groups in flight), block partials go to global memory and a single CTA folds them in a
+// fixed order; the five result words come back through the call's pinned slot.
+#include <cmath>
+#include <limits>
+#include <type_traits>
+
+#include "bitmap.h"
+
+namespace b2 {
+
+template <typename T>
+struct AccOf {
+  using type = typename std::conditional<std::is_floating_point<T>::value, double,
+                                         typename std::conditional<std::is_signed<T>::value, long long, unsigned long long>::type>::type;
+};
+
+template <typename T>
+struct Partial {
+  typename AccOf<T>::type sum;
+  double dsum;  // the same sum in double: MeanImpl accumulates in double so integers cannot overflow
+  long long count;
+  T mn, mx;
+};
+
+template <typename T>
+__device__ __forceinline__ void partial_init(Partial<T>& p) {
+  p.sum = 0;
+  p.dsum = 0.0;
+  p.count = 0;
+  if (std::is_floating_point<T>::value) {
+    p.mn = p.mx = static_cast<T>(nan(""));
+  } else {
+    p.mn = std::numeric_limits<T>::max();
+    p.mx = std::numeric_limits<T>::lowest();
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T min_of(T a, T b) {
+  if constexpr (std::is_floating_point<T>::value) return static_cast<T>(fmin(static_cast<double>(a), static_cast<double>(b)));
+  else return a < b ? a : b;
+}
+template <typename T>
+__device__ __forceinline__ T max_of(T a, T b) {
+  if constexpr (std::is_floating_point<T>::value) return static_cast<T>(fmax(static_cast<double>(a), static_cast<double>(b)));
+  else return a > b ? a : b;
+}
+
+template <typename T>
+__device__ __forceinline__ void partial_merge(Partial<T>& a, const Partial<T>& b) {
+  a.sum += b.sum;
+  a.dsum += b.dsum;
+  a.count += b.count;
+  a.mn = min_of(a.mn, b.mn);
+  a.mx = max_of(a.mx, b.mx);
+}
+
+template <typename T>
+__device__ __forceinline__ Partial<T> partial_shfl_down(const Partial<T>& p, int delta) {
+  Partial<T> o;
+  o.sum = __shfl_down_sync(0xffffffffu, p.sum, delta);
+  o.dsum = __shfl_down_sync(0xffffffffu, p.dsum, delta);
+  o.count = __shfl_down_sync(0xffffffffu, p.count, delta);
+  o.mn = __shfl_down_sync(0xffffffffu, p.mn, delta);
+  o.mx = __shfl_down_sync(0xffffffffu, p.mx, delta);
+  return o;
+}
+
+// block tree reduction in a fixed order; result valid in thread 0
+template <typename T>
+__device__ __forceinline__ Partial<T> block_reduce(Partial<T> p) {
+  __shared__ Partial<T> s_w[kBlock / 32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    Partial<T> o = partial_shfl_down(p, d);
+    partial_merge(p, o);
+  }
+  if (lane_id() == 0) s_w[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Partial<T> q;
+    partial_init(q);
+    if (threadIdx.x < kBlock / 32) q = s_w[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      Partial<T> o = partial_shfl_down(q, d);
+      partial_merge(q, o);
+    }
+    p = q;
+  }
+  return p;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) reduce_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
+                                                        Partial<T>* __restrict__ partials) {
+  Partial<T> p;
+  partial_init(p);
+  const unsigned lane = lane_id();
+  const int64_t n_groups = (n + 31) >> 5;
+  const int64_t warp0 = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * kBlock) >> 5;
+  constexpr int kU = 4;  // 32-row groups in flight per warp
+  for (int64_t g0 = warp0; g0 < n_groups; g0 += warps * kU) {
+    T v[kU];
+    bool ok[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t g = g0 + u * warps;
+      const int64_t i = (g << 5) + lane;
+      ok[u] = false;
+      v[u] = T(0);
+      if (g < n_groups && i < n) {
+        ok[u] = valid.present() ? ((valid.word32(g) >> lane) & 1u) != 0 : true;
+        if (ok[u]) v[u] = __ldcs(values + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (!ok[u]) continue;
+      p.sum += static_cast<typename AccOf<T>::type>(v[u]);
+      p.dsum += static_cast<double>(v[u]);
+      p.count += 1;
+      p.mn = min_of(p.mn, v[u]);
+      p.mx = max_of(p.mx, v[u]);
+    }
+  }
+  p = block_reduce(p);
+  if (threadIdx.x == 0) partials[blockIdx.x] = p;
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned long long widen_bits(T v) {
+  if constexpr (std::is_floating_point<T>::value) return static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(v)));
+  else if constexpr (std::is_signed<T>::value) return static_cast<unsigned long long>(static_cast<long long>(v));
+  else return static_cast<unsigned long long>(v);
+}
+
+// single CTA: fold the block partials (fixed order) and publish {count, sum, min, max, double sum}
+template <typename T>
+__global__ void __launch_bounds__(kBlock) reduce_final_kernel(const Partial<T>* __restrict__ partials, int n_partials,
+                                                              unsigned long long* out) {
+  Partial<T> p;
+  partial_init(p);
+  for (int i = threadIdx.x; i < n_partials; i += kBlock) partial_merge(p, partials[i]);
+  p = block_reduce(p);
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<unsigned long long>(p.count);
+    if constexpr (std::is_floating_point<T>::value) out[1] = static_cast<unsigned long long>(__double_as_longlong(p.sum));
+    else out[1] = static_cast<unsigned long long>(p.sum);
+    out[2] = widen_bits(p.mn);
+    out[3] = widen_bits(p.mx);
+    out[4] = static_cast<unsigned long long>(__double_as_longlong(p.dsum));
+  }
+}
+
+template <typename T>
+static int reduce_typed(B2Context* ctx, const B2Array* values, B2ReduceResult* out, cudaStream_t s) {
+  const int64_t n = values->length;
+  const T* v = static_cast<const T*>(values->data) + values->offset;
+  BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  const int grid = grid_for(n, kBlock * 8, ctx->sm_count * 8);
+  Temp partials(ctx, s);
+  B2_RETURN_NOT_OK(partials.alloc(sizeof(Partial<T>) * (size_t)grid));
+  ScalarSlot slot(ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  reduce_kernel<T><<<grid, kBlock, 0, s>>>(v, valid, n, partials.as<Partial<T>>());
+  B2_LAUNCHED();
+  reduce_final_kernel<T><<<1, kBlock, 0, s>>>(partials.as<Partial<T>>(), grid, reinterpret_cast<unsigned long long*>(slot.dev()));
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  out->count = slot.host()[0];
+  out->null_count = n - out->count;
+  out->sum_bits = static_cast<uint64_t>(slot.host()[1]);
+  out->min_bits = static_cast<uint64_t>(slot.host()[2]);
+  out->max_bits = static_cast<uint64_t>(slot.host()[3]);
+  out->dsum_bits = static_cast<uint64_t>(slot.host()[4]);
+  out->value_type = values->type;
+  out->acc_type = std::is_floating_point<T>::value ? B2_DOUBLE : (std::is_signed<T>::value ? B2_INT64 : B2_UINT64);
+  return B2_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_reduce(B2Context* ctx, const B2Array* values, B2ReduceResult* out, void* stream) {
+  if (!ctx || !values || !out) return set_error(B2_INVALID, "b2_reduce: null argument");
+  if (!type_is_numeric(values->type)) return set_error(B2_NOT_IMPLEMENTED, "sum/mean/min_max over type id %d", values->type);
+  if (values->length < 0 || values->offset < 0) return set_error(B2_INVALID, "negative length/offset");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->pick(stream);
+  switch (values->type) {
+    case B2_INT8: return reduce_typed<int8_t>(ctx, values, out, s);
+    case B2_UINT8: return reduce_typed<uint8_t>(ctx, values, out, s);
+    case B2_INT16: return reduce_typed<int16_t>(ctx, values, out, s);
+    case B2_UINT16: return reduce_typed<uint16_t>(ctx, values, out, s);
+    case B2_INT32: return reduce_typed<int32_t>(ctx, values, out, s);
+    case B2_UINT32: return reduce_typed<uint32_t>(ctx, values, out, s);
+    case B2_INT64: return reduce_typed<int64_t>(ctx, values, out, s);
+    case B2_UINT64: return reduce_typed<uint64_t>(ctx, values, out, s);
+    case B2_FLOAT: return reduce_typed<float>(ctx, values, out, s);
+    default: return reduce_typed<double>(ctx, values, out, s);
+  }
+}

@@ -91,6 +91,8 @@ def main():
             other = DeviceArray.from_pointers(ctx, pa.int64(), n, other_t.data_ptr())
             ms = timed(stream, lambda: bc.greater(values, other), args.reps)
             report("compare greater(int64,int64)", n, ms, n * (16 + 0.125 + 0.25))
+            ms = timed(stream, lambda: bc.sum(values), args.reps)
+            report("f2 sum/mean/min_max state of int64 (b2_reduce)", n, ms, n * (8 + 0.125))
             del other, other_t
         del values, vals_t, vvalid_t
 

@@ -271,6 +271,27 @@ B2_API int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream);
 B2_API int b2_grouper_reset(B2Grouper* g);
 
 /* ---------------------------------------------------------------------------
+ * Ungrouped sum / mean / min_max / count of one numeric column: everything the
+ * reference's scalar-aggregate states keep, in one pass.  Replaces SumImpl / MeanImpl
+ * (compute/kernels/aggregate_basic.inc.cc:49-107,227-290), MinMaxState / MinMaxImpl
+ * (:657-701,776-860) and CountImpl (compute/kernels/aggregate_basic.cc:98-130); the
+ * caller applies ScalarAggregateOptions{skip_nulls, min_count} (compute/api_aggregate.h:48-50)
+ * the way their Finalize does.
+ * ------------------------------------------------------------------------- */
+typedef struct B2ReduceResult {
+  int64_t count;      /* valid (non-null) rows */
+  int64_t null_count; /* length - count */
+  uint64_t sum_bits;  /* sum over valid rows in acc_type: int64 (wrapping) / uint64 / double bits */
+  uint64_t min_bits;  /* min over valid rows widened to int64 / uint64 / double bits; the type's
+                         anti-extremum (NaN for floats) when count == 0 or every value is NaN */
+  uint64_t max_bits;
+  uint64_t dsum_bits; /* the sum accumulated in double (what MeanImpl divides by count, :263-283) */
+  int32_t acc_type;   /* B2_INT64, B2_UINT64 or B2_DOUBLE (FindAccumulatorType) */
+  int32_t value_type;
+} B2ReduceResult;
+B2_API int b2_reduce(B2Context* ctx, const B2Array* values, B2ReduceResult* out, void* stream);
+
+/* ---------------------------------------------------------------------------
  * unique / value_counts / dictionary_encode over one fixed-width column.
  * Replaces UniqueAction / ValueCountsAction / DictEncodeAction + RegularHashKernel
  * (compute/kernels/vector_hash.cc:65-235,236-470; registration :782-830;

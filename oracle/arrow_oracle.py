@@ -421,6 +421,55 @@ class Grouper:
 
 
 # ---------------------------------------------------------------------------------------
+# Ungrouped aggregates   (kernels/aggregate_basic.inc.cc:49-107 SumImpl, :227-290 MeanImpl,
+# :657-701 MinMaxState, :776-860 MinMaxImpl; kernels/aggregate_basic.cc:98-130 CountImpl)
+# ---------------------------------------------------------------------------------------
+def _agg_acc(t):
+    if pa.types.is_floating(t):
+        return pa.float64(), np.float64
+    return (pa.int64(), np.int64) if pa.types.is_signed_integer(t) else (pa.uint64(), np.uint64)
+
+
+def scalar_sum(arr: pa.Array, skip_nulls=True, min_count=1) -> pa.Scalar:
+    v, valid = values(arr), validity(arr)
+    out_t, acc = _agg_acc(arr.type)
+    n_valid = int(valid.sum())
+    if (not skip_nulls and n_valid < len(arr)) or n_valid < min_count:
+        return pa.scalar(None, out_t)
+    with np.errstate(over="ignore"):
+        total = v[valid].astype(acc).sum(dtype=acc)  # integers wrap; floats: numpy's pairwise sum
+    return pa.scalar(total.item(), out_t)
+
+
+def scalar_mean(arr: pa.Array, skip_nulls=True, min_count=1) -> pa.Scalar:
+    valid = validity(arr)
+    n_valid = int(valid.sum())
+    if (not skip_nulls and n_valid < len(arr)) or n_valid < min_count:
+        return pa.scalar(None, pa.float64())
+    with np.errstate(invalid="ignore", divide="ignore"):  # 0 valid values and min_count == 0 -> 0/0 = NaN (:272-283)
+        return pa.scalar(float(values(arr)[valid].astype(np.float64).sum() / np.float64(n_valid)), pa.float64())  # double accumulator (:263-268)
+
+
+def scalar_min_max(arr: pa.Array, skip_nulls=True, min_count=1) -> pa.Scalar:
+    v, valid = values(arr), validity(arr)
+    st = pa.struct([("min", arr.type), ("max", arr.type)])
+    n_valid = int(valid.sum())
+    if (n_valid < len(arr) and not skip_nulls) or n_valid < max(1, min_count):
+        return pa.scalar({"min": None, "max": None}, st)
+    vv = v[valid]
+    if pa.types.is_floating(arr.type):  # std::fmin / std::fmax starting from NaN: NaNs are ignored
+        lo, hi = (np.nan, np.nan) if np.isnan(vv).all() else (np.nanmin(vv), np.nanmax(vv))
+    else:
+        lo, hi = vv.min(), vv.max()
+    return pa.scalar({"min": lo.item() if hasattr(lo, "item") else lo, "max": hi.item() if hasattr(hi, "item") else hi}, st)
+
+
+def scalar_count(arr: pa.Array, mode="only_valid") -> pa.Scalar:
+    n_valid = int(validity(arr).sum())
+    return pa.scalar({"only_valid": n_valid, "only_null": len(arr) - n_valid, "all": len(arr)}[mode], pa.int64())
+
+
+# ---------------------------------------------------------------------------------------
 # unique / value_counts / dictionary_encode   (kernels/vector_hash.cc:65-235, 782-830)
 # The memo table hands out indices in first-occurrence order (RegularHashKernel::DoAppend,
 # vector_hash.cc:300-340); UniqueAction and ValueCountsAction encode null as a value,

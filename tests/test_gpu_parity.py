@@ -505,3 +505,41 @@ def test_vector_hash_random(ctx, t):
     assert bc.call_function("unique", [dev(pa.array([3, 3, 1], t), ctx)]).to_arrow().equals(pa.array([3, 1], t))
     with pytest.raises(pa.ArrowNotImplementedError):
         bc.unique(dev(pa.array(["a", "b"]), ctx))
+
+
+# ---------------------------------------------------------------- ungrouped sum / mean / min_max / count
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_scalar_aggregates(ctx, t):
+    acc = ora._agg_acc(t)[0]
+    assert bc.sum(dev(pa.array([0, 1, 2, 3, 4, 5], t), ctx)) == pa.scalar(15, acc)          # TestNumericSumKernel.SimpleSum
+    assert bc.sum(dev(pa.array([0, None, 2, 3, None, 5], t), ctx)) == pa.scalar(10, acc)
+    assert bc.mean(dev(pa.array([1, 2, 3, 4, 5, 6, 7, 8], t), ctx)) == pa.scalar(4.5, pa.float64())
+    assert bc.min_max(dev(pa.array([5, None, 2, 3, 4], t), ctx)).as_py() == {"min": 2, "max": 5}
+    for n, null_p in ((0, 0.0), (1, 0.0), (1000, 0.0), (70001, 0.1), (5000, 1.0), (1 << 21, 0.3)):
+        a = random_array(t, n, null_p, SEED + n, offset=5)
+        d = dev(a, ctx)
+        for skip in (True, False):
+            for mc in (0, 1, 3):
+                want, got = pc.sum(a, skip_nulls=skip, min_count=mc), bc.sum(d, skip, mc)
+                if pa.types.is_floating(t) and want.is_valid:
+                    # float sums: the reference adds pairwise, the device in a fixed tree order (tolerance 1e-12 relative
+                    # to the sum of magnitudes)
+                    scale = float(np.abs(ora.values(a)[ora.validity(a)].astype(np.float64)).sum()) or 1.0
+                    assert got.is_valid and abs(got.as_py() - want.as_py()) <= 1e-12 * scale
+                else:
+                    assert got == want, (t, n, null_p, skip, mc)  # integer sums are bit-exact (wrapping)
+                wm, gm = pc.mean(a, skip_nulls=skip, min_count=mc), bc.mean(d, skip, mc)
+                assert gm.is_valid == wm.is_valid
+                if wm.is_valid:
+                    scale = float(np.abs(ora.values(a)[ora.validity(a)].astype(np.float64)).sum()) / max(1, len(a) - a.null_count)
+                    assert np.isnan(wm.as_py()) and np.isnan(gm.as_py()) or abs(gm.as_py() - wm.as_py()) <= 1e-12 * (scale or 1.0)
+                assert bc.min_max(d, skip, mc) == pc.min_max(a, skip_nulls=skip, min_count=mc), (t, n, null_p, skip, mc)
+                assert bc.min_max(d, skip, mc) == ora.scalar_min_max(a, skip, mc)
+        for mode in ("only_valid", "only_null", "all"):
+            assert bc.count(d, mode) == pc.count(a, mode=mode)
+            assert bc.count(d.slice(3, max(0, n - 7)), mode) == pc.count(a.slice(3, max(0, n - 7)), mode=mode)
+    if pa.types.is_floating(t):
+        nan = pa.array([np.nan, 1.0, None, -2.0, np.nan], t)
+        assert bc.min_max(dev(nan, ctx)) == pc.min_max(nan)
+        assert np.isnan(bc.min_max(dev(pa.array([np.nan, np.nan], t), ctx))["max"].as_py())
+    assert bc.call_function("sum", [dev(pa.array([1, 2], t), ctx)]) == pa.scalar(3, acc)

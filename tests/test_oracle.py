@@ -315,3 +315,47 @@ def test_vector_hash_vs_reference(t):
         assert ora.value_counts(a).equals(pc.value_counts(a))
         for mode in ("mask", "encode"):
             assert ora.dictionary_encode(a, mode).equals(pc.dictionary_encode(a, null_encoding=mode)), (t, n, mode)
+
+
+# Known answers from the reference's tests (compute/kernels/aggregate_test.cc): TestNumericSumKernel
+# SimpleSum "[0, 1, 2, 3, 4, 5]" -> 15 and "[0, null, 2, 3, null, 5]" -> 10, empty -> null,
+# min_count; TestPrimitiveMinMaxKernel "[5, 1, 2, 3, 4]" -> (1, 5), "[5, null, 2, 3, 4]" -> (2, 5);
+# TestMeanKernelNumeric "[1, 2, 3, 4, 5, 6, 7, 8]" -> 4.5.
+def test_kat_scalar_aggregates():
+    for t in NUMERIC_TYPES:
+        acc = ora._agg_acc(t)[0]
+        assert ora.scalar_sum(pa.array([0, 1, 2, 3, 4, 5], t)) == pa.scalar(15, acc)
+        assert ora.scalar_sum(pa.array([0, None, 2, 3, None, 5], t)) == pa.scalar(10, acc)
+        assert ora.scalar_sum(pa.array([], t)) == pa.scalar(None, acc)
+        assert ora.scalar_sum(pa.array([], t), min_count=0) == pa.scalar(0, acc)
+        assert ora.scalar_sum(pa.array([1, None], t), skip_nulls=False) == pa.scalar(None, acc)
+        assert ora.scalar_sum(pa.array([1, None], t), min_count=2) == pa.scalar(None, acc)
+        assert ora.scalar_mean(pa.array([1, 2, 3, 4, 5, 6, 7, 8], t)) == pa.scalar(4.5, pa.float64())
+        assert ora.scalar_min_max(pa.array([5, 1, 2, 3, 4], t)).as_py() == {"min": 1, "max": 5}
+        assert ora.scalar_min_max(pa.array([5, None, 2, 3, 4], t)).as_py() == {"min": 2, "max": 5}
+        assert ora.scalar_min_max(pa.array([5, None, 2], t), skip_nulls=False).as_py() == {"min": None, "max": None}
+        assert ora.scalar_count(pa.array([5, None, 2], t), "only_null") == pa.scalar(1, pa.int64())
+
+
+@pytest.mark.parametrize("t", NUMERIC_TYPES, ids=str)
+def test_scalar_aggregates_vs_reference(t):
+    for n, null_p in ((0, 0.0), (1, 0.0), (1000, 0.0), (70001, 0.1), (5000, 1.0)):
+        a = random_array(t, n, null_p, SEED + n, offset=5)
+        for skip in (True, False):
+            for mc in (0, 1, 3):
+                want = pc.sum(a, skip_nulls=skip, min_count=mc)
+                got = ora.scalar_sum(a, skip, mc)
+                if pa.types.is_floating(t) and want.is_valid:
+                    assert got.is_valid and np.isclose(got.as_py(), want.as_py(), rtol=1e-12, atol=0)
+                else:
+                    assert got == want, (t, n, null_p, skip, mc)
+                wm, gm = pc.mean(a, skip_nulls=skip, min_count=mc), ora.scalar_mean(a, skip, mc)
+                assert gm.is_valid == wm.is_valid and (not wm.is_valid or np.isclose(gm.as_py(), wm.as_py(), rtol=1e-12, equal_nan=True))
+                assert ora.scalar_min_max(a, skip, mc) == pc.min_max(a, skip_nulls=skip, min_count=mc)
+        for mode in ("only_valid", "only_null", "all"):
+            assert ora.scalar_count(a, mode) == pc.count(a, mode=mode)
+    if pa.types.is_floating(t):
+        nan = pa.array([np.nan, 1.0, None, -2.0, np.nan], t)
+        assert ora.scalar_min_max(nan) == pc.min_max(nan)
+        allnan = pa.array([np.nan, np.nan], t)
+        assert np.isnan(ora.scalar_min_max(allnan)["min"].as_py()) and np.isnan(pc.min_max(allnan)["min"].as_py())
