@@ -10,6 +10,9 @@
 // through BufferSpan::owner -> Buffer::address().
 #include "b200_compute.h"
 
+#include <cmath>
+#include <cstring>
+
 #include <arrow/compute/cast.h>
 #include <arrow/compute/registry.h>
 #include <arrow/util/checked_cast.h>
@@ -504,6 +507,185 @@ static Status AddHashFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
 }
 
 // ------------------------------------------------------------------------------------------
+// ungrouped sum / mean / min_max / count: the ScalarAggregateKernel contract
+// {init, consume, merge, finalize} (compute/kernel.h:640-700) over b2_reduce
+// ------------------------------------------------------------------------------------------
+enum ScalarAggKind { kAggSum, kAggMean, kAggMinMax, kAggCount };
+
+struct ScalarAggState : public cp::KernelState {
+  int kind = kAggSum;
+  Runtime* rt = nullptr;  // consume runs under a KernelContext without a kernel (exec.cc:1175-1177), so keep it here
+  cp::ScalarAggregateOptions options = cp::ScalarAggregateOptions::Defaults();
+  cp::CountOptions count_options = cp::CountOptions::Defaults();
+  std::shared_ptr<DataType> in_type;
+  int acc_type = B2_INT64;
+  int64_t length = 0, count = 0, nulls = 0;
+  uint64_t sum_bits = 0;  // int64 / uint64 sums wrap the same way in two's complement
+  double fsum = 0, dsum = 0;
+  uint64_t min_bits = 0, max_bits = 0;
+  bool has_minmax = false;
+
+  static double AsDouble(uint64_t b) {
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+  }
+  void MergeMinMax(uint64_t lo, uint64_t hi) {
+    if (!has_minmax) {
+      min_bits = lo;
+      max_bits = hi;
+      has_minmax = true;
+      return;
+    }
+    if (acc_type == B2_DOUBLE) {  // std::fmin / std::fmax: NaN is the identity (aggregate_basic.inc.cc:680-701)
+      double a = std::fmin(AsDouble(min_bits), AsDouble(lo)), b = std::fmax(AsDouble(max_bits), AsDouble(hi));
+      std::memcpy(&min_bits, &a, 8);
+      std::memcpy(&max_bits, &b, 8);
+    } else if (acc_type == B2_INT64) {
+      min_bits = static_cast<uint64_t>(std::min(static_cast<int64_t>(min_bits), static_cast<int64_t>(lo)));
+      max_bits = static_cast<uint64_t>(std::max(static_cast<int64_t>(max_bits), static_cast<int64_t>(hi)));
+    } else {
+      min_bits = std::min(min_bits, lo);
+      max_bits = std::max(max_bits, hi);
+    }
+  }
+};
+
+template <int KIND>
+static Result<std::unique_ptr<cp::KernelState>> ScalarAggInit(cp::KernelContext*, const cp::KernelInitArgs& args) {
+  auto st = std::make_unique<ScalarAggState>();
+  st->kind = KIND;
+  st->rt = checked_cast<const KernelData&>(*args.kernel->data).rt;
+  st->in_type = args.inputs[0].GetSharedPtr();
+  if (KIND == kAggCount) {
+    if (auto o = static_cast<const cp::CountOptions*>(args.options)) st->count_options = *o;
+  } else if (auto o = static_cast<const cp::ScalarAggregateOptions*>(args.options)) {
+    st->options = *o;
+  }
+  return st;
+}
+
+static Status ScalarAggConsume(cp::KernelContext* ctx, const cp::ExecSpan& batch) {
+  auto* st = checked_cast<ScalarAggState*>(ctx->state());
+  if (!batch[0].is_array()) return Status::NotImplemented("device aggregates over a scalar argument");
+  B2Array v;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &v));
+  st->length += v.length;
+  if (st->kind == kAggCount) {
+    int64_t valid = v.length;
+    if (v.validity && v.null_count != 0) B200_RETURN_NOT_OK(b2_bitmap_count(st->rt->context(), v.validity, v.offset, v.length, &valid, nullptr));
+    st->count += valid;
+    st->nulls += v.length - valid;
+    return Status::OK();
+  }
+  B2ReduceResult r;
+  B200_RETURN_NOT_OK(b2_reduce(st->rt->context(), &v, &r, nullptr));
+  st->acc_type = r.acc_type;
+  st->count += r.count;
+  st->nulls += r.null_count;
+  st->sum_bits += r.sum_bits;
+  st->fsum += ScalarAggState::AsDouble(r.sum_bits);
+  st->dsum += ScalarAggState::AsDouble(r.dsum_bits);
+  if (r.count > 0) st->MergeMinMax(r.min_bits, r.max_bits);
+  return Status::OK();
+}
+
+static Status ScalarAggMerge(cp::KernelContext*, cp::KernelState&& src, cp::KernelState* dst) {
+  auto& o = checked_cast<ScalarAggState&>(src);
+  auto* st = checked_cast<ScalarAggState*>(dst);
+  st->acc_type = o.length ? o.acc_type : st->acc_type;
+  st->length += o.length;
+  st->count += o.count;
+  st->nulls += o.nulls;
+  st->sum_bits += o.sum_bits;
+  st->fsum += o.fsum;
+  st->dsum += o.dsum;
+  if (o.has_minmax) st->MergeMinMax(o.min_bits, o.max_bits);
+  return Status::OK();
+}
+
+static Status ScalarAggFinalize(cp::KernelContext* ctx, Datum* out) {
+  auto* st = checked_cast<ScalarAggState*>(ctx->state());
+  const auto& o = st->options;
+  const bool floating = arrow::is_floating(st->in_type->id());
+  const bool is_signed = arrow::is_signed_integer(st->in_type->id());
+  switch (st->kind) {
+    case kAggCount: {
+      const auto mode = st->count_options.mode;
+      const int64_t v = mode == cp::CountOptions::ONLY_VALID ? st->count : (mode == cp::CountOptions::ONLY_NULL ? st->nulls : st->length);
+      *out = Datum(std::make_shared<arrow::Int64Scalar>(v));
+      return Status::OK();
+    }
+    case kAggSum: {
+      const bool null = (!o.skip_nulls && st->nulls > 0) || st->count < static_cast<int64_t>(o.min_count);
+      if (floating) *out = Datum(null ? std::make_shared<arrow::DoubleScalar>() : std::make_shared<arrow::DoubleScalar>(st->fsum));
+      else if (is_signed) *out = Datum(null ? std::make_shared<arrow::Int64Scalar>() : std::make_shared<arrow::Int64Scalar>(static_cast<int64_t>(st->sum_bits)));
+      else *out = Datum(null ? std::make_shared<arrow::UInt64Scalar>() : std::make_shared<arrow::UInt64Scalar>(st->sum_bits));
+      return Status::OK();
+    }
+    case kAggMean: {
+      const bool null = (!o.skip_nulls && st->nulls > 0) || st->count < static_cast<int64_t>(o.min_count);
+      *out = Datum(null ? std::make_shared<arrow::DoubleScalar>() : std::make_shared<arrow::DoubleScalar>(st->dsum / static_cast<double>(st->count)));
+      return Status::OK();
+    }
+    default: {
+      auto type = arrow::struct_({arrow::field("min", st->in_type), arrow::field("max", st->in_type)});
+      const int64_t min_count = std::max<int64_t>(1, o.min_count);  // aggregate_basic.inc.cc:783
+      std::shared_ptr<arrow::Scalar> lo = arrow::MakeNullScalar(st->in_type), hi = lo;
+      if (!((st->nulls > 0 && !o.skip_nulls) || st->count < min_count)) {
+        std::shared_ptr<arrow::Scalar> wlo, whi;
+        if (floating) {
+          wlo = std::make_shared<arrow::DoubleScalar>(ScalarAggState::AsDouble(st->min_bits));
+          whi = std::make_shared<arrow::DoubleScalar>(ScalarAggState::AsDouble(st->max_bits));
+        } else if (is_signed) {
+          wlo = std::make_shared<arrow::Int64Scalar>(static_cast<int64_t>(st->min_bits));
+          whi = std::make_shared<arrow::Int64Scalar>(static_cast<int64_t>(st->max_bits));
+        } else {
+          wlo = std::make_shared<arrow::UInt64Scalar>(st->min_bits);
+          whi = std::make_shared<arrow::UInt64Scalar>(st->max_bits);
+        }
+        ARROW_ASSIGN_OR_RAISE(lo, wlo->CastTo(st->in_type));
+        ARROW_ASSIGN_OR_RAISE(hi, whi->CastTo(st->in_type));
+      }
+      *out = Datum(std::make_shared<arrow::StructScalar>(arrow::ScalarVector{lo, hi}, type));
+      return Status::OK();
+    }
+  }
+}
+
+static Result<TypeHolder> SumType(cp::KernelContext*, const std::vector<TypeHolder>& types) {
+  const auto id = types[0].id();
+  if (arrow::is_floating(id)) return TypeHolder(arrow::float64());
+  return TypeHolder(arrow::is_signed_integer(id) ? arrow::int64() : arrow::uint64());
+}
+static Result<TypeHolder> MinMaxType(cp::KernelContext*, const std::vector<TypeHolder>& types) {
+  return TypeHolder(arrow::struct_({arrow::field("min", types[0].GetSharedPtr()), arrow::field("max", types[0].GetSharedPtr())}));
+}
+
+static Status AddScalarAggregates(cp::FunctionRegistry* reg, Runtime* rt) {
+  static const cp::ScalarAggregateOptions kAggDefaults = cp::ScalarAggregateOptions::Defaults();
+  static const cp::CountOptions kCountDefaults = cp::CountOptions::Defaults();
+  auto add = [&](const char* name, cp::KernelInit init, cp::OutputType out, const cp::FunctionOptions* defaults, const char* options_class,
+                 bool any_type) -> Status {
+    auto fn = std::make_shared<Forwarding<cp::ScalarAggregateFunction>>(name, cp::Arity::Unary(), DocFor({"array"}, options_class), defaults);
+    auto add_kernel = [&](cp::InputType in) {
+      cp::ScalarAggregateKernel k(cp::KernelSignature::Make({std::move(in)}, out), init, ScalarAggConsume, ScalarAggMerge, ScalarAggFinalize,
+                                  /*ordered=*/false);
+      k.data = std::make_shared<KernelData>(rt, 0);
+      return fn->AddKernel(std::move(k));
+    };
+    if (any_type) ARROW_RETURN_NOT_OK(add_kernel(cp::InputType::Any()));
+    else
+      for (const auto& ty : NumericTypes()) ARROW_RETURN_NOT_OK(add_kernel(cp::InputType(ty)));
+    return reg->AddFunction(std::move(fn), true);
+  };
+  ARROW_RETURN_NOT_OK(add("sum", ScalarAggInit<kAggSum>, cp::OutputType(SumType), &kAggDefaults, "ScalarAggregateOptions", false));
+  ARROW_RETURN_NOT_OK(add("mean", ScalarAggInit<kAggMean>, cp::OutputType(arrow::float64()), &kAggDefaults, "ScalarAggregateOptions", false));
+  ARROW_RETURN_NOT_OK(add("min_max", ScalarAggInit<kAggMinMax>, cp::OutputType(MinMaxType), &kAggDefaults, "ScalarAggregateOptions", false));
+  return add("count", ScalarAggInit<kAggCount>, cp::OutputType(arrow::int64()), &kCountDefaults, "CountOptions", true);
+}
+
+// ------------------------------------------------------------------------------------------
 // hash aggregates: the HashAggregateKernel contract (compute/kernel.h:720-769)
 // ------------------------------------------------------------------------------------------
 struct HashAggState : public cp::KernelState {
@@ -693,6 +875,7 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<CastFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddSelectionFunctions(reg, rt));
   ARROW_RETURN_NOT_OK(AddHashFunctions(reg, rt));
+  ARROW_RETURN_NOT_OK(AddScalarAggregates(reg, rt));
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},
                                               {"hash_count_all", B2_HASH_COUNT_ALL}, {"hash_mean", B2_HASH_MEAN},
                                               {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX}};

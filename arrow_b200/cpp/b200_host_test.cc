@@ -90,6 +90,7 @@ struct Harness {
   arrow_b200::Runtime* rt;
   cp::ExecContext cpu_ctx;
   cp::ExecContext gpu_ctx;
+  bool approx = false;  // float sums: the device adds in a fixed tree order, the reference pairwise
   explicit Harness(arrow_b200::Runtime* r)
       : rt(r), cpu_ctx(arrow::default_memory_pool()), gpu_ctx(arrow::default_memory_pool(), nullptr, r->registry()) {}
 
@@ -125,7 +126,8 @@ struct Harness {
     auto w = want->is_chunked_array() ? UNWRAP(arrow::Concatenate(want->chunked_array()->chunks())) : Host(*want);
     auto g = Host(*got);
     auto vst = g->ValidateFull();
-    if (!vst.ok() || !g->Equals(*w, arrow::EqualOptions::Defaults().nans_equal(true))) {
+    const auto eq = arrow::EqualOptions::Defaults().nans_equal(true);
+    if (!vst.ok() || !(approx ? g->ApproxEquals(*w, eq.atol(1e-6)) : g->Equals(*w, eq))) {
       std::cout << "FAIL " << what << ": arrays differ " << vst.ToString() << "\n  want: " << w->ToString().substr(0, 400)
                 << "\n  got:  " << g->ToString().substr(0, 400) << std::endl;
       std::exit(1);
@@ -243,6 +245,36 @@ int main() {
       cp::DictionaryEncodeOptions mask(cp::DictionaryEncodeOptions::MASK), encode(cp::DictionaryEncodeOptions::ENCODE);
       h.Check("dictionary_encode MASK" + tag, "dictionary_encode", {a}, &mask);
       h.Check("dictionary_encode ENCODE" + tag, "dictionary_encode", {a}, &encode);
+    }
+  }
+
+  // ---- ungrouped aggregates (kernels/aggregate_test.cc: TestNumericSumKernel, TestMeanKernelNumeric,
+  //      TestPrimitiveMinMaxKernel, TestCountKernel) ----
+  {
+    auto a64 = RandomNumeric<arrow::Int64Type>(80000, 0.1, 101, -300, 300);
+    auto au8 = RandomNumeric<arrow::UInt8Type>(80000, 0.0, 102, 0, 255);
+    auto af = RandomNumeric<arrow::DoubleType>(80000, 0.2, 103, -50, 50);
+    auto empty = a64->Slice(0, 0);
+    auto nulls = RandomNumeric<arrow::Int32Type>(100, 1.0, 104, 0, 1);
+    for (const auto& a : {a64, au8, af, empty, nulls, a64->Slice(11, 3000)}) {
+      const std::string tag = "(" + a->type()->ToString() + ", " + std::to_string(a->length()) + " rows)";
+      h.approx = a->type_id() == arrow::Type::DOUBLE;
+      for (bool skip : {true, false}) {
+        for (uint32_t mc : {0u, 1u, 4u}) {
+          cp::ScalarAggregateOptions o(skip, mc);
+          const std::string t2 = tag + (skip ? " skip_nulls" : " keep_nulls") + " min_count=" + std::to_string(mc);
+          h.Check("sum" + t2, "sum", {a}, &o);
+          h.approx = true;  // mean divides a double sum
+          h.Check("mean" + t2, "mean", {a}, &o);
+          h.approx = a->type_id() == arrow::Type::DOUBLE;
+          h.Check("min_max" + t2, "min_max", {a}, &o);
+        }
+      }
+      h.approx = false;
+      for (auto mode : {cp::CountOptions::ONLY_VALID, cp::CountOptions::ONLY_NULL, cp::CountOptions::ALL}) {
+        cp::CountOptions co(mode);
+        h.Check("count" + tag + " mode " + std::to_string(static_cast<int>(mode)), "count", {a}, &co);
+      }
     }
   }
 

@@ -15,9 +15,9 @@
 // value is NaN, as MinMaxState's quiet_NaN identity gives.
 //
 // B200 design: HBM streaming, W + 1/8 bytes read per row, nothing written.
-// Each warp walks 32-row groups (coalesced loads, one 32-bit validity word per group, four
-// groups in flight), block partials go to global memory and a single CTA folds them in a
-// fixed order; the five result words come back through the call's pinned slot.
+// Every lane loads 16 bytes per step (a warp covers 64..512 rows and 1..8 validity words), four
+// steps in flight; block partials go to global memory and a single CTA folds them in a fixed
+// order; the five result words come back through the call's pinned slot.
 #include <cmath>
 #include <limits>
 #include <type_traits>
@@ -35,7 +35,7 @@ struct AccOf {
 template <typename T>
 struct Partial {
   typename AccOf<T>::type sum;
-  double dsum;  // the same sum in double: MeanImpl accumulates in double so integers cannot overflow
+  long long hi;  // integers: bits 64..127 of the exact sum (MeanImpl must not see the int64 wrap-around)
   long long count;
   T mn, mx;
 };
@@ -43,7 +43,7 @@ struct Partial {
 template <typename T>
 __device__ __forceinline__ void partial_init(Partial<T>& p) {
   p.sum = 0;
-  p.dsum = 0.0;
+  p.hi = 0;
   p.count = 0;
   if (std::is_floating_point<T>::value) {
     p.mn = p.mx = static_cast<T>(nan(""));
@@ -66,8 +66,11 @@ __device__ __forceinline__ T max_of(T a, T b) {
 
 template <typename T>
 __device__ __forceinline__ void partial_merge(Partial<T>& a, const Partial<T>& b) {
+  if constexpr (!std::is_floating_point<T>::value) {
+    const unsigned long long old = static_cast<unsigned long long>(a.sum);
+    a.hi += b.hi + ((old + static_cast<unsigned long long>(b.sum)) < old ? 1 : 0);
+  }
   a.sum += b.sum;
-  a.dsum += b.dsum;
   a.count += b.count;
   a.mn = min_of(a.mn, b.mn);
   a.mx = max_of(a.mx, b.mx);
@@ -77,7 +80,7 @@ template <typename T>
 __device__ __forceinline__ Partial<T> partial_shfl_down(const Partial<T>& p, int delta) {
   Partial<T> o;
   o.sum = __shfl_down_sync(0xffffffffu, p.sum, delta);
-  o.dsum = __shfl_down_sync(0xffffffffu, p.dsum, delta);
+  o.hi = __shfl_down_sync(0xffffffffu, p.hi, delta);
   o.count = __shfl_down_sync(0xffffffffu, p.count, delta);
   o.mn = __shfl_down_sync(0xffffffffu, p.mn, delta);
   o.mx = __shfl_down_sync(0xffffffffu, p.mx, delta);
@@ -110,37 +113,89 @@ __device__ __forceinline__ Partial<T> block_reduce(Partial<T> p) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) reduce_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
+__device__ __forceinline__ void partial_add(Partial<T>& p, T v) {
+  if constexpr (!std::is_floating_point<T>::value) {
+    // exact 128-bit accumulation: sign-extend v, add with carry
+    const unsigned long long old = static_cast<unsigned long long>(p.sum);
+    const unsigned long long add = static_cast<unsigned long long>(static_cast<typename AccOf<T>::type>(v));
+    p.hi += (std::is_signed<T>::value && v < T(0) ? -1 : 0) + ((old + add) < old ? 1 : 0);
+  }
+  p.sum += static_cast<typename AccOf<T>::type>(v);
+  p.count += 1;
+  p.mn = min_of(p.mn, v);
+  p.mx = max_of(p.mx, v);
+}
+
+// VEC: every lane loads 16 bytes (E = 16 / sizeof(T) consecutive rows), so a warp covers 32 * E rows
+// per step and needs E validity bits per lane; four steps are in flight.  The scalar variant (one row
+// per lane per step) serves columns whose first value is not 16-byte aligned.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
                                                         Partial<T>* __restrict__ partials) {
   Partial<T> p;
   partial_init(p);
   const unsigned lane = lane_id();
-  const int64_t n_groups = (n + 31) >> 5;
   const int64_t warp0 = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
   const int64_t warps = ((int64_t)gridDim.x * kBlock) >> 5;
-  constexpr int kU = 4;  // 32-row groups in flight per warp
-  for (int64_t g0 = warp0; g0 < n_groups; g0 += warps * kU) {
-    T v[kU];
-    bool ok[kU];
+  if (VEC) {
+    constexpr int E = 16 / sizeof(T);
+    constexpr int kRows = 32 * E;  // rows per warp step: 64 .. 512 = 1 .. 8 validity words
+    constexpr int kU = 4;
+    const int64_t n_steps = (n + kRows - 1) / kRows;
+    for (int64_t s0 = warp0; s0 < n_steps; s0 += warps * kU) {
+      uint4 raw[kU];
+      unsigned bits[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t g = g0 + u * warps;
-      const int64_t i = (g << 5) + lane;
-      ok[u] = false;
-      v[u] = T(0);
-      if (g < n_groups && i < n) {
-        ok[u] = valid.present() ? ((valid.word32(g) >> lane) & 1u) != 0 : true;
-        if (ok[u]) v[u] = __ldcs(values + i);
+      for (int u = 0; u < kU; ++u) {
+        const int64_t step = s0 + u * warps;
+        const int64_t i0 = step * kRows + lane * E;
+        bits[u] = 0;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (step < n_steps && i0 < n) {
+          const int64_t rem = n - i0;
+          // the values are requested first and unconditionally: making the load wait for the validity
+          // word would put two DRAM round trips in series (null slots cost no extra sectors anyway)
+          if (rem >= E) {
+            raw[u] = __ldcs(reinterpret_cast<const uint4*>(values + i0));
+          } else {  // last, partial vector of the column
+            T tmp[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) tmp[e] = e < rem ? values[i0 + e] : T(0);
+            raw[u] = *reinterpret_cast<const uint4*>(tmp);
+          }
+          unsigned m = rem >= E ? ((E == 32) ? 0xffffffffu : ((1u << E) - 1u)) : ((1u << rem) - 1u);
+          if (valid.present()) m &= static_cast<unsigned>(valid.word(i0 >> 6) >> (i0 & 63));  // E divides 64: one word
+          bits[u] = m;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const T* v = reinterpret_cast<const T*>(&raw[u]);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if ((bits[u] >> e) & 1u) partial_add(p, v[e]);
       }
     }
+  } else {
+    const int64_t n_groups = (n + 31) >> 5;
+    constexpr int kU = 4;  // 32-row groups in flight per warp
+    for (int64_t g0 = warp0; g0 < n_groups; g0 += warps * kU) {
+      T v[kU];
+      bool ok[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      if (!ok[u]) continue;
-      p.sum += static_cast<typename AccOf<T>::type>(v[u]);
-      p.dsum += static_cast<double>(v[u]);
-      p.count += 1;
-      p.mn = min_of(p.mn, v[u]);
-      p.mx = max_of(p.mx, v[u]);
+      for (int u = 0; u < kU; ++u) {
+        const int64_t g = g0 + u * warps;
+        const int64_t i = (g << 5) + lane;
+        ok[u] = false;
+        v[u] = T(0);
+        if (g < n_groups && i < n) {
+          ok[u] = valid.present() ? ((valid.word32(g) >> lane) & 1u) != 0 : true;
+          if (ok[u]) v[u] = __ldcs(values + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (ok[u]) partial_add(p, v[u]);
     }
   }
   p = block_reduce(p);
@@ -168,7 +223,22 @@ __global__ void __launch_bounds__(kBlock) reduce_final_kernel(const Partial<T>* 
     else out[1] = static_cast<unsigned long long>(p.sum);
     out[2] = widen_bits(p.mn);
     out[3] = widen_bits(p.mx);
-    out[4] = static_cast<unsigned long long>(__double_as_longlong(p.dsum));
+    // the sum as a double (what MeanImpl divides): floats = the sum itself, integers = the exact 128-bit value rounded once
+    double ds;
+    if constexpr (std::is_floating_point<T>::value) ds = p.sum;
+    else {
+      // sign-magnitude first: hi * 2^64 + lo would cancel catastrophically for small negative sums
+      unsigned long long lo = static_cast<unsigned long long>(p.sum);
+      long long hi = p.hi;
+      const bool neg = hi < 0;
+      if (neg) {  // two's complement negate of the 128-bit value
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0 ? 1 : 0);
+      }
+      ds = ldexp(static_cast<double>(hi), 64) + static_cast<double>(lo);
+      if (neg) ds = -ds;
+    }
+    out[4] = static_cast<unsigned long long>(__double_as_longlong(ds));
   }
 }
 
@@ -182,7 +252,8 @@ static int reduce_typed(B2Context* ctx, const B2Array* values, B2ReduceResult* o
   B2_RETURN_NOT_OK(partials.alloc(sizeof(Partial<T>) * (size_t)grid));
   ScalarSlot slot(ctx);
   B2_RETURN_NOT_OK(slot.zero(s));
-  reduce_kernel<T><<<grid, kBlock, 0, s>>>(v, valid, n, partials.as<Partial<T>>());
+  if (aligned_to(v, 16)) reduce_kernel<T, true><<<grid, kBlock, 0, s>>>(v, valid, n, partials.as<Partial<T>>());
+  else reduce_kernel<T, false><<<grid, kBlock, 0, s>>>(v, valid, n, partials.as<Partial<T>>());
   B2_LAUNCHED();
   reduce_final_kernel<T><<<1, kBlock, 0, s>>>(partials.as<Partial<T>>(), grid, reinterpret_cast<unsigned long long*>(slot.dev()));
   B2_LAUNCHED();

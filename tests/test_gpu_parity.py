@@ -515,8 +515,10 @@ def test_scalar_aggregates(ctx, t):
     assert bc.sum(dev(pa.array([0, None, 2, 3, None, 5], t), ctx)) == pa.scalar(10, acc)
     assert bc.mean(dev(pa.array([1, 2, 3, 4, 5, 6, 7, 8], t), ctx)) == pa.scalar(4.5, pa.float64())
     assert bc.min_max(dev(pa.array([5, None, 2, 3, 4], t), ctx)).as_py() == {"min": 2, "max": 5}
-    for n, null_p in ((0, 0.0), (1, 0.0), (1000, 0.0), (70001, 0.1), (5000, 1.0), (1 << 21, 0.3)):
-        a = random_array(t, n, null_p, SEED + n, offset=5)
+    # offset 5: values not 16-byte aligned (scalar loads); offsets 0 / 16: the vectorised path, 16 with a bit offset
+    for n, null_p, off in ((0, 0.0, 5), (1, 0.0, 5), (1000, 0.0, 5), (70001, 0.1, 5), (5000, 1.0, 5), (1 << 21, 0.3, 5),
+                           (70001, 0.1, 0), (1 << 21, 0.3, 16), (1000, 0.0, 16), (37, 0.5, 0)):
+        a = random_array(t, n, null_p, SEED + n, offset=off)
         d = dev(a, ctx)
         for skip in (True, False):
             for mc in (0, 1, 3):
