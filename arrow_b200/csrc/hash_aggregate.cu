@@ -123,6 +123,82 @@ __global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __rest
   }
 }
 
+// Few groups (<= kPrivateMaxGroups): millions of rows update the same handful of state words, and
+// same-address global atomics retire at ~30 ns each (100 groups x 1B rows: 660 ms; merging equal
+// groups inside a warp does not help -- 32 rows over 100 groups are almost all distinct).  This
+// variant keeps a private copy of the whole state in shared memory per CTA (integer sums as two
+// 32-bit halves with an explicit carry: native ATOMS instead of a 64-bit CAS loop) and adds it to the
+// global state once at the end: grid x G global atomics in total.
+constexpr int kPrivateMaxGroups = 2048;
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) hashagg_consume_private_kernel(const T* __restrict__ values, BitmapReader valid,
+                                                                         const uint32_t* __restrict__ ids, int64_t n,
+                                                                         AggState st, int num_groups, int count_mode) {
+  constexpr bool kSum = KIND == B2_HASH_SUM || KIND == B2_HASH_MEAN;
+  constexpr bool kDouble = kSum && (std::is_floating_point<T>::value || KIND == B2_HASH_MEAN);
+  constexpr bool kCount = KIND == B2_HASH_COUNT || KIND == B2_HASH_COUNT_ALL;
+  __shared__ unsigned long long s_red[kCount ? 1 : kPrivateMaxGroups];
+  __shared__ unsigned int s_cnt[kPrivateMaxGroups];
+  __shared__ uint8_t s_null[kPrivateMaxGroups];
+  const unsigned long long identity = kSum ? 0ull : (KIND == B2_HASH_MIN ? ~0ull : 0ull);
+  for (int g = threadIdx.x; g < num_groups; g += kBlock) {
+    if (!kCount) s_red[g] = identity;
+    s_cnt[g] = 0;
+    s_null[g] = 0;
+  }
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint32_t g = __ldcs(ids + i);
+    if (kCount) {  // count_mode: 0 only valid, 1 only null, 2 all (count_all passes 2)
+      const bool ok = count_mode == 2 || valid.bit(i) == (count_mode == 0);
+      if (ok) atomicAdd(&s_cnt[g], 1u);
+      continue;
+    }
+    if (!valid.bit(i)) {
+      s_null[g] = 1;
+      continue;
+    }
+    const T v = __ldcs(values + i);
+    if (kSum) {
+      if (kDouble) {
+        atomicAdd(reinterpret_cast<double*>(&s_red[g]), static_cast<double>(v));
+      } else {
+        const unsigned long long b = std::is_signed<T>::value ? static_cast<unsigned long long>(static_cast<long long>(v))
+                                                             : static_cast<unsigned long long>(v);
+        unsigned int* half = reinterpret_cast<unsigned int*>(&s_red[g]);  // little endian: [0] = lo, [1] = hi
+        const unsigned int lo32 = static_cast<unsigned int>(b), hi32 = static_cast<unsigned int>(b >> 32);
+        const unsigned int old = atomicAdd(half, lo32);
+        const unsigned int carry = (old + lo32) < old ? 1u : 0u;
+        if (hi32 + carry) atomicAdd(half + 1, hi32 + carry);
+      }
+    } else if (v == v) {  // fmin / fmax skip NaN
+      if (KIND == B2_HASH_MIN) atomicMin(&s_red[g], minmax_encode<T>(v));
+      else atomicMax(&s_red[g], minmax_encode<T>(v));
+    }
+    atomicAdd(&s_cnt[g], 1u);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < num_groups; g += kBlock) {
+    if (s_null[g]) st.flags[g] |= 1;
+    const unsigned int c = s_cnt[g];
+    if (!c) continue;
+    if (kCount) {
+      atomicAdd(&st.counts[g], static_cast<unsigned long long>(c));
+      continue;
+    }
+    if (kSum) {
+      if (kDouble) atomicAdd(reinterpret_cast<double*>(&st.reduced[g]), __longlong_as_double((long long)s_red[g]));
+      else atomicAdd(&st.reduced[g], s_red[g]);
+    } else if (KIND == B2_HASH_MIN) {
+      atomicMin(&st.reduced[g], s_red[g]);
+    } else {
+      atomicMax(&st.reduced[g], s_red[g]);
+    }
+    atomicAdd(&st.counts[g], static_cast<unsigned long long>(c));
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) hashagg_countall_kernel(const uint32_t* __restrict__ ids, int64_t n,
                                                                   unsigned long long* counts) {
   const unsigned lane = lane_id();
@@ -248,6 +324,21 @@ static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* id
   // DRAM sector read-modify-write (47 ms per 1B rows at 10M groups).  Large batches are
   // therefore consumed in BANDS of group ids whose state stays L2-resident, re-streaming the
   // ids (and the values of the band's rows) once per band: 2 bands at 10M groups = 20 ms.
+  if (a->num_groups <= kPrivateMaxGroups && n >= (1 << 16)) {
+    const int g = (int)a->num_groups;
+    const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);  // few CTAs: each flushes the whole state once
+    switch (a->kind) {
+      case B2_HASH_SUM: hashagg_consume_private_kernel<T, B2_HASH_SUM><<<pgrid, kBlock, 0, s>>>(v, valid, id, n, a->st, g, 0); break;
+      case B2_HASH_MEAN: hashagg_consume_private_kernel<T, B2_HASH_MEAN><<<pgrid, kBlock, 0, s>>>(v, valid, id, n, a->st, g, 0); break;
+      case B2_HASH_MIN: hashagg_consume_private_kernel<T, B2_HASH_MIN><<<pgrid, kBlock, 0, s>>>(v, valid, id, n, a->st, g, 0); break;
+      case B2_HASH_COUNT:
+        hashagg_consume_private_kernel<T, B2_HASH_COUNT><<<pgrid, kBlock, 0, s>>>(v, valid, id, n, a->st, g, a->opt.count_mode);
+        break;
+      default: hashagg_consume_private_kernel<T, B2_HASH_MAX><<<pgrid, kBlock, 0, s>>>(v, valid, id, n, a->st, g, 0); break;
+    }
+    B2_LAUNCHED();
+    return B2_OK;
+  }
   const bool two_arrays = a->kind != B2_HASH_COUNT;
   const int64_t band_groups = (80ll << 20) / (two_arrays ? 16 : 8);
   int64_t bands = (a->num_groups + band_groups - 1) / band_groups;
@@ -357,8 +448,15 @@ int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, 
   const int64_t n = ids->length;
   if (n == 0) return B2_OK;
   const uint32_t* id = static_cast<const uint32_t*>(ids->data) + ids->offset;
+  const bool few_groups = a->num_groups <= kPrivateMaxGroups && n >= (1 << 16);
+  const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);
   if (a->kind == B2_HASH_COUNT_ALL) {
-    hashagg_countall_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(id, n, a->st.counts);
+    if (few_groups) {
+      hashagg_consume_private_kernel<uint8_t, B2_HASH_COUNT_ALL><<<pgrid, kBlock, 0, s>>>(
+          nullptr, BitmapReader(nullptr, 0, n), id, n, a->st, (int)a->num_groups, 2);
+    } else {
+      hashagg_countall_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(id, n, a->st.counts);
+    }
     B2_LAUNCHED();
     return B2_OK;
   }
@@ -367,8 +465,12 @@ int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, 
   if (a->kind == B2_HASH_COUNT && !type_is_numeric(values->type)) {
     // count only needs validity: any layout works
     BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
-    hashagg_consume_kernel<uint8_t, B2_HASH_COUNT><<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(
-        nullptr, valid, id, n, a->st, a->opt.count_mode, 0u, 0xffffffffu);
+    if (few_groups)
+      hashagg_consume_private_kernel<uint8_t, B2_HASH_COUNT><<<pgrid, kBlock, 0, s>>>(nullptr, valid, id, n, a->st,
+                                                                                      (int)a->num_groups, a->opt.count_mode);
+    else
+      hashagg_consume_kernel<uint8_t, B2_HASH_COUNT><<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(
+          nullptr, valid, id, n, a->st, a->opt.count_mode, 0u, 0xffffffffu);
     B2_LAUNCHED();
     return B2_OK;
   }

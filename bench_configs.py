@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--only", default="c1,cmp,c3,c4,c5,f1")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--groups", type=int, default=0, help="c3: number of distinct keys (default 10M at >= 100M rows)")
     args = ap.parse_args()
     only = set(args.only.split(","))
     n = args.rows
@@ -97,7 +98,7 @@ def main():
         del values, vals_t, vvalid_t
 
     if "c3" in only:
-        groups = 10_000_000 if n >= 100_000_000 else max(1000, n // 100)
+        groups = args.groups or (10_000_000 if n >= 100_000_000 else max(1000, n // 100))
         keys_t = torch.randint(0, groups, (n,), dtype=torch.int64, device="cuda", generator=gen)
         vals_t = torch.randint(-100, 101, (n,), dtype=torch.int64, device="cuda", generator=gen)
         vvalid_t, v_nulls = make_validity(torch, n, gen)
