@@ -324,7 +324,7 @@ static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* id
   // DRAM sector read-modify-write (47 ms per 1B rows at 10M groups).  Large batches are
   // therefore consumed in BANDS of group ids whose state stays L2-resident, re-streaming the
   // ids (and the values of the band's rows) once per band: 2 bands at 10M groups = 20 ms.
-  if (a->num_groups <= kPrivateMaxGroups && n >= (1 << 16)) {
+  if (a->num_groups <= kPrivateMaxGroups && n >= (1 << 14)) {
     const int g = (int)a->num_groups;
     const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);  // few CTAs: each flushes the whole state once
     switch (a->kind) {
@@ -448,7 +448,7 @@ int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, 
   const int64_t n = ids->length;
   if (n == 0) return B2_OK;
   const uint32_t* id = static_cast<const uint32_t*>(ids->data) + ids->offset;
-  const bool few_groups = a->num_groups <= kPrivateMaxGroups && n >= (1 << 16);
+  const bool few_groups = a->num_groups <= kPrivateMaxGroups && n >= (1 << 14);
   const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);
   if (a->kind == B2_HASH_COUNT_ALL) {
     if (few_groups) {

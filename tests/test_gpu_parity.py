@@ -545,3 +545,27 @@ def test_scalar_aggregates(ctx, t):
         assert bc.min_max(dev(nan, ctx)) == pc.min_max(nan)
         assert np.isnan(bc.min_max(dev(pa.array([np.nan, np.nan], t), ctx))["max"].as_py())
     assert bc.call_function("sum", [dev(pa.array([1, 2], t), ctx)]) == pa.scalar(3, acc)
+
+
+@pytest.mark.parametrize("vt", [pa.int64(), pa.int16(), pa.uint32(), pa.float64(), pa.float32()], ids=str)
+@pytest.mark.parametrize("groups", [1, 7, 2048, 2049])
+def test_hash_aggregates_few_groups_large(ctx, vt, groups):
+    """<= 2048 groups take the shared-memory privatised consume kernel (hot groups would serialise their
+    global atomics); 2049 the plain one.  Oracle = the reference engine (Acero group_by), sorted by key."""
+    import pyarrow.acero  # noqa: F401
+    n = 1 << 20
+    keys = random_array(pa.int64(), n, 0.02, SEED + groups, lo=0, hi=groups - 1)
+    vals = random_array(vt, n, 0.1, SEED + 3, lo=-100 if not pa.types.is_unsigned_integer(vt) else 0, hi=100)
+    fns = ["sum", "count", "mean", "min", "max"]
+    uniq, outs = bc.group_by([dev(keys, ctx)], [("hash_" + f, dev(vals, ctx), None) for f in fns] + [("hash_count_all", None, None)])
+    ref = pa.table({"k": keys, "v": vals}).group_by("k", use_threads=False).aggregate([("v", f) for f in fns] + [([], "count_all")]).sort_by("k")
+    mine = pa.table({"k": uniq[0].to_arrow(), **{"v_" + f: o.to_arrow() for f, o in zip(fns, outs)}, "count_all": outs[-1].to_arrow()}).sort_by("k")
+    assert mine["k"].combine_chunks().equals(ref["k"].combine_chunks())
+    for f in fns + ["count_all"]:
+        name = f if f == "count_all" else "v_" + f
+        got, want = mine[name].combine_chunks(), ref[name].combine_chunks()
+        if pa.types.is_floating(got.type) and f in ("sum", "mean"):
+            assert got.is_valid().equals(want.is_valid())
+            np.testing.assert_allclose(got.fill_null(0).to_numpy(), want.fill_null(0).to_numpy(), rtol=1e-9, atol=1e-6)
+        else:
+            assert got.equals(want), (vt, groups, f)
