@@ -112,18 +112,21 @@ __device__ __forceinline__ Partial<T> block_reduce(Partial<T> p) {
   return p;
 }
 
+// branch-free (the caller counts): a null slot adds 0 to the sum and leaves min / max alone (a divergent branch per
+// element cost more than the arithmetic it skipped)
 template <typename T>
-__device__ __forceinline__ void partial_add(Partial<T>& p, T v) {
+__device__ __forceinline__ void partial_add(Partial<T>& p, T v, bool ok) {
+  using Acc = typename AccOf<T>::type;
+  const T x = ok ? v : T(0);
   if constexpr (!std::is_floating_point<T>::value) {
-    // exact 128-bit accumulation: sign-extend v, add with carry
+    // exact 128-bit accumulation: sign-extend x, add with carry
     const unsigned long long old = static_cast<unsigned long long>(p.sum);
-    const unsigned long long add = static_cast<unsigned long long>(static_cast<typename AccOf<T>::type>(v));
-    p.hi += (std::is_signed<T>::value && v < T(0) ? -1 : 0) + ((old + add) < old ? 1 : 0);
+    const unsigned long long add = static_cast<unsigned long long>(static_cast<Acc>(x));
+    p.hi += (std::is_signed<T>::value && x < T(0) ? -1 : 0) + ((old + add) < old ? 1 : 0);
   }
-  p.sum += static_cast<typename AccOf<T>::type>(v);
-  p.count += 1;
-  p.mn = min_of(p.mn, v);
-  p.mx = max_of(p.mx, v);
+  p.sum += static_cast<Acc>(x);
+  p.mn = ok ? min_of(p.mn, v) : p.mn;
+  p.mx = ok ? max_of(p.mx, v) : p.mx;
 }
 
 // VEC: every lane loads 16 bytes (E = 16 / sizeof(T) consecutive rows), so a warp covers 32 * E rows
@@ -142,9 +145,14 @@ __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__
     constexpr int kRows = 32 * E;  // rows per warp step: 64 .. 512 = 1 .. 8 validity words
     constexpr int kU = 4;
     const int64_t n_steps = (n + kRows - 1) / kRows;
+    constexpr int W = E / 2;  // 64-bit validity words per step
+    constexpr unsigned kFull = E == 32 ? 0xffffffffu : ((1u << E) - 1u);
+    const int wsrc = (lane * E) >> 6, wsh = (lane * E) & 63;  // this lane's word inside a step, bit inside the word
     for (int64_t s0 = warp0; s0 < n_steps; s0 += warps * kU) {
       uint4 raw[kU];
       unsigned bits[kU];
+      // values first and unconditionally (null slots cost no extra sectors; waiting for the validity
+      // word would put two DRAM round trips in series)
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t step = s0 + u * warps;
@@ -153,27 +161,38 @@ __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__
         raw[u] = make_uint4(0, 0, 0, 0);
         if (step < n_steps && i0 < n) {
           const int64_t rem = n - i0;
-          // the values are requested first and unconditionally: making the load wait for the validity
-          // word would put two DRAM round trips in series (null slots cost no extra sectors anyway)
           if (rem >= E) {
             raw[u] = __ldcs(reinterpret_cast<const uint4*>(values + i0));
+            bits[u] = kFull;
           } else {  // last, partial vector of the column
             T tmp[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) tmp[e] = e < rem ? values[i0 + e] : T(0);
             raw[u] = *reinterpret_cast<const uint4*>(tmp);
+            bits[u] = (1u << rem) - 1u;
           }
-          unsigned m = rem >= E ? ((E == 32) ? 0xffffffffu : ((1u << E) - 1u)) : ((1u << rem) - 1u);
-          if (valid.present()) m &= static_cast<unsigned>(valid.word(i0 >> 6) >> (i0 & 63));  // E divides 64: one word
-          bits[u] = m;
+        }
+      }
+      // validity: the kU * W words of these steps are extracted ONCE, by lanes 0 .. kU*W-1, and handed
+      // round with shuffles (every lane redoing the unaligned-word extraction cost more than the sums)
+      if (valid.present()) {
+        unsigned long long mine = 0;
+        if (lane < kU * W) {
+          const int64_t step = s0 + (lane / W) * warps;
+          if (step < n_steps) mine = valid.word(step * W + (lane % W));
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const unsigned long long w = __shfl_sync(0xffffffffu, mine, u * W + wsrc);
+          bits[u] &= static_cast<unsigned>(w >> wsh);
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const T* v = reinterpret_cast<const T*>(&raw[u]);
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-          if ((bits[u] >> e) & 1u) partial_add(p, v[e]);
+        for (int e = 0; e < E; ++e) partial_add(p, v[e], ((bits[u] >> e) & 1u) != 0);
+        p.count += __popc(bits[u]);
       }
     }
   } else {
@@ -194,8 +213,10 @@ __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (ok[u]) partial_add(p, v[u]);
+      for (int u = 0; u < kU; ++u) {
+        partial_add(p, v[u], ok[u]);
+        p.count += ok[u] ? 1 : 0;
+      }
     }
   }
   p = block_reduce(p);
