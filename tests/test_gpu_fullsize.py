@@ -34,6 +34,14 @@ def torch_mod(ctx):
     return torch
 
 
+def run(ctx, torch, fn):
+    """torch (the checker) works on its own stream, the C-ABI calls on the context's: order them explicitly."""
+    torch.cuda.synchronize()
+    out = fn()
+    ctx.sync()
+    return out
+
+
 def random_bitmap(torch, n, p_set, gen):
     """packed LSB-first bitmap with Bernoulli(p_set) bits, its bool expansion is produced chunk-wise"""
     out = torch.zeros((n + 7) // 8 + 64, dtype=torch.uint8, device="cuda")
@@ -78,7 +86,7 @@ def test_fullsize_filter(ctx, torch_mod):
     vals = DeviceArray.from_pointers(ctx, pa.int64(), N, vals_t.data_ptr(), validity_ptr=valid_t.data_ptr(),
                                      null_count=N - n_valid)
     mask = DeviceArray.from_pointers(ctx, pa.bool_(), N, mask_t.data_ptr())
-    out = bc.filter(vals, mask)
+    out = run(ctx, torch, lambda: bc.filter(vals, mask))
     assert len(out) == n_sel
     sel = bits_to_bool(torch, mask_t, N)
     ok = bits_to_bool(torch, valid_t, N)
@@ -111,9 +119,9 @@ def test_fullsize_take_round_trip(ctx, torch_mod):
     vals = DeviceArray.from_pointers(ctx, pa.float64(), N, vals_t.data_ptr())
     perm = DeviceArray.from_pointers(ctx, pa.int64(), N, perm_t.data_ptr())
     inv = DeviceArray.from_pointers(ctx, pa.int64(), N, inv_t.data_ptr())
-    once = bc.take(vals, perm)
+    once = run(ctx, torch, lambda: bc.take(vals, perm))
     assert as_tensor(torch, once, torch.float64)[12345].item() == vals_t[perm_t[12345]].item()
-    back = bc.take(once, inv)
+    back = run(ctx, torch, lambda: bc.take(once, inv))
     assert torch.equal(as_tensor(torch, back, torch.float64), vals_t)
 
 
@@ -125,7 +133,7 @@ def test_fullsize_sort_indices(ctx, torch_mod):
     valid_t, n_valid = random_bitmap(torch, n, 0.9, gen)
     keys = DeviceArray.from_pointers(ctx, pa.int64(), n, keys_t.data_ptr(), validity_ptr=valid_t.data_ptr(),
                                      null_count=n - n_valid)
-    idx = as_tensor(torch, bc.array_sort_indices(keys), torch.int64)
+    idx = as_tensor(torch, run(ctx, torch, lambda: bc.array_sort_indices(keys)), torch.int64)
     seen = torch.zeros(n, dtype=torch.bool, device="cuda")
     seen[idx] = True
     assert bool(seen.all())  # a permutation
@@ -150,8 +158,8 @@ def test_fullsize_group_by(ctx, torch_mod):
     vals = DeviceArray.from_pointers(ctx, pa.int64(), N, vals_t.data_ptr(), validity_ptr=valid_t.data_ptr(),
                                      null_count=N - n_valid)
     g = bc.GroupBySumCount(pa.int64(), pa.int64(), expected_groups=groups, ctx=ctx)
-    g.consume(keys, vals)
-    out_keys, sums, counts = g.finalize()
+    run(ctx, torch, lambda: g.consume(keys, vals))
+    out_keys, sums, counts = run(ctx, torch, g.finalize)
     ok = bits_to_bool(torch, valid_t, N)
     want_sum = torch.zeros(groups, dtype=torch.int64, device="cuda").index_add_(0, keys_t[ok], vals_t[ok])
     want_cnt = torch.bincount(keys_t[ok], minlength=groups)
