@@ -50,6 +50,27 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        # NVML in-process (same counters nvidia-smi prints, but every 10 ms: the device-resident timed region
+        # is < 200 ms long); the nvidia-smi subprocess loop is the fallback
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [0x8, 0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap (nvml.h)
+        while not self.stop_flag.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = int(reasons(h))
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            self.stop_flag.wait(0.01)
+
+    def _smi_loop(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
