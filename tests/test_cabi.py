@@ -51,6 +51,31 @@ def test_struct_layout_matches_header():
     assert C.sizeof(cabi.B2CastOptions) == 16
     assert C.sizeof(cabi.B2HashAggOptions) == 16
     assert C.sizeof(cabi.B2Value) == 16
+    assert C.sizeof(cabi.B2ReduceResult) == 56
+
+
+def test_struct_layout_against_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct as gcc sees include/arrow_b200.h vs the ctypes mirror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"B2Array": cabi.B2Array, "B2Scalar": cabi.B2Scalar, "B2Value": cabi.B2Value, "B2CastOptions": cabi.B2CastOptions,
+               "B2HashAggOptions": cabi.B2HashAggOptions, "B2ReduceResult": cabi.B2ReduceResult}
+    lines = []
+    for name, st in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "arrow_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, st in structs.items():
+        assert int(got[name]) == C.sizeof(st), name
+        for field, _ in st._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(st, field).offset, f"{name}.{field}"
 
 
 def test_type_ids_follow_arrow():
