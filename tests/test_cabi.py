@@ -98,3 +98,37 @@ def test_common_numeric_matches_reference_dispatch():
     for a, b in itertools.product(types, types):
         want = pc.add(pa.array([1], a), pa.array([1], b)).type  # ArithmeticFunction::DispatchBest
         assert arrow_type(common_numeric([type_id(a), type_id(b)])) == want, f"{a},{b}"
+
+
+def test_plain_c_client_links_and_calls(tmp_path):
+    """The boundary is a C ABI: a C11 translation unit including only include/arrow_b200.h links against
+    libarrow_b200.so, and the context either comes up (GPU box) or fails loudly (no CPU fallback)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "arrow_b200", "lib")
+    src = tmp_path / "client.c"
+    src.write_text('''
+#include <stdio.h>
+#include "arrow_b200.h"
+int main(void) {
+  B2Context* ctx = NULL;
+  printf("version %s\\n", b2_version());
+  int st = b2_context_create(0, &ctx);
+  if (st != B2_OK) { printf("status %d: %s\\n", st, b2_last_error()); return 0; }
+  void* p = NULL;
+  if (b2_alloc(ctx, 1 << 20, &p) != B2_OK) return 2;
+  b2_free(ctx, p);
+  b2_context_destroy(ctx);
+  printf("context ok\\n");
+  return 0;
+}
+''')
+    exe = tmp_path / "client"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir,
+                           "-larrow_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "version arrow_b200" in out.stdout
+    assert "context ok" in out.stdout or "no CPU" in out.stdout, out.stdout
