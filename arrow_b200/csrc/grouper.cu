@@ -12,16 +12,23 @@
 // guarantees a bijection of that order).
 //
 // B200 design (per Consume call, all stream-ordered):
-//   insert : every row encodes its key (<= 64 bits incl. in-band null flags), claims or
-//            finds its slot with one 64-bit atomicCAS (linear probing), remembers the
-//            slot, and atomicMin's its row number into the slot if the group is new.
-//   flag   : row i is a "first occurrence" iff its slot is new and holds min row == i;
-//            flags are written as bitmap words (warp ballot).
-//   rank   : the Filter count+scan passes turn the flag bitmap into per-tile offsets, so
+//   insert : every row encodes its key (<= 64 bits incl. in-band null flags) and finds or claims
+//            its 16-byte slot {key, id, first_row} (linear probing, one 16-byte load per probe,
+//            one 64-bit atomicCAS to claim).  A group that already has an id (seen in an earlier
+//            batch) yields the row's id right away; a group that is new in this batch lowers the
+//            slot's first_row to the row number (atomicMin, skipped when a smaller row got there
+//            first -- the common case since rows are visited in ascending order).
+//   flag   : bit i = row i is the first occurrence of a new group.  Built from the table (one
+//            streaming pass over the slots) when the table is not larger than the batch, else
+//            from the unresolved rows.
+//   rank   : the Filter count+scan pass turns the flag bitmap into per-tile offsets, so
 //            new-group ids = num_groups + rank (first-occurrence order, no atomics).
 //   assign : first-occurrence rows publish id and append the encoded key to `uniques`.
-//   gather : out_ids[i] = id[slot[i]].
-// The table grows 4x (rehash from `uniques`) when the probe limit is hit or load > 1/2.
+//   gather : out_ids[i] = id[slot[i]] for the rows the insert pass left unresolved.
+// Lookup is one pass (probe + id read + validity ballot).  The table grows 4x (rehash from
+// `uniques`) when the probe limit is hit -- the insert pass stops at the first overflow -- or
+// when the load exceeds 1/2.  Every random access is one 32-byte sector: measured 25.5 ms
+// (insert) + 22.1 ms (gather) per 1B rows at 10M groups = the 42 G accesses/s DRAM ceiling.
 #include "hash_table.cuh"
 #include "selection.cuh"
 
