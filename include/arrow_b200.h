@@ -285,7 +285,8 @@ typedef struct B2ReduceResult {
   uint64_t min_bits;  /* min over valid rows widened to int64 / uint64 / double bits; the type's
                          anti-extremum (NaN for floats) when count == 0 or every value is NaN */
   uint64_t max_bits;
-  uint64_t dsum_bits; /* the sum accumulated in double (what MeanImpl divides by count, :263-283) */
+  uint64_t dsum_bits; /* the sum as a double for MeanImpl's sum / count (:263-283): floats = sum_bits,
+                         integers = the exact 128-bit sum rounded once (never the int64 wrap-around) */
   int32_t acc_type;   /* B2_INT64, B2_UINT64 or B2_DOUBLE (FindAccumulatorType) */
   int32_t value_type;
 } B2ReduceResult;
