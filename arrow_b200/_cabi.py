@@ -79,6 +79,9 @@ ARITH_OPS = {
     "add_checked": 16, "subtract_checked": 17, "multiply_checked": 18, "divide_checked": 19,
 }
 COMPARE_OPS = {"equal": 0, "not_equal": 1, "greater": 2, "greater_equal": 3, "less": 4, "less_equal": 5}
+BOOLEAN_OPS = {"and": 0, "or": 1, "xor": 2, "and_not": 3, "and_kleene": 4, "or_kleene": 5, "and_not_kleene": 6, "invert": 7}
+VALIDITY_OPS = {"is_valid": 0, "is_null": 1, "true_unless_null": 2, "is_nan": 3}
+COMM_ID_BYTES = 128
 HASH_AGG_KINDS = {"hash_sum": 0, "hash_count": 1, "hash_count_all": 2, "hash_mean": 3, "hash_min": 4,
                   "hash_max": 5, "hash_product": 6}
 
@@ -140,6 +143,20 @@ PROTOTYPES = [
     ("b2_groupby_sumcount_finalize", C.c_int, [_P, _A, _A, _A, _P]),
     ("b2_hash_partition", C.c_int, [_P, _A, C.c_int, _A, _P]),
     ("b2_range_partition", C.c_int, [_P, _A, _A, C.c_int, _A, _P]),
+    ("b2_bincount", C.c_int, [_P, _A, C.c_int, _I64P, _P]),
+    ("b2_boolean", C.c_int, [_P, C.c_int, _V, _V, _A, _P]),
+    ("b2_validity", C.c_int, [_P, C.c_int, _A, C.c_int, _A, _P]),
+    ("b2_comm_unique_id", C.c_int, [_P]),
+    ("b2_comm_init", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    ("b2_comm_destroy", None, [_P]),
+    ("b2_comm_rank", C.c_int, [_P]),
+    ("b2_comm_world", C.c_int, [_P]),
+    ("b2_comm_nccl_version", C.c_int, [C.POINTER(C.c_int)]),
+    ("b2_comm_group_start", C.c_int, [_P]),
+    ("b2_comm_group_end", C.c_int, [_P]),
+    ("b2_comm_all_gather", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b2_comm_all_reduce_i64", C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    ("b2_comm_all_to_all_v", C.c_int, [_P, _P, _I64P, _I64P, _P, _I64P, _I64P, _P]),
 ]
 
 _lib = None

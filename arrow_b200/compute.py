@@ -23,6 +23,7 @@ import numpy as np
 import pyarrow as pa
 
 from . import _cabi as cabi
+from .device import _NUMERIC as _NUMERIC_TYPES
 from .device import Context, DeviceArray, arrow_type, check, type_id
 
 Operand = Union[DeviceArray, pa.Scalar, int, float, bool, None]
@@ -68,6 +69,16 @@ def common_numeric(ids: Sequence[int]) -> int:
     return {8: cabi.INT8, 16: cabi.INT16, 32: cabi.INT32}.get(ms, cabi.INT64)
 
 
+def _require_numeric(t: pa.DataType) -> None:
+    """Only the ten genuinely numeric Arrow types reach the numeric kernels.  Temporal / dictionary /
+    other logical types share an integer STORAGE with them but not their semantics (the reference
+    rescales units in casts, kernels/scalar_cast_temporal.cc, and dispatches timestamp/duration
+    arithmetic to dedicated kernels, kernels/scalar_arithmetic.cc:1480-1529): refuse rather than
+    compute on raw storage."""
+    if t not in _NUMERIC_TYPES:
+        raise pa.ArrowNotImplementedError(f"Function has no kernel matching input types ({t}) on arrow_b200 device arrays")
+
+
 def _as_scalar(x) -> pa.Scalar:
     if isinstance(x, pa.Scalar):
         return x
@@ -105,12 +116,14 @@ def _prepare_binary(left: Operand, right: Operand):
     ids = []
     for x in (left, right):
         if isinstance(x, DeviceArray):
+            _require_numeric(x.type)
             ids.append(type_id(x.type))
             ops.append(x)
         else:
             s = _as_scalar(x)
             if pa.types.is_null(s.type):
                 raise pa.ArrowNotImplementedError("null-typed scalar operands are not supported")
+            _require_numeric(s.type)
             ids.append(type_id(s.type))
             ops.append(s)
     if not any(isinstance(o, DeviceArray) for o in ops):
@@ -151,8 +164,13 @@ def cast(arr: DeviceArray, target_type=None, safe: Optional[bool] = None, option
     target_type = pa.lib.ensure_type(target_type)
     if arr.type == target_type:
         return arr
+    # logical types (timestamp/date/time/duration/dictionary) have numeric STORAGE ids but unit / index
+    # semantics the numeric cast kernel does not implement: only exact numeric types pass
+    if arr.type not in _NUMERIC_TYPES or target_type not in _NUMERIC_TYPES:
+        raise pa.ArrowNotImplementedError(
+            f"Unsupported cast from {arr.type} to {target_type} using function cast_{target_type}")
     src, dst = type_id(arr.type), type_id(target_type)
-    if src not in _NUMERIC_IDS or dst not in _NUMERIC_IDS or pa.types.is_dictionary(arr.type):
+    if src not in _NUMERIC_IDS or dst not in _NUMERIC_IDS:
         raise pa.ArrowNotImplementedError(
             f"Unsupported cast from {arr.type} to {target_type} using function cast_{target_type}")
     ctx = arr.ctx
@@ -192,6 +210,64 @@ def greater(x, y): return _compare("greater", x, y)
 def greater_equal(x, y): return _compare("greater_equal", x, y)
 def less(x, y): return _compare("less", x, y)
 def less_equal(x, y): return _compare("less_equal", x, y)
+
+
+# ------------------------------------------------------------------------------------
+# boolean logic + validity predicates (kernels/scalar_boolean.cc, kernels/scalar_validity.cc)
+# ------------------------------------------------------------------------------------
+def _bool_value(x, keep):
+    v = cabi.B2Value()
+    if isinstance(x, DeviceArray):
+        if not pa.types.is_boolean(x.type):
+            raise pa.ArrowNotImplementedError(f"Function has no kernel matching input types ({x.type})")
+        c = x._c()
+        keep.append((x, c))
+        v.array, v.scalar = C.pointer(c), None
+    else:
+        s = _as_scalar(x)
+        if not (pa.types.is_boolean(s.type) or pa.types.is_null(s.type)):
+            raise pa.ArrowNotImplementedError(f"Function has no kernel matching input types ({s.type})")
+        sc = cabi.B2Scalar()
+        sc.type, sc.is_valid = cabi.BOOL, 1 if s.is_valid else 0
+        sc.bits = 1 if (s.is_valid and s.as_py()) else 0
+        keep.append(sc)
+        v.array, v.scalar = None, C.pointer(sc)
+    return v
+
+
+def _boolean(name: str, left, right=None) -> DeviceArray:
+    ctx = _ctx(left, right)
+    keep = []
+    lv = _bool_value(left, keep)
+    rv = _bool_value(right, keep) if name != "invert" else None
+    cout = cabi.B2Array()
+    check(ctx.lib.b2_boolean(ctx.handle, cabi.BOOLEAN_OPS[name], C.byref(lv), C.byref(rv) if rv is not None else None,
+                             C.byref(cout), ctx.stream))
+    return _out(ctx, cout, pa.bool_())
+
+
+def and_(x, y): return _boolean("and", x, y)
+def or_(x, y): return _boolean("or", x, y)
+def xor(x, y): return _boolean("xor", x, y)
+def and_not(x, y): return _boolean("and_not", x, y)
+def and_kleene(x, y): return _boolean("and_kleene", x, y)
+def or_kleene(x, y): return _boolean("or_kleene", x, y)
+def and_not_kleene(x, y): return _boolean("and_not_kleene", x, y)
+def invert(x): return _boolean("invert", x)
+
+
+def _validity(name: str, arr: DeviceArray, nan_is_null: bool = False) -> DeviceArray:
+    ctx = arr.ctx
+    ca, cout = arr._c(), cabi.B2Array()
+    check(ctx.lib.b2_validity(ctx.handle, cabi.VALIDITY_OPS[name], C.byref(ca), int(bool(nan_is_null)), C.byref(cout),
+                              ctx.stream))
+    return _out(ctx, cout, pa.bool_())
+
+
+def is_valid(x): return _validity("is_valid", x)
+def is_null(x, nan_is_null=False): return _validity("is_null", x, nan_is_null)
+def true_unless_null(x): return _validity("true_unless_null", x)
+def is_nan(x): return _validity("is_nan", x)
 
 
 # ------------------------------------------------------------------------------------
@@ -299,6 +375,7 @@ def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", orde
 # ungrouped aggregates (kernels/aggregate_basic.cc, aggregate_basic.inc.cc)
 # ------------------------------------------------------------------------------------
 def _reduce(arr: DeviceArray) -> "cabi.B2ReduceResult":
+    _require_numeric(arr.type)
     ctx = arr.ctx
     ca, r = arr._c(), cabi.B2ReduceResult()
     check(ctx.lib.b2_reduce(ctx.handle, C.byref(ca), C.byref(r), ctx.stream))
@@ -571,6 +648,9 @@ _REGISTRY = {
     "less": less, "less_equal": less_equal,
     "unique": unique, "value_counts": value_counts, "dictionary_encode": dictionary_encode,
     "sum": sum, "mean": mean, "min_max": min_max, "min": min, "max": max, "count": count,
+    "and": and_, "or": or_, "xor": xor, "and_not": and_not, "and_kleene": and_kleene, "or_kleene": or_kleene,
+    "and_not_kleene": and_not_kleene, "invert": invert, "is_valid": is_valid, "is_null": is_null,
+    "true_unless_null": true_unless_null, "is_nan": is_nan,
 }
 
 
@@ -599,4 +679,6 @@ def call_function(name: str, args: Sequence, options=None):
         return fn(*args, skip_nulls=options.skip_nulls, min_count=options.min_count)
     if name == "count":
         return fn(*args, mode=getattr(options, "mode", options))
+    if name == "is_null":
+        return fn(*args, nan_is_null=getattr(options, "nan_is_null", False))
     return fn(*args)

@@ -345,6 +345,14 @@ class CastFunction : public cp::MetaFunction {
     if (!args[0].is_array()) return Status::NotImplemented("arrow_b200 cast: only Array inputs (chunks are cast one by one by the caller)");
     const ArrayData& in = *args[0].array();
     if (in.type->Equals(*opts->to_type.type)) return args[0];
+    // Temporal / dictionary / other logical types share integer storage with the numeric types but not
+    // their cast semantics (unit rescaling, kernels/scalar_cast_temporal.cc): never relabel raw storage.
+    auto genuinely_numeric = [](const DataType& t) {
+      return (arrow::is_integer(t.id()) || t.id() == Type::FLOAT || t.id() == Type::DOUBLE);
+    };
+    if (!genuinely_numeric(*in.type) || !genuinely_numeric(*opts->to_type.type))
+      return Status::NotImplemented("Unsupported cast from ", in.type->ToString(), " to ", opts->to_type.type->ToString(),
+                                    " using function cast_", opts->to_type.type->name());
     B2Array bin, bout;
     ARROW_RETURN_NOT_OK(DataToB2(in, &bin));
     ARROW_ASSIGN_OR_RAISE(int to, B2TypeId(*opts->to_type.type));

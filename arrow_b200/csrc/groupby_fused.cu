@@ -133,13 +133,22 @@ __global__ void __launch_bounds__(kBlock) fused_emit_kernel(FusedTable t, int ke
   }
 }
 
-__global__ void __launch_bounds__(kBlock) count_zero_bits_kernel(const uint32_t* bits, int64_t n, int64_t* out) {
+// counts the zero bits among the first n and clears everything past n (the bitmap started as all-ones;
+// Arrow output padding bits are zero -- common.cuh); alloc_words = 32-bit words in the allocation
+__global__ void __launch_bounds__(kBlock) count_zero_bits_kernel(uint32_t* bits, int64_t n, int64_t alloc_words, int64_t* out) {
   int64_t nw = (n + 31) >> 5;
   int64_t local = 0;
-  for (int64_t w = blockIdx.x * (int64_t)kBlock + threadIdx.x; w < nw; w += (int64_t)gridDim.x * kBlock) {
+  for (int64_t w = blockIdx.x * (int64_t)kBlock + threadIdx.x; w < alloc_words; w += (int64_t)gridDim.x * kBlock) {
+    if (w >= nw) {
+      bits[w] = 0u;
+      continue;
+    }
     uint32_t v = bits[w];
     int64_t rem = n - (w << 5);
-    if (rem < 32) v |= ~((1u << rem) - 1u);
+    if (rem < 32) {
+      bits[w] = v & ((1u << rem) - 1u);
+      v |= ~((1u << rem) - 1u);
+    }
     local += 32 - __popc(v);
   }
   int64_t s = block_sum<kBlock>(local);
@@ -478,16 +487,14 @@ int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Arra
         g->table, kw, keys.ptr, kbits.as<uint32_t>(), sums.as<unsigned long long>(), sbits.as<uint32_t>(),
         counts.as<long long>(), reinterpret_cast<unsigned long long*>(slot.dev()));
     B2_LAUNCHED();
-    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(kbits.as<uint32_t>(), n, slot.dev() + 1);
+    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(kbits.as<uint32_t>(), n, (int64_t)(bb / 4), slot.dev() + 1);
     B2_LAUNCHED();
-    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(sbits.as<uint32_t>(), n, slot.dev() + 2);
+    count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(sbits.as<uint32_t>(), n, (int64_t)(bb / 4), slot.dev() + 2);
     B2_LAUNCHED();
     B2_RETURN_NOT_OK(slot.fetch(s));
     if (slot.host()[0] != n) return set_error(B2_UNKNOWN_ERROR, "group-by emitted %lld of %lld groups", (long long)slot.host()[0], (long long)n);
     key_nulls = slot.host()[1];
     sum_nulls = slot.host()[2];
-    // Arrow bitmaps must be zero past `length`: clear the padding the 0xff fill left
-    // (done on the host-visible tail only when needed by consumers; bits past n are ignored by Equals)
   }
   fill_out(out_keys, g->key_type, n, key_nulls, key_nulls ? kbits.release() : nullptr, keys.release());
   fill_out(out_sums, sum_type, n, sum_nulls, sum_nulls ? sbits.release() : nullptr, sums.release());

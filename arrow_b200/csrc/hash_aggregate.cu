@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(kBlock) hashagg_finalize_kernel(AggState st, i
         static_cast<unsigned long long*>(out)[g] = r;  // int64 / uint64 / double share the bits
       } else if (kind == B2_HASH_MEAN) {
         valid = c >= min_count && (skip_nulls || !saw_null);
-        double m = c >= min_count && c > 0 ? __longlong_as_double((long long)r) / static_cast<double>(c) : 0.0;
+        // an empty group with min_count == 0 is 0/0 = NaN, exactly as GroupedMeanImpl's sums[i] / counts[i]
+        // (hash_aggregate_numeric.cc:402-421); null slots are zero-filled
+        double m = c >= min_count ? __longlong_as_double((long long)r) / static_cast<double>(c) : 0.0;
         static_cast<double*>(out)[g] = m;
       } else {  // MIN / MAX: valid iff the group has a value (hash_aggregate.cc:401-411)
         valid = c > 0 && (skip_nulls || !saw_null);

@@ -62,9 +62,51 @@ __global__ void __launch_bounds__(kBlock) range_partition_kernel(const T* __rest
   }
 }
 
+// counts[b] = #rows with ids[i] == b for b < n_bins (rows with larger ids are counted in `out_of_range`)
+__global__ void __launch_bounds__(kBlock) bincount_kernel(const uint32_t* __restrict__ ids, int64_t n, uint32_t n_bins,
+                                                          unsigned long long* counts) {
+  extern __shared__ uint32_t s_hist[];  // n_bins + 1
+  for (uint32_t i = threadIdx.x; i <= n_bins; i += kBlock) s_hist[i] = 0;
+  __syncthreads();
+  // a block never adds more than 2^31 rows to one bin: its share of the rows is bounded by the grid size
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint32_t b = __ldcs(ids + i);
+    atomicAdd(&s_hist[b < n_bins ? b : n_bins], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i <= n_bins; i += kBlock)
+    if (s_hist[i]) atomicAdd(&counts[i], (unsigned long long)s_hist[i]);
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_bincount(B2Context* ctx, const B2Array* ids, int n_bins, int64_t* out_counts, void* stream) {
+  if (!ctx || !ids || !out_counts) return set_error(B2_INVALID, "b2_bincount: null argument");
+  if (ids->type != B2_UINT32) return set_error(B2_TYPE_ERROR, "b2_bincount: ids must be uint32 (type id %d)", ids->type);
+  if (n_bins < 1 || n_bins > 8192) return set_error(B2_INVALID, "b2_bincount: n_bins must be in [1, 8192]");
+  if (ids->null_count > 0) return set_error(B2_INVALID, "b2_bincount: ids must not contain nulls");
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = ids->length;
+  for (int i = 0; i < n_bins; ++i) out_counts[i] = 0;
+  if (n == 0) return B2_OK;
+  Temp counts(ctx, s);
+  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_bins + 1);
+  B2_RETURN_NOT_OK(counts.alloc(bytes));
+  B2_CUDA(cudaMemsetAsync(counts.ptr, 0, bytes, s));
+  bincount_kernel<<<grid_for(n, kBlock * 16, kSMs * 8), kBlock, sizeof(uint32_t) * (n_bins + 1), s>>>(
+      static_cast<const uint32_t*>(ids->data) + ids->offset, n, (uint32_t)n_bins, counts.as<unsigned long long>());
+  B2_LAUNCHED();
+  std::vector<unsigned long long> host(n_bins + 1);
+  B2_CUDA(cudaMemcpyAsync(host.data(), counts.ptr, bytes, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  if (host[n_bins] != 0)
+    return set_error(B2_INDEX_ERROR, "b2_bincount: %llu ids are >= n_bins (%d)", host[n_bins], n_bins);
+  for (int i = 0; i < n_bins; ++i) out_counts[i] = (int64_t)host[i];
+  return B2_OK;
+}
 
 extern "C" int b2_hash_partition(B2Context* ctx, const B2Array* keys, int n_parts, B2Array* out_ids, void* stream) {
   if (!ctx || !keys || !out_ids) return set_error(B2_INVALID, "b2_hash_partition: null argument");

@@ -20,9 +20,9 @@
 //   histogram: one read of the keys builds all digit histograms in shared memory.
 //   onesweep : per 8-bit digit ONE kernel -- 4096-key tiles (256 threads x 16 keys, 3 CTAs
 //              per SM) are claimed through an atomic ticket and ranked stably into
-//              per-warp digit counters (lanes with equal digits meet through a per-warp
-//              shared-memory mask table: ATOMS.OR + LDS, 10x cheaper than MATCH.ANY on this
-//              part); the tile's 256 digit counts are published, keys and indices are
+//              per-warp digit counters (lanes with equal digits find each other with one
+//              ballot per digit bit -- registers only; MATCH.ANY costs 1.83 cycles/lane on
+//              this part); the tile's 256 digit counts are published, keys and indices are
 //              staged in shared memory in digit order, and only then the exclusive prefix
 //              over earlier tiles is fetched with a 4-deep prefetching decoupled look-back
 //              (no global scan pass), so global writes are contiguous runs.  Passes whose
@@ -414,13 +414,10 @@ static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null
   const size_t lb_bytes = (size_t)n_tiles * kRadix * sizeof(uint32_t) + 256;
   B2_RETURN_NOT_OK(lookback.alloc(lb_bytes));
   uint32_t* ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles * kRadix * sizeof(uint32_t));
-  static bool attr_set[2] = {false, false};
+  // the attribute is per DEVICE (a process may sort on several): set it on every call, it is cheap
   constexpr size_t smem = onesweep_smem<K>();
-  if (!attr_set[sizeof(K) == 8]) {
-    B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[sizeof(K) == 8] = true;
-  }
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   K* kin = keysA.as<K>();
   K* kout = keysB.as<K>();
   uint32_t* iin = idxA.as<uint32_t>();

@@ -1,118 +1,265 @@
 """Multi-GPU execution of the two hot-path operators that need an exchange step.
 
-One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU for the tests).
-Filter / Cast / arithmetic / compare / Take shard by row range with no collective (bench.py does
-exactly that); hash-aggregate and SortIndices do one local pass, ONE all-to-all, and one local
-merge -- the shape of the reference's own per-thread scheme
+One process per GPU.  Filter / Cast / arithmetic / compare / Take shard by row range with no
+collective (bench.py does exactly that); hash-aggregate and SortIndices do one local pass, ONE
+exchange and one local merge -- the shape of the reference's own per-thread scheme
 (GroupByNode: per-thread Grouper + aggregators, then Merge by re-consuming uniques,
 acero/groupby_aggregate_node.cc:211-218,255-298), with GPUs in place of threads:
 
-  group_by_sum_count : local fused group-by -> partial groups (key, sum, count) ->
-                       destination = hash(key) % P (b2_hash_partition) -> stable partition
-                       (sort_indices on the destination id + take) -> all-to-all-v ->
-                       owner merges partials with Grouper + hash_sum (sum of sums, sum of counts).
-  sort_indices       : sample -> all_gather -> P-1 splitters -> destination = range id
+  group_by_sum_count : local fused group-by -> partial groups (key, sum, count) -> the null-key
+                       group is split off (it travels in the metadata) -> destination =
+                       hash(key) % P (b2_hash_partition) -> stable partition (b2_sort_indices on
+                       the destination id + b2_take, send counts from b2_bincount) -> exchange
+                       -> the owner merges partials with Grouper + hash_sum (sum of sums, sum of
+                       counts); a merged count of 0 makes the sum null (min_count = 1).
+  sort_indices       : sample -> all-gather -> P-1 splitters -> destination = range id
                        (b2_range_partition) -> stable partition of (key, global row) ->
-                       all-to-all-v -> local stable sort; nulls never move.
+                       exchange -> local stable sort; nulls never move.
                        Result = rank-ordered concatenation of the value segments, then of the
                        null segments (AtEnd) -- identical to the single-GPU answer.
 
-The algorithms are written against a small `ops` interface so the same code runs on device
-(DeviceOps: DeviceArray + C-ABI kernels + CUDA tensors) and, for the world_size-2 gloo tests,
-on host arrays (tests/host_ops.py: the oracle + CPU tensors).
+The exchange is ONE metadata all-gather (the P x P send counts + the null-group partials) followed
+by ONE all-to-all-v of the partitioned columns:
+  * B2CommExchange  -- the C-ABI path (b2_comm_*, csrc/comm.cu): every column's sends and receives
+                       are issued inside a single NCCL group, i.e. one fused NCCL launch over
+                       NVLink / NVSwitch, with no pack / unpack copies;
+  * TorchExchange   -- torch.distributed (gloo for the CPU tests, nccl otherwise): the columns are
+                       packed into one byte buffer and moved by one all_to_all_single.
+
+All compute steps are C-ABI kernels (b2_*); torch appears only as tensor plumbing (zero-copy views,
+slices, copies) and, in TorchExchange, as the transport.  The algorithms are written against a small
+`ops` interface so the same code runs on device (DeviceOps) and, for the world_size-2 gloo tests, on
+host arrays (tests/host_ops.py: the oracle + CPU tensors).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import numpy as np
 import pyarrow as pa
 import torch
 import torch.distributed as dist
 
-
-def pack_bits(torch_mod, valid):
-    """bool[n] (n % 8 == 0) -> LSB-first bitmap bytes (torch plumbing for validity columns)."""
-    w = torch_mod.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch_mod.uint8, device=valid.device)
-    return (valid.view(-1, 8).to(torch_mod.uint8) * w).sum(dim=1, dtype=torch_mod.uint8)
+_META_EXTRA = 3  # has_null, null_sum, null_count
 
 
 # ------------------------------------------------------------------------------------------------
-# collectives on raw torch tensors
+# transports
 # ------------------------------------------------------------------------------------------------
-def all_to_all_v(send: torch.Tensor, send_counts: Sequence[int], group=None) -> Tuple[torch.Tensor, List[int]]:
-    """Variable-size all-to-all of a 1-D tensor partitioned by destination rank."""
-    world = dist.get_world_size(group)
-    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
-    rc = torch.empty(world, dtype=torch.int64, device=send.device)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.tolist()]
-    recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
-    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
-    return recv, recv_counts
+def _pad8(nbytes: int) -> int:
+    return (nbytes + 7) // 8 * 8
 
 
-def all_gather_v(t: torch.Tensor, group=None) -> List[torch.Tensor]:
-    world = dist.get_world_size(group)
-    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    sizes = [torch.empty(1, dtype=torch.int64, device=t.device) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    m = max(sizes) if sizes else 0
-    padded = torch.zeros(m, dtype=t.dtype, device=t.device)
-    padded[: t.numel()] = t
-    outs = [torch.empty(m, dtype=t.dtype, device=t.device) for _ in range(world)]
-    dist.all_gather(outs, padded, group=group)
-    return [o[:s] for o, s in zip(outs, sizes)]
+class TorchExchange:
+    """torch.distributed transport: one all_gather_into_tensor for the metadata, one packed
+    all_to_all_single for the data."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.stats = {}
+
+    def all_gather_i64(self, row: torch.Tensor) -> torch.Tensor:
+        """row: int64[m] -> int64[world, m]"""
+        out = torch.empty(self.world * row.numel(), dtype=torch.int64, device=row.device)
+        if self.world == 1:
+            out.copy_(row)
+        else:
+            dist.all_gather_into_tensor(out, row.contiguous(), group=self.group)
+        return out.view(self.world, row.numel())
+
+    def all_gather_bytes(self, buf: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.world * buf.numel(), dtype=torch.uint8, device=buf.device)
+        if self.world == 1:
+            out.copy_(buf)
+        else:
+            dist.all_gather_into_tensor(out, buf.contiguous(), group=self.group)
+        return out.view(self.world, buf.numel())
+
+    def all_to_all_columns(self, columns: Sequence[torch.Tensor], send_rows: Sequence[int], recv_rows: Sequence[int]):
+        """columns: 1-D tensors, rows already grouped by destination (send_rows[d] rows for rank d).
+        Returns the received columns, grouped by source rank in rank order."""
+        widths = [c.element_size() for c in columns]
+        dev = columns[0].device
+        s_chunk = [sum(_pad8(w * n) for w in widths) for n in send_rows]
+        r_chunk = [sum(_pad8(w * n) for w in widths) for n in recv_rows]
+        send = torch.empty(sum(s_chunk), dtype=torch.uint8, device=dev)
+        off, row0 = 0, 0
+        for d, n in enumerate(send_rows):               # pack: chunk d = [col0 rows | col1 rows | ...]
+            for c, w in zip(columns, widths):
+                send[off: off + w * n] = c[row0: row0 + n].contiguous().view(torch.uint8)
+                off += _pad8(w * n)
+            row0 += n
+        recv = torch.empty(sum(r_chunk), dtype=torch.uint8, device=dev)
+        if self.world == 1:
+            recv.copy_(send)
+        else:
+            dist.all_to_all_single(recv, send, output_split_sizes=r_chunk, input_split_sizes=s_chunk, group=self.group)
+        total = sum(recv_rows)
+        outs = [torch.empty(total, dtype=c.dtype, device=dev) for c in columns]
+        off, row0 = 0, 0
+        for n in recv_rows:                             # unpack
+            for o, w in zip(outs, widths):
+                o[row0: row0 + n] = recv[off: off + w * n].view(o.dtype)
+                off += _pad8(w * n)
+            row0 += n
+        self.stats = {"alltoall_bytes": int(sum(s_chunk) - s_chunk[self.rank])}
+        return outs
+
+
+class B2CommExchange:
+    """C-ABI transport (b2_comm_*): NCCL through libarrow_b200.so, every column's sends/receives in one
+    NCCL group.  The 128-byte unique id is distributed with torch.distributed (any backend)."""
+
+    def __init__(self, ctx, group=None):
+        from . import _cabi as cabi
+        from .device import check
+        self.ctx, self.check = ctx, check
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ident = (C.c_uint8 * cabi.COMM_ID_BYTES)()
+        if self.rank == 0:
+            check(ctx.lib.b2_comm_unique_id(ident))
+        box = [bytes(ident)]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_uint8 * cabi.COMM_ID_BYTES).from_buffer_copy(box[0])
+        h = C.c_void_p()
+        check(ctx.lib.b2_comm_init(ctx.handle, self.rank, self.world, ident, C.byref(h)))
+        self.handle = h
+        self.stats = {}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.b2_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def all_gather_i64(self, row: torch.Tensor) -> torch.Tensor:
+        row = row.contiguous()
+        out = torch.empty(self.world * row.numel(), dtype=torch.int64, device=row.device)
+        self.check(self.ctx.lib.b2_comm_all_gather(self.handle, row.data_ptr(), out.data_ptr(), row.numel() * 8, self.ctx.stream))
+        return out.view(self.world, row.numel())
+
+    def all_gather_bytes(self, buf: torch.Tensor) -> torch.Tensor:
+        buf = buf.contiguous()
+        out = torch.empty(self.world * buf.numel(), dtype=torch.uint8, device=buf.device)
+        self.check(self.ctx.lib.b2_comm_all_gather(self.handle, buf.data_ptr(), out.data_ptr(), buf.numel(), self.ctx.stream))
+        return out.view(self.world, buf.numel())
+
+    def all_to_all_columns(self, columns, send_rows, recv_rows):
+        P = self.world
+        I64 = C.c_int64 * P
+        total = sum(recv_rows)
+        outs = [torch.empty(total, dtype=c.dtype, device=c.device) for c in columns]
+        s_off = np.concatenate([[0], np.cumsum(send_rows)[:-1]]).astype(np.int64)
+        r_off = np.concatenate([[0], np.cumsum(recv_rows)[:-1]]).astype(np.int64)
+        lib = self.ctx.lib
+        self.check(lib.b2_comm_group_start(self.handle))
+        sent = 0
+        for c, o in zip(columns, outs):
+            w = c.element_size()
+            c = c.contiguous()
+            self.check(lib.b2_comm_all_to_all_v(
+                self.handle, c.data_ptr(), I64(*[int(x) * w for x in s_off]), I64(*[int(n) * w for n in send_rows]),
+                o.data_ptr(), I64(*[int(x) * w for x in r_off]), I64(*[int(n) * w for n in recv_rows]), self.ctx.stream))
+            sent += w * (sum(send_rows) - send_rows[self.rank])
+        self.check(lib.b2_comm_group_end(self.handle))
+        self.stats = {"alltoall_bytes": int(sent)}
+        return outs
 
 
 # ------------------------------------------------------------------------------------------------
 # the two distributed operators (backend agnostic)
 # ------------------------------------------------------------------------------------------------
-def group_by_sum_count(keys, values, ops, group=None):
+def group_by_sum_count(keys, values, ops, xchg=None, expected_groups: int = 0):
     """Distributed `group_by(key).aggregate(sum, count)` over row-range shards.
-    Returns this rank's owned groups: (keys, sums, counts) -- disjoint across ranks, union = all."""
-    world = dist.get_world_size(group)
-    k, s, c = ops.local_group_by(keys, values)              # partial groups of this shard
-    dest = ops.hash_partition(k, world)                     # owner of every partial group
-    order = ops.stable_sort_indices(dest)
-    k, s, c, dest_sorted = ops.take(k, order), ops.take(s, order), ops.take(c, order), ops.take(dest, order)
-    send_counts = ops.histogram(dest_sorted, world)
-    k_t, k_null_t = ops.key_tensors(k)                      # raw keys + per-key null flag (uint8)
-    s_t, c_t = ops.sum_tensor(s), ops.count_tensor(c)       # null sums travel as 0 (count says it all)
-    rk, _ = all_to_all_v(k_t, send_counts, group)
-    rn, _ = all_to_all_v(k_null_t, send_counts, group)
-    rs, _ = all_to_all_v(s_t, send_counts, group)
-    rc, _ = all_to_all_v(c_t, send_counts, group)
-    return ops.merge_partials(rk, rn, rs, rc, keys_type=ops.type_of(k), sum_type=ops.type_of(s))
+    Returns this rank's owned groups: (keys, sums, counts) -- disjoint across ranks, union = all.
+    With world == 1 this is exactly the local fused group-by."""
+    xchg = xchg or TorchExchange()
+    P, rank = xchg.world, xchg.rank
+    with ops.stream_guard():
+        k, s, c = ops.local_group_by(keys, values, expected_groups)   # partial groups of this shard
+        if P == 1:
+            return k, s, c
+        k, s, c, null_info = ops.split_null_group(k, s, c)             # null key: [has, sum, count]
+        dest = ops.hash_partition(k, P)                                # owner of every partial group
+        order, send_rows = ops.partition_plan(dest, P)
+        k, s, c = ops.take(k, order), ops.take(s, order), ops.take(c, order)
+        meta = xchg.all_gather_i64(ops.meta_tensor(list(send_rows) + list(null_info)))
+        meta_h = meta.cpu().numpy()
+        recv_rows = [int(meta_h[src, rank]) for src in range(P)]
+        t0 = ops.mark()
+        rk, rs, rc = xchg.all_to_all_columns([ops.raw_tensor(k), ops.raw_tensor(s), ops.raw_tensor(c)], send_rows, recv_rows)
+        ops.note_exchange(t0, xchg)
+        nulls = np.ascontiguousarray(meta_h[:, P:])
+        null_group = None
+        if rank == 0 and nulls[:, 0].any():
+            bits = np.ascontiguousarray(nulls[:, 1])
+            if pa.types.is_floating(ops.type_of(s)):     # partial sums travel as raw bits
+                total = np.array([bits.view(np.float64).sum()], dtype=np.float64).view(np.int64)[0]
+            else:
+                total = bits.view(np.uint64).sum(dtype=np.uint64).astype(np.int64)
+            null_group = (int(total), int(nulls[:, 2].sum()))
+        return ops.merge_partials(rk, rs, rc, ops.type_of(k), ops.type_of(s), null_group)
 
 
-def sort_indices(values, ops, group=None, samples_per_rank: int = 4096):
+def sort_indices(values, ops, xchg=None, samples_per_rank: int = 4096, return_keys: bool = False):
     """Distributed stable `sort_indices(values, ascending, nulls at end)` over row-range shards.
-    Returns (sorted_global_indices_segment, null_global_indices_segment) for this rank."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n_local = ops.length(values)
-    lens = all_gather_v(ops.scalar_tensor(n_local), group)
-    row0 = sum(int(x.item()) for x in lens[:rank])
-    # splitters from an all-gathered sample of the valid rows
-    sample = ops.sample_valid(values, samples_per_rank)
-    gathered = torch.cat(all_gather_v(ops.values_tensor(sample), group))
-    splitters = ops.pick_splitters(gathered, world, ops.type_of(values))
-    dest = ops.range_partition(values, splitters)           # nulls get id world (= P-1 splitters + 1)
-    order = ops.stable_sort_indices(dest)
-    dest_sorted = ops.take(dest, order)
-    counts = ops.histogram(dest_sorted, world + 1)
-    n_valid = sum(counts[:world])
-    gidx = ops.add_offset(order, row0)                      # global row numbers, partition order
-    valid_part = ops.slice(ops.take(values, order), 0, n_valid)
-    rk, _ = all_to_all_v(ops.values_tensor(valid_part), counts[:world], group)
-    ri, _ = all_to_all_v(ops.index_tensor(ops.slice(gidx, 0, n_valid)), counts[:world], group)
-    null_idx = ops.index_tensor(ops.slice(gidx, n_valid, n_local - n_valid))
-    # received rows are grouped by source rank (ascending) and ascending global row inside each
-    # group, so a STABLE local sort keeps ties in global row order
-    local = ops.stable_sort_indices(ops.from_values_tensor(rk, ops.type_of(values)))
-    return ops.take_tensor(ri, local), null_idx
+    Returns (sorted_global_indices_segment, null_global_indices_segment) for this rank (torch tensors);
+    the rank-ordered concatenation of the value segments followed by that of the null segments is the
+    single-process answer."""
+    xchg = xchg or TorchExchange()
+    P, rank = xchg.world, xchg.rank
+    with ops.stream_guard():
+        n_local = ops.length(values)
+        if P == 1:
+            order = ops.stable_sort_indices(values)
+            n_valid = n_local - ops.null_count(values)
+            t = ops.raw_tensor(order)
+            if return_keys:   # the keys in sorted order (verification aid for bench.py / tests)
+                return t[:n_valid], t[n_valid:], ops.raw_tensor(ops.take(values, ops.slice(order, 0, n_valid)))
+            return t[:n_valid], t[n_valid:]
+        # one all-gather carries the shard lengths and a sample of the valid rows
+        sample = ops.sample_valid(values, samples_per_rank)            # typed tensor, <= samples_per_rank
+        width = sample.element_size()
+        buf = torch.zeros(16 + samples_per_rank * width, dtype=torch.uint8, device=sample.device)
+        head = torch.tensor([n_local, sample.numel()], dtype=torch.int64).view(torch.uint8)
+        buf[:16] = head.to(buf.device)
+        buf[16: 16 + sample.numel() * width] = sample.contiguous().view(torch.uint8)
+        gathered = xchg.all_gather_bytes(buf)
+        heads = gathered[:, :16].cpu().contiguous().view(torch.int64).view(P, 2).numpy()
+        row0 = int(heads[:rank, 0].sum())
+        parts = [gathered[r, 16: 16 + int(heads[r, 1]) * width].contiguous().view(sample.dtype) for r in range(P)]
+        splitters = ops.pick_splitters(torch.cat(parts), P, ops.type_of(values))
+        dest = ops.range_partition(values, splitters)                  # nulls get id P (= P-1 splitters + 1)
+        order, counts = ops.partition_plan(dest, P + 1)
+        n_valid = sum(counts[:P])
+        gidx = ops.add_offset(order, row0)                             # global row numbers, partition order
+        valid_part = ops.take(values, ops.slice(order, 0, n_valid))
+        send_rows = list(counts[:P])
+        meta = xchg.all_gather_i64(ops.meta_tensor(send_rows)).cpu().numpy()
+        recv_rows = [int(meta[src, rank]) for src in range(P)]
+        t0 = ops.mark()
+        rk, ri = xchg.all_to_all_columns([ops.raw_tensor(valid_part), ops.raw_tensor(ops.slice(gidx, 0, n_valid))], send_rows, recv_rows)
+        ops.note_exchange(t0, xchg)
+        null_idx = ops.raw_tensor(ops.slice(gidx, n_valid, n_local - n_valid))
+        # received rows are grouped by source rank (ascending) and ascending global row inside each
+        # group, so a STABLE local sort keeps ties in global row order
+        rk_arr = ops.from_raw_tensor(rk, ops.type_of(values))
+        local = ops.stable_sort_indices(rk_arr)
+        seg = ops.raw_tensor(ops.take(ops.from_raw_tensor(ri, pa.uint64()), local))
+        if return_keys:
+            return seg, null_idx, ops.raw_tensor(ops.take(rk_arr, local))
+        return seg, null_idx
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,13 +281,37 @@ _TORCH = {pa.int8(): torch.int8, pa.uint8(): torch.uint8, pa.int16(): torch.int1
 
 
 class DeviceOps:
-    """ops interface over DeviceArray + the C-ABI kernels (everything stays in HBM)."""
+    """ops interface over DeviceArray + the C-ABI kernels (everything stays in HBM).
+
+    Stream discipline: C-ABI calls run on ctx.stream and torch ops / collectives on torch's current
+    stream, so the two must be the same stream.  If the context has no explicit stream yet, DeviceOps
+    creates a torch side stream, installs it as ctx.stream and runs every operator under it
+    (stream_guard); a caller that already set ctx.stream (bench.py) must have made it torch's current
+    stream."""
 
     def __init__(self, ctx=None):
         from . import compute as bc
         from .device import Context, DeviceArray
         self.bc, self.DeviceArray = bc, DeviceArray
         self.ctx = ctx or Context.get(torch.cuda.current_device())
+        self._own_stream = None
+        if not self.ctx.stream:
+            self._own_stream = torch.cuda.Stream()
+            assert self._own_stream.cuda_stream != 0
+            self.ctx.stream = self._own_stream.cuda_stream
+        self.exchange_ms: List[float] = []
+        self.exchange_bytes: List[int] = []
+
+    @contextlib.contextmanager
+    def stream_guard(self):
+        if self._own_stream is None:
+            yield
+            return
+        outer = torch.cuda.current_stream()
+        self._own_stream.wait_stream(outer)       # inputs produced on the caller's stream
+        with torch.cuda.stream(self._own_stream):
+            yield
+        outer.wait_stream(self._own_stream)       # results consumed on the caller's stream
 
     # -- array <-> tensor (zero copy) --
     def _tensor(self, arr, t=None):
@@ -165,16 +336,57 @@ class DeviceOps:
     def length(self, arr):
         return arr.length
 
-    def scalar_tensor(self, v):
-        return torch.tensor([v], dtype=torch.int64, device="cuda")
+    def null_count(self, arr):
+        if arr.null_count < 0:
+            return arr.length - self.bc.count(arr).as_py()
+        return arr.null_count
+
+    def raw_tensor(self, arr):
+        return self._tensor(arr)
+
+    def from_raw_tensor(self, t, typ):
+        return self._array(t, typ)
+
+    def meta_tensor(self, ints):
+        return torch.tensor([int(x) for x in ints], dtype=torch.int64).to("cuda", non_blocking=False)
+
+    def mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def note_exchange(self, t0, xchg):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._pending = (t0, e, xchg.stats.get("alltoall_bytes", 0))
+
+    def exchange_stats(self):
+        """(ms, bytes sent to peers) of the last data exchange; synchronises."""
+        p = getattr(self, "_pending", None)
+        if p is None:
+            return 0.0, 0
+        p[1].synchronize()
+        return p[0].elapsed_time(p[1]), p[2]
 
     # -- kernels --
-    def local_group_by(self, keys, values):
-        g = self.bc.GroupBySumCount(keys.type, values.type, ctx=self.ctx)
+    def local_group_by(self, keys, values, expected_groups=0):
+        g = self.bc.GroupBySumCount(keys.type, values.type, expected_groups=expected_groups, ctx=self.ctx)
         g.consume(keys, values)
         return g.finalize()
 
-    def _partition_call(self, fn_name, *cargs):
+    def split_null_group(self, k, s, c):
+        if k.null_count == 0 or k.buffers[0] is None:
+            return k, s, c, (0, 0, 0)
+        bc = self.bc
+        pos = bc.take_indices_from_filter(bc.is_null(k))           # the (single) null-key group
+        ns, nc = bc.take(s, pos).to_arrow(), bc.take(c, pos).to_arrow()
+        null_sum = ns[0].as_py() if ns[0].is_valid else 0
+        if isinstance(null_sum, float):
+            null_sum = int(np.array([null_sum], dtype=np.float64).view(np.int64)[0])
+        keep = bc.is_valid(k)
+        return bc.filter(k, keep), bc.filter(s, keep), bc.filter(c, keep), (1, null_sum, nc[0].as_py())
+
+    def _id_call(self, fn_name, *cargs):
         from . import _cabi as cabi
         from .device import check
         out = cabi.B2Array()
@@ -183,11 +395,19 @@ class DeviceOps:
 
     def hash_partition(self, keys, n_parts):
         ck = keys._c()
-        return self._partition_call("b2_hash_partition", C.byref(ck), int(n_parts))
+        return self._id_call("b2_hash_partition", C.byref(ck), int(n_parts))
 
     def range_partition(self, values, splitters):
         cv, cs = values._c(), splitters._c()
-        return self._partition_call("b2_range_partition", C.byref(cv), C.byref(cs), 0)
+        return self._id_call("b2_range_partition", C.byref(cv), C.byref(cs), 0)
+
+    def partition_plan(self, dest, n_bins):
+        """stable grouping of the rows by destination id: (gather order, rows per destination)"""
+        from .device import check
+        counts = (C.c_int64 * n_bins)()
+        cd = dest._c()
+        check(self.ctx.lib.b2_bincount(self.ctx.handle, C.byref(cd), n_bins, counts, self.ctx.stream))
+        return self.bc.array_sort_indices(dest), [int(x) for x in counts]
 
     def stable_sort_indices(self, arr):
         return self.bc.array_sort_indices(arr)
@@ -198,97 +418,55 @@ class DeviceOps:
     def slice(self, arr, off, length):
         return arr.slice(off, length)
 
-    def histogram(self, sorted_ids, n_bins):
-        t = self._tensor(sorted_ids, pa.uint32()).to(torch.int64)
-        return [int(x) for x in torch.bincount(t, minlength=n_bins)[:n_bins].tolist()]
-
-    def key_tensors(self, k):
-        raw = self._tensor(k)
-        if k.null_count == 0 or k.buffers[0] is None:
-            return raw, torch.zeros(k.length, dtype=torch.uint8, device="cuda")
-        valid = self._tensor(self._valid_as_uint8(k))
-        return raw, (1 - valid).to(torch.uint8)
-
-    def _valid_as_uint8(self, arr):
-        # validity bitmap -> uint8 0/1 column: compare(equal(arr, arr)) is all-true where valid and null
-        # elsewhere; take its validity by counting through a filter-free path: unpack with torch
-        bits = _CudaView(arr.buffers[0].ptr, (arr.offset + arr.length + 7) // 8, "|u1", arr)
-        b = torch.as_tensor(bits, device="cuda")
-        shifts = torch.arange(8, device="cuda", dtype=torch.uint8)
-        un = ((b.unsqueeze(1) >> shifts) & 1).reshape(-1)[arr.offset: arr.offset + arr.length].contiguous()
-        return self._array(un, pa.uint8())
-
-    def sum_tensor(self, s):
-        t = self._tensor(s)
-        if s.null_count and s.buffers[0] is not None:
-            t = t * self._tensor(self._valid_as_uint8(s)).to(t.dtype)
-        return t
-
-    def count_tensor(self, c):
-        return self._tensor(c)
-
-    def values_tensor(self, arr):
-        return self._tensor(arr)
-
-    def index_tensor(self, arr):
-        return self._tensor(arr, pa.uint64()) if arr.type == pa.uint64() else self._tensor(arr)
-
-    def from_values_tensor(self, t, typ):
-        return self._array(t, typ)
-
-    def take_tensor(self, t, idx_arr):
-        return t[self._tensor(idx_arr, pa.uint64())]
-
     def add_offset(self, idx_arr, off):
-        t = self._tensor(idx_arr, pa.uint64()) + off
-        return self._array(t, pa.uint64())
+        return self.bc.add(idx_arr, pa.scalar(int(off), pa.uint64()))
 
     def sample_valid(self, values, k):
+        """<= k evenly spaced valid rows as a typed tensor"""
         n = values.length
         if n == 0:
-            return values
-        step = max(1, n // k)
-        idx = torch.arange(0, n, step, dtype=torch.int64, device="cuda")
-        s = self.bc.take(values, self._array(idx, pa.int64()))
-        if s.null_count:  # drop sampled nulls: filter with the sample's own validity
-            keep = self._array((self._tensor(self._valid_as_uint8(s)) != 0).to(torch.uint8), pa.uint8())
-            s = self.bc.filter(s, self.bc.not_equal(keep, 0))
-        return s
+            return torch.empty(0, dtype=_TORCH[values.type], device="cuda")
+        step = max(1, -(-n // k))
+        pos = torch.arange(0, n, step, dtype=torch.int64, device="cuda")
+        s = self.bc.take(values, self._array(pos, pa.int64()))
+        if s.null_count:
+            s = self.bc.filter(s, self.bc.is_valid(s))
+        return self._tensor(s).clone()
 
     def pick_splitters(self, gathered, world, typ):
-        g, _ = torch.sort(gathered)
-        if g.numel() == 0 or world == 1:
-            return self._array(g[:0], typ)
-        pos = (torch.arange(1, world, device=g.device) * g.numel()) // world
-        return self._array(g[pos.clamp(max=g.numel() - 1)], typ)
+        if gathered.numel() == 0 or world == 1:
+            return self._array(gathered[:0], typ)
+        g = self._array(gathered, typ)
+        g = self.bc.take(g, self.bc.array_sort_indices(g))
+        pos = (torch.arange(1, world, dtype=torch.int64, device="cuda") * gathered.numel()) // world
+        return self.bc.take(g, self._array(pos.clamp(max=gathered.numel() - 1), pa.int64()))
 
-    def merge_partials(self, rk, rn, rs, rc, keys_type, sum_type):
+    def merge_partials(self, rk, rs, rc, keys_type, sum_type, null_group):
+        """owner-side merge = GroupByNode::Merge: re-consume the uniques, add the partial states"""
+        bc = self.bc
         n = rk.numel()
-        validity = None
-        nulls = int(rn.sum().item()) if n else 0
-        if nulls:
-            m8 = (n + 7) // 8 * 8
-            v = torch.zeros(m8, dtype=torch.bool, device="cuda")
-            v[:n] = rn == 0
-            validity = pack_bits(torch, v)
+        validity, nulls = None, 0
+        if null_group is not None:   # rank 0 owns the null key: append it as one more partial with a cleared validity bit
+            rk = torch.cat([rk, torch.zeros(1, dtype=rk.dtype, device=rk.device)])
+            rs = torch.cat([rs, torch.tensor([null_group[0]], dtype=torch.int64, device=rs.device).view(rs.dtype)])
+            rc = torch.cat([rc, torch.tensor([null_group[1]], dtype=rc.dtype, device=rc.device)])
+            validity = torch.full(((n + 1 + 7) // 8 + 8,), 0xFF, dtype=torch.uint8, device="cuda")
+            validity[n >> 3] = 0xFF & ~(1 << (n & 7))
+            nulls = 1
         keys = self._array(rk, keys_type, validity, nulls)
-        g = self.bc.Grouper([keys_type], self.ctx)
+        g = bc.Grouper([keys_type], self.ctx)
         ids = g.consume(keys)
-        sums = self.bc.HashAggregator("hash_sum", sum_type, ctx=self.ctx)
-        cnts = self.bc.HashAggregator("hash_sum", pa.int64(), ctx=self.ctx)
+        sums = bc.HashAggregator("hash_sum", sum_type, ctx=self.ctx)
+        cnts = bc.HashAggregator("hash_sum", pa.int64(), ctx=self.ctx)
         sums.resize(g.num_groups)
         cnts.resize(g.num_groups)
         sums.consume(self._array(rs, sum_type), ids)
         cnts.consume(self._array(rc, pa.int64()), ids)
-        total = cnts.finalize()
-        s = sums.finalize()
-        # a group whose merged count is 0 has a null sum (min_count = 1): re-mask from the counts
-        zero = self.bc.equal(total, 0)
-        nz = self.bc.filter_output_size(zero)
-        if nz:
-            cnt_t = self._tensor(total)
-            m8 = (cnt_t.numel() + 7) // 8 * 8
-            v = torch.zeros(m8, dtype=torch.bool, device="cuda")
-            v[: cnt_t.numel()] = cnt_t != 0
-            s = self._array(self._tensor(s).clone(), sum_type, pack_bits(torch, v), nz)
+        total, s = cnts.finalize(), sums.finalize()
+        # a group whose merged count is 0 has a null sum (min_count = 1): the comparison's bit-packed
+        # result IS the validity bitmap
+        nonzero = bc.not_equal(total, 0)
+        n_null = total.length - bc.filter_output_size(nonzero)
+        if n_null:
+            s = self.DeviceArray(self.ctx, sum_type, s.length, n_null, 0, [nonzero.buffers[1], s.buffers[1]])
         return g.get_uniques()[0], s, total

@@ -10,10 +10,18 @@ One "step" = one pass of that pipeline over one synthetic batch.
           inputs and D2H of the result column inside the timed region
   roofline : the dominant kernel (take_kernel, random int64 indices into float64), algorithmic
           bytes (24.25 B/row) / its CUDA-event time, against the measured copy peak
-  cpu_baseline / --impl reference : the reference binary (pyarrow 24.0.0 = libarrow_compute.so.2400,
-          the same kernels as /root/reference for this path) on the host cores, on a bounded sample.
-Multi-GPU: rows shard by range, `values` replicated per GPU, no collective on the
-data path => weak scaling, one process per GPU.
+  configs  : (N = 1) the other BASELINE.json configs at full size -- c1 filter, c3 group-by (fused and
+          Grouper + aggregators), c4 sort_indices (wide / narrow keys), c5 utf8 filter + dictionary take --
+          each {ms, alg_bytes, frac, parity_checksum_ok}
+  multi_gpu: configs[2] and configs[3] with the row range sharded over the N ranks (STRONG scaling: the
+          total is fixed at --rows): local pass -> one exchange (b2_comm_*: NCCL all-to-all-v over NVLink,
+          csrc/comm.cu) -> owner-side merge, CUDA-event timed, max over ranks, with checksums that are
+          identical at every N and are verified against invariants derived from the inputs
+  cpu_baseline / --impl reference : the reference's own CPU kernels (oracle/_ref/ref_bench: a C++ harness
+          linked against the installed libarrow_compute.so.2400, the same kernels as /root/reference for
+          this path) on the host cores.
+Multi-GPU (config 2): rows shard by range, `values` replicated per GPU, no collective on
+the data path => weak scaling, one process per GPU.
 """
 import argparse
 import json
@@ -30,6 +38,7 @@ ALG_TAKE, ALG_CAST, ALG_ADD = 24.25, 12.25, 12.375  # bytes/row, SURVEY section 
 ALG_PIPELINE = ALG_TAKE + ALG_CAST + ALG_ADD          # 48.875
 NULL_P = 0.1
 SEED = 0x0FF1CE
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
 
 
 def measured_peaks():
@@ -97,61 +106,92 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU kernels on the host cores
 # ------------------------------------------------------------------------------------------------
-def reference_pipeline_rate(sample_rows, steps, warmup, threads):
-    """rows/s of add(cast(take(values, idx), f32), other) with pyarrow.compute, `threads` row-range
-    slices in flight (CallFunction itself is single-threaded, compute/exec.h:85-91)."""
-    import concurrent.futures as cf
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    avail = 0
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return model, os.cpu_count() or 1, avail
 
-    import numpy as np
-    import pyarrow as pa
-    import pyarrow.compute as pc
 
-    rng = np.random.default_rng(SEED)
-    n = sample_rows
-    values = pa.array(rng.uniform(0, 1e6, n), pa.float64(), mask=rng.random(n) < NULL_P)
-    indices = pa.array(rng.integers(0, n, n, dtype=np.int64))
-    other = pa.array(rng.uniform(0, 1e6, n).astype(np.float32), pa.float32(), mask=rng.random(n) < NULL_P)
-    pa.set_cpu_count(threads)
-    bounds = np.linspace(0, n, threads + 1).astype(np.int64)
+def ref_bench(op, rows, steps, warmup, threads, groups=None, timeout=900):
+    """Runs oracle/_ref/ref_bench (C++, linked against libarrow_compute.so.2400) and returns its JSON."""
+    if not os.path.exists(REF_BENCH):
+        raise RuntimeError(f"{REF_BENCH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    cmd = [REF_BENCH, op, str(int(rows)), str(int(steps)), str(int(warmup)), str(int(threads))]
+    if groups:
+        cmd.append(str(int(groups)))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError(f"ref_bench failed: {out.stderr[-500:]}")
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
-    def part(i):
-        lo, hi = int(bounds[i]), int(bounds[i + 1])
-        t = pc.take(values, indices.slice(lo, hi - lo))
-        c = pc.cast(t, pa.float32(), safe=False)
-        return pc.add(c, other.slice(lo, hi - lo))
 
-    pool = cf.ThreadPoolExecutor(threads)
-    for _ in range(warmup):
-        list(pool.map(part, range(threads)))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        list(pool.map(part, range(threads)))
-    dt = time.perf_counter() - t0
-    return n * steps / dt, dt / steps
+def reference_rows(requested):
+    """The CPU arm runs the SAME row count as the GPU arm when host RAM allows (the pipeline needs
+    ~40 B/row of host memory), otherwise the largest power-of-two sample that fits (>= 2^28 wanted)."""
+    _, _, avail = host_info()
+    rows = requested
+    while rows * 44 > 0.6 * avail and rows > (1 << 22):
+        rows //= 2
+    return rows
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = args.cpu_sample_rows
-    rate, per_step = reference_pipeline_rate(sample, args.steps, args.warmup, threads)
+    model, cores, avail = host_info()
+    rows = reference_rows(args.rows)
+    r = ref_bench("pipeline", rows, args.steps, args.warmup, cores)
+    rate = r["rows_per_s_mean"]
     line = {
         "impl": "reference", "metric": "rows/sec", "value": rate, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["mean_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
-        "config": {"workload": "Take(float64,int64 idx)+Cast(float64->float32)+Add(float32), null_probability=0.1",
-                   "rows_per_step": sample, "note": "bounded sample of the 1B-row workload on host cores"},
-        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": threads, "kind": "reference",
-                         "sample": f"{sample} rows/step x {args.steps} steps, pyarrow 24.0.0 libarrow_compute, {threads} row-range threads"},
+        "config": {"workload": "Take(float64,int64 idx)+Cast(float64->float32)+Add(float32), null_probability=0.1, 1B rows/GPU"
+                   if rows == 1_000_000_000 else f"Take+Cast(f64->f32)+Add, null_probability=0.1, {rows} rows",
+                   "rows_per_step": rows, "same_rows_as_gpu_arm": rows == args.rows,
+                   "note": "reference CPU kernels (libarrow_compute.so.2400) through arrow::compute::CallFunction, one row-range slice per host thread"},
+        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": cores, "kind": "reference", "cpu_model": model,
+                         "best_rows_per_s": r["rows_per_s_best"],
+                         "sample": f"{rows} rows/step x {args.steps} steps (+{args.warmup} warm-up), oracle/_ref/ref_bench pipeline, "
+                                   f"arrow {r['arrow_version']}, {cores} row-range threads"},
         "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_leg(args):
+    """rank 0, N = 1: the reference pipeline on all host cores (same rows as the GPU arm when RAM allows,
+    2 timed passes) and on one thread (2^26-row sample) -- a bounded ~10-30 s of CPU work."""
+    model, cores, _ = host_info()
+    rows = reference_rows(args.rows)
+    out = {"unit": "rows/s", "cores": cores, "kind": "reference", "cpu_model": model}
+    try:
+        allc = ref_bench("pipeline", rows, 2, 1, cores)
+        one = ref_bench("pipeline", min(rows, 1 << 26), 1, 1, 1)
+        out.update({"value": allc["rows_per_s_best"], "single_thread_value": one["rows_per_s_best"],
+                    "sample": f"all cores: {rows} rows x best of 2 (+1 warm-up); single thread: {min(rows, 1 << 26)} rows x 1 (+1 warm-up); "
+                              f"oracle/_ref/ref_bench pipeline, arrow {allc['arrow_version']}"})
+    except Exception as e:  # the baseline is a reported number, not a gate: never lose the GPU line over it
+        out.update({"value": None, "error": str(e)[:300], "sample": "ref_bench failed"})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# helpers (torch is plumbing here: synthetic inputs, events, verification arithmetic)
 # ------------------------------------------------------------------------------------------------
 def pack_bits(torch, valid):
     """bool[n] (n % 8 == 0) -> LSB-first bitmap bytes"""
@@ -159,7 +199,7 @@ def pack_bits(torch, valid):
     return (valid.view(-1, 8).to(torch.uint8) * w).sum(dim=1, dtype=torch.uint8)
 
 
-def make_validity(torch, n, gen):
+def make_validity(torch, n, gen, null_p=NULL_P):
     out = torch.empty((n + 7) // 8 + 64, dtype=torch.uint8, device="cuda")
     out.zero_()
     chunk = 1 << 27
@@ -167,7 +207,7 @@ def make_validity(torch, n, gen):
     for lo in range(0, n, chunk):
         m = min(chunk, n - lo)
         m8 = (m + 7) // 8 * 8
-        v = torch.rand(m8, device="cuda", generator=gen) >= NULL_P
+        v = torch.rand(m8, device="cuda", generator=gen) >= null_p
         if m8 != m:
             v[m:] = False
         nulls += int(m - v[:m].sum().item())
@@ -176,29 +216,503 @@ def make_validity(torch, n, gen):
     return out, nulls
 
 
+def make_mask(torch, n, gen, sel):
+    m8 = (n + 7) // 8 * 8
+    bits = torch.zeros(m8 // 8 + 64, dtype=torch.uint8, device="cuda")
+    chunk = 1 << 27
+    for lo in range(0, m8, chunk):
+        m = min(chunk, m8 - lo)
+        bits[lo // 8:(lo + m) // 8] = pack_bits(torch, torch.rand(m, device="cuda", generator=gen) < sel)
+    return bits
+
+
+def unpack_bits(torch, bits, n):
+    """LSB-first bitmap bytes -> bool[n] (verification only)"""
+    sh = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    return ((bits[: (n + 7) // 8].unsqueeze(1) >> sh) & 1).reshape(-1)[:n].bool()
+
+
+def mix64(torch, x):
+    """murmur3 fmix64 on int64 tensors (wrap-around arithmetic; logical shifts emulated)"""
+    def lsr(v, s):
+        return (v >> s) & ((1 << (64 - s)) - 1)
+    x = x ^ lsr(x, 33)
+    x = x * -49064778989728563            # 0xff51afd7ed558ccd
+    x = x ^ lsr(x, 33)
+    x = x * -4265267296055464877          # 0xc4ceb9fe1a85ec53
+    return x ^ lsr(x, 33)
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank's CPU threads (and therefore its first-touch / pinned allocations) to the NUMA node
+    its GPU hangs off: 8 ranks pulling 20 GB/step of pinned H2D through the wrong socket cost the e2e leg
+    30 % at N = 8 in round 1.  Best effort, silent when sysfs does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+class Env:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa = bind_to_gpu_numa(self.local)
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        from arrow_b200 import Context, _cabi
+        self.ctx = Context.get(self.local)
+        # a real (non-NULL) stream: the C-ABI treats stream 0 as "use the context's own stream", and
+        # torch.cuda.Event only times the stream it is recorded on
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self.ctx.stream = self.stream.cuda_stream  # all C-ABI calls are ordered on torch's current stream
+        self.lib = _cabi.lib()
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, ints):
+        t = self.torch.tensor([int(x) for x in ints], dtype=self.torch.int64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(x) for x in t.tolist()]
+
+    def timed(self, fn, reps, warmup=1):
+        torch = self.torch
+        for _ in range(warmup):
+            r = fn()
+            del r
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        for _ in range(reps):
+            r = fn()
+            del r
+        b.record(self.stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[0,2,3,4] at full size on one GPU (the `configs` array of the bench line)
+# ------------------------------------------------------------------------------------------------
+def run_configs(env, n):
+    import pyarrow as pa
+
+    import arrow_b200.compute as bc
+    from arrow_b200 import DeviceArray
+    torch, ctx = env.torch, env.ctx
+    peak, _ = measured_peaks()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(SEED + 17)
+    out = []
+    reps = 3
+    I64 = torch.int64
+
+    def entry(name, rows, ms, alg_bytes, ok, **extra):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        e = {"name": name, "rows": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3), "alg_bytes": alg_bytes, "gbs": gbs,
+             "frac": gbs / peak, "parity_checksum_ok": bool(ok)}
+        e.update(extra)
+        out.append(e)
+
+    # ---- c1: Filter(int64 values null_p 0.1, bool mask s = 0.5), DROP ----
+    vals_t = torch.randint(-100, 101, (n,), dtype=I64, device="cuda", generator=gen)
+    vvalid_t, v_nulls = make_validity(torch, n, gen)
+    values = DeviceArray.from_pointers(ctx, pa.int64(), n, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
+    mask_bits = make_mask(torch, n, gen, 0.5)
+    mask = DeviceArray.from_pointers(ctx, pa.bool_(), n, mask_bits.data_ptr())
+    ms = env.timed(lambda: bc.filter(values, mask), reps)
+    res = bc.filter(values, mask)
+    # parity: length = popcount(mask); order-sensitive checksum of the kept values and their validity
+    ok = True
+    kept = 0
+    chk_got = chk_want = 0
+    pos = 0
+    ov = unpack_bits(torch, torch.as_tensor(_view(res.buffers[0].ptr, (res.length + 7) // 8, "|u1", res), device="cuda"), res.length) \
+        if res.buffers[0] is not None else None
+    od = torch.as_tensor(_view(res.buffers[1].ptr, res.length, "<i8", res), device="cuda")
+    chunk = 1 << 27
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        sel = unpack_bits(torch, mask_bits[lo // 8:], m)
+        vv = unpack_bits(torch, vvalid_t[lo // 8:], m)
+        k = int(sel.sum().item())
+        want_v, want_ok = vals_t[lo:lo + m][sel], vv[sel]
+        got_v = od[pos:pos + k]
+        got_ok = ov[pos:pos + k] if ov is not None else torch.ones(k, dtype=torch.bool, device="cuda")
+        w = torch.arange(pos + 1, pos + k + 1, dtype=I64, device="cuda")
+        chk_want += int(((want_v * want_ok) * w).sum().item()) + int((want_ok * w).sum().item())
+        chk_got += int(((got_v * got_ok) * w).sum().item()) + int((got_ok * w).sum().item())
+        pos += k
+        kept += k
+        del sel, vv, want_v, want_ok, w
+    ok = kept == res.length and (chk_got - chk_want) % (1 << 64) == 0
+    entry("c1 filter int64 (values null_p 0.1, mask s=0.5, DROP)", n, ms, n * (8 + 0.125 + 0.125) + res.length * 8.125, ok,
+          selectivity=res.length / n)
+    del res, od, ov, mask, mask_bits, values, vals_t, vvalid_t
+    ctx.trim()
+    torch.cuda.empty_cache()
+
+    # ---- c3: group-by sum + count, int64 key (10M groups), int64 value null_p 0.1 ----
+    groups = 10_000_000 if n >= 100_000_000 else max(1000, n // 100)
+    keys_t = torch.randint(0, groups, (n,), dtype=I64, device="cuda", generator=gen)
+    vals_t = torch.randint(-100, 101, (n,), dtype=I64, device="cuda", generator=gen)
+    vvalid_t, v_nulls = make_validity(torch, n, gen)
+    keys = DeviceArray.from_pointers(ctx, pa.int64(), n, keys_t.data_ptr())
+    vals = DeviceArray.from_pointers(ctx, pa.int64(), n, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
+
+    def fused():
+        g = bc.GroupBySumCount(pa.int64(), pa.int64(), expected_groups=groups, ctx=ctx)
+        g.consume(keys, vals)
+        return g.finalize()
+
+    def unfused():
+        return bc.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None)])
+
+    # the independent answer: torch index_add_ / bincount on the same device columns
+    want_cnt = torch.zeros(groups, dtype=I64, device="cuda")
+    want_sum = torch.zeros(groups, dtype=I64, device="cuda")
+    want_rows = torch.zeros(groups, dtype=I64, device="cuda")
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        vv = unpack_bits(torch, vvalid_t[lo // 8:], m).to(I64)
+        kk = keys_t[lo:lo + m]
+        want_cnt.index_add_(0, kk, vv)
+        want_sum.index_add_(0, kk, vals_t[lo:lo + m] * vv)
+        want_rows.index_add_(0, kk, torch.ones_like(vv))
+        del vv
+    present = want_rows > 0
+
+    def check_groups(k, s, c):
+        kt = torch.as_tensor(_view(k.buffers[1].ptr, k.length, "<i8", k), device="cuda")
+        st = torch.as_tensor(_view(s.buffers[1].ptr, s.length, "<i8", s), device="cuda")
+        ct = torch.as_tensor(_view(c.buffers[1].ptr, c.length, "<i8", c), device="cuda")
+        if k.length != int(present.sum().item()) or k.null_count != 0:
+            return False
+        seen = torch.zeros(groups, dtype=torch.bool, device="cuda")
+        seen[kt] = True
+        if int(seen.sum().item()) != k.length:       # every key exactly once
+            return False
+        if not bool((ct == want_cnt[kt]).all().item()):
+            return False
+        nz = ct > 0
+        if not bool((st[nz] == want_sum[kt][nz]).all().item()):
+            return False
+        return s.null_count == int((~nz).sum().item())
+
+    ms = env.timed(fused, reps)
+    k, s, c = fused()
+    ng = k.length
+    ok = check_groups(k, s, c)
+    del k, s, c
+    entry("c3 group-by hash_sum+hash_count int64 key, 10M groups (fused b2_groupby_sumcount)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng)
+    ms = env.timed(unfused, 2)
+    (ku,), (su, cu) = unfused()
+    ok = check_groups(ku, su, cu)
+    del ku, su, cu
+    entry("c3 group-by via Grouper + 2 HashAggregators (the reference API shape)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng)
+    del keys, vals, keys_t, vals_t, vvalid_t, want_cnt, want_sum, want_rows, present
+    ctx.trim()
+    torch.cuda.empty_cache()
+
+    # ---- c4: SortIndices int64 + validity ----
+    m = n
+    for name, lo_v, hi_v in (("wide [-2^62,2^62)", -2**62, 2**62), ("narrow [0,4095]", 0, 4096)):
+        keys_t = torch.randint(lo_v, hi_v, (m,), dtype=I64, device="cuda", generator=gen)
+        kvalid_t, k_nulls = make_validity(torch, m, gen)
+        keys = DeviceArray.from_pointers(ctx, pa.int64(), m, keys_t.data_ptr(), validity_ptr=kvalid_t.data_ptr(), null_count=k_nulls)
+        ms = env.timed(lambda: bc.array_sort_indices(keys), 2)
+        idx = bc.array_sort_indices(keys)
+        it = torch.as_tensor(_view(idx.buffers[1].ptr, m, "<i8", idx), device="cuda")
+        nv = m - k_nulls
+        # stable permutation, keys non-decreasing with ties in index order, nulls last in index order
+        ok = True
+        prev_k = prev_i = None
+        for lo in range(0, nv, chunk):
+            hi = min(nv, lo + chunk)
+            sk, si = keys_t[it[lo:hi]], it[lo:hi]
+            good = (sk[1:] > sk[:-1]) | ((sk[1:] == sk[:-1]) & (si[1:] > si[:-1]))
+            ok = ok and bool(good.all().item())
+            if prev_k is not None:
+                ok = ok and (int(sk[0]) > prev_k or (int(sk[0]) == prev_k and int(si[0]) > prev_i))
+            prev_k, prev_i = int(sk[-1]), int(si[-1])
+            del sk, si, good
+        if k_nulls:
+            ni = it[nv:]
+            ok = ok and bool((ni[1:] > ni[:-1]).all().item())
+            ok = ok and not bool(unpack_bits(torch, kvalid_t, m)[ni].any().item())
+        ok = ok and (int(it.sum().item()) - m * (m - 1) // 2) % (1 << 64) == 0
+        entry(f"c4 sort_indices int64 {name}, null_p 0.1", m, ms, m * 16.125, ok)
+        del keys, keys_t, kvalid_t, idx, it
+        ctx.trim()
+        torch.cuda.empty_cache()
+
+    # ---- c5: large_utf8 Filter (500M strings, 0-32 B) + dictionary-encoded Take ----
+    m = n // 2
+    lens = torch.randint(0, 33, (m,), dtype=I64, device="cuda", generator=gen)
+    offs = torch.zeros(m + 1, dtype=I64, device="cuda")
+    torch.cumsum(lens, 0, out=offs[1:])
+    total = int(offs[-1].item())
+    del lens
+    data = torch.randint(97, 123, (total + 64,), dtype=torch.uint8, device="cuda", generator=gen)
+    svalid_t, s_nulls = make_validity(torch, m, gen)
+    strs = DeviceArray.from_pointers(ctx, pa.large_string(), m, offs.data_ptr(), validity_ptr=svalid_t.data_ptr(), null_count=s_nulls,
+                                     data2_ptr=data.data_ptr())
+    mask_bits = make_mask(torch, m, gen, 0.5)
+    mask = DeviceArray.from_pointers(ctx, pa.bool_(), m, mask_bits.data_ptr())
+    ms = env.timed(lambda: bc.filter(strs, mask), reps)
+    res = bc.filter(strs, mask)
+    L = total / max(m, 1)
+    # parity: kept rows, offsets = running sum of the kept lengths, validity of the kept rows, and a byte-exact
+    # comparison of the whole output data buffer against torch's own compaction (16M-row slabs)
+    sel = unpack_bits(torch, mask_bits, m)
+    ro = torch.as_tensor(_view(res.buffers[1].ptr, res.length + 1, "<i8", res), device="cuda")
+    ok = res.length == int(sel.sum().item()) and int(ro[0].item()) == 0
+    rd = torch.as_tensor(_view(res.buffers[2].ptr, max(int(ro[-1].item()), 1), "|u1", res), device="cuda") if ok else None
+    rv = unpack_bits(torch, torch.as_tensor(_view(res.buffers[0].ptr, (res.length + 7) // 8, "|u1", res), device="cuda"), res.length) \
+        if res.buffers[0] is not None else None
+    slab, k0 = 1 << 24, 0
+    for r0 in range(0, m, slab):
+        if not ok:
+            break
+        r1 = min(m, r0 + slab)
+        sc = sel[r0:r1]
+        ln = offs[r0 + 1:r1 + 1] - offs[r0:r1]
+        k1 = k0 + int(sc.sum().item())
+        ok = ok and bool(((ro[k0 + 1:k1 + 1] - ro[k0:k1]) == ln[sc]).all().item())
+        b0, b1 = int(offs[r0].item()), int(offs[r1].item())
+        want_bytes = data[b0:b1][torch.repeat_interleave(sc, ln)]
+        g0, g1 = int(ro[k0].item()), int(ro[k1].item())
+        ok = ok and (g1 - g0) == want_bytes.numel() and bool(torch.equal(rd[g0:g1], want_bytes))
+        want_valid = unpack_bits(torch, svalid_t[r0 // 8:], r1 - r0)[sc]
+        ok = ok and bool(((rv[k0:k1] if rv is not None else torch.ones(k1 - k0, dtype=torch.bool, device="cuda")) == want_valid).all().item())
+        k0 = k1
+        del sc, ln, want_bytes, want_valid
+    entry("c5 filter large_utf8 500M strings (0-32 B, null_p 0.1, s=0.5)", m, ms,
+          m * (8 + L + 0.25) + res.length * (8 + L + 0.125), ok, mean_len=L)
+    del res, strs, offs, data, svalid_t, mask, mask_bits, sel, ro, rd, rv
+    ctx.trim()
+    torch.cuda.empty_cache()
+    dict_idx_t = torch.randint(0, 1_000_000, (m,), dtype=torch.int32, device="cuda", generator=gen)
+    col = DeviceArray.from_pointers(ctx, pa.int32(), m, dict_idx_t.data_ptr())
+    take_idx_t = torch.randint(0, m, (m,), dtype=I64, device="cuda", generator=gen)
+    take_idx = DeviceArray.from_pointers(ctx, pa.int64(), m, take_idx_t.data_ptr())
+    ms = env.timed(lambda: bc.take(col, take_idx), reps)
+    res = bc.take(col, take_idx)
+    rt = torch.as_tensor(_view(res.buffers[1].ptr, m, "<i4", res), device="cuda")
+    ok = bool((rt == dict_idx_t[take_idx_t]).all().item())
+    entry("c5 dictionary take (int32 index column, uniform random int64 idx)", m, ms, m * (8 + 4 + 4), ok)
+    del res, rt, col, take_idx, dict_idx_t, take_idx_t
+    ctx.trim()
+    torch.cuda.empty_cache()
+    return out
+
+
+class _View:
+    def __init__(self, ptr, n, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _view(ptr, n, typestr, owner):
+    return _View(ptr, max(int(n), 0), typestr, owner)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[2] / configs[3] sharded over the ranks (strong scaling, one exchange each)
+# ------------------------------------------------------------------------------------------------
+BLOCK = 1 << 20  # rows generated per seed: the global dataset is identical at every N
+
+
+def run_multi_gpu(env, n_total, reps):
+    import pyarrow as pa
+
+    from arrow_b200 import DeviceArray
+    from arrow_b200 import distributed as d
+    torch, ctx, world, rank = env.torch, env.ctx, env.world, env.rank
+    I64 = torch.int64
+    ops = d.DeviceOps(ctx)
+    xchg = d.B2CommExchange(ctx)
+    n_blocks = (n_total + BLOCK - 1) // BLOCK
+    b0, b1 = rank * n_blocks // world, (rank + 1) * n_blocks // world
+    row0, row1 = b0 * BLOCK, min(b1 * BLOCK, n_total)
+    n_local = row1 - row0
+    groups = 10_000_000 if n_total >= 100_000_000 else max(1000, n_total // 100)
+    result = {"rows_total": n_total, "scaling": "strong", "transport": "b2_comm (NCCL all-to-all-v, one NCCL group per exchange)",
+              "rows_this_rank0": n_local}
+
+    def gen_columns(kind):
+        """kind 'groupby': keys uniform [0, groups), values uniform [-100, 100] null_p 0.1
+           kind 'sort'   : keys uniform [-2^62, 2^62) null_p 0.1 (returned as the `keys` column + validity)"""
+        keys = torch.empty(n_local, dtype=I64, device="cuda")
+        vals = torch.empty(n_local, dtype=I64, device="cuda") if kind == "groupby" else None
+        bits = torch.zeros(n_local // 8 + 64, dtype=torch.uint8, device="cuda")
+        g = torch.Generator(device="cuda")
+        nulls = 0
+        for b in range(b0, b1):
+            lo = b * BLOCK - row0
+            m = min(BLOCK, n_total - b * BLOCK)
+            g.manual_seed((SEED * 1000003 + b * 7 + (0 if kind == "groupby" else 3)) & 0x7FFFFFFFFFFF)
+            if kind == "groupby":
+                keys[lo:lo + m] = torch.randint(0, groups, (m,), dtype=I64, device="cuda", generator=g)
+                vals[lo:lo + m] = torch.randint(-100, 101, (m,), dtype=I64, device="cuda", generator=g)
+            else:
+                keys[lo:lo + m] = torch.randint(-2**62, 2**62, (m,), dtype=I64, device="cuda", generator=g)
+            v = torch.rand(BLOCK, device="cuda", generator=g) >= NULL_P
+            v[m:] = False
+            nulls += m - int(v.sum().item())
+            bits[lo // 8: lo // 8 + BLOCK // 8] = pack_bits(torch, v)
+        return keys, vals, bits, nulls
+
+    def leg(fn):
+        """CUDA-event time of `fn` (max over ranks), after one warm-up; also the exchange's own time"""
+        r = fn()
+        del r
+        env.sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms_list, x_list = [], []
+        xbytes = 0
+        for _ in range(reps):
+            env.sync_all()
+            a.record(env.stream)
+            r = fn()
+            b.record(env.stream)
+            torch.cuda.synchronize()
+            ms_list.append(env.max_over_ranks(a.elapsed_time(b)))
+            xm, xbytes = ops.exchange_stats() if world > 1 else (0.0, 0)
+            x_list.append(env.max_over_ranks(xm))
+        return r, sum(ms_list) / len(ms_list), sum(x_list) / len(x_list), xbytes
+
+    # ---- config 3: hash-aggregate ----
+    keys_t, vals_t, bits_t, v_nulls = gen_columns("groupby")
+    keys = DeviceArray.from_pointers(ctx, pa.int64(), n_local, keys_t.data_ptr())
+    vals = DeviceArray.from_pointers(ctx, pa.int64(), n_local, vals_t.data_ptr(), validity_ptr=bits_t.data_ptr(), null_count=v_nulls)
+    # expected_groups: a shard of >= 100 rows per key sees essentially every key
+    (k, s, c), ms, xms, xbytes = leg(lambda: d.group_by_sum_count(keys, vals, ops, xchg, expected_groups=groups))
+    kt = torch.as_tensor(_view(k.buffers[1].ptr, k.length, "<i8", k), device="cuda")
+    st = torch.as_tensor(_view(s.buffers[1].ptr, s.length, "<i8", s), device="cuda")
+    ct = torch.as_tensor(_view(c.buffers[1].ptr, c.length, "<i8", c), device="cuda")
+    # invariants derived from the INPUT columns (torch, independent of the kernels under test)
+    valid = unpack_bits(torch, bits_t, n_local).to(I64)
+    in_count, in_sum = int(valid.sum().item()), int((vals_t * valid).sum().item())
+    in_keysum = int((mix64(torch, keys_t) * valid).sum().item())
+    out_groups, out_count, out_sum = k.length, int(ct.sum().item()), int((st * (ct > 0)).sum().item())
+    out_keysum = int((mix64(torch, kt) * ct).sum().item())
+    out_distinct = int(mix64(torch, kt).sum().item())
+    checksum = int((mix64(torch, kt) * (2 * st * (ct > 0) + 1) * (2 * ct + 3)).sum().item())
+    tot = env.sum_over_ranks([in_count, in_sum, in_keysum, out_groups, out_count, out_sum, out_keysum, out_distinct, checksum])
+    wrap = lambda x: x % (1 << 64)
+    want_distinct = int(mix64(torch, torch.arange(groups, dtype=I64, device="cuda")).sum().item())
+    ok = (tot[0] == tot[4] and wrap(tot[1]) == wrap(tot[5]) and wrap(tot[2]) == wrap(tot[6]) and tot[3] <= groups
+          and (tot[3] != groups or wrap(tot[7]) == wrap(want_distinct)))
+    result["groupby"] = {"workload": f"hash_sum+hash_count, int64 key, {groups} groups, value null_p 0.1", "ms": ms,
+                         "rows_per_s": n_total / (ms * 1e-3), "alltoall_bytes_per_rank": xbytes, "alltoall_ms": xms,
+                         "alltoall_share": (xms / ms) if ms else None, "groups": tot[3],
+                         "alg_bytes": n_total * 16.125 + tot[3] * 24.25,
+                         "frac_of_peak_x_n": (n_total * 16.125 + tot[3] * 24.25) / (ms * 1e-3) / 1e9 / (measured_peaks()[0] * world),
+                         "checksum": wrap(tot[8]), "parity_checksum_ok": bool(ok)}
+    del k, s, c, kt, st, ct, keys, vals, keys_t, vals_t, bits_t, valid
+    ctx.trim()
+    torch.cuda.empty_cache()
+
+    # ---- config 4: SortIndices ----
+    keys_t, _, bits_t, k_nulls = gen_columns("sort")
+    keys = DeviceArray.from_pointers(ctx, pa.int64(), n_local, keys_t.data_ptr(), validity_ptr=bits_t.data_ptr(), null_count=k_nulls)
+    (seg, nulls_idx, skeys), ms, xms, xbytes = leg(lambda: d.sort_indices(keys, ops, xchg, return_keys=True))
+    valid = unpack_bits(torch, bits_t, n_local)
+    grow = torch.arange(row0, row1, dtype=I64, device="cuda")
+    in_pair = int((mix64(torch, grow) * keys_t * valid.to(I64)).sum().item())
+    out_pair = int((mix64(torch, seg) * skeys).sum().item())
+    good = (skeys[1:] > skeys[:-1]) | ((skeys[1:] == skeys[:-1]) & (seg[1:] > seg[:-1]))
+    local_ok = bool(good.all().item()) if skeys.numel() > 1 else True
+    if nulls_idx.numel() > 1:
+        local_ok = local_ok and bool((nulls_idx[1:] > nulls_idx[:-1]).all().item())
+    if nulls_idx.numel():
+        local_ok = local_ok and not bool(valid[nulls_idx - row0].any().item())
+    # rank boundaries: (last key, last idx) of rank r must sort before (first key, first idx) of rank r+1
+    edge = torch.zeros(4, dtype=I64, device="cuda")
+    if skeys.numel():
+        edge[0], edge[1], edge[2], edge[3] = skeys[0], seg[0], skeys[-1], seg[-1]
+    edges = [torch.zeros(4, dtype=I64, device="cuda") for _ in range(world)]
+    sizes = env.torch.tensor([skeys.numel()], dtype=I64, device="cuda")
+    all_sizes = [torch.zeros(1, dtype=I64, device="cuda") for _ in range(world)]
+    if world > 1:
+        env.dist.all_gather(edges, edge)
+        env.dist.all_gather(all_sizes, sizes)
+    else:
+        edges, all_sizes = [edge], [sizes]
+    prev = None
+    for e, z in zip(edges, all_sizes):
+        if int(z.item()) == 0:
+            continue
+        e = [int(x) for x in e.tolist()]
+        if prev is not None and not (e[0] > prev[0] or (e[0] == prev[0] and e[1] > prev[1])):
+            local_ok = False
+        prev = (e[2], e[3])
+    idx_sum = int(seg.sum().item()) + int(nulls_idx.sum().item())
+    checksum = int((mix64(torch, seg) * (skeys | 1)).sum().item())
+    tot = env.sum_over_ranks([in_pair, out_pair, seg.numel() + nulls_idx.numel(), idx_sum, 0 if local_ok else 1, nulls_idx.numel(),
+                              k_nulls, checksum])
+    ok = (wrap(tot[0]) == wrap(tot[1]) and tot[2] == n_total and wrap(tot[3]) == wrap(n_total * (n_total - 1) // 2) and tot[4] == 0
+          and tot[5] == tot[6])
+    result["sort"] = {"workload": "sort_indices int64 uniform [-2^62, 2^62), null_p 0.1, ascending, nulls at end", "ms": ms,
+                      "rows_per_s": n_total / (ms * 1e-3), "alltoall_bytes_per_rank": xbytes, "alltoall_ms": xms,
+                      "alltoall_share": (xms / ms) if ms else None, "alg_bytes": n_total * 16.125,
+                      "frac_of_peak_x_n": n_total * 16.125 / (ms * 1e-3) / 1e9 / (measured_peaks()[0] * world),
+                      "segment_rows_rank0": int(seg.numel()), "checksum": wrap(tot[7]), "parity_checksum_ok": bool(ok)}
+    del seg, nulls_idx, skeys, keys, keys_t, bits_t, valid, grow
+    xchg.close()
+    ctx.trim()
+    torch.cuda.empty_cache()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import numpy as np
     import pyarrow as pa
-    import torch
-    import torch.distributed as dist
 
+    env = Env(args)
+    torch, dist, ctx, stream, lib = env.torch, env.dist, env.ctx, env.stream, env.lib
+    world, rank, local = env.world, env.rank, env.local
     import arrow_b200.compute as bc
-    from arrow_b200 import Context, DeviceArray, PinnedBuffer, _cabi
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = Context.get(local)
-    # a real (non-NULL) stream: the C-ABI treats stream 0 as "use the context's own stream", and
-    # torch.cuda.Event only times the stream it is recorded on
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx.stream = stream.cuda_stream  # all C-ABI calls are ordered on torch's current stream
-    lib = _cabi.lib()
+    from arrow_b200 import DeviceArray, PinnedBuffer
 
     n = args.rows
     gen = torch.Generator(device="cuda")
@@ -218,23 +732,29 @@ def run_gpu(args):
         c = bc.cast(t, pa.float32(), safe=False)
         return bc.add(c, o)
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    sync_all, max_over_ranks = env.sync_all, env.max_over_ranks
 
     # ---- warm-up (also fills the pool so the timed region never calls cudaMalloc) ----
     for _ in range(args.warmup):
         out = pipeline(values, indices, other)
     out_nulls = out.null_count
-    del out
+    # parity of the step's result against a plain torch restatement of the same three ops (verification only)
+    ot = torch.as_tensor(_view(out.buffers[1].ptr, n, "<f4", out), device="cuda")
+    ovb = unpack_bits(torch, torch.as_tensor(_view(out.buffers[0].ptr, (n + 7) // 8, "|u1", out), device="cuda"), n) \
+        if out.buffers[0] is not None else torch.ones(n, dtype=torch.bool, device="cuda")
+    pipeline_ok = True
+    chunk = 1 << 27
+    vv_all = None
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        ii = idx_t[lo:lo + m]
+        want_valid = ((vvalid_t[ii >> 3] >> (ii & 7).to(torch.uint8)) & 1).bool() & unpack_bits(torch, ovalid_t[lo // 8:], m)
+        want = values_t[ii].to(torch.float32) + other_t[lo:lo + m]
+        got_valid = ovb[lo:lo + m]
+        pipeline_ok = pipeline_ok and bool((got_valid == want_valid).all().item())
+        pipeline_ok = pipeline_ok and bool((ot[lo:lo + m][want_valid] == want[want_valid]).all().item())
+        del ii, want_valid, want, got_valid
+    del out, ot, ovb
 
     # ---- per-kernel timing (events around each call; the call = its kernel + a bitmap kernel) ----
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -277,16 +797,7 @@ def run_gpu(args):
     sorted_idx_t = torch.clamp(torch.cumsum(inc, 0), max=n - 1)
     del inc
     sorted_idx = DeviceArray.from_pointers(ctx, pa.int64(), n, sorted_idx_t.data_ptr())
-    t = bc.take(values, sorted_idx)
-    del t
-    torch.cuda.synchronize()
-    ev[0].record(stream)
-    for _ in range(args.steps):
-        t = bc.take(values, sorted_idx)
-        del t
-    ev[1].record(stream)
-    torch.cuda.synchronize()
-    take_sorted_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    take_sorted_ms = env.timed(lambda: bc.take(values, sorted_idx), args.steps)
     del sorted_idx, sorted_idx_t
 
     # ---- e2e: pinned host inputs -> H2D -> pipeline -> D2H of the result column ----
@@ -323,7 +834,7 @@ def run_gpu(args):
     bounds = [min(m, (m * k // K) // 64 * 64) for k in range(K)] + [m]
 
     def e2e_step():
-        ci, co, cs = copy_in.cuda_stream, copy_out.cuda_stream, stream.cuda_stream
+        ci, co = copy_in.cuda_stream, copy_out.cuda_stream
         ctx.h2d(d_values.ptr, h_values.ptr, h_values.size, ci)
         ctx.h2d(d_vvalid.ptr, h_vvalid.ptr, h_vvalid.size, ci)
         ev_vals = torch.cuda.Event()
@@ -369,6 +880,24 @@ def run_gpu(args):
     sync_all()
     e2e_ms = max_over_ranks(max(start.elapsed_time(stop), (time.perf_counter() - t0) * 1e3)) / e2e_steps
     e2e_value = m * world / (e2e_ms * 1e-3)
+    del h_values, h_vvalid, h_idx, h_other, h_ovalid, h_out, h_outvalid, d_values, d_vvalid, d_idx, d_other, d_ovalid
+
+    # ---- free config 2's columns, then the other configs and the sharded legs ----
+    del values, indices, other, values_t, vvalid_t, idx_t, other_t, ovalid_t
+    ctx.trim()
+    torch.cuda.empty_cache()
+    configs = None
+    if world == 1 and not args.no_configs:
+        try:
+            configs = run_configs(env, args.rows)
+        except Exception as e:  # report, never lose the headline line
+            configs = [{"error": f"{type(e).__name__}: {e}"[:400]}]
+    multi = None
+    if not args.no_multi:
+        try:
+            multi = run_multi_gpu(env, args.multi_rows or args.rows, max(1, min(args.steps, 3)))
+        except Exception as e:
+            multi = {"error": f"{type(e).__name__}: {e}"[:400]}
 
     if rank != 0:
         if world > 1:
@@ -394,8 +923,8 @@ def run_gpu(args):
             traffic = tj["dram_bytes_per_row"] * n
         except Exception:
             traffic = None
-    cores = os.cpu_count() or 1
-    cpu_rate, _ = reference_pipeline_rate(args.cpu_sample_rows, 2, 1, cores)
+    cpu = cpu_baseline_leg(args) if world == 1 else {"value": None, "unit": "rows/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                                      "sample": "measured at N = 1 only (rank 0)"}
     line = {
         "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -404,17 +933,18 @@ def run_gpu(args):
                    if n == 1_000_000_000 else f"Take+Cast(f64->f32)+Add, null_probability=0.1, {n} rows/GPU",
                    "rows_per_gpu": n, "indices": "uniform random int64", "l2": "inputs (20 GB) are far larger than the 126 MB L2",
                    "pipeline_alg_bytes_per_row": ALG_PIPELINE, "pipeline_gbs": ALG_PIPELINE * n * world / (ms_per_step * 1e-3) / 1e9,
-                   "out_null_count": int(out_nulls)},
+                   "out_null_count": int(out_nulls), "parity_checksum_ok": bool(pipeline_ok), "numa_node": env.numa},
         "roofline": {"bound": "hbm", "achieved": take_gbs, "peak": peak, "unit": "GB/s", "frac": take_gbs / peak,
                      "traffic": traffic, "kernel": "take_kernel<8,int64_t,true>", "peak_source": peak_src,
                      "alg_bytes_per_launch": ALG_TAKE * n},
         "kernels": kernels,
-        "cpu_baseline": {"value": cpu_rate, "unit": "rows/s", "cores": cores, "kind": "reference",
-                         "sample": f"{args.cpu_sample_rows} rows x 2 steps of the same pipeline, pyarrow 24.0.0 libarrow_compute, {cores} row-range threads"},
+        "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "rows_per_gpu": m, "ms_per_step": e2e_ms, "chunks": K},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "configs": configs,
+        "multi_gpu": multi,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -427,10 +957,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (config 2) / total rows (configs, multi_gpu legs)")
+    ap.add_argument("--multi-rows", type=int, default=0, help="total rows of the sharded group-by / sort legs (0 = --rows)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU for the host-buffer leg (0 = same as --rows)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the indices/other columns in the host-buffer leg")
-    ap.add_argument("--cpu-sample-rows", type=int, default=1 << 25)
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` array (c1/c3/c4/c5 at full size, N = 1 only)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the sharded group-by / sort legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

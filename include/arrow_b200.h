@@ -211,6 +211,34 @@ B2_API int b2_compare(B2Context* ctx, int op, const B2Value* left, const B2Value
                       B2Array* out, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Boolean logic and validity predicates (what a filter Expression is made of).
+ * Replaces AndOp / OrOp / XorOp / AndNotOp / InvertOp and the Kleene variants
+ * (kernels/scalar_boolean.cc:30-270) and IsValidExec / IsNullExec / TrueUnlessNullExec / is_nan
+ * (kernels/scalar_validity.cc:35-311; NullOptions{nan_is_null} compute/api_scalar.h).
+ * Operands are B2_BOOL arrays (or one B2_BOOL scalar); `right` is NULL for B2_BOOL_INVERT.
+ * ------------------------------------------------------------------------- */
+typedef enum B2BooleanOp {
+  B2_BOOL_AND = 0,
+  B2_BOOL_OR = 1,
+  B2_BOOL_XOR = 2,
+  B2_BOOL_AND_NOT = 3,
+  B2_BOOL_AND_KLEENE = 4,
+  B2_BOOL_OR_KLEENE = 5,
+  B2_BOOL_AND_NOT_KLEENE = 6,
+  B2_BOOL_INVERT = 7
+} B2BooleanOp;
+B2_API int b2_boolean(B2Context* ctx, int op, const B2Value* left, const B2Value* right, B2Array* out,
+                      void* stream);
+typedef enum B2ValidityOp {
+  B2_IS_VALID = 0,
+  B2_IS_NULL = 1,          /* nan_is_null != 0: NaN values of float arrays count as null too */
+  B2_TRUE_UNLESS_NULL = 2,
+  B2_IS_NAN = 3            /* float32 / float64 only; null in -> null out */
+} B2ValidityOp;
+B2_API int b2_validity(B2Context* ctx, int op, const B2Array* in, int nan_is_null, B2Array* out,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------
  * Filter.  Replaces PrimitiveFilterExec / BinaryFilterExec /
  * DictionaryFilterExec (kernels/vector_selection_filter_internal.cc:445-510,
  * 806-856,871-881) and GetFilterOutputSize (:62-114).
@@ -377,6 +405,36 @@ B2_API int b2_hash_partition(B2Context* ctx, const B2Array* keys, int n_parts, B
                              void* stream);
 B2_API int b2_range_partition(B2Context* ctx, const B2Array* values, const B2Array* splitters,
                               int order, B2Array* out_ids, void* stream);
+/* out_counts[b] (HOST array of n_bins int64) = rows whose id == b: the send counts of the exchange.
+ * ids: B2_UINT32 without nulls, every id < n_bins (else B2_INDEX_ERROR); n_bins <= 8192. */
+B2_API int b2_bincount(B2Context* ctx, const B2Array* ids, int n_bins, int64_t* out_counts, void* stream);
+
+/* The exchange itself: one process per GPU, NCCL over NVLink / NVSwitch (resolved with dlopen at the
+ * first call; libarrow_b200.so does not link NCCL).  Rank 0 creates the 128-byte id, the host
+ * application distributes it (MPI, a torch.distributed store, a file) and every rank calls
+ * b2_comm_init with the same id.  All calls are stream-ordered on `stream` like every other entry.
+ *   all_gather    : recv[r * bytes_per_rank ..] = rank r's `send` (the P x P count matrix)
+ *   all_reduce_i64: element-wise sum / max / min of `count` int64 values
+ *   all_to_all_v  : rank p receives send[send_offsets[p] .. + send_bytes[p]) of every rank q at
+ *                   recv[recv_offsets[q] ..]; the P-1 sends and receives are one NCCL group
+ *                   (host arrays of `world` entries, in bytes; recv_bytes must match the peers' send_bytes) */
+#define B2_COMM_ID_BYTES 128
+typedef struct B2Comm B2Comm;
+typedef enum B2CommOp { B2_COMM_SUM = 0, B2_COMM_MAX = 1, B2_COMM_MIN = 2 } B2CommOp;
+B2_API int b2_comm_unique_id(uint8_t* out_id /* [B2_COMM_ID_BYTES] */);
+B2_API int b2_comm_init(B2Context* ctx, int rank, int world, const uint8_t* id, B2Comm** out);
+B2_API void b2_comm_destroy(B2Comm* comm);
+B2_API int b2_comm_rank(const B2Comm* comm);
+B2_API int b2_comm_world(const B2Comm* comm);
+B2_API int b2_comm_nccl_version(int* out);
+/* all_to_all_v calls between group_start and group_end (one per column) are issued as ONE NCCL launch */
+B2_API int b2_comm_group_start(B2Comm* comm);
+B2_API int b2_comm_group_end(B2Comm* comm);
+B2_API int b2_comm_all_gather(B2Comm* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+B2_API int b2_comm_all_reduce_i64(B2Comm* comm, const void* send, void* recv, int64_t count, int op, void* stream);
+B2_API int b2_comm_all_to_all_v(B2Comm* comm, const void* send, const int64_t* send_offsets,
+                                const int64_t* send_bytes, void* recv, const int64_t* recv_offsets,
+                                const int64_t* recv_bytes, void* stream);
 
 #ifdef __cplusplus
 }

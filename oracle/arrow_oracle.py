@@ -333,6 +333,60 @@ def compare(op: str, l, r) -> pa.Array:
 
 
 # ---------------------------------------------------------------------------------------
+# boolean logic + validity predicates
+#   (kernels/scalar_boolean.cc:30-270 AndOp/OrOp/XorOp/AndNotOp/InvertOp + Kleene*Op,
+#    kernels/scalar_validity.cc:35-311 IsValidExec/IsNullExec/TrueUnlessNullExec/is_nan)
+# ---------------------------------------------------------------------------------------
+def _bool_operand(x, n):
+    if isinstance(x, pa.Array):
+        return values(x), validity(x)
+    s = x if isinstance(x, pa.Scalar) else pa.scalar(x, pa.bool_())
+    if not s.is_valid:
+        return np.zeros(n, dtype=bool), np.zeros(n, dtype=bool)
+    return np.full(n, bool(s.as_py())), np.ones(n, dtype=bool)
+
+
+def boolean(op: str, l, r=None) -> pa.Array:
+    n = len(l) if isinstance(l, pa.Array) else len(r)
+    a, va = _bool_operand(l, n)
+    if op == "invert":
+        return make_array(pa.bool_(), ~a, va)
+    b, vb = _bool_operand(r, n)
+    if op == "and":
+        return make_array(pa.bool_(), a & b, va & vb)
+    if op == "or":
+        return make_array(pa.bool_(), a | b, va & vb)
+    if op == "xor":
+        return make_array(pa.bool_(), a ^ b, va & vb)
+    if op == "and_not":
+        return make_array(pa.bool_(), a & ~b, va & vb)
+    if op == "and_kleene":      # false AND anything = false (scalar_boolean.cc:138-210)
+        return make_array(pa.bool_(), a & b, (va & vb) | (va & ~a) | (vb & ~b))
+    if op == "or_kleene":       # true OR anything = true
+        return make_array(pa.bool_(), a | b, (va & vb) | (va & a) | (vb & b))
+    if op == "and_not_kleene":
+        return make_array(pa.bool_(), a & ~b, (va & vb) | (va & ~a) | (vb & b))
+    raise NotImplementedError(op)
+
+
+def validity_op(op: str, arr: pa.Array, nan_is_null: bool = False) -> pa.Array:
+    valid = validity(arr)
+    if op == "is_valid":
+        return make_array(pa.bool_(), valid)
+    if op == "true_unless_null":
+        return make_array(pa.bool_(), np.ones(len(arr), dtype=bool), valid)
+    nan = np.zeros(len(arr), dtype=bool)
+    if pa.types.is_floating(arr.type):
+        with np.errstate(all="ignore"):
+            nan = np.isnan(values(arr))
+    if op == "is_null":
+        return make_array(pa.bool_(), ~valid | (nan & valid if nan_is_null else False))
+    if op == "is_nan":
+        return make_array(pa.bool_(), nan, valid)
+    raise NotImplementedError(op)
+
+
+# ---------------------------------------------------------------------------------------
 # SortIndices   (kernels/vector_array_sort.cc:144-178,524-540; vector_sort_internal.h:113-305)
 # ---------------------------------------------------------------------------------------
 def sort_indices(arr: pa.Array, order: str = "ascending", null_placement: str = "at_end") -> pa.Array:

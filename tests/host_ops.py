@@ -1,6 +1,8 @@
 """Host stand-in for arrow_b200.distributed.DeviceOps, used only by the world_size-2 gloo tests:
 the same `ops` interface over pyarrow host arrays, the oracle and CPU tensors, so the exchange
 logic (partition, splits, all-to-all, merge, ordering) is exercised without a GPU."""
+import contextlib
+
 import numpy as np
 import pyarrow as pa
 import torch
@@ -23,18 +25,53 @@ def hash64(k: np.ndarray) -> np.ndarray:
 
 
 class HostOps:
+    """same method set as arrow_b200.distributed.DeviceOps"""
+
+    @contextlib.contextmanager
+    def stream_guard(self):
+        yield
+
     def type_of(self, arr):
         return arr.type
 
     def length(self, arr):
         return len(arr)
 
-    def scalar_tensor(self, v):
-        return torch.tensor([v], dtype=torch.int64)
+    def null_count(self, arr):
+        return arr.null_count
 
-    def local_group_by(self, keys, values):
+    def raw_tensor(self, arr):
+        v = ora.values(arr)
+        if v.dtype in (np.uint16, np.uint32, np.uint64):
+            v = v.view({2: np.int16, 4: np.int32, 8: np.int64}[v.dtype.itemsize])
+        return torch.from_numpy(v.copy())
+
+    def from_raw_tensor(self, t, typ):
+        return pa.array(t.numpy().view(ora.np_dtype(typ)), typ)
+
+    def meta_tensor(self, ints):
+        return torch.tensor([int(x) for x in ints], dtype=torch.int64)
+
+    def mark(self):
+        return None
+
+    def note_exchange(self, t0, xchg):
+        pass
+
+    def local_group_by(self, keys, values, expected_groups=0):
         uniq, (s, c) = ora.group_by([keys], [("hash_sum", values, None), ("hash_count", values, None)])
         return uniq[0], s, c
+
+    def split_null_group(self, k, s, c):
+        if k.null_count == 0:
+            return k, s, c, (0, 0, 0)
+        valid = ora.validity(k)
+        pos = int(np.flatnonzero(~valid)[0])
+        null_sum = s[pos].as_py() if s[pos].is_valid else 0
+        if isinstance(null_sum, float):
+            null_sum = int(np.array([null_sum], dtype=np.float64).view(np.int64)[0])
+        keep = pa.array(valid)
+        return ora.filter(k, keep), ora.filter(s, keep), ora.filter(c, keep), (1, null_sum, c[pos].as_py())
 
     def hash_partition(self, keys, n_parts):
         v, valid = ora.values(keys), ora.validity(keys)
@@ -48,6 +85,10 @@ class HostOps:
         ids = np.searchsorted(sp, v, side="right").astype(np.uint32)
         return pa.array(np.where(valid, ids, len(sp) + 1).astype(np.uint32))
 
+    def partition_plan(self, dest, n_bins):
+        counts = [int(x) for x in np.bincount(ora.values(dest), minlength=n_bins)[:n_bins]]
+        return ora.sort_indices(dest), counts
+
     def stable_sort_indices(self, arr):
         return ora.sort_indices(arr)
 
@@ -57,39 +98,16 @@ class HostOps:
     def slice(self, arr, off, length):
         return arr.slice(off, length)
 
-    def histogram(self, sorted_ids, n_bins):
-        return [int(x) for x in np.bincount(ora.values(sorted_ids), minlength=n_bins)[:n_bins]]
-
-    def key_tensors(self, k):
-        return torch.from_numpy(ora.values(k).copy()), torch.from_numpy((~ora.validity(k)).astype(np.uint8))
-
-    def sum_tensor(self, s):
-        return torch.from_numpy(np.where(ora.validity(s), ora.values(s), 0).copy())
-
-    def count_tensor(self, c):
-        return torch.from_numpy(ora.values(c).copy())
-
-    def values_tensor(self, arr):
-        return torch.from_numpy(ora.values(arr).copy())
-
-    def index_tensor(self, arr):
-        return torch.from_numpy(ora.values(arr).astype(np.int64))
-
-    def from_values_tensor(self, t, typ):
-        return pa.array(t.numpy(), typ)
-
-    def take_tensor(self, t, idx_arr):
-        return t[torch.from_numpy(ora.values(idx_arr).astype(np.int64))]
-
     def add_offset(self, idx_arr, off):
         return pa.array(ora.values(idx_arr).astype(np.uint64) + np.uint64(off), pa.uint64())
 
     def sample_valid(self, values, k):
         n = len(values)
         if n == 0:
-            return values
-        s = values.take(pa.array(np.arange(0, n, max(1, n // k))))
-        return s.drop_null()
+            return torch.empty(0, dtype=torch.int64)
+        step = max(1, -(-n // k))
+        s = values.take(pa.array(np.arange(0, n, step))).drop_null()
+        return self.raw_tensor(s)
 
     def pick_splitters(self, gathered, world, typ):
         g, _ = torch.sort(gathered)
@@ -98,10 +116,17 @@ class HostOps:
         pos = (torch.arange(1, world) * g.numel()) // world
         return pa.array(g[pos.clamp(max=g.numel() - 1)].numpy(), typ)
 
-    def merge_partials(self, rk, rn, rs, rc, keys_type, sum_type):
-        keys = pa.array(rk.numpy(), keys_type, mask=rn.numpy().astype(bool))
-        uniq, (s, c) = ora.group_by([keys], [("hash_sum", pa.array(rs.numpy(), sum_type), None),
-                                              ("hash_sum", pa.array(rc.numpy(), pa.int64()), None)])
-        cv = ora.values(c)
-        s = ora.make_array(sum_type, ora.values(s), cv != 0)
+    def merge_partials(self, rk, rs, rc, keys_type, sum_type, null_group):
+        kv, sv, cv = rk.numpy(), rs.numpy().view(ora.np_dtype(sum_type)), rc.numpy()
+        mask = np.zeros(len(kv), dtype=bool)
+        if null_group is not None:
+            kv = np.concatenate([kv, np.zeros(1, kv.dtype)])
+            sv = np.concatenate([sv, np.array([null_group[0]], dtype=np.int64).view(sv.dtype)])
+            cv = np.concatenate([cv, np.array([null_group[1]], dtype=cv.dtype)])
+            mask = np.concatenate([mask, [True]])
+        keys = pa.array(kv.view(ora.np_dtype(keys_type)), keys_type, mask=mask)
+        uniq, (s, c) = ora.group_by([keys], [("hash_sum", pa.array(sv, sum_type), None),
+                                              ("hash_sum", pa.array(cv, pa.int64()), None)])
+        cnt = ora.values(c)
+        s = ora.make_array(sum_type, ora.values(s), cnt != 0)
         return uniq[0], s, c

@@ -42,10 +42,10 @@ def _worker(rank, world, port, out_dir):
     n = 20001
     keys, vals, sortkeys, dup = _data(n)
     lo, hi = rank * n // world, (rank + 1) * n // world
-    k, s, c = d.group_by_sum_count(keys.slice(lo, hi - lo), vals.slice(lo, hi - lo), ops)
+    k, s, c = d.group_by_sum_count(keys.slice(lo, hi - lo), vals.slice(lo, hi - lo), ops, d.TorchExchange())
     res = {"k": k.to_pylist(), "s": s.to_pylist(), "c": c.to_pylist()}
     for name, col in (("wide", sortkeys), ("dup", dup)):
-        seg, nulls = d.sort_indices(col.slice(lo, hi - lo), ops, samples_per_rank=64)
+        seg, nulls = d.sort_indices(col.slice(lo, hi - lo), ops, d.TorchExchange(), samples_per_rank=64)
         res[name] = (seg.tolist(), nulls.tolist())
     torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
