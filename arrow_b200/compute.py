@@ -627,6 +627,12 @@ class GroupBySumCount:
         ck, cv = keys._c(), values._c()
         check(self.ctx.lib.b2_groupby_sumcount_consume(self.handle, C.byref(ck), C.byref(cv), self.ctx.stream))
 
+    def path_counts(self):
+        """(compact, general, atomic) chunks consumed so far -- which internal path did the work"""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.ctx.lib.b2_groupby_sumcount_path_counts(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def finalize(self):
         k, s, c = cabi.B2Array(), cabi.B2Array(), cabi.B2Array()
         check(self.ctx.lib.b2_groupby_sumcount_finalize(self.handle, C.byref(k), C.byref(s), C.byref(c),

@@ -18,6 +18,7 @@
 #include "bitmap.h"
 #include "hash_table.cuh"
 #include "groupby_partitioned.cuh"
+#include "groupby_compact.cuh"
 
 namespace b2 {
 
@@ -167,6 +168,7 @@ struct B2GroupBySumCount {
   uint64_t groups = 0;
   int64_t hint = 0;  // expected number of groups (0 = unknown); refined after every chunk
   bool hint_given = false;
+  int64_t chunks_compact = 0, chunks_general = 0, chunks_atomic = 0;  // which path consumed each chunk
 };
 
 constexpr int64_t kPartMinRows = 1ll << 21;  // below this the plain atomic path is cheaper than 5 launches
@@ -227,6 +229,7 @@ static int fused_consume(B2GroupBySumCount* g, const B2Array* keys, const B2Arra
   BitmapReader vv(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
   if (n >= kPartMinRows) return fused_consume_partitioned<V>(g, keys, values, s);
   if (!g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
+  ++g->chunks_atomic;
   for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
     const int64_t cn = n - row0 < kChunkRows ? n - row0 : kChunkRows;
     Temp pend_a(ctx, s), pend_b(ctx, s);
@@ -323,6 +326,158 @@ static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, in
   return B2_OK;
 }
 
+// ---- compact path (groupby_compact.cuh): 8-byte tuples, bulk-async loads -------------------------
+static inline int bit_width_u64(unsigned long long v) {
+  int b = 0;
+  while (v) {
+    ++b;
+    v >>= 1;
+  }
+  return b;
+}
+
+static bool g_compact_enabled = true;  // B2_GROUPBY_COMPACT=0 forces the general path (tests exercise both)
+
+// Runs one chunk on the compact path when the measured key range and the (verified) value window fit one
+// 64-bit tuple.  *done = false means "not applicable" (or the value window was violated): nothing has
+// touched the global table and the caller runs the general path on the same chunk.
+template <int KW>
+static int try_compact_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, int passes, cudaStream_t s,
+                             unsigned long long* d_counters, unsigned long long* ovf_pairs, unsigned int* ovf_counts,
+                             uint64_t ovf_cap, bool* done) {
+  *done = false;
+  B2Context* ctx = g->ctx;
+  if (!g_compact_enabled || passes == 0) return B2_OK;
+  const int vt = g->value_type;
+  if (vt == B2_FLOAT || vt == B2_DOUBLE) return B2_OK;  // float sums accumulate in double: general path
+  const int vw = type_width(vt);
+  const bool vsigned = vt == B2_INT8 || vt == B2_INT16 || vt == B2_INT32 || vt == B2_INT64;
+  const int kt = g->key_type;
+  const bool ksigned = kt == B2_INT8 || kt == B2_INT16 || kt == B2_INT32 || kt == B2_INT64;
+  const unsigned long long kflip = ksigned ? (1ull << (8 * KW - 1)) : 0ull;
+
+  // 1. stats: exact key range, null keys, both digit histograms; a sample of the 64-bit value range
+  Temp hist(ctx, s), dbase(ctx, s);
+  B2_RETURN_NOT_OK(hist.alloc(sizeof(unsigned long long) * 2 * kPartRadix));
+  B2_RETURN_NOT_OK(dbase.alloc(sizeof(uint32_t) * 2 * kPartRadix));
+  B2_CUDA(cudaMemsetAsync(hist.ptr, 0, sizeof(unsigned long long) * 2 * kPartRadix, s));
+  ScalarSlot sslot(ctx);
+  B2_RETURN_NOT_OK(sslot.zero(s));
+  CompactStats* d_stats = reinterpret_cast<CompactStats*>(sslot.dev());
+  static_assert(sizeof(CompactStats) <= 64, "CompactStats must fit the front of a scalar slot");
+  B2_CUDA(cudaMemsetAsync(&d_stats->kmin, 0xff, 8, s));
+  B2_CUDA(cudaMemsetAsync(&d_stats->vmin, 0xff, 8, s));
+  compact_stats_kernel<KW><<<grid_for(cn, kBlock * 16, ctx->sm_count * 8), kBlock, 0, s>>>(
+      raw.keys, raw.key_valid, raw.row0, cn, kflip, passes, hist.as<unsigned long long>(), d_stats);
+  B2_LAUNCHED();
+  if (vw == 8) {
+    const int64_t step = cn > 65536 ? cn / 65536 : 1;
+    compact_value_sample_kernel<<<64, kBlock, 0, s>>>(static_cast<const unsigned long long*>(raw.values), raw.val_valid, raw.row0,
+                                                     cn, step, vsigned, d_stats);
+    B2_LAUNCHED();
+  }
+  part_scan_kernel<<<passes, kPartRadix, 0, s>>>(hist.as<unsigned long long>(), dbase.as<uint32_t>());
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(sslot.fetch(s));
+  CompactStats st;
+  memcpy(&st, const_cast<const int64_t*>(reinterpret_cast<volatile int64_t*>(sslot.host())), sizeof(st));
+  const int64_t n_tuples = cn - (int64_t)st.null_keys;
+  if (n_tuples <= 0) return B2_OK;  // every key null: general path
+
+  // 2. tuple encoding
+  CompactEnc enc;
+  enc.kmin = st.kmin;
+  enc.kflip = kflip;
+  enc.kb = bit_width_u64(st.kmax - st.kmin);
+  if (enc.kb < 1) enc.kb = 1;
+  if (vw <= 4) {  // the type's own range: nothing to verify
+    enc.vb = 8 * vw;
+    enc.vbase = vsigned ? static_cast<unsigned long long>(-(1ll << (8 * vw - 1))) : 0ull;
+  } else if (st.sampled == 0) {
+    enc.vb = 8;
+    enc.vbase = 0;
+  } else {
+    const unsigned long long flip = vsigned ? 0x8000000000000000ull : 0ull;
+    const unsigned long long range = st.vmax - st.vmin;  // in the order-preserving domain
+    const int need = bit_width_u64(range);
+    int vb = need + 2 < 8 ? 8 : need + 2;  // 4x the sampled range: rows outside it are still caught by the pass-1 check
+    if (enc.kb + vb + 1 > 64) vb = 63 - enc.kb;
+    if (vb < need || vb < 1 || vb > 62) return B2_OK;
+    const unsigned long long slack = (((1ull << vb) - 1ull) - range) / 2;
+    enc.vb = vb;
+    enc.vbase = (st.vmin ^ flip) - slack;  // wrap-around is fine: v' = bits - vbase (mod 2^64)
+  }
+  if (enc.kb + enc.vb + 1 > 64) return B2_OK;
+
+  // 3. passes
+  const uint32_t n_tiles_in = (uint32_t)((cn + kCTile - 1) / kCTile);
+  const uint32_t n_tiles_t = (uint32_t)((n_tuples + kCTile - 1) / kCTile);
+  Temp bufA(ctx, s), bufB(ctx, s), lookback(ctx, s);
+  B2_RETURN_NOT_OK(bufA.alloc((size_t)n_tiles_t * kCTile * 8 + 256));
+  if (passes > 1) B2_RETURN_NOT_OK(bufB.alloc((size_t)n_tiles_t * kCTile * 8 + 256));
+  const size_t lb_bytes = (size_t)n_tiles_in * kPartRadix * sizeof(uint32_t) + 256;
+  B2_RETURN_NOT_OK(lookback.alloc(lb_bytes));
+  B2_CUDA(cudaMemsetAsync(lookback.ptr, 0, lb_bytes, s));
+  B2_RETURN_NOT_OK(sslot.zero(s));  // reuse the slot: [0] overflow flag, [1..3] null-key accumulator
+  CompactArgs a{};
+  a.keys = static_cast<const uint8_t*>(raw.keys) + (size_t)raw.row0 * KW;
+  a.vals = static_cast<const uint8_t*>(raw.values) + (size_t)raw.row0 * vw;
+  a.kw = KW;
+  a.vw = vw;
+  a.vsigned = vsigned;
+  a.bulk_ok = aligned_to(a.keys, 16) && aligned_to(a.vals, 16);
+  a.key_valid = raw.key_valid;
+  a.val_valid = raw.val_valid;
+  a.row0 = raw.row0;
+  a.in = nullptr;
+  a.out = bufA.as<unsigned long long>();
+  a.n = (uint32_t)cn;
+  a.enc = enc;
+  a.shift = 24;
+  a.digit_base = dbase.as<uint32_t>();
+  a.lookback = lookback.as<uint32_t>();
+  a.ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles_in * kPartRadix * sizeof(uint32_t));
+  a.overflow = reinterpret_cast<unsigned int*>(sslot.dev());
+  a.null_acc = reinterpret_cast<unsigned long long*>(sslot.dev() + 1);
+  const int max_ctas = ctx->sm_count * 2;
+  B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_pass_smem(true)));
+  compact_pass_kernel<true><<<(int)n_tiles_in < max_ctas ? (int)n_tiles_in : max_ctas, kCThreads, compact_pass_smem(true), s>>>(a);
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(sslot.fetch(s));
+  if (sslot.host()[0] != 0) return B2_OK;  // a value outside the sampled window: redo the chunk on the general path
+  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts, ovf_cap};
+  if (st.null_keys) {
+    compact_null_flush_kernel<<<1, 32, 0, s>>>(tref, reinterpret_cast<const unsigned long long*>(sslot.dev() + 1), d_counters);
+    B2_LAUNCHED();
+  }
+  const unsigned long long* sorted = bufA.as<unsigned long long>();
+  if (passes > 1) {
+    const size_t lb2 = (size_t)n_tiles_t * kPartRadix * sizeof(uint32_t) + 256;
+    B2_CUDA(cudaMemsetAsync(lookback.ptr, 0, lb2, s));
+    a.in = bufA.as<unsigned long long>();
+    a.out = bufB.as<unsigned long long>();
+    a.n = (uint32_t)n_tuples;
+    a.shift = 16;
+    a.digit_base = dbase.as<uint32_t>() + kPartRadix;
+    a.ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles_t * kPartRadix * sizeof(uint32_t));
+    B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_pass_smem(false)));
+    compact_pass_kernel<false><<<(int)n_tiles_t < max_ctas ? (int)n_tiles_t : max_ctas, kCThreads, compact_pass_smem(false), s>>>(a);
+    B2_LAUNCHED();
+    sorted = bufB.as<unsigned long long>();
+  }
+  const bool narrow = enc.kb <= 31 && enc.vb <= 19;
+  if (narrow) {
+    B2_CUDA(cudaFuncSetAttribute(compact_preagg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_preagg_smem<true>()));
+    compact_preagg_kernel<true><<<max_ctas, kCThreads, compact_preagg_smem<true>(), s>>>(sorted, (uint32_t)n_tuples, enc, tref, d_counters);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(compact_preagg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_preagg_smem<false>()));
+    compact_preagg_kernel<false><<<max_ctas, kCThreads, compact_preagg_smem<false>(), s>>>(sorted, (uint32_t)n_tuples, enc, tref, d_counters);
+  }
+  B2_LAUNCHED();
+  *done = true;
+  return B2_OK;
+}
+
 template <typename V>
 static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, const B2Array* values, cudaStream_t s) {
   B2Context* ctx = g->ctx;
@@ -355,7 +510,7 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     const int64_t cn = remaining < max_chunk ? remaining : max_chunk;
     const uint64_t ovf_cap = static_cast<uint64_t>(cn < kChunkRows ? cn : kChunkRows);
     const int64_t est = g->hint > 0 ? g->hint : (g->groups > 0 ? (int64_t)g->groups : (1ll << 40));
-    const int passes = est <= 1500 ? 0 : (est <= 400000 ? 1 : 2);
+    const int passes = est <= 1500 ? 0 : (est <= 200000 ? 1 : 2);
     // parking space for entries that hit the probe limit (worst case: every row of the chunk)
     Temp ovf_pairs(ctx, s), ovf_counts(ctx, s);
     B2_RETURN_NOT_OK(ovf_pairs.alloc(16 * (size_t)ovf_cap));
@@ -365,13 +520,27 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     raw.row0 = row0;
     unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
     int st;
+    bool done = false;
+    unsigned long long* op = ovf_pairs.as<unsigned long long>();
+    unsigned int* oc = ovf_counts.as<unsigned int>();
     switch (kw) {
-      case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
-      default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap); break;
+      case 1: st = try_compact_chunk<1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
+      case 2: st = try_compact_chunk<2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
+      case 4: st = try_compact_chunk<4>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
+      default: st = try_compact_chunk<8>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
     }
     if (st != B2_OK) return st;
+    if (done) ++g->chunks_compact;
+    else ++g->chunks_general;
+    if (!done) {
+      switch (kw) {
+        case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
+        case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
+        case 4: st = run_partitioned_chunk<V, 4>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
+        default: st = run_partitioned_chunk<V, 8>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
+      }
+      if (st != B2_OK) return st;
+    }
     B2_RETURN_NOT_OK(slot.fetch(s));
     if (slot.host()[2] != 0)
       return set_error(B2_CAPACITY_ERROR, "group-by: %lld more groups than the table sized from expected_groups=%lld can absorb in one batch; "
@@ -410,6 +579,10 @@ extern "C" {
 int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_type, int64_t expected_groups,
                                B2GroupBySumCount** out) {
   if (!ctx || !out) return set_error(B2_INVALID, "b2_groupby_sumcount_create: null argument");
+  {
+    const char* e = getenv("B2_GROUPBY_COMPACT");
+    g_compact_enabled = !(e && e[0] == '0');
+  }
   if (type_width(key_type) == 0) return set_error(B2_NOT_IMPLEMENTED, "group-by key type id %d", key_type);
   if (!type_is_numeric(value_type)) return set_error(B2_NOT_IMPLEMENTED, "group-by value type id %d", value_type);
   B2_CUDA(cudaSetDevice(ctx->device));
@@ -456,6 +629,14 @@ int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys, const
     case B2_FLOAT: return fused_consume<float>(g, keys, values, s);
     default: return fused_consume<double>(g, keys, values, s);
   }
+}
+
+int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* compact, int64_t* general, int64_t* atomic) {
+  if (!g) return set_error(B2_INVALID, "b2_groupby_sumcount_path_counts: null argument");
+  if (compact) *compact = g->chunks_compact;
+  if (general) *general = g->chunks_general;
+  if (atomic) *atomic = g->chunks_atomic;
+  return B2_OK;
 }
 
 int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Array* out_sums, B2Array* out_counts,

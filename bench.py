@@ -132,7 +132,12 @@ def ref_bench(op, rows, steps, warmup, threads, groups=None, timeout=900):
     cmd = [REF_BENCH, op, str(int(rows)), str(int(steps)), str(int(warmup)), str(int(threads))]
     if groups:
         cmd.append(str(int(groups)))
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    def all_cpus():  # the GPU arm pinned this process to its GPU's NUMA node: the CPU arm gets every host thread back
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, preexec_fn=all_cpus)
     if out.returncode != 0:
         raise RuntimeError(f"ref_bench failed: {out.stderr[-500:]}")
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -395,9 +400,12 @@ def run_configs(env, n):
     keys = DeviceArray.from_pointers(ctx, pa.int64(), n, keys_t.data_ptr())
     vals = DeviceArray.from_pointers(ctx, pa.int64(), n, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
 
+    paths = {}
+
     def fused():
         g = bc.GroupBySumCount(pa.int64(), pa.int64(), expected_groups=groups, ctx=ctx)
         g.consume(keys, vals)
+        paths["counts"] = g.path_counts()
         return g.finalize()
 
     def unfused():
@@ -439,7 +447,8 @@ def run_configs(env, n):
     ng = k.length
     ok = check_groups(k, s, c)
     del k, s, c
-    entry("c3 group-by hash_sum+hash_count int64 key, 10M groups (fused b2_groupby_sumcount)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng)
+    entry("c3 group-by hash_sum+hash_count int64 key, 10M groups (fused b2_groupby_sumcount)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng,
+          chunks_compact_general_atomic=list(paths.get("counts", ())))
     ms = env.timed(unfused, 2)
     (ku,), (su, cu) = unfused()
     ok = check_groups(ku, su, cu)
@@ -511,17 +520,20 @@ def run_configs(env, n):
             break
         r1 = min(m, r0 + slab)
         sc = sel[r0:r1]
-        ln = offs[r0 + 1:r1 + 1] - offs[r0:r1]
+        row_valid = unpack_bits(torch, svalid_t[r0 // 8:], r1 - r0)
+        # a null string contributes no bytes to the output (the reference appends a null = repeats the offset,
+        # vector_selection_filter_internal.cc:598-856), whatever its slot spans in the input
+        ln = (offs[r0 + 1:r1 + 1] - offs[r0:r1]) * row_valid
         k1 = k0 + int(sc.sum().item())
         ok = ok and bool(((ro[k0 + 1:k1 + 1] - ro[k0:k1]) == ln[sc]).all().item())
         b0, b1 = int(offs[r0].item()), int(offs[r1].item())
-        want_bytes = data[b0:b1][torch.repeat_interleave(sc, ln)]
+        want_bytes = data[b0:b1][torch.repeat_interleave(sc & row_valid, offs[r0 + 1:r1 + 1] - offs[r0:r1])]
         g0, g1 = int(ro[k0].item()), int(ro[k1].item())
         ok = ok and (g1 - g0) == want_bytes.numel() and bool(torch.equal(rd[g0:g1], want_bytes))
-        want_valid = unpack_bits(torch, svalid_t[r0 // 8:], r1 - r0)[sc]
+        want_valid = row_valid[sc]
         ok = ok and bool(((rv[k0:k1] if rv is not None else torch.ones(k1 - k0, dtype=torch.bool, device="cuda")) == want_valid).all().item())
         k0 = k1
-        del sc, ln, want_bytes, want_valid
+        del sc, ln, want_bytes, want_valid, row_valid
     entry("c5 filter large_utf8 500M strings (0-32 B, null_p 0.1, s=0.5)", m, ms,
           m * (8 + L + 0.25) + res.length * (8 + L + 0.125), ok, mean_len=L)
     del res, strs, offs, data, svalid_t, mask, mask_bits, sel, ro, rd, rv
@@ -580,7 +592,7 @@ def run_multi_gpu(env, n_total, reps):
            kind 'sort'   : keys uniform [-2^62, 2^62) null_p 0.1 (returned as the `keys` column + validity)"""
         keys = torch.empty(n_local, dtype=I64, device="cuda")
         vals = torch.empty(n_local, dtype=I64, device="cuda") if kind == "groupby" else None
-        bits = torch.zeros(n_local // 8 + 64, dtype=torch.uint8, device="cuda")
+        bits = torch.zeros(n_local // 8 + BLOCK // 8 + 64, dtype=torch.uint8, device="cuda")
         g = torch.Generator(device="cuda")
         nulls = 0
         for b in range(b0, b1):

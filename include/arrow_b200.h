@@ -389,7 +389,13 @@ B2_API int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t 
 B2_API void b2_groupby_sumcount_destroy(B2GroupBySumCount* g);
 B2_API int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys,
                                        const B2Array* values, void* stream);
-/* out_keys / out_sums / out_counts: num_groups long, first-occurrence order */
+/* how many consume() chunks ran on each internal path (diagnostics for tests / bench):
+ *   compact : 8-byte tuples + bulk-async partition passes (narrow key range, verified value window)
+ *   general : 17-byte tuples, any key / value
+ *   atomic  : small batches, one global-table update per row */
+B2_API int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* compact, int64_t* general,
+                                           int64_t* atomic);
+/* out_keys / out_sums / out_counts: num_groups long, group order unspecified */
 B2_API int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys,
                                         B2Array* out_sums, B2Array* out_counts, void* stream);
 

@@ -68,3 +68,89 @@ def test_partitioned_group_by_types_and_batches(ctx):
     k2 = pa.array(rng.integers(0, 900_000, 3 * n, dtype=np.int64))
     v2 = pa.array(rng.integers(-100, 100, 3 * n, dtype=np.int64), mask=rng.random(3 * n) < 0.1)
     check(ctx, k2, v2, 10_000, batches=3)
+
+
+# ---- the compact path (csrc/groupby_compact.cuh): 8-byte tuples, bulk-async partition passes ----------
+def check_path(ctx, keys, vals, hint, want_path, batches=1, offset=0):
+    g = bc.GroupBySumCount(keys.type, vals.type, expected_groups=hint, ctx=ctx)
+    n = len(keys)
+    dk, dv = DeviceArray.from_arrow(keys, ctx), DeviceArray.from_arrow(vals, ctx)
+    keys, vals = keys.slice(offset), vals.slice(offset)
+    dk, dv = dk.slice(offset), dv.slice(offset)
+    n -= offset
+    for b in range(batches):
+        lo, hi = b * n // batches, (b + 1) * n // batches
+        g.consume(dk.slice(lo, hi - lo), dv.slice(lo, hi - lo))
+    compact, general, atomic = g.path_counts()
+    if want_path == "compact":
+        assert compact == batches and general == 0, (compact, general, atomic)
+    elif want_path == "general":
+        assert general == batches and compact == 0, (compact, general, atomic)
+    k, s, c = [x.to_arrow() for x in g.finalize()]
+    got = pa.table({"k": k, "v_sum": s, "v_count": c}).sort_by("k")
+    want = reference(keys, vals)
+    assert got["k"].combine_chunks().equals(want["k"].combine_chunks())
+    assert got["v_count"].combine_chunks().equals(want["v_count"].combine_chunks())
+    assert got["v_sum"].combine_chunks().equals(want["v_sum"].combine_chunks())
+
+
+@pytest.mark.parametrize("groups,hint", [(50_000, 50_000), (600_000, 600_000), (600_000, 0)])
+@pytest.mark.parametrize("offset", [0, 1])
+def test_compact_group_by_narrow(ctx, groups, hint, offset):
+    """int64 keys in [0, groups), int64 values in [-100, 100]: 32-bit shared-memory slots; offset 1 makes the
+    column pointers 8- but not 16-byte aligned, which takes the plain-load branch of the tile loader"""
+    n = 3_000_001 + offset
+    rng = np.random.default_rng(SEED + groups + offset)
+    keys = pa.array(rng.integers(0, groups, n, dtype=np.int64), mask=rng.random(n) < 0.01)
+    vals = pa.array(rng.integers(-100, 101, n, dtype=np.int64), mask=rng.random(n) < 0.1)
+    check_path(ctx, keys, vals, hint, "compact", offset=offset)
+
+
+def test_compact_group_by_wide_slots_types_and_batches(ctx):
+    n = 2_600_000
+    rng = np.random.default_rng(SEED + 7)
+    # key range 2^40, value range 2^21: 64-bit shared-memory slots
+    k = pa.array(rng.integers(-2**39, 2**39, 400_000, dtype=np.int64)[rng.integers(0, 400_000, n)], mask=rng.random(n) < 0.02)
+    v = pa.array(rng.integers(-2**20, 2**20, n, dtype=np.int64), mask=rng.random(n) < 0.1)
+    check_path(ctx, k, v, 400_000, "compact")
+    # narrow native types: the value window is the type's own range (nothing sampled)
+    k32 = pa.array(rng.integers(-70000, 70000, n, dtype=np.int32), mask=rng.random(n) < 0.02)
+    v16 = pa.array(rng.integers(-30000, 30000, n, dtype=np.int16), mask=rng.random(n) < 0.1)
+    check_path(ctx, k32, v16, 140_000, "compact")
+    ku16 = pa.array(rng.integers(0, 60000, n, dtype=np.uint16))
+    vu8 = pa.array(rng.integers(0, 255, n, dtype=np.uint8), mask=rng.random(n) < 0.5)
+    check_path(ctx, ku16, vu8, 0, "compact")
+    vu64 = pa.array(rng.integers(2**63, 2**63 + 1000, n, dtype=np.uint64), mask=rng.random(n) < 0.1)  # sums wrap like the reference
+    check_path(ctx, ku16, vu64, 60_000, "compact")
+    # a group whose every value is null must exist with sum = null, count = 0; an all-null-key batch
+    kk = rng.integers(0, 500_000, n, dtype=np.int64)
+    vv = rng.integers(-5, 5, n, dtype=np.int64)
+    check_path(ctx, pa.array(kk), pa.array(vv, mask=(kk % 7 == 0) | (rng.random(n) < 0.05)), 500_000, "compact")
+    check_path(ctx, pa.array(kk, mask=np.ones(n, dtype=bool)), pa.array(vv), 0, None)
+    # several consume() calls, growing past the hint
+    k2 = pa.array(rng.integers(0, 900_000, 3 * n, dtype=np.int64))
+    v2 = pa.array(rng.integers(-100, 100, 3 * n, dtype=np.int64), mask=rng.random(3 * n) < 0.1)
+    check_path(ctx, k2, v2, 10_000, "compact", batches=3)
+
+
+def test_compact_value_window_is_verified_not_trusted(ctx):
+    """64-bit values: the window comes from a SAMPLE; one row far outside it (at an unsampled position) must
+    send the chunk to the general path, never corrupt the sum"""
+    n = 2_500_000
+    rng = np.random.default_rng(SEED + 11)
+    k = pa.array(rng.integers(0, 300_000, n, dtype=np.int64))
+    v = rng.integers(-100, 101, n, dtype=np.int64)
+    v[1_234_567] = 2**61 + 12345          # n / 65536 = 38: row 1234567 is not a multiple of 38
+    v[1_234_569] = -2**62
+    assert 1_234_567 % (n // 65536) != 0 and 1_234_569 % (n // 65536) != 0
+    m = rng.random(n) < 0.1
+    m[1_234_567] = m[1_234_569] = False
+    check_path(ctx, k, pa.array(v, mask=m), 300_000, "general")
+    # and the general path on data the compact path would take (B2_GROUPBY_COMPACT=0)
+    import os
+    os.environ["B2_GROUPBY_COMPACT"] = "0"
+    try:
+        v2 = pa.array(rng.integers(-100, 101, n, dtype=np.int64), mask=rng.random(n) < 0.1)
+        check_path(ctx, k, v2, 300_000, "general")
+    finally:
+        del os.environ["B2_GROUPBY_COMPACT"]
