@@ -589,12 +589,24 @@ class HashAggregator:
         return _out(self.ctx, cout, arrow_type(cout.type))
 
 
-def group_by(keys: Sequence[DeviceArray], aggregates: Sequence[tuple]):
+def group_by(keys: Sequence[DeviceArray], aggregates: Sequence[tuple], fused: bool = True):
     """The Acero aggregate node's Consume/Finalize over one batch
     (acero/groupby_aggregate_node.cc:210-253,300-337): aggregates = [(function, values|None, opts)].
-    Returns (unique key columns, [aggregate columns])."""
+    Returns (unique key columns, [aggregate columns]); group order is unspecified (as under use_threads in the
+    reference, whose tests sort by key)."""
     if isinstance(keys, DeviceArray):
         keys = [keys]
+    # config 3's shape -- one fixed-width key, hash_sum / hash_count(only_valid) with default options over one value
+    # column -- takes the fused path (b2_groupby_sumcount_*), exactly as the C++ b200_aggregate node does; set
+    # fused=False in an aggregate's options dict ... or pass any non-default option to force the Grouper path
+    if fused and len(keys) == 1 and aggregates and all(
+            fn in ("hash_sum", "hash_count") and values is not None and not opts and values is aggregates[0][1]
+            for fn, values, opts in aggregates) and keys[0].type in _NUMERIC_TYPES and aggregates[0][1].type in _NUMERIC_TYPES \
+            and not pa.types.is_floating(keys[0].type):
+        gb = GroupBySumCount(keys[0].type, aggregates[0][1].type, ctx=keys[0].ctx)
+        gb.consume(keys[0], aggregates[0][1])
+        k, s_, c_ = gb.finalize()
+        return [k], [s_ if fn == "hash_sum" else c_ for fn, _, _ in aggregates]
     g = Grouper([k.type for k in keys], keys[0].ctx)
     ids = g.consume(keys)
     outs = []

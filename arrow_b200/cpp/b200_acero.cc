@@ -18,7 +18,10 @@
 #include <arrow/acero/options.h>
 #include <arrow/acero/query_context.h>
 #include <arrow/compute/expression.h>
+#include <arrow/array/concatenate.h>
 #include <arrow/table.h>
+
+#include <algorithm>
 
 #include <mutex>
 
@@ -71,7 +74,21 @@ class DeviceNode : public ac::ExecNode {
 
 // ------------------------------------------------------------------------------------------
 // aggregate (group-by)
+//
+// B200-first shape: the reference node consumes every <= 32Ki-row ExecBatch
+// as it arrives (kMaxBatchSize, acero/exec_plan.h:57); on a GPU that is 256 KB per launch, three orders of
+// magnitude below what a kernel needs to reach the HBM rate.  This node therefore
+//   * COALESCES: host batches are parked (only the key / aggregate-target columns) until
+//     kCoalesceRows rows are pending or the input ends, then concatenated, moved with one H2D copy per
+//     column and consumed as one device batch; batches that already live on the device and are large are
+//     consumed at once;
+//   * takes the FUSED path when the plan is config 3's shape -- one fixed-width key, every aggregate a
+//     hash_sum / hash_count(only_valid) with default options over one value column: the batch goes to
+//     b2_groupby_sumcount_consume (radix-partitioned, pre-aggregated in shared memory, no uint32 id column);
+//     any other plan runs Grouper::Consume + HashAggregateKernel::consume exactly like the reference node.
 // ------------------------------------------------------------------------------------------
+constexpr int64_t kCoalesceRows = 16ll << 20;
+
 class AggregateNode : public DeviceNode {
  public:
   struct Agg {
@@ -79,7 +96,30 @@ class AggregateNode : public DeviceNode {
     std::unique_ptr<cp::KernelState> state;
     std::unique_ptr<cp::KernelContext> kctx;
     int target;  // input column, -1 for hash_count_all
+    bool is_count = false;
   };
+
+  static bool DefaultOptions(const std::string& fn, const cp::FunctionOptions* o) {
+    if (o == nullptr) return true;
+    if (fn == "hash_sum") {
+      auto* s = dynamic_cast<const cp::ScalarAggregateOptions*>(o);
+      return s && s->skip_nulls && s->min_count == 1;
+    }
+    if (fn == "hash_count") {
+      auto* c = dynamic_cast<const cp::CountOptions*>(o);
+      return c && c->mode == cp::CountOptions::ONLY_VALID;
+    }
+    return false;
+  }
+
+  static bool FixedWidthNumericStorage(const arrow::DataType& t) {
+    switch (t.id()) {
+      case arrow::Type::INT8: case arrow::Type::UINT8: case arrow::Type::INT16: case arrow::Type::UINT16:
+      case arrow::Type::INT32: case arrow::Type::UINT32: case arrow::Type::INT64: case arrow::Type::UINT64:
+        return true;
+      default: return false;
+    }
+  }
 
   static Result<ac::ExecNode*> Make(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, const ac::ExecNodeOptions& options) {
     const auto& opts = static_cast<const ac::AggregateNodeOptions&>(options);
@@ -101,6 +141,8 @@ class AggregateNode : public DeviceNode {
     std::unique_ptr<AggregateNode> guard(node);
     node->key_idx_ = key_idx;
     ARROW_ASSIGN_OR_RAISE(node->grouper_, MakeGrouper(key_types, rt));
+    bool fusable = key_idx.size() == 1 && FixedWidthNumericStorage(*in_schema.field(key_idx[0])->type()) && !opts.aggregates.empty();
+    int fused_target = -1;
     for (const auto& a : opts.aggregates) {
       // GetKernel/InitKernel, acero/aggregate_internal.cc:67-123
       ARROW_ASSIGN_OR_RAISE(auto function, rt->registry()->GetFunction(a.function));
@@ -121,9 +163,33 @@ class AggregateNode : public DeviceNode {
       ARROW_ASSIGN_OR_RAISE(agg.state, agg.kernel->init(agg.kctx.get(), cp::KernelInitArgs{kernel, in_types, fo}));
       agg.kctx->SetState(agg.state.get());
       agg.target = target;
+      agg.is_count = a.function == "hash_count";
       ARROW_ASSIGN_OR_RAISE(auto out_type, kernel->signature->out_type().Resolve(agg.kctx.get(), in_types));
       fields.push_back(arrow::field(a.name.empty() ? a.function : a.name, out_type.GetSharedPtr()));
+      // fused path: hash_sum / hash_count(only_valid), default options, one shared numeric value column
+      const bool ok_fn = (a.function == "hash_sum" || a.function == "hash_count") && DefaultOptions(a.function, a.options.get());
+      const bool ok_type = target >= 0 && (FixedWidthNumericStorage(*in_schema.field(target)->type()) ||
+                                           in_schema.field(target)->type()->id() == arrow::Type::FLOAT ||
+                                           in_schema.field(target)->type()->id() == arrow::Type::DOUBLE);
+      if (!ok_fn || !ok_type || (fused_target >= 0 && fused_target != target)) fusable = false;
+      if (target >= 0 && fused_target < 0) fused_target = target;
       node->aggs_.push_back(std::move(agg));
+    }
+    if (const char* e = getenv("B200_AGGREGATE_FUSED")) fusable = fusable && e[0] != '0';
+    if (fusable) {
+      B2Array probe_k, probe_v;  // type ids through the same mapping the kernels use
+      auto kd = arrow::ArrayData::Make(in_schema.field(key_idx[0])->type(), 0, {nullptr, nullptr});
+      auto vd = arrow::ArrayData::Make(in_schema.field(fused_target)->type(), 0, {nullptr, nullptr});
+      ARROW_RETURN_NOT_OK(DataToB2(*kd, &probe_k));
+      ARROW_RETURN_NOT_OK(DataToB2(*vd, &probe_v));
+      B2GroupBySumCount* h = nullptr;
+      int st = b2_groupby_sumcount_create(rt->context(), probe_k.type, probe_v.type, 0, &h);
+      if (st == B2_OK) {
+        node->fused_.reset(h);
+        node->fused_target_ = fused_target;
+      } else if (st != B2_NOT_IMPLEMENTED) {
+        return Status::UnknownError("b2_groupby_sumcount_create: ", b2_last_error());
+      }
     }
     node->SetSchema(arrow::schema(std::move(fields)));
     return plan->AddNode(std::move(guard));
@@ -135,22 +201,28 @@ class AggregateNode : public DeviceNode {
 
   Status InputReceived(ac::ExecNode*, cp::ExecBatch batch) override {
     std::lock_guard<std::mutex> lk(mu_);
-    // Consume, groupby_aggregate_node.cc:210-253
-    cp::ExecBatch keys({}, batch.length);
-    for (int i : key_idx_) {
-      ARROW_ASSIGN_OR_RAISE(auto d, ColumnToDevice(rt_, batch.values[i], batch.length));
-      keys.values.push_back(std::move(d));
-    }
-    ARROW_ASSIGN_OR_RAISE(Datum ids, grouper_->Consume(cp::ExecSpan(keys)));
-    for (auto& a : aggs_) {
-      ARROW_RETURN_NOT_OK(a.kernel->resize(a.kctx.get(), grouper_->num_groups()));
-      cp::ExecBatch in({}, batch.length);
-      if (a.target >= 0) {
-        ARROW_ASSIGN_OR_RAISE(auto d, ColumnToDevice(rt_, batch.values[a.target], batch.length));
-        in.values.push_back(std::move(d));
+    // park the columns this node reads (keys + aggregate targets); everything else is dropped here
+    std::vector<int> cols = NeededColumns();
+    bool all_device = true;
+    std::vector<std::shared_ptr<arrow::ArrayData>> row;
+    for (int c : cols) {
+      const Datum& v = batch.values[c];
+      std::shared_ptr<arrow::ArrayData> d;
+      if (v.is_scalar()) {
+        ARROW_ASSIGN_OR_RAISE(auto arr, arrow::MakeArrayFromScalar(*v.scalar(), batch.length));
+        d = arr->data();
+      } else {
+        d = v.array();
       }
-      in.values.push_back(ids);
-      ARROW_RETURN_NOT_OK(a.kernel->consume(a.kctx.get(), cp::ExecSpan(in)));
+      all_device = all_device && IsOnDevice(*d);
+      row.push_back(std::move(d));
+    }
+    if (all_device && batch.length >= kCoalesceRows / 4 && pending_rows_ == 0) {
+      ARROW_RETURN_NOT_OK(ConsumeDevice(row, batch.length));  // already resident and large: no staging
+    } else {
+      for (size_t i = 0; i < cols.size(); ++i) pending_[i].push_back(arrow::MakeArray(row[i]));
+      pending_rows_ += batch.length;
+      if (pending_rows_ >= kCoalesceRows) ARROW_RETURN_NOT_OK(Flush());
     }
     ++seen_;
     return MaybeFinish();
@@ -162,10 +234,94 @@ class AggregateNode : public DeviceNode {
   }
 
  private:
+  struct FusedDeleter {
+    void operator()(B2GroupBySumCount* g) const { b2_groupby_sumcount_destroy(g); }
+  };
+
+  // distinct input columns read by this node, keys first; also sizes pending_
+  std::vector<int> NeededColumns() {
+    if (needed_.empty()) {
+      for (int k : key_idx_) needed_.push_back(k);
+      for (auto& a : aggs_)
+        if (a.target >= 0 && std::find(needed_.begin(), needed_.end(), a.target) == needed_.end()) needed_.push_back(a.target);
+      pending_.resize(needed_.size());
+    }
+    return needed_;
+  }
+  int Slot(int column) const { return static_cast<int>(std::find(needed_.begin(), needed_.end(), column) - needed_.begin()); }
+
+  // concatenate the parked host chunks, one H2D copy per column, consume as ONE device batch
+  Status Flush() {
+    if (pending_rows_ == 0) return Status::OK();
+    std::vector<std::shared_ptr<arrow::ArrayData>> dev;
+    for (auto& chunks : pending_) {
+      std::shared_ptr<arrow::Array> whole;
+      if (chunks.size() == 1) whole = chunks[0];
+      else { ARROW_ASSIGN_OR_RAISE(whole, arrow::Concatenate(chunks, plan_->query_context()->memory_pool())); }
+      if (IsOnDevice(*whole->data())) dev.push_back(whole->data());
+      else { ARROW_ASSIGN_OR_RAISE(auto d, ToDevice(*whole->data(), rt_->memory_manager())); dev.push_back(std::move(d)); }
+      chunks.clear();
+    }
+    const int64_t rows = pending_rows_;
+    pending_rows_ = 0;
+    return ConsumeDevice(dev, rows);
+  }
+
+  // Consume, groupby_aggregate_node.cc:210-253, on one device batch (columns in NeededColumns() order)
+  Status ConsumeDevice(const std::vector<std::shared_ptr<arrow::ArrayData>>& cols, int64_t length) {
+    ++device_batches_;
+    if (fused_) {
+      B2Array k, v;
+      ARROW_RETURN_NOT_OK(DataToB2(*cols[Slot(key_idx_[0])], &k));
+      ARROW_RETURN_NOT_OK(DataToB2(*cols[Slot(fused_target_)], &v));
+      if (b2_groupby_sumcount_consume(fused_.get(), &k, &v, nullptr) != B2_OK)
+        return Status::UnknownError("b2_groupby_sumcount_consume: ", b2_last_error());
+      return Status::OK();
+    }
+    cp::ExecBatch keys({}, length);
+    for (int i : key_idx_) keys.values.emplace_back(cols[Slot(i)]);
+    ARROW_ASSIGN_OR_RAISE(Datum ids, grouper_->Consume(cp::ExecSpan(keys)));
+    for (auto& a : aggs_) {
+      ARROW_RETURN_NOT_OK(a.kernel->resize(a.kctx.get(), grouper_->num_groups()));
+      cp::ExecBatch in({}, length);
+      if (a.target >= 0) in.values.emplace_back(cols[Slot(a.target)]);
+      in.values.push_back(ids);
+      ARROW_RETURN_NOT_OK(a.kernel->consume(a.kctx.get(), cp::ExecSpan(in)));
+    }
+    return Status::OK();
+  }
+
   Status MaybeFinish() {
     if (total_ < 0 || seen_ < total_ || done_) return Status::OK();
     done_ = true;
+    NeededColumns();
+    ARROW_RETURN_NOT_OK(Flush());
     // Finalize, groupby_aggregate_node.cc:300-337: [keys..., aggregates...]
+    if (fused_) {
+      B2Array k, s, c;
+      if (b2_groupby_sumcount_finalize(fused_.get(), &k, &s, &c, nullptr) != B2_OK)
+        return Status::UnknownError("b2_groupby_sumcount_finalize: ", b2_last_error());
+      cp::ExecBatch out({}, k.length);
+      ARROW_ASSIGN_OR_RAISE(auto hk, ToHost(*AdoptOutput(rt_, k, output_schema_->field(0)->type())));
+      out.values.emplace_back(std::move(hk));
+      std::shared_ptr<arrow::ArrayData> hs, hc;
+      std::shared_ptr<arrow::DataType> sum_type;
+      for (size_t i = 0; i < aggs_.size(); ++i)
+        if (!aggs_[i].is_count) sum_type = output_schema_->field(static_cast<int>(key_idx_.size() + i))->type();
+      auto ds = AdoptOutput(rt_, s, sum_type ? sum_type : arrow::int64());  // adopt even if unused: the buffers are ours to free
+      auto dc = AdoptOutput(rt_, c, arrow::int64());
+      for (auto& a : aggs_) {
+        if (a.is_count) {
+          if (!hc) { ARROW_ASSIGN_OR_RAISE(hc, ToHost(*dc)); }
+          out.values.emplace_back(hc);
+        } else {
+          if (!hs) { ARROW_ASSIGN_OR_RAISE(hs, ToHost(*ds)); }
+          out.values.emplace_back(hs);
+        }
+      }
+      ARROW_RETURN_NOT_OK(output_->InputReceived(this, std::move(out)));
+      return output_->InputFinished(this, 1);
+    }
     ARROW_ASSIGN_OR_RAISE(cp::ExecBatch uniques, grouper_->GetUniques());
     cp::ExecBatch out({}, grouper_->num_groups());
     for (auto& k : uniques.values) {
@@ -185,6 +341,12 @@ class AggregateNode : public DeviceNode {
   std::vector<int> key_idx_;
   std::unique_ptr<cp::Grouper> grouper_;
   std::vector<Agg> aggs_;
+  std::unique_ptr<B2GroupBySumCount, FusedDeleter> fused_;
+  int fused_target_ = -1;
+  std::vector<int> needed_;
+  std::vector<arrow::ArrayVector> pending_;
+  int64_t pending_rows_ = 0;
+  int device_batches_ = 0;
   int seen_ = 0, total_ = -1;
   bool done_ = false;
 };

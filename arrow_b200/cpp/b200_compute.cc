@@ -715,7 +715,8 @@ static std::shared_ptr<DataType> HashAggOutType(int kind, const DataType& in) {
   switch (kind) {
     case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return arrow::int64();
     case B2_HASH_MEAN: return arrow::float64();
-    case B2_HASH_SUM:
+    case B2_HASH_ANY: case B2_HASH_ALL: return arrow::boolean();
+    case B2_HASH_SUM: case B2_HASH_PRODUCT:
       if (arrow::is_signed_integer(in.id())) return arrow::int64();
       if (arrow::is_unsigned_integer(in.id())) return arrow::uint64();
       return arrow::float64();
@@ -800,6 +801,8 @@ static Status AddHashAggregate(cp::FunctionRegistry* reg, Runtime* rt, const std
     ARROW_RETURN_NOT_OK(add({cp::InputType(arrow::uint32())}));
   } else if (kind == B2_HASH_COUNT) {
     ARROW_RETURN_NOT_OK(add({cp::InputType::Any(), cp::InputType(arrow::uint32())}));
+  } else if (kind == B2_HASH_ANY || kind == B2_HASH_ALL) {
+    ARROW_RETURN_NOT_OK(add({cp::InputType(arrow::boolean()), cp::InputType(arrow::uint32())}));
   } else {
     for (const auto& ty : NumericTypes()) ARROW_RETURN_NOT_OK(add({cp::InputType(ty), cp::InputType(arrow::uint32())}));
   }
@@ -886,7 +889,8 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   ARROW_RETURN_NOT_OK(AddScalarAggregates(reg, rt));
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},
                                               {"hash_count_all", B2_HASH_COUNT_ALL}, {"hash_mean", B2_HASH_MEAN},
-                                              {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX}};
+                                              {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX},
+                                              {"hash_product", B2_HASH_PRODUCT}, {"hash_any", B2_HASH_ANY}, {"hash_all", B2_HASH_ALL}};
   for (const auto& a : aggs) ARROW_RETURN_NOT_OK(AddHashAggregate(reg, rt, a.first, a.second));
   return Status::OK();
 }

@@ -11,8 +11,10 @@
 #include <arrow/compute/row/grouper.h>
 #include <arrow/acero/exec_plan.h>
 #include <arrow/acero/options.h>
+#include <arrow/c/bridge.h>
 #include <arrow/table.h>
 
+#include <chrono>
 #include <iostream>
 #include <random>
 
@@ -136,7 +138,40 @@ struct Harness {
   }
 };
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "--bench-groupby") {
+    // config 3 through the reference's own entry point: DeclarationToTable(table_source -> b200_aggregate) over a
+    // DEVICE-resident table handed over as one batch (the node consumes large device batches without staging).
+    namespace ac = arrow::acero;
+    const int64_t rows = argc > 2 ? atoll(argv[2]) : 100000000;
+    const int64_t groups = argc > 3 ? atoll(argv[3]) : 10000000;
+    const int reps = argc > 4 ? atoi(argv[4]) : 3;
+    auto rt = UNWRAP(arrow_b200::Runtime::Get(0));
+    CHECK_OK(arrow_b200::RegisterAceroNodes());
+    auto k = RandomNumeric<arrow::Int64Type>(rows, 0.0, 91, 0, groups - 1);
+    auto v = RandomNumeric<arrow::Int64Type>(rows, 0.1, 92, -100, 100);
+    auto dk = arrow::MakeArray(UNWRAP(arrow_b200::ToDevice(*k->data(), rt->memory_manager())));
+    auto dv = arrow::MakeArray(UNWRAP(arrow_b200::ToDevice(*v->data(), rt->memory_manager())));
+    auto schema = arrow::schema({arrow::field("k", arrow::int64()), arrow::field("v", arrow::int64())});
+    auto table = arrow::Table::Make(schema, {dk, dv});
+    std::vector<cp::Aggregate> aggs = {{"hash_sum", nullptr, "v", "v_sum"}, {"hash_count", nullptr, "v", "v_count"}};
+    double best = 1e30;
+    int64_t out_groups = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      ac::Declaration plan = ac::Declaration::Sequence({{"table_source", ac::TableSourceNodeOptions(table, rows)},
+                                                        {"b200_aggregate", ac::AggregateNodeOptions(aggs, {"k"})}});
+      auto t0 = std::chrono::steady_clock::now();
+      auto out = UNWRAP(ac::DeclarationToTable(std::move(plan), /*use_threads=*/false));
+      double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (r > 0 && s < best) best = s;
+      out_groups = out->num_rows();
+    }
+    printf("{\"bench\": \"DeclarationToTable(table_source -> b200_aggregate[hash_sum, hash_count]) on a device-resident table\", "
+           "\"rows\": %lld, \"groups\": %lld, \"best_ms\": %.3f, \"rows_per_s\": %.1f, \"note\": \"wall clock incl. plan setup, finalize and D2H of the group table\"}\n",
+           (long long)rows, (long long)out_groups, best * 1e3, rows / best);
+    return 0;
+  }
+
   CHECK_OK(cp::Initialize());
   auto rt_r = arrow_b200::Runtime::Get(0);
   if (!rt_r.ok()) {
@@ -300,7 +335,7 @@ int main() {
 
     // ---- hash aggregate kernels driven exactly as acero/aggregate_internal.cc:67-123 does ----
     auto vals = RandomNumeric<arrow::Int64Type>(50000, 0.1, 78, -100, 100);
-    for (const char* fn : {"hash_sum", "hash_count", "hash_min", "hash_max", "hash_mean"}) {
+    for (const char* fn : {"hash_sum", "hash_count", "hash_min", "hash_max", "hash_mean", "hash_product"}) {
       auto run = [&](cp::ExecContext* ctx, const Datum& v, const Datum& ids, uint32_t groups) -> Datum {
         auto function = UNWRAP(ctx->func_registry()->GetFunction(fn));
         auto kernel = static_cast<const cp::HashAggregateKernel*>(UNWRAP(function->DispatchExact({arrow::int64(), arrow::uint32()})));
@@ -340,6 +375,46 @@ int main() {
     }
     std::cout << "OK   host arrays pass through to the parent registry" << std::endl;
   }
+  // ---- C Device Data Interface round trip (c/bridge.h:192,238; c/abi.h:140-157) ----
+  {
+    // producer side: a device array computed by our kernels leaves through ExportDeviceArray with a sync event
+    cp::FilterOptions drop(cp::FilterOptions::DROP);
+    auto filtered = UNWRAP(cp::CallFunction("filter", {h.Dev(i64a), h.Dev(mask)}, &drop, &h.gpu_ctx));
+    struct ArrowDeviceArray c_arr;
+    struct ArrowSchema c_schema;
+    CHECK_OK(arrow_b200::ExportDeviceArray(*filtered.make_array(), h.rt->memory_manager(), &c_arr, &c_schema));
+    ++g_checks;
+    if (c_arr.device_type != ARROW_DEVICE_CUDA || c_arr.device_id != 0 || c_arr.sync_event == nullptr ||
+        c_arr.array.length != filtered.length() || c_arr.array.n_buffers != 2) {
+      std::cout << "FAIL ExportDeviceArray: device_type " << c_arr.device_type << " sync_event " << c_arr.sync_event << std::endl;
+      return 1;
+    }
+    // consumer side: zero-copy import (our stream waits on the producer's event), then run a kernel on it
+    auto type = UNWRAP(arrow::ImportType(&c_schema));
+    const void* exported_ptr = c_arr.array.buffers[1];
+    auto imported = UNWRAP(arrow_b200::ImportDeviceArray(&c_arr, type, h.rt->memory_manager()));
+    if (reinterpret_cast<const void*>(imported->data()->buffers[1]->address()) != exported_ptr || !arrow_b200::IsOnDevice(*imported->data())) {
+      std::cout << "FAIL ImportDeviceArray is not zero-copy" << std::endl;
+      return 1;
+    }
+    auto doubled = UNWRAP(cp::CallFunction("add", {Datum(imported), Datum(imported)}, nullptr, &h.gpu_ctx));
+    auto want_f = UNWRAP(cp::CallFunction("filter", {i64a, mask}, &drop, &h.cpu_ctx));
+    auto want_d = UNWRAP(cp::CallFunction("add", {want_f, want_f}, nullptr, &h.cpu_ctx));
+    if (!h.Host(doubled)->Equals(*want_d.make_array())) {
+      std::cout << "FAIL kernel on an imported ArrowDeviceArray" << std::endl;
+      return 1;
+    }
+    // SyncEvent / Stream objects of the device work on their own too (Device::MakeStream, MakeDeviceSyncEvent)
+    auto ev = UNWRAP(h.rt->memory_manager()->MakeDeviceSyncEvent());
+    auto st = UNWRAP(h.rt->device()->MakeStream());
+    CHECK_OK(ev->Record(*st));
+    CHECK_OK(st->WaitEvent(*ev));
+    CHECK_OK(ev->Wait());
+    CHECK_OK(st->Synchronize());
+    std::cout << "OK   ArrowDeviceArray export -> import round trip (ARROW_DEVICE_CUDA, sync event honoured, zero copy, " << imported->length()
+              << " rows) and a kernel on the imported array" << std::endl;
+  }
+
   // ---- Acero: the same Declarations with the stock node names and with the b200_ factories ----
   {
     namespace ac = arrow::acero;
@@ -376,6 +451,25 @@ int main() {
       return 1;
     }
     std::cout << "OK   b200_aggregate == aggregate (" << got->num_rows() << " groups over " << rows << " rows in 32Ki-row batches)" << std::endl;
+    // config 3's shape: one int64 key, hash_sum + hash_count over one column -> the node takes the fused
+    // b2_groupby_sumcount path (and B200_AGGREGATE_FUSED=0 forces the Grouper + aggregators path: both must agree)
+    for (const char* fused : {"1", "0"}) {
+      setenv("B200_AGGREGATE_FUSED", fused, 1);
+      std::vector<cp::Aggregate> aggs2 = {{"hash_sum", nullptr, "v", "v_sum"}, {"hash_count", nullptr, "v", "v_count"}};
+      auto want2 = sorted(run("aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs2, std::vector<arrow::FieldRef>{"k"})), "k");
+      auto got2 = sorted(run("b200_aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs2, std::vector<arrow::FieldRef>{"k"})), "k");
+      ++g_checks;
+      auto want2_sel = UNWRAP(want2->SelectColumns({UNWRAP(arrow::FieldRef("k").FindOne(*want2->schema())).indices()[0],
+                                                    UNWRAP(arrow::FieldRef("v_sum").FindOne(*want2->schema())).indices()[0],
+                                                    UNWRAP(arrow::FieldRef("v_count").FindOne(*want2->schema())).indices()[0]}));
+      if (!got2->Equals(*want2_sel)) {
+        std::cout << "FAIL b200_aggregate (sum+count, fused=" << fused << ")\n want " << want2_sel->ToString().substr(0, 600) << "\n got "
+                  << got2->ToString().substr(0, 600) << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_aggregate hash_sum+hash_count == aggregate (B200_AGGREGATE_FUSED=" << fused << ", " << got2->num_rows() << " groups)" << std::endl;
+    }
+    unsetenv("B200_AGGREGATE_FUSED");
     // filter: the predicate is an Expression bound against the nested registry
     auto pred = cp::greater(cp::call("add", {cp::field_ref("v"), cp::field_ref("k")}), cp::literal(int64_t(400)));
     auto fwant = run("filter", std::make_shared<ac::FilterNodeOptions>(pred));

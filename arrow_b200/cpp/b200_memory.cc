@@ -1,6 +1,7 @@
 // b200_memory.cc -- see b200_memory.h
 #include "b200_memory.h"
 
+#include <arrow/c/bridge.h>
 #include <arrow/io/interfaces.h>
 #include <arrow/util/logging.h>
 
@@ -41,7 +42,97 @@ class B200Buffer : public arrow::MutableBuffer {
   void* ptr_;
 };
 
+// the context's non-blocking stream (or a caller's cudaStream_t*) behind arrow::Device::Stream
+class B200Stream : public arrow::Device::Stream {
+ public:
+  B200Stream(B2Context* ctx, void* stream_ptr, release_fn_t release) : arrow::Device::Stream(stream_ptr, std::move(release)), ctx_(ctx) {}
+  void* cuda_stream() const { return stream_ ? *reinterpret_cast<void* const*>(stream_.get()) : nullptr; }
+  Status WaitEvent(const arrow::Device::SyncEvent& ev) override {
+    void* raw = const_cast<arrow::Device::SyncEvent&>(ev).get_raw();
+    if (!raw) return Status::OK();
+    B200_RETURN_NOT_OK(b2_stream_wait_event(ctx_, cuda_stream(), *reinterpret_cast<void**>(raw)));
+    return Status::OK();
+  }
+  Status Synchronize() const override {
+    B200_RETURN_NOT_OK(b2_sync(ctx_, cuda_stream()));
+    return Status::OK();
+  }
+
+ private:
+  B2Context* ctx_;
+};
+
+// cudaEvent_t* behind arrow::Device::SyncEvent (the layout ArrowDeviceArray.sync_event has for CUDA)
+class B200SyncEvent : public arrow::Device::SyncEvent {
+ public:
+  B200SyncEvent(B2Context* ctx, void* event_ptr, release_fn_t release) : arrow::Device::SyncEvent(event_ptr, std::move(release)), ctx_(ctx) {}
+  Status Wait() override {
+    B200_RETURN_NOT_OK(b2_event_synchronize(*reinterpret_cast<void**>(get_raw())));
+    return Status::OK();
+  }
+  Status Record(const arrow::Device::Stream& s) override {
+    const void* raw = s.get_raw();
+    void* stream = raw ? *reinterpret_cast<void* const*>(raw) : nullptr;
+    B200_RETURN_NOT_OK(b2_event_record(ctx_, *reinterpret_cast<void**>(get_raw()), stream));
+    return Status::OK();
+  }
+
+ private:
+  B2Context* ctx_;
+};
+
 }  // namespace
+
+Result<std::shared_ptr<arrow::Device::Stream>> B200Device::MakeStream() {
+  void** holder = new void*(b2_context_stream(ctx_));
+  return std::shared_ptr<arrow::Device::Stream>(new B200Stream(ctx_, holder, [](void* p) { delete reinterpret_cast<void**>(p); }));
+}
+
+Result<std::shared_ptr<arrow::Device::Stream>> B200Device::WrapStream(void* cuda_stream_ptr, arrow::Device::Stream::release_fn_t release) {
+  return std::shared_ptr<arrow::Device::Stream>(new B200Stream(ctx_, cuda_stream_ptr, release ? std::move(release) : [](void*) {}));
+}
+
+Result<std::shared_ptr<arrow::Device::SyncEvent>> B200MemoryManager::MakeDeviceSyncEvent() {
+  void* ev = nullptr;
+  B200_RETURN_NOT_OK(b2_event_create(context(), &ev));
+  void** holder = new void*(ev);
+  return std::shared_ptr<arrow::Device::SyncEvent>(new B200SyncEvent(context(), holder, [](void* p) {
+    void** h = reinterpret_cast<void**>(p);
+    b2_event_destroy(*h);
+    delete h;
+  }));
+}
+
+Result<std::shared_ptr<arrow::Device::SyncEvent>> B200MemoryManager::WrapDeviceSyncEvent(
+    void* sync_event, arrow::Device::SyncEvent::release_fn_t release_sync_event) {
+  return std::shared_ptr<arrow::Device::SyncEvent>(
+      new B200SyncEvent(context(), sync_event, release_sync_event ? std::move(release_sync_event) : [](void*) {}));
+}
+
+Status ExportDeviceArray(const arrow::Array& array, const std::shared_ptr<arrow::MemoryManager>& mm, struct ArrowDeviceArray* out,
+                         struct ArrowSchema* out_schema) {
+  ARROW_ASSIGN_OR_RAISE(auto sync, mm->MakeDeviceSyncEvent());
+  ARROW_ASSIGN_OR_RAISE(auto stream, mm->device()->MakeStream());
+  ARROW_RETURN_NOT_OK(sync->Record(*stream));
+  return arrow::ExportDeviceArray(array, std::move(sync), out, out_schema);
+}
+
+Result<std::shared_ptr<arrow::Array>> ImportDeviceArray(struct ArrowDeviceArray* array, std::shared_ptr<arrow::DataType> type,
+                                                        const std::shared_ptr<arrow::MemoryManager>& mm) {
+  if (array->device_type != ARROW_DEVICE_CUDA && array->device_type != ARROW_DEVICE_CUDA_MANAGED)
+    return Status::Invalid("arrow_b200::ImportDeviceArray: device_type ", array->device_type, " is not CUDA memory");
+  void* event_ptr = array->sync_event;
+  void* event = event_ptr ? *reinterpret_cast<void**>(event_ptr) : nullptr;
+  auto* b2mm = static_cast<B200MemoryManager*>(mm.get());
+  // order our stream behind the producer BEFORE the structure (and with it the event) can be released
+  if (event) B200_RETURN_NOT_OK(b2_stream_wait_event(b2mm->context(), nullptr, event));
+  auto mapper = [mm](ArrowDeviceType, int64_t) -> Result<std::shared_ptr<arrow::MemoryManager>> { return mm; };
+  ARROW_ASSIGN_OR_RAISE(auto imported, arrow::ImportDeviceArray(array, std::move(type), mapper));
+  // a device array must carry an explicit null_count (ArrayData::GetNullCount would read the bitmap on the host)
+  if (imported->data()->null_count.load() == arrow::kUnknownNullCount && imported->data()->buffers[0] == nullptr)
+    imported->data()->null_count = 0;
+  return imported;
+}
 
 Result<std::shared_ptr<B200Device>> B200Device::Make(int device_number) {
   B2Context* ctx = nullptr;

@@ -9,6 +9,7 @@
 // read via ArraySpan.buffers[i].owner (array/data.h:525-532).
 #pragma once
 #include <arrow/api.h>
+#include <arrow/c/abi.h>
 #include <arrow/device.h>
 
 #include "arrow_b200.h"
@@ -28,6 +29,10 @@ class B200Device : public arrow::Device {
   std::shared_ptr<arrow::MemoryManager> default_memory_manager() override;
   arrow::DeviceAllocationType device_type() const override { return arrow::DeviceAllocationType::kCUDA; }
   B2Context* context() const { return ctx_; }
+  // the context's own stream as an arrow::Device::Stream (SyncEvent::Record / Stream::WaitEvent operate on it)
+  arrow::Result<std::shared_ptr<arrow::Device::Stream>> MakeStream() override;
+  arrow::Result<std::shared_ptr<arrow::Device::Stream>> WrapStream(void* cuda_stream_ptr,
+                                                                   arrow::Device::Stream::release_fn_t release) override;
 
  private:
   explicit B200Device(int n, B2Context* ctx) : arrow::Device(/*is_cpu=*/false), device_number_(n), ctx_(ctx) {}
@@ -45,6 +50,11 @@ class B200MemoryManager : public arrow::MemoryManager {
   B2Context* context() const { return static_cast<B200Device*>(device_.get())->context(); }
   // take ownership of a pool pointer returned by a C-ABI entry point
   std::shared_ptr<arrow::Buffer> Adopt(const void* ptr, int64_t size);
+  // C Device Data Interface synchronisation: a cudaEvent_t behind arrow::Device::SyncEvent (device.h:142-165);
+  // get_raw() is the cudaEvent_t* that ArrowDeviceArray.sync_event carries for ARROW_DEVICE_CUDA
+  arrow::Result<std::shared_ptr<arrow::Device::SyncEvent>> MakeDeviceSyncEvent() override;
+  arrow::Result<std::shared_ptr<arrow::Device::SyncEvent>> WrapDeviceSyncEvent(
+      void* sync_event, arrow::Device::SyncEvent::release_fn_t release_sync_event) override;
 
  protected:
   arrow::Result<std::shared_ptr<arrow::Buffer>> CopyBufferFrom(const std::shared_ptr<arrow::Buffer>& buf,
@@ -70,5 +80,16 @@ arrow::Result<std::shared_ptr<arrow::ArrayData>> ToDevice(const arrow::ArrayData
                                                           const std::shared_ptr<arrow::MemoryManager>& mm);
 arrow::Result<std::shared_ptr<arrow::ArrayData>> ToHost(const arrow::ArrayData& device);
 bool IsOnDevice(const arrow::ArrayData& data);
+
+// ---- C Device Data Interface (c/bridge.h:192,238) for pool-backed arrays ----
+// Export: records a fresh event on the context stream (every kernel that produced the buffers was ordered
+// on it) and hands the array out as an ArrowDeviceArray{device_type = ARROW_DEVICE_CUDA, sync_event = cudaEvent_t*};
+// the exported structure keeps the buffers and the event alive until its release callback runs.
+arrow::Status ExportDeviceArray(const arrow::Array& array, const std::shared_ptr<arrow::MemoryManager>& mm,
+                                struct ArrowDeviceArray* out, struct ArrowSchema* out_schema = nullptr);
+// Import: wraps the producer's device pointers (zero copy) in buffers of OUR memory manager and makes the
+// context stream wait on the producer's sync_event before any kernel of ours can touch them.
+arrow::Result<std::shared_ptr<arrow::Array>> ImportDeviceArray(struct ArrowDeviceArray* array, std::shared_ptr<arrow::DataType> type,
+                                                               const std::shared_ptr<arrow::MemoryManager>& mm);
 
 }  // namespace arrow_b200

@@ -277,6 +277,37 @@ int b2_host_free(void* ptr) {
   return B2_OK;
 }
 
+// ---- events: what ArrowDeviceArray.sync_event points at for ARROW_DEVICE_CUDA is a cudaEvent_t ----
+int b2_event_create(B2Context* ctx, void** out_event) {
+  if (!ctx || !out_event) return set_error(B2_INVALID, "b2_event_create: null argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaEvent_t e;
+  B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *out_event = e;
+  return B2_OK;
+}
+int b2_event_destroy(void* event) {
+  if (event) B2_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return B2_OK;
+}
+int b2_event_record(B2Context* ctx, void* event, void* stream) {
+  if (!ctx || !event) return set_error(B2_INVALID, "b2_event_record: null argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), ctx->pick(stream)));
+  return B2_OK;
+}
+int b2_event_synchronize(void* event) {
+  if (!event) return set_error(B2_INVALID, "b2_event_synchronize: null argument");
+  B2_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+  return B2_OK;
+}
+int b2_stream_wait_event(B2Context* ctx, void* stream, void* event) {
+  if (!ctx || !event) return set_error(B2_INVALID, "b2_stream_wait_event: null argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaStreamWaitEvent(ctx->pick(stream), static_cast<cudaEvent_t>(event), 0));
+  return B2_OK;
+}
+
 const char* b2_last_error(void) { return b2::t_last_error.c_str(); }
 const char* b2_version(void) { return "arrow_b200 0.1.0 (sm_100a)"; }
 int64_t b2_launch_count(void) { return b2::g_launches.load(); }

@@ -7,6 +7,8 @@
 //                                      kernels/hash_aggregate_numeric.cc:44-190,274-295,359-434
 //   GroupedCountImpl / GroupedCountAllImpl      kernels/hash_aggregate.cc:61-272
 //   GroupedMinMaxImpl (hash_min / hash_max)     kernels/hash_aggregate.cc:330-420
+//   GroupedProductImpl (hash_product)           kernels/hash_aggregate_numeric.cc:311-335
+//   GroupedAnyImpl / GroupedAllImpl             kernels/hash_aggregate.cc:1232-1397
 //   VisitGroupedValues                          kernels/hash_aggregate_internal.h:148-171
 // Semantics kept: integer sums accumulate in int64/uint64 with wrap-around (unsigned
 // add), float sums and all means in double; count modes ONLY_VALID/ONLY_NULL/ALL;
@@ -120,6 +122,24 @@ __global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __rest
         atomicAdd(&st.reduced[g], static_cast<unsigned long long>(v));
       }
       atomicAdd(&st.counts[g], 1ull);
+    } else if (KIND == B2_HASH_PRODUCT) {
+      // no hardware multiply-atomic: CAS loop.  Integers multiply mod 2^64 (MultiplyTraits, wrap-around as the
+      // reference's to_unsigned product) so the result is order independent and bit-exact; floats in double.
+      unsigned long long* p = &st.reduced[g];
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p), assumed;
+      do {
+        assumed = old;
+        unsigned long long next;
+        if (std::is_floating_point<T>::value) {
+          next = static_cast<unsigned long long>(__double_as_longlong(__longlong_as_double((long long)assumed) * static_cast<double>(v)));
+        } else if (std::is_signed<T>::value) {
+          next = assumed * static_cast<unsigned long long>(static_cast<long long>(v));
+        } else {
+          next = assumed * static_cast<unsigned long long>(v);
+        }
+        old = atomicCAS(p, assumed, next);
+      } while (old != assumed);
+      atomicAdd(&st.counts[g], 1ull);
     } else {  // MIN / MAX
       if (v == v) {  // fmin/fmax skip NaN
         if (KIND == B2_HASH_MIN) atomicMin(&st.reduced[g], minmax_encode<T>(v));
@@ -128,6 +148,53 @@ __global__ void __launch_bounds__(kBlock) hashagg_consume_kernel(const T* __rest
       atomicAdd(&st.counts[g], 1ull);
     }
   }
+}
+
+// hash_any / hash_all over a bit-packed boolean column (GroupedAnyImpl / GroupedAllImpl, hash_aggregate.cc:1232-1397):
+// reduced[g] is 0/1; any = OR (starts 0), all = AND (starts 1); a null row only clears the group's no_nulls flag
+__global__ void __launch_bounds__(kBlock) hashagg_bool_kernel(BitmapReader data, BitmapReader valid, const uint32_t* __restrict__ ids,
+                                                              int64_t n, AggState st, int kind) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint32_t g = __ldcs(ids + i);
+    if (!valid.bit(i)) {
+      st.flags[g] |= 1;
+      continue;
+    }
+    const bool v = data.bit(i);
+    if (kind == B2_HASH_ANY) {
+      if (v) st.reduced[g] = 1ull;   // benign race: every writer stores the same value
+    } else if (!v) {
+      st.reduced[g] = 0ull;
+    }
+    atomicAdd(&st.counts[g], 1ull);
+  }
+}
+
+// any / all -> boolean column.  Validity: count >= min_count, and with skip_nulls = false a group that saw a null
+// is null unless the value is already decided (any: true; all: false) -- AdjustForMinCount, hash_aggregate.cc:1376-1396
+__global__ void __launch_bounds__(kBlock) hashagg_finalize_bool_kernel(AggState st, int64_t n, int kind, int skip_nulls,
+                                                                       uint32_t min_count, uint32_t* out_data, uint32_t* out_validity,
+                                                                       int64_t* valid_count) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    const int64_t g = (w << 5) + lane_id();
+    bool value = false, valid = false;
+    if (g < n) {
+      value = st.reduced[g] != 0ull;
+      const bool saw_null = st.flags[g] & 1;
+      valid = st.counts[g] >= min_count;
+      if (!skip_nulls) valid = valid && (!saw_null || (kind == B2_HASH_ANY ? value : !value));
+    }
+    const unsigned dword = __ballot_sync(0xffffffffu, value), vword = __ballot_sync(0xffffffffu, valid);
+    if (lane_id() == 0) {
+      out_data[w] = dword;
+      out_validity[w] = vword;
+      local += __popc(vword);
+    }
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
 }
 
 // Few groups (<= kPrivateMaxGroups): millions of rows update the same handful of state words, and
@@ -237,6 +304,20 @@ __global__ void __launch_bounds__(kBlock) hashagg_merge_kernel(AggState dst, Agg
       atomicMin(&dst.reduced[g], src.reduced[i]);
     } else if (kind == B2_HASH_MAX) {
       atomicMax(&dst.reduced[g], src.reduced[i]);
+    } else if (kind == B2_HASH_ANY) {
+      atomicOr(&dst.reduced[g], src.reduced[i]);
+    } else if (kind == B2_HASH_ALL) {
+      atomicAnd(&dst.reduced[g], src.reduced[i]);
+    } else if (kind == B2_HASH_PRODUCT) {
+      unsigned long long* p = &dst.reduced[g];
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p), assumed;
+      do {
+        assumed = old;
+        const unsigned long long next = acc == ACC_F64
+            ? static_cast<unsigned long long>(__double_as_longlong(__longlong_as_double((long long)assumed) * __longlong_as_double((long long)src.reduced[i])))
+            : assumed * src.reduced[i];
+        old = atomicCAS(p, assumed, next);
+      } while (old != assumed);
     }
   }
 }
@@ -258,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) hashagg_finalize_kernel(AggState st, i
       if (kind == B2_HASH_COUNT || kind == B2_HASH_COUNT_ALL) {
         static_cast<long long*>(out)[g] = static_cast<long long>(c);
         valid = true;
-      } else if (kind == B2_HASH_SUM) {
+      } else if (kind == B2_HASH_SUM || kind == B2_HASH_PRODUCT) {
         valid = c >= min_count && (skip_nulls || !saw_null);
         static_cast<unsigned long long*>(out)[g] = r;  // int64 / uint64 / double share the bits
       } else if (kind == B2_HASH_MEAN) {
@@ -318,7 +399,9 @@ static unsigned long long agg_identity(const B2HashAgg* a) {
   const bool flt = a->acc == ACC_F64;
   if (a->kind == B2_HASH_MIN) return flt ? 0xfff0000000000000ull : ~0ull;
   if (a->kind == B2_HASH_MAX) return flt ? 0x000fffffffffffffull : 0ull;
-  return 0ull;  // sum / mean: 0 (== 0.0)
+  if (a->kind == B2_HASH_PRODUCT) return flt ? 0x3ff0000000000000ull : 1ull;  // MultiplyTraits::one
+  if (a->kind == B2_HASH_ALL) return 1ull;
+  return 0ull;  // sum / mean: 0 (== 0.0); any: false
 }
 
 template <typename T>
@@ -333,7 +416,7 @@ static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* id
   // DRAM sector read-modify-write (47 ms per 1B rows at 10M groups).  Large batches are
   // therefore consumed in BANDS of group ids whose state stays L2-resident, re-streaming the
   // ids (and the values of the band's rows) once per band: 2 bands at 10M groups = 20 ms.
-  if (a->num_groups <= kPrivateMaxGroups && n >= (1 << 14)) {
+  if (a->num_groups <= kPrivateMaxGroups && n >= (1 << 14) && a->kind != B2_HASH_PRODUCT) {
     const int g = (int)a->num_groups;
     const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);  // few CTAs: each flushes the whole state once
     switch (a->kind) {
@@ -361,6 +444,7 @@ static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* id
       case B2_HASH_MEAN: hashagg_consume_kernel<T, B2_HASH_MEAN><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0, lo, hi); break;
       case B2_HASH_MIN: hashagg_consume_kernel<T, B2_HASH_MIN><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0, lo, hi); break;
       case B2_HASH_MAX: hashagg_consume_kernel<T, B2_HASH_MAX><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0, lo, hi); break;
+      case B2_HASH_PRODUCT: hashagg_consume_kernel<T, B2_HASH_PRODUCT><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, 0, lo, hi); break;
       case B2_HASH_COUNT:
         hashagg_consume_kernel<T, B2_HASH_COUNT><<<grid, kBlock, 0, s>>>(v, valid, id, n, a->st, a->opt.count_mode, lo, hi);
         break;
@@ -376,10 +460,13 @@ extern "C" {
 int b2_hashagg_create(B2Context* ctx, int kind, int32_t value_type, const B2HashAggOptions* options,
                       B2HashAgg** out) {
   if (!ctx || !out) return set_error(B2_INVALID, "b2_hashagg_create: null argument");
-  if (kind < B2_HASH_SUM || kind > B2_HASH_MAX)
+  if (kind < B2_HASH_SUM || kind > B2_HASH_ALL)
     return set_error(B2_NOT_IMPLEMENTED, "hash aggregate kind %d is not implemented", kind);
-  if (kind != B2_HASH_COUNT_ALL && kind != B2_HASH_COUNT && !type_is_numeric(value_type))
+  if (kind == B2_HASH_ANY || kind == B2_HASH_ALL) {
+    if (value_type != B2_BOOL) return set_error(B2_NOT_IMPLEMENTED, "hash_any / hash_all need a boolean column (type id %d)", value_type);
+  } else if (kind != B2_HASH_COUNT_ALL && kind != B2_HASH_COUNT && !type_is_numeric(value_type)) {
     return set_error(B2_NOT_IMPLEMENTED, "hash aggregate over value type id %d", value_type);
+  }
   B2HashAgg* a = new B2HashAgg();
   a->ctx = ctx;
   a->kind = kind;
@@ -406,7 +493,8 @@ int32_t b2_hashagg_out_type(const B2HashAgg* a) {
   switch (a->kind) {
     case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return B2_INT64;
     case B2_HASH_MEAN: return B2_DOUBLE;
-    case B2_HASH_SUM: return a->acc == ACC_I64 ? B2_INT64 : a->acc == ACC_U64 ? B2_UINT64 : B2_DOUBLE;
+    case B2_HASH_SUM: case B2_HASH_PRODUCT: return a->acc == ACC_I64 ? B2_INT64 : a->acc == ACC_U64 ? B2_UINT64 : B2_DOUBLE;
+    case B2_HASH_ANY: case B2_HASH_ALL: return B2_BOOL;
     default: return a->value_type;
   }
 }
@@ -485,6 +573,13 @@ int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, 
   }
   if (values->type != a->value_type && a->kind != B2_HASH_COUNT)
     return set_error(B2_TYPE_ERROR, "hash aggregate was created for type id %d, got %d", a->value_type, values->type);
+  if (a->kind == B2_HASH_ANY || a->kind == B2_HASH_ALL) {
+    BitmapReader data(values->data, values->offset, n);
+    BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+    hashagg_bool_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(data, valid, id, n, a->st, a->kind);
+    B2_LAUNCHED();
+    return B2_OK;
+  }
   switch (values->type) {
     case B2_INT8: return launch_consume<int8_t>(a, values, ids, s);
     case B2_UINT8: return launch_consume<uint8_t>(a, values, ids, s);
@@ -525,6 +620,24 @@ int b2_hashagg_finalize(B2HashAgg* a, B2Array* out, void* stream) {
   const int64_t n = a->num_groups;
   const int out_type = b2_hashagg_out_type(a);
   Temp data(ctx, s), bits(ctx, s);
+  if (out_type == B2_BOOL) {
+    B2_RETURN_NOT_OK(data.alloc(bitmap_alloc_bytes(n)));
+    int64_t bnulls = 0;
+    if (n > 0) {
+      B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
+      B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
+      B2_CUDA(cudaMemsetAsync(data.ptr, 0, bitmap_alloc_bytes(n), s));
+      ScalarSlot slot(ctx);
+      B2_RETURN_NOT_OK(slot.zero(s));
+      hashagg_finalize_bool_kernel<<<grid_for(n, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+          a->st, n, a->kind, a->opt.skip_nulls, a->opt.min_count, data.as<uint32_t>(), bits.as<uint32_t>(), slot.dev());
+      B2_LAUNCHED();
+      B2_RETURN_NOT_OK(slot.fetch(s));
+      bnulls = n - slot.host()[0];
+    }
+    fill_out(out, B2_BOOL, n, bnulls, bnulls ? bits.release() : nullptr, data.release());
+    return B2_OK;
+  }
   B2_RETURN_NOT_OK(data.alloc((size_t)n * type_width(out_type)));
   int64_t nulls = 0;
   if (n > 0) {

@@ -409,7 +409,7 @@ def run_configs(env, n):
         return g.finalize()
 
     def unfused():
-        return bc.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None)])
+        return bc.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None)], fused=False)
 
     # the independent answer: torch index_add_ / bincount on the same device columns
     want_cnt = torch.zeros(groups, dtype=I64, device="cuda")
@@ -664,7 +664,8 @@ def run_multi_gpu(env, n_total, reps):
     # ---- config 4: SortIndices ----
     keys_t, _, bits_t, k_nulls = gen_columns("sort")
     keys = DeviceArray.from_pointers(ctx, pa.int64(), n_local, keys_t.data_ptr(), validity_ptr=bits_t.data_ptr(), null_count=k_nulls)
-    (seg, nulls_idx, skeys), ms, xms, xbytes = leg(lambda: d.sort_indices(keys, ops, xchg, return_keys=True))
+    _, ms, xms, xbytes = leg(lambda: d.sort_indices(keys, ops, xchg))
+    seg, nulls_idx, skeys = d.sort_indices(keys, ops, xchg, return_keys=True)  # untimed: also returns the keys in sorted order
     valid = unpack_bits(torch, bits_t, n_local)
     grow = torch.arange(row0, row1, dtype=I64, device="cuda")
     in_pair = int((mix64(torch, grow) * keys_t * valid.to(I64)).sum().item())

@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--only", default="c1,cmp,c3,c4,c5,f1")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--fused-only", action="store_true", help="c3: stop after the fused group-by")
     ap.add_argument("--groups", type=int, default=0, help="c3: number of distinct keys (default 10M at >= 100M rows)")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -105,16 +106,22 @@ def main():
         keys = DeviceArray.from_pointers(ctx, pa.int64(), n, keys_t.data_ptr())
         vals = DeviceArray.from_pointers(ctx, pa.int64(), n, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
 
+        paths = {}
+
         def fused():
             g = bc.GroupBySumCount(pa.int64(), pa.int64(), expected_groups=groups, ctx=ctx)
             g.consume(keys, vals)
+            paths["counts"] = g.path_counts()
             return g.finalize()
         ms = timed(stream, fused, args.reps, warmup=1)
         ng = len(fused()[0])
-        report("c3 group-by sum+count (fused table)", n, ms, n * 16.125 + ng * 24.25, {"groups": ng})
+        report("c3 group-by sum+count (fused table)", n, ms, n * 16.125 + ng * 24.25,
+               {"groups": ng, "chunks_compact_general_atomic": list(paths["counts"])})
+        if args.fused_only:
+            return
 
         def unfused():
-            return bc.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None)])
+            return bc.group_by([keys], [("hash_sum", vals, None), ("hash_count", vals, None)], fused=False)
         ms = timed(stream, unfused, max(1, args.reps - 1), warmup=1)
         report("c3 group-by sum+count (Grouper + 2 HashAggregators)", n, ms, n * 16.125 + ng * 24.25, {"groups": ng})
         del keys, vals, keys_t, vals_t, vvalid_t

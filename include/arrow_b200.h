@@ -134,6 +134,15 @@ B2_API int b2_sync(B2Context* ctx, void* stream);
 B2_API int b2_memcpy_h2d(B2Context* ctx, void* dst, const void* src, size_t n, void* stream);
 B2_API int b2_memcpy_d2h(B2Context* ctx, void* dst, const void* src, size_t n, void* stream);
 B2_API int b2_memset(B2Context* ctx, void* dst, int byte, size_t n, void* stream);
+/* Events (cudaEvent_t as void*): the synchronisation object of the C Device Data Interface --
+ * ArrowDeviceArray.sync_event is a cudaEvent_t* for ARROW_DEVICE_CUDA (c/abi.h:140-157); the producer
+ * records it after the last kernel that writes the buffers, the consumer makes its stream wait on it
+ * (arrow::Device::SyncEvent / Stream::WaitEvent, device.h:86-165). */
+B2_API int b2_event_create(B2Context* ctx, void** out_event);
+B2_API int b2_event_destroy(void* event);
+B2_API int b2_event_record(B2Context* ctx, void* event, void* stream);
+B2_API int b2_event_synchronize(void* event);
+B2_API int b2_stream_wait_event(B2Context* ctx, void* stream, void* event);
 /* pinned host staging (CudaHostBuffer, cuda_memory.h:113) */
 B2_API int b2_host_alloc(size_t nbytes, void** out);
 B2_API int b2_host_free(void* ptr);
@@ -351,7 +360,9 @@ typedef enum B2HashAggKind {
   B2_HASH_MEAN = 3,
   B2_HASH_MIN = 4,
   B2_HASH_MAX = 5,
-  B2_HASH_PRODUCT = 6
+  B2_HASH_PRODUCT = 6, /* GroupedProductImpl, hash_aggregate_numeric.cc:311-335 (integers wrap mod 2^64) */
+  B2_HASH_ANY = 7,     /* GroupedAnyImpl / GroupedAllImpl over a B2_BOOL column, hash_aggregate.cc:1232-1397 */
+  B2_HASH_ALL = 8
 } B2HashAggKind;
 typedef struct B2HashAggOptions {
   int32_t skip_nulls;  /* ScalarAggregateOptions (api_aggregate.h:48-50), default 1 */

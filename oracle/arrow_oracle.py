@@ -597,6 +597,21 @@ def hash_aggregate(function: str, vals, ids: pa.Array, num_groups: int, *, skip_
         with np.errstate(all="ignore"):
             np.add.at(acc, g[valid], v[valid].astype(dt))  # row order; integer adds wrap
         return make_array(t, acc, ok)
+    if function == "hash_product":   # GroupedProductImpl, hash_aggregate_numeric.cc:311-335: integers wrap mod 2^64
+        t = _sum_type(vals.type)
+        dt = np_dtype(t)
+        acc = np.ones(num_groups, dtype=dt)
+        with np.errstate(all="ignore"):
+            np.multiply.at(acc, g[valid], v[valid].astype(dt))
+        return make_array(t, acc, ok)
+    if function in ("hash_any", "hash_all"):   # GroupedBooleanAggregator, hash_aggregate.cc:1232-1397
+        hit = v[valid] if function == "hash_any" else ~v[valid]
+        seen = np.bincount(g[valid][hit], minlength=num_groups) > 0
+        out = seen if function == "hash_any" else ~seen
+        ok = counts >= min_count
+        if not skip_nulls:   # a null leaves the group undecided unless the value is already forced (Kleene)
+            ok &= ~saw_null | (out if function == "hash_any" else ~out)
+        return make_array(pa.bool_(), out, ok)
     if function == "hash_mean":
         acc = np.zeros(num_groups, dtype=np.float64)
         np.add.at(acc, g[valid], v[valid].astype(np.float64))
