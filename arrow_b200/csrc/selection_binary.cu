@@ -220,6 +220,78 @@ __device__ __forceinline__ void copy_tile_bytes(const uint8_t* __restrict__ src,
   }
 }
 
+// ---- staged copy: row-driven gather into shared memory, chunk-driven coalesced write-out -------------
+// The chunk-driven copy above spends ~700 thread-instructions per kept 16-byte string (a coarse-index lookup,
+// a binary search and two funnel-shifted segment merges PER OUTPUT CHUNK; profiles/binfilter_prof_r01: issue
+// bound at 11 warp-instructions per row).  Here every thread takes whole ROWS instead: it fetches the row with
+// aligned 8-byte loads, shifts each 8-byte group to the byte position the row has in the tile's output range
+// and ORs the (at most three) 32-bit words into a zero-initialised shared staging buffer -- neighbouring rows
+// share boundary words, native ATOMS.OR merges them without byte stores.  The staged range is then written with
+// aligned 16-byte stores (the staging offset is congruent to the global address mod 16) and re-zeroed.  Ranges
+// larger than the buffer are processed in rounds; a row that straddles a round boundary is clipped.
+constexpr int kStageBytes = 36864;
+constexpr int kStageRound = kStageBytes - 32;  // output bytes per round (multiple of 16; 15 bytes of skew + one spill word fit)
+
+__device__ __forceinline__ void stage_row_bytes(const uint8_t* g, uint32_t* stage_words, uint32_t so, uint32_t n) {
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(reinterpret_cast<uintptr_t>(g) & ~uintptr_t(7));
+  const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(g) & 7) * 8;
+  unsigned long long w0 = __ldg(q);
+  for (uint32_t done = 0; done < n; done += 8) {
+    const uint32_t cnt = n - done < 8u ? n - done : 8u;
+    unsigned long long w1 = 0;
+    if (sh + cnt * 8 > 64 || done + 8 < n) w1 = __ldg(q + (done >> 3) + 1);  // only words that hold bytes of this row
+    unsigned long long v = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    w0 = w1;
+    if (cnt < 8) v &= (1ull << (cnt * 8)) - 1ull;
+    const uint32_t o = so + done;
+    const unsigned a = (o & 3u) * 8;
+    uint32_t* w = stage_words + (o >> 2);
+    const uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    const uint32_t x0 = lo << a, x1 = a ? (hi << a) | (lo >> (32 - a)) : hi, x2 = a ? hi >> (32 - a) : 0u;
+    if (x0) atomicOr(w, x0);
+    if (x1) atomicOr(w + 1, x1);
+    if (x2) atomicOr(w + 2, x2);
+  }
+}
+
+template <typename SrcT>
+__device__ __forceinline__ void copy_tile_bytes_staged(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t out_base,
+                                                       int64_t tile_bytes, const uint32_t* s_out, const SrcT* s_src, int n_rows,
+                                                       uint4* stage /* kStageBytes + 16, zero on entry, zero on exit */) {
+  if (tile_bytes == 0) return;
+  uint8_t* d0 = dst + out_base;
+  const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(d0) & 15);
+  uint32_t* words = reinterpret_cast<uint32_t*>(stage);
+  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(stage);
+  for (int64_t base = 0; base < tile_bytes; base += kStageRound) {
+    const int64_t end = base + kStageRound < tile_bytes ? base + kStageRound : tile_bytes;
+    for (int j = threadIdx.x; j < n_rows; j += blockDim.x) {
+      const int64_t a = s_out[j], b = s_out[j + 1];
+      if (b <= base || a >= end || a == b) continue;
+      const int64_t lo = a > base ? a : base, hi = b < end ? b : end;
+      stage_row_bytes(src + static_cast<int64_t>(s_src[j]) + (lo - a), words, m + static_cast<uint32_t>(lo - base),
+                      static_cast<uint32_t>(hi - lo));
+    }
+    __syncthreads();
+    // write-out: staging offset of output byte p is m + (p - base), congruent to its global address mod 16
+    const uint32_t len = static_cast<uint32_t>(end - base);
+    uint32_t head = (16u - m) & 15u;
+    if (head > len) head = len;
+    const uint32_t chunks = (len - head) >> 4;
+    const uint32_t tail0 = head + (chunks << 4);
+    uint8_t* g0 = d0 + base;
+    for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x)
+      *reinterpret_cast<uint4*>(g0 + head + (c << 4)) = stage[(m + head + (c << 4)) >> 4];
+    for (uint32_t e = threadIdx.x; e < head + (len - tail0); e += blockDim.x) {
+      const uint32_t p = e < head ? e : tail0 + (e - head);
+      g0[p] = sbytes[m + p];
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < ((m + len + 4 + 15) >> 4); c += blockDim.x) stage[c] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Filter
 // ------------------------------------------------------------------------------------------
@@ -234,10 +306,14 @@ struct BinFilterArgs {
   uint8_t* out_data;
   uint32_t* out_validity;  // zero-initialised or NULL
   int64_t n;
+  bool staged;             // copy pass: row-driven staged copy (dynamic shared memory = kStageBytes + 16)
 };
 
 template <typename OffT, bool COPY, bool HAS_VALID>
 __global__ void __launch_bounds__(kBinThreads) filter_binary_kernel(BinFilterArgs<OffT> a) {
+  extern __shared__ uint4 s_stage[];
+  if (COPY && a.staged)
+    for (int i = threadIdx.x; i < (kStageBytes + 16) / 16; i += kBinThreads) s_stage[i] = make_uint4(0, 0, 0, 0);
   __shared__ uint64_t s_sel[kTileWords];
   __shared__ uint64_t s_ov[kTileWords];
   __shared__ uint32_t s_prefix[kTileWords];
@@ -340,7 +416,8 @@ __global__ void __launch_bounds__(kBinThreads) filter_binary_kernel(BinFilterArg
     if (tile == gridDim.x - 1) a.out_offsets[out_row_base + n_rows] = static_cast<OffT>(byte_base + total);
   }
   __syncthreads();
-  copy_tile_bytes<uint32_t>(a.data + tile_src0, a.data, a.out_data, byte_base, total, s_out, s_src, n_rows);
+  if (a.staged) copy_tile_bytes_staged<uint32_t>(a.data + tile_src0, a.out_data, byte_base, total, s_out, s_src, n_rows, s_stage);
+  else copy_tile_bytes<uint32_t>(a.data + tile_src0, a.data, a.out_data, byte_base, total, s_out, s_src, n_rows);
   if (HAS_VALID) {
     const unsigned bit_base = static_cast<unsigned>(out_row_base & 31);
     const unsigned q_end = bit_base + n_rows;
@@ -352,6 +429,12 @@ __global__ void __launch_bounds__(kBinThreads) filter_binary_kernel(BinFilterArg
       else if (wv) atomicOr(&gw[i], wv);
     }
   }
+}
+
+// B2_BINARY_STAGED=0 selects the chunk-driven copy (kept for unaligned data buffers and for A/B measurements)
+static bool binary_copy_staged() {
+  const char* e = getenv("B2_BINARY_STAGED");
+  return !(e && e[0] == '0');
 }
 
 template <typename OffT>
@@ -384,6 +467,7 @@ static int filter_binary_typed(B2Context* ctx, const B2Array* values, const B2Ar
   a.out_data = nullptr;
   a.out_validity = nullptr;
   a.n = n;
+  a.staged = false;
   filter_binary_kernel<OffT, false, false><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
   B2_LAUNCHED();
   ScalarSlot slot(ctx);
@@ -406,8 +490,16 @@ static int filter_binary_typed(B2Context* ctx, const B2Array* values, const B2Ar
   a.out_offsets = offs.as<OffT>();
   a.out_data = data.as<uint8_t>();
   a.out_validity = bits.as<uint32_t>();
-  if (has_valid) filter_binary_kernel<OffT, true, true><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
-  else filter_binary_kernel<OffT, true, false><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
+  // aligned 8-byte source words need an 8-byte aligned data buffer (else the chunk-driven byte path runs)
+  a.staged = binary_copy_staged() && (reinterpret_cast<uintptr_t>(a.data) & 7) == 0;
+  const size_t dyn = a.staged ? kStageBytes + 16 : 0;
+  if (has_valid) {
+    B2_CUDA(cudaFuncSetAttribute(filter_binary_kernel<OffT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes + 16));
+    filter_binary_kernel<OffT, true, true><<<(unsigned)n_tiles, kBinThreads, dyn, s>>>(a);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(filter_binary_kernel<OffT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes + 16));
+    filter_binary_kernel<OffT, true, false><<<(unsigned)n_tiles, kBinThreads, dyn, s>>>(a);
+  }
   B2_LAUNCHED();
   int64_t null_count = has_valid ? out_len - out_valid : 0;
   fill_out(out, values->type, out_len, null_count, has_valid ? bits.release() : nullptr, offs.release(), data.release());
@@ -438,6 +530,7 @@ struct BinTakeArgs {
   uint32_t* out_validity;
   int64_t* valid_count;
   unsigned long long* first_bad;
+  bool staged;
 };
 
 template <typename Idx>
@@ -452,10 +545,13 @@ __global__ void __launch_bounds__(kBinThreads) take_binary_kernel(BinTakeArgs<Of
   __shared__ uint32_t s_out[COPY ? kTakeTile + 1 : 1];
   __shared__ int64_t s_src[COPY ? kTakeTile : 1];
   __shared__ uint32_t s_bits[COPY ? kTakeTile / 32 : 1];
+  extern __shared__ uint4 s_stage[];
   const int64_t tile = blockIdx.x;
   const int64_t row0 = tile * kTakeTile + threadIdx.x * kTakeRowsPerThread;
   if (COPY)
     for (int i = threadIdx.x; i < kTakeTile / 32; i += kBinThreads) s_bits[i] = 0;
+  if (COPY && a.staged)
+    for (int i = threadIdx.x; i < (kStageBytes + 16) / 16; i += kBinThreads) s_stage[i] = make_uint4(0, 0, 0, 0);
   uint32_t len[kTakeRowsPerThread];
   int64_t src[kTakeRowsPerThread];
   unsigned vb = 0;
@@ -504,7 +600,8 @@ __global__ void __launch_bounds__(kBinThreads) take_binary_kernel(BinTakeArgs<Of
     if (tile == gridDim.x - 1) a.out_offsets[a.n] = static_cast<OffT>(byte_base + total);
   }
   __syncthreads();
-  copy_tile_bytes<int64_t>(a.data, a.data, a.out_data, byte_base, total, s_out, s_src, tile_n);
+  if (a.staged) copy_tile_bytes_staged<int64_t>(a.data, a.out_data, byte_base, total, s_out, s_src, tile_n, s_stage);
+  else copy_tile_bytes<int64_t>(a.data, a.data, a.out_data, byte_base, total, s_out, s_src, tile_n);
   if (a.out_validity) {
     int64_t cnt = 0;
     if (threadIdx.x < kTakeTile / 32 && (int)threadIdx.x * 32 < tile_n) {
@@ -543,6 +640,7 @@ static int take_binary_typed(B2Context* ctx, const B2Array* values, const B2Arra
   a.out_validity = nullptr;
   a.valid_count = slot.dev() + 1;
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 2);
+  a.staged = false;
   if (n == 0) {
     Temp offs(ctx, s);
     B2_RETURN_NOT_OK(offs.alloc(sizeof(OffT)));
@@ -572,7 +670,9 @@ static int take_binary_typed(B2Context* ctx, const B2Array* values, const B2Arra
   a.out_offsets = offs.as<OffT>();
   a.out_data = data.as<uint8_t>();
   a.out_validity = has_valid ? bits.as<uint32_t>() : nullptr;
-  take_binary_kernel<OffT, Idx, true><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
+  a.staged = binary_copy_staged() && (reinterpret_cast<uintptr_t>(a.data) & 7) == 0;
+  B2_CUDA(cudaFuncSetAttribute(take_binary_kernel<OffT, Idx, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes + 16));
+  take_binary_kernel<OffT, Idx, true><<<(unsigned)n_tiles, kBinThreads, a.staged ? kStageBytes + 16 : 0, s>>>(a);
   B2_LAUNCHED();
   int64_t null_count = 0;
   if (has_valid) {
