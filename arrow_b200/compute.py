@@ -639,6 +639,11 @@ class GroupBySumCount:
         ck, cv = keys._c(), values._c()
         check(self.ctx.lib.b2_groupby_sumcount_consume(self.handle, C.byref(ck), C.byref(cv), self.ctx.stream))
 
+    def merge(self, keys: DeviceArray, sums: DeviceArray, counts: DeviceArray):
+        """add partial (key, sum, count) states of another group-by (HashAggregateKernel::merge for the fused table)"""
+        ck, cs, cc = keys._c(), sums._c(), counts._c()
+        check(self.ctx.lib.b2_groupby_sumcount_merge(self.handle, C.byref(ck), C.byref(cs), C.byref(cc), self.ctx.stream))
+
     def path_counts(self):
         """(compact, general, atomic) chunks consumed so far -- which internal path did the work"""
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -177,7 +177,8 @@ constexpr size_t compact_pass_smem(bool first) {
   return (first ? (size_t)kCTile * 16 : (size_t)kCTile * 8) + (size_t)kCTile * 8;
 }
 
-template <bool FIRST>
+// KW / VW: key / value byte widths known at compile time for the common shapes (8,8) and (4,4); 0 = read a.kw / a.vw
+template <bool FIRST, int KW, int VW>
 __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* in_keys = smem;                                                       // FIRST: kCTile * kw bytes (<= 32 KB)
@@ -187,9 +188,11 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
   __shared__ uint32_t s_cnt[kPartRadix], s_bin[kPartRadix], s_gbase[kPartRadix];
   __shared__ uint32_t s_warp_tot[kPartRadix / 32];
   __shared__ uint32_t s_cur, s_total;
+  __shared__ uint8_t s_dig[kCTile];  // digit of every staged tuple: the write-out does not recompute the hash
   __shared__ __align__(8) uint64_t s_bar;
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kw = KW ? KW : a.kw, vw = VW ? VW : a.vw;
   const uint32_t n_tiles = (a.n + kCTile - 1) / kCTile;
   const CompactEnc enc = a.enc;
   const unsigned long long vmask = (enc.vb >= 64) ? ~0ull : ((1ull << enc.vb) - 1ull);
@@ -202,20 +205,20 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
       const bool bulk = a.bulk_ok && tile_n == (uint32_t)kCTile;
       if (bulk) {
         if (tid == 0) {
-          const uint32_t bk = (uint32_t)kCTile * a.kw, bv = (uint32_t)kCTile * a.vw;
+          const uint32_t bk = (uint32_t)kCTile * kw, bv = (uint32_t)kCTile * vw;
           mbar_arrive_expect_tx(&s_bar, bk + bv);
-          bulk_copy_g2s_chunked(in_keys, a.keys + (size_t)base * a.kw, bk, &s_bar);
-          bulk_copy_g2s_chunked(in_vals, a.vals + (size_t)base * a.vw, bv, &s_bar);
+          bulk_copy_g2s_chunked(in_keys, a.keys + (size_t)base * kw, bk, &s_bar);
+          bulk_copy_g2s_chunked(in_vals, a.vals + (size_t)base * vw, bv, &s_bar);
         }
       } else {  // unaligned slice or the partial last tile: exact-bounds element copies by every thread
         for (uint32_t i = tid; i < tile_n; i += kCThreads) {
-          switch (a.kw) {
+          switch (kw) {
             case 1: in_keys[i] = a.keys[(size_t)base + i]; break;
             case 2: reinterpret_cast<uint16_t*>(in_keys)[i] = reinterpret_cast<const uint16_t*>(a.keys)[(size_t)base + i]; break;
             case 4: reinterpret_cast<uint32_t*>(in_keys)[i] = reinterpret_cast<const uint32_t*>(a.keys)[(size_t)base + i]; break;
             default: reinterpret_cast<unsigned long long*>(in_keys)[i] = reinterpret_cast<const unsigned long long*>(a.keys)[(size_t)base + i]; break;
           }
-          switch (a.vw) {
+          switch (vw) {
             case 1: in_vals[i] = a.vals[(size_t)base + i]; break;
             case 2: reinterpret_cast<uint16_t*>(in_vals)[i] = reinterpret_cast<const uint16_t*>(a.vals)[(size_t)base + i]; break;
             case 4: reinterpret_cast<uint32_t*>(in_vals)[i] = reinterpret_cast<const uint32_t*>(a.vals)[(size_t)base + i]; break;
@@ -234,10 +237,14 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
     }
   };
 
+  // tile tickets: the atomic's round trip (~1 us) must never sit between two barriers, so thread 0 always holds
+  // the ticket AFTER the next one in a register (fetched a whole iteration before it is published)
+  uint32_t ticket_ahead = 0;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
     s_cur = atomicAdd(a.ticket, 1u);
+    ticket_ahead = atomicAdd(a.ticket, 1u);
   }
   for (int i = tid; i < kPartRadix; i += kCThreads) s_cnt[i] = 0;
   __syncthreads();
@@ -252,12 +259,19 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
     // validity bits of this thread's rows (row = j * 512 + tid): fetched before the wait so the loads overlap it
     uint32_t kvalid = 0xffu, vvalid = 0xffu;
     if (FIRST) {
+      // lane j (< 8) loads the key-validity word of row group j, lane 8 + j the value-validity word; a shuffle hands
+      // every lane its own bit (32 lanes calling word32 each cost 50 instructions per row)
+      uint32_t word = 0xffffffffu;
+      if (lane < 2 * kCItems) {
+        const int j = lane & (kCItems - 1);
+        const int64_t w = (a.row0 + base + j * kCThreads + warp * 32) >> 5;  // row0 and base are multiples of 32
+        word = lane < kCItems ? a.key_valid.word32(w) : a.val_valid.word32(w);
+      }
       kvalid = vvalid = 0;
 #pragma unroll
       for (int j = 0; j < kCItems; ++j) {
-        const int64_t w = (a.row0 + base + j * kCThreads + warp * 32) >> 5;  // row0 and base are multiples of 32
-        kvalid |= ((a.key_valid.word32(w) >> lane) & 1u) << j;
-        vvalid |= ((a.val_valid.word32(w) >> lane) & 1u) << j;
+        kvalid |= ((__shfl_sync(0xffffffffu, word, j) >> lane) & 1u) << j;
+        vvalid |= ((__shfl_sync(0xffffffffu, word, kCItems + j) >> lane) & 1u) << j;
       }
     }
     mbar_wait(&s_bar, parity);
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
       t[j] = 0;
       if (r >= tile_n) continue;
       if (FIRST) {
-        const unsigned long long vbits = load_value_bits(in_vals, a.vw, a.vsigned, r);
+        const unsigned long long vbits = load_value_bits(in_vals, vw, a.vsigned, r);
         const bool vv = (vvalid >> j) & 1u;
         if (!((kvalid >> j) & 1u)) {  // null key: straight into the null group's accumulator
           ++null_rows;
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
           }
           continue;
         }
-        const unsigned long long kp = (load_key_bits(in_keys, a.kw, r) ^ enc.kflip) - enc.kmin;
+        const unsigned long long kp = (load_key_bits(in_keys, kw, r) ^ enc.kflip) - enc.kmin;
         const unsigned long long vp = vbits - enc.vbase;
         if (vv && (vp & ~vmask)) atomicOr(a.overflow, 1u);
         t[j] = (kp << (enc.vb + 1)) | (vv ? ((vp & vmask) << 1) | 1ull : 0ull);
@@ -295,7 +309,10 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
     }
     __syncthreads();  // every row of the tile is in registers and counted: the input buffer is free
 
-    if (tid == 0) s_cur = atomicAdd(a.ticket, 1u);
+    if (tid == 0) {
+      s_cur = ticket_ahead;
+      ticket_ahead = ticket_ahead < n_tiles ? atomicAdd(a.ticket, 1u) : ticket_ahead;  // consumed one iteration from now
+    }
     uint32_t run = 0, incl = 0;
     if (tid < kPartRadix) {
       run = s_cnt[tid];
@@ -330,7 +347,9 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
 #pragma unroll
     for (int j = 0; j < kCItems; ++j) {
       if (rank_dig[j] == 0xffffffffu) continue;
-      stage[s_bin[rank_dig[j] >> 16] + (rank_dig[j] & 0xffffu)] = t[j];
+      const uint32_t pos = s_bin[rank_dig[j] >> 16] + (rank_dig[j] & 0xffffu);
+      stage[pos] = t[j];
+      s_dig[pos] = static_cast<uint8_t>(rank_dig[j] >> 16);
     }
     if (tid < kPartRadix) {
       uint32_t excl = 0;
@@ -346,9 +365,7 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
     for (int j = 0; j < kCItems; ++j) {
       const uint32_t p = j * kCThreads + tid;
       if (p < total) {
-        const unsigned long long v = stage[p];
-        const uint32_t d = (compact_hash(compact_key(v, enc) + enc.kmin) >> a.shift) & (kPartRadix - 1);
-        __stcs(a.out + s_gbase[d] + p, v);
+        __stcs(a.out + s_gbase[s_dig[p]] + p, stage[p]);
       }
     }
     __syncthreads();  // stage and s_gbase are reused by the next tile
@@ -445,48 +462,67 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_preagg_kernel(const unsi
     const uint32_t g = chunk_of(c);
     const uint32_t rows = g >= n_chunks ? 0u : ((n - g * kCChunk) < (uint32_t)kCChunk ? (n - g * kCChunk) : (uint32_t)kCChunk);
     const unsigned long long* src = buf + (size_t)(c & 1) * kCChunk;
-#pragma unroll 4
-    for (uint32_t i = tid; i < rows; i += kCThreads) {
-      const unsigned long long t = src[i];
-      const unsigned long long kp = t >> (enc.vb + 1);
-      const unsigned long long vp = (t >> 1) & vmask;
-      const bool vv = t & 1ull;
-      unsigned s = compact_hash(kp + enc.kmin) & (kCSlots - 1);  // low bits: independent of the two partition digits
-      int slot = -1;
-      for (int probe = 0; probe < kCProbe; ++probe) {
+    // rows are handled kB at a time per thread: all tuples, hashes and first probes of a batch are issued before the
+    // dependent shared-memory work of any of them (the serial version ran at 28 % issue utilisation, stalled on LDS -> ATOMS chains)
+    constexpr int kB = 4;
+    for (uint32_t i0 = tid; i0 < rows; i0 += kB * kCThreads) {
+      unsigned long long tt[kB];
+      unsigned s0[kB];
+      unsigned long long first[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const uint32_t i = i0 + u * kCThreads;
+        tt[u] = i < rows ? src[i] : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        s0[u] = compact_hash((tt[u] >> (enc.vb + 1)) + enc.kmin) & (kCSlots - 1);  // low bits: independent of the two partition digits
+        first[u] = NARROW ? static_cast<unsigned long long>(k32[s0[u]]) : k64[s0[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (i0 + u * kCThreads >= rows) continue;
+        const unsigned long long t = tt[u];
+        const unsigned long long kp = t >> (enc.vb + 1);
+        const unsigned long long vp = (t >> 1) & vmask;
+        const bool vv = t & 1ull;
+        unsigned s = s0[u];
+        int slot = -1;
+        for (int probe = 0; probe < kCProbe; ++probe) {
+          if (NARROW) {
+            const uint32_t cur = probe == 0 ? static_cast<uint32_t>(first[u]) : k32[s];
+            if (cur == (uint32_t)kp) { slot = s; break; }
+            if (cur == 0xffffffffu) {
+              const uint32_t old = atomicCAS(&k32[s], 0xffffffffu, (uint32_t)kp);
+              if (old == 0xffffffffu || old == (uint32_t)kp) { slot = s; break; }
+            }
+          } else {
+            const unsigned long long cur = probe == 0 ? first[u] : k64[s];
+            if (cur == kp) { slot = s; break; }
+            if (cur == kEmptyKey) {
+              const unsigned long long old = atomicCAS(&k64[s], (unsigned long long)kEmptyKey, kp);
+              if (old == kEmptyKey || old == kp) { slot = s; break; }
+            }
+          }
+          s = (s + 1) & (kCSlots - 1);
+        }
+        if (slot < 0) {  // the slice holds too many distinct keys: this row goes straight to the global table
+          global_accumulate<false>(table, (kp + enc.kmin) ^ enc.kflip, false, vp + enc.vbase, vv ? 1u : 0u, counters);
+          continue;
+        }
         if (NARROW) {
-          const uint32_t cur = k32[s];
-          if (cur == (uint32_t)kp) { slot = s; break; }
-          if (cur == 0xffffffffu) {
-            const uint32_t old = atomicCAS(&k32[s], 0xffffffffu, (uint32_t)kp);
-            if (old == 0xffffffffu || old == (uint32_t)kp) { slot = s; break; }
+          if (vv) {
+            atomicAdd(&s32[slot], (uint32_t)vp);
+            atomicAdd(&c32[slot], 1u);
           }
-        } else {
-          const unsigned long long cur = k64[s];
-          if (cur == kp) { slot = s; break; }
-          if (cur == kEmptyKey) {
-            const unsigned long long old = atomicCAS(&k64[s], (unsigned long long)kEmptyKey, kp);
-            if (old == kEmptyKey || old == kp) { slot = s; break; }
-          }
+        } else if (vv) {
+          unsigned int* half = reinterpret_cast<unsigned int*>(&s64[slot]);  // [0] = lo, [1] = hi; explicit carry (native ATOMS only)
+          const unsigned int lo32 = static_cast<unsigned int>(vp), hi32 = static_cast<unsigned int>(vp >> 32);
+          const unsigned int old = atomicAdd(half, lo32);
+          const unsigned int carry = (old + lo32) < old ? 1u : 0u;
+          if (hi32 + carry) atomicAdd(half + 1, hi32 + carry);
+          atomicAdd(&c64[slot], 1u);
         }
-        s = (s + 1) & (kCSlots - 1);
-      }
-      if (slot < 0) {  // the slice holds too many distinct keys: this row goes straight to the global table
-        global_accumulate<false>(table, (kp + enc.kmin) ^ enc.kflip, false, vp + enc.vbase, vv ? 1u : 0u, counters);
-        continue;
-      }
-      if (NARROW) {
-        if (vv) {
-          atomicAdd(&s32[slot], (uint32_t)vp);
-          atomicAdd(&c32[slot], 1u);
-        }
-      } else if (vv) {
-        unsigned int* half = reinterpret_cast<unsigned int*>(&s64[slot]);  // [0] = lo, [1] = hi; explicit carry (native ATOMS only)
-        const unsigned int lo32 = static_cast<unsigned int>(vp), hi32 = static_cast<unsigned int>(vp >> 32);
-        const unsigned int old = atomicAdd(half, lo32);
-        const unsigned int carry = (old + lo32) < old ? 1u : 0u;
-        if (hi32 + carry) atomicAdd(half + 1, hi32 + carry);
-        atomicAdd(&c64[slot], 1u);
       }
     }
     __syncthreads();  // chunk consumed: its buffer may be refilled; the table is complete if the slice ends here

@@ -72,6 +72,36 @@ __global__ void __launch_bounds__(kBlock) fused_consume_kernel(const void* __res
   }
 }
 
+// partial states (key, sum, count) of another group-by -- a peer GPU's groups after the exchange, or another
+// thread's table -- added into this table: the fused twin of HashAggregateKernel::merge
+// (compute/kernel.h:720-725, GroupByNode::Merge acero/groupby_aggregate_node.cc:255-298)
+template <bool IS_FLOAT, int KW>
+__global__ void __launch_bounds__(kBlock) fused_merge_kernel(const void* __restrict__ keys, BitmapReader key_valid,
+                                                             const unsigned long long* __restrict__ sums,
+                                                             const long long* __restrict__ counts, int64_t n, const uint32_t* pending_in,
+                                                             FusedTable t, uint32_t* pending_out, unsigned long long* counters) {
+  for (int64_t j = blockIdx.x * (int64_t)kBlock + threadIdx.x; j < n; j += (int64_t)gridDim.x * kBlock) {
+    const int64_t i = pending_in ? pending_in[j] : j;
+    const bool knull = !key_valid.bit(i);
+    const uint64_t key = knull ? 0 : load_key_bits(keys, KW, i);
+    bool inserted;
+    int64_t slot = table_find_or_insert(t.slots, t.mask, kSlotWords, key, knull, &inserted);
+    if (slot < 0) {
+      unsigned long long k = atomicAdd(&counters[0], 1ull);
+      pending_out[k] = static_cast<uint32_t>(i);
+      continue;
+    }
+    if (inserted) atomicAdd(&counters[1], 1ull);
+    const long long c = counts[i];
+    if (c > 0) {  // a partial with count 0 only asserts that the group exists (its sum slot is null)
+      unsigned long long* p = t.slots + slot * kSlotWords;
+      if (IS_FLOAT) atomicAdd(reinterpret_cast<double*>(p + 1), __longlong_as_double((long long)sums[i]));
+      else atomicAdd(p + 1, sums[i]);
+      atomicAdd(p + 2, static_cast<unsigned long long>(c));
+    }
+  }
+}
+
 // move every occupied slot of `src` into `dst` (growth)
 __global__ void __launch_bounds__(kBlock) fused_rehash_kernel(FusedTable src, FusedTable dst, int64_t* overflow) {
   for (uint64_t i = blockIdx.x * (uint64_t)kBlock + threadIdx.x; i < src.mask + 3; i += (uint64_t)gridDim.x * kBlock) {
@@ -440,8 +470,20 @@ static int try_compact_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_
   a.overflow = reinterpret_cast<unsigned int*>(sslot.dev());
   a.null_acc = reinterpret_cast<unsigned long long*>(sslot.dev() + 1);
   const int max_ctas = ctx->sm_count * 2;
-  B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_pass_smem(true)));
-  compact_pass_kernel<true><<<(int)n_tiles_in < max_ctas ? (int)n_tiles_in : max_ctas, kCThreads, compact_pass_smem(true), s>>>(a);
+  {
+    const int grid1 = (int)n_tiles_in < max_ctas ? (int)n_tiles_in : max_ctas;
+    const size_t sm1 = compact_pass_smem(true);
+    if (KW == 8 && vw == 8) {
+      B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<true, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      compact_pass_kernel<true, 8, 8><<<grid1, kCThreads, sm1, s>>>(a);
+    } else if (KW == 4 && vw == 4) {
+      B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      compact_pass_kernel<true, 4, 4><<<grid1, kCThreads, sm1, s>>>(a);
+    } else {
+      B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      compact_pass_kernel<true, 0, 0><<<grid1, kCThreads, sm1, s>>>(a);
+    }
+  }
   B2_LAUNCHED();
   B2_RETURN_NOT_OK(sslot.fetch(s));
   if (sslot.host()[0] != 0) return B2_OK;  // a value outside the sampled window: redo the chunk on the general path
@@ -460,8 +502,8 @@ static int try_compact_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_
     a.shift = 16;
     a.digit_base = dbase.as<uint32_t>() + kPartRadix;
     a.ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles_t * kPartRadix * sizeof(uint32_t));
-    B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_pass_smem(false)));
-    compact_pass_kernel<false><<<(int)n_tiles_t < max_ctas ? (int)n_tiles_t : max_ctas, kCThreads, compact_pass_smem(false), s>>>(a);
+    B2_CUDA(cudaFuncSetAttribute(compact_pass_kernel<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compact_pass_smem(false)));
+    compact_pass_kernel<false, 0, 0><<<(int)n_tiles_t < max_ctas ? (int)n_tiles_t : max_ctas, kCThreads, compact_pass_smem(false), s>>>(a);
     B2_LAUNCHED();
     sorted = bufB.as<unsigned long long>();
   }
@@ -629,6 +671,67 @@ int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys, const
     case B2_FLOAT: return fused_consume<float>(g, keys, values, s);
     default: return fused_consume<double>(g, keys, values, s);
   }
+}
+
+int b2_groupby_sumcount_merge(B2GroupBySumCount* g, const B2Array* keys, const B2Array* sums, const B2Array* counts, void* stream) {
+  if (!g || !keys || !sums || !counts) return set_error(B2_INVALID, "b2_groupby_sumcount_merge: null argument");
+  if (keys->type != g->key_type) return set_error(B2_TYPE_ERROR, "merge: key type id %d, expected %d", keys->type, g->key_type);
+  const bool flt = g->value_type == B2_FLOAT || g->value_type == B2_DOUBLE;
+  const int sum_type = flt ? B2_DOUBLE
+                           : (g->value_type == B2_UINT8 || g->value_type == B2_UINT16 || g->value_type == B2_UINT32 || g->value_type == B2_UINT64)
+                                 ? B2_UINT64 : B2_INT64;
+  if (sums->type != sum_type || counts->type != B2_INT64)
+    return set_error(B2_TYPE_ERROR, "merge: sums must have type id %d and counts int64 (got %d, %d)", sum_type, sums->type, counts->type);
+  if (sums->length != keys->length || counts->length != keys->length) return set_error(B2_INVALID, "merge: columns differ in length");
+  if (keys->length >= (1ll << 32)) return set_error(B2_NOT_IMPLEMENTED, "merge: at most 2^32 - 1 partial groups per call");
+  B2Context* ctx = g->ctx;
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = keys->length;
+  if (n == 0) return B2_OK;
+  // size the table for the partials up front: every partial may be a new group
+  const uint64_t want = next_pow2(2 * (g->groups + (uint64_t)n));
+  if (!g->table.slots) {
+    if (want > g->cap) g->cap = want;
+    B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
+  } else if (want > g->cap) {
+    B2_RETURN_NOT_OK(fused_grow(g, want, s));
+  }
+  const int kw = type_width(g->key_type);
+  const void* kdata = static_cast<const char*>(keys->data) + keys->offset * kw;
+  const unsigned long long* sdata = static_cast<const unsigned long long*>(sums->data) + sums->offset;
+  const long long* cdata = static_cast<const long long*>(counts->data) + counts->offset;
+  BitmapReader kv(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
+  Temp pend_a(ctx, s), pend_b(ctx, s);
+  B2_RETURN_NOT_OK(pend_a.alloc(sizeof(uint32_t) * (size_t)n));
+  const uint32_t* pin = nullptr;
+  uint32_t* pout = pend_a.as<uint32_t>();
+  int64_t todo = n;
+  while (todo > 0) {
+    ScalarSlot slot(ctx);
+    B2_RETURN_NOT_OK(slot.zero(s));
+    unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
+    const int grid = grid_for(todo, kBlock * 4, kSMs * 16);
+#define B2_MERGE_LAUNCH(F, W) fused_merge_kernel<F, W><<<grid, kBlock, 0, s>>>(kdata, kv, sdata, cdata, todo, pin, g->table, pout, dc)
+    if (flt) {
+      switch (kw) { case 1: B2_MERGE_LAUNCH(true, 1); break; case 2: B2_MERGE_LAUNCH(true, 2); break; case 4: B2_MERGE_LAUNCH(true, 4); break; default: B2_MERGE_LAUNCH(true, 8); break; }
+    } else {
+      switch (kw) { case 1: B2_MERGE_LAUNCH(false, 1); break; case 2: B2_MERGE_LAUNCH(false, 2); break; case 4: B2_MERGE_LAUNCH(false, 4); break; default: B2_MERGE_LAUNCH(false, 8); break; }
+    }
+#undef B2_MERGE_LAUNCH
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    const int64_t pending = slot.host()[0];
+    g->groups += static_cast<uint64_t>(slot.host()[1]);
+    if (pending == 0) break;
+    B2_RETURN_NOT_OK(fused_grow(g, g->cap * 2, s));  // a neighbourhood hit the probe limit: grow, retry only those partials
+    if (!pend_b.ptr) B2_RETURN_NOT_OK(pend_b.alloc(sizeof(uint32_t) * (size_t)n));
+    pin = pout;
+    pout = (pout == pend_a.as<uint32_t>()) ? pend_b.as<uint32_t>() : pend_a.as<uint32_t>();
+    todo = pending;
+  }
+  if (g->hint <= 0 || (int64_t)g->groups > g->hint) g->hint = (int64_t)g->groups;
+  return B2_OK;
 }
 
 int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* compact, int64_t* general, int64_t* atomic) {

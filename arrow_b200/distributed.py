@@ -454,19 +454,8 @@ class DeviceOps:
             validity[n >> 3] = 0xFF & ~(1 << (n & 7))
             nulls = 1
         keys = self._array(rk, keys_type, validity, nulls)
-        g = bc.Grouper([keys_type], self.ctx)
-        ids = g.consume(keys)
-        sums = bc.HashAggregator("hash_sum", sum_type, ctx=self.ctx)
-        cnts = bc.HashAggregator("hash_sum", pa.int64(), ctx=self.ctx)
-        sums.resize(g.num_groups)
-        cnts.resize(g.num_groups)
-        sums.consume(self._array(rs, sum_type), ids)
-        cnts.consume(self._array(rc, pa.int64()), ids)
-        total, s = cnts.finalize(), sums.finalize()
-        # a group whose merged count is 0 has a null sum (min_count = 1): the comparison's bit-packed
-        # result IS the validity bitmap
-        nonzero = bc.not_equal(total, 0)
-        n_null = total.length - bc.filter_output_size(nonzero)
-        if n_null:
-            s = self.DeviceArray(self.ctx, sum_type, s.length, n_null, 0, [nonzero.buffers[1], s.buffers[1]])
-        return g.get_uniques()[0], s, total
+        # one kernel: every partial finds / claims its key's slot and adds its sum and count (b2_groupby_sumcount_merge)
+        value_type = {pa.int64(): pa.int64(), pa.uint64(): pa.uint64(), pa.float64(): pa.float64()}[sum_type]
+        g = bc.GroupBySumCount(keys_type, value_type, expected_groups=max(1, n), ctx=self.ctx)
+        g.merge(keys, self._array(rs, sum_type), self._array(rc, pa.int64()))
+        return g.finalize()

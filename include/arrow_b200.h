@@ -400,6 +400,12 @@ B2_API int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t 
 B2_API void b2_groupby_sumcount_destroy(B2GroupBySumCount* g);
 B2_API int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys,
                                        const B2Array* values, void* stream);
+/* Adds partial states into the table: keys / sums (the accumulator type b2_groupby_sumcount_finalize returns) /
+ * counts (int64) of ANOTHER group-by over the same key and value types -- a peer GPU's groups after the exchange, or
+ * another thread's.  The fused twin of HashAggregateKernel::merge (compute/kernel.h:720-725) as GroupByNode::Merge uses
+ * it (acero/groupby_aggregate_node.cc:255-298).  A partial with count 0 only asserts the group exists. */
+B2_API int b2_groupby_sumcount_merge(B2GroupBySumCount* g, const B2Array* keys, const B2Array* sums,
+                                     const B2Array* counts, void* stream);
 /* how many consume() chunks ran on each internal path (diagnostics for tests / bench):
  *   compact : 8-byte tuples + bulk-async partition passes (narrow key range, verified value window)
  *   general : 17-byte tuples, any key / value

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call C: ncu --set full of the compact group-by kernels (200M rows, cheap replay)
+# round 2, GPU call C2: ncu --set full of the compact partition passes (200M rows, cheap replay)
 set -x
 mkdir -p gpurun_out
 cap() {  # name regex skip
@@ -10,8 +10,5 @@ cap() {  # name regex skip
   python scripts/ncu_summary.py gpurun_out/$1_raw.csv > gpurun_out/$1_summary.txt 2>&1
   cat gpurun_out/$1_summary.txt
 }
-cap cpass1_prof 'compact_pass_kernel<1' 1
-cap cpass0_prof 'compact_pass_kernel<0' 1
-cap cpreagg_prof 'compact_preagg_kernel' 1
-cap cstats_prof 'compact_stats_kernel' 1
-ls -la gpurun_out/*.ncu-rep | tail
+cap cpass1_prof 'compact_pass_kernel' 2
+cap cpass0_prof 'compact_pass_kernel' 3

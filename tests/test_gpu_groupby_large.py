@@ -154,3 +154,35 @@ def test_compact_value_window_is_verified_not_trusted(ctx):
         check_path(ctx, k, v2, 300_000, "general")
     finally:
         del os.environ["B2_GROUPBY_COMPACT"]
+
+
+def test_fused_merge_of_partial_states(ctx):
+    """b2_groupby_sumcount_merge: the partial (key, sum, count) tables of two shards added into a third table must
+    equal one group-by over all rows (what the owner GPU does after the exchange, and GroupByNode::Merge per thread)"""
+    n = 2_400_000
+    rng = np.random.default_rng(SEED + 21)
+    for vt, mk in ((pa.int64(), lambda: rng.integers(-100, 101, n, dtype=np.int64)), (pa.float64(), lambda: rng.uniform(-1, 1, n)),
+                   (pa.uint32(), lambda: rng.integers(0, 1000, n, dtype=np.uint32))):
+        keys = pa.array(rng.integers(0, 300_000, n, dtype=np.int64), mask=rng.random(n) < 0.01)
+        kk = keys.to_numpy(zero_copy_only=False)
+        vals = pa.array(mk(), vt, mask=(rng.random(n) < 0.1) | (np.nan_to_num(kk, nan=1) % 11 == 0))  # some groups: only null values
+        parts = []
+        for lo, hi in ((0, n // 3), (n // 3, n)):
+            g = bc.GroupBySumCount(keys.type, vt, ctx=ctx)
+            g.consume(DeviceArray.from_arrow(keys.slice(lo, hi - lo), ctx), DeviceArray.from_arrow(vals.slice(lo, hi - lo), ctx))
+            parts.append(g.finalize())
+        sum_type = parts[0][1].type
+        m = bc.GroupBySumCount(keys.type, sum_type, ctx=ctx)
+        for k, s, c in parts:
+            m.merge(k, s, c)
+        k, s, c = [x.to_arrow() for x in m.finalize()]
+        got = pa.table({"k": k, "v_sum": s, "v_count": c}).sort_by("k")
+        want = reference(keys, vals)
+        assert got["k"].combine_chunks().equals(want["k"].combine_chunks())
+        assert got["v_count"].combine_chunks().equals(want["v_count"].combine_chunks())
+        gs, ws = got["v_sum"].combine_chunks(), want["v_sum"].combine_chunks()
+        if pa.types.is_integer(vt):
+            assert gs.equals(ws.cast(gs.type))
+        else:
+            assert gs.is_valid().equals(ws.is_valid())
+            np.testing.assert_allclose(gs.fill_null(0).to_numpy(), ws.fill_null(0).to_numpy(), rtol=1e-9, atol=1e-6)
