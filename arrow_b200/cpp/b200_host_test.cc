@@ -17,6 +17,7 @@
 #include <chrono>
 #include <iostream>
 #include <random>
+#include <thread>
 
 #include "b200_compute.h"
 
@@ -146,10 +147,42 @@ int main(int argc, char** argv) {
     const int64_t rows = argc > 2 ? atoll(argv[2]) : 100000000;
     const int64_t groups = argc > 3 ? atoll(argv[3]) : 10000000;
     const int reps = argc > 4 ? atoi(argv[4]) : 3;
+    CHECK_OK(cp::Initialize());
     auto rt = UNWRAP(arrow_b200::Runtime::Get(0));
     CHECK_OK(arrow_b200::RegisterAceroNodes());
-    auto k = RandomNumeric<arrow::Int64Type>(rows, 0.0, 91, 0, groups - 1);
-    auto v = RandomNumeric<arrow::Int64Type>(rows, 0.1, 92, -100, 100);
+    // counter-based generator filled by all host threads (1B rows through a builder would take minutes)
+    auto mix = [](uint64_t x) {
+      x += 0x9e3779b97f4a7c15ull;
+      x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+      x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+      return x ^ (x >> 31);
+    };
+    std::shared_ptr<arrow::Buffer> kbuf = UNWRAP(arrow::AllocateBuffer(rows * 8)), vbuf = UNWRAP(arrow::AllocateBuffer(rows * 8));
+    std::shared_ptr<arrow::Buffer> bits = UNWRAP(arrow::AllocateBuffer((rows + 7) / 8 + 8));
+    memset(bits->mutable_data(), 0, bits->size());
+    const int T = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<int64_t> null_counts(T, 0);
+    {
+      std::vector<std::thread> ts;
+      for (int t = 0; t < T; ++t)
+        ts.emplace_back([&, t] {
+          const int64_t lo = rows * t / T / 64 * 64, hi = t == T - 1 ? rows : rows * (t + 1) / T / 64 * 64;
+          auto* kk = reinterpret_cast<int64_t*>(kbuf->mutable_data());
+          auto* vv = reinterpret_cast<int64_t*>(vbuf->mutable_data());
+          uint8_t* bb = bits->mutable_data();
+          for (int64_t i = lo; i < hi; ++i) {
+            kk[i] = (int64_t)(mix(91 * 0x9e3779b1ull + i) % (uint64_t)groups);
+            vv[i] = (int64_t)(mix(92 * 0x9e3779b1ull + i) % 201) - 100;
+            if (mix(93 * 0x9e3779b1ull + i) % 10 != 0) bb[i >> 3] |= uint8_t(1u << (i & 7));  // one writer per 64-row range
+            else ++null_counts[t];
+          }
+        });
+      for (auto& t : ts) t.join();
+    }
+    int64_t v_nulls = 0;
+    for (auto x : null_counts) v_nulls += x;
+    auto k = arrow::MakeArray(arrow::ArrayData::Make(arrow::int64(), rows, {nullptr, kbuf}, 0));
+    auto v = arrow::MakeArray(arrow::ArrayData::Make(arrow::int64(), rows, {bits, vbuf}, v_nulls));
     auto dk = arrow::MakeArray(UNWRAP(arrow_b200::ToDevice(*k->data(), rt->memory_manager())));
     auto dv = arrow::MakeArray(UNWRAP(arrow_b200::ToDevice(*v->data(), rt->memory_manager())));
     auto schema = arrow::schema({arrow::field("k", arrow::int64()), arrow::field("v", arrow::int64())});

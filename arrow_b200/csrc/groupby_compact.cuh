@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
     }
     mbar_wait(&s_bar, parity);
     parity ^= 1u;
-    __syncthreads();  // plain-load fallback: the other threads' writes to the input buffer
+    // bulk copies are visible to every thread that observed the barrier phase; only the plain-load fallback (unaligned
+    // slice / partial last tile) needs a CTA barrier for the other threads' writes -- the condition is uniform per tile
+    if (FIRST && !(a.bulk_ok && tile_n == (uint32_t)kCTile)) __syncthreads();
 
     unsigned long long t[kCItems];
     uint32_t rank_dig[kCItems];
@@ -368,7 +370,8 @@ __global__ void __launch_bounds__(kCThreads, 2) compact_pass_kernel(CompactArgs 
         __stcs(a.out + s_gbase[s_dig[p]] + p, stage[p]);
       }
     }
-    __syncthreads();  // stage and s_gbase are reused by the next tile
+    // no barrier here: the next tile writes `stage`, `s_dig` and `s_gbase` only after its own two barriers (counts complete,
+    // offsets ready), which no thread passes before it has finished this write-out
     tile = next_tile;
   }
 

@@ -58,7 +58,7 @@ def test_outputs_come_from_the_installed_allocator():
     assert outs["take"].to_arrow().equals(ora.take(values, idx))
     assert outs["filter"].to_arrow().equals(ora.filter(values, mask))
     assert len(served) > len(outs)           # temporaries were served by the callbacks as well ...
-    del outs, dv, di, dm, dk, uk, s, c
+    del outs, dv, di, dm, dk, uk, s, c, arr, b, name
     import gc
     gc.collect()
     assert not live, f"{len(live)} allocations were never returned to the allocator (temporaries must be freed)"
