@@ -217,9 +217,19 @@ class AggregateNode : public DeviceNode {
       all_device = all_device && IsOnDevice(*d);
       row.push_back(std::move(d));
     }
-    if (all_device && batch.length >= kCoalesceRows / 4 && pending_rows_ == 0) {
-      ARROW_RETURN_NOT_OK(ConsumeDevice(row, batch.length));  // already resident and large: no staging
+    if (all_device) {
+      // Device-resident input.  The stock SourceNode cuts every morsel into kMaxBatchSize (32Ki-row) slices
+      // (SliceAndDeliverMorsel, acero/source_node.cc:122-165): consecutive slices are adjacent views of the same buffers,
+      // so they are glued back together -- zero copy -- into one run that is consumed when it stops growing.
+      ARROW_RETURN_NOT_OK(Flush());  // host rows parked earlier keep their arrival order
+      if (!ExtendRun(row, batch.length)) {
+        ARROW_RETURN_NOT_OK(FlushRun());
+        run_ = row;
+        run_rows_ = batch.length;
+      }
+      if (run_rows_ >= kMaxRunRows) ARROW_RETURN_NOT_OK(FlushRun());
     } else {
+      ARROW_RETURN_NOT_OK(FlushRun());
       for (size_t i = 0; i < cols.size(); ++i) pending_[i].push_back(arrow::MakeArray(row[i]));
       pending_rows_ += batch.length;
       if (pending_rows_ >= kCoalesceRows) ARROW_RETURN_NOT_OK(Flush());
@@ -249,6 +259,36 @@ class AggregateNode : public DeviceNode {
     return needed_;
   }
   int Slot(int column) const { return static_cast<int>(std::find(needed_.begin(), needed_.end(), column) - needed_.begin()); }
+
+  // does `row` continue the current device run (same buffers, offset == end of the run) in every column?
+  bool ExtendRun(const std::vector<std::shared_ptr<arrow::ArrayData>>& row, int64_t length) {
+    if (run_.empty() || run_.size() != row.size()) return false;
+    for (size_t i = 0; i < row.size(); ++i) {
+      const auto& a = *run_[i];
+      const auto& b = *row[i];
+      if (a.buffers.size() != b.buffers.size() || !a.child_data.empty() || !b.child_data.empty() || a.dictionary || b.dictionary) return false;
+      for (size_t k = 0; k < a.buffers.size(); ++k)
+        if (a.buffers[k].get() != b.buffers[k].get()) return false;
+      if (b.offset != a.offset + run_rows_) return false;
+    }
+    run_rows_ += length;
+    return true;
+  }
+
+  Status FlushRun() {
+    if (run_.empty()) return Status::OK();
+    std::vector<std::shared_ptr<arrow::ArrayData>> cols;
+    for (auto& d : run_) {
+      auto whole = d->Copy();  // shallow: shares the buffers
+      whole->length = run_rows_;
+      whole->null_count = whole->buffers[0] ? arrow::kUnknownNullCount : 0;
+      cols.push_back(std::move(whole));
+    }
+    const int64_t rows = run_rows_;
+    run_.clear();
+    run_rows_ = 0;
+    return ConsumeDevice(cols, rows);
+  }
 
   // concatenate the parked host chunks, one H2D copy per column, consume as ONE device batch
   Status Flush() {
@@ -296,6 +336,7 @@ class AggregateNode : public DeviceNode {
     done_ = true;
     NeededColumns();
     ARROW_RETURN_NOT_OK(Flush());
+    ARROW_RETURN_NOT_OK(FlushRun());
     // Finalize, groupby_aggregate_node.cc:300-337: [keys..., aggregates...]
     if (fused_) {
       B2Array k, s, c;
@@ -346,6 +387,9 @@ class AggregateNode : public DeviceNode {
   std::vector<int> needed_;
   std::vector<arrow::ArrayVector> pending_;
   int64_t pending_rows_ = 0;
+  std::vector<std::shared_ptr<arrow::ArrayData>> run_;  // current run of adjacent device slices (one ArrayData per needed column)
+  int64_t run_rows_ = 0;
+  static constexpr int64_t kMaxRunRows = (1ll << 30) - (1 << 16);
   int device_batches_ = 0;
   int seen_ = 0, total_ = -1;
   bool done_ = false;

@@ -503,6 +503,26 @@ int main(int argc, char** argv) {
       std::cout << "OK   b200_aggregate hash_sum+hash_count == aggregate (B200_AGGREGATE_FUSED=" << fused << ", " << got2->num_rows() << " groups)" << std::endl;
     }
     unsetenv("B200_AGGREGATE_FUSED");
+    // a DEVICE-resident table through the stock table_source: it arrives as adjacent 32Ki-row slices of the same device
+    // buffers (SliceAndDeliverMorsel), which b200_aggregate glues back into one run without copying
+    {
+      auto dtable = arrow::Table::Make(table->schema(), {arrow::MakeArray(h.Dev(k).array()), arrow::MakeArray(h.Dev(v).array()),
+                                                         arrow::MakeArray(h.Dev(w).array())});
+      std::vector<cp::Aggregate> aggs3 = {{"hash_sum", nullptr, "v", "v_sum"}, {"hash_count", nullptr, "v", "v_count"}};
+      ac::Declaration plan = ac::Declaration::Sequence({{"table_source", ac::TableSourceNodeOptions(dtable, 1 << 15)},
+                                                        {"b200_aggregate", ac::AggregateNodeOptions(aggs3, {"k"})}});
+      auto got3 = sorted(UNWRAP(ac::DeclarationToTable(std::move(plan), /*use_threads=*/false)), "k");
+      auto want3 = sorted(run("aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs3, std::vector<arrow::FieldRef>{"k"})), "k");
+      auto want3_sel = UNWRAP(want3->SelectColumns({UNWRAP(arrow::FieldRef("k").FindOne(*want3->schema())).indices()[0],
+                                                    UNWRAP(arrow::FieldRef("v_sum").FindOne(*want3->schema())).indices()[0],
+                                                    UNWRAP(arrow::FieldRef("v_count").FindOne(*want3->schema())).indices()[0]}));
+      ++g_checks;
+      if (!got3->Equals(*want3_sel)) {
+        std::cout << "FAIL b200_aggregate over a device-resident table" << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_aggregate over a device-resident table_source (adjacent device slices glued, no host round trip)" << std::endl;
+    }
     // filter: the predicate is an Expression bound against the nested registry
     auto pred = cp::greater(cp::call("add", {cp::field_ref("v"), cp::field_ref("k")}), cp::literal(int64_t(400)));
     auto fwant = run("filter", std::make_shared<ac::FilterNodeOptions>(pred));

@@ -101,3 +101,20 @@ def test_binary_filter_unaligned_data_buffer(ctx, shift):
         assert_equal(bc.filter(aligned, dev(mask, ctx), ns).to_arrow(), want, ns)
     idx = random_array(pa.int32(), 5000, 0.05, SEED + 2, lo=0, hi=n - 1)
     assert_equal(bc.take(moved, dev(idx, ctx)).to_arrow(), pc.take(vals, idx))
+
+
+@pytest.mark.parametrize("t", STRING_TYPES, ids=str)
+def test_binary_filter_take_staged_copy(ctx, t, monkeypatch):
+    """the opt-in row-driven staged copy (B2_BINARY_STAGED=1, csrc/selection_binary.cu): same results, incl. rows longer
+    than the 32-byte fast path and tiles whose output exceeds one staging round"""
+    monkeypatch.setenv("B2_BINARY_STAGED", "1")
+    for n, lo, hi in ((1500, 0, 32), (50000, 0, 32), (9000, 0, 3), (3000, 100, 400), (20000, 0, 70)):
+        for null_p in (0.0, 0.1):
+            vals = random_array(t, n, null_p, SEED + n, lo=lo, hi=hi, offset=3)
+            for true_p, mask_null in ((0.5, 0.0), (0.999, 0.3)):
+                mask = random_array(pa.bool_(), n, mask_null, SEED + 1, hi=true_p, offset=2)
+                for ns in ("drop", "emit_null"):
+                    assert_equal(bc.filter(dev(vals, ctx), dev(mask, ctx), ns).to_arrow(), ora.filter(vals, mask, ns),
+                                 f"staged {t} n={n} {lo}-{hi} {null_p} {true_p} {ns}")
+            idx = random_array(pa.int64(), n // 2 + 7, null_p, SEED + 5, lo=0, hi=n - 1, offset=3)
+            assert_equal(bc.take(dev(vals, ctx), dev(idx, ctx)).to_arrow(), ora.take(vals, idx), f"staged take {t} n={n}")
