@@ -147,7 +147,7 @@ PROTOTYPES = [
     ("b2_groupby_sumcount_consume", C.c_int, [_P, _A, _A, _P]),
     ("b2_groupby_sumcount_finalize", C.c_int, [_P, _A, _A, _A, _P]),
     ("b2_groupby_sumcount_merge", C.c_int, [_P, _A, _A, _A, _P]),
-    ("b2_groupby_sumcount_path_counts", C.c_int, [_P, _I64P, _I64P, _I64P]),
+    ("b2_groupby_sumcount_path_counts", C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
     ("b2_hash_partition", C.c_int, [_P, _A, C.c_int, _A, _P]),
     ("b2_range_partition", C.c_int, [_P, _A, _A, C.c_int, _A, _P]),
     ("b2_bincount", C.c_int, [_P, _A, C.c_int, _I64P, _P]),

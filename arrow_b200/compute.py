@@ -645,10 +645,10 @@ class GroupBySumCount:
         check(self.ctx.lib.b2_groupby_sumcount_merge(self.handle, C.byref(ck), C.byref(cs), C.byref(cc), self.ctx.stream))
 
     def path_counts(self):
-        """(compact, general, atomic) chunks consumed so far -- which internal path did the work"""
-        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
-        check(self.ctx.lib.b2_groupby_sumcount_path_counts(self.handle, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+        """{dense, compact, general, atomic}: chunks consumed so far by each internal path"""
+        d, a, b, c = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.ctx.lib.b2_groupby_sumcount_path_counts(self.handle, C.byref(d), C.byref(a), C.byref(b), C.byref(c)))
+        return {"dense": d.value, "compact": a.value, "general": b.value, "atomic": c.value}
 
     def finalize(self):
         k, s, c = cabi.B2Array(), cabi.B2Array(), cabi.B2Array()

@@ -19,6 +19,7 @@
 #include "hash_table.cuh"
 #include "groupby_partitioned.cuh"
 #include "groupby_compact.cuh"
+#include "groupby_dense.cuh"
 
 namespace b2 {
 
@@ -198,7 +199,7 @@ struct B2GroupBySumCount {
   uint64_t groups = 0;
   int64_t hint = 0;  // expected number of groups (0 = unknown); refined after every chunk
   bool hint_given = false;
-  int64_t chunks_compact = 0, chunks_general = 0, chunks_atomic = 0;  // which path consumed each chunk
+  int64_t chunks_compact = 0, chunks_general = 0, chunks_atomic = 0, chunks_dense = 0;  // which path consumed each chunk
 };
 
 constexpr int64_t kPartMinRows = 1ll << 21;  // below this the plain atomic path is cheaper than 5 launches
@@ -367,6 +368,128 @@ static inline int bit_width_u64(unsigned long long v) {
 }
 
 static bool g_compact_enabled = true;  // B2_GROUPBY_COMPACT=0 forces the general path (tests exercise both)
+static bool g_dense_enabled = true;    // B2_GROUPBY_DENSE=0 skips the direct-addressed path
+static int64_t g_dense_band_bytes = 96ll << 20;  // B2_DENSE_BAND_MB: packed state applied per launch (L2 residency)
+
+// Runs one chunk on the direct-addressed path (groupby_dense.cuh) when a sample says the keys are dense and the values
+// narrow.  *done = false: not applicable, or a row fell outside the sampled windows -- nothing has touched the global table.
+template <int KW>
+static int try_dense_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t cn, cudaStream_t s, unsigned long long* d_counters,
+                           unsigned long long* ovf_pairs, unsigned int* ovf_counts, uint64_t ovf_cap, bool* done) {
+  *done = false;
+  B2Context* ctx = g->ctx;
+  if (!g_dense_enabled || cn < (1 << 22)) return B2_OK;
+  const int vt = g->value_type;
+  if (vt == B2_FLOAT || vt == B2_DOUBLE) return B2_OK;
+  const int vw = type_width(vt);
+  const bool vsigned = vt == B2_INT8 || vt == B2_INT16 || vt == B2_INT32 || vt == B2_INT64;
+  const int kt = g->key_type;
+  const bool ksigned = kt == B2_INT8 || kt == B2_INT16 || kt == B2_INT32 || kt == B2_INT64;
+  const unsigned long long kflip = ksigned ? (1ull << (8 * KW - 1)) : 0ull;
+  // 1. sample keys (and 64-bit values)
+  ScalarSlot sslot(ctx);
+  B2_RETURN_NOT_OK(sslot.zero(s));
+  CompactStats* d_stats = reinterpret_cast<CompactStats*>(sslot.dev());
+  B2_CUDA(cudaMemsetAsync(&d_stats->kmin, 0xff, 8, s));
+  B2_CUDA(cudaMemsetAsync(&d_stats->vmin, 0xff, 8, s));
+  const int64_t step = cn > 65536 ? cn / 65536 : 1;
+  dense_sample_kernel<KW><<<64, kBlock, 0, s>>>(raw.keys, raw.key_valid, static_cast<const unsigned long long*>(raw.values), raw.val_valid,
+                                                raw.row0, cn, step, kflip, vw == 8, vsigned, d_stats);
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(sslot.fetch(s));
+  CompactStats st;
+  memcpy(&st, const_cast<const int64_t*>(reinterpret_cast<volatile int64_t*>(sslot.host())), sizeof(st));
+  if (st.kmax < st.kmin) return B2_OK;  // no valid key in the sample
+  const unsigned long long krange = st.kmax - st.kmin + 1;
+  if (krange == 0 || krange > kDenseMaxRange) return B2_OK;
+  const unsigned long long slack = krange / 64 + 1024;  // rows outside the padded window are caught by the kernel's check
+  unsigned long long kmin = st.kmin > slack ? st.kmin - slack : 0ull;
+  unsigned long long range = (st.kmax - kmin) + 1 + slack;
+  if (range > kDenseMaxRange + kDenseMaxRange / 32) return B2_OK;
+  if ((unsigned long long)cn < 4 * range) return B2_OK;  // too few rows per slot: flushing the table would dominate
+  // value window (as on the compact path)
+  int vb;
+  unsigned long long vbase;
+  if (vw <= 4) {
+    vb = 8 * vw;
+    vbase = vsigned ? static_cast<unsigned long long>(-(1ll << (8 * vw - 1))) : 0ull;
+  } else if (st.sampled == 0) {
+    vb = 8;
+    vbase = 0;
+  } else {
+    const unsigned long long flip = vsigned ? 0x8000000000000000ull : 0ull;
+    const unsigned long long vrange = st.vmax - st.vmin;
+    const int need = bit_width_u64(vrange);
+    vb = need + 2 < 8 ? 8 : need + 2;
+    if (vb > 62) return B2_OK;
+    vbase = (st.vmin ^ flip) - ((((1ull << vb) - 1ull) - vrange) / 2);
+  }
+  const int m = (63 - vb) / 2;          // rows per sub-batch = 2^m: count needs m + 1 bits, sum needs vb + m bits
+  if (m < 22) return B2_OK;             // wide values: a drain every < 4M rows costs more than it saves
+  const int64_t sub = m >= 30 ? (1ll << 30) : (1ll << m);
+  const int sb = vb + m;
+  // 2. state
+  Temp packed(ctx, s), sums(ctx, s), counts(ctx, s), exists(ctx, s);
+  const size_t words = (size_t)range;
+  B2_RETURN_NOT_OK(packed.alloc(words * 8));
+  B2_RETURN_NOT_OK(sums.alloc(words * 8));
+  B2_RETURN_NOT_OK(counts.alloc(words * 8));
+  B2_RETURN_NOT_OK(exists.alloc((words / 32 + 2) * 4));
+  B2_CUDA(cudaMemsetAsync(packed.ptr, 0, words * 8, s));
+  B2_CUDA(cudaMemsetAsync(sums.ptr, 0, words * 8, s));
+  B2_CUDA(cudaMemsetAsync(counts.ptr, 0, words * 8, s));
+  B2_CUDA(cudaMemsetAsync(exists.ptr, 0, (words / 32 + 2) * 4, s));
+  B2_RETURN_NOT_OK(sslot.zero(s));  // [0] overflow flag, [1..3] null-key accumulator
+  DenseArgs a{};
+  a.kw = KW;
+  a.vw = vw;
+  a.vsigned = vsigned;
+  a.key_valid = raw.key_valid;
+  a.val_valid = raw.val_valid;
+  a.kmin = kmin;
+  a.kflip = kflip;
+  a.range = range;
+  a.vbase = vbase;
+  a.vb = vb;
+  a.sb = sb;
+  a.table = packed.as<unsigned long long>();
+  a.exists = exists.as<uint32_t>();
+  a.overflow = reinterpret_cast<unsigned int*>(sslot.dev());
+  a.null_acc = reinterpret_cast<unsigned long long*>(sslot.dev() + 1);
+  const unsigned long long band_keys = (unsigned long long)(g_dense_band_bytes / 8);
+  const int bands = (int)((range + band_keys - 1) / band_keys);
+  const int grid = grid_for(cn < sub ? cn : sub, kBlock * 16, ctx->sm_count * 8);
+  for (int64_t off = 0; off < cn; off += sub) {
+    const int64_t rows = cn - off < sub ? cn - off : sub;
+    a.row0 = raw.row0 + off;
+    a.n = rows;
+    a.keys = static_cast<const uint8_t*>(raw.keys) + (size_t)a.row0 * KW;
+    a.vals = static_cast<const uint8_t*>(raw.values) + (size_t)a.row0 * vw;
+    for (int b = 0; b < bands; ++b) {
+      a.band_lo = (unsigned long long)b * band_keys;
+      a.band_hi = b == bands - 1 ? range : a.band_lo + band_keys;
+      if (KW == 8 && vw == 8) dense_consume_kernel<8, 8><<<grid, kBlock, 0, s>>>(a);
+      else if (KW == 4 && vw == 4) dense_consume_kernel<4, 4><<<grid, kBlock, 0, s>>>(a);
+      else dense_consume_kernel<0, 0><<<grid, kBlock, 0, s>>>(a);
+      B2_LAUNCHED();
+    }
+    dense_drain_kernel<<<grid_for((int64_t)range, kBlock * 8, ctx->sm_count * 8), kBlock, 0, s>>>(
+        packed.as<unsigned long long>(), range, sb, vbase, sums.as<unsigned long long>(), counts.as<unsigned long long>());
+    B2_LAUNCHED();
+  }
+  B2_RETURN_NOT_OK(sslot.fetch(s));
+  if (sslot.host()[0] != 0) return B2_OK;  // a row outside the sampled windows: partitioned path
+  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts, ovf_cap};
+  if (sslot.host()[3] != 0) {
+    compact_null_flush_kernel<<<1, 32, 0, s>>>(tref, reinterpret_cast<const unsigned long long*>(sslot.dev() + 1), d_counters);
+    B2_LAUNCHED();
+  }
+  dense_flush_kernel<<<grid_for((int64_t)range, kBlock * 4, ctx->sm_count * 16), kBlock, 0, s>>>(
+      sums.as<unsigned long long>(), counts.as<unsigned long long>(), exists.as<uint32_t>(), range, kmin, kflip, tref, d_counters);
+  B2_LAUNCHED();
+  *done = true;
+  return B2_OK;
+}
 
 // Runs one chunk on the compact path when the measured key range and the (verified) value window fit one
 // 64-bit tuple.  *done = false means "not applicable" (or the value window was violated): nothing has
@@ -565,7 +688,16 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     bool done = false;
     unsigned long long* op = ovf_pairs.as<unsigned long long>();
     unsigned int* oc = ovf_counts.as<unsigned int>();
+    bool dense_done = false;
     switch (kw) {
+      case 1: st = try_dense_chunk<1>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
+      case 2: st = try_dense_chunk<2>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
+      case 4: st = try_dense_chunk<4>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
+      default: st = try_dense_chunk<8>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
+    }
+    if (st != B2_OK) return st;
+    if (dense_done) ++g->chunks_dense;
+    if (!dense_done) switch (kw) {
       case 1: st = try_compact_chunk<1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
       case 2: st = try_compact_chunk<2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
       case 4: st = try_compact_chunk<4>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
@@ -573,8 +705,8 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     }
     if (st != B2_OK) return st;
     if (done) ++g->chunks_compact;
-    else ++g->chunks_general;
-    if (!done) {
+    else if (!dense_done) ++g->chunks_general;
+    if (!done && !dense_done) {
       switch (kw) {
         case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
         case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
@@ -624,6 +756,10 @@ int b2_groupby_sumcount_create(B2Context* ctx, int32_t key_type, int32_t value_t
   {
     const char* e = getenv("B2_GROUPBY_COMPACT");
     g_compact_enabled = !(e && e[0] == '0');
+    const char* d = getenv("B2_GROUPBY_DENSE");
+    g_dense_enabled = !(d && d[0] == '0');
+    const char* bm = getenv("B2_DENSE_BAND_MB");
+    if (bm && atoll(bm) > 0) g_dense_band_bytes = atoll(bm) << 20;
   }
   if (type_width(key_type) == 0) return set_error(B2_NOT_IMPLEMENTED, "group-by key type id %d", key_type);
   if (!type_is_numeric(value_type)) return set_error(B2_NOT_IMPLEMENTED, "group-by value type id %d", value_type);
@@ -734,8 +870,9 @@ int b2_groupby_sumcount_merge(B2GroupBySumCount* g, const B2Array* keys, const B
   return B2_OK;
 }
 
-int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* compact, int64_t* general, int64_t* atomic) {
+int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* dense, int64_t* compact, int64_t* general, int64_t* atomic) {
   if (!g) return set_error(B2_INVALID, "b2_groupby_sumcount_path_counts: null argument");
+  if (dense) *dense = g->chunks_dense;
   if (compact) *compact = g->chunks_compact;
   if (general) *general = g->chunks_general;
   if (atomic) *atomic = g->chunks_atomic;

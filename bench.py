@@ -448,7 +448,7 @@ def run_configs(env, n):
     ok = check_groups(k, s, c)
     del k, s, c
     entry("c3 group-by hash_sum+hash_count int64 key, 10M groups (fused b2_groupby_sumcount)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng,
-          chunks_compact_general_atomic=list(paths.get("counts", ())))
+          paths=paths.get("counts"))
     ms = env.timed(unfused, 2)
     (ku,), (su, cu) = unfused()
     ok = check_groups(ku, su, cu)

@@ -116,7 +116,7 @@ def main():
         ms = timed(stream, fused, args.reps, warmup=1)
         ng = len(fused()[0])
         report("c3 group-by sum+count (fused table)", n, ms, n * 16.125 + ng * 24.25,
-               {"groups": ng, "chunks_compact_general_atomic": list(paths["counts"])})
+               {"groups": ng, "paths": paths["counts"]})
         if args.fused_only:
             return
 

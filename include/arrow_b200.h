@@ -407,11 +407,12 @@ B2_API int b2_groupby_sumcount_consume(B2GroupBySumCount* g, const B2Array* keys
 B2_API int b2_groupby_sumcount_merge(B2GroupBySumCount* g, const B2Array* keys, const B2Array* sums,
                                      const B2Array* counts, void* stream);
 /* how many consume() chunks ran on each internal path (diagnostics for tests / bench):
- *   compact : 8-byte tuples + bulk-async partition passes (narrow key range, verified value window)
+ *   dense   : direct-addressed packed state in L2, one reduction per row (dense key range, narrow verified value window)
+ *   compact : 8-byte tuples + bulk-async partition passes (key range + value window fit 63 bits)
  *   general : 17-byte tuples, any key / value
  *   atomic  : small batches, one global-table update per row */
-B2_API int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* compact, int64_t* general,
-                                           int64_t* atomic);
+B2_API int b2_groupby_sumcount_path_counts(const B2GroupBySumCount* g, int64_t* dense, int64_t* compact,
+                                           int64_t* general, int64_t* atomic);
 /* out_keys / out_sums / out_counts: num_groups long, group order unspecified */
 B2_API int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys,
                                         B2Array* out_sums, B2Array* out_counts, void* stream);

@@ -81,11 +81,9 @@ def check_path(ctx, keys, vals, hint, want_path, batches=1, offset=0):
     for b in range(batches):
         lo, hi = b * n // batches, (b + 1) * n // batches
         g.consume(dk.slice(lo, hi - lo), dv.slice(lo, hi - lo))
-    compact, general, atomic = g.path_counts()
-    if want_path == "compact":
-        assert compact == batches and general == 0, (compact, general, atomic)
-    elif want_path == "general":
-        assert general == batches and compact == 0, (compact, general, atomic)
+    paths = g.path_counts()
+    if want_path is not None:
+        assert paths[want_path] == batches and sum(paths.values()) == batches, paths
     k, s, c = [x.to_arrow() for x in g.finalize()]
     got = pa.table({"k": k, "v_sum": s, "v_count": c}).sort_by("k")
     want = reference(keys, vals)
@@ -186,3 +184,61 @@ def test_fused_merge_of_partial_states(ctx):
         else:
             assert gs.is_valid().equals(ws.is_valid())
             np.testing.assert_allclose(gs.fill_null(0).to_numpy(), ws.fill_null(0).to_numpy(), rtol=1e-9, atol=1e-6)
+
+
+# ---- the direct-addressed path (csrc/groupby_dense.cuh): dense keys, packed state in L2 -----------------------------
+@pytest.mark.parametrize("offset", [0, 1])
+def test_dense_group_by(ctx, offset):
+    """>= 2^22 rows over a dense key range: one reduction per row into table[key - kmin]"""
+    n = 4_700_000 + offset
+    rng = np.random.default_rng(SEED + 31 + offset)
+    keys = pa.array(rng.integers(-250_000, 250_000, n, dtype=np.int64), mask=rng.random(n) < 0.01)   # negative keys: sign-flip encoding
+    vals = pa.array(rng.integers(-100, 101, n, dtype=np.int64), mask=rng.random(n) < 0.1)
+    check_path(ctx, keys, vals, 500_000, "dense", offset=offset)
+    check_path(ctx, keys, vals, 0, "dense", offset=offset)
+
+
+def test_dense_group_by_types_null_groups_and_batches(ctx):
+    n = 4_400_000
+    rng = np.random.default_rng(SEED + 37)
+    # a group whose every value is null must exist with sum = null, count = 0 (the `exists` bitmap)
+    kk = rng.integers(0, 300_000, n, dtype=np.int64)
+    vv = rng.integers(-5, 5, n, dtype=np.int64)
+    check_path(ctx, pa.array(kk), pa.array(vv, mask=(kk % 7 == 0) | (rng.random(n) < 0.05)), 300_000, "dense")
+    # narrow native types: int32 keys, int16 / uint8 values (window = the type's range)
+    k32 = pa.array(rng.integers(-70000, 70000, n, dtype=np.int32), mask=rng.random(n) < 0.02)
+    v16 = pa.array(rng.integers(-30000, 30000, n, dtype=np.int16), mask=rng.random(n) < 0.1)
+    check_path(ctx, k32, v16, 140_000, "dense")
+    ku16 = pa.array(rng.integers(0, 60000, n, dtype=np.uint16))
+    vu8 = pa.array(rng.integers(0, 255, n, dtype=np.uint8), mask=rng.random(n) < 0.5)
+    check_path(ctx, ku16, vu8, 0, "dense")
+    # unsigned 64-bit values around 2^63: sums wrap exactly like the reference
+    vu64 = pa.array(rng.integers(2**63, 2**63 + 1000, n, dtype=np.uint64), mask=rng.random(n) < 0.1)
+    check_path(ctx, ku16, vu64, 60_000, "dense")
+    # several consume() calls into one table
+    k2 = pa.array(rng.integers(0, 900_000, 3 * n, dtype=np.int64))
+    v2 = pa.array(rng.integers(-100, 100, 3 * n, dtype=np.int64), mask=rng.random(3 * n) < 0.1)
+    check_path(ctx, k2, v2, 0, "dense", batches=3)
+
+
+def test_dense_windows_are_verified_not_trusted(ctx):
+    """both windows come from a 64Ki-row SAMPLE: a key or a value outside them (at an unsampled row) must send the batch
+    to the partitioned path instead of corrupting a neighbour's state"""
+    n = 4_500_000
+    step = n // 65536
+    rng = np.random.default_rng(SEED + 41)
+    k = rng.integers(0, 400_000, n, dtype=np.int64)
+    v = rng.integers(-100, 101, n, dtype=np.int64)
+    m = rng.random(n) < 0.1
+    assert 2_000_001 % step != 0 and 2_000_003 % step != 0
+    k2 = k.copy()
+    k2[2_000_001] = 900_000_000              # key far outside the sampled range
+    check_path(ctx, pa.array(k2), pa.array(v, mask=m), 0, "compact")
+    v2 = v.copy()
+    v2[2_000_003] = 2**40                    # value far outside the sampled window -> dense and compact both refuse
+    m2 = m.copy()
+    m2[2_000_003] = False
+    check_path(ctx, pa.array(k), pa.array(v2, mask=m2), 0, "general")
+    k3 = k.copy()
+    k3[2_000_001] = -5                       # just below the sampled minimum but inside the slack: still dense
+    check_path(ctx, pa.array(k3), pa.array(v, mask=m), 0, "dense")
