@@ -200,6 +200,16 @@ struct B2GroupBySumCount {
   int64_t hint = 0;  // expected number of groups (0 = unknown); refined after every chunk
   bool hint_given = false;
   int64_t chunks_compact = 0, chunks_general = 0, chunks_atomic = 0, chunks_dense = 0;  // which path consumed each chunk
+  // Direct-addressed state (groupby_dense.cuh) accumulated by dense chunks.  It coexists with the hash table: finalize
+  // emits straight from it when the table was never needed, otherwise flushes it into the table first.
+  struct Dense {
+    bool active = false;
+    unsigned long long kmin = 0, kflip = 0, range = 0;
+    unsigned long long* sums = nullptr;
+    unsigned long long* counts = nullptr;
+    uint32_t* exists = nullptr;
+    unsigned long long null_sum = 0, null_cnt = 0, null_rows = 0;  // the null-key group (host copies)
+  } dense;
 };
 
 constexpr int64_t kPartMinRows = 1ll << 21;  // below this the plain atomic path is cheaper than 5 launches
@@ -357,6 +367,100 @@ static int run_partitioned_chunk(B2GroupBySumCount* g, const RawColumns& raw, in
   return B2_OK;
 }
 
+// ---- shared helpers of the partitioned / dense paths ---------------------------------------------------
+static int ensure_table(B2GroupBySumCount* g, uint64_t min_cap, cudaStream_t s) {
+  if (g->table.slots) return B2_OK;
+  if (min_cap > g->cap) g->cap = min_cap;
+  return fused_alloc(g->ctx, g->cap, &g->table, s);
+}
+
+// After kernels that insert through global_accumulate: read the counters, grow the table and replay whatever was parked
+// because a neighbourhood hit the probe limit.  counters = slot: [0] parked, [1] inserted, [2] did not fit the parking area.
+template <bool IS_FLOAT>
+static int absorb_parked(B2GroupBySumCount* g, ScalarSlot& slot, Temp& ovf_pairs, Temp& ovf_counts, cudaStream_t s) {
+  B2Context* ctx = g->ctx;
+  unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  if (slot.host()[2] != 0)
+    return set_error(B2_CAPACITY_ERROR, "group-by: %lld more groups than the table sized from expected_groups=%lld can absorb in one batch; "
+                     "pass a larger expected_groups (or 0 to let the table grow chunk by chunk)", (long long)slot.host()[2], (long long)g->hint);
+  int64_t parked = slot.host()[0];
+  g->groups += static_cast<uint64_t>(slot.host()[1]);
+  while (parked > 0) {
+    // the table filled up: grow it and replay the parked (key, sum, count) entries
+    B2_RETURN_NOT_OK(fused_grow(g, next_pow2(4 * (g->groups + (uint64_t)parked)), s));
+    Temp p2(ctx, s), c2(ctx, s);
+    B2_RETURN_NOT_OK(p2.alloc(16 * (size_t)parked));
+    B2_RETURN_NOT_OK(c2.alloc(4 * (size_t)parked));
+    FusedTableRef tref{g->table.slots, g->table.mask, p2.as<unsigned long long>(), c2.as<unsigned int>(), (uint64_t)parked};
+    B2_RETURN_NOT_OK(slot.zero(s));
+    replay_overflow_kernel<IS_FLOAT><<<grid_for(parked, kBlock * 4, ctx->sm_count * 8), kBlock, 0, s>>>(
+        tref, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), parked, dc);
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(slot.fetch(s));
+    g->groups += static_cast<uint64_t>(slot.host()[1]);
+    const int64_t again = slot.host()[0];
+    if (again > 0) {  // (only if the grown table is somehow still too small) keep the remainder parked
+      B2_CUDA(cudaMemcpyAsync(ovf_pairs.ptr, p2.ptr, 16 * (size_t)again, cudaMemcpyDeviceToDevice, s));
+      B2_CUDA(cudaMemcpyAsync(ovf_counts.ptr, c2.ptr, 4 * (size_t)again, cudaMemcpyDeviceToDevice, s));
+    }
+    parked = again;
+  }
+  if (g->groups * 2 > g->cap) B2_RETURN_NOT_OK(fused_grow(g, next_pow2(g->groups * 4), s));
+  return B2_OK;
+}
+
+static void dense_release(B2GroupBySumCount* g, cudaStream_t s) {
+  auto& d = g->dense;
+  if (d.sums) g->ctx->free(d.sums, s);
+  if (d.counts) g->ctx->free(d.counts, s);
+  if (d.exists) g->ctx->free(d.exists, s);
+  d = B2GroupBySumCount::Dense();
+}
+
+// number of groups held by the dense state (incl. those whose every value was null), and how many have count 0
+static int dense_count(B2GroupBySumCount* g, int64_t* groups, int64_t* empty, cudaStream_t s) {
+  ScalarSlot slot(g->ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  dense_count_kernel<<<grid_for((int64_t)g->dense.range, kBlock * 8, g->ctx->sm_count * 8), kBlock, 0, s>>>(g->dense.counts, g->dense.exists,
+                                                                                                       g->dense.range, slot.dev());
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  *groups = slot.host()[0];
+  *empty = slot.host()[1];
+  return B2_OK;
+}
+
+// dense state -> the global table (one insert per group), then the dense arrays are released
+static int flush_dense(B2GroupBySumCount* g, cudaStream_t s) {
+  auto& d = g->dense;
+  if (!d.active) return B2_OK;
+  B2Context* ctx = g->ctx;
+  int64_t nd = 0, empty = 0;
+  B2_RETURN_NOT_OK(dense_count(g, &nd, &empty, s));
+  const uint64_t want = next_pow2(2 * (g->groups + (uint64_t)nd + 1));
+  B2_RETURN_NOT_OK(ensure_table(g, want, s));
+  if (want > g->cap) B2_RETURN_NOT_OK(fused_grow(g, want, s));
+  Temp ovf_pairs(ctx, s), ovf_counts(ctx, s);
+  const uint64_t ovf_cap = (uint64_t)nd + 2;
+  B2_RETURN_NOT_OK(ovf_pairs.alloc(16 * (size_t)ovf_cap));
+  B2_RETURN_NOT_OK(ovf_counts.alloc(4 * (size_t)ovf_cap));
+  ScalarSlot slot(ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  unsigned long long* dc = reinterpret_cast<unsigned long long*>(slot.dev());
+  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), ovf_cap};
+  if (d.null_rows) {
+    dense_null_flush_kernel<<<1, 32, 0, s>>>(tref, d.null_sum, d.null_cnt, dc);
+    B2_LAUNCHED();
+  }
+  dense_flush_kernel<<<grid_for((int64_t)d.range, kBlock * 4, ctx->sm_count * 16), kBlock, 0, s>>>(d.sums, d.counts, d.exists, d.range, d.kmin,
+                                                                                                 d.kflip, tref, dc);
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(absorb_parked<false>(g, slot, ovf_pairs, ovf_counts, s));
+  dense_release(g, s);
+  return B2_OK;
+}
+
 // ---- compact path (groupby_compact.cuh): 8-byte tuples, bulk-async loads -------------------------
 static inline int bit_width_u64(unsigned long long v) {
   int b = 0;
@@ -369,7 +473,7 @@ static inline int bit_width_u64(unsigned long long v) {
 
 static bool g_compact_enabled = true;  // B2_GROUPBY_COMPACT=0 forces the general path (tests exercise both)
 static bool g_dense_enabled = true;    // B2_GROUPBY_DENSE=0 skips the direct-addressed path
-static int64_t g_dense_band_bytes = 96ll << 20;  // B2_DENSE_BAND_MB: packed state applied per launch (L2 residency)
+static int64_t g_dense_band_bytes = 48ll << 20;  // B2_DENSE_BAND_MB: packed state applied per launch (L2 residency)
 
 // Runs one chunk on the direct-addressed path (groupby_dense.cuh) when a sample says the keys are dense and the values
 // narrow.  *done = false: not applicable, or a row fell outside the sampled windows -- nothing has touched the global table.
@@ -405,6 +509,13 @@ static int try_dense_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t 
   const unsigned long long slack = krange / 64 + 1024;  // rows outside the padded window are caught by the kernel's check
   unsigned long long kmin = st.kmin > slack ? st.kmin - slack : 0ull;
   unsigned long long range = (st.kmax - kmin) + 1 + slack;
+  // a later batch whose sample falls inside the window of the state already held keeps that window: its result is
+  // added to the state element-wise instead of going through the hash table
+  const bool reuse = g->dense.active && g->dense.kflip == kflip && st.kmin >= g->dense.kmin && st.kmax < g->dense.kmin + g->dense.range;
+  if (reuse) {
+    kmin = g->dense.kmin;
+    range = g->dense.range;
+  }
   if (range > kDenseMaxRange + kDenseMaxRange / 32) return B2_OK;
   if ((unsigned long long)cn < 4 * range) return B2_OK;  // too few rows per slot: flushing the table would dominate
   // value window (as on the compact path)
@@ -478,15 +589,31 @@ static int try_dense_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t 
     B2_LAUNCHED();
   }
   B2_RETURN_NOT_OK(sslot.fetch(s));
-  if (sslot.host()[0] != 0) return B2_OK;  // a row outside the sampled windows: partitioned path
-  FusedTableRef tref{g->table.slots, g->table.mask, ovf_pairs, ovf_counts, ovf_cap};
-  if (sslot.host()[3] != 0) {
-    compact_null_flush_kernel<<<1, 32, 0, s>>>(tref, reinterpret_cast<const unsigned long long*>(sslot.dev() + 1), d_counters);
+  if (sslot.host()[0] != 0) return B2_OK;  // a row outside the sampled windows: partitioned path (this chunk's arrays are dropped)
+  auto& d = g->dense;
+  const unsigned long long n_sum = static_cast<unsigned long long>(sslot.host()[1]), n_cnt = static_cast<unsigned long long>(sslot.host()[2]),
+                           n_rows = static_cast<unsigned long long>(sslot.host()[3]);
+  if (reuse) {
+    dense_merge_kernel<<<grid_for((int64_t)range, kBlock * 8, ctx->sm_count * 8), kBlock, 0, s>>>(
+        d.sums, d.counts, d.exists, sums.as<unsigned long long>(), counts.as<unsigned long long>(), exists.as<uint32_t>(), range);
     B2_LAUNCHED();
+  } else {
+    B2_RETURN_NOT_OK(flush_dense(g, s));  // a state with another window goes to the hash table first
+    d.active = true;
+    d.kmin = kmin;
+    d.kflip = kflip;
+    d.range = range;
+    d.sums = static_cast<unsigned long long*>(sums.release());
+    d.counts = static_cast<unsigned long long*>(counts.release());
+    d.exists = static_cast<uint32_t*>(exists.release());
   }
-  dense_flush_kernel<<<grid_for((int64_t)range, kBlock * 4, ctx->sm_count * 16), kBlock, 0, s>>>(
-      sums.as<unsigned long long>(), counts.as<unsigned long long>(), exists.as<uint32_t>(), range, kmin, kflip, tref, d_counters);
-  B2_LAUNCHED();
+  d.null_sum += n_sum;
+  d.null_cnt += n_cnt;
+  d.null_rows += n_rows;
+  (void)d_counters;
+  (void)ovf_pairs;
+  (void)ovf_counts;
+  (void)ovf_cap;
   *done = true;
   return B2_OK;
 }
@@ -653,11 +780,6 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
   raw.values = static_cast<const V*>(values->data) + values->offset;
   raw.key_valid = BitmapReader(keys->null_count == 0 ? nullptr : keys->validity, keys->offset, n);
   raw.val_valid = BitmapReader(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
-  if (!g->table.slots) {
-    uint64_t want = next_pow2(2 * (uint64_t)(g->hint > (1 << 19) ? g->hint : (1 << 19)));
-    if (want > g->cap) g->cap = want;
-    B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
-  }
   constexpr bool kFloat = std::is_floating_point<V>::value;
   // Chunking.  Pre-aggregation pays off in proportion to how often a key repeats INSIDE one chunk, so
   // chunks should be as large as memory allows (tuples: 2 x 17 B/row).  Entries that hit a full table
@@ -696,8 +818,14 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
       default: st = try_dense_chunk<8>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
     }
     if (st != B2_OK) return st;
-    if (dense_done) ++g->chunks_dense;
-    if (!dense_done) switch (kw) {
+    if (dense_done) {
+      ++g->chunks_dense;
+      row0 += cn;
+      continue;  // the hash table was not touched (it may not even exist yet)
+    }
+    // the partitioned paths insert into the global table: create it on first use
+    B2_RETURN_NOT_OK(ensure_table(g, next_pow2(2 * (uint64_t)(g->hint > (1 << 19) ? g->hint : (1 << 19))), s));
+    switch (kw) {
       case 1: st = try_compact_chunk<1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
       case 2: st = try_compact_chunk<2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
       case 4: st = try_compact_chunk<4>(g, raw, cn, passes, s, dc, op, oc, ovf_cap, &done); break;
@@ -705,8 +833,8 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     }
     if (st != B2_OK) return st;
     if (done) ++g->chunks_compact;
-    else if (!dense_done) ++g->chunks_general;
-    if (!done && !dense_done) {
+    else ++g->chunks_general;
+    if (!done) {
       switch (kw) {
         case 1: st = run_partitioned_chunk<V, 1>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
         case 2: st = run_partitioned_chunk<V, 2>(g, raw, cn, passes, s, dc, op, oc, ovf_cap); break;
@@ -715,33 +843,7 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
       }
       if (st != B2_OK) return st;
     }
-    B2_RETURN_NOT_OK(slot.fetch(s));
-    if (slot.host()[2] != 0)
-      return set_error(B2_CAPACITY_ERROR, "group-by: %lld more groups than the table sized from expected_groups=%lld can absorb in one batch; "
-                       "pass a larger expected_groups (or 0 to let the table grow chunk by chunk)", (long long)slot.host()[2], (long long)g->hint);
-    int64_t parked = slot.host()[0];
-    g->groups += static_cast<uint64_t>(slot.host()[1]);
-    while (parked > 0) {
-      // the table filled up inside this chunk: grow it and replay the parked (key, sum, count) entries
-      B2_RETURN_NOT_OK(fused_grow(g, next_pow2(4 * (g->groups + (uint64_t)parked)), s));
-      Temp p2(ctx, s), c2(ctx, s);
-      B2_RETURN_NOT_OK(p2.alloc(16 * (size_t)parked));
-      B2_RETURN_NOT_OK(c2.alloc(4 * (size_t)parked));
-      FusedTableRef tref{g->table.slots, g->table.mask, p2.as<unsigned long long>(), c2.as<unsigned int>(), (uint64_t)parked};
-      B2_RETURN_NOT_OK(slot.zero(s));
-      replay_overflow_kernel<kFloat><<<grid_for(parked, kBlock * 4, ctx->sm_count * 8), kBlock, 0, s>>>(
-          tref, ovf_pairs.as<unsigned long long>(), ovf_counts.as<unsigned int>(), parked, dc);
-      B2_LAUNCHED();
-      B2_RETURN_NOT_OK(slot.fetch(s));
-      g->groups += static_cast<uint64_t>(slot.host()[1]);
-      const int64_t again = slot.host()[0];
-      if (again > 0) {  // (only if the grown table is somehow still too small) keep the remainder parked
-        B2_CUDA(cudaMemcpyAsync(ovf_pairs.ptr, p2.ptr, 16 * (size_t)again, cudaMemcpyDeviceToDevice, s));
-        B2_CUDA(cudaMemcpyAsync(ovf_counts.ptr, c2.ptr, 4 * (size_t)again, cudaMemcpyDeviceToDevice, s));
-      }
-      parked = again;
-    }
-    if (g->groups * 2 > g->cap) B2_RETURN_NOT_OK(fused_grow(g, next_pow2(g->groups * 4), s));
+    B2_RETURN_NOT_OK(absorb_parked<kFloat>(g, slot, ovf_pairs, ovf_counts, s));
     if (g->hint <= 0 || (int64_t)g->groups > g->hint) g->hint = (int64_t)g->groups;  // measured cardinality
     row0 += cn;
   }
@@ -783,6 +885,7 @@ void b2_groupby_sumcount_destroy(B2GroupBySumCount* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
   if (g->table.slots) g->ctx->free(g->table.slots, g->ctx->stream);
+  dense_release(g, g->ctx->stream);
   delete g;
 }
 
@@ -885,8 +988,15 @@ int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Arra
   B2Context* ctx = g->ctx;
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
-  if (!g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
-  const int64_t n = static_cast<int64_t>(g->groups);
+  // dense state: emitted directly when the hash table was never needed (the single-batch dense case: no table is ever
+  // allocated, initialised or scanned); otherwise it joins the table first
+  const bool dense_direct = g->dense.active && g->table.slots == nullptr;
+  int64_t n_dense = 0, dense_empty = 0;
+  if (g->dense.active && !dense_direct) B2_RETURN_NOT_OK(flush_dense(g, s));
+  if (dense_direct) B2_RETURN_NOT_OK(dense_count(g, &n_dense, &dense_empty, s));
+  if (!dense_direct && !g->table.slots) B2_RETURN_NOT_OK(fused_alloc(ctx, g->cap, &g->table, s));
+  const int dense_null = dense_direct && g->dense.null_rows ? 1 : 0;
+  const int64_t n = dense_direct ? n_dense + dense_null : static_cast<int64_t>(g->groups);
   const int kw = type_width(g->key_type);
   const int sum_type = (g->value_type == B2_FLOAT || g->value_type == B2_DOUBLE) ? B2_DOUBLE
                        : (g->value_type == B2_UINT8 || g->value_type == B2_UINT16 || g->value_type == B2_UINT32 ||
@@ -904,16 +1014,25 @@ int b2_groupby_sumcount_finalize(B2GroupBySumCount* g, B2Array* out_keys, B2Arra
     B2_CUDA(cudaMemsetAsync(sbits.ptr, 0xff, bb, s));
     ScalarSlot slot(ctx);
     B2_RETURN_NOT_OK(slot.zero(s));
-    fused_emit_kernel<<<grid_for((int64_t)g->cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
-        g->table, kw, keys.ptr, kbits.as<uint32_t>(), sums.as<unsigned long long>(), sbits.as<uint32_t>(),
-        counts.as<long long>(), reinterpret_cast<unsigned long long*>(slot.dev()));
+    if (dense_direct) {
+      const auto& d = g->dense;
+      dense_emit_kernel<<<grid_for((int64_t)d.range, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+          d.sums, d.counts, d.exists, d.range, d.kmin, d.kflip, kw, keys.ptr, kbits.as<uint32_t>(), sums.as<unsigned long long>(),
+          sbits.as<uint32_t>(), counts.as<long long>(), reinterpret_cast<unsigned long long*>(slot.dev()), dense_null, d.null_sum, d.null_cnt,
+          (unsigned long long)n_dense);
+    } else {
+      fused_emit_kernel<<<grid_for((int64_t)g->cap + 2, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+          g->table, kw, keys.ptr, kbits.as<uint32_t>(), sums.as<unsigned long long>(), sbits.as<uint32_t>(),
+          counts.as<long long>(), reinterpret_cast<unsigned long long*>(slot.dev()));
+    }
     B2_LAUNCHED();
     count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(kbits.as<uint32_t>(), n, (int64_t)(bb / 4), slot.dev() + 1);
     B2_LAUNCHED();
     count_zero_bits_kernel<<<grid_for(n, kBlock * 32 * 4, kSMs * 4), kBlock, 0, s>>>(sbits.as<uint32_t>(), n, (int64_t)(bb / 4), slot.dev() + 2);
     B2_LAUNCHED();
     B2_RETURN_NOT_OK(slot.fetch(s));
-    if (slot.host()[0] != n) return set_error(B2_UNKNOWN_ERROR, "group-by emitted %lld of %lld groups", (long long)slot.host()[0], (long long)n);
+    const int64_t emitted = slot.host()[0] + dense_null;
+    if (emitted != n) return set_error(B2_UNKNOWN_ERROR, "group-by emitted %lld of %lld groups", (long long)emitted, (long long)n);
     key_nulls = slot.host()[1];
     sum_nulls = slot.host()[2];
   }

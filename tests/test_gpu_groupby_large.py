@@ -242,3 +242,41 @@ def test_dense_windows_are_verified_not_trusted(ctx):
     k3 = k.copy()
     k3[2_000_001] = -5                       # just below the sampled minimum but inside the slack: still dense
     check_path(ctx, pa.array(k3), pa.array(v, mask=m), 0, "dense")
+
+
+def test_dense_state_coexists_with_the_hash_table(ctx):
+    """consume() calls that take different paths into one object: dense, dense with another window (the first state is
+    flushed into the table), compact, general (full-range keys), and a merge of partial states -- finalize must join all"""
+    rng = np.random.default_rng(SEED + 43)
+    n = 4_300_000
+    batches = [
+        (rng.integers(0, 200_000, n, dtype=np.int64), "dense"),
+        (rng.integers(100_000, 300_000, n, dtype=np.int64), "dense"),            # sample inside [0, 200k + slack)? no: new window
+        (rng.integers(5_000_000, 5_400_000, n, dtype=np.int64), "dense"),        # disjoint window
+        (rng.integers(0, 600_000, 2_500_000, dtype=np.int64), "compact"),        # < 2^22 rows: partitioned
+        (np.concatenate([rng.integers(0, 600_000, 2_400_000, dtype=np.int64), [np.iinfo(np.int64).min, -1, np.iinfo(np.int64).max]]), "general"),
+    ]
+    g = bc.GroupBySumCount(pa.int64(), pa.int64(), ctx=ctx)
+    all_k, all_v = [], []
+    for kk, _ in batches:
+        keys = pa.array(kk, mask=rng.random(len(kk)) < 0.01)
+        vals = pa.array(rng.integers(-100, 101, len(kk), dtype=np.int64), mask=rng.random(len(kk)) < 0.1)
+        g.consume(DeviceArray.from_arrow(keys, ctx), DeviceArray.from_arrow(vals, ctx))
+        all_k.append(keys)
+        all_v.append(vals)
+    paths = g.path_counts()
+    assert paths == {"dense": 3, "compact": 1, "general": 1, "atomic": 0}, paths
+    # plus partial states of a sixth shard, merged the way the owner GPU does after the exchange
+    k6 = pa.array(rng.integers(0, 700_000, 2_200_000, dtype=np.int64))
+    v6 = pa.array(rng.integers(-100, 101, 2_200_000, dtype=np.int64), mask=rng.random(2_200_000) < 0.1)
+    h = bc.GroupBySumCount(pa.int64(), pa.int64(), ctx=ctx)
+    h.consume(DeviceArray.from_arrow(k6, ctx), DeviceArray.from_arrow(v6, ctx))
+    g.merge(*h.finalize())
+    all_k.append(k6)
+    all_v.append(v6)
+    k, s, c = [x.to_arrow() for x in g.finalize()]
+    got = pa.table({"k": k, "v_sum": s, "v_count": c}).sort_by("k")
+    want = reference(pa.concat_arrays(all_k), pa.concat_arrays(all_v))
+    assert got["k"].combine_chunks().equals(want["k"].combine_chunks())
+    assert got["v_count"].combine_chunks().equals(want["v_count"].combine_chunks())
+    assert got["v_sum"].combine_chunks().equals(want["v_sum"].combine_chunks())
