@@ -124,6 +124,7 @@ PROTOTYPES = [
     ("b2_filter", C.c_int, [_P, _A, _A, C.c_int, _A, _P]),
     ("b2_filter_indices", C.c_int, [_P, _A, C.c_int, _A, _P]),
     ("b2_take", C.c_int, [_P, _A, _A, C.c_int, _A, _P]),
+    ("b2_take_cast_arith", C.c_int, [_P, _A, _A, C.c_int32, C.c_int, _V, _A, _P]),
     ("b2_binary_data_size", C.c_int, [_P, _A, _I64P, _P]),
     ("b2_sort_indices", C.c_int, [_P, _A, C.c_int, C.c_int, _A, _P]),
     ("b2_grouper_create", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.POINTER(_P)]),

@@ -329,6 +329,28 @@ def take(values: DeviceArray, indices: DeviceArray, boundscheck: bool = True) ->
     return _out(ctx, cout, values.type, values.dictionary)
 
 
+def take_cast_arith(values: DeviceArray, indices: DeviceArray, target_type, op: str, other) -> DeviceArray:
+    """Fused `op(cast(take(values, indices), target_type, safe=False), other)` -- one kernel instead of three
+    (b2_take_cast_arith; the reference evaluates the same Expression kernel by kernel, compute/expression.cc:722-797).
+    Falls back to the three calls for operand shapes the fused kernel does not cover."""
+    target_type = pa.lib.ensure_type(target_type)
+    fusable = (values.type in (pa.float64(), pa.float32(), pa.int64(), pa.int32()) and target_type in (pa.float32(), pa.float64())
+               and indices.type in (pa.int32(), pa.uint32(), pa.int64(), pa.uint64()) and op in ("add", "subtract", "multiply")
+               and isinstance(other, DeviceArray) and other.type == target_type and len(other) == len(indices))
+    if not fusable:
+        return _arith(op, cast(take(values, indices), target_type, safe=False), other)
+    ctx = values.ctx
+    keep = []
+    ov = cabi.B2Value()
+    co = other._c()
+    keep.append(co)
+    ov.array, ov.scalar = C.pointer(co), None
+    cv, ci, cout = values._c(), indices._c(), cabi.B2Array()
+    check(ctx.lib.b2_take_cast_arith(ctx.handle, C.byref(cv), C.byref(ci), type_id(target_type), cabi.ARITH_OPS[op], C.byref(ov),
+                                     C.byref(cout), ctx.stream))
+    return _out(ctx, cout, target_type)
+
+
 def array_take(values, indices, boundscheck=True):
     return take(values, indices, boundscheck)
 

@@ -740,10 +740,16 @@ def run_gpu(args):
     indices = DeviceArray.from_pointers(ctx, pa.int64(), n, idx_t.data_ptr())
     other = DeviceArray.from_pointers(ctx, pa.float32(), n, other_t.data_ptr(), validity_ptr=ovalid_t.data_ptr(), null_count=o_nulls)
 
-    def pipeline(v, i, o):
+    def pipeline_unfused(v, i, o):   # three CallFunction-equivalent calls
         t = bc.take(v, i)
         c = bc.cast(t, pa.float32(), safe=False)
         return bc.add(c, o)
+
+    def pipeline(v, i, o):           # the same expression through the fused entry point (b2_take_cast_arith): one kernel
+        return bc.take_cast_arith(v, i, pa.float32(), "add", o)
+
+    if args.unfused:
+        pipeline = pipeline_unfused
 
     sync_all, max_over_ranks = env.sync_all, env.max_over_ranks
 
@@ -785,6 +791,7 @@ def run_gpu(args):
         k_ms += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
         del t, c, o
     k_ms /= args.steps
+    fused_ms = env.timed(lambda: bc.take_cast_arith(values, indices, pa.float32(), "add", other), args.steps)
 
     # ---- timed region: K steps, device resident ----
     sampler = ClockSampler(local) if rank == 0 else None
@@ -927,6 +934,9 @@ def run_gpu(args):
          "gbs": ALG_CAST * n / (k_ms[1] * 1e-3) / 1e9, "frac": ALG_CAST * n / (k_ms[1] * 1e-3) / 1e9 / peak},
         {"name": "map2_kernel<float> (add)", "ms": float(k_ms[2]), "alg_bytes_per_row": ALG_ADD,
          "gbs": ALG_ADD * n / (k_ms[2] * 1e-3) / 1e9, "frac": ALG_ADD * n / (k_ms[2] * 1e-3) / 1e9 / peak},
+        {"name": "take_cast_arith_kernel<double,int64,float> (fused take+cast+add, random idx)", "ms": float(fused_ms),
+         "alg_bytes_per_row": ALG_PIPELINE, "gbs": ALG_PIPELINE * n / (fused_ms * 1e-3) / 1e9,
+         "frac": ALG_PIPELINE * n / (fused_ms * 1e-3) / 1e9 / peak},
     ]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "take_traffic.json")
@@ -946,7 +956,9 @@ def run_gpu(args):
                    if n == 1_000_000_000 else f"Take+Cast(f64->f32)+Add, null_probability=0.1, {n} rows/GPU",
                    "rows_per_gpu": n, "indices": "uniform random int64", "l2": "inputs (20 GB) are far larger than the 126 MB L2",
                    "pipeline_alg_bytes_per_row": ALG_PIPELINE, "pipeline_gbs": ALG_PIPELINE * n * world / (ms_per_step * 1e-3) / 1e9,
-                   "out_null_count": int(out_nulls), "parity_checksum_ok": bool(pipeline_ok), "numa_node": env.numa},
+                   "out_null_count": int(out_nulls), "parity_checksum_ok": bool(pipeline_ok), "numa_node": env.numa,
+                   "calls_per_step": "3 (take, cast, add)" if args.unfused else "1 (b2_take_cast_arith: the fused take+cast+add kernel)",
+                   "unfused_ms_per_step": float(k_ms.sum())},
         "roofline": {"bound": "hbm", "achieved": take_gbs, "peak": peak, "unit": "GB/s", "frac": take_gbs / peak,
                      "traffic": traffic, "kernel": "take_kernel<8,int64_t,true>", "peak_source": peak_src,
                      "alg_bytes_per_launch": ALG_TAKE * n},
@@ -976,6 +988,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the indices/other columns in the host-buffer leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` array (c1/c3/c4/c5 at full size, N = 1 only)")
     ap.add_argument("--no-multi", action="store_true", help="skip the sharded group-by / sort legs")
+    ap.add_argument("--unfused", action="store_true", help="run the pipeline as three calls (take, cast, add) instead of the fused kernel")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

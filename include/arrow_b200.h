@@ -271,6 +271,15 @@ B2_API int b2_filter_indices(B2Context* ctx, const B2Array* mask, int null_selec
 B2_API int b2_take(B2Context* ctx, const B2Array* values, const B2Array* indices,
                    int boundscheck, B2Array* out, void* stream);
 
+/* Fused Take -> Cast -> arithmetic: out[i] = op(cast<to_type>(values[indices[i]]), other[i]) in one pass, i.e. the
+ * Expression add(cast(take(values, indices), T), other) that ExecuteScalarExpression (compute/expression.cc:722-797) runs
+ * as three kernels with two materialised intermediates.  Results are identical to b2_take + b2_cast_numeric(unsafe) +
+ * b2_binary_arith: same validity (indices AND values-at-index AND other), same IndexError, one IEEE operation per slot.
+ * values: float64 / float32 / int64 / int32; indices: 32- or 64-bit integers; to_type: B2_FLOAT or B2_DOUBLE;
+ * op: B2_ADD / B2_SUBTRACT / B2_MULTIPLY; other: array (or valid scalar) of to_type. */
+B2_API int b2_take_cast_arith(B2Context* ctx, const B2Array* values, const B2Array* indices, int32_t to_type, int op,
+                              const B2Value* other, B2Array* out, void* stream);
+
 /* Bytes of character data a (large_)utf8/binary array spans: offsets[offset+length] -
  * offsets[offset] (one D2H read).  Lets the host size the data buffer of an output the
  * way BufferSpan::size does (array/data.h:525-532). */
