@@ -154,10 +154,30 @@ __global__ void __launch_bounds__(kBlock) dense_consume_kernel(DenseArgs a) {
   }
 }
 
-// packed words of one sub-batch -> 64-bit sums (of the real values) and counts; the packed table is zeroed again
+// largest count field in the packed table: the drain after a sub-batch is only NEEDED when the next sub-batch could push
+// a count past its m + 1 bits, i.e. when max_count + rows_of_next_sub_batch >= 2^(m+1) (for keys spread over many groups it never is)
+__global__ void __launch_bounds__(kBlock) dense_maxcount_kernel(const unsigned long long* __restrict__ table, unsigned long long range, int sb,
+                                                                unsigned long long* max_count) {
+  unsigned long long m = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)kBlock + threadIdx.x; i < range; i += (unsigned long long)gridDim.x * kBlock) {
+    const unsigned long long c = table[i] >> sb;
+    m = c > m ? c : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_down_sync(0xffffffffu, m, o);
+    m = v > m ? v : m;
+  }
+  if (lane_id() == 0 && m) atomicMax(max_count, m);
+}
+
+// packed words accumulated so far -> 64-bit sums (of the real values) and counts; the packed table is zeroed again.
+// `guard` != NULL: skip the whole pass unless *guard + next_rows could overflow a count field (see dense_maxcount_kernel).
 __global__ void __launch_bounds__(kBlock) dense_drain_kernel(unsigned long long* table, unsigned long long range, int sb,
                                                              unsigned long long vbase, unsigned long long* sums,
-                                                             unsigned long long* counts) {
+                                                             unsigned long long* counts, const unsigned long long* guard,
+                                                             unsigned long long next_rows, unsigned long long limit) {
+  if (guard && *guard + next_rows < limit) return;
   const unsigned long long smask = (1ull << sb) - 1ull;
   for (unsigned long long i = blockIdx.x * (unsigned long long)kBlock + threadIdx.x; i < range; i += (unsigned long long)gridDim.x * kBlock) {
     const unsigned long long p = table[i];

@@ -584,8 +584,20 @@ static int try_dense_chunk(B2GroupBySumCount* g, const RawColumns& raw, int64_t 
       else dense_consume_kernel<0, 0><<<grid, kBlock, 0, s>>>(a);
       B2_LAUNCHED();
     }
-    dense_drain_kernel<<<grid_for((int64_t)range, kBlock * 8, ctx->sm_count * 8), kBlock, 0, s>>>(
-        packed.as<unsigned long long>(), range, sb, vbase, sums.as<unsigned long long>(), counts.as<unsigned long long>());
+    // Fold the packed words into the 64-bit arrays only when the NEXT sub-batch could overflow a count field (2^m rows of
+    // one key): a cheap max-count pass (reads the table once) guards the drain; the last sub-batch always drains.
+    const bool last = off + sub >= cn;
+    const int dgrid = grid_for((int64_t)range, kBlock * 8, ctx->sm_count * 8);
+    unsigned long long* d_max = reinterpret_cast<unsigned long long*>(sslot.dev() + 4);
+    if (!last) {
+      B2_CUDA(cudaMemsetAsync(d_max, 0, 8, s));
+      dense_maxcount_kernel<<<dgrid, kBlock, 0, s>>>(packed.as<unsigned long long>(), range, sb, d_max);
+      B2_LAUNCHED();
+    }
+    const int64_t next_rows = last ? 0 : (cn - off - sub < sub ? cn - off - sub : sub);
+    dense_drain_kernel<<<dgrid, kBlock, 0, s>>>(packed.as<unsigned long long>(), range, sb, vbase, sums.as<unsigned long long>(),
+                                                counts.as<unsigned long long>(), last ? nullptr : d_max, (unsigned long long)next_rows,
+                                                1ull << m);
     B2_LAUNCHED();
   }
   B2_RETURN_NOT_OK(sslot.fetch(s));
@@ -794,6 +806,27 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
   if (max_chunk > mem_rows) max_chunk = mem_rows > kChunkRows ? mem_rows / kPartTile * kPartTile : kChunkRows;
   for (int64_t row0 = 0; row0 < n;) {
     const int64_t remaining = n - row0;
+    // the direct-addressed path needs no per-row scratch memory: it is offered everything that is left, whatever the
+    // memory-driven chunk size of the partitioned paths
+    {
+      ScalarSlot dslot(ctx);
+      B2_RETURN_NOT_OK(dslot.zero(s));
+      raw.row0 = row0;
+      bool dense_all = false;
+      int dst;
+      unsigned long long* ddc = reinterpret_cast<unsigned long long*>(dslot.dev());
+      switch (kw) {
+        case 1: dst = try_dense_chunk<1>(g, raw, remaining, s, ddc, nullptr, nullptr, 0, &dense_all); break;
+        case 2: dst = try_dense_chunk<2>(g, raw, remaining, s, ddc, nullptr, nullptr, 0, &dense_all); break;
+        case 4: dst = try_dense_chunk<4>(g, raw, remaining, s, ddc, nullptr, nullptr, 0, &dense_all); break;
+        default: dst = try_dense_chunk<8>(g, raw, remaining, s, ddc, nullptr, nullptr, 0, &dense_all); break;
+      }
+      if (dst != B2_OK) return dst;
+      if (dense_all) {
+        ++g->chunks_dense;
+        break;
+      }
+    }
     const int64_t cn = remaining < max_chunk ? remaining : max_chunk;
     const uint64_t ovf_cap = static_cast<uint64_t>(cn < kChunkRows ? cn : kChunkRows);
     const int64_t est = g->hint > 0 ? g->hint : (g->groups > 0 ? (int64_t)g->groups : (1ll << 40));
@@ -810,19 +843,6 @@ static int fused_consume_partitioned(B2GroupBySumCount* g, const B2Array* keys, 
     bool done = false;
     unsigned long long* op = ovf_pairs.as<unsigned long long>();
     unsigned int* oc = ovf_counts.as<unsigned int>();
-    bool dense_done = false;
-    switch (kw) {
-      case 1: st = try_dense_chunk<1>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
-      case 2: st = try_dense_chunk<2>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
-      case 4: st = try_dense_chunk<4>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
-      default: st = try_dense_chunk<8>(g, raw, cn, s, dc, op, oc, ovf_cap, &dense_done); break;
-    }
-    if (st != B2_OK) return st;
-    if (dense_done) {
-      ++g->chunks_dense;
-      row0 += cn;
-      continue;  // the hash table was not touched (it may not even exist yet)
-    }
     // the partitioned paths insert into the global table: create it on first use
     B2_RETURN_NOT_OK(ensure_table(g, next_pow2(2 * (uint64_t)(g->hint > (1 << 19) ? g->hint : (1 << 19))), s));
     switch (kw) {

@@ -172,3 +172,32 @@ def test_fullsize_group_by(ctx, torch_mod):
     has = want_cnt[k] > 0  # groups whose values are all null finalize to a null sum (min_count = 1)
     assert torch.equal(s[has], want_sum[k][has])
     assert sums.null_count == int((~has).sum().item())
+
+
+def test_dense_group_by_hot_key_drains(ctx, torch_mod):
+    """direct-addressed group-by with a HOT key: more than 2^26 rows of one key force the guarded drain between
+    sub-batches (groupby_dense.cuh: the packed count field of a sub-batch holds 2^26 rows for this value window)"""
+    torch = torch_mod
+    n = min(N, 300_000_000)
+    groups = 1_000_000
+    gen = torch.Generator(device="cuda").manual_seed(SEED + 9)
+    keys_t = torch.randint(0, groups, (n,), dtype=torch.int64, device="cuda", generator=gen)
+    keys_t[torch.rand(n, device="cuda", generator=gen) < 0.6] = 777            # ~180M rows of one key
+    vals_t = torch.randint(-100, 101, (n,), dtype=torch.int64, device="cuda", generator=gen)
+    valid_t, n_valid = random_bitmap(torch, n, 0.9, gen)
+    keys = DeviceArray.from_pointers(ctx, pa.int64(), n, keys_t.data_ptr())
+    vals = DeviceArray.from_pointers(ctx, pa.int64(), n, vals_t.data_ptr(), validity_ptr=valid_t.data_ptr(), null_count=n - n_valid)
+    g = bc.GroupBySumCount(pa.int64(), pa.int64(), ctx=ctx)
+    run(ctx, torch, lambda: g.consume(keys, vals))
+    assert g.path_counts()["dense"] == 1
+    out_keys, sums, counts = run(ctx, torch, g.finalize)
+    ok = bits_to_bool(torch, valid_t, n)
+    want_sum = torch.zeros(groups, dtype=torch.int64, device="cuda").index_add_(0, keys_t[ok], vals_t[ok])
+    want_cnt = torch.bincount(keys_t[ok], minlength=groups)
+    present = torch.bincount(keys_t, minlength=groups) > 0
+    k = as_tensor(torch, out_keys, torch.int64)
+    assert len(out_keys) == int(present.sum().item())
+    assert torch.equal(as_tensor(torch, counts, torch.int64), want_cnt[k])
+    has = want_cnt[k] > 0
+    assert torch.equal(as_tensor(torch, sums, torch.int64)[has], want_sum[k][has])
+    assert int(want_cnt[777].item()) > (1 << 26)
