@@ -243,4 +243,29 @@ __device__ __forceinline__ uint32_t lookback_exclusive(const volatile uint32_t* 
   return excl;
 }
 
+// 64-bit-cell variant for columns of 2^30 rows or more (bits 63:62 = flag, bits 61:0 = count)
+__device__ __forceinline__ unsigned long long lookback_exclusive64(const volatile unsigned long long* col, int64_t tile, size_t stride) {
+  unsigned long long excl = 0;
+  int64_t t = tile - 1;
+  while (t >= 0) {
+    unsigned long long c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (t - k >= 0) ? col[static_cast<size_t>(t - k) * stride] : (2ull << 62);
+    bool done = false;
+    int used = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned f = static_cast<unsigned>(c[k] >> 62);
+      if (!done && used == k && f != 0) {
+        excl += c[k] & 0x3fffffffffffffffull;
+        ++used;
+        done = f == 2;
+      }
+    }
+    if (done) break;
+    t -= used;
+  }
+  return excl;
+}
+
 }  // namespace b2

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const K* __res
   __shared__ uint32_t s_hist[8 * kRadix];
   for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) s_hist[i] = 0;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * kSortThreads + threadIdx.x; i < n; i += gridDim.x * kSortThreads) {
+  for (uint64_t i = blockIdx.x * kSortThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kSortThreads) {  // 64-bit: n may be close to 2^32
     K k = __ldcs(keys + i);
 #pragma unroll
     for (int p = 0; p < (int)sizeof(K); ++p)
@@ -189,7 +189,7 @@ struct OnesweepArgs {
   uint32_t n;
   int shift;
   const uint32_t* digit_base;  // [256] exclusive bin offsets of this pass
-  uint32_t* lookback;          // [n_tiles][256], zeroed
+  void* lookback;              // [n_tiles][256] cells (uint32, or uint64 for >= 2^30 rows), zeroed
   uint32_t* ticket;            // zeroed
 };
 
@@ -199,7 +199,8 @@ constexpr size_t onesweep_smem() {
          kRadix * sizeof(uint32_t);
 }
 
-template <typename K, bool LAST>
+// WIDE: 64-bit look-back cells -- an inclusive prefix no longer fits 30 bits once the column has 2^30 rows
+template <typename K, bool LAST, bool WIDE>
 __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<K> a) {
   extern __shared__ __align__(16) uint8_t smem[];
   K* s_keys = reinterpret_cast<K*>(smem);
@@ -272,9 +273,15 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
     }
     count = run;
     if (tid == kRadix - 1) count -= (kSortTile - tile_n);  // padding keys are all-ones
-    volatile uint32_t* lb = a.lookback;
-    if (tile == 0) lb[tid] = kFlagIncl | count;
-    else lb[(size_t)tile * kRadix + tid] = kFlagAgg | count;
+    if (WIDE) {
+      volatile unsigned long long* lb = static_cast<volatile unsigned long long*>(a.lookback);
+      if (tile == 0) lb[tid] = (2ull << 62) | count;
+      else lb[(size_t)tile * kRadix + tid] = (1ull << 62) | count;
+    } else {
+      volatile uint32_t* lb = static_cast<volatile uint32_t*>(a.lookback);
+      if (tile == 0) lb[tid] = kFlagIncl | count;
+      else lb[(size_t)tile * kRadix + tid] = kFlagAgg | count;
+    }
     // block exclusive scan of `run` over the 256 digits (padding only occupies the tail of bin 255)
     incl = run;
 #pragma unroll
@@ -310,8 +317,16 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_kernel(OnesweepArgs<
   if (tid < kRadix) {
     uint32_t excl = 0;
     if (tile > 0) {
-      excl = lookback_exclusive(a.lookback + tid, tile, kRadix);
-      reinterpret_cast<volatile uint32_t*>(a.lookback)[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
+      if (WIDE) {
+        volatile unsigned long long* lb = static_cast<volatile unsigned long long*>(a.lookback);
+        const unsigned long long e = lookback_exclusive64(lb + tid, tile, kRadix);
+        lb[(size_t)tile * kRadix + tid] = (2ull << 62) | (e + count);
+        excl = static_cast<uint32_t>(e);  // < 2^32: positions stay 32-bit
+      } else {
+        volatile uint32_t* lb = static_cast<volatile uint32_t*>(a.lookback);
+        excl = lookback_exclusive(lb + tid, tile, kRadix);
+        lb[(size_t)tile * kRadix + tid] = kFlagIncl | (excl + count);
+      }
     }
     s_gbase[tid] = a.digit_base[tid] + excl - bin_off;
   }
@@ -411,13 +426,17 @@ static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null
   }
   const uint32_t n_tiles = (uint32_t)((nv + kSortTile - 1) / kSortTile);
   Temp lookback(ctx, s);
-  const size_t lb_bytes = (size_t)n_tiles * kRadix * sizeof(uint32_t) + 256;
+  const bool wide = nv >= (1ll << 30);
+  const size_t cell = wide ? sizeof(unsigned long long) : sizeof(uint32_t);
+  const size_t lb_bytes = (size_t)n_tiles * kRadix * cell + 256;
   B2_RETURN_NOT_OK(lookback.alloc(lb_bytes));
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles * kRadix * sizeof(uint32_t));
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(lookback.as<char>() + (size_t)n_tiles * kRadix * cell);
   // the attribute is per DEVICE (a process may sort on several): set it on every call, it is cheap
   constexpr size_t smem = onesweep_smem<K>();
-  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   K* kin = keysA.as<K>();
   K* kout = keysB.as<K>();
   uint32_t* iin = idxA.as<uint32_t>();
@@ -435,10 +454,15 @@ static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null
     a.n = (uint32_t)nv;
     a.shift = p * kRadixBits;
     a.digit_base = dbase.as<uint32_t>() + p * kRadix;
-    a.lookback = lookback.as<uint32_t>();
+    a.lookback = lookback.ptr;
     a.ticket = ticket;
-    if (last) onesweep_kernel<K, true><<<n_tiles, kSortThreads, smem, s>>>(a);
-    else onesweep_kernel<K, false><<<n_tiles, kSortThreads, smem, s>>>(a);
+    if (wide) {
+      if (last) onesweep_kernel<K, true, true><<<n_tiles, kSortThreads, smem, s>>>(a);
+      else onesweep_kernel<K, false, true><<<n_tiles, kSortThreads, smem, s>>>(a);
+    } else {
+      if (last) onesweep_kernel<K, true, false><<<n_tiles, kSortThreads, smem, s>>>(a);
+      else onesweep_kernel<K, false, false><<<n_tiles, kSortThreads, smem, s>>>(a);
+    }
     B2_LAUNCHED();
     K* tk = kin; kin = kout; kout = tk;
     uint32_t* ti = iin; iin = iout; iout = ti;
@@ -459,8 +483,8 @@ extern "C" int b2_sort_indices(B2Context* ctx, const B2Array* values, int order,
   if (!type_is_numeric(values->type))
     return set_error(B2_NOT_IMPLEMENTED, "sort_indices: unsupported type id %d", values->type);
   const int64_t n = values->length;
-  if (n >= (1ll << 30))
-    return set_error(B2_NOT_IMPLEMENTED, "sort_indices: arrays of 2^30 rows or more must be sorted as chunks");
+  if (n >= (1ll << 32) - 8192)  // row numbers travel as uint32 between the passes
+    return set_error(B2_NOT_IMPLEMENTED, "sort_indices: arrays of 2^32 rows or more must be sorted as chunks");
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
   Temp data(ctx, s);

@@ -125,9 +125,13 @@ def test_fullsize_take_round_trip(ctx, torch_mod):
     assert torch.equal(as_tensor(torch, back, torch.float64), vals_t)
 
 
-def test_fullsize_sort_indices(ctx, torch_mod):
+@pytest.mark.parametrize("beyond_2_30", [False, True])
+def test_fullsize_sort_indices(ctx, torch_mod, beyond_2_30):
+    """beyond_2_30: 2^30 + 70001 rows -- the 64-bit look-back cells of the radix passes (round 1 refused >= 2^30 rows)"""
     torch = torch_mod
-    n = min(N, (1 << 30) - 1)
+    if beyond_2_30 and N < 1_000_000_000:
+        pytest.skip("full-size run only")
+    n = (1 << 30) + 70001 if beyond_2_30 else min(N, (1 << 30) - 1)
     gen = torch.Generator(device="cuda").manual_seed(SEED + 2)
     keys_t = torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device="cuda", generator=gen)
     valid_t, n_valid = random_bitmap(torch, n, 0.9, gen)
