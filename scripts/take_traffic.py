@@ -20,7 +20,7 @@ from bench import SEED, make_validity
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=1_000_000_000)
-ap.add_argument("--variants", default="valid,novalid")
+ap.add_argument("--variants", default="valid,novalid,fused")
 args = ap.parse_args()
 n = args.rows
 torch.cuda.set_device(0)
@@ -33,6 +33,17 @@ idx_t = torch.randint(0, n, (n,), dtype=torch.int64, device="cuda", generator=ge
 torch.cuda.synchronize()
 idx = DeviceArray.from_pointers(ctx, pa.int64(), n, idx_t.data_ptr())
 for v in args.variants.split(","):
+    if v == "fused":   # launch 3: the fused take+cast+add kernel of the bench step (take_cast_arith_kernel<double,long,float,true>)
+        other_t = torch.rand(n, dtype=torch.float32, device="cuda", generator=gen) * 1e6
+        ovalid_t, o_nulls = make_validity(torch, n, gen)
+        torch.cuda.synchronize()
+        values = DeviceArray.from_pointers(ctx, pa.float64(), n, values_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
+        other = DeviceArray.from_pointers(ctx, pa.float32(), n, other_t.data_ptr(), validity_ptr=ovalid_t.data_ptr(), null_count=o_nulls)
+        out = bc.take_cast_arith(values, idx, pa.float32(), "add", other)
+        ctx.sync()
+        print(v, "nulls", out.null_count, flush=True)
+        del out
+        continue
     if v == "valid":
         values = DeviceArray.from_pointers(ctx, pa.float64(), n, values_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
     else:
