@@ -127,6 +127,7 @@ PROTOTYPES = [
     ("b2_take_cast_arith", C.c_int, [_P, _A, _A, C.c_int32, C.c_int, _V, _A, _P]),
     ("b2_binary_data_size", C.c_int, [_P, _A, _I64P, _P]),
     ("b2_sort_indices", C.c_int, [_P, _A, C.c_int, C.c_int, _A, _P]),
+    ("b2_sort_payload", C.c_int, [_P, _A, _A, C.c_int, C.c_int, _A, _P]),
     ("b2_grouper_create", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.POINTER(_P)]),
     ("b2_grouper_destroy", None, [_P]),
     ("b2_grouper_consume", C.c_int, [_P, _A, _A, _P]),
@@ -152,6 +153,7 @@ PROTOTYPES = [
     ("b2_hash_partition", C.c_int, [_P, _A, C.c_int, _A, _P]),
     ("b2_range_partition", C.c_int, [_P, _A, _A, C.c_int, _A, _P]),
     ("b2_bincount", C.c_int, [_P, _A, C.c_int, _I64P, _P]),
+    ("b2_range_split", C.c_int, [_P, _A, _A, C.c_int, C.c_uint64, _A, _A, _I64P, _P]),
     ("b2_boolean", C.c_int, [_P, C.c_int, _V, _V, _A, _P]),
     ("b2_validity", C.c_int, [_P, C.c_int, _A, C.c_int, _A, _P]),
     ("b2_comm_unique_id", C.c_int, [_P]),

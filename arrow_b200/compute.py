@@ -383,6 +383,16 @@ def array_sort_indices(arr: DeviceArray, order="ascending", null_placement="at_e
     return _out(ctx, cout, pa.uint64())
 
 
+def sort_payload(arr: DeviceArray, payload: DeviceArray, order="ascending", null_placement="at_end") -> DeviceArray:
+    """stable sort of `arr` where row i carries payload[i] (uint32) instead of i: returns the payloads in sorted order
+    (uint64) -- array_sort_indices followed by take(payload, indices), in the radix passes themselves"""
+    ctx = arr.ctx
+    ca, cp_, cout = arr._c(), payload._c(), cabi.B2Array()
+    check(ctx.lib.b2_sort_payload(ctx.handle, C.byref(ca), C.byref(cp_), _order(order), _placement(null_placement),
+                                  C.byref(cout), ctx.stream))
+    return _out(ctx, cout, pa.uint64())
+
+
 def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", order=None) -> DeviceArray:
     """sort_indices meta function on one array (kernels/vector_sort.cc:856-924)."""
     o = "ascending"

@@ -10,6 +10,7 @@
 //                        Descending); null rows get id = n_splitters + 1 (they do not move).
 // Both are streaming HBM-bound passes: read W B/row, write 4 B/row.
 #include <type_traits>
+#include <vector>
 
 #include "bitmap.h"
 #include "hash_table.cuh"
@@ -62,6 +63,144 @@ __global__ void __launch_bounds__(kBlock) range_partition_kernel(const T* __rest
   }
 }
 
+// ---- range split: the sender side of the distributed SortIndices in two streaming passes -------------------------------
+// Stable (P+1)-way split of (value, row number) pairs by range id: bin = #splitters <= value in SortIndices' total order,
+// null rows in bin P.  Replaces range ids + sort_indices(ids) + two takes + an offset add (five passes over the shard) by
+// count -> scan -> scatter; the row numbers leave as uint32 (row_base + i), ready to be the payload of b2_sort_payload.
+constexpr int kSplitTile = 2048;
+constexpr int kSplitMaxBins = 32;  // P + 1 <= 32 (one bin per lane)
+
+template <typename T>
+__device__ __forceinline__ uint32_t range_bin(const T* __restrict__ values, const BitmapReader& valid, int64_t i, const uint64_t* s_split,
+                                              int n_split, bool descending) {
+  if (!valid.bit(i)) return static_cast<uint32_t>(n_split) + 1;
+  const uint64_t k = total_order_key<T>(values[i], descending);
+  uint32_t p = 0;
+  for (int j = 0; j < n_split; ++j) p += (s_split[j] <= k) ? 1u : 0u;
+  return p;
+}
+
+// tile_counts[bin * n_tiles + tile] = rows of the tile that fall in `bin` (bin-major: one scan gives absolute positions)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) range_split_count_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
+                                                                   const T* __restrict__ splitters, int n_split, bool descending,
+                                                                   int64_t n_tiles, int64_t* __restrict__ tile_counts) {
+  __shared__ uint64_t s_split[64];
+  __shared__ uint32_t s_cnt[kSplitMaxBins];
+  if (threadIdx.x < n_split) s_split[threadIdx.x] = total_order_key<T>(splitters[threadIdx.x], descending);
+  if (threadIdx.x < kSplitMaxBins) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const unsigned lane = lane_id();
+  uint32_t mine = 0;  // lane b counts bin b
+  for (int r = threadIdx.x; r < kSplitTile; r += kBlock) {
+    const int64_t i = tile * kSplitTile + r;
+    const uint32_t b = i < n ? range_bin<T>(values, valid, i, s_split, n_split, descending) : 0xffffffffu;
+    for (int q = 0; q <= n_split + 1; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, b == (uint32_t)q);
+      if ((int)lane == q) mine += __popc(m);
+    }
+  }
+  if ((int)lane <= n_split + 1 && mine) atomicAdd(&s_cnt[lane], mine);
+  __syncthreads();
+  if ((int)threadIdx.x <= n_split + 1) tile_counts[(int64_t)threadIdx.x * n_tiles + tile] = s_cnt[threadIdx.x];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) range_split_scatter_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
+                                                                     const T* __restrict__ splitters, int n_split, bool descending,
+                                                                     int64_t n_tiles, const int64_t* __restrict__ tile_offsets,
+                                                                     uint32_t row_base, T* __restrict__ out_values,
+                                                                     uint32_t* __restrict__ out_rows) {
+  __shared__ uint64_t s_split[64];
+  __shared__ uint32_t s_warp[kWarpsPerBlock][kSplitMaxBins];  // rows of each warp per bin, then exclusive over warps
+  if (threadIdx.x < n_split) s_split[threadIdx.x] = total_order_key<T>(splitters[threadIdx.x], descending);
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  constexpr int kRowsPerWarp = kSplitTile / kWarpsPerBlock;  // 256 consecutive rows per warp: rank order = row order
+  const int64_t w0 = tile * kSplitTile + (int64_t)warp * kRowsPerWarp;
+  const int bins = n_split + 2;
+  // pass A: this warp's rows per bin
+  uint32_t mine = 0;
+  uint32_t b_of[kRowsPerWarp / 32];
+#pragma unroll
+  for (int it = 0; it < kRowsPerWarp / 32; ++it) {
+    const int64_t i = w0 + it * 32 + lane;
+    b_of[it] = i < n ? range_bin<T>(values, valid, i, s_split, n_split, descending) : 0xffffffffu;
+    for (int q = 0; q < bins; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, b_of[it] == (uint32_t)q);
+      if ((int)lane == q) mine += __popc(m);
+    }
+  }
+  if ((int)lane < kSplitMaxBins) s_warp[warp][lane] = mine;
+  __syncthreads();
+  if (threadIdx.x < kSplitMaxBins) {  // exclusive over the warps, per bin
+    uint32_t run = 0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) {
+      const uint32_t c = s_warp[w][threadIdx.x];
+      s_warp[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // pass B: positions.  lane q keeps the running count of bin q inside this warp
+  uint32_t running = 0;
+#pragma unroll
+  for (int it = 0; it < kRowsPerWarp / 32; ++it) {
+    const int64_t i = w0 + it * 32 + lane;
+    const uint32_t b = b_of[it];
+    uint32_t rank = 0, before = 0;
+    for (int q = 0; q < bins; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, b == (uint32_t)q);
+      const uint32_t run_q = __shfl_sync(0xffffffffu, running, q);
+      if (b == (uint32_t)q) {
+        rank = __popc(m & lanemask_lt());
+        before = run_q;
+      }
+      if ((int)lane == q) running += __popc(m);
+    }
+    if (i < n) {
+      const int64_t pos = tile_offsets[(int64_t)b * n_tiles + tile] + s_warp[warp][b] + before + rank;
+      out_values[pos] = values[i];
+      out_rows[pos] = row_base + static_cast<uint32_t>(i);
+    }
+  }
+}
+
+// exclusive scan of a long int64 array by one CTA (same scheme as selection_binary.cu's tile scan)
+__global__ void __launch_bounds__(1024) split_scan_kernel(const int64_t* counts, int64_t n, int64_t* offsets) {
+  __shared__ int64_t warp_tot[32];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+  int64_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += counts[i];
+  int64_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int64_t w = warp_tot[t], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += v;
+    }
+    warp_tot[t] = wi - w;
+  }
+  __syncthreads();
+  int64_t run = incl - sum + warp_tot[t >> 5];
+  for (int64_t i = lo; i < hi; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+}
+
 // counts[b] = #rows with ids[i] == b for b < n_bins (rows with larger ids are counted in `out_of_range`)
 __global__ void __launch_bounds__(kBlock) bincount_kernel(const uint32_t* __restrict__ ids, int64_t n, uint32_t n_bins,
                                                           unsigned long long* counts) {
@@ -81,6 +220,73 @@ __global__ void __launch_bounds__(kBlock) bincount_kernel(const uint32_t* __rest
 }  // namespace b2
 
 using namespace b2;
+
+template <typename T>
+static int run_range_split(B2Context* ctx, const B2Array* values, const B2Array* splitters, int order, uint32_t row_base, void* out_values,
+                           uint32_t* out_rows, int64_t* out_counts, cudaStream_t s) {
+  const int64_t n = values->length;
+  const int n_split = (int)splitters->length;
+  const int bins = n_split + 2;
+  const int64_t n_tiles = (n + kSplitTile - 1) / kSplitTile;
+  Temp counts(ctx, s), offsets(ctx, s);
+  B2_RETURN_NOT_OK(counts.alloc(sizeof(int64_t) * (size_t)(bins * n_tiles)));
+  B2_RETURN_NOT_OK(offsets.alloc(sizeof(int64_t) * (size_t)(bins * n_tiles)));
+  BitmapReader valid(values->null_count == 0 ? nullptr : values->validity, values->offset, n);
+  const T* v = static_cast<const T*>(values->data) + values->offset;
+  const T* sp = static_cast<const T*>(splitters->data) + splitters->offset;
+  range_split_count_kernel<T><<<(unsigned)n_tiles, kBlock, 0, s>>>(v, valid, n, sp, n_split, order == 1, n_tiles, counts.as<int64_t>());
+  B2_LAUNCHED();
+  split_scan_kernel<<<1, 1024, 0, s>>>(counts.as<int64_t>(), (int64_t)bins * n_tiles, offsets.as<int64_t>());
+  B2_LAUNCHED();
+  range_split_scatter_kernel<T><<<(unsigned)n_tiles, kBlock, 0, s>>>(v, valid, n, sp, n_split, order == 1, n_tiles, offsets.as<int64_t>(),
+                                                                       row_base, static_cast<T*>(out_values), out_rows);
+  B2_LAUNCHED();
+  // bin sizes = differences of the bins' first offsets
+  std::vector<int64_t> first(bins);
+  for (int b = 0; b < bins; ++b)
+    B2_CUDA(cudaMemcpyAsync(&first[b], offsets.as<int64_t>() + (int64_t)b * n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < bins; ++b) out_counts[b] = (b + 1 < bins ? first[b + 1] : n) - first[b];
+  return B2_OK;
+}
+
+extern "C" int b2_range_split(B2Context* ctx, const B2Array* values, const B2Array* splitters, int order, uint64_t row_base,
+                              B2Array* out_values, B2Array* out_rows, int64_t* out_counts, void* stream) {
+  if (!ctx || !values || !splitters || !out_values || !out_rows || !out_counts) return set_error(B2_INVALID, "b2_range_split: null argument");
+  if (values->type != splitters->type) return set_error(B2_TYPE_ERROR, "splitters must have the values' type");
+  if (splitters->length > kSplitMaxBins - 2) return set_error(B2_INVALID, "at most %d splitters", kSplitMaxBins - 2);
+  if (splitters->null_count > 0) return set_error(B2_INVALID, "splitters must not contain nulls");
+  if (!type_is_numeric(values->type)) return set_error(B2_NOT_IMPLEMENTED, "b2_range_split: type id %d", values->type);
+  const int64_t n = values->length;
+  if (row_base + (uint64_t)n >= (1ull << 32)) return set_error(B2_NOT_IMPLEMENTED, "b2_range_split: row numbers must fit 32 bits");
+  cudaStream_t s = ctx->pick(stream);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  const int w = type_width(values->type);
+  Temp ov(ctx, s), orows(ctx, s);
+  B2_RETURN_NOT_OK(ov.alloc((size_t)n * w));
+  B2_RETURN_NOT_OK(orows.alloc(sizeof(uint32_t) * (size_t)n));
+  for (int b = 0; b < (int)splitters->length + 2; ++b) out_counts[b] = 0;
+  if (n > 0) {
+    int st;
+    const uint32_t rb = (uint32_t)row_base;
+    switch (values->type) {
+      case B2_INT8: st = run_range_split<int8_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_UINT8: st = run_range_split<uint8_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_INT16: st = run_range_split<int16_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_UINT16: st = run_range_split<uint16_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_INT32: st = run_range_split<int32_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_UINT32: st = run_range_split<uint32_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_INT64: st = run_range_split<int64_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_UINT64: st = run_range_split<uint64_t>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      case B2_FLOAT: st = run_range_split<float>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+      default: st = run_range_split<double>(ctx, values, splitters, order, rb, ov.ptr, orows.as<uint32_t>(), out_counts, s); break;
+    }
+    if (st != B2_OK) return st;
+  }
+  fill_out(out_values, values->type, n, 0, nullptr, ov.release());
+  fill_out(out_rows, B2_UINT32, n, 0, nullptr, orows.release());
+  return B2_OK;
+}
 
 extern "C" int b2_bincount(B2Context* ctx, const B2Array* ids, int n_bins, int64_t* out_counts, void* stream) {
   if (!ctx || !ids || !out_counts) return set_error(B2_INVALID, "b2_bincount: null argument");

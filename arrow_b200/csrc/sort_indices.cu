@@ -87,6 +87,7 @@ struct PrepareArgs {
   typename KeyOf<T>::type* keys;
   uint32_t* idx;
   uint64_t* out_nulls;  // final slots of the null rows (already offset to the null region)
+  const uint32_t* payload;  // NULL: row numbers; else the value that travels with row i instead of i (b2_sort_payload)
   int64_t n;
   bool descending, nan_first;
 };
@@ -129,9 +130,9 @@ __global__ void __launch_bounds__(kBlock) sort_prepare_kernel(PrepareArgs<T> a) 
     if ((selw >> (r & 63)) & 1) {
       T v = __ldcs(a.values + row);
       a.keys[vbase + before] = ordered_key<T>(v, a.descending, a.nan_first);
-      a.idx[vbase + before] = static_cast<uint32_t>(row);
+      a.idx[vbase + before] = a.payload ? a.payload[row] : static_cast<uint32_t>(row);
     } else {
-      a.out_nulls[nbase + (r - before)] = static_cast<uint64_t>(row);
+      a.out_nulls[nbase + (r - before)] = a.payload ? static_cast<uint64_t>(a.payload[row]) : static_cast<uint64_t>(row);
     }
   }
 }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kBlock) widen_idx_kernel(const uint32_t* in, u
 
 template <typename T>
 static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null_placement, uint64_t* out,
-                      cudaStream_t s) {
+                      cudaStream_t s, const uint32_t* payload = nullptr) {
   using K = typename KeyOf<T>::type;
   const int64_t n = values->length;
   const bool descending = order == 1, at_start = null_placement == 0;
@@ -385,6 +386,7 @@ static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null
     pa.keys = keysA.as<K>();
     pa.idx = idxA.as<uint32_t>();
     pa.out_nulls = out_nulls;
+    pa.payload = payload;
     pa.n = n;
     pa.descending = descending;
     pa.nan_first = at_start;
@@ -474,8 +476,22 @@ static int sort_typed(B2Context* ctx, const B2Array* values, int order, int null
 
 using namespace b2;
 
+static int sort_run(B2Context* ctx, const B2Array* values, int order, int null_placement, const uint32_t* payload, B2Array* out, void* stream);
+
 extern "C" int b2_sort_indices(B2Context* ctx, const B2Array* values, int order, int null_placement,
                                B2Array* out, void* stream) {
+  return sort_run(ctx, values, order, null_placement, nullptr, out, stream);
+}
+
+extern "C" int b2_sort_payload(B2Context* ctx, const B2Array* values, const B2Array* payload, int order, int null_placement,
+                               B2Array* out, void* stream) {
+  if (!payload) return set_error(B2_INVALID, "b2_sort_payload: null argument");
+  if (payload->type != B2_UINT32 || payload->null_count > 0 || !values || payload->length != values->length)
+    return set_error(B2_INVALID, "b2_sort_payload: payload must be a uint32 array without nulls of the values' length");
+  return sort_run(ctx, values, order, null_placement, static_cast<const uint32_t*>(payload->data) + payload->offset, out, stream);
+}
+
+static int sort_run(B2Context* ctx, const B2Array* values, int order, int null_placement, const uint32_t* payload, B2Array* out, void* stream) {
   if (!ctx || !values || !out) return set_error(B2_INVALID, "b2_sort_indices: null argument");
   if (order != 0 && order != 1) return set_error(B2_INVALID, "bad sort order %d", order);
   if (null_placement != 0 && null_placement != 1) return set_error(B2_INVALID, "bad null placement %d", null_placement);
@@ -493,16 +509,16 @@ extern "C" int b2_sort_indices(B2Context* ctx, const B2Array* values, int order,
     int st;
     uint64_t* o = data.as<uint64_t>();
     switch (values->type) {
-      case B2_INT8: st = sort_typed<int8_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_UINT8: st = sort_typed<uint8_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_INT16: st = sort_typed<int16_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_UINT16: st = sort_typed<uint16_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_INT32: st = sort_typed<int32_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_UINT32: st = sort_typed<uint32_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_INT64: st = sort_typed<int64_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_UINT64: st = sort_typed<uint64_t>(ctx, values, order, null_placement, o, s); break;
-      case B2_FLOAT: st = sort_typed<float>(ctx, values, order, null_placement, o, s); break;
-      default: st = sort_typed<double>(ctx, values, order, null_placement, o, s); break;
+      case B2_INT8: st = sort_typed<int8_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_UINT8: st = sort_typed<uint8_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_INT16: st = sort_typed<int16_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_UINT16: st = sort_typed<uint16_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_INT32: st = sort_typed<int32_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_UINT32: st = sort_typed<uint32_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_INT64: st = sort_typed<int64_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_UINT64: st = sort_typed<uint64_t>(ctx, values, order, null_placement, o, s, payload); break;
+      case B2_FLOAT: st = sort_typed<float>(ctx, values, order, null_placement, o, s, payload); break;
+      default: st = sort_typed<double>(ctx, values, order, null_placement, o, s, payload); break;
     }
     if (st != B2_OK) return st;
   }

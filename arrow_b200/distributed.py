@@ -240,23 +240,38 @@ def sort_indices(values, ops, xchg=None, samples_per_rank: int = 4096, return_ke
         row0 = int(heads[:rank, 0].sum())
         parts = [gathered[r, 16: 16 + int(heads[r, 1]) * width].contiguous().view(sample.dtype) for r in range(P)]
         splitters = ops.pick_splitters(torch.cat(parts), P, ops.type_of(values))
-        dest = ops.range_partition(values, splitters)                  # nulls get id P (= P-1 splitters + 1)
-        order, counts = ops.partition_plan(dest, P + 1)
-        n_valid = sum(counts[:P])
-        gidx = ops.add_offset(order, row0)                             # global row numbers, partition order
-        valid_part = ops.take(values, ops.slice(order, 0, n_valid))
+        n_total = int(heads[:, 0].sum())
+        narrow = n_total < (1 << 32)        # global row numbers fit 32 bits: they travel as uint32 and ride along the
+        if narrow:                          # owner's radix passes as the sort payload (no gather afterwards)
+            # one stable split of (value, global row) by range id: count -> scan -> scatter (b2_range_split)
+            valid_all, rows_all, counts = ops.range_split(values, splitters, row0)
+            n_valid = sum(counts[:P])
+            valid_part, gsend = ops.slice(valid_all, 0, n_valid), ops.slice(rows_all, 0, n_valid)
+            null_idx = ops.raw_tensor(ops.slice(rows_all, n_valid, n_local - n_valid))
+            null_idx = null_idx.to(torch.int64) & 0xFFFFFFFF
+        else:
+            dest = ops.range_partition(values, splitters)              # nulls get id P (= P-1 splitters + 1)
+            order, counts = ops.partition_plan(dest, P + 1)
+            n_valid = sum(counts[:P])
+            gidx = ops.add_offset(order, row0)                         # global row numbers, partition order
+            valid_part = ops.take(values, ops.slice(order, 0, n_valid))
+            gsend = ops.slice(gidx, 0, n_valid)
+            null_idx = ops.raw_tensor(ops.slice(gidx, n_valid, n_local - n_valid))
         send_rows = list(counts[:P])
         meta = xchg.all_gather_i64(ops.meta_tensor(send_rows)).cpu().numpy()
         recv_rows = [int(meta[src, rank]) for src in range(P)]
         t0 = ops.mark()
-        rk, ri = xchg.all_to_all_columns([ops.raw_tensor(valid_part), ops.raw_tensor(ops.slice(gidx, 0, n_valid))], send_rows, recv_rows)
+        rk, ri = xchg.all_to_all_columns([ops.raw_tensor(valid_part), ops.raw_tensor(gsend)], send_rows, recv_rows)
         ops.note_exchange(t0, xchg)
-        null_idx = ops.raw_tensor(ops.slice(gidx, n_valid, n_local - n_valid))
         # received rows are grouped by source rank (ascending) and ascending global row inside each
         # group, so a STABLE local sort keeps ties in global row order
         rk_arr = ops.from_raw_tensor(rk, ops.type_of(values))
+        if narrow and not return_keys:
+            return ops.raw_tensor(ops.sort_payload(rk_arr, ops.from_raw_tensor(ri, pa.uint32()))), null_idx
         local = ops.stable_sort_indices(rk_arr)
-        seg = ops.raw_tensor(ops.take(ops.from_raw_tensor(ri, pa.uint64()), local))
+        seg = ops.raw_tensor(ops.take(ops.from_raw_tensor(ri, pa.uint32() if narrow else pa.uint64()), local))
+        if narrow:
+            seg = seg.to(torch.int64) & 0xFFFFFFFF if seg.dtype != torch.int64 else seg
         if return_keys:
             return seg, null_idx, ops.raw_tensor(ops.take(rk_arr, local))
         return seg, null_idx
@@ -420,6 +435,24 @@ class DeviceOps:
 
     def add_offset(self, idx_arr, off):
         return self.bc.add(idx_arr, pa.scalar(int(off), pa.uint64()))
+
+    def range_split(self, values, splitters, row0):
+        """(values regrouped by destination, uint32 global rows regrouped the same way, rows per destination [+ nulls last])"""
+        from . import _cabi as cabi
+        from .device import check
+        n_bins = splitters.length + 2
+        counts = (C.c_int64 * n_bins)()
+        cv, cs, ov, orows = values._c(), splitters._c(), cabi.B2Array(), cabi.B2Array()
+        check(self.ctx.lib.b2_range_split(self.ctx.handle, C.byref(cv), C.byref(cs), 0, int(row0), C.byref(ov), C.byref(orows), counts,
+                                          self.ctx.stream))
+        return (self.DeviceArray._from_c(self.ctx, ov, values.type), self.DeviceArray._from_c(self.ctx, orows, pa.uint32()),
+                [int(x) for x in counts])
+
+    def to_uint32(self, arr):
+        return self.bc.cast(arr, pa.uint32(), safe=False)
+
+    def sort_payload(self, arr, payload):
+        return self.bc.sort_payload(arr, payload)
 
     def sample_valid(self, values, k):
         """<= k evenly spaced valid rows as a typed tensor"""

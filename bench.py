@@ -665,7 +665,10 @@ def run_multi_gpu(env, n_total, reps):
     keys_t, _, bits_t, k_nulls = gen_columns("sort")
     keys = DeviceArray.from_pointers(ctx, pa.int64(), n_local, keys_t.data_ptr(), validity_ptr=bits_t.data_ptr(), null_count=k_nulls)
     _, ms, xms, xbytes = leg(lambda: d.sort_indices(keys, ops, xchg))
-    seg, nulls_idx, skeys = d.sort_indices(keys, ops, xchg, return_keys=True)  # untimed: also returns the keys in sorted order
+    seg_fast, nulls_fast = d.sort_indices(keys, ops, xchg)                      # the timed path's own answer ...
+    seg, nulls_idx, skeys = d.sort_indices(keys, ops, xchg, return_keys=True)  # ... and the variant that also returns the sorted keys
+    same_answer = bool(torch.equal(seg_fast, seg)) and bool(torch.equal(nulls_fast, nulls_idx))
+    del seg_fast, nulls_fast
     valid = unpack_bits(torch, bits_t, n_local)
     grow = torch.arange(row0, row1, dtype=I64, device="cuda")
     in_pair = int((mix64(torch, grow) * keys_t * valid.to(I64)).sum().item())
@@ -698,6 +701,7 @@ def run_multi_gpu(env, n_total, reps):
         prev = (e[2], e[3])
     idx_sum = int(seg.sum().item()) + int(nulls_idx.sum().item())
     checksum = int((mix64(torch, seg) * (skeys | 1)).sum().item())
+    local_ok = local_ok and same_answer
     tot = env.sum_over_ranks([in_pair, out_pair, seg.numel() + nulls_idx.numel(), idx_sum, 0 if local_ok else 1, nulls_idx.numel(),
                               k_nulls, checksum])
     ok = (wrap(tot[0]) == wrap(tot[1]) and tot[2] == n_total and wrap(tot[3]) == wrap(n_total * (n_total - 1) // 2) and tot[4] == 0

@@ -294,6 +294,12 @@ B2_API int b2_binary_data_size(B2Context* ctx, const B2Array* array, int64_t* ou
  * ------------------------------------------------------------------------- */
 B2_API int b2_sort_indices(B2Context* ctx, const B2Array* values, int order,
                            int null_placement, B2Array* out, void* stream);
+/* The same stable sort, but row i carries payload[i] (B2_UINT32, no nulls) instead of its row number i:
+ * out[k] = payload of the k-th row in sorted order (B2_UINT64).  The owner GPU of the distributed SortIndices sorts the
+ * received (key, global row) pairs with it, so the row numbers ride along the radix passes instead of being gathered
+ * afterwards (b2_sort_indices + b2_take = a second, random-access-bound pass). */
+B2_API int b2_sort_payload(B2Context* ctx, const B2Array* values, const B2Array* payload, int order,
+                           int null_placement, B2Array* out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Grouper.  Replaces Grouper::{Make,Consume,Lookup,GetUniques,num_groups,Reset}
@@ -438,6 +444,15 @@ B2_API int b2_hash_partition(B2Context* ctx, const B2Array* keys, int n_parts, B
                              void* stream);
 B2_API int b2_range_partition(B2Context* ctx, const B2Array* values, const B2Array* splitters,
                               int order, B2Array* out_ids, void* stream);
+/* Sender side of the distributed SortIndices in one call: a STABLE split of (value, row number) pairs by range id
+ * (bin b = #splitters <= value in SortIndices' order, b = 0 .. n_splitters; rows with a null value form the last bin).
+ *   out_values : values regrouped bin by bin (row order kept inside a bin), no validity
+ *   out_rows   : B2_UINT32 row_base + original row, regrouped the same way (the payload of b2_sort_payload at the owner)
+ *   out_counts : HOST array of n_splitters + 2 int64 = rows per bin
+ * count -> scan -> scatter: two streaming passes instead of ids + sort_indices(ids) + two takes + an offset add. */
+B2_API int b2_range_split(B2Context* ctx, const B2Array* values, const B2Array* splitters, int order,
+                          uint64_t row_base, B2Array* out_values, B2Array* out_rows, int64_t* out_counts,
+                          void* stream);
 /* out_counts[b] (HOST array of n_bins int64) = rows whose id == b: the send counts of the exchange.
  * ids: B2_UINT32 without nulls, every id < n_bins (else B2_INDEX_ERROR); n_bins <= 8192. */
 B2_API int b2_bincount(B2Context* ctx, const B2Array* ids, int n_bins, int64_t* out_counts, void* stream);

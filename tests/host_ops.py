@@ -101,6 +101,20 @@ class HostOps:
     def add_offset(self, idx_arr, off):
         return pa.array(ora.values(idx_arr).astype(np.uint64) + np.uint64(off), pa.uint64())
 
+    def range_split(self, values, splitters, row0):
+        v, valid = ora.values(values), ora.validity(values)
+        sp = ora.values(splitters)
+        ids = np.where(valid, np.searchsorted(sp, v, side="right"), len(sp) + 1)
+        order = np.argsort(ids, kind="stable")
+        counts = [int(x) for x in np.bincount(ids, minlength=len(sp) + 2)]
+        return (ora.make_array(values.type, v[order]), pa.array((order + row0).astype(np.uint32), pa.uint32()), counts)
+
+    def to_uint32(self, arr):
+        return pa.array(ora.values(arr).astype(np.uint32), pa.uint32())
+
+    def sort_payload(self, arr, payload):
+        return pa.array(ora.values(ora.take(payload, ora.sort_indices(arr))).astype(np.uint64), pa.uint64())
+
     def sample_valid(self, values, k):
         n = len(values)
         if n == 0:

@@ -569,3 +569,16 @@ def test_hash_aggregates_few_groups_large(ctx, vt, groups):
             np.testing.assert_allclose(got.fill_null(0).to_numpy(), want.fill_null(0).to_numpy(), rtol=1e-9, atol=1e-6)
         else:
             assert got.equals(want), (vt, groups, f)
+
+
+@pytest.mark.parametrize("t", [pa.int64(), pa.float32(), pa.uint16()], ids=str)
+def test_sort_payload_equals_sort_indices_then_take(ctx, t):
+    """b2_sort_payload: the payload rides along the radix passes; result = take(payload, sort_indices(values))"""
+    for n, null_p in ((0, 0.0), (1, 0.0), (5000, 0.1), (200_003, 0.3)):
+        vals = random_array(t, n, null_p, SEED + n, lo=0, hi=50, offset=3)     # many ties: stability matters
+        payload = pa.array(np.random.default_rng(SEED).integers(0, 2**32, n, dtype=np.uint32))
+        for order in ("ascending", "descending"):
+            for placement in ("at_end", "at_start"):
+                got = bc.sort_payload(dev(vals, ctx), dev(payload, ctx), order, placement).to_arrow()
+                want = pc.take(payload, pc.array_sort_indices(vals, order=order, null_placement=placement)).cast(pa.uint64())
+                assert got.equals(want), f"{t} n={n} {order} {placement}"
