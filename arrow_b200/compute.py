@@ -628,17 +628,23 @@ def group_by(keys: Sequence[DeviceArray], aggregates: Sequence[tuple], fused: bo
     reference, whose tests sort by key)."""
     if isinstance(keys, DeviceArray):
         keys = [keys]
-    # config 3's shape -- one fixed-width key, hash_sum / hash_count(only_valid) with default options over one value
-    # column -- takes the fused path (b2_groupby_sumcount_*), exactly as the C++ b200_aggregate node does; set
-    # fused=False in an aggregate's options dict ... or pass any non-default option to force the Grouper path
+    # config 3's shape -- one fixed-width key, hash_sum / hash_count(only_valid) / hash_mean with default options over
+    # one value column -- takes the fused path (b2_groupby_sumcount_*), exactly as the C++ b200_aggregate node does;
+    # pass fused=False or any option to force the Grouper path.  hash_mean = sum / count of the same state; 64-bit
+    # integer columns keep the unfused kernel (the reference's mean accumulates in double,
+    # hash_aggregate_numeric.cc:353-356, which an exact int64 sum that wraps would not match).
     if fused and len(keys) == 1 and aggregates and all(
-            fn in ("hash_sum", "hash_count") and values is not None and not opts and values is aggregates[0][1]
+            fn in ("hash_sum", "hash_count", "hash_mean") and values is not None and not opts and values is aggregates[0][1]
             for fn, values, opts in aggregates) and keys[0].type in _NUMERIC_TYPES and aggregates[0][1].type in _NUMERIC_TYPES \
-            and not pa.types.is_floating(keys[0].type):
+            and not pa.types.is_floating(keys[0].type) \
+            and not (any(fn == "hash_mean" for fn, _, _ in aggregates) and aggregates[0][1].type in (pa.int64(), pa.uint64())):
         gb = GroupBySumCount(keys[0].type, aggregates[0][1].type, ctx=keys[0].ctx)
         gb.consume(keys[0], aggregates[0][1])
         k, s_, c_ = gb.finalize()
-        return [k], [s_ if fn == "hash_sum" else c_ for fn, _, _ in aggregates]
+        m_ = None
+        if any(fn == "hash_mean" for fn, _, _ in aggregates):
+            m_ = divide(cast(s_, pa.float64(), safe=False), cast(c_, pa.float64(), safe=False))
+        return [k], [{"hash_sum": s_, "hash_count": c_, "hash_mean": m_}[fn] for fn, _, _ in aggregates]
     g = Grouper([k.type for k in keys], keys[0].ctx)
     ids = g.consume(keys)
     outs = []

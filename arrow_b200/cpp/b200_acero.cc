@@ -97,11 +97,12 @@ class AggregateNode : public DeviceNode {
     std::unique_ptr<cp::KernelContext> kctx;
     int target;  // input column, -1 for hash_count_all
     bool is_count = false;
+    bool is_mean = false;  // fused path only: mean = sum / count at Finalize
   };
 
   static bool DefaultOptions(const std::string& fn, const cp::FunctionOptions* o) {
     if (o == nullptr) return true;
-    if (fn == "hash_sum") {
+    if (fn == "hash_sum" || fn == "hash_mean") {
       auto* s = dynamic_cast<const cp::ScalarAggregateOptions*>(o);
       return s && s->skip_nulls && s->min_count == 1;
     }
@@ -164,13 +165,19 @@ class AggregateNode : public DeviceNode {
       agg.kctx->SetState(agg.state.get());
       agg.target = target;
       agg.is_count = a.function == "hash_count";
+      agg.is_mean = a.function == "hash_mean";
       ARROW_ASSIGN_OR_RAISE(auto out_type, kernel->signature->out_type().Resolve(agg.kctx.get(), in_types));
       fields.push_back(arrow::field(a.name.empty() ? a.function : a.name, out_type.GetSharedPtr()));
-      // fused path: hash_sum / hash_count(only_valid), default options, one shared numeric value column
-      const bool ok_fn = (a.function == "hash_sum" || a.function == "hash_count") && DefaultOptions(a.function, a.options.get());
-      const bool ok_type = target >= 0 && (FixedWidthNumericStorage(*in_schema.field(target)->type()) ||
-                                           in_schema.field(target)->type()->id() == arrow::Type::FLOAT ||
-                                           in_schema.field(target)->type()->id() == arrow::Type::DOUBLE);
+      // fused path: hash_sum / hash_count(only_valid) / hash_mean, default options, one shared numeric value column.
+      // hash_mean = sum / count of the same state; the reference accumulates means in double
+      // (hash_aggregate_numeric.cc:353-356), so 64-bit integer columns -- whose exact sum may wrap where the double
+      // does not -- keep the unfused kernel.
+      const bool ok_fn = (a.function == "hash_sum" || a.function == "hash_count" || a.function == "hash_mean") &&
+                         DefaultOptions(a.function, a.options.get());
+      const auto target_id = target >= 0 ? in_schema.field(target)->type()->id() : arrow::Type::NA;
+      bool ok_type = target >= 0 && (FixedWidthNumericStorage(*in_schema.field(target)->type()) ||
+                                     target_id == arrow::Type::FLOAT || target_id == arrow::Type::DOUBLE);
+      if (a.function == "hash_mean" && (target_id == arrow::Type::INT64 || target_id == arrow::Type::UINT64)) ok_type = false;
       if (!ok_fn || !ok_type || (fused_target >= 0 && fused_target != target)) fusable = false;
       if (target >= 0 && fused_target < 0) fused_target = target;
       node->aggs_.push_back(std::move(agg));
@@ -345,16 +352,20 @@ class AggregateNode : public DeviceNode {
       cp::ExecBatch out({}, k.length);
       ARROW_ASSIGN_OR_RAISE(auto hk, ToHost(*AdoptOutput(rt_, k, output_schema_->field(0)->type())));
       out.values.emplace_back(std::move(hk));
-      std::shared_ptr<arrow::ArrayData> hs, hc;
-      std::shared_ptr<arrow::DataType> sum_type;
-      for (size_t i = 0; i < aggs_.size(); ++i)
-        if (!aggs_[i].is_count) sum_type = output_schema_->field(static_cast<int>(key_idx_.size() + i))->type();
-      auto ds = AdoptOutput(rt_, s, sum_type ? sum_type : arrow::int64());  // adopt even if unused: the buffers are ours to free
+      std::shared_ptr<arrow::ArrayData> hs, hc, hm;
+      const auto sum_type = s.type == B2_DOUBLE ? arrow::float64() : (s.type == B2_UINT64 ? arrow::uint64() : arrow::int64());
+      auto ds = AdoptOutput(rt_, s, sum_type);  // adopt even if unused: the buffers are ours to free
       auto dc = AdoptOutput(rt_, c, arrow::int64());
       for (auto& a : aggs_) {
         if (a.is_count) {
           if (!hc) { ARROW_ASSIGN_OR_RAISE(hc, ToHost(*dc)); }
           out.values.emplace_back(hc);
+        } else if (a.is_mean) {
+          if (!hm) {
+            ARROW_ASSIGN_OR_RAISE(auto dm, DeviceMean(s, c));
+            ARROW_ASSIGN_OR_RAISE(hm, ToHost(*dm));
+          }
+          out.values.emplace_back(hm);
         } else {
           if (!hs) { ARROW_ASSIGN_OR_RAISE(hs, ToHost(*ds)); }
           out.values.emplace_back(hs);
@@ -379,6 +390,23 @@ class AggregateNode : public DeviceNode {
     ARROW_RETURN_NOT_OK(output_->InputReceived(this, std::move(out)));
     return output_->InputFinished(this, 1);
   }
+  // double(sum) / double(count) on the device; a group without valid values has a null sum, hence a null mean
+  Result<std::shared_ptr<arrow::ArrayData>> DeviceMean(const B2Array& sums, const B2Array& counts) {
+    B2Context* ctx = rt_->context();
+    B2CastOptions to_double{B2_DOUBLE, 1, 1, 0};  // unsafe: sums beyond 2^53 round, as a double accumulator would
+    B2Array fs = sums, fc{}, q{};
+    std::shared_ptr<arrow::ArrayData> keep_s, keep_c;
+    if (sums.type != B2_DOUBLE) {
+      if (b2_cast_numeric(ctx, &sums, &to_double, &fs, nullptr) != B2_OK) return Status::UnknownError("b2_cast_numeric: ", b2_last_error());
+      keep_s = AdoptOutput(rt_, fs, arrow::float64());
+    }
+    if (b2_cast_numeric(ctx, &counts, &to_double, &fc, nullptr) != B2_OK) return Status::UnknownError("b2_cast_numeric: ", b2_last_error());
+    keep_c = AdoptOutput(rt_, fc, arrow::float64());
+    B2Value l{&fs, nullptr}, r{&fc, nullptr};
+    if (b2_binary_arith(ctx, B2_DIVIDE, &l, &r, &q, nullptr) != B2_OK) return Status::UnknownError("b2_binary_arith: ", b2_last_error());
+    return AdoptOutput(rt_, q, arrow::float64());
+  }
+
   std::vector<int> key_idx_;
   std::unique_ptr<cp::Grouper> grouper_;
   std::vector<Agg> aggs_;

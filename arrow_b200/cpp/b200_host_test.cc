@@ -502,6 +502,27 @@ int main(int argc, char** argv) {
       }
       std::cout << "OK   b200_aggregate hash_sum+hash_count == aggregate (B200_AGGREGATE_FUSED=" << fused << ", " << got2->num_rows() << " groups)" << std::endl;
     }
+    // hash_mean rides the same fused state (mean = sum / count at Finalize); doubles compared approximately, as the
+    // reference's own aggregate tests do for float sums (acero/hash_aggregate_test.cc:3641-3663)
+    for (const char* fused : {"1", "0"}) {
+      setenv("B200_AGGREGATE_FUSED", fused, 1);
+      std::vector<cp::Aggregate> aggs4 = {{"hash_mean", nullptr, "w", "w_mean"}, {"hash_count", nullptr, "w", "w_count"},
+                                          {"hash_sum", nullptr, "w", "w_sum"}};
+      auto want4 = sorted(run("aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs4, std::vector<arrow::FieldRef>{"k"})), "k");
+      auto got4 = sorted(run("b200_aggregate", std::make_shared<ac::AggregateNodeOptions>(aggs4, std::vector<arrow::FieldRef>{"k"})), "k");
+      ++g_checks;
+      bool same = got4->num_rows() == want4->num_rows();
+      for (const char* name : {"k", "w_mean", "w_count", "w_sum"}) {
+        auto a = got4->GetColumnByName(name), b = want4->GetColumnByName(name);
+        same = same && a && b && a->ApproxEquals(*b, arrow::EqualOptions::Defaults().atol(1e-9));
+      }
+      if (!same) {
+        std::cout << "FAIL b200_aggregate (mean+count+sum of a double column, fused=" << fused << ")\n want " << want4->ToString().substr(0, 600)
+                  << "\n got " << got4->ToString().substr(0, 600) << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_aggregate hash_mean+hash_count+hash_sum(double) ~= aggregate (B200_AGGREGATE_FUSED=" << fused << ")" << std::endl;
+    }
     unsetenv("B200_AGGREGATE_FUSED");
     // a DEVICE-resident table through the stock table_source: it arrives as adjacent 32Ki-row slices of the same device
     // buffers (SliceAndDeliverMorsel), which b200_aggregate glues back into one run without copying

@@ -29,6 +29,15 @@
 // `uniques`) when the probe limit is hit -- the insert pass stops at the first overflow -- or
 // when the load exceeds 1/2.  Every random access is one 32-byte sector: measured 25.5 ms
 // (insert) + 22.1 ms (gather) per 1B rows at 10M groups = the 42 G accesses/s DRAM ceiling.
+//
+// Direct-addressed mode (one integer key column whose values span <= 2^24): the hash table is
+// replaced by two uint32 arrays indexed by key - window_lo, {id} and {first_row}, each small enough
+// to stay L2-resident, so the two random accesses per row never reach DRAM.  The window is exact
+// (a min/max pass over the batch precedes every Consume), grows by re-seating the uniques, and the
+// grouper falls back to the hash table -- rebuilt from the same uniques -- the first time a batch
+// does not fit.  Ids, uniques and Lookup results are identical in both modes.
+#include <cstdlib>
+
 #include "hash_table.cuh"
 #include "selection.cuh"
 
@@ -74,6 +83,18 @@ struct GrouperTable {
   uint64_t mask;
   __host__ __device__ uint32_t* id_ptr(uint64_t slot) const { return reinterpret_cast<uint32_t*>(slots + slot * 2 + 1); }
   __host__ __device__ uint32_t* first_row_ptr(uint64_t slot) const { return id_ptr(slot) + 1; }
+};
+
+// direct-addressed mode (see the header comment)
+constexpr uint64_t kDirectMaxRange = 1ull << 24;
+
+struct DirectTable {
+  uint32_t* id;         // [cap + 1]; entry `cap` is the null group
+  uint32_t* first_row;  // [cap + 1]
+  uint64_t lo;          // order-preserving encoding of entry 0
+  uint64_t cap;
+  uint64_t flip;        // sign bit of a signed key type (makes the unsigned order the value order)
+  __host__ __device__ uint64_t index(uint64_t enc, bool is_null) const { return is_null ? cap : (enc ^ flip) - lo; }
 };
 
 __global__ void __launch_bounds__(kBlock) grouper_init_kernel(GrouperTable t) {
@@ -199,8 +220,9 @@ __global__ void __launch_bounds__(kBlock) grouper_flag_slots_kernel(GrouperTable
   }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(kBlock) grouper_assign_kernel(KeyLayout L, KeyColumns c, int64_t n,
-                                                                GrouperTable t, const uint32_t* row_slot,
+                                                                GrouperTable t, DirectTable d, const uint32_t* row_slot,
                                                                 BitmapReader flags, const int64_t* tile_offsets,
                                                                 uint32_t base_id, uint64_t* uniq_keys,
                                                                 uint8_t* uniq_null) {
@@ -237,7 +259,8 @@ __global__ void __launch_bounds__(kBlock) grouper_assign_kernel(KeyLayout L, Key
     const uint32_t id = base_id + static_cast<uint32_t>(vbase + rank);
     bool is_null;
     uint64_t enc = encode_row(L, c, row, &is_null);
-    *t.id_ptr(row_slot[row]) = id;
+    if (DIRECT) d.id[d.index(enc, is_null)] = id;
+    else *t.id_ptr(row_slot[row]) = id;
     uniq_keys[id] = enc;
     uniq_null[id] = is_null ? 1 : 0;
   }
@@ -317,6 +340,144 @@ __global__ void __launch_bounds__(kBlock) grouper_decode_kernel(KeyLayout L, int
   if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
 }
 
+// ---------------------------------------------------------------------------
+// direct-addressed mode
+// ---------------------------------------------------------------------------
+// mm[0] = min, mm[1] = max of the order-preserving encoding over the valid rows
+__global__ void __launch_bounds__(kBlock) grouper_minmax_kernel(const void* data, int width, BitmapReader valid,
+                                                                int64_t n, uint64_t flip, unsigned long long* mm) {
+  uint64_t lo = ~0ull, hi = 0;
+  constexpr int kPer = 4;
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t i0 = blockIdx.x * (int64_t)kBlock + threadIdx.x; i0 < n; i0 += stride * kPer) {
+    uint64_t v[kPer];
+    bool ok[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int64_t i = i0 + k * stride;
+      ok[k] = i < n && valid.bit(i);
+      v[k] = ok[k] ? load_key_bits(data, width, i) ^ flip : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (!ok[k]) continue;
+      lo = v[k] < lo ? v[k] : lo;
+      hi = v[k] > hi ? v[k] : hi;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if (lane_id() == 0 && lo <= hi) {
+    atomicMin(mm, (unsigned long long)lo);
+    atomicMax(mm + 1, (unsigned long long)hi);
+  }
+}
+
+// Pass A: rows of groups that have no id yet lower first_row (guarded, so almost always a plain L2
+// read); unless the grouper is FRESH, rows of known groups get their id here.
+template <bool FRESH>
+__global__ void __launch_bounds__(kBlock) grouper_direct_first_kernel(const void* data, int width, BitmapReader valid,
+                                                                      int64_t n, DirectTable t, uint32_t* out_ids) {
+  constexpr int kPer = 4;
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t i0 = blockIdx.x * (int64_t)kBlock + threadIdx.x; i0 < n; i0 += stride * kPer) {
+    uint64_t idx[kPer];
+    uint32_t id[kPer], fr[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int64_t i = i0 + k * stride;
+      idx[k] = ~0ull;
+      if (i < n) idx[k] = t.index(load_key_bits(data, width, i), !valid.bit(i));
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      id[k] = kNoId;
+      if (!FRESH && idx[k] != ~0ull) id[k] = t.id[idx[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      fr[k] = 0;
+      if (idx[k] != ~0ull && id[k] == kNoId) fr[k] = *reinterpret_cast<volatile uint32_t*>(t.first_row + idx[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int64_t i = i0 + k * stride;
+      if (idx[k] == ~0ull) continue;
+      if (id[k] == kNoId && fr[k] > static_cast<uint32_t>(i)) atomicMin(t.first_row + idx[k], static_cast<uint32_t>(i));
+      if (!FRESH) out_ids[i] = id[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_direct_flag_kernel(DirectTable t, uint32_t* flags) {
+  for (uint64_t e = blockIdx.x * (uint64_t)kBlock + threadIdx.x; e <= t.cap; e += (uint64_t)gridDim.x * kBlock) {
+    const uint32_t first_row = __ldcs(t.first_row + e);
+    if (first_row != 0xffffffffu && t.id[e] == kNoId) atomicOr(flags + (first_row >> 5), 1u << (first_row & 31));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_direct_gather_kernel(const void* data, int width, BitmapReader valid,
+                                                                       int64_t n, DirectTable t,
+                                                                       uint32_t* __restrict__ out) {
+  constexpr int kPer = 4;
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t i0 = blockIdx.x * (int64_t)kBlock + threadIdx.x; i0 < n; i0 += stride * kPer) {
+    uint64_t idx[kPer];
+    uint32_t id[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int64_t i = i0 + k * stride;
+      idx[k] = ~0ull;
+      if (i < n) idx[k] = t.index(load_key_bits(data, width, i), !valid.bit(i));
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (idx[k] != ~0ull) id[k] = t.id[idx[k]];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (idx[k] != ~0ull) __stcs(out + i0 + k * stride, id[k]);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_direct_reseat_kernel(DirectTable t, const uint64_t* uniq_keys,
+                                                                       const uint8_t* uniq_null, uint32_t n_groups) {
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < n_groups; g += gridDim.x * kBlock)
+    t.id[t.index(uniq_keys[g], uniq_null[g] != 0)] = g;
+}
+
+__global__ void __launch_bounds__(kBlock) grouper_direct_lookup_kernel(const void* data, int width, BitmapReader valid,
+                                                                       int64_t n, DirectTable t, uint32_t* out,
+                                                                       uint32_t* out_validity, int64_t* valid_count) {
+  int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    int64_t i = (w << 5) + lane_id();
+    bool ok = false;
+    if (i < n) {
+      uint32_t id = kNoId;
+      if (!valid.bit(i)) {
+        id = t.id[t.cap];
+      } else {
+        const uint64_t ord = load_key_bits(data, width, i) ^ t.flip;
+        if (ord >= t.lo && ord - t.lo < t.cap) id = t.id[ord - t.lo];
+      }
+      ok = id != kNoId;
+      out[i] = ok ? id : 0u;
+    }
+    unsigned word = __ballot_sync(0xffffffffu, ok);
+    if (lane_id() == 0) {
+      out_validity[w] = word;
+      local += __popc(word);
+    }
+  }
+  int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -331,7 +492,65 @@ struct B2Grouper {
   uint64_t* uniq_keys = nullptr;
   uint8_t* uniq_null = nullptr;
   uint64_t uniq_cap = 0;
+  // direct-addressed mode
+  bool direct_eligible = false;  // one integer key column, not yet known to be too wide
+  bool direct = false;
+  DirectTable dt{};
+  uint64_t obs_min = ~0ull, obs_max = 0;  // order-preserving encoding, over every valid key seen
 };
+
+static bool grouper_direct_enabled() {
+  const char* e = std::getenv("B2_GROUPER_DIRECT");
+  return !(e && e[0] == '0');
+}
+
+static bool grouper_type_is_integer(int32_t t) { return t >= B2_UINT8 && t <= B2_INT64; }
+
+static uint64_t grouper_sign_flip(int32_t t) {
+  switch (t) {
+    case B2_INT8: return 1ull << 7;
+    case B2_INT16: return 1ull << 15;
+    case B2_INT32: return 1ull << 31;
+    case B2_INT64: return 1ull << 63;
+    default: return 0;
+  }
+}
+
+static void grouper_free_direct(B2Grouper* g, cudaStream_t s) {
+  if (g->dt.id) g->ctx->free(g->dt.id, s);
+  if (g->dt.first_row) g->ctx->free(g->dt.first_row, s);
+  g->dt = DirectTable{};
+  g->direct = false;
+}
+
+// (re)seat the direct table on a window that covers [mn, mx] with headroom on both sides
+static int grouper_build_direct(B2Grouper* g, uint64_t mn, uint64_t mx, cudaStream_t s) {
+  const uint64_t span = mx - mn + 1;
+  uint64_t cap = next_pow2(span * 2 < 1024 ? 1024 : span * 2);
+  if (cap > kDirectMaxRange) cap = kDirectMaxRange;
+  const uint64_t pad = (cap - span) / 2;
+  uint64_t lo = mn >= pad ? mn - pad : 0;
+  if (lo > ~0ull - (cap - 1)) lo = ~0ull - (cap - 1);
+  const uint64_t flip = grouper_sign_flip(g->key_types[0]);
+  grouper_free_direct(g, s);
+  void *a, *b;
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 1) * 4, &a, s));
+  B2_RETURN_NOT_OK(g->ctx->alloc((cap + 1) * 4, &b, s));
+  B2_CUDA(cudaMemsetAsync(a, 0xff, (cap + 1) * 4, s));
+  B2_CUDA(cudaMemsetAsync(b, 0xff, (cap + 1) * 4, s));
+  g->dt.id = static_cast<uint32_t*>(a);
+  g->dt.first_row = static_cast<uint32_t*>(b);
+  g->dt.lo = lo;
+  g->dt.cap = cap;
+  g->dt.flip = flip;
+  g->direct = true;
+  if (g->num_groups) {
+    grouper_direct_reseat_kernel<<<grid_for(g->num_groups, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+        g->dt, g->uniq_keys, g->uniq_null, g->num_groups);
+    B2_LAUNCHED();
+  }
+  return B2_OK;
+}
 
 static void grouper_free_table(B2Grouper* g, cudaStream_t s) {
   if (g->table.slots) g->ctx->free(g->table.slots, s);
@@ -412,9 +631,92 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
     fill_out(out_ids, B2_UINT32, 0, 0, nullptr, ids.release());
     return B2_OK;
   }
+  const int grid = grid_for(n, kBlock * 4, kSMs * 8);
+
+  // direct-addressed mode: fit the window to this batch, or leave the mode for good
+  if (insert && g->direct_eligible) {
+    ScalarSlot mm(ctx);
+    B2_RETURN_NOT_OK(mm.zero(s));
+    B2_CUDA(cudaMemsetAsync(mm.dev(), 0xff, 8, s));
+    grouper_minmax_kernel<<<grid, kBlock, 0, s>>>(cols.data[0], g->layout.width[0], cols.valid[0], n, 
+                                                  grouper_sign_flip(g->key_types[0]),
+                                                  reinterpret_cast<unsigned long long*>(mm.dev()));
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(mm.fetch(s));
+    uint64_t mn = static_cast<uint64_t>(mm.host()[0]), mx = static_cast<uint64_t>(mm.host()[1]);
+    if (mn <= mx) {
+      if (mn < g->obs_min) g->obs_min = mn;
+      if (mx > g->obs_max) g->obs_max = mx;
+    }
+    const bool seen_any = g->obs_min <= g->obs_max;
+    const uint64_t lo_need = seen_any ? g->obs_min : 0, hi_need = seen_any ? g->obs_max : 0;
+    const uint64_t width = hi_need - lo_need;  // span - 1
+    const uint64_t roomy = (uint64_t)n * 8 > 65536 ? (uint64_t)n * 8 : 65536;
+    bool fits = width < kDirectMaxRange && (g->direct || width < roomy);
+    if (fits) {
+      if (!g->direct || lo_need < g->dt.lo || hi_need - g->dt.lo >= g->dt.cap)
+        B2_RETURN_NOT_OK(grouper_build_direct(g, lo_need, hi_need, s));
+    } else {
+      const bool was_direct = g->direct;
+      grouper_free_direct(g, s);
+      g->direct_eligible = false;
+      if (was_direct) B2_RETURN_NOT_OK(grouper_rebuild(g, next_pow2((uint64_t)g->num_groups * 4 + 1024), s));
+    }
+  }
+
+  if (g->direct) {
+    const void* kd = cols.data[0];
+    const int kw = g->layout.width[0];
+    if (!insert) {
+      Temp bits(ctx, s);
+      B2_RETURN_NOT_OK(bits.alloc(bitmap_alloc_bytes(n)));
+      B2_CUDA(cudaMemsetAsync(bits.ptr, 0, bitmap_alloc_bytes(n), s));
+      ScalarSlot slot(ctx);
+      B2_RETURN_NOT_OK(slot.zero(s));
+      grouper_direct_lookup_kernel<<<grid, kBlock, 0, s>>>(kd, kw, cols.valid[0], n, g->dt, ids.as<uint32_t>(),
+                                                           bits.as<uint32_t>(), slot.dev());
+      B2_LAUNCHED();
+      B2_RETURN_NOT_OK(slot.fetch(s));
+      int64_t nulls = n - slot.host()[0];
+      fill_out(out_ids, B2_UINT32, n, nulls, nulls ? bits.release() : nullptr, ids.release());
+      return B2_OK;
+    }
+    const bool fresh = g->num_groups == 0;
+    if (fresh) grouper_direct_first_kernel<true><<<grid, kBlock, 0, s>>>(kd, kw, cols.valid[0], n, g->dt, ids.as<uint32_t>());
+    else grouper_direct_first_kernel<false><<<grid, kBlock, 0, s>>>(kd, kw, cols.valid[0], n, g->dt, ids.as<uint32_t>());
+    B2_LAUNCHED();
+    Temp flags(ctx, s);
+    B2_RETURN_NOT_OK(flags.alloc(bitmap_alloc_bytes(n)));
+    B2_CUDA(cudaMemsetAsync(flags.ptr, 0, bitmap_alloc_bytes(n), s));
+    grouper_direct_flag_kernel<<<grid_for((int64_t)g->dt.cap + 1, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+        g->dt, flags.as<uint32_t>());
+    B2_LAUNCHED();
+    FilterBitmaps fb;
+    fb.mask_data = BitmapReader(flags.ptr, 0, n);
+    fb.mask_valid = BitmapReader(nullptr, 0, n);
+    fb.values_valid = BitmapReader(nullptr, 0, n);
+    fb.emit_null = 0;
+    Temp offsets(ctx, s);
+    int64_t n_new = 0, unused = 0;
+    B2_RETURN_NOT_OK(filter_plan(ctx, fb, n, false, &offsets, &n_new, &unused, s));
+    if ((uint64_t)g->num_groups + (uint64_t)n_new >= kNoId)
+      return set_error(B2_CAPACITY_ERROR, "grouper: more than 2^32-1 groups");
+    if (n_new > 0) {
+      B2_RETURN_NOT_OK(grouper_reserve_uniques(g, (uint64_t)g->num_groups + n_new, s));
+      grouper_assign_kernel<true><<<(unsigned)tiles_for(n), kBlock, 0, s>>>(
+          g->layout, cols, n, g->table, g->dt, nullptr, fb.mask_data, offsets.as<int64_t>(), g->num_groups,
+          g->uniq_keys, g->uniq_null);
+      B2_LAUNCHED();
+      g->num_groups += static_cast<uint32_t>(n_new);
+      grouper_direct_gather_kernel<<<grid, kBlock, 0, s>>>(kd, kw, cols.valid[0], n, g->dt, ids.as<uint32_t>());
+      B2_LAUNCHED();
+    }
+    fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
+    return B2_OK;
+  }
+
   Temp row_slot(ctx, s);
   B2_RETURN_NOT_OK(row_slot.alloc(sizeof(uint32_t) * (size_t)n));
-  const int grid = grid_for(n, kBlock * 4, kSMs * 8);
 
   if (!insert) {
     if (g->cap == 0) B2_RETURN_NOT_OK(grouper_rebuild(g, 1024, s));
@@ -470,7 +772,7 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
     return set_error(B2_CAPACITY_ERROR, "grouper: more than 2^32-1 groups");
   if (n_new > 0) {
     B2_RETURN_NOT_OK(grouper_reserve_uniques(g, (uint64_t)g->num_groups + n_new, s));
-    grouper_assign_kernel<<<(unsigned)tiles_for(n), kBlock, 0, s>>>(g->layout, cols, n, g->table,
+    grouper_assign_kernel<false><<<(unsigned)tiles_for(n), kBlock, 0, s>>>(g->layout, cols, n, g->table, g->dt,
                                                                    row_slot.as<uint32_t>(), fb.mask_data,
                                                                    offsets.as<int64_t>(), g->num_groups,
                                                                    g->uniq_keys, g->uniq_null);
@@ -515,6 +817,7 @@ int b2_grouper_create(B2Context* ctx, const int32_t* key_types, int n_keys, B2Gr
   g->ctx = ctx;
   g->layout = L;
   for (int j = 0; j < n_keys; ++j) g->key_types[j] = key_types[j];
+  g->direct_eligible = n_keys == 1 && grouper_type_is_integer(key_types[0]) && grouper_direct_enabled();
   *out = g;
   return B2_OK;
 }
@@ -524,6 +827,7 @@ void b2_grouper_destroy(B2Grouper* g) {
   cudaSetDevice(g->ctx->device);
   cudaStream_t s = g->ctx->stream;
   grouper_free_table(g, s);
+  grouper_free_direct(g, s);
   if (g->uniq_keys) g->ctx->free(g->uniq_keys, s);
   if (g->uniq_null) g->ctx->free(g->uniq_null, s);
   delete g;
@@ -578,6 +882,10 @@ int b2_grouper_reset(B2Grouper* g) {
   B2_CUDA(cudaSetDevice(g->ctx->device));
   cudaStream_t s = g->ctx->stream;
   grouper_free_table(g, s);
+  grouper_free_direct(g, s);
+  g->direct_eligible = g->layout.n_keys == 1 && grouper_type_is_integer(g->key_types[0]) && grouper_direct_enabled();
+  g->obs_min = ~0ull;
+  g->obs_max = 0;
   g->num_groups = 0;
   return B2_OK;
 }

@@ -46,22 +46,32 @@ __global__ void __launch_bounds__(kBlock) remap_ids_kernel(const uint32_t* __res
 }
 
 // counts[id] += 1 per row.  Lanes of a warp holding the same id are merged first (MATCH.ANY, one
-// atomic per distinct id per warp): a hot value -- e.g. the null entry of a column with 10 % nulls --
-// would otherwise serialise tens of millions of atomics on one L2 address (50 ms per 500M rows).
+// atomic per distinct id per warp): a hot value would otherwise serialise tens of millions of atomics
+// on one L2 address (50 ms per 500M rows).  The null entry -- the usual hot value, 10 % of the rows
+// even after the merge still means one atomic per warp on ONE address -- is counted in registers
+// and added once per warp at the end.
 __global__ void __launch_bounds__(kBlock) count_ids_kernel(const uint32_t* __restrict__ ids, int64_t n,
+                                                           uint32_t null_id, bool has_null,
                                                            unsigned long long* counts) {
   const unsigned lane = lane_id();
   const int64_t stride = (int64_t)gridDim.x * kBlock;
+  unsigned long long nulls = 0;
   for (int64_t base = blockIdx.x * (int64_t)kBlock + (threadIdx.x & ~31u); base < n; base += stride) {
     const int64_t i = base + lane;
-    const bool in = i < n;
+    bool in = i < n;
     const uint32_t g = in ? __ldcs(ids + i) : 0u;
+    if (has_null) {
+      const bool is_null = in && g == null_id;
+      nulls += __popc(__ballot_sync(0xffffffffu, is_null));
+      in = in && !is_null;
+    }
     const unsigned live = __ballot_sync(0xffffffffu, in);
     if (in) {
       const unsigned peers = __match_any_sync(live, g);
       if ((peers & lanemask_lt()) == 0) atomicAdd(&counts[g], static_cast<unsigned long long>(__popc(peers)));
     }
   }
+  if (has_null && lane == 0 && nulls) atomicAdd(&counts[null_id], nulls);
 }
 
 }  // namespace b2
@@ -153,6 +163,7 @@ extern "C" int b2_vector_hash(B2Context* ctx, const B2Array* values, int null_en
     B2_CUDA(cudaMemsetAsync(counts.ptr, 0, sizeof(int64_t) * (size_t)(n_groups ? n_groups : 1), s));
     if (n > 0) {
       count_ids_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(static_cast<const uint32_t*>(ids.a.data), n,
+                                                                           null_id, has_null,
                                                                            counts.as<unsigned long long>());
       B2_LAUNCHED();
     }

@@ -582,3 +582,27 @@ def test_sort_payload_equals_sort_indices_then_take(ctx, t):
                 got = bc.sort_payload(dev(vals, ctx), dev(payload, ctx), order, placement).to_arrow()
                 want = pc.take(payload, pc.array_sort_indices(vals, order=order, null_placement=placement)).cast(pa.uint64())
                 assert got.equals(want), f"{t} n={n} {order} {placement}"
+
+
+@pytest.mark.parametrize("vt", [pa.int32(), pa.uint16(), pa.float32(), pa.float64(), pa.int64()], ids=str)
+def test_group_by_mean_rides_the_fused_state(ctx, vt):
+    # hash_mean = sum / count of the fused table (GroupedMeanImpl::DoMean, hash_aggregate_numeric.cc:398-402); int64
+    # columns stay on the unfused kernel -- either way the answer is the reference engine's
+    n = 50000
+    keys = random_array(pa.int32(), n, 0.05, SEED, lo=-50, hi=400)
+    vals = random_array(vt, n, 0.2, SEED + 5, lo=0 if pa.types.is_unsigned_integer(vt) else -1000, hi=1000)
+    dk, dvv = dev(keys, ctx), dev(vals, ctx)
+    uniq, (mean, cnt, total) = bc.group_by([dk], [("hash_mean", dvv, None), ("hash_count", dvv, None), ("hash_sum", dvv, None)])
+    mine = pa.table({"k": uniq[0].to_arrow(), "m": mean.to_arrow(), "c": cnt.to_arrow(), "s": total.to_arrow()}).sort_by("k")
+    import pyarrow.acero  # noqa: F401
+    ref = pa.table({"k": keys, "v": vals}).group_by("k", use_threads=False).aggregate([("v", "mean"), ("v", "count"), ("v", "sum")]).sort_by("k")
+    assert mine["k"].combine_chunks().equals(ref["k"].combine_chunks())
+    assert mine["c"].combine_chunks().equals(ref["v_count"].combine_chunks())
+    got, want = mine["m"].combine_chunks(), ref["v_mean"].combine_chunks()
+    assert got.type == pa.float64() and got.is_valid().equals(want.is_valid())
+    np.testing.assert_allclose(got.fill_null(0).to_numpy(), want.fill_null(0).to_numpy(), rtol=1e-12, atol=1e-12)
+    # and the unfused path agrees
+    _, (mean2,) = bc.group_by([dk], [("hash_mean", dvv, None)], fused=False)
+    uniq2, _ = bc.group_by([dk], [("hash_count", dvv, None)], fused=False)
+    m2 = pa.table({"k": uniq2[0].to_arrow(), "m": mean2.to_arrow()}).sort_by("k")["m"].combine_chunks()
+    np.testing.assert_allclose(m2.fill_null(0).to_numpy(), want.fill_null(0).to_numpy(), rtol=1e-12, atol=1e-12)
