@@ -431,6 +431,15 @@ static int launch_consume(B2HashAgg* a, const B2Array* values, const B2Array* id
     B2_LAUNCHED();
     return B2_OK;
   }
+  // hash_sum over an integer column: the dense packed-state path of the fused group-by with the group ids as keys --
+  // one RED per row instead of two atomics (groupby_fused.cu dense_sum_count_by_id).  The has-null flags it does not
+  // maintain only matter to skip_nulls = false.
+  if (a->kind == B2_HASH_SUM && std::is_integral<T>::value && (a->opt.skip_nulls || values->null_count == 0)) {
+    bool done = false;
+    B2_RETURN_NOT_OK(dense_sum_count_by_id(a->ctx, id, (uint64_t)a->num_groups, v, values->type, valid, n, a->st.reduced,
+                                           a->st.counts, s, &done));
+    if (done) return B2_OK;
+  }
   const bool two_arrays = a->kind != B2_HASH_COUNT;
   const int64_t band_groups = (80ll << 20) / (two_arrays ? 16 : 8);
   int64_t bands = (a->num_groups + band_groups - 1) / band_groups;

@@ -8,6 +8,11 @@
 
 namespace b2 {
 
+// groupby_fused.cu: sums[id] += value, counts[id] += 1 over the valid values through the dense packed-state path
+int dense_sum_count_by_id(B2Context* ctx, const uint32_t* ids, uint64_t num_groups, const void* values, int value_type,
+                          BitmapReader val_valid, int64_t n, unsigned long long* sums, unsigned long long* counts,
+                          cudaStream_t s, bool* done);
+
 constexpr uint64_t kEmptyKey = 0xffffffffffffffffull;
 constexpr int kMaxProbe = 256;
 
