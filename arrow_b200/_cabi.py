@@ -128,6 +128,7 @@ PROTOTYPES = [
     ("b2_binary_data_size", C.c_int, [_P, _A, _I64P, _P]),
     ("b2_sort_indices", C.c_int, [_P, _A, C.c_int, C.c_int, _A, _P]),
     ("b2_sort_payload", C.c_int, [_P, _A, _A, C.c_int, C.c_int, _A, _P]),
+    ("b2_sort_indices_multi", C.c_int, [_P, _A, C.c_int, C.POINTER(C.c_int32), C.c_int, _A, _P]),
     ("b2_grouper_create", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.POINTER(_P)]),
     ("b2_grouper_destroy", None, [_P]),
     ("b2_grouper_consume", C.c_int, [_P, _A, _A, _P]),
@@ -156,6 +157,7 @@ PROTOTYPES = [
     ("b2_range_split", C.c_int, [_P, _A, _A, C.c_int, C.c_uint64, _A, _A, _I64P, _P]),
     ("b2_boolean", C.c_int, [_P, C.c_int, _V, _V, _A, _P]),
     ("b2_validity", C.c_int, [_P, C.c_int, _A, C.c_int, _A, _P]),
+    ("b2_if_else", C.c_int, [_P, _V, _V, _V, _A, _P]),
     ("b2_comm_unique_id", C.c_int, [_P]),
     ("b2_comm_init", C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     ("b2_comm_destroy", None, [_P]),

@@ -270,6 +270,45 @@ def true_unless_null(x): return _validity("true_unless_null", x)
 def is_nan(x): return _validity("is_nan", x)
 
 
+def if_else(cond, left, right) -> DeviceArray:
+    """if_else (kernels/scalar_if_else.cc:62-520): cond ? left : right, null where cond or the chosen side is null.
+    cond: boolean DeviceArray or scalar; left / right: DeviceArrays or scalars, numerics promoted to their common type
+    like the reference's DispatchBest (scalar_if_else.cc:1227-1266), or both boolean."""
+    ctx = _ctx(cond, left, right)
+    keep = []
+    cv = _bool_value(cond, keep)
+    sides = [x if isinstance(x, DeviceArray) else _as_scalar(x) for x in (left, right)]
+    types = [x.type for x in sides]
+    if all(pa.types.is_boolean(t) or pa.types.is_null(t) for t in types):
+        vals = [_bool_value(x, keep) for x in (left, right)]
+        out_type = pa.bool_()
+    else:
+        for t in types:
+            if pa.types.is_null(t):
+                raise pa.ArrowNotImplementedError("null-typed scalar operands are not supported")
+            _require_numeric(t)
+        ids = [type_id(t) for t in types]
+        tid = ids[0] if ids[0] == ids[1] else common_numeric(ids)
+        out_type = arrow_type(tid)
+        vals = []
+        for x, i in zip(sides, ids):
+            v = cabi.B2Value()
+            if isinstance(x, DeviceArray):
+                if i != tid:
+                    x = cast(x, out_type)
+                c = x._c()
+                keep.append((x, c))
+                v.array, v.scalar = C.pointer(c), None
+            else:
+                sc = _scalar_to(x, tid)
+                keep.append(sc)
+                v.array, v.scalar = None, C.pointer(sc)
+            vals.append(v)
+    cout = cabi.B2Array()
+    check(ctx.lib.b2_if_else(ctx.handle, C.byref(cv), C.byref(vals[0]), C.byref(vals[1]), C.byref(cout), ctx.stream))
+    return _out(ctx, cout, out_type)
+
+
 # ------------------------------------------------------------------------------------
 # selection
 # ------------------------------------------------------------------------------------
@@ -393,8 +432,27 @@ def sort_payload(arr: DeviceArray, payload: DeviceArray, order="ascending", null
     return _out(ctx, cout, pa.uint64())
 
 
-def sort_indices(arr: DeviceArray, sort_keys=None, null_placement="at_end", order=None) -> DeviceArray:
-    """sort_indices meta function on one array (kernels/vector_sort.cc:856-924)."""
+def sort_indices(arr, sort_keys=None, null_placement="at_end", order=None) -> DeviceArray:
+    """sort_indices meta function (kernels/vector_sort.cc:850-1027): on one array, or -- given a mapping
+    {name: DeviceArray} (a record batch / table of device columns) and sort_keys = [(name, order), ...] -- the
+    multi-key sort: ordered by the first key, ties by the next, stable (b2_sort_indices_multi)."""
+    if isinstance(arr, dict):
+        if not sort_keys:
+            raise pa.ArrowInvalid("Must specify one or more sort keys")
+        cols, orders = [], []
+        for k in sort_keys:
+            name, o = (k[0], k[1]) if isinstance(k, (tuple, list)) else (k, "ascending")
+            if name not in arr:
+                raise pa.ArrowInvalid(f"No match for FieldRef.Name({name})")
+            _require_numeric(arr[name].type)
+            cols.append(arr[name])
+            orders.append(_order(o))
+        ctx = cols[0].ctx
+        cks = (cabi.B2Array * len(cols))(*[c._c() for c in cols])
+        cor = (C.c_int32 * len(cols))(*orders)
+        cout = cabi.B2Array()
+        check(ctx.lib.b2_sort_indices_multi(ctx.handle, cks, len(cols), cor, _placement(null_placement), C.byref(cout), ctx.stream))
+        return _out(ctx, cout, pa.uint64())
     o = "ascending"
     if sort_keys:
         o = sort_keys[0][1] if isinstance(sort_keys[0], (tuple, list)) else sort_keys[0]
@@ -702,6 +760,7 @@ class GroupBySumCount:
 _REGISTRY = {
     "cast": cast, "filter": filter, "array_filter": array_filter, "take": take, "array_take": array_take,
     "sort_indices": sort_indices, "array_sort_indices": array_sort_indices,
+    "if_else": if_else,
     "add": add, "subtract": subtract, "multiply": multiply, "divide": divide,
     "add_checked": add_checked, "subtract_checked": subtract_checked,
     "multiply_checked": multiply_checked, "divide_checked": divide_checked,

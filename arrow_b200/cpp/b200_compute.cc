@@ -138,6 +138,13 @@ static bool AnyOnDevice(const std::vector<Datum>& args) {
     if (a.is_chunked_array())
       for (const auto& c : a.chunked_array()->chunks())
         if (IsOnDevice(*c->data())) return true;
+    if (a.kind() == Datum::RECORD_BATCH)
+      for (const auto& c : a.record_batch()->column_data())
+        if (IsOnDevice(*c)) return true;
+    if (a.kind() == Datum::TABLE)
+      for (const auto& col : a.table()->columns())
+        for (const auto& c : col->chunks())
+          if (IsOnDevice(*c->data())) return true;
   }
   return false;
 }
@@ -329,6 +336,109 @@ static Status AddBinaryFunction(cp::FunctionRegistry* reg, Runtime* rt, const st
 }
 
 // ------------------------------------------------------------------------------------------
+// boolean logic, validity predicates, if_else (kernels/scalar_boolean.cc, scalar_validity.cc, scalar_if_else.cc):
+// the kernels an Expression (filter predicate, projection) is made of besides arithmetic and compare
+// ------------------------------------------------------------------------------------------
+static Status BooleanExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  BinaryOperand l, r;
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[0], &l));
+  if (batch.num_values() > 1) ARROW_RETURN_NOT_OK(MakeOperand(batch[1], &r));
+  B2Array o;
+  B200_RETURN_NOT_OK(b2_boolean(kd.rt->context(), kd.op, &l.value, batch.num_values() > 1 ? &r.value : nullptr, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, arrow::boolean()), out);
+  return Status::OK();
+}
+
+static Status ValidityExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  if (!batch[0].is_array()) return Status::NotImplemented("arrow_b200: validity predicates need an array argument");
+  B2Array in, o;
+  ARROW_RETURN_NOT_OK(SpanToB2(batch[0].array, &in));
+  const int nan_is_null = (kd.op == B2_IS_NULL && ctx->state()) ? OptionsState<cp::NullOptions>::Get(ctx).nan_is_null : 0;
+  B200_RETURN_NOT_OK(b2_validity(kd.rt->context(), kd.op, &in, nan_is_null, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, arrow::boolean()), out);
+  return Status::OK();
+}
+
+static Status IfElseExec(cp::KernelContext* ctx, const cp::ExecSpan& batch, cp::ExecResult* out) {
+  const KernelData& kd = DataOf(ctx);
+  BinaryOperand c, l, r;
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[0], &c));
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[1], &l));
+  ARROW_RETURN_NOT_OK(MakeOperand(batch[2], &r));
+  B2Array o;
+  B200_RETURN_NOT_OK(b2_if_else(kd.rt->context(), &c.value, &l.value, &r.value, &o, nullptr));
+  MoveInto(AdoptOutput(kd.rt, o, out->type()->GetSharedPtr()), out);
+  return Status::OK();
+}
+
+// IfElseFunction::DispatchBest (kernels/scalar_if_else.cc:1227-1266): left / right are cast to their common numeric type
+class IfElseFunction : public Forwarding<cp::ScalarFunction> {
+ public:
+  using Forwarding<cp::ScalarFunction>::Forwarding;
+  Result<const cp::Kernel*> DispatchBest(std::vector<TypeHolder>* values) const override {
+    auto exact = DispatchExact(*values);
+    if (exact.ok() || values->size() != 3) return exact;
+    if (auto common = CommonNumeric({(*values)[1], (*values)[2]})) {
+      (*values)[1] = (*values)[2] = common;
+      return DispatchExact(*values);
+    }
+    return exact;
+  }
+};
+
+static cp::ScalarKernel DeviceScalarKernel(Runtime* rt, std::vector<cp::InputType> in, cp::OutputType out, cp::ArrayKernelExec exec,
+                                           int op, cp::KernelInit init = nullptr) {
+  cp::ScalarKernel k(std::move(in), std::move(out), exec, init);
+  k.null_handling = cp::NullHandling::COMPUTED_NO_PREALLOCATE;
+  k.mem_allocation = cp::MemAllocation::NO_PREALLOCATE;
+  k.can_write_into_slices = false;
+  k.data = std::make_shared<KernelData>(rt, op);
+  return k;
+}
+
+static Status AddLogicFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
+  const std::pair<const char*, int> binary[] = {{"and", B2_BOOL_AND}, {"or", B2_BOOL_OR}, {"xor", B2_BOOL_XOR},
+                                                {"and_not", B2_BOOL_AND_NOT}, {"and_kleene", B2_BOOL_AND_KLEENE},
+                                                {"or_kleene", B2_BOOL_OR_KLEENE}, {"and_not_kleene", B2_BOOL_AND_NOT_KLEENE}};
+  const auto b = cp::InputType(arrow::boolean());
+  for (const auto& f : binary) {
+    auto fn = std::make_shared<Forwarding<cp::ScalarFunction>>(f.first, cp::Arity::Binary(), DocFor({"x", "y"}));
+    ARROW_RETURN_NOT_OK(fn->AddKernel(DeviceScalarKernel(rt, {b, b}, cp::OutputType(arrow::boolean()), BooleanExec, f.second)));
+    ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(fn), true));
+  }
+  {
+    auto fn = std::make_shared<Forwarding<cp::ScalarFunction>>("invert", cp::Arity::Unary(), DocFor({"values"}));
+    ARROW_RETURN_NOT_OK(fn->AddKernel(DeviceScalarKernel(rt, {b}, cp::OutputType(arrow::boolean()), BooleanExec, B2_BOOL_INVERT)));
+    ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(fn), true));
+  }
+  static const cp::NullOptions kNullDefaults = cp::NullOptions::Defaults();
+  const std::pair<const char*, int> unary[] = {{"is_valid", B2_IS_VALID}, {"is_null", B2_IS_NULL},
+                                               {"true_unless_null", B2_TRUE_UNLESS_NULL}, {"is_nan", B2_IS_NAN}};
+  for (const auto& f : unary) {
+    const bool with_options = f.second == B2_IS_NULL;
+    auto fn = with_options ? std::make_shared<Forwarding<cp::ScalarFunction>>(f.first, cp::Arity::Unary(), DocFor({"values"}, "NullOptions"),
+                                                                              &kNullDefaults)
+                           : std::make_shared<Forwarding<cp::ScalarFunction>>(f.first, cp::Arity::Unary(), DocFor({"values"}));
+    auto types = NumericTypes();
+    if (f.second != B2_IS_NAN) types.push_back(arrow::boolean());
+    for (const auto& ty : types) {
+      if (f.second == B2_IS_NAN && !arrow::is_floating(ty->id())) continue;
+      ARROW_RETURN_NOT_OK(fn->AddKernel(DeviceScalarKernel(rt, {cp::InputType(ty)}, cp::OutputType(arrow::boolean()), ValidityExec, f.second,
+                                                           with_options ? OptionsState<cp::NullOptions>::Init : nullptr)));
+    }
+    ARROW_RETURN_NOT_OK(reg->AddFunction(std::move(fn), true));
+  }
+  auto fn = std::make_shared<IfElseFunction>("if_else", cp::Arity::Ternary(), DocFor({"cond", "left", "right"}));
+  auto types = NumericTypes();
+  types.push_back(arrow::boolean());
+  for (const auto& ty : types)
+    ARROW_RETURN_NOT_OK(fn->AddKernel(DeviceScalarKernel(rt, {b, cp::InputType(ty), cp::InputType(ty)}, cp::OutputType(ty), IfElseExec, 0)));
+  return reg->AddFunction(std::move(fn), true);
+}
+
+// ------------------------------------------------------------------------------------------
 // cast: a MetaFunction like the reference's CastMetaFunction (compute/cast.cc:78-127)
 // ------------------------------------------------------------------------------------------
 class CastFunction : public cp::MetaFunction {
@@ -368,6 +478,53 @@ class CastFunction : public cp::MetaFunction {
  private:
   Runtime* rt_;
 };
+
+// sort_indices on a record batch / single-chunk table of device columns: the multi-key sort (kernels/vector_sort.cc:850-1027
+// SortIndicesMetaFunction -> :386-600 MultipleKeyRecordBatchSorter).  Arrays and chunked arrays keep the stock meta
+// function, which reaches array_sort_indices above through this registry.
+class SortIndicesFunction : public cp::MetaFunction {
+ public:
+  explicit SortIndicesFunction(Runtime* rt)
+      : cp::MetaFunction("sort_indices", cp::Arity::Unary(), DocFor({"input"}, "SortOptions"), &kDefaults), rt_(rt) {}
+  Result<Datum> ExecuteImpl(const std::vector<Datum>& args, const cp::FunctionOptions* options, cp::ExecContext* ctx) const override {
+    const bool tabular = args[0].kind() == Datum::RECORD_BATCH || args[0].kind() == Datum::TABLE;
+    if (!tabular || !AnyOnDevice(args)) {
+      ARROW_ASSIGN_OR_RAISE(auto parent, cp::GetFunctionRegistry()->GetFunction("sort_indices"));
+      return parent->Execute(args, options, ctx);
+    }
+    const auto& so = options ? *static_cast<const cp::SortOptions*>(options) : kDefaults;
+    if (so.sort_keys.empty()) return Status::Invalid("Must specify one or more sort keys");
+    std::shared_ptr<arrow::Schema> schema = args[0].schema();
+    std::vector<B2Array> keys(so.sort_keys.size());
+    std::vector<int32_t> orders(so.sort_keys.size());
+    for (size_t k = 0; k < so.sort_keys.size(); ++k) {
+      ARROW_ASSIGN_OR_RAISE(auto match, so.sort_keys[k].target.FindOne(*schema));
+      if (match.indices().size() != 1) return Status::NotImplemented("arrow_b200 sort_indices: nested sort keys");
+      const int col = match.indices()[0];
+      std::shared_ptr<ArrayData> data;
+      if (args[0].kind() == Datum::RECORD_BATCH) {
+        data = args[0].record_batch()->column_data(col);
+      } else {
+        const auto& chunked = args[0].table()->column(col);
+        if (chunked->num_chunks() != 1) return Status::NotImplemented("arrow_b200 sort_indices: device tables must hold one chunk per column");
+        data = chunked->chunk(0)->data();
+      }
+      if (!arrow::is_integer(data->type->id()) && !arrow::is_floating(data->type->id()))
+        return Status::NotImplemented("arrow_b200 sort_indices: sort key of type ", data->type->ToString());
+      ARROW_RETURN_NOT_OK(DataToB2(*data, &keys[k]));
+      orders[k] = so.sort_keys[k].order == cp::SortOrder::Descending ? 1 : 0;
+    }
+    B2Array o;
+    B200_RETURN_NOT_OK(b2_sort_indices_multi(rt_->context(), keys.data(), static_cast<int>(keys.size()), orders.data(),
+                                             so.null_placement == cp::NullPlacement::AtEnd ? 1 : 0, &o, nullptr));
+    return Datum(AdoptOutput(rt_, o, arrow::uint64()));
+  }
+
+ private:
+  static const cp::SortOptions kDefaults;
+  Runtime* rt_;
+};
+const cp::SortOptions SortIndicesFunction::kDefaults = cp::SortOptions::Defaults();
 
 // ------------------------------------------------------------------------------------------
 // selection + sort vector kernels
@@ -883,8 +1040,10 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   const std::pair<const char*, int> cmp[] = {{"equal", B2_EQUAL}, {"not_equal", B2_NOT_EQUAL}, {"greater", B2_GREATER},
                                              {"greater_equal", B2_GREATER_EQUAL}, {"less", B2_LESS}, {"less_equal", B2_LESS_EQUAL}};
   for (const auto& c : cmp) ARROW_RETURN_NOT_OK(AddBinaryFunction(reg, rt, c.first, c.second, true));
+  ARROW_RETURN_NOT_OK(AddLogicFunctions(reg, rt));
   ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<CastFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddSelectionFunctions(reg, rt));
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<SortIndicesFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddHashFunctions(reg, rt));
   ARROW_RETURN_NOT_OK(AddScalarAggregates(reg, rt));
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},

@@ -250,6 +250,31 @@ int main(int argc, char** argv) {
   }
   h.Check("less(int32,int64) implicit cast", "less", {i32, i64a});
 
+  // ---- boolean logic, validity predicates, if_else (the rest of what an Expression is made of) ----
+  {
+    auto ba = UNWRAP(cp::CallFunction("greater", {i64a, Datum(int64_t(10))}, nullptr, &h.cpu_ctx)).make_array();   // has nulls
+    auto bb = UNWRAP(cp::CallFunction("less", {f32a, Datum(5e5f)}, nullptr, &h.cpu_ctx)).make_array();
+    for (const char* fn : {"and", "or", "xor", "and_not", "and_kleene", "or_kleene", "and_not_kleene"}) {
+      h.Check(std::string(fn) + "(bool,bool)", fn, {ba, bb});
+      h.Check(std::string(fn) + "(bool,scalar)", fn, {ba, Datum(true)});
+      h.Check(std::string(fn) + "(sliced,sliced)", fn, {ba->Slice(5, 3000), bb->Slice(70, 3000)});
+    }
+    h.Check("invert(bool)", "invert", {ba});
+    for (const char* fn : {"is_valid", "is_null", "true_unless_null"}) {
+      h.Check(std::string(fn) + "(int64)", fn, {i64a});
+      h.Check(std::string(fn) + "(bool)", fn, {ba});
+    }
+    h.Check("is_nan(float32)", "is_nan", {f32a});
+    cp::NullOptions nan_is_null(true);
+    h.Check("is_null(float32, nan_is_null)", "is_null", {UNWRAP(cp::CallFunction("divide", {f32a, UNWRAP(cp::Subtract(f32a, f32a, cp::ArithmeticOptions(), &h.cpu_ctx))}, nullptr, &h.cpu_ctx)).make_array()}, &nan_is_null);
+    h.Check("if_else(bool,int64,int64)", "if_else", {ba, i64a, i64b});
+    h.Check("if_else(bool,int32,int64) implicit cast", "if_else", {ba, i32, i64a});
+    h.Check("if_else(bool,float32,scalar)", "if_else", {bb, f32a, Datum(1.25f)});
+    h.Check("if_else(scalar,int64,int64)", "if_else", {Datum(false), i64a, i64b});
+    h.Check("if_else(bool,bool,bool)", "if_else", {ba, bb, ba});
+    h.Check("if_else(sliced)", "if_else", {ba->Slice(3, 4000), i64a->Slice(9, 4000), i64b->Slice(1, 4000)});
+  }
+
   // ---- cast ----
   auto cast_to = [&](const std::shared_ptr<arrow::DataType>& t, bool safe) {
     return safe ? cp::CastOptions::Safe(t) : cp::CastOptions::Unsafe(t);
@@ -286,6 +311,49 @@ int main(int argc, char** argv) {
     arrow::Int32Builder b;
     CHECK_OK(b.AppendValues({0, 5, static_cast<int32_t>(n), 1}));
     h.Check("take out of bounds error", "take", {i64a, UNWRAP(b.Finish())});
+  }
+
+  // ---- multi-key sort_indices over a record batch of device columns ----
+  {
+    auto ka = RandomNumeric<arrow::Int32Type>(30000, 0.1, 0x0ff1e1, 0, 6);
+    auto kb = RandomNumeric<arrow::DoubleType>(30000, 0.1, 0x0ff1e2, 0, 4);
+    kb = UNWRAP(cp::CallFunction("round", {kb}, nullptr, &h.cpu_ctx)).make_array();   // duplicates
+    auto kc = RandomNumeric<arrow::Int64Type>(30000, 0.0, 0x0ff1e3, -2, 2);
+    auto schema = arrow::schema({arrow::field("a", arrow::int32()), arrow::field("b", arrow::float64()), arrow::field("c", arrow::int64())});
+    auto host_batch = arrow::RecordBatch::Make(schema, 30000, {ka, kb, kc});
+    auto dev_batch = arrow::RecordBatch::Make(schema, 30000, {arrow::MakeArray(h.Dev(ka).array()), arrow::MakeArray(h.Dev(kb).array()),
+                                                             arrow::MakeArray(h.Dev(kc).array())});
+    for (auto np : {cp::NullPlacement::AtEnd, cp::NullPlacement::AtStart}) {
+      cp::SortOptions so({cp::SortKey("b", cp::SortOrder::Descending), cp::SortKey("a", cp::SortOrder::Ascending),
+                          cp::SortKey("c", cp::SortOrder::Descending)}, np);
+      auto want = UNWRAP(cp::CallFunction("sort_indices", {Datum(host_batch)}, &so, &h.cpu_ctx)).make_array();
+      auto got_d = UNWRAP(cp::CallFunction("sort_indices", {Datum(dev_batch)}, &so, &h.gpu_ctx));
+      auto got = arrow::MakeArray(UNWRAP(arrow_b200::ToHost(*got_d.array())));
+      ++g_checks;
+      if (!got->Equals(*want)) {
+        int64_t bad = 0;
+        auto g64 = std::static_pointer_cast<arrow::UInt64Array>(got), w64 = std::static_pointer_cast<arrow::UInt64Array>(want);
+        while (bad < got->length() && bad < want->length() && g64->Value(bad) == w64->Value(bad)) ++bad;
+        std::cout << "FAIL sort_indices(record batch, 3 keys): lengths " << got->length() << " / " << want->length() << ", first difference at "
+                  << bad << " got " << (bad < got->length() ? g64->Value(bad) : 0) << " want " << (bad < want->length() ? w64->Value(bad) : 0)
+                  << " type " << got->type()->ToString() << std::endl;
+        int64_t diffs = 0;
+        for (int64_t i = 0; i < got->length(); ++i) diffs += g64->Value(i) != w64->Value(i);
+        std::cout << "  " << diffs << " positions differ" << std::endl;
+        for (uint64_t row : {g64->Value(bad), w64->Value(bad)})
+          std::cout << "  row " << row << ": a=" << ka->GetScalar(row).ValueOrDie()->ToString() << " b=" << kb->GetScalar(row).ValueOrDie()->ToString()
+                    << " c=" << kc->GetScalar(row).ValueOrDie()->ToString() << std::endl;
+        // each key alone, to see which round goes wrong
+        for (const char* name : {"a", "b", "c"}) {
+          cp::SortOptions one({cp::SortKey(name, cp::SortOrder::Descending)}, np);
+          auto w1 = UNWRAP(cp::CallFunction("sort_indices", {Datum(host_batch)}, &one, &h.cpu_ctx)).make_array();
+          auto g1 = arrow::MakeArray(UNWRAP(arrow_b200::ToHost(*UNWRAP(cp::CallFunction("sort_indices", {Datum(dev_batch)}, &one, &h.gpu_ctx)).array())));
+          std::cout << "  single key " << name << " desc: " << (g1->Equals(*w1) ? "equal" : "DIFFERENT") << std::endl;
+        }
+        return 1;
+      }
+    }
+    std::cout << "OK   sort_indices(record batch of device columns, 3 keys, both null placements)" << std::endl;
   }
 
   // ---- sort_indices ----

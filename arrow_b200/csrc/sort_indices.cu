@@ -525,3 +525,57 @@ static int sort_run(B2Context* ctx, const B2Array* values, int order, int null_p
   fill_out(out, B2_UINT64, n, 0, nullptr, data.release());
   return B2_OK;
 }
+
+// Multi-key sort (SortIndices over a record batch / table, kernels/vector_sort.cc:386-600 MultipleKeyRecordBatchSorter
+// and :850-1027): rows ordered by keys[0], ties by keys[1], ...; per key its own order, one null placement; nulls (then
+// NaNs) of a key compare equal among themselves and fall through to the next key; stable.
+//
+// B200 design: least-significant key first, every round a STABLE single-key radix sort whose payload is the
+// permutation so far -- round k gathers key k through the current permutation (b2_take) and sorts it with the
+// permutation riding along the radix passes (sort_run's payload), so no comparator and no per-row key tuple exist.
+namespace {
+struct PoolArray {  // a C-ABI output whose buffers go back to the pool unless released
+  B2Context* ctx;
+  cudaStream_t s;
+  B2Array a{};
+  bool owned = false;
+  PoolArray(B2Context* c, cudaStream_t st) : ctx(c), s(st) {}
+  ~PoolArray() { reset(); }
+  void reset() {
+    if (!owned) return;
+    if (a.validity) ctx->free(const_cast<void*>(a.validity), s);
+    if (a.data) ctx->free(const_cast<void*>(a.data), s);
+    if (a.data2) ctx->free(const_cast<void*>(a.data2), s);
+    owned = false;
+    a = B2Array{};
+  }
+};
+}  // namespace
+
+extern "C" int b2_sort_indices_multi(B2Context* ctx, const B2Array* keys, int n_keys, const int32_t* orders, int null_placement,
+                                     B2Array* out, void* stream) {
+  if (!ctx || !keys || !orders || !out) return set_error(B2_INVALID, "b2_sort_indices_multi: null argument");
+  if (n_keys < 1) return set_error(B2_INVALID, "Must specify one or more sort keys");
+  for (int k = 1; k < n_keys; ++k)
+    if (keys[k].length != keys[0].length) return set_error(B2_INVALID, "sort keys differ in length");
+  cudaStream_t s = ctx->pick(stream);
+  PoolArray perm(ctx, s);
+  B2_RETURN_NOT_OK(sort_run(ctx, &keys[n_keys - 1], orders[n_keys - 1], null_placement, nullptr, &perm.a, stream));
+  perm.owned = true;
+  for (int k = n_keys - 2; k >= 0; --k) {
+    PoolArray perm32(ctx, s), gathered(ctx, s), next(ctx, s);
+    B2CastOptions narrow{B2_UINT32, 1, 1, 0};  // row numbers < 2^32 (sort_run's limit)
+    B2_RETURN_NOT_OK(b2_cast_numeric(ctx, &perm.a, &narrow, &perm32.a, stream));
+    perm32.owned = true;
+    perm.reset();
+    B2_RETURN_NOT_OK(b2_take(ctx, &keys[k], &perm32.a, /*boundscheck=*/0, &gathered.a, stream));
+    gathered.owned = true;
+    B2_RETURN_NOT_OK(sort_run(ctx, &gathered.a, orders[k], null_placement,
+                              static_cast<const uint32_t*>(perm32.a.data) + perm32.a.offset, &next.a, stream));
+    perm.a = next.a;
+    perm.owned = true;
+  }
+  *out = perm.a;
+  perm.owned = false;
+  return B2_OK;
+}

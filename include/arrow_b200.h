@@ -247,6 +247,14 @@ typedef enum B2ValidityOp {
 B2_API int b2_validity(B2Context* ctx, int op, const B2Array* in, int nan_is_null, B2Array* out,
                        void* stream);
 
+/* if_else(cond, left, right).  Replaces IfElseFunctor<Type>::Call and the AAA/ASA/AAS/ASS shapes
+ * (kernels/scalar_if_else.cc:62-520): out = cond ? left : right; out is null where cond is null or the chosen side
+ * is.  cond: boolean array or scalar; left / right: arrays or scalars of ONE fixed-width numeric or boolean type (the
+ * caller applies DispatchBest's casts); at least one of the three is an array, arrays agree in length
+ * (else B2_INVALID "Array arguments must all be the same length"). */
+B2_API int b2_if_else(B2Context* ctx, const B2Value* cond, const B2Value* left, const B2Value* right,
+                      B2Array* out, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Filter.  Replaces PrimitiveFilterExec / BinaryFilterExec /
  * DictionaryFilterExec (kernels/vector_selection_filter_internal.cc:445-510,
@@ -300,6 +308,11 @@ B2_API int b2_sort_indices(B2Context* ctx, const B2Array* values, int order,
  * afterwards (b2_sort_indices + b2_take = a second, random-access-bound pass). */
 B2_API int b2_sort_payload(B2Context* ctx, const B2Array* values, const B2Array* payload, int order,
                            int null_placement, B2Array* out, void* stream);
+/* Multi-key SortIndices (record batch / table sort, kernels/vector_sort.cc:386-600,850-1027): rows ordered by keys[0],
+ * ties by keys[1], ...; orders[k] = 0 ascending / 1 descending per key; one null placement (0 = AtStart, 1 = AtEnd); stable.  Every key column
+ * is numeric and of the same length (< 2^32 - 8192 rows).  out: B2_UINT64 row indices. */
+B2_API int b2_sort_indices_multi(B2Context* ctx, const B2Array* keys, int n_keys, const int32_t* orders,
+                                 int null_placement, B2Array* out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Grouper.  Replaces Grouper::{Make,Consume,Lookup,GetUniques,num_groups,Reset}

@@ -386,6 +386,29 @@ def validity_op(op: str, arr: pa.Array, nan_is_null: bool = False) -> pa.Array:
     raise NotImplementedError(op)
 
 
+def if_else(cond, left, right) -> pa.Array:
+    """if_else (kernels/scalar_if_else.cc:62-520): out = cond ? left : right; valid = cond valid AND the chosen side's
+    validity.  Numeric left / right are promoted to CommonNumeric first (scalar_if_else.cc:1227-1266)."""
+    n = next(len(x) for x in (cond, left, right) if isinstance(x, pa.Array))
+    c, vc = _bool_operand(cond, n)
+    sides = [x if isinstance(x, (pa.Array, pa.Scalar)) else pa.scalar(x) for x in (left, right)]
+    if all(pa.types.is_boolean(x.type) for x in sides):
+        (l, vl), (r, vr) = (_bool_operand(x, n) for x in sides)
+        return make_array(pa.bool_(), np.where(c, l, r), vc & np.where(c, vl, vr))
+    t = sides[0].type if sides[0].type == sides[1].type else common_numeric([x.type for x in sides])
+    dt = np_dtype(t)
+    cols = []
+    for x in sides:
+        if isinstance(x, pa.Array):
+            cols.append((values(x).astype(dt), validity(x)))
+        elif x.is_valid:
+            cols.append((np.full(n, x.as_py(), dtype=dt), np.ones(n, dtype=bool)))
+        else:
+            cols.append((np.zeros(n, dtype=dt), np.zeros(n, dtype=bool)))
+    (l, vl), (r, vr) = cols
+    return make_array(t, np.where(c, l, r), vc & np.where(c, vl, vr))
+
+
 # ---------------------------------------------------------------------------------------
 # SortIndices   (kernels/vector_array_sort.cc:144-178,524-540; vector_sort_internal.h:113-305)
 # ---------------------------------------------------------------------------------------
@@ -414,6 +437,19 @@ def sort_indices(arr: pa.Array, order: str = "ascending", null_placement: str = 
     rest = rest[perm]
     out = np.concatenate([rest, nans, nulls] if null_placement == "at_end" else [nulls, nans, rest])
     return make_array(pa.uint64(), out)
+
+
+def sort_indices_multi(columns, sort_keys, null_placement: str = "at_end") -> pa.Array:
+    """SortIndices over a record batch (kernels/vector_sort.cc:386-600): lexicographic over sort_keys = [(name, order)],
+    stable.  Restated as the reference's own fallback states it -- a stable sort per key from the least significant key
+    to the most significant one, each with the single-key rules of sort_indices above (nulls, then NaNs, compare equal
+    among themselves)."""
+    n = len(next(iter(columns.values())))
+    perm = np.arange(n, dtype=np.uint64)
+    for name, order in reversed(list(sort_keys)):
+        col = columns[name].take(pa.array(perm))
+        perm = perm[values(sort_indices(col, order, null_placement)).astype(np.int64)]
+    return pa.array(perm, pa.uint64())
 
 
 # ---------------------------------------------------------------------------------------
