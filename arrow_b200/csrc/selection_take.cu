@@ -18,6 +18,7 @@
 // granular (32 B fetched per 8 B element for random indices): algorithmic bytes/row are
 // idx + 2*W + 2/8 (24.25 for int64 idx / float64) but DRAM traffic
 // for uniformly random indices is ~idx + 32 + W.
+#include <cstdlib>
 #include <type_traits>
 
 #include "bitmap.h"
@@ -54,6 +55,7 @@ struct TakeArgs {
   int64_t* valid_count;    // device counter (popcount of out validity)
   unsigned long long* first_bad;  // device, ~0 initially
   bool vec_ok;
+  int64_t band_rows;  // validity of values[j] is probed here only for j < band_rows (INT64_MAX: every row); see take_bands
 };
 
 // pack each lane's V bits (bit k = element lane*V+k) into V warp-wide words;
@@ -69,6 +71,95 @@ __device__ __forceinline__ unsigned warp_pack_bits(unsigned m, unsigned lane) {
     if (lane == j) mine = w;
   }
   return mine;
+}
+
+
+// ---- validity probes in L2-sized bands ---------------------------------------------------------------------------------
+// A random probe of the values' validity bitmap is a DRAM access whenever the bitmap does not stay in L2, and DRAM
+// random accesses (not bytes) are what bounds Take: 42-44 G/s on this part whatever is fetched
+// (profiles/gather_probe_r01.csv); at 1B rows the 125 MB bitmap misses on ~45 % of the probes
+// (profiles/take_traffic.json), a third of the kernel's DRAM accesses.  So for big bitmaps the bitmap is cut
+// into K bands of <= B2_TAKE_BAND_MB each: the gather kernel probes band 0 only (rows whose index falls in another
+// band are provisionally valid), and K-1 follow-up launches re-stream the INDICES (sequential, 1.2 ps/row) and
+// clear the bits of band b -- every launch's probes hit a bitmap slice that fits L2.  Results are identical.
+__device__ __forceinline__ bool probe_band0(const BitmapReader& valid, uint64_t j, int64_t band_rows, uint64_t pol) {
+  return static_cast<int64_t>(j) < band_rows ? valid.bit_hint(static_cast<int64_t>(j), pol) : true;
+}
+
+struct TakeBandArgs {
+  const void* indices;  // advanced by offset
+  BitmapReader values_valid;
+  int64_t lo, rows;     // this launch probes lo <= j < lo + rows
+  int64_t n;
+  uint32_t* out_validity;  // bit i set: index i valid, in bounds (and the fused kernel's other operand valid)
+  int64_t* valid_count;
+  bool vec_ok;
+};
+
+template <typename UIdx>  // uint32_t / uint64_t: a set output bit implies 0 <= j < values_length, so signedness is moot
+__global__ void __launch_bounds__(kBlock) take_validity_band_kernel(TakeBandArgs a) {
+  constexpr int V = 16 / sizeof(UIdx);
+  constexpr int UU = kUnroll;
+  constexpr int64_t kWarpTile = 32 * V * UU;
+  constexpr int64_t kTile = kWarpTile * kWarpsPerBlock;
+  const unsigned lane = lane_id();
+  const UIdx* __restrict__ idx = static_cast<const UIdx*>(a.indices);
+  const uint64_t pol_bitmap = l2_policy_evict_last();
+  const uint64_t lo = static_cast<uint64_t>(a.lo), rows = static_cast<uint64_t>(a.rows);
+  int64_t cleared = 0;
+  for (int64_t tile = (int64_t)blockIdx.x * kTile; tile < a.n; tile += (int64_t)gridDim.x * kTile) {
+    const int64_t wb = tile + (int64_t)(threadIdx.x >> 5) * kWarpTile;
+    if (wb >= a.n) continue;
+    if (a.vec_ok && wb + kWarpTile <= a.n) {
+      Vec<UIdx, V> ix[UU];
+      unsigned cur[UU];
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        const int64_t i0 = wb + u * 32 * V + lane * V;
+        ix[u] = load_vec<UIdx, V>(idx + i0);
+        cur[u] = (a.out_validity[i0 >> 5] >> (i0 & 31)) & ((1u << V) - 1u);  // V divides 32: no straddling
+      }
+      unsigned clear[UU];
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        clear[u] = 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const uint64_t j = static_cast<uint64_t>(ix[u].v[k]);
+          if (((cur[u] >> k) & 1u) && (j - lo) < rows)
+            clear[u] |= (a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) ? 0u : 1u) << k;
+        }
+      }
+      __syncwarp();  // every lane has read its output word before the owners rewrite them
+#pragma unroll
+      for (int u = 0; u < UU; ++u) {
+        const unsigned w = warp_pack_bits<V>(clear[u], lane);
+        if (lane < V && w) {
+          uint32_t* word = a.out_validity + ((wb + u * 32 * V) >> 5) + lane;
+          *word &= ~w;  // this lane owns the word: probed bits were set, so exactly popc(w) bits go
+          cleared += __popc(w);
+        }
+      }
+    } else {
+      const int64_t end = wb + kWarpTile < a.n ? wb + kWarpTile : a.n;
+      for (int64_t base = wb; base < end; base += 32) {
+        const int64_t i = base + lane;
+        bool clr = false;
+        const uint32_t curw = a.out_validity[base >> 5];
+        if (i < end && ((curw >> lane) & 1u)) {
+          const uint64_t j = static_cast<uint64_t>(idx[i]);
+          if ((j - lo) < rows) clr = !a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap);
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, clr);
+        if (lane == 0 && w) {
+          a.out_validity[base >> 5] = curw & ~w;
+          cleared += __popc(w);
+        }
+      }
+    }
+  }
+  const int64_t s = block_sum<kBlock>(cleared);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(a.valid_count), static_cast<unsigned long long>(-s));
 }
 
 template <int W, typename Idx, bool HAS_VALID>
@@ -118,7 +209,7 @@ __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
           if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(wb + u * 32 * V + lane * V + k));
           if (iv && inb) {
             g[u].v[k] = ld_hint<T>(vals + j, pol_values);
-            if (HAS_VALID) gvalid[u] |= (a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) ? 1u : 0u) << k;
+            if (HAS_VALID) gvalid[u] |= (probe_band0(a.values_valid, j, a.band_rows, pol_bitmap) ? 1u : 0u) << k;
           } else {
             g[u].v[k] = zero_value<T>();
           }
@@ -150,7 +241,7 @@ __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
           if (iv && !inb) atomicMin(a.first_bad, static_cast<unsigned long long>(i));
           if (iv && inb) {
             out[i] = ld_hint<T>(vals + j, pol_values);
-            ov = HAS_VALID ? a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) : true;
+            ov = HAS_VALID ? probe_band0(a.values_valid, j, a.band_rows, pol_bitmap) : true;
           } else {
             out[i] = zero_value<T>();
           }
@@ -220,6 +311,7 @@ struct FusedTakeArgs {
   int64_t* valid_count;
   unsigned long long* first_bad;
   bool vec_ok;
+  int64_t band_rows;  // as in TakeArgs
 };
 
 template <typename OT>
@@ -280,7 +372,7 @@ __global__ void __launch_bounds__(kBlock) take_cast_arith_kernel(FusedTakeArgs a
           if (iv && inb) {
             g = ld_hint<VT>(vals + j, pol_values);
             if (HAS_VALID && ((rvalid[u] >> k) & 1u))
-              gvalid[u] |= (a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap) ? 1u : 0u) << k;
+              gvalid[u] |= (probe_band0(a.values_valid, j, a.band_rows, pol_bitmap) ? 1u : 0u) << k;
           }
           r[u].v[k] = fused_apply<OT>(a.op, static_cast<OT>(g), oth[u].v[k]);
         }
@@ -311,7 +403,7 @@ __global__ void __launch_bounds__(kBlock) take_cast_arith_kernel(FusedTakeArgs a
           VT g = VT(0);
           if (iv && inb) {
             g = ld_hint<VT>(vals + j, pol_values);
-            ov = HAS_VALID ? (a.other_valid.bit(i) && a.values_valid.bit_hint(static_cast<int64_t>(j), pol_bitmap)) : true;
+            ov = HAS_VALID ? (a.other_valid.bit(i) && probe_band0(a.values_valid, j, a.band_rows, pol_bitmap)) : true;
           }
           out[i] = fused_apply<OT>(a.op, static_cast<OT>(g), other ? other[i] : oscalar);
         }
@@ -362,6 +454,52 @@ static int launch_fused_take_val(int value_type, int idx_type, const FusedTakeAr
     case B2_INT32: return launch_fused_take_idx<int32_t, OT>(idx_type, a, has_valid, s);
     default: return set_error(B2_NOT_IMPLEMENTED, "b2_take_cast_arith: float64 / float32 / int64 / int32 values only (type id %d)", value_type);
   }
+}
+
+
+// Band plan (see probe_band0).  Banding pays when the probes would thrash: a bitmap well beyond what L2 keeps
+// (measured: a 64 MB table gathers at 211 G/s, a 128 MB one at 96 G/s) and enough rows that every bitmap line is
+// probed many times; each extra band costs one sequential pass over the indices.
+struct TakeBands {
+  int k = 1;
+  int64_t rows = INT64_MAX;
+};
+
+static TakeBands take_bands(const B2Array* values, int64_t n, int iw) {
+  TakeBands b;
+  // B2_TAKE_BAND_MB: band size (0 disables); B2_TAKE_BAND_KB: the same in KB and without the size thresholds (tests)
+  const char* ekb = getenv("B2_TAKE_BAND_KB");
+  const char* emb = getenv("B2_TAKE_BAND_MB");
+  int64_t band = ekb ? (strtol(ekb, nullptr, 10) << 10) : ((emb ? strtol(emb, nullptr, 10) : 48) << 20);
+  if (band <= 0 || values->null_count == 0 || !values->validity || (iw != 4 && iw != 8)) return b;
+  const int64_t bytes = values->length >> 3;
+  if (!ekb && (bytes < 2 * band || n < (1 << 24))) return b;
+  const int64_t k = (bytes + band - 1) / band;
+  if (k < 2 || k > 6) return b;  // beyond 6 the index re-reads would cost what the misses do
+  b.k = static_cast<int>(k);
+  b.rows = (((values->length + k - 1) / k) + 1023) & ~int64_t(1023);
+  return b;
+}
+
+static int launch_take_bands(const TakeBands& bands, const void* indices, int iw, const BitmapReader& values_valid, int64_t n,
+                             uint32_t* out_validity, int64_t* valid_count, cudaStream_t s) {
+  for (int b = 1; b < bands.k; ++b) {
+    TakeBandArgs a;
+    a.indices = indices;
+    a.values_valid = values_valid;
+    a.lo = b * bands.rows;
+    a.rows = bands.rows;
+    a.n = n;
+    a.out_validity = out_validity;
+    a.valid_count = valid_count;
+    a.vec_ok = aligned_to(indices, 16);
+    const int64_t tile = (int64_t)32 * (16 / iw) * kUnroll * kWarpsPerBlock;
+    const int grid = grid_for(n, tile, kSMs * 8 * 16);
+    if (iw == 4) take_validity_band_kernel<uint32_t><<<grid, kBlock, 0, s>>>(a);
+    else take_validity_band_kernel<uint64_t><<<grid, kBlock, 0, s>>>(a);
+    B2_LAUNCHED();
+  }
+  return B2_OK;
 }
 
 int take_bool(B2Context* ctx, const B2Array* values, const B2Array* indices, B2Array* out, cudaStream_t s);  // selection_bool.cu
@@ -466,10 +604,13 @@ extern "C" int b2_take_cast_arith(B2Context* ctx, const B2Array* values, const B
   a.valid_count = slot.dev();
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 1);
   a.vec_ok = aligned_to(a.indices, 16) && aligned_to(a.out, 16) && (!a.other || aligned_to(a.other, 16));
+  const TakeBands bands = take_bands(values, n, iw);
+  a.band_rows = bands.rows;
   if (scalar_null) return set_error(B2_NOT_IMPLEMENTED, "b2_take_cast_arith: null scalar operand (the result is all null; use the unfused kernels)");
   int st = to_type == B2_FLOAT ? launch_fused_take_val<float>(values->type, indices->type, a, has_valid, s)
                                : launch_fused_take_val<double>(values->type, indices->type, a, has_valid, s);
   if (st != B2_OK) return st;
+  B2_RETURN_NOT_OK(launch_take_bands(bands, a.indices, iw, a.values_valid, n, a.out_validity, a.valid_count, s));
   B2_RETURN_NOT_OK(slot.fetch(s));
   const uint64_t bad = static_cast<uint64_t>(slot.host()[1]);
   if (bad != ~0ull) return index_error(indices, bad, s);
@@ -524,6 +665,8 @@ extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* ind
   a.valid_count = slot.dev();
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 1);
   a.vec_ok = aligned_to(a.indices, 16) && aligned_to(a.out, 16);
+  const TakeBands bands = take_bands(values, n, iw);
+  a.band_rows = bands.rows;
   int st;
   switch (width) {
     case 1: st = launch_take_w<1>(indices->type, a, has_valid, s); break;
@@ -533,6 +676,7 @@ extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* ind
     default: st = launch_take_w<16>(indices->type, a, has_valid, s); break;
   }
   if (st != B2_OK) return st;
+  B2_RETURN_NOT_OK(launch_take_bands(bands, a.indices, iw, a.values_valid, n, a.out_validity, a.valid_count, s));
   B2_RETURN_NOT_OK(slot.fetch(s));
   uint64_t bad = static_cast<uint64_t>(slot.host()[1]);
   if (bad != ~0ull) {

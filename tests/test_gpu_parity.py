@@ -148,6 +148,36 @@ def test_take_random(ctx, t, it):
             assert_equal(got.to_arrow(), pc.take(v, idx))
 
 
+@pytest.mark.parametrize("it", [pa.int32(), pa.uint32(), pa.int64(), pa.uint64()], ids=str)
+@pytest.mark.parametrize("band_kb", ["1", "2", "3"])
+def test_take_validity_bands(ctx, it, band_kb, monkeypatch):
+    """Big validity bitmaps are probed in L2-sized bands (selection_take.cu take_bands): the gather kernel probes band 0,
+    follow-up launches clear the bits of the other bands.  B2_TAKE_BAND_KB forces the banded path at test sizes
+    (1 KB of bitmap = 8192 rows per band); results must equal the unbanded kernel, the oracle and the reference."""
+    monkeypatch.setenv("B2_TAKE_BAND_KB", band_kb)
+    for t in (pa.float64(), pa.int32(), pa.uint8()):
+        for n_v, n, vnull, inull, off in ((40000, 100003, 0.1, 0.0, 0), (33000, 70000, 0.5, 0.1, 3), (16384, 5, 0.9, 0.0, 1),
+                                          (45000, 262144, 0.02, 0.02, 0)):
+            v = random_array(t, n_v, vnull, SEED + n, offset=off)
+            idx = random_array(it, n, inull, SEED + 7, lo=0, hi=n_v - 1, offset=off)
+            got = bc.take(dev(v, ctx), dev(idx, ctx))
+            want = ora.take(v, idx)
+            assert_equal(got.to_arrow(), want, f"{t} {it} band={band_kb} n={n}")
+            assert got.null_count == want.null_count
+            assert_equal(got.to_arrow(), pc.take(v, idx))
+    # the fused pipeline shares the band plan
+    values = random_array(pa.float64(), 40000, 0.2, SEED, lo=-1000, hi=1000)
+    idx = random_array(it, 150001, 0.05, SEED + 1, lo=0, hi=39999, offset=1)
+    other = random_array(pa.float32(), 150001, 0.1, SEED + 2, lo=-10, hi=10, offset=2)
+    got = bc.take_cast_arith(dev(values, ctx), dev(idx, ctx), pa.float32(), "add", dev(other, ctx))
+    ref = pc.add(pc.cast(pc.take(values, idx), pa.float32(), safe=False), other)
+    assert got.to_arrow().equals(ref) and got.null_count == ref.null_count
+    # an out-of-range index still raises, with the follow-up launches in the queue
+    bad = pa.array([1, 2, 40000, 3] * 10, it)
+    with pytest.raises(pa.ArrowIndexError, match="Index 40000 out of bounds"):
+        bc.take(dev(values, ctx), dev(bad, ctx))
+
+
 def test_take_errors(ctx):
     v = dev(pa.array(range(100), pa.int64()), ctx)
     for bad, it in ((100, pa.int32()), (-1, pa.int64()), (2**40, pa.int64()), (200, pa.uint8())):
