@@ -589,7 +589,7 @@ def dictionary_encode(arr: DeviceArray, null_encoding="mask") -> DeviceArray:
 # grouper + hash aggregates
 # ------------------------------------------------------------------------------------
 class Grouper:
-    """arrow::compute::Grouper (compute/row/grouper.h:104-196) over fixed-width key columns."""
+    """arrow::compute::Grouper (compute/row/grouper.h:104-196) over fixed-width and utf8 / binary key columns."""
 
     def __init__(self, key_types: Sequence[pa.DataType], ctx: Optional[Context] = None):
         self.ctx = ctx or Context.get()

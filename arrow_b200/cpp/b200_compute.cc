@@ -660,7 +660,10 @@ static Status AddHashFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   auto counts = std::make_shared<Forwarding<cp::VectorFunction>>("value_counts", cp::Arity::Unary(), DocFor({"array"}, ""), nullptr);
   auto encode = std::make_shared<Forwarding<cp::VectorFunction>>("dictionary_encode", cp::Arity::Unary(),
                                                                  DocFor({"array"}, "DictionaryEncodeOptions"), &kDictDefaults);
-  for (const auto& ty : NumericTypes()) {
+  // numeric columns and (r2) utf8 / binary ones: the string grouper of csrc/grouper_wide.cu (vector_hash.cc:782-830 registers both)
+  std::vector<std::shared_ptr<DataType>> hashable = NumericTypes();
+  for (const auto& ty : {arrow::utf8(), arrow::large_utf8(), arrow::binary(), arrow::large_binary()}) hashable.push_back(ty);
+  for (const auto& ty : hashable) {
     ARROW_RETURN_NOT_OK(unique->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(FirstType), UniqueExec, nullptr)));
     ARROW_RETURN_NOT_OK(counts->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(ValueCountsType), ValueCountsExec, nullptr)));
     ARROW_RETURN_NOT_OK(encode->AddKernel(MakeVectorKernel(rt, {cp::InputType(ty)}, cp::OutputType(DictEncodeType), DictEncodeExec,

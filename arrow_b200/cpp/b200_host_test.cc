@@ -374,7 +374,27 @@ int main(int argc, char** argv) {
     auto k16 = RandomNumeric<arrow::UInt16Type>(60000, 0.0, 92, 0, 2000);
     auto kf = RandomNumeric<arrow::Int32Type>(5000, 0.3, 93, 0, 40);
     auto kf64 = UNWRAP(cp::Cast(*kf, arrow::float64()));
-    for (const auto& a : {k64, k16, kf64, k64->Slice(7, 1000)}) {
+    // strings: 300 distinct words drawn 40000 times (r2: utf8 / binary through the verified-hash string grouper)
+    std::shared_ptr<arrow::Array> words, lwords;
+    {
+      arrow::StringBuilder sb;
+      arrow::LargeBinaryBuilder lb;
+      auto pick = RandomNumeric<arrow::Int32Type>(40000, 0.05, 94, 0, 299);
+      const auto& pv = static_cast<const arrow::Int32Array&>(*pick);
+      for (int64_t i = 0; i < pv.length(); ++i) {
+        if (pv.IsNull(i)) {
+          (void)sb.AppendNull();
+          (void)lb.AppendNull();
+        } else {
+          const std::string w = std::string(static_cast<size_t>(pv.Value(i) % 7), 'a' + pv.Value(i) % 26) + std::to_string(pv.Value(i));
+          (void)sb.Append(w);
+          (void)lb.Append(w);
+        }
+      }
+      words = UNWRAP(sb.Finish());
+      lwords = UNWRAP(lb.Finish());
+    }
+    for (const auto& a : {k64, k16, kf64, k64->Slice(7, 1000), words, lwords, words->Slice(3, 999)}) {
       const std::string tag = "(" + a->type()->ToString() + ", " + std::to_string(a->length()) + " rows)";
       h.Check("unique" + tag, "unique", {a});
       h.Check("value_counts" + tag, "value_counts", {a});
@@ -433,6 +453,55 @@ int main(int argc, char** argv) {
       return 1;
     }
     std::cout << "OK   grouper consume/uniques (" << dev->num_groups() << " groups, Take(uniques, ids) == keys)" << std::endl;
+
+    // (r2) utf8 key and a 3-column key wider than 64 bits: same contract, plus Lookup of known / unknown rows
+    {
+      arrow::StringBuilder sb;
+      const auto& kv = static_cast<const arrow::Int64Array&>(*keys);
+      for (int64_t i = 0; i < kv.length(); ++i) {
+        if (kv.IsNull(i)) (void)sb.AppendNull();
+        else (void)sb.Append("key-" + std::to_string(kv.Value(i) * 1000003));
+      }
+      auto skeys = UNWRAP(sb.Finish());
+      auto k2 = RandomNumeric<arrow::Int64Type>(50000, 0.05, 79, 0, 3);
+      auto k3 = RandomNumeric<arrow::DoubleType>(50000, 0.0, 80, 0, 2);
+      k3 = UNWRAP(cp::Cast(*UNWRAP(cp::Cast(*k3, arrow::int32(), cp::CastOptions::Unsafe())), arrow::float64()));
+      struct Case { std::vector<arrow::TypeHolder> types; std::vector<std::shared_ptr<arrow::Array>> cols; const char* name; };
+      const std::vector<Case> cases = {{{arrow::utf8()}, {skeys}, "utf8"},
+                                       {{arrow::int64(), arrow::utf8(), arrow::float64()}, {k2, skeys, k3}, "int64+utf8+float64"},
+                                       {{arrow::int64(), arrow::int64()}, {keys, k2}, "int64+int64"}};
+      for (const auto& c : cases) {
+        auto r = UNWRAP(cp::Grouper::Make(c.types, &h.cpu_ctx));
+        auto d = UNWRAP(arrow_b200::MakeGrouper(c.types, h.rt));
+        std::vector<Datum> hv, dv;
+        for (const auto& col : c.cols) {
+          hv.emplace_back(col);
+          dv.emplace_back(h.Dev(col));
+        }
+        cp::ExecBatch hb2(hv, keys->length()), db2(dv, keys->length());
+        auto rid = UNWRAP(r->Consume(cp::ExecSpan(hb2)));
+        auto did = h.Host(UNWRAP(d->Consume(cp::ExecSpan(db2))));
+        auto du = UNWRAP(d->GetUniques());
+        bool ok = d->num_groups() == r->num_groups();
+        (void)rid;  // the stock ids are only a bijection of first-occurrence order; ours are compared through the uniques
+        for (size_t j = 0; ok && j < c.cols.size(); ++j) {
+          auto t = UNWRAP(cp::Take(h.Host(du.values[j]), did, cp::TakeOptions::Defaults(), &h.cpu_ctx));
+          ok = t.make_array()->Equals(*c.cols[j]);
+        }
+        // Lookup: the first 1000 rows are known, a sliced + shifted copy is partly unknown
+        std::vector<Datum> lv;
+        for (const auto& col : c.cols) lv.emplace_back(h.Dev(col->Slice(100, 1000)));
+        cp::ExecBatch lb2(lv, 1000);
+        auto look = h.Host(UNWRAP(d->Lookup(cp::ExecSpan(lb2))));
+        ok = ok && look->Equals(*did->Slice(100, 1000)) && d->num_groups() == r->num_groups();
+        ++g_checks;
+        if (!ok) {
+          std::cout << "FAIL grouper " << c.name << ": groups " << d->num_groups() << " vs " << r->num_groups() << std::endl;
+          return 1;
+        }
+        std::cout << "OK   grouper " << c.name << " keys (" << d->num_groups() << " groups = stock grouper's, Take(uniques, ids) == keys, Lookup)" << std::endl;
+      }
+    }
 
     // ---- hash aggregate kernels driven exactly as acero/aggregate_internal.cc:67-123 does ----
     auto vals = RandomNumeric<arrow::Int64Type>(50000, 0.1, 78, -100, 100);

@@ -478,12 +478,22 @@ __global__ void __launch_bounds__(kBlock) grouper_direct_lookup_kernel(const voi
   if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
 }
 
+// utf8 / binary keys and keys wider than 64 bits: grouper_wide.cu (parts reduced to ids by this file's kernel, then folded)
+struct WideGrouper;
+int wide_create(B2Context* ctx, const int32_t* key_types, int n_keys, WideGrouper** out);
+void wide_destroy(WideGrouper* g);
+int wide_reset(WideGrouper* g);
+uint32_t wide_num_groups(const WideGrouper* g);
+int wide_run(WideGrouper* g, const B2Array* keys, B2Array* out_ids, bool insert, cudaStream_t s);
+int wide_uniques(WideGrouper* g, B2Array* out_keys, cudaStream_t s);
+
 }  // namespace b2
 
 using namespace b2;
 
 struct B2Grouper {
   B2Context* ctx;
+  WideGrouper* wide = nullptr;  // set: every call is forwarded
   KeyLayout layout;
   int32_t key_types[kMaxKeys];
   GrouperTable table{};
@@ -800,6 +810,24 @@ int b2_grouper_create(B2Context* ctx, const int32_t* key_types, int n_keys, B2Gr
   KeyLayout L{};
   L.n_keys = n_keys;
   int bits = 0;
+  {
+    bool wide = false;
+    int total = 0;
+    for (int j = 0; j < n_keys; ++j) {
+      wide = wide || type_is_binary_like(key_types[j]);
+      total += 8 * type_width(key_types[j]) + (n_keys > 1 ? 1 : 0);
+    }
+    if (wide || total > 64) {
+      WideGrouper* w = nullptr;
+      B2_RETURN_NOT_OK(wide_create(ctx, key_types, n_keys, &w));
+      B2Grouper* g = new B2Grouper();
+      g->ctx = ctx;
+      g->wide = w;
+      g->layout.n_keys = n_keys;
+      *out = g;
+      return B2_OK;
+    }
+  }
   for (int j = 0; j < n_keys; ++j) {
     int w = type_width(key_types[j]);
     if (w == 0) return set_error(B2_NOT_IMPLEMENTED, "grouper: key type id %d is not fixed-width", key_types[j]);
@@ -826,6 +854,7 @@ void b2_grouper_destroy(B2Grouper* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
   cudaStream_t s = g->ctx->stream;
+  if (g->wide) wide_destroy(g->wide);
   grouper_free_table(g, s);
   grouper_free_direct(g, s);
   if (g->uniq_keys) g->ctx->free(g->uniq_keys, s);
@@ -836,18 +865,20 @@ void b2_grouper_destroy(B2Grouper* g) {
 int b2_grouper_consume(B2Grouper* g, const B2Array* keys, B2Array* out_ids, void* stream) {
   if (!g || !out_ids) return set_error(B2_INVALID, "b2_grouper_consume: null argument");
   B2_CUDA(cudaSetDevice(g->ctx->device));
+  if (g->wide) return wide_run(g->wide, keys, out_ids, true, g->ctx->pick(stream));
   return grouper_run(g, keys, out_ids, true, g->ctx->pick(stream));
 }
 
 int b2_grouper_lookup(B2Grouper* g, const B2Array* keys, B2Array* out_ids, void* stream) {
   if (!g || !out_ids) return set_error(B2_INVALID, "b2_grouper_lookup: null argument");
   B2_CUDA(cudaSetDevice(g->ctx->device));
+  if (g->wide) return wide_run(g->wide, keys, out_ids, false, g->ctx->pick(stream));
   return grouper_run(g, keys, out_ids, false, g->ctx->pick(stream));
 }
 
 int b2_grouper_num_groups(const B2Grouper* g, uint32_t* out) {
   if (!g || !out) return set_error(B2_INVALID, "b2_grouper_num_groups: null argument");
-  *out = g->num_groups;
+  *out = g->wide ? wide_num_groups(g->wide) : g->num_groups;
   return B2_OK;
 }
 
@@ -856,6 +887,7 @@ int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream) {
   B2Context* ctx = g->ctx;
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
+  if (g->wide) return wide_uniques(g->wide, out_keys, s);
   const uint32_t n = g->num_groups;
   for (int j = 0; j < g->layout.n_keys; ++j) {
     Temp data(ctx, s), bits(ctx, s);
@@ -880,6 +912,7 @@ int b2_grouper_uniques(B2Grouper* g, B2Array* out_keys, void* stream) {
 int b2_grouper_reset(B2Grouper* g) {
   if (!g) return set_error(B2_INVALID, "b2_grouper_reset: null argument");
   B2_CUDA(cudaSetDevice(g->ctx->device));
+  if (g->wide) return wide_reset(g->wide);
   cudaStream_t s = g->ctx->stream;
   grouper_free_table(g, s);
   grouper_free_direct(g, s);

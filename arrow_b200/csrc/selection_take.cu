@@ -473,7 +473,7 @@ static TakeBands take_bands(const B2Array* values, int64_t n, int iw) {
   int64_t band = ekb ? (strtol(ekb, nullptr, 10) << 10) : ((emb ? strtol(emb, nullptr, 10) : 48) << 20);
   if (band <= 0 || values->null_count == 0 || !values->validity || (iw != 4 && iw != 8)) return b;
   const int64_t bytes = values->length >> 3;
-  if (!ekb && (bytes < 2 * band || n < (1 << 24))) return b;
+  if (!ekb && (bytes * 4 < band * 5 || n < (1 << 24))) return b;  // a bitmap up to 1.25 bands is left alone
   const int64_t k = (bytes + band - 1) / band;
   if (k < 2 || k > 6) return b;  // beyond 6 the index re-reads would cost what the misses do
   b.k = static_cast<int>(k);

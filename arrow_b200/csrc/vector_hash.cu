@@ -108,8 +108,8 @@ extern "C" int b2_vector_hash(B2Context* ctx, const B2Array* values, int null_en
                               B2Array* out_dictionary, B2Array* out_counts, void* stream) {
   if (!ctx || !values || !out_dictionary) return set_error(B2_INVALID, "b2_vector_hash: null argument");
   if (null_encoding != 0 && null_encoding != 1) return set_error(B2_INVALID, "b2_vector_hash: null_encoding must be 0 (MASK) or 1 (ENCODE)");
-  if (type_width(values->type) == 0)
-    return set_error(B2_NOT_IMPLEMENTED, "unique/value_counts/dictionary_encode: type id %d is not fixed-width", values->type);
+  if (type_width(values->type) == 0 && !type_is_binary_like(values->type))
+    return set_error(B2_NOT_IMPLEMENTED, "unique/value_counts/dictionary_encode: type id %d is neither fixed-width nor utf8 / binary", values->type);
   B2_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->pick(stream);
   const int64_t n = values->length;

@@ -316,8 +316,11 @@ B2_API int b2_sort_indices_multi(B2Context* ctx, const B2Array* keys, int n_keys
 
 /* ---------------------------------------------------------------------------
  * Grouper.  Replaces Grouper::{Make,Consume,Lookup,GetUniques,num_groups,Reset}
- * (compute/row/grouper.h:104-196; GrouperFastImpl row/grouper.cc:555-963) for
- * fixed-width key columns (1..n_keys columns, each 1/2/4/8 bytes wide).
+ * (compute/row/grouper.h:104-196; GrouperFastImpl row/grouper.cc:555-963, GrouperImpl :300-553)
+ * for 1..8 key columns, each fixed-width numeric (1/2/4/8 bytes) or utf8 / binary / large_utf8 /
+ * large_binary.  Keys that pack into 64 bits use one table (csrc/grouper.cu); wider keys and string
+ * keys are reduced part by part to 32-bit ids and folded (csrc/grouper_wide.cu; strings through a
+ * 64-bit hash whose every row is verified against the stored key bytes).
  * Group ids are dense uint32 assigned in first-occurrence row order.
  * ------------------------------------------------------------------------- */
 typedef struct B2Grouper B2Grouper;

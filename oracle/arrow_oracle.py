@@ -464,13 +464,21 @@ class Grouper:
         self.uniques = []  # list of tuples (per column: bytes or None)
 
     def _rows(self, keys):
+        # one bytes object per key value: the raw little-endian bytes of a fixed-width value, the bytes of a
+        # utf8 / binary value (row/encode_internal.cc encodes both into the row; var-length ones with their length)
         cols = []
         for k in keys:
-            v, valid = values(k), validity(k)
-            raw = v.view(np.uint8).reshape(len(v), -1) if len(v) else np.zeros((0, 1), np.uint8)
+            valid = validity(k)
+            if _is_binary(k.type):
+                offs, data = strings(k)
+                raw = [data[offs[i]:offs[i + 1]].tobytes() for i in range(len(k))]
+            else:
+                v = values(k)
+                raw = v.view(np.uint8).reshape(len(v), -1) if len(v) else np.zeros((0, 1), np.uint8)
+                raw = [raw[i].tobytes() for i in range(len(v))]
             cols.append((raw, valid))
         for i in range(len(keys[0])):
-            yield tuple(raw[i].tobytes() if valid[i] else None for raw, valid in cols)
+            yield tuple(raw[i] if valid[i] else None for raw, valid in cols)
 
     def consume(self, keys) -> pa.Array:
         if isinstance(keys, pa.Array):
@@ -502,8 +510,13 @@ class Grouper:
     def get_uniques(self):
         out = []
         for j, t in enumerate(self.key_types):
-            dt = np_dtype(t)
             valid = np.array([u[j] is not None for u in self.uniques], dtype=bool)
+            if _is_binary(t):
+                lens = np.array([len(u[j]) if u[j] is not None else 0 for u in self.uniques], dtype=np.int64)
+                data = np.frombuffer(b"".join(u[j] for u in self.uniques if u[j] is not None), dtype=np.uint8)
+                out.append(make_strings(t, lens, data, valid))
+                continue
+            dt = np_dtype(t)
             vals = np.array([np.frombuffer(u[j], dtype=dt)[0] if u[j] is not None else 0 for u in self.uniques],
                             dtype=dt)
             out.append(make_array(t, vals, valid))
@@ -566,6 +579,22 @@ def scalar_count(arr: pa.Array, mode="only_valid") -> pa.Scalar:
 # DictEncodeAction only with DictionaryEncodeOptions::ENCODE (api_vector.h:66-82).
 # ---------------------------------------------------------------------------------------
 def _memo(arr: pa.Array, encode_nulls: bool):
+    if _is_binary(arr.type):  # BinaryMemoTable: the same first-occurrence indices over the value bytes
+        valid = validity(arr)
+        offs, data = strings(arr)
+        table, order, idx = {}, [], np.zeros(len(arr), dtype=np.int32)
+        for i in range(len(arr)):
+            if not valid[i] and not encode_nulls:
+                continue
+            key = data[offs[i]:offs[i + 1]].tobytes() if valid[i] else None
+            g = table.get(key)
+            if g is None:
+                g = table[key] = len(order)
+                order.append(i)
+            idx[i] = g
+        order = np.array(order, dtype=np.int64)
+        uniq_valid = valid[order] if len(order) else np.zeros(0, bool)
+        return idx, _gather_strings(arr, order, uniq_valid)
     v, valid = values(arr), validity(arr)
     raw = v.view(np.uint8).reshape(len(v), -1) if len(v) else np.zeros((0, 1), np.uint8)
     table, order, idx = {}, [], np.zeros(len(v), dtype=np.int32)

@@ -359,3 +359,27 @@ def test_scalar_aggregates_vs_reference(t):
         assert ora.scalar_min_max(nan) == pc.min_max(nan)
         allnan = pa.array([np.nan, np.nan], t)
         assert np.isnan(ora.scalar_min_max(allnan)["min"].as_py()) and np.isnan(pc.min_max(allnan)["min"].as_py())
+
+
+@pytest.mark.parametrize("t", [pa.string(), pa.large_string(), pa.binary(), pa.large_binary()], ids=str)
+def test_string_vector_hash_and_grouper_vs_reference(t):
+    """oracle unique / value_counts / dictionary_encode and Grouper over utf8 / binary values against the reference binary
+    (vector_hash.cc:782-830; Grouper ids through Take(uniques, ids) == keys, row/grouper_test.cc:736-760)."""
+    rng = np.random.default_rng(SEED)
+    vocab = [bytes(rng.integers(97, 123, int(rng.integers(0, 12)), dtype=np.uint8)) for _ in range(200)]
+    is_bin = pa.types.is_binary(t) or pa.types.is_large_binary(t)
+    vals = [None if rng.random() < 0.1 else (vocab[i] if is_bin else vocab[i].decode()) for i in rng.integers(0, 200, 3003)]
+    arr = pa.array(vals, t).slice(3)
+    assert ora.unique(arr).equals(pc.unique(arr))
+    assert ora.value_counts(arr).equals(pc.value_counts(arr))
+    for enc in ("mask", "encode"):
+        assert ora.dictionary_encode(arr, enc).equals(pc.dictionary_encode(arr, enc))
+    other = pa.array(rng.integers(0, 3, len(arr)), pa.int64())
+    g = ora.Grouper([t, pa.int64()])
+    ids = g.consume([arr, other])
+    u = g.get_uniques()
+    assert pc.take(u[0], ids).equals(arr) and pc.take(u[1], ids).equals(other)
+    ref = pa.table([arr, other], names=["a", "b"]).group_by(["a", "b"], use_threads=False).aggregate([])
+    assert g.num_groups == ref.num_rows
+    look = g.lookup([pa.array([vals[3], "never-seen" if not is_bin else b"never-seen"], t), pa.array([int(other[0].as_py()), 0], pa.int64())])
+    assert look.to_pylist() == [0, None]
