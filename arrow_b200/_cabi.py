@@ -83,7 +83,7 @@ BOOLEAN_OPS = {"and": 0, "or": 1, "xor": 2, "and_not": 3, "and_kleene": 4, "or_k
 VALIDITY_OPS = {"is_valid": 0, "is_null": 1, "true_unless_null": 2, "is_nan": 3}
 COMM_ID_BYTES = 128
 HASH_AGG_KINDS = {"hash_sum": 0, "hash_count": 1, "hash_count_all": 2, "hash_mean": 3, "hash_min": 4,
-                  "hash_max": 5, "hash_product": 6, "hash_any": 7, "hash_all": 8}
+                  "hash_max": 5, "hash_product": 6, "hash_any": 7, "hash_all": 8, "hash_count_distinct": 9}
 
 # every symbol include/arrow_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p

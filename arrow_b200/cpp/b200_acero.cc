@@ -4,6 +4,7 @@
 // acero/exec_plan.h:125-345,353-369):
 //   GroupByNode  acero/groupby_aggregate_node.cc:62-453  -> "b200_aggregate"
 //   FilterNode   acero/filter_node.cc:74-106              -> "b200_filter"
+//   ProjectNode  acero/project_node.cc:43-120             -> "b200_project"
 //   OrderByNode  acero/order_by_node.cc:44-161            -> "b200_order_by"
 // Options are the reference's own (AggregateNodeOptions, FilterNodeOptions,
 // OrderByNodeOptions, acero/options.h:250-260,335-351,539-546).
@@ -424,9 +425,99 @@ class AggregateNode : public DeviceNode {
 };
 
 // ------------------------------------------------------------------------------------------
-// filter: ExecuteScalarExpression + Filter on every column (acero/filter_node.cc:74-106)
+// filter / project: the map-style nodes (acero/filter_node.cc:74-106, acero/project_node.cc:83-104)
+//
+// B200-first shape: the reference evaluates the expression on every <= 32Ki-row
+// ExecBatch.  Here host batches are COALESCED (kMapCoalesceRows rows or the end of input, one H2D copy per column), the
+// expression runs once per coalesced batch through the nested registry (every call is a GPU kernel), and the result
+// STAYS ON THE DEVICE when the consumer is another b200_ node -- table_source -> b200_filter -> b200_project ->
+// b200_aggregate crosses PCIe once on the way in and once, group-sized, on the way out.  Batches that already live on the
+// device are processed as they are (no copy).
 // ------------------------------------------------------------------------------------------
-class FilterNode : public DeviceNode {
+constexpr int64_t kMapCoalesceRows = 4ll << 20;
+
+class MapNode : public DeviceNode {
+ public:
+  MapNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
+      : DeviceNode(plan, std::move(inputs), std::move(s), rt) {}
+
+  Status InputReceived(ac::ExecNode*, cp::ExecBatch batch) override {
+    std::lock_guard<std::mutex> lk(mu_);
+    bool all_device = !batch.values.empty();
+    for (auto& v : batch.values) all_device = all_device && v.is_array() && IsOnDevice(*v.array());
+    if (all_device) {
+      ARROW_RETURN_NOT_OK(Flush());
+      ARROW_RETURN_NOT_OK(Process(batch));
+    } else {
+      if (pending_.empty()) pending_.resize(batch.values.size());
+      for (size_t i = 0; i < batch.values.size(); ++i) {
+        if (batch.values[i].is_scalar()) {
+          ARROW_ASSIGN_OR_RAISE(auto arr, arrow::MakeArrayFromScalar(*batch.values[i].scalar(), batch.length));
+          pending_[i].push_back(std::move(arr));
+        } else if (IsOnDevice(*batch.values[i].array())) {
+          ARROW_ASSIGN_OR_RAISE(auto hst, ToHost(*batch.values[i].array()));  // a mixed batch: park it with the host ones
+          pending_[i].push_back(arrow::MakeArray(hst));
+        } else {
+          pending_[i].push_back(batch.values[i].make_array());
+        }
+      }
+      pending_rows_ += batch.length;
+      if (pending_rows_ >= kMapCoalesceRows) ARROW_RETURN_NOT_OK(Flush());
+    }
+    ++seen_;
+    return MaybeFinish();
+  }
+  Status InputFinished(ac::ExecNode*, int total) override {
+    std::lock_guard<std::mutex> lk(mu_);
+    total_ = total;
+    return MaybeFinish();
+  }
+
+ protected:
+  // device batch in, device batch out; an empty optional result drops the batch
+  virtual Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) = 0;
+
+ private:
+  Status Flush() {
+    if (pending_rows_ == 0) return Status::OK();
+    cp::ExecBatch dev({}, pending_rows_);
+    for (auto& chunks : pending_) {
+      std::shared_ptr<arrow::Array> whole;
+      if (chunks.size() == 1) whole = chunks[0];
+      else { ARROW_ASSIGN_OR_RAISE(whole, arrow::Concatenate(chunks, plan_->query_context()->memory_pool())); }
+      ARROW_ASSIGN_OR_RAISE(auto d, ToDevice(*whole->data(), rt_->memory_manager()));
+      dev.values.emplace_back(std::move(d));
+      chunks.clear();
+    }
+    pending_rows_ = 0;
+    return Process(dev);
+  }
+  Status Process(const cp::ExecBatch& dev) {
+    ARROW_ASSIGN_OR_RAISE(cp::ExecBatch out, Transform(dev));
+    if (out.length == 0 && emitted_ > 0) return Status::OK();
+    if (dynamic_cast<DeviceNode*>(output_) == nullptr) {  // a stock consumer reads host memory
+      for (auto& v : out.values) {
+        if (!v.is_array() || !IsOnDevice(*v.array())) continue;
+        ARROW_ASSIGN_OR_RAISE(auto hst, ToHost(*v.array()));
+        v = Datum(std::move(hst));
+      }
+    }
+    ++emitted_;
+    return output_->InputReceived(this, std::move(out));
+  }
+  Status MaybeFinish() {
+    if (total_ < 0 || seen_ < total_ || done_) return Status::OK();
+    done_ = true;
+    ARROW_RETURN_NOT_OK(Flush());
+    return output_->InputFinished(this, emitted_);
+  }
+  std::vector<arrow::ArrayVector> pending_;
+  int64_t pending_rows_ = 0;
+  int seen_ = 0, total_ = -1, emitted_ = 0;
+  bool done_ = false;
+};
+
+class FilterNode : public MapNode {
  public:
   static Result<ac::ExecNode*> Make(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, const ac::ExecNodeOptions& options) {
     const auto& opts = static_cast<const ac::FilterNodeOptions&>(options);
@@ -443,34 +534,77 @@ class FilterNode : public DeviceNode {
     return plan->AddNode(std::move(node));
   }
   FilterNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
-      : DeviceNode(plan, std::move(inputs), std::move(s), rt) {}
+      : MapNode(plan, std::move(inputs), std::move(s), rt) {}
   const char* kind_name() const override { return "B200FilterNode"; }
 
-  Status InputReceived(ac::ExecNode*, cp::ExecBatch batch) override {
-    cp::ExecBatch out({}, 0);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      cp::ExecBatch dev({}, batch.length);
-      for (auto& v : batch.values) {
-        ARROW_ASSIGN_OR_RAISE(auto d, ColumnToDevice(rt_, v, batch.length));
-        dev.values.push_back(std::move(d));
-      }
-      ARROW_ASSIGN_OR_RAISE(Datum mask, cp::ExecuteScalarExpression(filter_, dev, &ctx_));
-      if (mask.is_scalar()) return Status::NotImplemented("b200_filter: scalar filter result");
+ protected:
+  Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) override {
+    ARROW_ASSIGN_OR_RAISE(Datum mask, cp::ExecuteScalarExpression(filter_, dev, &ctx_));
+    if (mask.is_scalar()) {  // filter_node.cc:85-98: true keeps the batch, false / null drops every row
+      const auto& b = mask.scalar_as<arrow::BooleanScalar>();
+      if (b.is_valid && b.value) return dev;
+      cp::ExecBatch none({}, 0);
       for (auto& v : dev.values) {
-        ARROW_ASSIGN_OR_RAISE(Datum f, cp::CallFunction("filter", {v, mask}, &drop_, &ctx_));
-        ARROW_ASSIGN_OR_RAISE(auto h, ToHost(*f.array()));
-        out.length = h->length;
-        out.values.emplace_back(std::move(h));
+        ARROW_ASSIGN_OR_RAISE(auto empty, arrow::MakeEmptyArray(v.type()));
+        none.values.emplace_back(empty);
       }
+      return none;
     }
-    return output_->InputReceived(this, std::move(out));
+    cp::ExecBatch out({}, 0);
+    for (auto& v : dev.values) {
+      ARROW_ASSIGN_OR_RAISE(Datum f, cp::CallFunction("filter", {v, mask}, &drop_, &ctx_));
+      out.length = f.length();
+      out.values.emplace_back(std::move(f));
+    }
+    return out;
   }
-  Status InputFinished(ac::ExecNode*, int total) override { return output_->InputFinished(this, total); }
 
  private:
   cp::Expression filter_;
   cp::FilterOptions drop_{cp::FilterOptions::DROP};
+};
+
+class ProjectNode : public MapNode {
+ public:
+  static Result<ac::ExecNode*> Make(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, const ac::ExecNodeOptions& options) {
+    const auto& opts = static_cast<const ac::ProjectNodeOptions&>(options);
+    if (inputs.size() != 1) return Status::Invalid("b200_project needs exactly one input");
+    ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
+    auto in_schema = inputs[0]->output_schema();
+    cp::ExecContext bind_ctx(plan->query_context()->memory_pool(), nullptr, rt->registry());
+    std::vector<cp::Expression> exprs = opts.expressions;
+    std::vector<std::string> names = opts.names;
+    if (names.empty())  // project_node.cc:56-61
+      for (const auto& e : exprs) names.push_back(e.ToString());
+    if (names.size() != exprs.size()) return Status::Invalid("b200_project: ", exprs.size(), " expressions but ", names.size(), " names");
+    arrow::FieldVector fields;
+    for (size_t i = 0; i < exprs.size(); ++i) {
+      if (!exprs[i].IsBound()) { ARROW_ASSIGN_OR_RAISE(exprs[i], exprs[i].Bind(*in_schema, &bind_ctx)); }
+      fields.push_back(arrow::field(names[i], exprs[i].type()->GetSharedPtr()));
+    }
+    auto node = std::make_unique<ProjectNode>(plan, inputs, arrow::schema(std::move(fields)), rt);
+    node->exprs_ = std::move(exprs);
+    return plan->AddNode(std::move(node));
+  }
+  ProjectNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
+      : MapNode(plan, std::move(inputs), std::move(s), rt) {}
+  const char* kind_name() const override { return "B200ProjectNode"; }
+
+ protected:
+  Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) override {
+    cp::ExecBatch out({}, dev.length);
+    for (const auto& e : exprs_) {
+      ARROW_ASSIGN_OR_RAISE(Datum v, cp::ExecuteScalarExpression(e, dev, &ctx_));
+      if (v.is_scalar()) {  // a literal column: materialise it on the device like every other column
+        ARROW_ASSIGN_OR_RAISE(v, ColumnToDevice(rt_, v, dev.length));
+      }
+      out.values.emplace_back(std::move(v));
+    }
+    return out;
+  }
+
+ private:
+  std::vector<cp::Expression> exprs_;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -481,12 +615,12 @@ class OrderByNode : public DeviceNode {
   static Result<ac::ExecNode*> Make(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, const ac::ExecNodeOptions& options) {
     const auto& opts = static_cast<const ac::OrderByNodeOptions&>(options);
     if (inputs.size() != 1) return Status::Invalid("b200_order_by needs exactly one input");
-    if (opts.ordering.sort_keys().size() != 1) return Status::NotImplemented("b200_order_by: exactly one sort key");
+    if (opts.ordering.sort_keys().empty()) return Status::Invalid("`ordering` must be an explicit non-empty ordering");  // order_by_node.cc:62-65
     ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
     auto schema = inputs[0]->output_schema();
     auto node = std::make_unique<OrderByNode>(plan, inputs, schema, rt);
-    ARROW_ASSIGN_OR_RAISE(node->key_, FieldIndex(opts.ordering.sort_keys()[0].target, *schema));
-    node->sort_ = cp::ArraySortOptions(opts.ordering.sort_keys()[0].order, opts.ordering.null_placement());
+    for (const auto& k : opts.ordering.sort_keys()) { ARROW_RETURN_NOT_OK(FieldIndex(k.target, *schema).status()); }
+    node->sort_ = cp::SortOptions(opts.ordering.sort_keys(), opts.ordering.null_placement());
     return plan->AddNode(std::move(node));
   }
   OrderByNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
@@ -495,6 +629,12 @@ class OrderByNode : public DeviceNode {
 
   Status InputReceived(ac::ExecNode*, cp::ExecBatch batch) override {
     std::lock_guard<std::mutex> lk(mu_);
+    for (auto& v : batch.values) {  // an upstream b200_ node hands device columns over: the accumulation below is host-side
+      if (v.is_array() && IsOnDevice(*v.array())) {
+        ARROW_ASSIGN_OR_RAISE(auto hst, ToHost(*v.array()));
+        v = Datum(std::move(hst));
+      }
+    }
     ARROW_ASSIGN_OR_RAISE(auto rb, batch.ToRecordBatch(output_schema_));
     batches_.push_back(std::move(rb));
     ++seen_;
@@ -514,16 +654,24 @@ class OrderByNode : public DeviceNode {
     ARROW_ASSIGN_OR_RAISE(table, table->CombineChunks());
     cp::ExecBatch out({}, table->num_rows());
     if (table->num_rows() > 0) {
-      std::vector<Datum> dev;
+      // one H2D copy per column, SortIndices over the device record batch (any number of keys: b2_sort_indices_multi),
+      // Take of every column (order_by_node.cc:117-124 does the same two calls on the CPU)
+      std::vector<std::shared_ptr<arrow::ArrayData>> dev;
       for (const auto& col : table->columns()) {
         ARROW_ASSIGN_OR_RAISE(auto d, ToDevice(*col->chunk(0)->data(), rt_->memory_manager()));
-        dev.emplace_back(std::move(d));
+        dev.push_back(std::move(d));
       }
-      ARROW_ASSIGN_OR_RAISE(Datum idx, cp::CallFunction("array_sort_indices", {dev[key_]}, &sort_, &ctx_));
+      auto rb = arrow::RecordBatch::Make(output_schema_, table->num_rows(), dev);
+      ARROW_ASSIGN_OR_RAISE(Datum idx, cp::CallFunction("sort_indices", {Datum(rb)}, &sort_, &ctx_));
+      const bool keep_on_device = dynamic_cast<DeviceNode*>(output_) != nullptr;
       for (auto& d : dev) {
-        ARROW_ASSIGN_OR_RAISE(Datum t, cp::CallFunction("take", {d, idx}, nullptr, &ctx_));
-        ARROW_ASSIGN_OR_RAISE(auto h, ToHost(*t.array()));
-        out.values.emplace_back(std::move(h));
+        ARROW_ASSIGN_OR_RAISE(Datum t, cp::CallFunction("take", {Datum(d), idx}, nullptr, &ctx_));
+        if (keep_on_device) {
+          out.values.emplace_back(std::move(t));
+        } else {
+          ARROW_ASSIGN_OR_RAISE(auto h, ToHost(*t.array()));
+          out.values.emplace_back(std::move(h));
+        }
       }
     } else {
       for (const auto& f : output_schema_->fields()) {
@@ -534,8 +682,7 @@ class OrderByNode : public DeviceNode {
     ARROW_RETURN_NOT_OK(output_->InputReceived(this, std::move(out)));
     return output_->InputFinished(this, 1);
   }
-  int key_ = 0;
-  cp::ArraySortOptions sort_{cp::SortOrder::Ascending, cp::NullPlacement::AtEnd};
+  cp::SortOptions sort_{{}, cp::NullPlacement::AtEnd};
   std::vector<std::shared_ptr<arrow::RecordBatch>> batches_;
   int seen_ = 0, total_ = -1;
   bool done_ = false;
@@ -543,7 +690,7 @@ class OrderByNode : public DeviceNode {
 
 }  // namespace
 
-// Adds "b200_aggregate", "b200_filter", "b200_order_by" to the default ExecFactoryRegistry
+// Adds "b200_aggregate", "b200_filter", "b200_project", "b200_order_by" to the default ExecFactoryRegistry
 // (acero/exec_plan.h:355-368; the default registry refuses duplicates of the stock names,
 // acero/exec_plan.cc:1132-1143, hence the prefix).
 Status RegisterAceroNodes() {
@@ -553,6 +700,7 @@ Status RegisterAceroNodes() {
     auto* reg = ac::default_exec_factory_registry();
     st = reg->AddFactory("b200_aggregate", AggregateNode::Make);
     if (st.ok()) st = reg->AddFactory("b200_filter", FilterNode::Make);
+    if (st.ok()) st = reg->AddFactory("b200_project", ProjectNode::Make);
     if (st.ok()) st = reg->AddFactory("b200_order_by", OrderByNode::Make);
   });
   return st;

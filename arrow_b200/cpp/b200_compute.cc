@@ -889,7 +889,7 @@ static Result<std::unique_ptr<cp::KernelState>> HashAggInit(cp::KernelContext* c
   auto st = std::make_unique<HashAggState>();
   st->rt = kd.rt;
   B2HashAggOptions o{1, 1, 0, 0};
-  if (kd.kind == B2_HASH_COUNT) {
+  if (kd.kind == B2_HASH_COUNT || kd.kind == B2_HASH_COUNT_DISTINCT) {
     if (auto co = static_cast<const cp::CountOptions*>(args.options))
       o.count_mode = co->mode == cp::CountOptions::ONLY_VALID ? 0 : co->mode == cp::CountOptions::ONLY_NULL ? 1 : 2;
   } else if (kd.kind != B2_HASH_COUNT_ALL) {
@@ -940,12 +940,13 @@ static Status HashAggFinalize(cp::KernelContext* ctx, Datum* out) {
 static Status AddHashAggregate(cp::FunctionRegistry* reg, Runtime* rt, const std::string& name, int kind) {
   static const cp::ScalarAggregateOptions kAggDefaults = cp::ScalarAggregateOptions::Defaults();
   static const cp::CountOptions kCountDefaults = cp::CountOptions::Defaults();
-  const cp::FunctionOptions* defaults = kind == B2_HASH_COUNT ? static_cast<const cp::FunctionOptions*>(&kCountDefaults)
+  const bool count_opts = kind == B2_HASH_COUNT || kind == B2_HASH_COUNT_DISTINCT;
+  const cp::FunctionOptions* defaults = count_opts ? static_cast<const cp::FunctionOptions*>(&kCountDefaults)
                                         : kind == B2_HASH_COUNT_ALL ? nullptr : &kAggDefaults;
   auto fn = std::make_shared<cp::HashAggregateFunction>(
       name, kind == B2_HASH_COUNT_ALL ? cp::Arity::Unary() : cp::Arity::Binary(),
       kind == B2_HASH_COUNT_ALL ? DocFor({"group_id_array"})
-                                : DocFor({"array", "group_id_array"}, kind == B2_HASH_COUNT ? "CountOptions" : "ScalarAggregateOptions"),
+                                : DocFor({"array", "group_id_array"}, count_opts ? "CountOptions" : "ScalarAggregateOptions"),
       defaults);
   auto out_resolver = [kind](cp::KernelContext* ctx, const std::vector<TypeHolder>& types) -> Result<TypeHolder> {
     if (kind == B2_HASH_COUNT_ALL) return TypeHolder(arrow::int64());
@@ -963,6 +964,10 @@ static Status AddHashAggregate(cp::FunctionRegistry* reg, Runtime* rt, const std
     ARROW_RETURN_NOT_OK(add({cp::InputType::Any(), cp::InputType(arrow::uint32())}));
   } else if (kind == B2_HASH_ANY || kind == B2_HASH_ALL) {
     ARROW_RETURN_NOT_OK(add({cp::InputType(arrow::boolean()), cp::InputType(arrow::uint32())}));
+  } else if (kind == B2_HASH_COUNT_DISTINCT) {
+    for (const auto& ty : NumericTypes()) ARROW_RETURN_NOT_OK(add({cp::InputType(ty), cp::InputType(arrow::uint32())}));
+    for (const auto& ty : {arrow::utf8(), arrow::large_utf8(), arrow::binary(), arrow::large_binary()})
+      ARROW_RETURN_NOT_OK(add({cp::InputType(ty), cp::InputType(arrow::uint32())}));
   } else {
     for (const auto& ty : NumericTypes()) ARROW_RETURN_NOT_OK(add({cp::InputType(ty), cp::InputType(arrow::uint32())}));
   }
@@ -1052,7 +1057,8 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},
                                               {"hash_count_all", B2_HASH_COUNT_ALL}, {"hash_mean", B2_HASH_MEAN},
                                               {"hash_min", B2_HASH_MIN}, {"hash_max", B2_HASH_MAX},
-                                              {"hash_product", B2_HASH_PRODUCT}, {"hash_any", B2_HASH_ANY}, {"hash_all", B2_HASH_ALL}};
+                                              {"hash_product", B2_HASH_PRODUCT}, {"hash_any", B2_HASH_ANY}, {"hash_all", B2_HASH_ALL},
+                                              {"hash_count_distinct", B2_HASH_COUNT_DISTINCT}};
   for (const auto& a : aggs) ARROW_RETURN_NOT_OK(AddHashAggregate(reg, rt, a.first, a.second));
   return Status::OK();
 }

@@ -701,6 +701,55 @@ int main(int argc, char** argv) {
       return 1;
     }
     std::cout << "OK   b200_order_by == order_by (stable, descending, nulls first)" << std::endl;
+    // (r2) two sort keys: k descending, then v ascending (b2_sort_indices_multi behind sort_indices on the device record batch)
+    {
+      cp::Ordering ord2({cp::SortKey("k", cp::SortOrder::Descending), cp::SortKey("v", cp::SortOrder::Ascending)}, cp::NullPlacement::AtEnd);
+      auto want2 = run("order_by", std::make_shared<ac::OrderByNodeOptions>(ord2));
+      auto got2 = run("b200_order_by", std::make_shared<ac::OrderByNodeOptions>(ord2));
+      ++g_checks;
+      if (!got2->CombineChunks().ValueOrDie()->Equals(*want2->CombineChunks().ValueOrDie())) {
+        std::cout << "FAIL b200_order_by (two keys)" << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_order_by == order_by (two keys: k descending, v ascending, nulls last)" << std::endl;
+    }
+    // (r2) project alone, then the device-resident pipeline filter -> project -> aggregate: with the b200_ factories the
+    // columns cross PCIe once on the way in (coalesced) and the 1000 groups once on the way out
+    {
+      std::vector<cp::Expression> exprs = {cp::field_ref("k"), cp::call("multiply", {cp::field_ref("v"), cp::literal(int64_t(3))}),
+                                           cp::call("add", {cp::call("cast", {cp::field_ref("v")}, cp::CastOptions::Unsafe(arrow::float64())), cp::field_ref("w")})};
+      std::vector<std::string> names = {"k", "v3", "vw"};
+      auto pwant = run("project", std::make_shared<ac::ProjectNodeOptions>(exprs, names));
+      auto pgot = run("b200_project", std::make_shared<ac::ProjectNodeOptions>(exprs, names));
+      ++g_checks;
+      if (!pgot->CombineChunks().ValueOrDie()->Equals(*pwant->CombineChunks().ValueOrDie())) {
+        std::cout << "FAIL b200_project\n want " << pwant->ToString().substr(0, 400) << "\n got " << pgot->ToString().substr(0, 400) << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_project == project (field ref, multiply by a literal, add(cast(v, float64), w))" << std::endl;
+      std::vector<cp::Aggregate> paggs = {{"hash_sum", nullptr, "v3", "s"}, {"hash_count", nullptr, "v3", "c"}, {"hash_max", nullptr, "vw", "m"}};
+      auto pipeline = [&](const std::string& prefix) {
+        ac::Declaration plan = ac::Declaration::Sequence(
+            {{"table_source", ac::TableSourceNodeOptions(table, 1 << 15)},
+             {prefix + "filter", ac::FilterNodeOptions(pred)},
+             {prefix + "project", ac::ProjectNodeOptions(exprs, names)},
+             {prefix + "aggregate", ac::AggregateNodeOptions(paggs, {"k"})}});
+        return sorted(UNWRAP(ac::DeclarationToTable(std::move(plan), /*use_threads=*/false)), "k");
+      };
+      auto want3 = pipeline(""), got3 = pipeline("b200_");
+      ++g_checks;
+      bool same = got3->num_rows() == want3->num_rows();
+      for (const char* name : {"k", "s", "c", "m"}) {
+        auto a = got3->GetColumnByName(name), b = want3->GetColumnByName(name);
+        same = same && a && b && a->Equals(*b);
+      }
+      if (!same) {
+        std::cout << "FAIL b200 filter -> project -> aggregate\n want " << want3->ToString().substr(0, 600) << "\n got " << got3->ToString().substr(0, 600) << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_filter -> b200_project -> b200_aggregate == filter -> project -> aggregate (" << got3->num_rows()
+                << " groups; intermediate batches stayed on the device)" << std::endl;
+    }
   }
   std::cout << "PASS " << g_checks << " checks; " << b2_launch_count() << " kernels launched by libarrow_b200.so" << std::endl;
   return 0;

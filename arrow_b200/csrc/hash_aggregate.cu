@@ -391,7 +391,22 @@ struct B2HashAgg {
   AggState st{};
   int64_t num_groups = 0;
   int64_t cap = 0;
+  B2Grouper* pairs = nullptr;  // hash_count_distinct: the distinct (value, group id) pairs seen so far
 };
+
+namespace {
+struct PoolOut {  // a C-ABI output whose buffers go back to the pool
+  B2Context* ctx;
+  cudaStream_t s;
+  B2Array a{};
+  PoolOut(B2Context* c, cudaStream_t st) : ctx(c), s(st) {}
+  ~PoolOut() {
+    if (a.validity) ctx->free(const_cast<void*>(a.validity), s);
+    if (a.data) ctx->free(const_cast<void*>(a.data), s);
+    if (a.data2) ctx->free(const_cast<void*>(a.data2), s);
+  }
+};
+}  // namespace
 
 static unsigned long long agg_identity(const B2HashAgg* a) {
   // anti-extrema in the ordered encoding (AntiExtrema<T>, hash_aggregate.cc:349-350):
@@ -469,8 +484,28 @@ extern "C" {
 int b2_hashagg_create(B2Context* ctx, int kind, int32_t value_type, const B2HashAggOptions* options,
                       B2HashAgg** out) {
   if (!ctx || !out) return set_error(B2_INVALID, "b2_hashagg_create: null argument");
-  if (kind < B2_HASH_SUM || kind > B2_HASH_ALL)
+  if (kind < B2_HASH_SUM || kind > B2_HASH_COUNT_DISTINCT)
     return set_error(B2_NOT_IMPLEMENTED, "hash aggregate kind %d is not implemented", kind);
+  if (kind == B2_HASH_COUNT_DISTINCT) {
+    // GroupedCountDistinctImpl keeps a Grouper over (value, group id) (hash_aggregate.cc:1400-1478, made by
+    // GroupedDistinctInit :1560-1575); the pair is wider than 64 bits for 8-byte and string values: grouper_wide.cu
+    if (!type_is_numeric(value_type) && !type_is_binary_like(value_type))
+      return set_error(B2_NOT_IMPLEMENTED, "hash_count_distinct over value type id %d", value_type);
+    B2HashAgg* a = new B2HashAgg();
+    a->ctx = ctx;
+    a->kind = kind;
+    a->value_type = value_type;
+    a->acc = ACC_I64;
+    a->opt = options ? *options : B2HashAggOptions{1, 1, 0, 0};
+    const int32_t kt[2] = {value_type, B2_UINT32};
+    const int st = b2_grouper_create(ctx, kt, 2, &a->pairs);
+    if (st != B2_OK) {
+      delete a;
+      return st;
+    }
+    *out = a;
+    return B2_OK;
+  }
   if (kind == B2_HASH_ANY || kind == B2_HASH_ALL) {
     if (value_type != B2_BOOL) return set_error(B2_NOT_IMPLEMENTED, "hash_any / hash_all need a boolean column (type id %d)", value_type);
   } else if (kind != B2_HASH_COUNT_ALL && kind != B2_HASH_COUNT && !type_is_numeric(value_type)) {
@@ -494,13 +529,14 @@ void b2_hashagg_destroy(B2HashAgg* a) {
   if (a->st.reduced) a->ctx->free(a->st.reduced, s);
   if (a->st.counts) a->ctx->free(a->st.counts, s);
   if (a->st.flags) a->ctx->free(a->st.flags, s);
+  if (a->pairs) b2_grouper_destroy(a->pairs);
   delete a;
 }
 
 int32_t b2_hashagg_out_type(const B2HashAgg* a) {
   if (!a) return B2_NA;
   switch (a->kind) {
-    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return B2_INT64;
+    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: case B2_HASH_COUNT_DISTINCT: return B2_INT64;
     case B2_HASH_MEAN: return B2_DOUBLE;
     case B2_HASH_SUM: case B2_HASH_PRODUCT: return a->acc == ACC_I64 ? B2_INT64 : a->acc == ACC_U64 ? B2_UINT64 : B2_DOUBLE;
     case B2_HASH_ANY: case B2_HASH_ALL: return B2_BOOL;
@@ -514,6 +550,10 @@ int b2_hashagg_resize(B2HashAgg* a, int64_t num_groups, void* stream) {
   B2Context* ctx = a->ctx;
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
+  if (a->kind == B2_HASH_COUNT_DISTINCT) {  // the state is the pair grouper; only the group count is kept (:1408-1411)
+    a->num_groups = num_groups;
+    return B2_OK;
+  }
   if (num_groups > a->cap) {
     int64_t cap = static_cast<int64_t>(next_pow2(num_groups < 1024 ? 1024 : num_groups));
     void *r, *c, *f;
@@ -553,6 +593,15 @@ int b2_hashagg_consume(B2HashAgg* a, const B2Array* values, const B2Array* ids, 
   B2_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = ids->length;
   if (n == 0) return B2_OK;
+  if (a->kind == B2_HASH_COUNT_DISTINCT) {
+    if (!values) return set_error(B2_INVALID, "hash aggregate needs a value column");
+    if (values->length != n) return set_error(B2_INVALID, "values and group ids differ in length");
+    if (values->type != a->value_type)
+      return set_error(B2_TYPE_ERROR, "hash aggregate was created for type id %d, got %d", a->value_type, values->type);
+    const B2Array keys[2] = {*values, *ids};
+    PoolOut pair_ids(ctx, s);
+    return b2_grouper_consume(a->pairs, keys, &pair_ids.a, s);
+  }
   const uint32_t* id = static_cast<const uint32_t*>(ids->data) + ids->offset;
   const bool few_groups = a->num_groups <= kPrivateMaxGroups && n >= (1 << 14);
   const int pgrid = grid_for(n, kBlock * 64, kSMs * 8);
@@ -614,6 +663,18 @@ int b2_hashagg_merge(B2HashAgg* a, B2HashAgg* other, const B2Array* group_id_map
   cudaStream_t s = ctx->pick(stream);
   B2_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = other->num_groups;
+  if (a->kind == B2_HASH_COUNT_DISTINCT) {
+    // other's distinct (value, group) pairs with the group ids translated, consumed like a batch (:1418-1439)
+    B2Array pairs[2] = {};
+    B2_RETURN_NOT_OK(b2_grouper_uniques(other->pairs, pairs, s));
+    PoolOut vals(ctx, s), gids(ctx, s), mapped(ctx, s), pair_ids(ctx, s);
+    vals.a = pairs[0];
+    gids.a = pairs[1];
+    if (pairs[0].length == 0) return B2_OK;
+    B2_RETURN_NOT_OK(b2_take(ctx, group_id_mapping, &gids.a, 1, &mapped.a, s));
+    const B2Array keys[2] = {vals.a, mapped.a};
+    return b2_grouper_consume(a->pairs, keys, &pair_ids.a, s);
+  }
   if (n == 0) return B2_OK;
   const uint32_t* map = static_cast<const uint32_t*>(group_id_mapping->data) + group_id_mapping->offset;
   hashagg_merge_kernel<<<grid_for(n, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(a->st, other->st, map, n, a->kind, a->acc);
@@ -628,6 +689,22 @@ int b2_hashagg_finalize(B2HashAgg* a, B2Array* out, void* stream) {
   B2_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = a->num_groups;
   const int out_type = b2_hashagg_out_type(a);
+  if (a->kind == B2_HASH_COUNT_DISTINCT) {
+    // counts[g] = distinct values of group g that CountOptions::mode admits (:1441-1468) = hash_count over the pairs
+    B2Array pairs[2] = {};
+    B2_RETURN_NOT_OK(b2_grouper_uniques(a->pairs, pairs, s));
+    PoolOut vals(ctx, s), gids(ctx, s);
+    vals.a = pairs[0];
+    gids.a = pairs[1];
+    B2HashAgg* counter = nullptr;
+    B2HashAggOptions co{1, 0, a->opt.count_mode, 0};
+    B2_RETURN_NOT_OK(b2_hashagg_create(ctx, B2_HASH_COUNT, a->value_type, &co, &counter));
+    int st = b2_hashagg_resize(counter, n, s);
+    if (st == B2_OK) st = b2_hashagg_consume(counter, &vals.a, &gids.a, s);
+    if (st == B2_OK) st = b2_hashagg_finalize(counter, out, s);
+    b2_hashagg_destroy(counter);
+    return st;
+  }
   Temp data(ctx, s), bits(ctx, s);
   if (out_type == B2_BOOL) {
     B2_RETURN_NOT_OK(data.alloc(bitmap_alloc_bytes(n)));

@@ -79,7 +79,7 @@ __device__ __forceinline__ unsigned warp_pack_bits(unsigned m, unsigned lane) {
 // random accesses (not bytes) are what bounds Take: 42-44 G/s on this part whatever is fetched
 // (profiles/gather_probe_r01.csv); at 1B rows the 125 MB bitmap misses on ~45 % of the probes
 // (profiles/take_traffic.json), a third of the kernel's DRAM accesses.  So for big bitmaps the bitmap is cut
-// into K bands of <= B2_TAKE_BAND_MB each: the gather kernel probes band 0 only (rows whose index falls in another
+// into K bands of <= B2_TAKE_BAND_MB (default 64) each: the gather kernel probes band 0 only (rows whose index falls in another
 // band are provisionally valid), and K-1 follow-up launches re-stream the INDICES (sequential, 1.2 ps/row) and
 // clear the bits of band b -- every launch's probes hit a bitmap slice that fits L2.  Results are identical.
 __device__ __forceinline__ bool probe_band0(const BitmapReader& valid, uint64_t j, int64_t band_rows, uint64_t pol) {
@@ -470,7 +470,7 @@ static TakeBands take_bands(const B2Array* values, int64_t n, int iw) {
   // B2_TAKE_BAND_MB: band size (0 disables); B2_TAKE_BAND_KB: the same in KB and without the size thresholds (tests)
   const char* ekb = getenv("B2_TAKE_BAND_KB");
   const char* emb = getenv("B2_TAKE_BAND_MB");
-  int64_t band = ekb ? (strtol(ekb, nullptr, 10) << 10) : ((emb ? strtol(emb, nullptr, 10) : 48) << 20);
+  int64_t band = ekb ? (strtol(ekb, nullptr, 10) << 10) : ((emb ? strtol(emb, nullptr, 10) : 64) << 20);
   if (band <= 0 || values->null_count == 0 || !values->validity || (iw != 4 && iw != 8)) return b;
   const int64_t bytes = values->length >> 3;
   if (!ekb && (bytes * 4 < band * 5 || n < (1 << 24))) return b;  // a bitmap up to 1.25 bands is left alone

@@ -393,7 +393,9 @@ typedef enum B2HashAggKind {
   B2_HASH_MAX = 5,
   B2_HASH_PRODUCT = 6, /* GroupedProductImpl, hash_aggregate_numeric.cc:311-335 (integers wrap mod 2^64) */
   B2_HASH_ANY = 7,     /* GroupedAnyImpl / GroupedAllImpl over a B2_BOOL column, hash_aggregate.cc:1232-1397 */
-  B2_HASH_ALL = 8
+  B2_HASH_ALL = 8,
+  B2_HASH_COUNT_DISTINCT = 9 /* GroupedCountDistinctImpl, hash_aggregate.cc:1400-1478: distinct (value, group) pairs
+                                through a Grouper, counted per group under CountOptions::mode; numeric and utf8 / binary values */
 } B2HashAggKind;
 typedef struct B2HashAggOptions {
   int32_t skip_nulls;  /* ScalarAggregateOptions (api_aggregate.h:48-50), default 1 */

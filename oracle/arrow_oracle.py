@@ -646,6 +646,15 @@ def hash_aggregate(function: str, vals, ids: pa.Array, num_groups: int, *, skip_
     g = values(ids).astype(np.int64)
     if function == "hash_count_all":
         return make_array(pa.int64(), np.bincount(g, minlength=num_groups).astype(np.int64))
+    if function == "hash_count_distinct":
+        # GroupedCountDistinctImpl (hash_aggregate.cc:1400-1478): a Grouper over (value, group id); Finalize counts the
+        # distinct pairs per group that CountOptions::mode admits (a null is one more distinct value under "all")
+        pairs = Grouper([vals.type, pa.uint32()])
+        pairs.consume([vals, ids])
+        uv, ug = pairs.get_uniques()
+        ok, gg = validity(uv), values(ug).astype(np.int64)
+        sel = ok if mode == "only_valid" else (~ok if mode == "only_null" else np.ones(len(gg), bool))
+        return make_array(pa.int64(), np.bincount(gg[sel], minlength=num_groups).astype(np.int64))
     v, valid = values(vals), validity(vals)
     if function == "hash_count":
         sel = valid if mode == "only_valid" else (~valid if mode == "only_null" else np.ones(len(g), bool))

@@ -86,3 +86,81 @@ def test_gpu_product_any_all_merge(ctx):
         merged = pa.table({"k": g1.get_uniques()[0].to_arrow(), "v": a1.finalize().to_arrow()}).sort_by("k")
         want = pa.table({"k": whole_u[0].to_arrow(), "v": whole.to_arrow()}).sort_by("k")
         assert merged.equals(want), fn
+
+
+# ---- hash_count_distinct (GroupedCountDistinctImpl, kernels/hash_aggregate.cc:1400-1478) ----------------------------
+def _distinct_data(n, offset=0):
+    rng = np.random.default_rng(SEED + 9)
+    m = n + offset
+    keys = pa.array(rng.integers(0, 30, m), mask=rng.random(m) < 0.05).slice(offset)
+    i64 = pa.array(rng.integers(-5, 6, m, dtype=np.int64) * (1 << 40), mask=rng.random(m) < 0.1).slice(offset)
+    u8 = pa.array(rng.integers(0, 7, m, dtype=np.uint8), mask=rng.random(m) < 0.1).slice(offset)
+    f64 = pa.array(rng.integers(0, 9, m).astype(np.float64) / 4, mask=rng.random(m) < 0.1).slice(offset)
+    words = [None if rng.random() < 0.1 else "w" * int(k % 4) + str(int(k)) for k in rng.integers(0, 12, m)]
+    st = pa.array(words, pa.string()).slice(offset)
+    return keys, [i64, u8, f64, st]
+
+
+@pytest.mark.parametrize("mode", ["only_valid", "only_null", "all"])
+def test_oracle_count_distinct_vs_reference_binary(mode):
+    keys, cols = _distinct_data(4000, 3)
+    o = pc.CountOptions(mode=mode)
+    names = [f"c{j}" for j in range(len(cols))]
+    t = pa.table([keys] + cols, names=["k"] + names).group_by("k", use_threads=False).aggregate(
+        [(nm, "count_distinct", o) for nm in names]).sort_by("k")
+    uniq, outs = ora.group_by([keys], [("hash_count_distinct", c, dict(mode=mode)) for c in cols])
+    mine = pa.table([uniq[0]] + outs, names=["k"] + [nm + "_count_distinct" for nm in names]).sort_by("k")
+    for c in mine.column_names:
+        assert mine[c].combine_chunks().equals(t[c].combine_chunks()), (c, mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["only_valid", "only_null", "all"])
+@pytest.mark.parametrize("offset", [0, 5])
+def test_gpu_count_distinct_vs_oracle(ctx, mode, offset):
+    import arrow_b200.compute as bc
+    from arrow_b200 import DeviceArray
+    keys, cols = _distinct_data(50000, offset)
+    dk = DeviceArray.from_arrow(keys, ctx)
+    uniq, outs = bc.group_by([dk], [("hash_count_distinct", DeviceArray.from_arrow(c, ctx), dict(mode=mode)) for c in cols])
+    ouniq, oouts = ora.group_by([keys], [("hash_count_distinct", c, dict(mode=mode)) for c in cols])
+    assert uniq[0].to_arrow().equals(ouniq[0])
+    for c, got, want in zip(cols, outs, oouts):
+        assert got.to_arrow().equals(want), (c.type, mode)
+        assert got.null_count == 0
+
+
+@pytest.mark.gpu
+def test_gpu_count_distinct_merge(ctx):
+    """two partial states over different group numberings merged through a group_id_mapping = one state over the
+    concatenated input (HashAggregateKernel::merge, kernel.h:757; GroupedCountDistinctImpl::Merge :1418-1439)"""
+    import arrow_b200.compute as bc
+    from arrow_b200 import DeviceArray
+    keys, cols = _distinct_data(30000)
+    half = len(keys) // 2
+    for col in cols:
+        g_all = bc.Grouper([keys.type], ctx)
+        whole = bc.HashAggregator("hash_count_distinct", col.type, mode="all", ctx=ctx)
+        ids = g_all.consume(DeviceArray.from_arrow(keys, ctx))
+        whole.resize(g_all.num_groups)
+        whole.consume(DeviceArray.from_arrow(col, ctx), ids)
+        want = whole.finalize().to_arrow()
+        # partial A over the first half (its own grouper), partial B over the second half
+        ga, gb = bc.Grouper([keys.type], ctx), bc.Grouper([keys.type], ctx)
+        a = bc.HashAggregator("hash_count_distinct", col.type, mode="all", ctx=ctx)
+        b = bc.HashAggregator("hash_count_distinct", col.type, mode="all", ctx=ctx)
+        ia = ga.consume(DeviceArray.from_arrow(keys.slice(0, half), ctx))
+        a.resize(ga.num_groups)
+        a.consume(DeviceArray.from_arrow(col.slice(0, half), ctx), ia)
+        ib = gb.consume(DeviceArray.from_arrow(keys.slice(half), ctx))
+        b.resize(gb.num_groups)
+        b.consume(DeviceArray.from_arrow(col.slice(half), ctx), ib)
+        mapping = ga.consume(gb.get_uniques()[0])        # B's groups in A's numbering (new ones appended)
+        a.resize(ga.num_groups)
+        a.merge(b, mapping)
+        got = a.finalize().to_arrow()
+        # A's numbering is a permutation of the whole-input numbering: compare through the keys
+        ka, kw = ga.get_uniques()[0].to_arrow(), g_all.get_uniques()[0].to_arrow()
+        ta = pa.table({"k": ka, "c": got}).sort_by("k")
+        tw = pa.table({"k": kw, "c": want}).sort_by("k")
+        assert ta.equals(tw), col.type
