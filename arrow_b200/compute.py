@@ -461,6 +461,24 @@ def sort_indices(arr, sort_keys=None, null_placement="at_end", order=None) -> De
     return array_sort_indices(arr, o, null_placement)
 
 
+def select_k_unstable(arr: DeviceArray, k: int, sort_keys=None, null_placement="at_end") -> DeviceArray:
+    """select_k_unstable (kernels/vector_select_k.cc:157-232, SelectKOptions api_vector.h:178-214) on one array: the
+    indices of the first k rows in sort order; sort_keys = [(ignored name, order)] as in the reference.  Ties come out in
+    row order (= sort_indices(...)[:k]), one of the answers the reference's unstable selection may give."""
+    if k < 0:
+        raise pa.ArrowInvalid(f"select_k_unstable requires a nonnegative `k`, got {k}")
+    o = "ascending"
+    if sort_keys:
+        if len(sort_keys) != 1:
+            raise pa.ArrowNotImplementedError("arrow_b200 select_k_unstable: one sort key (use sort_indices for several)")
+        o = sort_keys[0][1] if isinstance(sort_keys[0], (tuple, list)) else "ascending"
+    _require_numeric(arr.type)
+    ctx = arr.ctx
+    ca, cout = arr._c(), cabi.B2Array()
+    check(ctx.lib.b2_select_k(ctx.handle, C.byref(ca), int(k), _order(o), _placement(null_placement), C.byref(cout), ctx.stream))
+    return _out(ctx, cout, pa.uint64())
+
+
 # ------------------------------------------------------------------------------------
 # ungrouped aggregates (kernels/aggregate_basic.cc, aggregate_basic.inc.cc)
 # ------------------------------------------------------------------------------------
@@ -759,7 +777,7 @@ class GroupBySumCount:
 # ------------------------------------------------------------------------------------
 _REGISTRY = {
     "cast": cast, "filter": filter, "array_filter": array_filter, "take": take, "array_take": array_take,
-    "sort_indices": sort_indices, "array_sort_indices": array_sort_indices,
+    "sort_indices": sort_indices, "array_sort_indices": array_sort_indices, "select_k_unstable": select_k_unstable,
     "if_else": if_else,
     "add": add, "subtract": subtract, "multiply": multiply, "divide": divide,
     "add_checked": add_checked, "subtract_checked": subtract_checked,
@@ -793,6 +811,8 @@ def call_function(name: str, args: Sequence, options=None):
         return fn(*args, boundscheck=getattr(options, "boundscheck", True))
     if name == "array_sort_indices":
         return fn(*args, order=options.order, null_placement=options.null_placement)
+    if name == "select_k_unstable":
+        return fn(*args, k=options.k, sort_keys=[(str(n), o) for n, o in options.sort_keys])
     if name == "dictionary_encode":
         return fn(*args, null_encoding=getattr(options, "null_encoding", options))
     if name in ("sum", "mean", "min_max", "min", "max"):

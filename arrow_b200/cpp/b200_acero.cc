@@ -474,8 +474,29 @@ class MapNode : public DeviceNode {
   }
 
  protected:
-  // device batch in, device batch out; an empty optional result drops the batch
+  // device batch in, device batch out
   virtual Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) = 0;
+
+  // Expression evaluation on a device batch.  ExecuteScalarExpression needs a BOUND expression, and Bind resolves every
+  // "cast" call -- explicit or implicit -- to the stock CPU cast kernels (GetCastFunction, compute/expression.cc:560-575),
+  // which would dereference device pointers.  So the tree is walked here and every call goes through CallFunction on the
+  // nested registry: cast is the device meta function, implicit casts are inserted by Function::Execute through the same
+  // registry, all-scalar sub-expressions fall through to the parent (host) kernels.
+  Result<Datum> Eval(const cp::Expression& e, const cp::ExecBatch& dev) {
+    if (const Datum* lit = e.literal()) return *lit;
+    if (const arrow::FieldRef* ref = e.field_ref()) {
+      ARROW_ASSIGN_OR_RAISE(int i, FieldIndex(*ref, *inputs_[0]->output_schema()));
+      return dev.values[i];
+    }
+    const cp::Expression::Call* call = e.call();
+    if (!call) return Status::Invalid("b200 node: unsupported expression ", e.ToString());
+    std::vector<Datum> args;
+    for (const auto& a : call->arguments) {
+      ARROW_ASSIGN_OR_RAISE(Datum v, Eval(a, dev));
+      args.push_back(std::move(v));
+    }
+    return cp::CallFunction(call->function_name, args, call->options.get(), &ctx_);
+  }
 
  private:
   Status Flush() {
@@ -525,12 +546,13 @@ class FilterNode : public MapNode {
     ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
     auto schema = inputs[0]->output_schema();
     auto node = std::make_unique<FilterNode>(plan, inputs, schema, rt);
-    // binding against the nested registry resolves e.g. greater(add(a, b), 3) to the GPU kernels
-    ARROW_ASSIGN_OR_RAISE(node->filter_, opts.filter_expression.IsBound() ? Result<cp::Expression>(opts.filter_expression)
-                                                                         : opts.filter_expression.Bind(*schema, &node->ctx_));
-    if (node->filter_.type()->id() != arrow::Type::BOOL)
-      return Status::TypeError("Filter expression must evaluate to bool, but ", node->filter_.ToString(), " evaluates to ",
-                               node->filter_.type()->ToString());
+    // bound (against the stock registry) only to type-check it, filter_node.cc:52-63; evaluation is MapNode::Eval
+    ARROW_ASSIGN_OR_RAISE(auto bound, opts.filter_expression.IsBound() ? Result<cp::Expression>(opts.filter_expression)
+                                                                      : opts.filter_expression.Bind(*schema));
+    if (bound.type()->id() != arrow::Type::BOOL)
+      return Status::TypeError("Filter expression must evaluate to bool, but ", bound.ToString(), " evaluates to ",
+                               bound.type()->ToString());
+    node->filter_ = opts.filter_expression;
     return plan->AddNode(std::move(node));
   }
   FilterNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
@@ -539,7 +561,7 @@ class FilterNode : public MapNode {
 
  protected:
   Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) override {
-    ARROW_ASSIGN_OR_RAISE(Datum mask, cp::ExecuteScalarExpression(filter_, dev, &ctx_));
+    ARROW_ASSIGN_OR_RAISE(Datum mask, Eval(filter_, dev));
     if (mask.is_scalar()) {  // filter_node.cc:85-98: true keeps the batch, false / null drops every row
       const auto& b = mask.scalar_as<arrow::BooleanScalar>();
       if (b.is_valid && b.value) return dev;
@@ -571,16 +593,15 @@ class ProjectNode : public MapNode {
     if (inputs.size() != 1) return Status::Invalid("b200_project needs exactly one input");
     ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
     auto in_schema = inputs[0]->output_schema();
-    cp::ExecContext bind_ctx(plan->query_context()->memory_pool(), nullptr, rt->registry());
     std::vector<cp::Expression> exprs = opts.expressions;
     std::vector<std::string> names = opts.names;
     if (names.empty())  // project_node.cc:56-61
       for (const auto& e : exprs) names.push_back(e.ToString());
     if (names.size() != exprs.size()) return Status::Invalid("b200_project: ", exprs.size(), " expressions but ", names.size(), " names");
     arrow::FieldVector fields;
-    for (size_t i = 0; i < exprs.size(); ++i) {
-      if (!exprs[i].IsBound()) { ARROW_ASSIGN_OR_RAISE(exprs[i], exprs[i].Bind(*in_schema, &bind_ctx)); }
-      fields.push_back(arrow::field(names[i], exprs[i].type()->GetSharedPtr()));
+    for (size_t i = 0; i < exprs.size(); ++i) {  // bound (stock registry) for the output type only; evaluation is MapNode::Eval
+      ARROW_ASSIGN_OR_RAISE(auto bound, exprs[i].IsBound() ? Result<cp::Expression>(exprs[i]) : exprs[i].Bind(*in_schema));
+      fields.push_back(arrow::field(names[i], bound.type()->GetSharedPtr()));
     }
     auto node = std::make_unique<ProjectNode>(plan, inputs, arrow::schema(std::move(fields)), rt);
     node->exprs_ = std::move(exprs);
@@ -594,7 +615,7 @@ class ProjectNode : public MapNode {
   Result<cp::ExecBatch> Transform(const cp::ExecBatch& dev) override {
     cp::ExecBatch out({}, dev.length);
     for (const auto& e : exprs_) {
-      ARROW_ASSIGN_OR_RAISE(Datum v, cp::ExecuteScalarExpression(e, dev, &ctx_));
+      ARROW_ASSIGN_OR_RAISE(Datum v, Eval(e, dev));
       if (v.is_scalar()) {  // a literal column: materialise it on the device like every other column
         ARROW_ASSIGN_OR_RAISE(v, ColumnToDevice(rt_, v, dev.length));
       }

@@ -526,6 +526,35 @@ class SortIndicesFunction : public cp::MetaFunction {
 };
 const cp::SortOptions SortIndicesFunction::kDefaults = cp::SortOptions::Defaults();
 
+// select_k_unstable on a device array (SelectKUnstableMetaFunction, kernels/vector_select_k.cc:615-690): b2_select_k --
+// a sampled threshold, one compare pass, a sort of the few candidates; anything else goes to the stock function
+class SelectKFunction : public cp::MetaFunction {
+ public:
+  explicit SelectKFunction(Runtime* rt)
+      : cp::MetaFunction("select_k_unstable", cp::Arity::Unary(), DocFor({"input"}, "SelectKOptions"), &kDefaults), rt_(rt) {}
+  Result<Datum> ExecuteImpl(const std::vector<Datum>& args, const cp::FunctionOptions* options, cp::ExecContext* ctx) const override {
+    if (!args[0].is_array() || !AnyOnDevice(args)) {
+      ARROW_ASSIGN_OR_RAISE(auto parent, cp::GetFunctionRegistry()->GetFunction("select_k_unstable"));
+      return parent->Execute(args, options, ctx);
+    }
+    const auto& so = options ? *static_cast<const cp::SelectKOptions*>(options) : kDefaults;
+    if (so.k < 0) return Status::Invalid("select_k_unstable requires a nonnegative `k`, got ", so.k);
+    if (so.sort_keys.size() != 1) return Status::Invalid("select_k_unstable on an array takes exactly one sort key");
+    const auto& type = *args[0].type();
+    if (!arrow::is_integer(type.id()) && !arrow::is_floating(type.id()))
+      return Status::NotImplemented("arrow_b200 select_k_unstable: values of type ", type.ToString());
+    B2Array v, o;
+    ARROW_RETURN_NOT_OK(DataToB2(*args[0].array(), &v));
+    B200_RETURN_NOT_OK(b2_select_k(rt_->context(), &v, so.k, so.sort_keys[0].order == cp::SortOrder::Descending ? 1 : 0, /*AtEnd=*/1, &o, nullptr));
+    return Datum(AdoptOutput(rt_, o, arrow::uint64()));
+  }
+
+ private:
+  static const cp::SelectKOptions kDefaults;
+  Runtime* rt_;
+};
+const cp::SelectKOptions SelectKFunction::kDefaults = cp::SelectKOptions::Defaults();
+
 // ------------------------------------------------------------------------------------------
 // selection + sort vector kernels
 // ------------------------------------------------------------------------------------------
@@ -1052,6 +1081,7 @@ Status RegisterFunctions(cp::FunctionRegistry* reg, Runtime* rt) {
   ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<CastFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddSelectionFunctions(reg, rt));
   ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<SortIndicesFunction>(rt), true));
+  ARROW_RETURN_NOT_OK(reg->AddFunction(std::make_shared<SelectKFunction>(rt), true));
   ARROW_RETURN_NOT_OK(AddHashFunctions(reg, rt));
   ARROW_RETURN_NOT_OK(AddScalarAggregates(reg, rt));
   const std::pair<const char*, int> aggs[] = {{"hash_sum", B2_HASH_SUM}, {"hash_count", B2_HASH_COUNT},

@@ -368,6 +368,30 @@ int main(int argc, char** argv) {
     }
   }
 
+  // ---- select_k_unstable (kernels/vector_select_k_test.cc): k below the number of non-null values, where every
+  //      version of the reference agrees; ties compared through the selected VALUES (the selection is unstable) ----
+  {
+    auto big = RandomNumeric<arrow::Int64Type>(3000000, 0.1, 55, -1000000000, 1000000000);
+    auto bigf = UNWRAP(cp::Cast(*RandomNumeric<arrow::Int32Type>(2500000, 0.05, 56, -50000, 50000), arrow::float64()));
+    for (const std::shared_ptr<arrow::Array>& a : {big, bigf, big->Slice(5, 100000)}) {
+      for (auto order : {cp::SortOrder::Ascending, cp::SortOrder::Descending}) {
+        for (int64_t kk : {int64_t(0), int64_t(1), int64_t(1000), int64_t(70000)}) {
+          cp::SelectKOptions so(kk, {cp::SortKey("not-used", order)});
+          auto want = UNWRAP(cp::CallFunction("select_k_unstable", {Datum(a)}, &so, &h.cpu_ctx));
+          auto got = h.Host(UNWRAP(cp::CallFunction("select_k_unstable", {h.Dev(Datum(a))}, &so, &h.gpu_ctx)));
+          auto wv = UNWRAP(cp::Take(a, want, cp::TakeOptions::Defaults(), &h.cpu_ctx));
+          auto gv = UNWRAP(cp::Take(a, got, cp::TakeOptions::Defaults(), &h.cpu_ctx));
+          ++g_checks;
+          if (got->length() != kk || !gv.make_array()->Equals(*wv.make_array())) {
+            std::cout << "FAIL select_k_unstable k=" << kk << " " << a->type()->ToString() << std::endl;
+            return 1;
+          }
+        }
+      }
+      std::cout << "OK   select_k_unstable(" << a->type()->ToString() << ", " << a->length() << " rows) k = 0 / 1 / 1000 / 70000, both orders" << std::endl;
+    }
+  }
+
   // ---- unique / value_counts / dictionary_encode (kernels/vector_hash_test.cc:159-250) ----
   {
     auto k64 = RandomNumeric<arrow::Int64Type>(60000, 0.05, 91, -300, 300);

@@ -162,6 +162,32 @@ __global__ void __launch_bounds__(kBlock) take_validity_band_kernel(TakeBandArgs
   if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(a.valid_count), static_cast<unsigned long long>(-s));
 }
 
+// The probes leave the bitmap's lines in L2 with evict_last priority.  A 125 MB bitmap probed in two bands marks the WHOLE
+// L2 that way, and the next streaming kernel of the caller then runs with next to no usable cache (measured: the add of the
+// bench pipeline took 10.6 ms instead of 2.5 ms right after such a take).  So the take hands the lines back:
+// applypriority resets them to evict_normal, one instruction per 128-byte line (1M lines for 1B rows).
+__global__ void __launch_bounds__(kBlock) l2_demote_kernel(const char* base, int64_t lines) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < lines; i += (int64_t)gridDim.x * kBlock)
+    asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + i * 128) : "memory");
+}
+
+// Are the indices clustered?  2048 evenly spaced pairs (idx[p], idx[p+1]): the share whose targets lie within 64Ki rows
+// (8 KB of bitmap) of each other.  Clustered / monotonic indices probe the bitmap almost sequentially -- banding would only
+// add passes over the indices (measured: monotonic take 4.5 -> 6.1 ms).
+template <typename UIdx>
+__global__ void __launch_bounds__(kBlock) idx_locality_kernel(const UIdx* __restrict__ idx, int64_t n, int64_t* near) {
+  constexpr int kPairs = 2048;
+  int local = 0;
+  for (int s = threadIdx.x; s < kPairs; s += kBlock) {
+    const int64_t p = (n - 1) / kPairs * s;
+    const uint64_t a = static_cast<uint64_t>(idx[p]), b = static_cast<uint64_t>(idx[p + 1]);
+    const uint64_t d = a > b ? a - b : b - a;
+    local += d < 65536 ? 1 : 0;
+  }
+  const int64_t t = block_sum<kBlock>(local);
+  if (threadIdx.x == 0) *near = t;
+}
+
 template <int W, typename Idx, bool HAS_VALID>
 __global__ void __launch_bounds__(kBlock) take_kernel(TakeArgs a) {
   using T = typename TakeBytes<W>::type;
@@ -481,6 +507,34 @@ static TakeBands take_bands(const B2Array* values, int64_t n, int iw) {
   return b;
 }
 
+// drop the banding for clustered indices (one tiny kernel + read-back; only reached for >= 16M-row takes of big bitmaps)
+static int take_bands_check_locality(B2Context* ctx, TakeBands* bands, const void* indices, int iw, int64_t n, cudaStream_t s) {
+  if (bands->k < 2 || getenv("B2_TAKE_BAND_KB")) return B2_OK;
+  ScalarSlot slot(ctx);
+  B2_RETURN_NOT_OK(slot.zero(s));
+  if (iw == 4) idx_locality_kernel<uint32_t><<<1, kBlock, 0, s>>>(static_cast<const uint32_t*>(indices), n, slot.dev());
+  else idx_locality_kernel<uint64_t><<<1, kBlock, 0, s>>>(static_cast<const uint64_t*>(indices), n, slot.dev());
+  B2_LAUNCHED();
+  B2_RETURN_NOT_OK(slot.fetch(s));
+  if (slot.host()[0] > 1024) *bands = TakeBands{};
+  return B2_OK;
+}
+
+// hand the bitmap's L2 lines back (see l2_demote_kernel); worth a launch only when the bitmap is a real share of L2
+static int take_demote_bitmap(const B2Array* values, cudaStream_t s) {
+  if (values->null_count == 0 || !values->validity) return B2_OK;
+  const int64_t bytes = values->length >> 3;
+  if (bytes < (8 << 20)) return B2_OK;
+  const char* e = getenv("B2_TAKE_DEMOTE");
+  if (e && e[0] == '0') return B2_OK;
+  const uintptr_t p0 = (reinterpret_cast<uintptr_t>(values->validity) + (values->offset >> 3)) & ~uintptr_t(127);
+  const uintptr_t p1 = reinterpret_cast<uintptr_t>(values->validity) + ((values->offset + values->length + 7) >> 3);
+  const int64_t lines = static_cast<int64_t>((p1 - p0 + 127) / 128);
+  l2_demote_kernel<<<grid_for(lines, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(reinterpret_cast<const char*>(p0), lines);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
 static int launch_take_bands(const TakeBands& bands, const void* indices, int iw, const BitmapReader& values_valid, int64_t n,
                              uint32_t* out_validity, int64_t* valid_count, cudaStream_t s) {
   for (int b = 1; b < bands.k; ++b) {
@@ -604,13 +658,15 @@ extern "C" int b2_take_cast_arith(B2Context* ctx, const B2Array* values, const B
   a.valid_count = slot.dev();
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 1);
   a.vec_ok = aligned_to(a.indices, 16) && aligned_to(a.out, 16) && (!a.other || aligned_to(a.other, 16));
-  const TakeBands bands = take_bands(values, n, iw);
+  TakeBands bands = take_bands(values, n, iw);
+  B2_RETURN_NOT_OK(take_bands_check_locality(ctx, &bands, a.indices, iw, n, s));
   a.band_rows = bands.rows;
   if (scalar_null) return set_error(B2_NOT_IMPLEMENTED, "b2_take_cast_arith: null scalar operand (the result is all null; use the unfused kernels)");
   int st = to_type == B2_FLOAT ? launch_fused_take_val<float>(values->type, indices->type, a, has_valid, s)
                                : launch_fused_take_val<double>(values->type, indices->type, a, has_valid, s);
   if (st != B2_OK) return st;
   B2_RETURN_NOT_OK(launch_take_bands(bands, a.indices, iw, a.values_valid, n, a.out_validity, a.valid_count, s));
+  if (has_valid) B2_RETURN_NOT_OK(take_demote_bitmap(values, s));
   B2_RETURN_NOT_OK(slot.fetch(s));
   const uint64_t bad = static_cast<uint64_t>(slot.host()[1]);
   if (bad != ~0ull) return index_error(indices, bad, s);
@@ -665,7 +721,8 @@ extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* ind
   a.valid_count = slot.dev();
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 1);
   a.vec_ok = aligned_to(a.indices, 16) && aligned_to(a.out, 16);
-  const TakeBands bands = take_bands(values, n, iw);
+  TakeBands bands = take_bands(values, n, iw);
+  B2_RETURN_NOT_OK(take_bands_check_locality(ctx, &bands, a.indices, iw, n, s));
   a.band_rows = bands.rows;
   int st;
   switch (width) {
@@ -677,6 +734,7 @@ extern "C" int b2_take(B2Context* ctx, const B2Array* values, const B2Array* ind
   }
   if (st != B2_OK) return st;
   B2_RETURN_NOT_OK(launch_take_bands(bands, a.indices, iw, a.values_valid, n, a.out_validity, a.valid_count, s));
+  if (has_valid) B2_RETURN_NOT_OK(take_demote_bitmap(values, s));
   B2_RETURN_NOT_OK(slot.fetch(s));
   uint64_t bad = static_cast<uint64_t>(slot.host()[1]);
   if (bad != ~0ull) {

@@ -314,6 +314,12 @@ B2_API int b2_sort_payload(B2Context* ctx, const B2Array* values, const B2Array*
 B2_API int b2_sort_indices_multi(B2Context* ctx, const B2Array* keys, int n_keys, const int32_t* orders,
                                  int null_placement, B2Array* out, void* stream);
 
+/* select_k_unstable over one numeric column (ArraySelector, kernels/vector_select_k.cc:157-232): out = the B2_UINT64
+ * indices of the first min(k, length) rows in sort order = b2_sort_indices(...)[0:k] (ties in row order).  For k << n the
+ * column is read once: a sampled threshold, one compare pass, a sort of the few candidates (csrc/select_k.cu). */
+B2_API int b2_select_k(B2Context* ctx, const B2Array* values, int64_t k, int order, int null_placement,
+                       B2Array* out, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Grouper.  Replaces Grouper::{Make,Consume,Lookup,GetUniques,num_groups,Reset}
  * (compute/row/grouper.h:104-196; GrouperFastImpl row/grouper.cc:555-963, GrouperImpl :300-553)

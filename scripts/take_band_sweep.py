@@ -54,8 +54,38 @@ def timed(fn, reps=3):
     return round(best, 3), nulls
 
 
+def pipeline_tail(reps=3):
+    """cast + add right after a take: what the take leaves behind in L2 (evict_last lines) is their problem"""
+    best = None
+    for r in range(reps + 1):
+        t = bc.take(values, idx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        c = bc.cast(t, pa.float32(), safe=False)
+        o = bc.add(c, other)
+        e1.record()
+        e1.synchronize()
+        del t, c, o
+        if r:
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+    return round(best, 3)
+
+
+inc = torch.randint(0, 3, (n,), dtype=torch.int64, device="cuda", generator=gen)
+mono_t = torch.clamp(torch.cumsum(inc, 0), max=n - 1)
+del inc
+mono = DeviceArray.from_pointers(ctx, pa.int64(), n, mono_t.data_ptr())
+
 for b in args.bands.split(","):
+    demote = "1"
+    if b.endswith("nd"):   # e.g. "64nd": 64 MB bands without the L2 demotion pass
+        b, demote = b[:-2], "0"
+    os.environ["B2_TAKE_DEMOTE"] = demote
     os.environ["B2_TAKE_BAND_MB"] = b
+    t_mono, _ = timed(lambda: bc.take(values, mono))
+    t_tail = pipeline_tail()
+    print(json.dumps({"band_mb": b, "demote": demote, "take_monotonic_ms": t_mono, "cast_add_after_take_ms": t_tail}), flush=True)
     t_take, n_take = timed(lambda: bc.take(values, idx))
     t_take32, n_take32 = timed(lambda: bc.take(values, idx32))
     t_fused, n_fused = timed(lambda: bc.take_cast_arith(values, idx, pa.float32(), "add", other))
