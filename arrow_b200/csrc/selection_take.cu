@@ -162,14 +162,11 @@ __global__ void __launch_bounds__(kBlock) take_validity_band_kernel(TakeBandArgs
   if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(a.valid_count), static_cast<unsigned long long>(-s));
 }
 
-// The probes leave the bitmap's lines in L2 with evict_last priority.  A 125 MB bitmap probed in two bands marks the WHOLE
-// L2 that way, and the next streaming kernel of the caller then runs with next to no usable cache (measured: the add of the
-// bench pipeline took 10.6 ms instead of 2.5 ms right after such a take).  So the take hands the lines back:
-// applypriority resets them to evict_normal, one instruction per 128-byte line (1M lines for 1B rows).
-__global__ void __launch_bounds__(kBlock) l2_demote_kernel(const char* base, int64_t lines) {
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < lines; i += (int64_t)gridDim.x * kBlock)
-    asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + i * 128) : "memory");
-}
+// The probes leave the bitmap's lines in L2 with evict_last priority; probed in two bands, a 125 MB bitmap marks the whole
+// L2 that way.  The take therefore hands the lines back when it is done (launch_l2_demote, bitmap.cu: applypriority
+// evict_normal, one instruction per 128-byte line, ~20 us for 1B rows).  Measured (profiles/take_band_sweep_r02.jsonl):
+// the cast + add that follow the take run at the same speed with and without it, so this is insurance for callers whose
+// next kernel wants the cache, not a measured win.
 
 // Are the indices clustered?  2048 evenly spaced pairs (idx[p], idx[p+1]): the share whose targets lie within 64Ki rows
 // (8 KB of bitmap) of each other.  Clustered / monotonic indices probe the bitmap almost sequentially -- banding would only
@@ -527,12 +524,8 @@ static int take_demote_bitmap(const B2Array* values, cudaStream_t s) {
   if (bytes < (8 << 20)) return B2_OK;
   const char* e = getenv("B2_TAKE_DEMOTE");
   if (e && e[0] == '0') return B2_OK;
-  const uintptr_t p0 = (reinterpret_cast<uintptr_t>(values->validity) + (values->offset >> 3)) & ~uintptr_t(127);
-  const uintptr_t p1 = reinterpret_cast<uintptr_t>(values->validity) + ((values->offset + values->length + 7) >> 3);
-  const int64_t lines = static_cast<int64_t>((p1 - p0 + 127) / 128);
-  l2_demote_kernel<<<grid_for(lines, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(reinterpret_cast<const char*>(p0), lines);
-  B2_LAUNCHED();
-  return B2_OK;
+  const char* p0 = static_cast<const char*>(values->validity) + (values->offset >> 3);
+  return launch_l2_demote(p0, (values->length + 7) >> 3, s);
 }
 
 static int launch_take_bands(const TakeBands& bands, const void* indices, int iw, const BitmapReader& values_valid, int64_t n,
