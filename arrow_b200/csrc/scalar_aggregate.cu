@@ -112,7 +112,7 @@ __device__ __forceinline__ Partial<T> block_reduce(Partial<T> p) {
   return p;
 }
 
-// Per-thread accumulator of the streaming loop.  ncu on the first version of this kernel (profiles/reduce_prof_r02_summary.txt):
+// Per-thread accumulator of the streaming loop.  ncu on the first version of this kernel (profiles/reduce_prof_r02a_summary.txt, after: reduce_prof_r02b_summary.txt):
 // 62 instructions per element, 44 % issue-active, 59 % of the stalls waiting for loads -- the exact 128-bit sum (carry and
 // sign tests per element), per-load bounds tests and 64-bit index arithmetic were the cost, not the bytes.  Now:
 //   * 64-bit integers accumulate their low and high 32-bit halves in two 64-bit counters (no carry logic; a thread sees
