@@ -198,6 +198,45 @@ Result<std::shared_ptr<arrow::Array>> ImportDeviceArray(struct ArrowDeviceArray*
   return imported;
 }
 
+namespace {
+// orders the context stream behind the sync events of every buffer of every batch it hands out
+class OrderedDeviceReader : public arrow::RecordBatchReader {
+ public:
+  OrderedDeviceReader(std::shared_ptr<arrow::RecordBatchReader> inner, std::shared_ptr<arrow::MemoryManager> mm)
+      : inner_(std::move(inner)), mm_(std::move(mm)) {}
+  std::shared_ptr<arrow::Schema> schema() const override { return inner_->schema(); }
+  arrow::DeviceAllocationType device_type() const override { return arrow::DeviceAllocationType::kCUDA; }
+  Status ReadNext(std::shared_ptr<arrow::RecordBatch>* out) override {
+    ARROW_RETURN_NOT_OK(inner_->ReadNext(out));
+    if (!*out) return Status::OK();
+    ARROW_ASSIGN_OR_RAISE(auto stream, mm_->device()->MakeStream());
+    for (const auto& col : (*out)->column_data()) {
+      for (const auto& buf : col->buffers) {
+        if (!buf) continue;
+        if (auto ev = buf->device_sync_event()) ARROW_RETURN_NOT_OK(stream->WaitEvent(*ev));
+      }
+      // a device array must carry an explicit null_count (GetNullCount would read the bitmap on the host)
+      if (col->null_count.load() == arrow::kUnknownNullCount && col->buffers[0] == nullptr) col->null_count = 0;
+    }
+    return Status::OK();
+  }
+  Status Close() override { return inner_->Close(); }
+
+ private:
+  std::shared_ptr<arrow::RecordBatchReader> inner_;
+  std::shared_ptr<arrow::MemoryManager> mm_;
+};
+}  // namespace
+
+Result<std::shared_ptr<arrow::RecordBatchReader>> ImportDeviceRecordBatchReader(struct ArrowDeviceArrayStream* stream,
+                                                                                const std::shared_ptr<arrow::MemoryManager>& mm) {
+  if (stream->device_type != ARROW_DEVICE_CUDA && stream->device_type != ARROW_DEVICE_CUDA_MANAGED)
+    return Status::Invalid("arrow_b200::ImportDeviceRecordBatchReader: device_type ", stream->device_type, " is not CUDA memory");
+  auto mapper = [mm](ArrowDeviceType, int64_t) -> Result<std::shared_ptr<arrow::MemoryManager>> { return mm; };
+  ARROW_ASSIGN_OR_RAISE(auto inner, arrow::ImportDeviceRecordBatchReader(stream, mapper));
+  return std::shared_ptr<arrow::RecordBatchReader>(new OrderedDeviceReader(std::move(inner), mm));
+}
+
 Result<std::shared_ptr<B200Device>> B200Device::Make(int device_number) {
   B2Context* ctx = nullptr;
   B200_RETURN_NOT_OK(b2_context_create(device_number, &ctx));

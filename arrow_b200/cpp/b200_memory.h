@@ -92,4 +92,11 @@ arrow::Status ExportDeviceArray(const arrow::Array& array, const std::shared_ptr
 arrow::Result<std::shared_ptr<arrow::Array>> ImportDeviceArray(struct ArrowDeviceArray* array, std::shared_ptr<arrow::DataType> type,
                                                                const std::shared_ptr<arrow::MemoryManager>& mm);
 
+// ---- C Device STREAM interface (c/abi.h ArrowDeviceArrayStream, c/bridge.h:334,386): ingest of a producer's stream of
+// device record batches.  Every batch is wrapped zero-copy in buffers of OUR memory manager (the DeviceMemoryMapper hands
+// it out for ARROW_DEVICE_CUDA) and the context stream is ordered behind the producer's per-buffer sync events before
+// the batch is returned, so the batches can go straight into the kernels / a `record_batch_reader_source` of a b200_ plan.
+arrow::Result<std::shared_ptr<arrow::RecordBatchReader>> ImportDeviceRecordBatchReader(struct ArrowDeviceArrayStream* stream,
+                                                                                     const std::shared_ptr<arrow::MemoryManager>& mm);
+
 }  // namespace arrow_b200

@@ -231,6 +231,30 @@ def make_mask(torch, n, gen, sel):
     return bits
 
 
+def make_word_column(torch, gen, m, vocab):
+    """m strings drawn from `vocab` distinct words of 8..16 bytes (large_utf8 layout: int64 offsets + bytes); word k = the 5
+    base-26 digits of k followed by a k-dependent tail, so a key string decodes back to k.  Returns (k per row, offsets, bytes, total)"""
+    I64 = torch.int64
+    kid = torch.randint(0, vocab, (m,), dtype=I64, device="cuda", generator=gen)
+    lens = 8 + (kid * 7) % 9
+    offs = torch.zeros(m + 1, dtype=I64, device="cuda")
+    torch.cumsum(lens, 0, out=offs[1:])
+    total = int(offs[-1].item())
+    data = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    cs = 1 << 24
+    for lo in range(0, m, cs):
+        hi = min(m, lo + cs)
+        ln = lens[lo:hi]
+        b0, b1 = int(offs[lo].item()), int(offs[hi].item())
+        kk = torch.repeat_interleave(kid[lo:hi], ln)
+        j = torch.arange(b0, b1, device="cuda", dtype=I64) - torch.repeat_interleave(offs[lo:hi], ln)
+        head = (kk // torch.pow(26, 4 - j.clamp(max=4))) % 26
+        digit = torch.where(j < 5, head, (kk * 31 + j * 7) % 26)
+        data[b0:b1] = (97 + digit).to(torch.uint8)
+        del kk, j, head, digit, ln
+    return kid, offs, data, total
+
+
 def unpack_bits(torch, bits, n):
     """LSB-first bitmap bytes -> bool[n] (verification only)"""
     sh = torch.arange(8, device=bits.device, dtype=torch.uint8)
@@ -455,6 +479,51 @@ def run_configs(env, n):
     del ku, su, cu
     entry("c3 group-by via Grouper + 2 HashAggregators (the reference API shape)", n, ms, n * 16.125 + ng * 24.25, ok, groups=ng)
     del keys, vals, keys_t, vals_t, vvalid_t, want_cnt, want_sum, want_rows, present
+    ctx.trim()
+    torch.cuda.empty_cache()
+
+    # ---- c3u: group-by sum + count with a large_utf8 KEY (north_star: hash-aggregate over utf8 columns) ----
+    # n/2 strings drawn from a vocabulary of 1M words of 8..16 bytes; word k = the 5 base-26 digits of k + a k-dependent
+    # tail, so the result's key strings can be decoded back to k on the device and checked against index_add_
+    m = n // 2
+    vocab = 1_000_000 if m >= 10_000_000 else max(100, m // 100)
+    kid, offs, data, total = make_word_column(torch, gen, m, vocab)
+    vals_t = torch.randint(-100, 101, (m,), dtype=I64, device="cuda", generator=gen)
+    vvalid_t, v_nulls = make_validity(torch, m, gen)
+    skeys = DeviceArray.from_pointers(ctx, pa.large_string(), m, offs.data_ptr(), data2_ptr=data.data_ptr())
+    vals = DeviceArray.from_pointers(ctx, pa.int64(), m, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
+
+    def string_group_by():
+        return bc.group_by([skeys], [("hash_sum", vals, None), ("hash_count", vals, None)], fused=False)
+    ms = env.timed(string_group_by, 2)
+    (ku,), (su, cu) = string_group_by()
+    want_cnt = torch.zeros(vocab, dtype=I64, device="cuda")
+    want_sum = torch.zeros(vocab, dtype=I64, device="cuda")
+    want_rows = torch.zeros(vocab, dtype=I64, device="cuda")
+    for lo in range(0, m, chunk):
+        hi = min(m, lo + chunk)
+        vv = unpack_bits(torch, vvalid_t[lo // 8:], hi - lo).to(I64)
+        want_cnt.index_add_(0, kid[lo:hi], vv)
+        want_sum.index_add_(0, kid[lo:hi], vals_t[lo:hi] * vv)
+        want_rows.index_add_(0, kid[lo:hi], torch.ones_like(vv))
+        del vv
+    ng = ku.length
+    ko = torch.as_tensor(_view(ku.buffers[1].ptr, ng + 1, "<i8", ku), device="cuda")
+    kb = torch.as_tensor(_view(ku.buffers[2].ptr, int(ko[-1].item()) if ng else 0, "|u1", ku), device="cuda")
+    dec = torch.zeros(ng, dtype=I64, device="cuda")
+    for j in range(5):
+        dec = dec * 26 + (kb[ko[:-1] + j].to(I64) - 97)
+    st = torch.as_tensor(_view(su.buffers[1].ptr, ng, "<i8", su), device="cuda")
+    ct = torch.as_tensor(_view(cu.buffers[1].ptr, ng, "<i8", cu), device="cuda")
+    ok = ng == int((want_rows > 0).sum().item()) and ku.null_count == 0
+    ok = ok and int(torch.unique(dec).numel()) == ng and bool(((ko[1:] - ko[:-1]) == 8 + (dec * 7) % 9).all().item())
+    ok = ok and bool((ct == want_cnt[dec]).all().item())
+    nz = ct > 0
+    ok = ok and bool((st[nz] == want_sum[dec][nz]).all().item()) and su.null_count == int((~nz).sum().item())
+    L = total / m
+    entry("c3 group-by hash_sum+hash_count, large_utf8 key (1M distinct words of 8-16 B; string Grouper + 2 HashAggregators)", m, ms,
+          m * (8 + L + 8.125) + ng * (8 + L + 16.25), ok, groups=ng, mean_len=L)
+    del ku, su, cu, ko, kb, dec, st, ct, skeys, vals, kid, offs, data, vals_t, vvalid_t, want_cnt, want_sum, want_rows
     ctx.trim()
     torch.cuda.empty_cache()
 

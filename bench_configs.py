@@ -2,6 +2,7 @@
 """bench_configs.py -- the other BASELINE.json configs at scale (not the driver's bench line):
   c1  Filter(int64, bool mask)            1B rows, values null_p 0.1, mask non-null, s = 0.5
   c3  group-by sum+count, int64 key/value 1B rows, 10M groups (fused table and Grouper+aggregators)
+  c3u group-by / dictionary_encode with a large_utf8 key   500M strings from 1M distinct words (not in the default --only list)
   c4  SortIndices int64 + validity        1B rows (wide range) and narrow range [0, 4095]
   f1  dictionary_encode / value_counts of an int64 column (1M distinct values), 500M rows
   c5  large_utf8 Filter                   500M strings, 0-32 B, null_p 0.1, s = 0.5  (+ dictionary Take)
@@ -125,6 +126,25 @@ def main():
         ms = timed(stream, unfused, max(1, args.reps - 1), warmup=1)
         report("c3 group-by sum+count (Grouper + 2 HashAggregators)", n, ms, n * 16.125 + ng * 24.25, {"groups": ng})
         del keys, vals, keys_t, vals_t, vvalid_t
+
+    if "c3u" in only:
+        # group-by with a large_utf8 key: n/2 strings from 1M distinct words of 8-16 B (bench.make_word_column)
+        from bench import make_word_column
+        m = n // 2
+        vocab = 1_000_000 if m >= 10_000_000 else max(100, m // 100)
+        kid, offs, data, total = make_word_column(torch, gen, m, vocab)
+        vals_t = torch.randint(-100, 101, (m,), dtype=torch.int64, device="cuda", generator=gen)
+        vvalid_t, v_nulls = make_validity(torch, m, gen)
+        skeys = DeviceArray.from_pointers(ctx, pa.large_string(), m, offs.data_ptr(), data2_ptr=data.data_ptr())
+        vals = DeviceArray.from_pointers(ctx, pa.int64(), m, vals_t.data_ptr(), validity_ptr=vvalid_t.data_ptr(), null_count=v_nulls)
+        ms = timed(stream, lambda: bc.group_by([skeys], [("hash_sum", vals, None), ("hash_count", vals, None)], fused=False),
+                   max(1, args.reps - 1), warmup=1)
+        L = total / m
+        report("c3u group-by sum+count, large_utf8 key (1M distinct words)", m, ms, m * (8 + L + 8.125) + vocab * (8 + L + 16.25),
+               {"groups": vocab, "mean_len": L})
+        ms = timed(stream, lambda: bc.dictionary_encode(skeys), max(1, args.reps - 1), warmup=1)
+        report("f1 dictionary_encode large_utf8 (1M distinct words)", m, ms, m * (8 + L + 4) + vocab * (8 + L), {"mean_len": L})
+        del skeys, vals, kid, offs, data, vals_t, vvalid_t
 
     if "c4" in only:
         m = min(n, (1 << 30) - 1)
