@@ -1026,10 +1026,12 @@ def run_gpu(args):
     else:
         fused_gbs = ALG_PIPELINE * n / (fused_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak, "traffic": traffic,
-                    "kernel": "take_cast_arith_kernel<double,int64_t,float,true>", "peak_source": peak_src,
-                    "alg_bytes_per_launch": ALG_PIPELINE * n,
-                    "note": "random 8-byte gathers: DRAM moves ~128 B per gathered value and ~57 B per validity probe (profiles/take_traffic.json), "
-                            "so the byte roofline is not reachable; monotonic indices run the same gather at 0.83"}
+                    "kernel": "take_cast_arith_kernel<double,int64_t,float,true> (+ its take_validity_band_kernel pass: one call)",
+                    "peak_source": peak_src, "alg_bytes_per_launch": ALG_PIPELINE * n,
+                    "note": "time and traffic are those of the whole b2_take_cast_arith call = the gather kernel (26.9 ms under ncu) + one "
+                            "validity band pass (2.9 ms). Random 8-byte gathers: DRAM moves ~127 B per gathered value and DRAM accesses, not "
+                            "bytes, are the limit (42-44 G/s, profiles/gather_probe_r01.csv), so the byte roofline is not reachable; "
+                            "monotonic indices run the same gather at 0.82 (profiles/take_traffic.json, take_band_sweep_r02.jsonl)"}
     cpu = cpu_baseline_leg(args) if world == 1 else {"value": None, "unit": "rows/s", "cores": os.cpu_count() or 1, "kind": "reference",
                                                       "sample": "measured at N = 1 only (rank 0)"}
     line = {
