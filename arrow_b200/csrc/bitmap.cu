@@ -8,6 +8,8 @@
 // One thread produces one aligned 64-bit output word from funnel-shifted input
 // words, so arbitrary (non byte-aligned) slice offsets cost one extra load.
 // Algorithmic bytes: 1/8 B per row per bitmap read or written.
+#include <cstdlib>
+
 #include "bitmap.h"
 
 namespace b2 {
@@ -45,7 +47,13 @@ __global__ void __launch_bounds__(kBlock) l2_demote_kernel(const char* base, int
 }
 
 int launch_l2_demote(const void* p, int64_t bytes, cudaStream_t s) {
-  if (!p || bytes <= 0) return B2_OK;
+  // OFF unless B2_L2_DEMOTE=1: measured (profiles/l2_demote_r02.jsonl) it buys the kernels that follow nothing, and bench runs
+  // with it enabled showed the dense group-by (whose table lives on evict_last reductions) slower afterwards
+  static const bool enabled = [] {
+    const char* e = getenv("B2_L2_DEMOTE");
+    return e && e[0] == '1';
+  }();
+  if (!enabled || !p || bytes <= 0) return B2_OK;
   const uintptr_t p0 = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(127);
   const uintptr_t p1 = reinterpret_cast<uintptr_t>(p) + static_cast<uintptr_t>(bytes);
   const int64_t lines = static_cast<int64_t>((p1 - p0 + 127) / 128);

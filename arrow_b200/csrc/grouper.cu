@@ -504,6 +504,7 @@ struct B2Grouper {
   uint64_t uniq_cap = 0;
   // direct-addressed mode
   bool direct_eligible = false;  // one integer key column, not yet known to be too wide
+  bool never_direct = false;     // set by callers whose keys are hashes (grouper_wide.cu): skip the min/max probing
   bool direct = false;
   DirectTable dt{};
   uint64_t obs_min = ~0ull, obs_max = 0;  // order-preserving encoding, over every valid key seen
@@ -629,8 +630,29 @@ static int grouper_columns(const B2Grouper* g, const B2Array* keys, KeyColumns* 
   return B2_OK;
 }
 
-static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool insert, cudaStream_t s) {
+// rows (B2_UINT32, ascending = id order) at which the groups NEW in this batch first occur: the set bits of `flags`
+static int grouper_new_rows(B2Context* ctx, const void* flags, int64_t n, B2Array* out_rows, cudaStream_t s) {
+  B2Array mask{};
+  mask.type = B2_BOOL;
+  mask.data = flags;
+  mask.length = n;
+  B2Array rows{};
+  B2_RETURN_NOT_OK(b2_filter_indices(ctx, &mask, 0, &rows, s));
+  if (rows.type == B2_UINT32) {
+    *out_rows = rows;
+    return B2_OK;
+  }
+  B2CastOptions wide{B2_UINT32, 1, 1, 0};  // short batches come back as uint16
+  const int st = b2_cast_numeric(ctx, &rows, &wide, out_rows, s);
+  if (rows.data) ctx->free(const_cast<void*>(rows.data), s);
+  if (rows.validity) ctx->free(const_cast<void*>(rows.validity), s);
+  return st;
+}
+
+static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool insert, cudaStream_t s,
+                       B2Array* out_new_rows = nullptr) {
   B2Context* ctx = g->ctx;
+  if (out_new_rows) fill_out(out_new_rows, B2_UINT32, 0, 0, nullptr, nullptr);
   KeyColumns cols;
   int64_t n;
   B2_RETURN_NOT_OK(grouper_columns(g, keys, &cols, &n));
@@ -720,6 +742,7 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
       g->num_groups += static_cast<uint32_t>(n_new);
       grouper_direct_gather_kernel<<<grid, kBlock, 0, s>>>(kd, kw, cols.valid[0], n, g->dt, ids.as<uint32_t>());
       B2_LAUNCHED();
+      if (out_new_rows) B2_RETURN_NOT_OK(grouper_new_rows(ctx, flags.ptr, n, out_new_rows, s));
     }
     fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
     return B2_OK;
@@ -792,6 +815,7 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
   if (n_new > 0) {  // otherwise the probe resolved every row
     grouper_gather_kernel<<<grid, kBlock, 0, s>>>(n, g->table, row_slot.as<uint32_t>(), ids.as<uint32_t>());
     B2_LAUNCHED();
+    if (out_new_rows) B2_RETURN_NOT_OK(grouper_new_rows(ctx, flags.ptr, n, out_new_rows, s));
   }
   fill_out(out_ids, B2_UINT32, n, 0, nullptr, ids.release());
   // keep load factor <= 1/2 for the next batch
@@ -801,6 +825,19 @@ static int grouper_run(B2Grouper* g, const B2Array* keys, B2Array* out_ids, bool
   }
   return B2_OK;
 }
+
+namespace b2 {
+// internal to the library (grouper_wide.cu): keys that are hashes never fit a direct-addressed window -- skip the probing
+void grouper_never_direct(B2Grouper* g) {
+  g->never_direct = true;
+  g->direct_eligible = false;
+}
+// Consume that also returns the rows at which this batch's new groups first occur (in id order)
+int grouper_consume_new_rows(B2Grouper* g, const B2Array* keys, B2Array* out_ids, B2Array* out_new_rows, cudaStream_t s) {
+  B2_CUDA(cudaSetDevice(g->ctx->device));
+  return grouper_run(g, keys, out_ids, true, s, out_new_rows);
+}
+}  // namespace b2
 
 extern "C" {
 
@@ -916,7 +953,7 @@ int b2_grouper_reset(B2Grouper* g) {
   cudaStream_t s = g->ctx->stream;
   grouper_free_table(g, s);
   grouper_free_direct(g, s);
-  g->direct_eligible = g->layout.n_keys == 1 && grouper_type_is_integer(g->key_types[0]) && grouper_direct_enabled();
+  g->direct_eligible = !g->never_direct && g->layout.n_keys == 1 && grouper_type_is_integer(g->key_types[0]) && grouper_direct_enabled();
   g->obs_min = ~0ull;
   g->obs_max = 0;
   g->num_groups = 0;

@@ -13,7 +13,8 @@
 // is reduced to dense 32-bit ids on its own:
 //   * a fixed-width part is the 64-bit grouper of grouper.cu (16-byte slots, one sector per probe);
 //   * a string part hashes every value to 64 bits (aligned 8-byte loads, funnel-shifted), groups the HASHES with
-//     the same 64-bit grouper, appends the first occurrence of every new hash to a string store, and then VERIFIES
+//     the same 64-bit grouper (which also reports the rows where new groups first occur -- its own first-occurrence
+//     flags), appends those first occurrences to a string store (b2_take), and then VERIFIES
 //     every row of the batch against the store entry of its id, byte for byte.  A verified batch is exact; a
 //     mismatch (two different strings with one 64-bit hash) rolls the batch back, re-seeds the hash, rebuilds the
 //     part from its store and repeats -- results never depend on the hash.
@@ -29,6 +30,9 @@
 #include "context.h"
 
 namespace b2 {
+
+void grouper_never_direct(B2Grouper* g);  // grouper.cu
+int grouper_consume_new_rows(B2Grouper* g, const B2Array* keys, B2Array* out_ids, B2Array* out_new_rows, cudaStream_t s);
 
 namespace {
 
@@ -112,24 +116,31 @@ __global__ void __launch_bounds__(kBlock) hash_strings_kernel(const OffT* __rest
   }
 }
 
-// first[id - base] = smallest row carrying that (new) id
-__global__ void __launch_bounds__(kBlock) first_rows_kernel(const uint32_t* __restrict__ ids, int64_t n, uint32_t base,
-                                                            uint32_t* first) {
-  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-    const uint32_t g = ids[i];
-    if (g >= base && first[g - base] > static_cast<uint32_t>(i)) atomicMin(first + (g - base), static_cast<uint32_t>(i));
-  }
-}
+// One 32-byte record per stored value = ONE L2 sector per verification: word 0 = length (bit 31: the null value), then the
+// first 28 bytes zero-padded.  The verify pass is bound by random L2 requests (211 G/s measured, bench_micro/gather_probe),
+// and {null flag, two offsets, the bytes} were four to five of them per row; values longer than 28 bytes fetch their
+// tail from the byte store.
+constexpr int kRecBytes = 28;
+constexpr uint32_t kRecNull = 0x80000000u;
 
 // append the taken first occurrences (offsets start at taken_off[0]) behind group `base`
 template <typename OffT>
-__global__ void __launch_bounds__(kBlock) store_append_kernel(const OffT* __restrict__ taken_off, BitmapReader taken_valid,
-                                                              int64_t n_new, int64_t byte_base, int64_t* store_off,
-                                                              uint8_t* store_null, uint32_t base) {
+__global__ void __launch_bounds__(kBlock) store_append_kernel(const OffT* __restrict__ taken_off, const uint8_t* __restrict__ taken_bytes,
+                                                              BitmapReader taken_valid, int64_t n_new, int64_t byte_base, int64_t* store_off,
+                                                              uint8_t* store_null, uint4* store_rec, uint32_t base) {
   const int64_t o0 = static_cast<int64_t>(taken_off[0]);
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n_new; i += (int64_t)gridDim.x * kBlock) {
-    store_off[base + i + 1] = byte_base + static_cast<int64_t>(taken_off[i + 1]) - o0;
-    store_null[base + i] = taken_valid.bit(i) ? 0 : 1;
+    const int64_t b0 = static_cast<int64_t>(taken_off[i]), b1 = static_cast<int64_t>(taken_off[i + 1]);
+    const bool is_null = !taken_valid.bit(i);
+    store_off[base + i + 1] = byte_base + b1 - o0;
+    store_null[base + i] = is_null ? 1 : 0;
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t len = b1 - b0;
+    w[0] = is_null ? kRecNull : static_cast<uint32_t>(len > 0x7fffffff ? 0x7fffffff : len);
+    const int head = len < kRecBytes ? static_cast<int>(len) : kRecBytes;
+    for (int k = 0; k < head; ++k) w[1 + (k >> 2)] |= static_cast<uint32_t>(taken_bytes[b0 + k]) << (8 * (k & 3));
+    store_rec[2 * (base + i)] = make_uint4(w[0], w[1], w[2], w[3]);
+    store_rec[2 * (base + i) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(kBlock) verify_kernel(const OffT* __restrict__
                                                         BitmapReader valid, int64_t n, const uint32_t* __restrict__ ids,
                                                         BitmapReader ids_valid, const int64_t* __restrict__ store_off,
                                                         const uint8_t* __restrict__ store_bytes,
-                                                        const uint8_t* __restrict__ store_null, uint32_t* out_validity,
+                                                        const uint4* __restrict__ store_rec, uint32_t* out_validity,
                                                         int64_t* counter) {
   const int64_t nw = (n + 31) >> 5;
   int64_t local = 0;
@@ -151,13 +162,28 @@ __global__ void __launch_bounds__(kBlock) verify_kernel(const OffT* __restrict__
       known = out_validity ? ids_valid.bit(i) : true;
       if (known) {
         const uint32_t g = ids[i];
+        const uint4 r0 = __ldg(store_rec + 2 * static_cast<int64_t>(g)), r1 = __ldg(store_rec + 2 * static_cast<int64_t>(g) + 1);
         const bool rnull = !valid.bit(i);
-        if (rnull || store_null[g]) {
-          match = rnull && store_null[g];
+        if (rnull || r0.x == kRecNull) {
+          match = rnull && r0.x == kRecNull;
         } else {
           const int64_t o0 = static_cast<int64_t>(offs[i]), len = static_cast<int64_t>(offs[i + 1]) - o0;
-          const int64_t s0 = store_off[g];
-          match = (store_off[g + 1] - s0 == len) && bytes_equal(bytes + o0, store_bytes + s0, len);
+          match = static_cast<int64_t>(r0.x) == len || (r0.x == 0x7fffffffu && len >= 0x7fffffff);
+          if (match) {
+            const uint32_t rw[7] = {r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const int64_t head = len < kRecBytes ? len : kRecBytes;
+            for (int64_t o = 0; o < head && match; o += 8) {
+              const int nb = head - o >= 8 ? 8 : static_cast<int>(head - o);
+              const int k = static_cast<int>(o >> 2);
+              uint64_t want = rw[k] | (nb > 4 ? static_cast<uint64_t>(rw[k + 1]) << 32 : 0ull);
+              if (nb < 8) want &= (1ull << (8 * nb)) - 1ull;
+              match = load_bytes8(bytes + o0 + o, nb) == want;
+            }
+            if (match && len > kRecBytes) {  // the tail lives in the byte store
+              const int64_t s0 = store_off[g];
+              match = (store_off[g + 1] - s0 == len) && bytes_equal(bytes + o0 + kRecBytes, store_bytes + s0 + kRecBytes, len - kRecBytes);
+            }
+          }
         }
       }
     }
@@ -241,6 +267,7 @@ struct StringPart {
   // store of the distinct values in id order
   int64_t* off = nullptr;  // [cap_groups + 1]
   uint8_t* is_null = nullptr;
+  uint4* rec = nullptr;  // [2 * cap_groups]: the 32-byte verification records
   uint8_t* bytes = nullptr;
   uint64_t cap_groups = 0, cap_bytes = 0;
   uint32_t n = 0;
@@ -256,12 +283,15 @@ struct StringPart {
       hash_bits = static_cast<int>(strtol(e, nullptr, 10));
       if (hash_bits < 1 || hash_bits > 64) hash_bits = 64;
     }
-    return b2_grouper_create(ctx, &kt, 1, &inner);
+    B2_RETURN_NOT_OK(b2_grouper_create(ctx, &kt, 1, &inner));
+    grouper_never_direct(inner);
+    return B2_OK;
   }
   void destroy(cudaStream_t s) {
     if (inner) b2_grouper_destroy(inner);
     if (off) ctx->free(off, s);
     if (is_null) ctx->free(is_null, s);
+    if (rec) ctx->free(rec, s);
     if (bytes) ctx->free(bytes, s);
   }
   int reset() {
@@ -275,19 +305,23 @@ struct StringPart {
     if (groups > cap_groups || !off) {
       uint64_t cap = 1024;
       while (cap < groups) cap <<= 1;
-      void *o, *nl;
+      void *o, *nl, *rc;
       B2_RETURN_NOT_OK(ctx->alloc((cap + 1) * 8, &o, s));
       B2_RETURN_NOT_OK(ctx->alloc(cap, &nl, s));
+      B2_RETURN_NOT_OK(ctx->alloc(cap * 32, &rc, s));
       if (off) {
         B2_CUDA(cudaMemcpyAsync(o, off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, s));
         B2_CUDA(cudaMemcpyAsync(nl, is_null, n, cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(cudaMemcpyAsync(rc, rec, (size_t)n * 32, cudaMemcpyDeviceToDevice, s));
         ctx->free(off, s);
         ctx->free(is_null, s);
+        ctx->free(rec, s);
       } else {
         B2_CUDA(cudaMemsetAsync(o, 0, 8, s));
       }
       off = static_cast<int64_t*>(o);
       is_null = static_cast<uint8_t*>(nl);
+      rec = static_cast<uint4*>(rc);
       cap_groups = cap;
     }
     if (nbytes > cap_bytes || !bytes) {
@@ -367,7 +401,7 @@ struct StringPart {
       B2_RETURN_NOT_OK(reserve(1, 1, s));  // an empty store still needs addressable arrays
       verify_kernel<OffT><<<grid1(n_rows), kBlock, 0, s>>>(offs, data, valid, n_rows, static_cast<const uint32_t*>(ids.a.data),
                                                            BitmapReader(ids.a.null_count == 0 ? nullptr : ids.a.validity, 0, n_rows),
-                                                           off, bytes, is_null, bits.as<uint32_t>(), slot.dev());
+                                                           off, bytes, rec, bits.as<uint32_t>(), slot.dev());
       B2_LAUNCHED();
       B2_RETURN_NOT_OK(slot.fetch(s));
       const int64_t nulls = n_rows - slot.host()[0];
@@ -379,8 +413,9 @@ struct StringPart {
     for (int attempt = 0; attempt < 16; ++attempt) {
       B2_RETURN_NOT_OK(hash_batch<OffT>(col, hashes.as<uint64_t>(), s));
       B2Array h = u64_array(hashes.ptr, n_rows);
-      Owned ids(ctx, s);
-      B2_RETURN_NOT_OK(b2_grouper_consume(inner, &h, &ids.a, s));
+      Owned ids(ctx, s), first(ctx, s);
+      // the 64-bit grouper already knows where this batch's new groups first occur (its first-occurrence flags): ask for the rows
+      B2_RETURN_NOT_OK(grouper_consume_new_rows(inner, &h, &ids.a, &first.a, s));
       uint32_t total = 0;
       B2_RETURN_NOT_OK(b2_grouper_num_groups(inner, &total));
       const uint32_t n_new = total - n;
@@ -388,20 +423,16 @@ struct StringPart {
       int64_t new_bytes = 0;
       bool new_null = false;
       if (n_new) {
-        Temp first(ctx, s);
-        B2_RETURN_NOT_OK(first.alloc(sizeof(uint32_t) * (size_t)n_new));
-        B2_CUDA(cudaMemsetAsync(first.ptr, 0xff, sizeof(uint32_t) * (size_t)n_new, s));
-        first_rows_kernel<<<grid1(n_rows), kBlock, 0, s>>>(id_ptr, n_rows, n, first.as<uint32_t>());
-        B2_LAUNCHED();
-        B2Array fr = u32_array(first.ptr, n_new);
+        if (first.a.length != (int64_t)n_new) return set_error(B2_UNKNOWN_ERROR, "grouper: first-occurrence rows out of step with the new groups");
+        B2Array fr = u32_array(first.a.data, n_new);
         Owned taken(ctx, s);
         B2_RETURN_NOT_OK(b2_take(ctx, col, &fr, 0, &taken.a, s));
         B2_RETURN_NOT_OK(b2_binary_data_size(ctx, &taken.a, &new_bytes, s));
         new_null = taken.a.null_count > 0;
         B2_RETURN_NOT_OK(reserve((uint64_t)n + n_new, (uint64_t)(n_bytes + new_bytes), s));
         store_append_kernel<OffT><<<grid1(n_new), kBlock, 0, s>>>(
-            static_cast<const OffT*>(taken.a.data) + taken.a.offset,
-            BitmapReader(taken.a.null_count == 0 ? nullptr : taken.a.validity, taken.a.offset, n_new), n_new, n_bytes, off, is_null, n);
+            static_cast<const OffT*>(taken.a.data) + taken.a.offset, static_cast<const uint8_t*>(taken.a.data2),
+            BitmapReader(taken.a.null_count == 0 ? nullptr : taken.a.validity, taken.a.offset, n_new), n_new, n_bytes, off, is_null, rec, n);
         B2_LAUNCHED();
         if (new_bytes) {
           OffT first_off = 0;  // the taken array starts at offset 0 of its own data buffer
@@ -413,7 +444,7 @@ struct StringPart {
       }
       ScalarSlot slot(ctx);
       B2_RETURN_NOT_OK(slot.zero(s));
-      verify_kernel<OffT><<<grid1(n_rows), kBlock, 0, s>>>(offs, data, valid, n_rows, id_ptr, BitmapReader(), off, bytes, is_null,
+      verify_kernel<OffT><<<grid1(n_rows), kBlock, 0, s>>>(offs, data, valid, n_rows, id_ptr, BitmapReader(), off, bytes, rec,
                                                            nullptr, slot.dev());
       B2_LAUNCHED();
       B2_RETURN_NOT_OK(slot.fetch(s));

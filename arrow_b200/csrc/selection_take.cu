@@ -162,11 +162,10 @@ __global__ void __launch_bounds__(kBlock) take_validity_band_kernel(TakeBandArgs
   if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(a.valid_count), static_cast<unsigned long long>(-s));
 }
 
-// The probes leave the bitmap's lines in L2 with evict_last priority; probed in two bands, a 125 MB bitmap marks the whole
-// L2 that way.  The take therefore hands the lines back when it is done (launch_l2_demote, bitmap.cu: applypriority
-// evict_normal, one instruction per 128-byte line, ~20 us for 1B rows).  Measured (profiles/take_band_sweep_r02.jsonl):
-// the cast + add that follow the take run at the same speed with and without it, so this is insurance for callers whose
-// next kernel wants the cache, not a measured win.
+// The probes leave the bitmap's lines in L2 with evict_last priority.  launch_l2_demote (bitmap.cu: applypriority
+// evict_normal, one instruction per 128-byte line) can hand them back at the end of the call; it is OFF by default
+// (B2_L2_DEMOTE=1 enables it): the cast + add that follow the take run at the same speed with and without it
+// (profiles/take_band_sweep_r02.jsonl).
 
 // Are the indices clustered?  2048 evenly spaced pairs (idx[p], idx[p+1]): the share whose targets lie within 64Ki rows
 // (8 KB of bitmap) of each other.  Clustered / monotonic indices probe the bitmap almost sequentially -- banding would only
@@ -522,8 +521,6 @@ static int take_demote_bitmap(const B2Array* values, cudaStream_t s) {
   if (values->null_count == 0 || !values->validity) return B2_OK;
   const int64_t bytes = values->length >> 3;
   if (bytes < (8 << 20)) return B2_OK;
-  const char* e = getenv("B2_TAKE_DEMOTE");
-  if (e && e[0] == '0') return B2_OK;
   const char* p0 = static_cast<const char*>(values->validity) + (values->offset >> 3);
   return launch_l2_demote(p0, (values->length + 7) >> 3, s);
 }

@@ -81,7 +81,7 @@ for b in args.bands.split(","):
     demote = "1"
     if b.endswith("nd"):   # e.g. "64nd": 64 MB bands without the L2 demotion pass
         b, demote = b[:-2], "0"
-    os.environ["B2_TAKE_DEMOTE"] = demote
+    os.environ["B2_L2_DEMOTE"] = demote  # read once per process by the library: only the first value counts
     os.environ["B2_TAKE_BAND_MB"] = b
     t_mono, _ = timed(lambda: bc.take(values, mono))
     t_tail = pipeline_tail()
