@@ -358,6 +358,7 @@ struct BinFilterArgs {
   uint32_t* out_validity;  // zero-initialised or NULL
   int64_t n;
   bool staged;             // copy pass: row-driven staged copy (dynamic shared memory = kStageBytes + 16)
+  int64_t* oversize;       // sizes pass, 64-bit offsets: set when a tile's source span does not fit the 32-bit staging
 };
 
 template <typename OffT, bool COPY, bool HAS_VALID, bool STAGED>
@@ -447,7 +448,15 @@ __global__ void __launch_bounds__(kBinThreads, STAGED ? 3 : 1) filter_binary_ker
     total += s_wtot[w];
   }
   if (!COPY) {
-    if (threadIdx.x == 0) a.tile_bytes[tile] = total;
+    if (threadIdx.x == 0) {
+      a.tile_bytes[tile] = total;
+      // lengths, staged offsets and sources are 32-bit and tile-relative: with 64-bit offsets a tile whose SOURCE span reaches
+      // 4 GiB (a single value that large, or 4096 huge ones) would wrap silently -- report it instead
+      if (sizeof(OffT) == 8 && a.oversize) {
+        const int64_t end = row0 + kTileRows < a.n ? row0 + kTileRows : a.n;
+        if (static_cast<int64_t>(a.offsets[end]) - static_cast<int64_t>(tile_src0) >= (1ll << 32)) *a.oversize = 1;
+      }
+    }
     return;
   }
   const int64_t byte_base = a.tile_bytes[tile];
@@ -522,16 +531,19 @@ static int filter_binary_typed(B2Context* ctx, const B2Array* values, const B2Ar
   a.out_validity = nullptr;
   a.n = n;
   a.staged = false;
-  filter_binary_kernel<OffT, false, false, false><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
-  B2_LAUNCHED();
   ScalarSlot slot(ctx);
   B2_RETURN_NOT_OK(slot.zero(s));
+  a.oversize = slot.dev() + 3;
+  filter_binary_kernel<OffT, false, false, false><<<(unsigned)n_tiles, kBinThreads, 0, s>>>(a);
+  B2_LAUNCHED();
   tile_scan64_kernel<<<1, 1024, 0, s>>>(tile_bytes.as<int64_t>(), n_tiles, byte_offsets.as<int64_t>(), slot.dev());
   B2_LAUNCHED();
   B2_RETURN_NOT_OK(slot.fetch(s));
   const int64_t total_bytes = slot.host()[0];
   if (sizeof(OffT) == 4 && total_bytes > 2147483646ll)
     return set_error(B2_INVALID, "Filter operation overflowed binary array capacity");
+  if (slot.host()[3] != 0)
+    return set_error(B2_NOT_IMPLEMENTED, "filter: a 4096-row tile of this large_utf8 / large_binary array spans 4 GiB or more of value bytes");
   Temp offs(ctx, s), data(ctx, s), bits(ctx, s);
   B2_RETURN_NOT_OK(offs.alloc(sizeof(OffT) * (size_t)(out_len + 1)));
   B2_RETURN_NOT_OK(data.alloc((size_t)total_bytes + 16));
@@ -590,6 +602,7 @@ struct BinTakeArgs {
   int64_t* valid_count;
   unsigned long long* first_bad;
   bool staged;
+  int64_t* oversize;  // sizes pass, 64-bit offsets: a taken value or a tile's total does not fit the 32-bit staging
 };
 
 template <typename Idx>
@@ -629,14 +642,17 @@ __global__ void __launch_bounds__(kBinThreads) take_binary_kernel(BinTakeArgs<Of
         len[k] = static_cast<uint32_t>(o1 - o0);
         src[k] = static_cast<int64_t>(o0);
         vb |= 1u << k;
-        local += len[k];
+        local += static_cast<int64_t>(o1) - static_cast<int64_t>(o0);  // the true length: a wrapped one must not hide an oversize tile
       }
     }
   }
   int64_t total;
   const int64_t excl = block_excl_scan(local, &total);
   if (!COPY) {
-    if (threadIdx.x == 0) a.tile_bytes[tile] = total;
+    if (threadIdx.x == 0) {
+      a.tile_bytes[tile] = total;
+      if (sizeof(OffT) == 8 && a.oversize && total >= (1ll << 32)) *a.oversize = 1;  // covers a single value >= 4 GiB too
+    }
     return;
   }
   const int64_t byte_base = a.tile_bytes[tile];
@@ -699,6 +715,7 @@ static int take_binary_typed(B2Context* ctx, const B2Array* values, const B2Arra
   a.out_validity = nullptr;
   a.valid_count = slot.dev() + 1;
   a.first_bad = reinterpret_cast<unsigned long long*>(slot.dev() + 2);
+  a.oversize = slot.dev() + 3;
   a.staged = false;
   if (n == 0) {
     Temp offs(ctx, s);
@@ -717,6 +734,8 @@ static int take_binary_typed(B2Context* ctx, const B2Array* values, const B2Arra
   const int64_t total_bytes = slot.host()[0];
   if (sizeof(OffT) == 4 && total_bytes > 2147483646ll)
     return set_error(B2_INVALID, "Take operation overflowed binary array capacity");  // vector_selection_internal.cc:519-523
+  if (slot.host()[3] != 0)
+    return set_error(B2_NOT_IMPLEMENTED, "take: 2048 taken rows of this large_utf8 / large_binary array hold 4 GiB or more of value bytes");
   Temp offs(ctx, s), data(ctx, s), bits(ctx, s);
   B2_RETURN_NOT_OK(offs.alloc(sizeof(OffT) * (size_t)(n + 1)));
   B2_RETURN_NOT_OK(data.alloc((size_t)total_bytes + 16));

@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kBlock) take_validity_band_kernel(TakeBandArgs
 
 // The probes leave the bitmap's lines in L2 with evict_last priority.  launch_l2_demote (bitmap.cu: applypriority
 // evict_normal, one instruction per 128-byte line) can hand them back at the end of the call; it is OFF by default
-// (B2_L2_DEMOTE=1 enables it): the cast + add that follow the take run at the same speed with and without it
-// (profiles/take_band_sweep_r02.jsonl).
+// (B2_L2_DEMOTE=1 enables it): the cast + add and the dense group-by that follow a take run at the same speed with and
+// without it (profiles/l2_demote_r02.jsonl).
 
 // Are the indices clustered?  2048 evenly spaced pairs (idx[p], idx[p+1]): the share whose targets lie within 64Ki rows
 // (8 KB of bitmap) of each other.  Clustered / monotonic indices probe the bitmap almost sequentially -- banding would only

@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(kBlock) remap_ids_kernel(const uint32_t* __res
 // on one L2 address (50 ms per 500M rows).  The null entry -- the usual hot value, 10 % of the rows
 // even after the merge still means one atomic per warp on ONE address -- is counted in registers
 // and added once per warp at the end.
+// MERGE = false (large dictionaries): equal ids inside one warp are rare, so the MATCH.ANY (58 issue cycles per warp on this
+// part, profiles/smem_probe_r01.txt) costs more than the atomics it saves; every row is one RED into the L2-resident counts.
+template <bool MERGE>
 __global__ void __launch_bounds__(kBlock) count_ids_kernel(const uint32_t* __restrict__ ids, int64_t n,
                                                            uint32_t null_id, bool has_null,
                                                            unsigned long long* counts) {
@@ -67,8 +70,12 @@ __global__ void __launch_bounds__(kBlock) count_ids_kernel(const uint32_t* __res
     }
     const unsigned live = __ballot_sync(0xffffffffu, in);
     if (in) {
-      const unsigned peers = __match_any_sync(live, g);
-      if ((peers & lanemask_lt()) == 0) atomicAdd(&counts[g], static_cast<unsigned long long>(__popc(peers)));
+      if (MERGE) {
+        const unsigned peers = __match_any_sync(live, g);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(&counts[g], static_cast<unsigned long long>(__popc(peers)));
+      } else {
+        atomicAdd(&counts[g], 1ull);
+      }
     }
   }
   if (has_null && lane == 0 && nulls) atomicAdd(&counts[null_id], nulls);
@@ -162,9 +169,10 @@ extern "C" int b2_vector_hash(B2Context* ctx, const B2Array* values, int null_en
     B2_RETURN_NOT_OK(counts.alloc(sizeof(int64_t) * (size_t)(n_groups ? n_groups : 1)));
     B2_CUDA(cudaMemsetAsync(counts.ptr, 0, sizeof(int64_t) * (size_t)(n_groups ? n_groups : 1), s));
     if (n > 0) {
-      count_ids_kernel<<<grid_for(n, kBlock * 4, kSMs * 16), kBlock, 0, s>>>(static_cast<const uint32_t*>(ids.a.data), n,
-                                                                           null_id, has_null,
-                                                                           counts.as<unsigned long long>());
+      const int cgrid = grid_for(n, kBlock * 4, kSMs * 16);
+      const uint32_t* idp = static_cast<const uint32_t*>(ids.a.data);
+      if (n_groups >= 65536) count_ids_kernel<false><<<cgrid, kBlock, 0, s>>>(idp, n, null_id, has_null, counts.as<unsigned long long>());
+      else count_ids_kernel<true><<<cgrid, kBlock, 0, s>>>(idp, n, null_id, has_null, counts.as<unsigned long long>());
       B2_LAUNCHED();
     }
   }

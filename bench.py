@@ -679,6 +679,8 @@ def run_multi_gpu(env, n_total, reps):
             bits[lo // 8: lo // 8 + BLOCK // 8] = pack_bits(torch, v)
         return keys, vals, bits, nulls
 
+    last_reps = []
+
     def leg(fn):
         """CUDA-event time of `fn` (max over ranks), after one warm-up; also the exchange's own time"""
         r = fn()
@@ -696,7 +698,12 @@ def run_multi_gpu(env, n_total, reps):
             ms_list.append(env.max_over_ranks(a.elapsed_time(b)))
             xm, xbytes = ops.exchange_stats() if world > 1 else (0.0, 0)
             x_list.append(env.max_over_ranks(xm))
-        return r, sum(ms_list) / len(ms_list), sum(x_list) / len(x_list), xbytes
+        # median, not mean: a repetition that had to cudaMalloc (the pool was trimmed between legs) costs 2-7x and is not what the
+        # exchange leg measures; every repetition is kept in `reps_ms`
+        order = sorted(range(len(ms_list)), key=lambda i: ms_list[i])
+        mid = order[len(order) // 2]
+        last_reps[:] = [round(x, 3) for x in ms_list]
+        return r, ms_list[mid], x_list[mid], xbytes
 
     # ---- config 3: hash-aggregate ----
     keys_t, vals_t, bits_t, v_nulls = gen_columns("groupby")
@@ -725,7 +732,7 @@ def run_multi_gpu(env, n_total, reps):
                          "alltoall_share": (xms / ms) if ms else None, "groups": tot[3],
                          "alg_bytes": n_total * 16.125 + tot[3] * 24.25,
                          "frac_of_peak_x_n": (n_total * 16.125 + tot[3] * 24.25) / (ms * 1e-3) / 1e9 / (measured_peaks()[0] * world),
-                         "checksum": wrap(tot[8]), "parity_checksum_ok": bool(ok)}
+                         "checksum": wrap(tot[8]), "parity_checksum_ok": bool(ok), "reps_ms": list(last_reps)}
     del k, s, c, kt, st, ct, keys, vals, keys_t, vals_t, bits_t, valid
     ctx.trim()
     torch.cuda.empty_cache()
@@ -734,6 +741,7 @@ def run_multi_gpu(env, n_total, reps):
     keys_t, _, bits_t, k_nulls = gen_columns("sort")
     keys = DeviceArray.from_pointers(ctx, pa.int64(), n_local, keys_t.data_ptr(), validity_ptr=bits_t.data_ptr(), null_count=k_nulls)
     _, ms, xms, xbytes = leg(lambda: d.sort_indices(keys, ops, xchg))
+    sort_reps = list(last_reps)
     seg_fast, nulls_fast = d.sort_indices(keys, ops, xchg)                      # the timed path's own answer ...
     seg, nulls_idx, skeys = d.sort_indices(keys, ops, xchg, return_keys=True)  # ... and the variant that also returns the sorted keys
     same_answer = bool(torch.equal(seg_fast, seg)) and bool(torch.equal(nulls_fast, nulls_idx))
@@ -779,7 +787,8 @@ def run_multi_gpu(env, n_total, reps):
                       "rows_per_s": n_total / (ms * 1e-3), "alltoall_bytes_per_rank": xbytes, "alltoall_ms": xms,
                       "alltoall_share": (xms / ms) if ms else None, "alg_bytes": n_total * 16.125,
                       "frac_of_peak_x_n": n_total * 16.125 / (ms * 1e-3) / 1e9 / (measured_peaks()[0] * world),
-                      "segment_rows_rank0": int(seg.numel()), "checksum": wrap(tot[7]), "parity_checksum_ok": bool(ok)}
+                      "segment_rows_rank0": int(seg.numel()), "checksum": wrap(tot[7]), "parity_checksum_ok": bool(ok),
+                      "reps_ms": sort_reps}
     del seg, nulls_idx, skeys, keys, keys_t, bits_t, valid, grow
     xchg.close()
     ctx.trim()

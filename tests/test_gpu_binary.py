@@ -118,3 +118,21 @@ def test_binary_filter_take_staged_copy(ctx, t, monkeypatch):
                                  f"staged {t} n={n} {lo}-{hi} {null_p} {true_p} {ns}")
             idx = random_array(pa.int64(), n // 2 + 7, null_p, SEED + 5, lo=0, hi=n - 1, offset=3)
             assert_equal(bc.take(dev(vals, ctx), dev(idx, ctx)).to_arrow(), ora.take(vals, idx), f"staged take {t} n={n}")
+
+
+def test_large_binary_values_beyond_4gib_are_refused(ctx):
+    """64-bit offsets: the selection kernels stage lengths / offsets tile-relative in 32 bits, so a tile whose value bytes
+    reach 4 GiB must be reported, not wrapped.  The offsets below CLAIM a 5 GiB value; only the sizes pass
+    runs before the error, so the (tiny) data buffer is never dereferenced."""
+    import torch
+    offs_t = torch.tensor([0, 3, 3 + (5 << 30), 8 + (5 << 30), 9 + (5 << 30)], dtype=torch.int64, device="cuda")
+    data_t = torch.full((64,), ord("x"), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    d = DeviceArray.from_pointers(ctx, pa.large_binary(), 4, offs_t.data_ptr(), data2_ptr=data_t.data_ptr())
+    with pytest.raises(pa.ArrowNotImplementedError, match="4 GiB"):
+        bc.filter(d, DeviceArray.from_arrow(pa.array([True, True, False, True]), ctx))
+    with pytest.raises(pa.ArrowNotImplementedError, match="4 GiB"):
+        bc.take(d, DeviceArray.from_arrow(pa.array([0, 1], pa.int32()), ctx))
+    # rows that do not touch the huge value are fine for take (its tiles are about the TAKEN rows)
+    got = bc.take(d, DeviceArray.from_arrow(pa.array([0, 0], pa.int32()), ctx)).to_arrow()
+    assert got.to_pylist() == [b"xxx", b"xxx"]
