@@ -658,6 +658,35 @@ class Grouper:
         check(self.ctx.lib.b2_grouper_reset(self.handle))
 
 
+JOIN_TYPES = {"inner": 0, "left outer": 1, "left semi": 2, "left anti": 3}
+
+
+def hash_join_indices(left_keys: Sequence[DeviceArray], right_keys: Sequence[DeviceArray], join_type: str = "inner"):
+    """The matching row pairs of an equi-join (the build / probe / match core of acero's HashJoinNode, hash_join_node.cc;
+    join types as pyarrow.Table.join spells them).  Returns (left_indices, right_indices) as uint32 DeviceArrays -- for
+    "left outer" right_indices is null where a left row found no match, for "left semi" / "left anti" right_indices is None.
+    A null key matches nothing.  Gather the payload columns with take()."""
+    if isinstance(left_keys, DeviceArray):
+        left_keys = [left_keys]
+    if isinstance(right_keys, DeviceArray):
+        right_keys = [right_keys]
+    if join_type not in JOIN_TYPES:
+        raise ValueError(f'"{join_type}" is not a supported join type ({", ".join(JOIN_TYPES)})')
+    if len(left_keys) != len(right_keys) or not left_keys:
+        raise pa.ArrowInvalid("join needs the same, non-zero number of key columns on both sides")
+    for l, r in zip(left_keys, right_keys):
+        if l.type != r.type:
+            raise pa.ArrowInvalid(f"Incompatible data types for corresponding join field keys: {l.type} and {r.type}")
+    ctx = left_keys[0].ctx
+    cl = (cabi.B2Array * len(left_keys))(*[k._c() for k in left_keys])
+    cr = (cabi.B2Array * len(right_keys))(*[k._c() for k in right_keys])
+    ol, orr = cabi.B2Array(), cabi.B2Array()
+    pairs = JOIN_TYPES[join_type] < 2
+    check(ctx.lib.b2_hash_join(ctx.handle, cl, cr, len(left_keys), JOIN_TYPES[join_type], C.byref(ol), C.byref(orr) if pairs else None,
+                               ctx.stream))
+    return _out(ctx, ol, pa.uint32()), (_out(ctx, orr, pa.uint32()) if pairs else None)
+
+
 class HashAggregator:
     """One HashAggregateKernel state (compute/kernel.h:720-769): resize/consume/merge/finalize."""
 

@@ -718,3 +718,38 @@ def group_by(keys, aggregates):
     ids = gr.consume(keys)
     outs = [hash_aggregate(fn, vals, ids, gr.num_groups, **(opts or {})) for fn, vals, opts in aggregates]
     return gr.get_uniques(), outs
+
+
+# ---------------------------------------------------------------------------------------
+# Hash join: the matching row pairs   (acero/hash_join_node.cc, acero/swiss_join.cc; JoinType acero/options.h:365-374;
+# JoinKeyCmp::EQ: a null key matches nothing)
+# ---------------------------------------------------------------------------------------
+def hash_join_indices(left_keys, right_keys, join_type: str = "inner"):
+    """(left rows, right rows or None) in left-row order, matches of a left row in right-row order; right is None (a null
+    index) for the unmatched rows of "left outer"; "left semi" / "left anti" return (left rows, None)."""
+    lrows = list(Grouper([k.type for k in left_keys])._rows(left_keys))
+    rrows = list(Grouper([k.type for k in right_keys])._rows(right_keys))
+    table = {}
+    for j, row in enumerate(rrows):
+        if any(v is None for v in row):
+            continue
+        table.setdefault(row, []).append(j)
+    left, right = [], []
+    for i, row in enumerate(lrows):
+        hits = [] if any(v is None for v in row) else table.get(row, [])
+        if join_type == "inner":
+            left += [i] * len(hits)
+            right += hits
+        elif join_type == "left outer":
+            left += [i] * max(1, len(hits))
+            right += hits if hits else [None]
+        elif join_type == "left semi":
+            left += [i] if hits else []
+        elif join_type == "left anti":
+            left += [] if hits else [i]
+        else:
+            raise ValueError(join_type)
+    li = pa.array(left, pa.uint32())
+    if join_type in ("left semi", "left anti"):
+        return li, None
+    return li, pa.array(right, pa.uint32())

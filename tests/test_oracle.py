@@ -383,3 +383,24 @@ def test_string_vector_hash_and_grouper_vs_reference(t):
     assert g.num_groups == ref.num_rows
     look = g.lookup([pa.array([vals[3], "never-seen" if not is_bin else b"never-seen"], t), pa.array([int(other[0].as_py()), 0], pa.int64())])
     assert look.to_pylist() == [0, None]
+
+
+@pytest.mark.parametrize("join_type", ["inner", "left outer", "left semi", "left anti"])
+def test_hash_join_indices_vs_reference(join_type):
+    """oracle join pairs against the reference binary's HashJoinNode (pyarrow.Table.join): null keys match nothing,
+    every matching pair appears exactly once, unmatched left rows are null-extended for the outer join."""
+    rng = np.random.default_rng(SEED + 3)
+    n_l, n_r = 700, 500
+    lk = [pa.array(rng.integers(0, 40, n_l), pa.int64(), mask=rng.random(n_l) < 0.1),
+          pa.array([None if rng.random() < 0.05 else "s" + str(int(x)) for x in rng.integers(0, 3, n_l)], pa.string())]
+    rk = [pa.array(rng.integers(0, 45, n_r), pa.int64(), mask=rng.random(n_r) < 0.1),
+          pa.array([None if rng.random() < 0.05 else "s" + str(int(x)) for x in rng.integers(0, 3, n_r)], pa.string())]
+    l, r = ora.hash_join_indices(lk, rk, join_type)
+    lt = pa.table({"a": lk[0], "b": lk[1], "lrow": np.arange(n_l)})
+    rt = pa.table({"a": rk[0], "b": rk[1], "rrow": np.arange(n_r)})
+    out = lt.join(rt, keys=["a", "b"], join_type=join_type, use_threads=False)
+    rrow = out["rrow"].to_pylist() if "rrow" in out.column_names else [None] * out.num_rows
+    ref = sorted(zip(out["lrow"].to_pylist(), [(-1 if x is None else x) for x in rrow]))
+    mine = sorted(zip(l.to_pylist(), [(-1 if x is None else x) for x in (r.to_pylist() if r is not None else [None] * len(l))]))
+    assert mine == ref
+    assert l.to_pylist() == sorted(l.to_pylist())  # left-row order
