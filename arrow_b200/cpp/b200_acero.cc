@@ -6,6 +6,7 @@
 //   FilterNode   acero/filter_node.cc:74-106              -> "b200_filter"
 //   ProjectNode  acero/project_node.cc:43-120             -> "b200_project"
 //   OrderByNode  acero/order_by_node.cc:44-161            -> "b200_order_by"
+//   HashJoinNode acero/hash_join_node.cc:690-1100         -> "b200_hashjoin"
 // Options are the reference's own (AggregateNodeOptions, FilterNodeOptions,
 // OrderByNodeOptions, acero/options.h:250-260,335-351,539-546).
 //
@@ -709,9 +710,164 @@ class OrderByNode : public DeviceNode {
   bool done_ = false;
 };
 
+// ------------------------------------------------------------------------------------------
+// hashjoin: build / probe / materialize of HashJoinNode (acero/hash_join_node.cc:690-1100, swiss_join.cc) for equality keys.
+// Both inputs are accumulated (one H2D copy per column, or none for device batches), b2_hash_join yields the matching
+// row pairs, and every output column is one Take through them -- the reference's materialize step, on the device.
+// INNER / LEFT_* / RIGHT_* (the right variants swap the sides); a residual filter, JoinKeyCmp::IS and FULL_OUTER are refused.
+// ------------------------------------------------------------------------------------------
+class HashJoinNode : public DeviceNode {
+ public:
+  static Result<ac::ExecNode*> Make(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, const ac::ExecNodeOptions& options) {
+    const auto& o = static_cast<const ac::HashJoinNodeOptions&>(options);
+    if (inputs.size() != 2) return Status::Invalid("b200_hashjoin needs exactly two inputs");
+    if (o.left_keys.empty() || o.left_keys.size() != o.right_keys.size()) return Status::Invalid("b200_hashjoin: key lists of equal, non-zero size");
+    if (!(o.filter == cp::literal(true))) return Status::NotImplemented("b200_hashjoin: residual filter");
+    for (auto c : o.key_cmp)
+      if (c != ac::JoinKeyCmp::EQ) return Status::NotImplemented("b200_hashjoin: JoinKeyCmp::IS");
+    if (o.join_type == ac::JoinType::FULL_OUTER) return Status::NotImplemented("b200_hashjoin: FULL_OUTER");
+    ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
+    const auto ls = inputs[0]->output_schema(), rs = inputs[1]->output_schema();
+    std::vector<int> lkeys, rkeys, lout, rout;
+    for (size_t j = 0; j < o.left_keys.size(); ++j) {
+      ARROW_ASSIGN_OR_RAISE(int a, FieldIndex(o.left_keys[j], *ls));
+      ARROW_ASSIGN_OR_RAISE(int b, FieldIndex(o.right_keys[j], *rs));
+      if (!ls->field(a)->type()->Equals(*rs->field(b)->type()))
+        return Status::Invalid("Incompatible data types for corresponding join field keys: ", ls->field(a)->ToString(), " and ", rs->field(b)->ToString());
+      lkeys.push_back(a);
+      rkeys.push_back(b);
+    }
+    const bool semi_left = o.join_type == ac::JoinType::LEFT_SEMI || o.join_type == ac::JoinType::LEFT_ANTI;
+    const bool semi_right = o.join_type == ac::JoinType::RIGHT_SEMI || o.join_type == ac::JoinType::RIGHT_ANTI;
+    if (o.output_all) {  // hash_join_node.cc HashJoinSchema::Init: all fields of the sides the join type keeps
+      if (!semi_right) for (int i = 0; i < ls->num_fields(); ++i) lout.push_back(i);
+      if (!semi_left) for (int i = 0; i < rs->num_fields(); ++i) rout.push_back(i);
+    } else {
+      for (const auto& r : o.left_output) { ARROW_ASSIGN_OR_RAISE(int i, FieldIndex(r, *ls)); lout.push_back(i); }
+      for (const auto& r : o.right_output) { ARROW_ASSIGN_OR_RAISE(int i, FieldIndex(r, *rs)); rout.push_back(i); }
+      if ((semi_left && !rout.empty()) || (semi_right && !lout.empty()))
+        return Status::Invalid("semi / anti joins output the fields of one side only");
+    }
+    arrow::FieldVector fields;
+    for (int i : lout) fields.push_back(ls->field(i)->WithName(ls->field(i)->name() + o.output_suffix_for_left));
+    for (int i : rout) fields.push_back(rs->field(i)->WithName(rs->field(i)->name() + o.output_suffix_for_right));
+    auto node = std::make_unique<HashJoinNode>(plan, inputs, arrow::schema(std::move(fields)), rt);
+    node->type_ = o.join_type;
+    node->keys_[0] = std::move(lkeys);
+    node->keys_[1] = std::move(rkeys);
+    node->out_[0] = std::move(lout);
+    node->out_[1] = std::move(rout);
+    return plan->AddNode(std::move(node));
+  }
+  HashJoinNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
+      : DeviceNode(plan, std::move(inputs), std::move(s), rt) {}
+  const char* kind_name() const override { return "B200HashJoinNode"; }
+  // two inputs: pause / resume are forwarded to both
+  void PauseProducing(ac::ExecNode*, int32_t counter) override { for (auto* in : inputs_) in->PauseProducing(this, counter); }
+  void ResumeProducing(ac::ExecNode*, int32_t counter) override { for (auto* in : inputs_) in->ResumeProducing(this, counter); }
+
+  Status InputReceived(ac::ExecNode* input, cp::ExecBatch batch) override {
+    std::lock_guard<std::mutex> lk(mu_);
+    const int side = input == inputs_[0] ? 0 : 1;
+    if (pending_[side].empty()) pending_[side].resize(batch.values.size());
+    for (size_t i = 0; i < batch.values.size(); ++i) {
+      if (batch.values[i].is_scalar()) {
+        ARROW_ASSIGN_OR_RAISE(auto arr, arrow::MakeArrayFromScalar(*batch.values[i].scalar(), batch.length));
+        pending_[side][i].push_back(std::move(arr));
+      } else if (IsOnDevice(*batch.values[i].array())) {
+        ARROW_ASSIGN_OR_RAISE(auto hst, ToHost(*batch.values[i].array()));
+        pending_[side][i].push_back(arrow::MakeArray(hst));
+      } else {
+        pending_[side][i].push_back(batch.values[i].make_array());
+      }
+    }
+    rows_[side] += batch.length;
+    ++seen_[side];
+    return MaybeFinish();
+  }
+  Status InputFinished(ac::ExecNode* input, int total) override {
+    std::lock_guard<std::mutex> lk(mu_);
+    total_[input == inputs_[0] ? 0 : 1] = total;
+    return MaybeFinish();
+  }
+
+ private:
+  // the columns of one side on the device (one concatenation + one H2D copy per column)
+  Result<std::vector<std::shared_ptr<arrow::ArrayData>>> SideToDevice(int side) {
+    std::vector<std::shared_ptr<arrow::ArrayData>> cols;
+    const auto& schema = *inputs_[side]->output_schema();
+    for (int i = 0; i < schema.num_fields(); ++i) {
+      std::shared_ptr<arrow::Array> whole;
+      if (pending_[side].empty() || pending_[side][i].empty()) { ARROW_ASSIGN_OR_RAISE(whole, arrow::MakeEmptyArray(schema.field(i)->type())); }
+      else if (pending_[side][i].size() == 1) whole = pending_[side][i][0];
+      else { ARROW_ASSIGN_OR_RAISE(whole, arrow::Concatenate(pending_[side][i], plan_->query_context()->memory_pool())); }
+      ARROW_ASSIGN_OR_RAISE(auto d, ToDevice(*whole->data(), rt_->memory_manager()));
+      cols.push_back(std::move(d));
+    }
+    pending_[side].clear();
+    return cols;
+  }
+
+  Status MaybeFinish() {
+    for (int side = 0; side < 2; ++side)
+      if (total_[side] < 0 || seen_[side] < total_[side]) return Status::OK();
+    if (done_) return Status::OK();
+    done_ = true;
+    ARROW_ASSIGN_OR_RAISE(auto left, SideToDevice(0));
+    ARROW_ASSIGN_OR_RAISE(auto right, SideToDevice(1));
+    // RIGHT_* = the LEFT_* join of the swapped sides
+    const bool swap = type_ == ac::JoinType::RIGHT_SEMI || type_ == ac::JoinType::RIGHT_ANTI || type_ == ac::JoinType::RIGHT_OUTER;
+    int b2_type = B2_JOIN_INNER;
+    switch (type_) {
+      case ac::JoinType::LEFT_OUTER: case ac::JoinType::RIGHT_OUTER: b2_type = B2_JOIN_LEFT_OUTER; break;
+      case ac::JoinType::LEFT_SEMI: case ac::JoinType::RIGHT_SEMI: b2_type = B2_JOIN_LEFT_SEMI; break;
+      case ac::JoinType::LEFT_ANTI: case ac::JoinType::RIGHT_ANTI: b2_type = B2_JOIN_LEFT_ANTI; break;
+      default: break;
+    }
+    auto& probe = swap ? right : left;
+    auto& build = swap ? left : right;
+    std::vector<B2Array> pk(keys_[0].size()), bk(keys_[0].size());
+    for (size_t j = 0; j < pk.size(); ++j) {
+      ARROW_RETURN_NOT_OK(DataToB2(*probe[keys_[swap ? 1 : 0][j]], &pk[j]));
+      ARROW_RETURN_NOT_OK(DataToB2(*build[keys_[swap ? 0 : 1][j]], &bk[j]));
+    }
+    const bool pairs = b2_type == B2_JOIN_INNER || b2_type == B2_JOIN_LEFT_OUTER;
+    B2Array pi{}, bi{};
+    if (b2_hash_join(rt_->context(), pk.data(), bk.data(), static_cast<int>(pk.size()), b2_type, &pi, pairs ? &bi : nullptr, nullptr) != B2_OK)
+      return Status::UnknownError("b2_hash_join: ", b2_last_error());
+    Datum probe_idx(AdoptOutput(rt_, pi, arrow::uint32())), build_idx;
+    if (pairs) build_idx = Datum(AdoptOutput(rt_, bi, arrow::uint32()));
+    const Datum& left_idx = swap ? build_idx : probe_idx;
+    const Datum& right_idx = swap ? probe_idx : build_idx;
+    cp::ExecBatch out({}, probe_idx.length());
+    const bool keep_on_device = dynamic_cast<DeviceNode*>(output_) != nullptr;
+    auto gather = [&](const std::shared_ptr<arrow::ArrayData>& col, const Datum& idx) -> Status {
+      ARROW_ASSIGN_OR_RAISE(Datum t, cp::CallFunction("take", {Datum(col), idx}, nullptr, &ctx_));
+      if (keep_on_device) {
+        out.values.emplace_back(std::move(t));
+      } else {
+        ARROW_ASSIGN_OR_RAISE(auto h, ToHost(*t.array()));
+        out.values.emplace_back(std::move(h));
+      }
+      return Status::OK();
+    };
+    for (int i : out_[0]) ARROW_RETURN_NOT_OK(gather(left[i], left_idx));
+    for (int i : out_[1]) ARROW_RETURN_NOT_OK(gather(right[i], right_idx));
+    ARROW_RETURN_NOT_OK(output_->InputReceived(this, std::move(out)));
+    return output_->InputFinished(this, 1);
+  }
+
+  ac::JoinType type_ = ac::JoinType::INNER;
+  std::vector<int> keys_[2], out_[2];
+  std::vector<arrow::ArrayVector> pending_[2];
+  int64_t rows_[2] = {0, 0};
+  int seen_[2] = {0, 0}, total_[2] = {-1, -1};
+  bool done_ = false;
+};
+
 }  // namespace
 
-// Adds "b200_aggregate", "b200_filter", "b200_project", "b200_order_by" to the default ExecFactoryRegistry
+// Adds "b200_aggregate", "b200_filter", "b200_project", "b200_order_by", "b200_hashjoin" to the default ExecFactoryRegistry
 // (acero/exec_plan.h:355-368; the default registry refuses duplicates of the stock names,
 // acero/exec_plan.cc:1132-1143, hence the prefix).
 Status RegisterAceroNodes() {
@@ -723,6 +879,7 @@ Status RegisterAceroNodes() {
     if (st.ok()) st = reg->AddFactory("b200_filter", FilterNode::Make);
     if (st.ok()) st = reg->AddFactory("b200_project", ProjectNode::Make);
     if (st.ok()) st = reg->AddFactory("b200_order_by", OrderByNode::Make);
+    if (st.ok()) st = reg->AddFactory("b200_hashjoin", HashJoinNode::Make);
   });
   return st;
 }

@@ -775,6 +775,47 @@ int main(int argc, char** argv) {
                 << " groups; intermediate batches stayed on the device)" << std::endl;
     }
   }
+  // ---- (r2) hash join: stock "hashjoin" vs "b200_hashjoin" over the same two tables, rows compared sorted by every column
+  //      (the join's output order is unspecified in the reference) ----
+  {
+    namespace ac = arrow::acero;
+    const int64_t nl = 120000, nr = 9000;
+    auto lk = RandomNumeric<arrow::Int64Type>(nl, 0.05, 301, 0, 12000);
+    auto lv = RandomNumeric<arrow::DoubleType>(nl, 0.1, 302, 0, 100);
+    auto rk = RandomNumeric<arrow::Int64Type>(nr, 0.05, 303, 0, 12000);
+    auto rv = RandomNumeric<arrow::Int32Type>(nr, 0.1, 304, -50, 50);
+    auto ltab = arrow::Table::Make(arrow::schema({arrow::field("k", arrow::int64()), arrow::field("lv", arrow::float64())}), {lk, lv});
+    auto rtab = arrow::Table::Make(arrow::schema({arrow::field("k", arrow::int64()), arrow::field("rv", arrow::int32())}), {rk, rv});
+    auto sorted_all = [&](std::shared_ptr<arrow::Table> t) {
+      std::vector<cp::SortKey> keys;
+      for (const auto& f : t->schema()->fields()) keys.emplace_back(f->name());
+      auto idx = UNWRAP(cp::SortIndices(Datum(t), cp::SortOptions(keys), &h.cpu_ctx));
+      return UNWRAP(cp::Take(Datum(t), Datum(idx), cp::TakeOptions::Defaults(), &h.cpu_ctx)).table()->CombineChunks().ValueOrDie();
+    };
+    const std::pair<ac::JoinType, const char*> kinds[] = {{ac::JoinType::INNER, "INNER"}, {ac::JoinType::LEFT_OUTER, "LEFT_OUTER"},
+                                                          {ac::JoinType::LEFT_SEMI, "LEFT_SEMI"}, {ac::JoinType::LEFT_ANTI, "LEFT_ANTI"},
+                                                          {ac::JoinType::RIGHT_OUTER, "RIGHT_OUTER"}, {ac::JoinType::RIGHT_SEMI, "RIGHT_SEMI"}};
+    for (const auto& kind : kinds) {
+      auto run_join = [&](const std::string& factory) {
+        ac::Declaration left{"table_source", ac::TableSourceNodeOptions(ltab, 1 << 15)};
+        ac::Declaration right{"table_source", ac::TableSourceNodeOptions(rtab, 1 << 15)};
+        ac::HashJoinNodeOptions opts(kind.first, {"k"}, {"k"}, cp::literal(true), "_l", "_r");
+        ac::Declaration join{factory, {left, right}, opts};
+        return UNWRAP(ac::DeclarationToTable(std::move(join), /*use_threads=*/false));
+      };
+      auto want = run_join("hashjoin"), got = run_join("b200_hashjoin");
+      ++g_checks;
+      bool same = got->schema()->Equals(*want->schema()) && got->num_rows() == want->num_rows();
+      if (same && got->num_rows() > 0) same = sorted_all(got)->Equals(*sorted_all(want));
+      if (!same) {
+        std::cout << "FAIL b200_hashjoin " << kind.second << ": " << got->num_rows() << " rows vs " << want->num_rows() << "\n want schema "
+                  << want->schema()->ToString() << "\n got schema " << got->schema()->ToString() << std::endl;
+        return 1;
+      }
+      std::cout << "OK   b200_hashjoin == hashjoin (" << kind.second << ", " << got->num_rows() << " rows, " << got->num_columns() << " columns)" << std::endl;
+    }
+  }
+
   // ---- (r2) C Device STREAM ingest: a producer's ArrowDeviceArrayStream of device record batches -> our reader -> an
   //      Acero plan (record_batch_reader_source -> b200_aggregate) without touching host memory ----
   {

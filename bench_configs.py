@@ -3,6 +3,7 @@
   c1  Filter(int64, bool mask)            1B rows, values null_p 0.1, mask non-null, s = 0.5
   c3  group-by sum+count, int64 key/value 1B rows, 10M groups (fused table and Grouper+aggregators)
   c3u group-by / dictionary_encode with a large_utf8 key   500M strings from 1M distinct words (not in the default --only list)
+  join inner hash join: n/2 probe rows against 10M unique build keys (not in the default --only list)
   c4  SortIndices int64 + validity        1B rows (wide range) and narrow range [0, 4095]
   f1  dictionary_encode / value_counts of an int64 column (1M distinct values), 500M rows
   c5  large_utf8 Filter                   500M strings, 0-32 B, null_p 0.1, s = 0.5  (+ dictionary Take)
@@ -40,6 +41,15 @@ def timed(stream, fn, reps, warmup=2):
     b.record(stream)
     torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
+
+
+class _Cai:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _cai(ptr, n, typestr):
+    return _Cai(ptr, n, typestr)
 
 
 def report(name, n, ms, alg_bytes, extra=None):
@@ -145,6 +155,27 @@ def main():
         ms = timed(stream, lambda: bc.dictionary_encode(skeys), max(1, args.reps - 1), warmup=1)
         report("f1 dictionary_encode large_utf8 (1M distinct words)", m, ms, m * (8 + L + 4) + vocab * (8 + L), {"mean_len": L})
         del skeys, vals, kid, offs, data, vals_t, vvalid_t
+
+    if "join" in only:
+        # inner hash join: n/2 probe rows (int64 keys, uniform over 1.25x the build keys, so 80 % match) against 10M unique build keys
+        m = n // 2
+        nb = 10_000_000 if m >= 100_000_000 else max(1000, m // 50)
+        build_t = torch.randperm(int(nb * 1.25), device="cuda", generator=gen)[:nb].to(torch.int64)
+        probe_t = torch.randint(0, int(nb * 1.25), (m,), dtype=torch.int64, device="cuda", generator=gen)
+        build = DeviceArray.from_pointers(ctx, pa.int64(), nb, build_t.data_ptr())
+        probe = DeviceArray.from_pointers(ctx, pa.int64(), m, probe_t.data_ptr())
+        ms = timed(stream, lambda: bc.hash_join_indices([probe], [build], "inner"), max(1, args.reps - 1), warmup=1)
+        li, ri = bc.hash_join_indices([probe], [build], "inner")
+        pairs = len(li)
+        # parity: every emitted pair has equal keys, and the pair count equals the number of probe keys present in the build side
+        lt = torch.as_tensor(_cai(li.buffers[1].ptr, pairs, "<u4"), device="cuda").to(torch.int64)
+        rt = torch.as_tensor(_cai(ri.buffers[1].ptr, pairs, "<u4"), device="cuda").to(torch.int64)
+        present = torch.zeros(int(nb * 1.25), dtype=torch.bool, device="cuda")
+        present[build_t] = True
+        ok = bool((probe_t[lt] == build_t[rt]).all().item()) and pairs == int(present[probe_t].sum().item())
+        report("join inner: 10M unique int64 build keys, probe keys 80 % matching", m, ms, m * 8 + nb * 8 + pairs * 8,
+               {"build_rows": nb, "pairs": pairs, "parity_ok": ok})
+        del build, probe, build_t, probe_t, li, ri, lt, rt, present
 
     if "c4" in only:
         m = min(n, (1 << 30) - 1)
