@@ -59,8 +59,9 @@ Result<int> FieldIndex(const arrow::FieldRef& ref, const arrow::Schema& schema) 
 // common plumbing: one input, forwards pause/resume, counts batches
 class DeviceNode : public ac::ExecNode {
  public:
-  DeviceNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> schema, Runtime* rt)
-      : ac::ExecNode(plan, std::move(inputs), {"target"}, std::move(schema)),
+  DeviceNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> schema, Runtime* rt,
+             std::vector<std::string> input_labels = {"target"})
+      : ac::ExecNode(plan, std::move(inputs), std::move(input_labels), std::move(schema)),
         rt_(rt),
         ctx_(plan->query_context()->memory_pool(), nullptr, rt->registry()) {}
   Status StartProducing() override { return Status::OK(); }
@@ -760,7 +761,7 @@ class HashJoinNode : public DeviceNode {
     return plan->AddNode(std::move(node));
   }
   HashJoinNode(ac::ExecPlan* plan, std::vector<ac::ExecNode*> inputs, std::shared_ptr<arrow::Schema> s, Runtime* rt)
-      : DeviceNode(plan, std::move(inputs), std::move(s), rt) {}
+      : DeviceNode(plan, std::move(inputs), std::move(s), rt, {"left", "right"}) {}
   const char* kind_name() const override { return "B200HashJoinNode"; }
   // two inputs: pause / resume are forwarded to both
   void PauseProducing(ac::ExecNode*, int32_t counter) override { for (auto* in : inputs_) in->PauseProducing(this, counter); }

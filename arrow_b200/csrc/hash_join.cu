@@ -37,6 +37,7 @@ struct Out {  // a C-ABI output whose buffers go back to the pool unless handed 
 };
 
 constexpr int kScanTile = 4096;
+constexpr uint32_t kNoMatch = 0xffffffffu;
 
 // per-row output count of the probe side -> counts[i] (uint32) and the sum per 4096-row tile
 //   matched rows emit cnt[id]; unmatched rows emit 1 when `outer` (the null-extended row) else 0
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) emit_pairs_kernel(const uint32_t* __re
                                                             const unsigned long long* __restrict__ cnt, const int64_t* __restrict__ run_start,
                                                             const uint32_t* __restrict__ build_rows, const int64_t* __restrict__ row_off,
                                                             int64_t n, uint32_t* __restrict__ out_left, uint32_t* __restrict__ out_right,
-                                                            uint32_t* out_right_validity) {
+                                                            bool outer) {
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
     const int64_t base = row_off[i];
     unsigned long long c = 0;
@@ -155,9 +156,9 @@ __global__ void __launch_bounds__(kBlock) emit_pairs_kernel(const uint32_t* __re
       c = cnt[g];
     }
     if (c == 0) {
-      if (out_right_validity) {  // LEFT OUTER: the null-extended row (validity bit stays 0)
+      if (outer) {  // LEFT OUTER: the null-extended row, marked for right_validity_kernel (no row number reaches 2^32 - 16)
         out_left[base] = static_cast<uint32_t>(i);
-        out_right[base] = 0;
+        out_right[base] = kNoMatch;
       }
       continue;
     }
@@ -165,9 +166,30 @@ __global__ void __launch_bounds__(kBlock) emit_pairs_kernel(const uint32_t* __re
     for (unsigned long long k = 0; k < c; ++k) {
       out_left[base + k] = static_cast<uint32_t>(i);
       out_right[base + k] = build_rows[r0 + k];
-      if (out_right_validity) atomicOr(out_right_validity + ((base + k) >> 5), 1u << ((base + k) & 31));
     }
   }
+}
+
+// LEFT OUTER: validity of the right indices = "not the marker"; the marker is replaced by 0; one ballot per 32 pairs
+__global__ void __launch_bounds__(kBlock) right_validity_kernel(uint32_t* __restrict__ out_right, int64_t n, uint32_t* __restrict__ validity,
+                                                                int64_t* valid_count) {
+  const int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    const int64_t i = (w << 5) + lane_id();
+    bool ok = false;
+    if (i < n) {
+      ok = out_right[i] != kNoMatch;
+      if (!ok) out_right[i] = 0;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, ok);
+    if (lane_id() == 0) {
+      validity[w] = word;
+      local += __popc(word);
+    }
+  }
+  const int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(valid_count), (unsigned long long)s);
 }
 
 // bit i = probe row i has (SEMI) / has no (ANTI) match
@@ -360,12 +382,13 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
   if (total > 0) {
     emit_pairs_kernel<<<grid_for(nl, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, d_cnt, run_start.as<int64_t>(),
                                                                           build_rows.as<uint32_t>(), row_off.as<int64_t>(), nl,
-                                                                          ol.as<uint32_t>(), orr.as<uint32_t>(), outer ? obits.as<uint32_t>() : nullptr);
+                                                                          ol.as<uint32_t>(), orr.as<uint32_t>(), outer);
     B2_LAUNCHED();
     if (outer) {
       ScalarSlot vs(ctx);
       B2_RETURN_NOT_OK(vs.zero(s));
-      B2_RETURN_NOT_OK(launch_bitmap_and(obits.ptr, 0, nullptr, 0, total, nullptr, vs.dev(), s));
+      right_validity_kernel<<<grid_for(total, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(orr.as<uint32_t>(), total, obits.as<uint32_t>(), vs.dev());
+      B2_LAUNCHED();
       B2_RETURN_NOT_OK(vs.fetch(s));
       right_nulls = total - vs.host()[0];
     }
