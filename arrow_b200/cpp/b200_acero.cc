@@ -749,9 +749,21 @@ class HashJoinNode : public DeviceNode {
       if ((semi_left && !rout.empty()) || (semi_right && !lout.empty()))
         return Status::Invalid("semi / anti joins output the fields of one side only");
     }
+    // the suffixes only disambiguate names that both sides output (HashJoinSchema::MakeOutputSchema, hash_join_node.cc:388-433)
+    auto collides = [](const std::string& name, const arrow::Schema& other, const std::vector<int>& other_out) {
+      for (int i : other_out)
+        if (other.field(i)->name() == name) return true;
+      return false;
+    };
     arrow::FieldVector fields;
-    for (int i : lout) fields.push_back(ls->field(i)->WithName(ls->field(i)->name() + o.output_suffix_for_left));
-    for (int i : rout) fields.push_back(rs->field(i)->WithName(rs->field(i)->name() + o.output_suffix_for_right));
+    for (int i : lout) {
+      const auto& f = ls->field(i);
+      fields.push_back(collides(f->name(), *rs, rout) ? f->WithName(f->name() + o.output_suffix_for_left) : f);
+    }
+    for (int i : rout) {
+      const auto& f = rs->field(i);
+      fields.push_back(collides(f->name(), *ls, lout) ? f->WithName(f->name() + o.output_suffix_for_right) : f);
+    }
     auto node = std::make_unique<HashJoinNode>(plan, inputs, arrow::schema(std::move(fields)), rt);
     node->type_ = o.join_type;
     node->keys_[0] = std::move(lkeys);

@@ -1,4 +1,4 @@
-// vector_hash.cu -- unique / value_counts / dictionary_encode over one fixed-width column.
+// vector_hash.cu -- unique / value_counts / dictionary_encode over one fixed-width or utf8 / binary column.
 //
 // Replaces:
 //   UniqueAction / ValueCountsAction / DictEncodeAction + RegularHashKernel

@@ -381,7 +381,7 @@ typedef struct B2ReduceResult {
 B2_API int b2_reduce(B2Context* ctx, const B2Array* values, B2ReduceResult* out, void* stream);
 
 /* ---------------------------------------------------------------------------
- * unique / value_counts / dictionary_encode over one fixed-width column.
+ * unique / value_counts / dictionary_encode over one fixed-width numeric or utf8 / binary column.
  * Replaces UniqueAction / ValueCountsAction / DictEncodeAction + RegularHashKernel
  * (compute/kernels/vector_hash.cc:65-235,236-470; registration :782-830;
  * DictionaryEncodeOptions compute/api_vector.h:66-82).
