@@ -597,6 +597,20 @@ def value_counts_to_struct(values: DeviceArray, counts: DeviceArray) -> pa.Struc
     return pa.StructArray.from_arrays([values.to_arrow(), counts.to_arrow()], names=["values", "counts"])
 
 
+def count_distinct(arr: DeviceArray, mode: str = "only_valid") -> pa.Scalar:
+    """count_distinct (CountDistinctImpl, kernels/aggregate_basic.cc:141-230; CountOptions api_aggregate.h:64-78): the size of
+    the memo table = the number of uniques, with the null entry counted under only_null / all."""
+    u = unique(arr)
+    has_null = 1 if u.null_count > 0 else 0
+    if mode == "only_valid":
+        return pa.scalar(len(u) - has_null, pa.int64())
+    if mode == "only_null":
+        return pa.scalar(has_null, pa.int64())
+    if mode == "all":
+        return pa.scalar(len(u), pa.int64())
+    raise ValueError(f'"{mode}" is not a valid count mode')
+
+
 def dictionary_encode(arr: DeviceArray, null_encoding="mask") -> DeviceArray:
     """dictionary_encode: int32 indices + dictionary (vector_hash.cc:173-232,826;
     DictionaryEncodeOptions api_vector.h:66-82)."""
@@ -658,13 +672,14 @@ class Grouper:
         check(self.ctx.lib.b2_grouper_reset(self.handle))
 
 
-JOIN_TYPES = {"inner": 0, "left outer": 1, "left semi": 2, "left anti": 3}
+JOIN_TYPES = {"inner": 0, "left outer": 1, "left semi": 2, "left anti": 3, "full outer": 4}
 
 
 def hash_join_indices(left_keys: Sequence[DeviceArray], right_keys: Sequence[DeviceArray], join_type: str = "inner"):
     """The matching row pairs of an equi-join (the build / probe / match core of acero's HashJoinNode, hash_join_node.cc;
     join types as pyarrow.Table.join spells them).  Returns (left_indices, right_indices) as uint32 DeviceArrays -- for
-    "left outer" right_indices is null where a left row found no match, for "left semi" / "left anti" right_indices is None.
+    "left outer" right_indices is null where a left row found no match ("full outer" appends the unmatched right rows with a
+    null left index), for "left semi" / "left anti" right_indices is None.
     A null key matches nothing.  Gather the payload columns with take()."""
     if isinstance(left_keys, DeviceArray):
         left_keys = [left_keys]
@@ -681,7 +696,7 @@ def hash_join_indices(left_keys: Sequence[DeviceArray], right_keys: Sequence[Dev
     cl = (cabi.B2Array * len(left_keys))(*[k._c() for k in left_keys])
     cr = (cabi.B2Array * len(right_keys))(*[k._c() for k in right_keys])
     ol, orr = cabi.B2Array(), cabi.B2Array()
-    pairs = JOIN_TYPES[join_type] < 2
+    pairs = JOIN_TYPES[join_type] in (0, 1, 4)
     check(ctx.lib.b2_hash_join(ctx.handle, cl, cr, len(left_keys), JOIN_TYPES[join_type], C.byref(ol), C.byref(orr) if pairs else None,
                                ctx.stream))
     return _out(ctx, ol, pa.uint32()), (_out(ctx, orr, pa.uint32()) if pairs else None)
@@ -813,7 +828,7 @@ _REGISTRY = {
     "multiply_checked": multiply_checked, "divide_checked": divide_checked,
     "equal": equal, "not_equal": not_equal, "greater": greater, "greater_equal": greater_equal,
     "less": less, "less_equal": less_equal,
-    "unique": unique, "value_counts": value_counts, "dictionary_encode": dictionary_encode,
+    "unique": unique, "value_counts": value_counts, "dictionary_encode": dictionary_encode, "count_distinct": count_distinct,
     "sum": sum, "mean": mean, "min_max": min_max, "min": min, "max": max, "count": count,
     "and": and_, "or": or_, "xor": xor, "and_not": and_not, "and_kleene": and_kleene, "or_kleene": or_kleene,
     "and_not_kleene": and_not_kleene, "invert": invert, "is_valid": is_valid, "is_null": is_null,
@@ -853,7 +868,7 @@ def call_function(name: str, args: Sequence, options=None):
         return fn(*args, null_encoding=getattr(options, "null_encoding", options))
     if name in ("sum", "mean", "min_max", "min", "max"):
         return fn(*args, skip_nulls=options.skip_nulls, min_count=options.min_count)
-    if name == "count":
+    if name in ("count", "count_distinct"):
         return fn(*args, mode=getattr(options, "mode", options))
     if name == "is_null":
         return fn(*args, nan_is_null=getattr(options, "nan_is_null", False))

@@ -715,7 +715,7 @@ class OrderByNode : public DeviceNode {
 // hashjoin: build / probe / materialize of HashJoinNode (acero/hash_join_node.cc:690-1100, swiss_join.cc) for equality keys.
 // Both inputs are accumulated (one H2D copy per column, or none for device batches), b2_hash_join yields the matching
 // row pairs, and every output column is one Take through them -- the reference's materialize step, on the device.
-// INNER / LEFT_* / RIGHT_* (the right variants swap the sides); a residual filter, JoinKeyCmp::IS and FULL_OUTER are refused.
+// All eight join types (the RIGHT variants swap the sides); a residual filter and JoinKeyCmp::IS are refused.
 // ------------------------------------------------------------------------------------------
 class HashJoinNode : public DeviceNode {
  public:
@@ -726,7 +726,6 @@ class HashJoinNode : public DeviceNode {
     if (!(o.filter == cp::literal(true))) return Status::NotImplemented("b200_hashjoin: residual filter");
     for (auto c : o.key_cmp)
       if (c != ac::JoinKeyCmp::EQ) return Status::NotImplemented("b200_hashjoin: JoinKeyCmp::IS");
-    if (o.join_type == ac::JoinType::FULL_OUTER) return Status::NotImplemented("b200_hashjoin: FULL_OUTER");
     ARROW_ASSIGN_OR_RAISE(Runtime * rt, Runtime::Get(0));
     const auto ls = inputs[0]->output_schema(), rs = inputs[1]->output_schema();
     std::vector<int> lkeys, rkeys, lout, rout;
@@ -835,6 +834,7 @@ class HashJoinNode : public DeviceNode {
       case ac::JoinType::LEFT_OUTER: case ac::JoinType::RIGHT_OUTER: b2_type = B2_JOIN_LEFT_OUTER; break;
       case ac::JoinType::LEFT_SEMI: case ac::JoinType::RIGHT_SEMI: b2_type = B2_JOIN_LEFT_SEMI; break;
       case ac::JoinType::LEFT_ANTI: case ac::JoinType::RIGHT_ANTI: b2_type = B2_JOIN_LEFT_ANTI; break;
+      case ac::JoinType::FULL_OUTER: b2_type = B2_JOIN_FULL_OUTER; break;
       default: break;
     }
     auto& probe = swap ? right : left;
@@ -844,7 +844,7 @@ class HashJoinNode : public DeviceNode {
       ARROW_RETURN_NOT_OK(DataToB2(*probe[keys_[swap ? 1 : 0][j]], &pk[j]));
       ARROW_RETURN_NOT_OK(DataToB2(*build[keys_[swap ? 0 : 1][j]], &bk[j]));
     }
-    const bool pairs = b2_type == B2_JOIN_INNER || b2_type == B2_JOIN_LEFT_OUTER;
+    const bool pairs = b2_type == B2_JOIN_INNER || b2_type == B2_JOIN_LEFT_OUTER || b2_type == B2_JOIN_FULL_OUTER;
     B2Array pi{}, bi{};
     if (b2_hash_join(rt_->context(), pk.data(), bk.data(), static_cast<int>(pk.size()), b2_type, &pi, pairs ? &bi : nullptr, nullptr) != B2_OK)
       return Status::UnknownError("b2_hash_join: ", b2_last_error());

@@ -2,8 +2,8 @@
 //
 // Replaces the match / materialize core of HashJoinNode (acero/hash_join_node.cc, acero/swiss_join.cc: build a SwissTable
 // over the build side's row-encoded keys, probe it with the other side, emit row-id pairs that the node then uses to Take
-// the payload columns) for INNER / LEFT OUTER / LEFT SEMI / LEFT ANTI joins with equality keys (JoinKeyCmp::EQ,
-// acero/options.h:384-392: a null key matches nothing).
+// the payload columns) for INNER / LEFT OUTER / FULL OUTER / LEFT SEMI / LEFT ANTI joins with equality keys (JoinKeyCmp::EQ,
+// acero/options.h:384-392: a null key matches nothing); the RIGHT variants are the same joins with the sides swapped.
 //
 // B200 design: the join is the Grouper plus three streaming passes -- no second hash table and no per-row chains.
 //   build : Grouper::Consume on the RIGHT keys gives every right row a dense group id; a per-id COUNT (only rows whose
@@ -208,6 +208,57 @@ __global__ void __launch_bounds__(kBlock) semi_mask_kernel(const uint32_t* __res
   }
 }
 
+// FULL OUTER: matched[g] = 1 for every group some probe row hits (idempotent byte stores, no atomics)
+__global__ void __launch_bounds__(kBlock) mark_matched_kernel(const uint32_t* __restrict__ ids, BitmapReader ids_valid, BitmapReader keys_valid,
+                                                              int64_t n, uint8_t* matched) {
+  for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    if (ids_valid.bit(i) && keys_valid.bit(i)) matched[ids[i]] = 1;
+}
+
+// FULL OUTER: bit r = build row r found no partner (its key has a null, or no probe row hit its group)
+__global__ void __launch_bounds__(kBlock) unmatched_build_kernel(const uint32_t* __restrict__ ids, BitmapReader keys_valid, const uint8_t* __restrict__ matched,
+                                                                 int64_t n, uint32_t* __restrict__ mask) {
+  const int64_t nw = (n + 31) >> 5;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    const int64_t i = (w << 5) + lane_id();
+    const bool lonely = i < n && !(keys_valid.bit(i) && matched[ids[i]]);
+    const unsigned word = __ballot_sync(0xffffffffu, lonely);
+    if (lane_id() == 0) mask[w] = word;
+  }
+}
+
+// FULL OUTER: the tail of the result = (null, unmatched build row); validity of both index columns over the whole result
+__global__ void __launch_bounds__(kBlock) full_outer_finish_kernel(uint32_t* __restrict__ out_left, uint32_t* __restrict__ out_right,
+                                                                   const uint32_t* __restrict__ lonely_rows, int64_t head, int64_t n,
+                                                                   uint32_t* __restrict__ left_validity, uint32_t* __restrict__ right_validity,
+                                                                   int64_t* right_valid_count) {
+  const int64_t nw = (n + 31) >> 5;
+  int64_t local = 0;
+  for (int64_t w = (blockIdx.x * (int64_t)kBlock + threadIdx.x) >> 5; w < nw; w += ((int64_t)gridDim.x * kBlock) >> 5) {
+    const int64_t i = (w << 5) + lane_id();
+    bool lv = false, rv = false;
+    if (i < n) {
+      if (i < head) {
+        lv = true;
+        rv = out_right[i] != kNoMatch;
+        if (!rv) out_right[i] = 0;
+      } else {
+        out_left[i] = 0;
+        out_right[i] = lonely_rows[i - head];
+        rv = true;
+      }
+    }
+    const unsigned lw = __ballot_sync(0xffffffffu, lv), rw = __ballot_sync(0xffffffffu, rv);
+    if (lane_id() == 0) {
+      left_validity[w] = lw;
+      right_validity[w] = rw;
+      local += __popc(rw);
+    }
+  }
+  const int64_t s = block_sum<kBlock>(local);
+  if (threadIdx.x == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(right_valid_count), (unsigned long long)s);
+}
+
 // AND of the validity bitmaps of all key columns, re-based to bit 0; *out = NULL when no column has nulls
 int keys_validity(B2Context* ctx, const B2Array* keys, int n_keys, int64_t n, Temp* bits, const void** out, cudaStream_t s) {
   *out = nullptr;
@@ -245,8 +296,9 @@ using namespace b2;
 extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Array* right_keys, int n_keys, int join_type,
                             B2Array* out_left, B2Array* out_right, void* stream) {
   if (!ctx || !left_keys || !right_keys || !out_left) return set_error(B2_INVALID, "b2_hash_join: null argument");
-  if (join_type < B2_JOIN_INNER || join_type > B2_JOIN_LEFT_ANTI) return set_error(B2_NOT_IMPLEMENTED, "b2_hash_join: join type %d", join_type);
-  const bool pairs = join_type == B2_JOIN_INNER || join_type == B2_JOIN_LEFT_OUTER;
+  if (join_type < B2_JOIN_INNER || join_type > B2_JOIN_FULL_OUTER) return set_error(B2_NOT_IMPLEMENTED, "b2_hash_join: join type %d", join_type);
+  const bool full = join_type == B2_JOIN_FULL_OUTER;
+  const bool pairs = join_type == B2_JOIN_INNER || join_type == B2_JOIN_LEFT_OUTER || full;
   if (pairs && !out_right) return set_error(B2_INVALID, "b2_hash_join: this join type returns right indices too");
   if (n_keys < 1) return set_error(B2_INVALID, "b2_hash_join: at least one key column");
   const int64_t nl = left_keys[0].length, nr = right_keys[0].length;
@@ -351,7 +403,7 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
   }
 
   // ---- emit ----
-  const bool outer = join_type == B2_JOIN_LEFT_OUTER;
+  const bool outer = join_type == B2_JOIN_LEFT_OUTER || full;
   const int64_t l_tiles = (nl + kScanTile - 1) / kScanTile;
   Temp counts(ctx, s), l_sums(ctx, s), l_offs(ctx, s), row_off(ctx, s);
   B2_RETURN_NOT_OK(counts.alloc(sizeof(uint32_t) * (size_t)(nl ? nl : 1)));
@@ -371,7 +423,40 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
     total = slot.host()[0];
   }
   if (total > 0xfffffff0ll * 16) return set_error(B2_CAPACITY_ERROR, "b2_hash_join: %lld result pairs; join the sides in chunks", (long long)total);
-  Temp ol(ctx, s), orr(ctx, s), obits(ctx, s);
+  // FULL OUTER: the build rows nobody matched follow the probe side's pairs
+  Out lonely(ctx, s);
+  int64_t n_lonely = 0;
+  if (full && nr > 0) {
+    Temp matched(ctx, s), lmask(ctx, s);
+    B2_RETURN_NOT_OK(matched.alloc(groups ? groups : 1));
+    B2_CUDA(cudaMemsetAsync(matched.ptr, 0, groups ? groups : 1, s));
+    if (nl > 0) {
+      mark_matched_kernel<<<grid_for(nl, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, nl, matched.as<uint8_t>());
+      B2_LAUNCHED();
+    }
+    B2_RETURN_NOT_OK(lmask.alloc(bitmap_alloc_bytes(nr)));
+    B2_CUDA(cudaMemsetAsync(lmask.ptr, 0, bitmap_alloc_bytes(nr), s));
+    unmatched_build_kernel<<<grid_for(nr, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(static_cast<const uint32_t*>(rids.a.data), BitmapReader(rvalid, 0, nr),
+                                                                            matched.as<uint8_t>(), nr, lmask.as<uint32_t>());
+    B2_LAUNCHED();
+    B2Array m{};
+    m.type = B2_BOOL;
+    m.data = lmask.ptr;
+    m.length = nr;
+    Out rows(ctx, s);
+    B2_RETURN_NOT_OK(b2_filter_indices(ctx, &m, 0, &rows.a, s));
+    if (rows.a.type == B2_UINT32 || rows.a.length == 0) {
+      lonely.a = rows.a;
+      rows.a = B2Array{};
+    } else {
+      B2CastOptions wide{B2_UINT32, 1, 1, 0};
+      B2_RETURN_NOT_OK(b2_cast_numeric(ctx, &rows.a, &wide, &lonely.a, s));
+    }
+    n_lonely = lonely.a.length;
+  }
+  const int64_t head = total;
+  total += n_lonely;
+  Temp ol(ctx, s), orr(ctx, s), obits(ctx, s), lbits(ctx, s);
   B2_RETURN_NOT_OK(ol.alloc(sizeof(uint32_t) * (size_t)(total ? total : 1)));
   B2_RETURN_NOT_OK(orr.alloc(sizeof(uint32_t) * (size_t)(total ? total : 1)));
   int64_t right_nulls = 0;
@@ -379,19 +464,34 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
     B2_RETURN_NOT_OK(obits.alloc(bitmap_alloc_bytes(total)));
     B2_CUDA(cudaMemsetAsync(obits.ptr, 0, bitmap_alloc_bytes(total), s));
   }
-  if (total > 0) {
+  if (full) {
+    B2_RETURN_NOT_OK(lbits.alloc(bitmap_alloc_bytes(total)));
+    B2_CUDA(cudaMemsetAsync(lbits.ptr, 0, bitmap_alloc_bytes(total), s));
+  }
+  if (head > 0) {
     emit_pairs_kernel<<<grid_for(nl, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, d_cnt, run_start.as<int64_t>(),
                                                                           build_rows.as<uint32_t>(), row_off.as<int64_t>(), nl,
                                                                           ol.as<uint32_t>(), orr.as<uint32_t>(), outer);
     B2_LAUNCHED();
-    if (outer) {
-      ScalarSlot vs(ctx);
-      B2_RETURN_NOT_OK(vs.zero(s));
+  }
+  if (outer && total > 0) {
+    ScalarSlot vs(ctx);
+    B2_RETURN_NOT_OK(vs.zero(s));
+    if (full) {
+      full_outer_finish_kernel<<<grid_for(total, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(
+          ol.as<uint32_t>(), orr.as<uint32_t>(), static_cast<const uint32_t*>(lonely.a.data), head, total, lbits.as<uint32_t>(),
+          obits.as<uint32_t>(), vs.dev());
+    } else {
       right_validity_kernel<<<grid_for(total, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(orr.as<uint32_t>(), total, obits.as<uint32_t>(), vs.dev());
-      B2_LAUNCHED();
-      B2_RETURN_NOT_OK(vs.fetch(s));
-      right_nulls = total - vs.host()[0];
     }
+    B2_LAUNCHED();
+    B2_RETURN_NOT_OK(vs.fetch(s));
+    right_nulls = total - vs.host()[0];
+  }
+  if (full) {
+    fill_out(out_left, B2_UINT32, total, n_lonely, n_lonely ? lbits.release() : nullptr, ol.release());
+    fill_out(out_right, B2_UINT32, total, right_nulls, right_nulls ? obits.release() : nullptr, orr.release());
+    return B2_OK;
   }
   fill_out(out_left, B2_UINT32, total, 0, nullptr, ol.release());
   fill_out(out_right, B2_UINT32, total, right_nulls, right_nulls ? obits.release() : nullptr, orr.release());

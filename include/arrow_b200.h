@@ -326,11 +326,18 @@ B2_API int b2_select_k(B2Context* ctx, const B2Array* values, int64_t k, int ord
  * matches nothing).  left_keys / right_keys: n_keys columns each, pairwise of equal type (anything the Grouper takes).
  *   INNER       out_left[k], out_right[k] (B2_UINT32, no nulls) = the k-th matching pair
  *   LEFT_OUTER  as INNER plus one pair per unmatched left row whose out_right slot is null
+ *   FULL_OUTER  as LEFT_OUTER, followed by one pair per unmatched right row whose out_left slot is null
  *   LEFT_SEMI / LEFT_ANTI   out_left = the left rows with / without a match (out_right may be NULL)
  * Pairs come in left-row order, the matches of one left row in right-row order (the reference's order is unspecified).
  * The caller gathers the payload columns with b2_take, as HashJoinNode's materialize step does.
  * ------------------------------------------------------------------------- */
-typedef enum B2JoinType { B2_JOIN_INNER = 0, B2_JOIN_LEFT_OUTER = 1, B2_JOIN_LEFT_SEMI = 2, B2_JOIN_LEFT_ANTI = 3 } B2JoinType;
+typedef enum B2JoinType {
+  B2_JOIN_INNER = 0,
+  B2_JOIN_LEFT_OUTER = 1,
+  B2_JOIN_LEFT_SEMI = 2,
+  B2_JOIN_LEFT_ANTI = 3,
+  B2_JOIN_FULL_OUTER = 4
+} B2JoinType;
 B2_API int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Array* right_keys, int n_keys, int join_type,
                         B2Array* out_left, B2Array* out_right, void* stream);
 

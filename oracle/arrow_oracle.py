@@ -740,7 +740,7 @@ def hash_join_indices(left_keys, right_keys, join_type: str = "inner"):
         if join_type == "inner":
             left += [i] * len(hits)
             right += hits
-        elif join_type == "left outer":
+        elif join_type in ("left outer", "full outer"):
             left += [i] * max(1, len(hits))
             right += hits if hits else [None]
         elif join_type == "left semi":
@@ -749,6 +749,11 @@ def hash_join_indices(left_keys, right_keys, join_type: str = "inner"):
             left += [] if hits else [i]
         else:
             raise ValueError(join_type)
+    if join_type == "full outer":  # then the right rows nobody matched (null key, or no equal left key), in row order
+        hit_right = {j for j in right if j is not None}
+        lonely = [j for j in range(len(rrows)) if j not in hit_right]
+        left += [None] * len(lonely)
+        right += lonely
     li = pa.array(left, pa.uint32())
     if join_type in ("left semi", "left anti"):
         return li, None

@@ -143,6 +143,8 @@ def test_vector_hash_strings(ctx, t):
             want = pc.dictionary_encode(arr, enc)
             assert got.equals(want), f"{t} {enc} n={n}"
             assert got.equals(ora.dictionary_encode(arr, enc))
+        for mode in ("only_valid", "only_null", "all"):
+            assert bc.count_distinct(d, mode).as_py() == pc.count_distinct(arr, mode=mode).as_py()
 
 
 def test_group_by_string_and_wide_keys(ctx):

@@ -12,7 +12,7 @@ from tests.test_gpu_grouper_wide import words
 from tests.util import SEED, random_array
 
 pytestmark = pytest.mark.gpu
-JOIN_TYPES = ["inner", "left outer", "left semi", "left anti"]
+JOIN_TYPES = ["inner", "left outer", "left semi", "left anti", "full outer"]
 
 
 def dev(arr, ctx):
@@ -25,7 +25,7 @@ def reference_pairs(left_keys, right_keys, join_type):
     lt = pa.table(list(left_keys) + [pa.array(np.arange(len(left_keys[0]), dtype=np.int64))], names=names + ["lrow"])
     rt = pa.table(list(right_keys) + [pa.array(np.arange(len(right_keys[0]), dtype=np.int64))], names=names + ["rrow"])
     out = lt.join(rt, keys=names, join_type=join_type, use_threads=False)
-    lrow = out["lrow"].to_pylist()
+    lrow = [(-1 if l is None else l) for l in out["lrow"].to_pylist()]
     rrow = out["rrow"].to_pylist() if "rrow" in out.column_names else [None] * len(lrow)
     return sorted(zip(lrow, [(-1 if r is None else r) for r in rrow]))
 
@@ -40,7 +40,9 @@ def check(ctx, left_keys, right_keys, join_type):
     else:
         assert got_r.to_arrow().equals(want_r), join_type
         assert got_r.null_count == want_r.null_count
-        mine = sorted(zip(got_l.to_arrow().to_pylist(), [(-1 if r is None else r) for r in got_r.to_arrow().to_pylist()]))
+        assert got_l.null_count == want_l.null_count
+        mine = sorted(zip([(-1 if l is None else l) for l in got_l.to_arrow().to_pylist()],
+                          [(-1 if r is None else r) for r in got_r.to_arrow().to_pylist()]))
     ref = reference_pairs(left_keys, right_keys, join_type)
     if join_type in ("left semi", "left anti"):
         ref = sorted((l, -1) for l, _ in ref)
