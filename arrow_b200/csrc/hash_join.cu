@@ -39,25 +39,36 @@ struct Out {  // a C-ABI output whose buffers go back to the pool unless handed 
 constexpr int kScanTile = 4096;
 constexpr uint32_t kNoMatch = 0xffffffffu;
 
-// per-row output count of the probe side -> counts[i] (uint32) and the sum per 4096-row tile
-//   matched rows emit cnt[id]; unmatched rows emit 1 when `outer` (the null-extended row) else 0
+// per-row MATCH count of the probe side -> counts[i] (uint32; 0 = no partner) and the OUTPUT rows per 4096-row tile
+// (an outer join emits one null-extended row for an unmatched probe row).  cnt32 is 4 bytes per group: 40 MB at 10M groups,
+// L2-resident, where the 64-bit counts were not.
 __global__ void __launch_bounds__(kBlock) probe_counts_kernel(const uint32_t* __restrict__ ids, BitmapReader ids_valid, BitmapReader keys_valid,
-                                                              const unsigned long long* __restrict__ cnt, int64_t n, bool outer,
+                                                              const uint32_t* __restrict__ cnt32, int64_t n, bool outer,
                                                               uint32_t* __restrict__ counts, int64_t* __restrict__ tile_sums) {
   const int64_t tile = blockIdx.x;
   int64_t local = 0;
   for (int r = threadIdx.x; r < kScanTile; r += kBlock) {
     const int64_t i = tile * kScanTile + r;
     if (i >= n) break;
-    unsigned long long c = 0;
-    if (ids_valid.bit(i) && keys_valid.bit(i)) c = cnt[ids[i]];
-    if (c > 0xffffffffull) c = 0xffffffffull;  // caught by the caller through the total (pairs do not fit anyway)
-    if (c == 0 && outer) c = 1;
-    counts[i] = static_cast<uint32_t>(c);
-    local += static_cast<int64_t>(c);
+    uint32_t c = 0;
+    if (ids_valid.bit(i) && keys_valid.bit(i)) c = cnt32[ids[i]];
+    counts[i] = c;
+    local += (c == 0 && outer) ? 1 : static_cast<int64_t>(c);
   }
   const int64_t s = block_sum<kBlock>(local);
   if (threadIdx.x == 0) tile_sums[tile] = s;
+}
+
+// per group: cnt32[g] = its build rows (saturated), where32[g] = the build row itself when there is exactly one (the
+// dimension-table case: the emit pass then needs ONE random access per probe row), else the start of its run in build_rows
+__global__ void __launch_bounds__(kBlock) group_records_kernel(const unsigned long long* __restrict__ cnt, const int64_t* __restrict__ run_start,
+                                                               const uint32_t* __restrict__ build_rows, int64_t groups,
+                                                               uint32_t* __restrict__ cnt32, uint32_t* __restrict__ where32) {
+  for (int64_t g = blockIdx.x * (int64_t)kBlock + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kBlock) {
+    const unsigned long long c = cnt[g];
+    cnt32[g] = c > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(c);
+    if (where32) where32[g] = c == 0 ? 0u : (c == 1 ? build_rows[run_start[g]] : static_cast<uint32_t>(run_start[g]));
+  }
 }
 
 // single block: exclusive scan of up to ~2^31 tile sums (1024 threads, each a contiguous span); total -> *total
@@ -109,9 +120,10 @@ __global__ void __launch_bounds__(kBlock) tile_sums_u64_kernel(const unsigned lo
 }
 
 // tile-local exclusive scan (one thread block per tile, 16 consecutive elements per thread) + the tile's offset
+//   min_one: a zero counts as one (the null-extended row of an outer join)
 template <typename In>
 __global__ void __launch_bounds__(kBlock) tile_scan_kernel(const In* __restrict__ v, int64_t n, const int64_t* __restrict__ tile_offsets,
-                                                           int64_t* __restrict__ out) {
+                                                           int64_t* __restrict__ out, bool min_one) {
   __shared__ int64_t warp_tot[kBlock / 32];
   constexpr int kPer = kScanTile / kBlock;
   const int64_t tile = blockIdx.x;
@@ -120,6 +132,7 @@ __global__ void __launch_bounds__(kBlock) tile_scan_kernel(const In* __restrict_
 #pragma unroll
   for (int k = 0; k < kPer; ++k) {
     vals[k] = i0 + k < n ? static_cast<int64_t>(v[i0 + k]) : 0;
+    if (min_one && i0 + k < n && vals[k] == 0) vals[k] = 1;
     sum += vals[k];
   }
   int64_t incl = sum;
@@ -141,31 +154,32 @@ __global__ void __launch_bounds__(kBlock) tile_scan_kernel(const In* __restrict_
   }
 }
 
-// one thread per probe row: its pairs go to [row_off[i], row_off[i] + counts[i])
-__global__ void __launch_bounds__(kBlock) emit_pairs_kernel(const uint32_t* __restrict__ ids, BitmapReader ids_valid, BitmapReader keys_valid,
-                                                            const unsigned long long* __restrict__ cnt, const int64_t* __restrict__ run_start,
-                                                            const uint32_t* __restrict__ build_rows, const int64_t* __restrict__ row_off,
-                                                            int64_t n, uint32_t* __restrict__ out_left, uint32_t* __restrict__ out_right,
-                                                            bool outer) {
+// one thread per probe row: its pairs go to [row_off[i], row_off[i] + max(counts[i], outer)); the match count comes from the
+// streamed counts[], so the only random accesses are where32[g] and -- for groups with several build rows -- their run
+__global__ void __launch_bounds__(kBlock) emit_pairs_kernel(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ counts,
+                                                            const uint32_t* __restrict__ where32, const uint32_t* __restrict__ build_rows,
+                                                            const int64_t* __restrict__ row_off, int64_t n, uint32_t* __restrict__ out_left,
+                                                            uint32_t* __restrict__ out_right, bool outer) {
   for (int64_t i = blockIdx.x * (int64_t)kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-    const int64_t base = row_off[i];
-    unsigned long long c = 0;
-    uint32_t g = 0;
-    if (ids_valid.bit(i) && keys_valid.bit(i)) {
-      g = ids[i];
-      c = cnt[g];
-    }
+    const uint32_t c = counts[i];
     if (c == 0) {
-      if (outer) {  // LEFT OUTER: the null-extended row, marked for right_validity_kernel (no row number reaches 2^32 - 16)
+      if (outer) {  // the null-extended row, marked for the validity pass (no row number reaches 2^32 - 16)
+        const int64_t base = row_off[i];
         out_left[base] = static_cast<uint32_t>(i);
         out_right[base] = kNoMatch;
       }
       continue;
     }
-    const int64_t r0 = run_start[g];
-    for (unsigned long long k = 0; k < c; ++k) {
+    const int64_t base = row_off[i];
+    const uint32_t w = where32[ids[i]];
+    if (c == 1) {
+      out_left[base] = static_cast<uint32_t>(i);
+      out_right[base] = w;
+      continue;
+    }
+    for (uint32_t k = 0; k < c; ++k) {
       out_left[base + k] = static_cast<uint32_t>(i);
-      out_right[base + k] = build_rows[r0 + k];
+      out_right[base + k] = build_rows[static_cast<int64_t>(w) + k];
     }
   }
 }
@@ -343,7 +357,7 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
 
   ScalarSlot slot(ctx);
   B2_RETURN_NOT_OK(slot.zero(s));
-  Temp run_start(ctx, s), build_rows(ctx, s);
+  Temp run_start(ctx, s), build_rows(ctx, s), cnt32(ctx, s), where32(ctx, s);
   if (pairs) {
     const int64_t g_tiles = (static_cast<int64_t>(groups) + kScanTile - 1) / kScanTile;
     Temp g_sums(ctx, s), g_offs(ctx, s);
@@ -355,7 +369,7 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
       B2_LAUNCHED();
       scan_tiles_kernel<<<1, 1024, 0, s>>>(g_sums.as<int64_t>(), g_tiles, g_offs.as<int64_t>(), nullptr);
       B2_LAUNCHED();
-      tile_scan_kernel<unsigned long long><<<(unsigned)g_tiles, kBlock, 0, s>>>(d_cnt, groups, g_offs.as<int64_t>(), run_start.as<int64_t>());
+      tile_scan_kernel<unsigned long long><<<(unsigned)g_tiles, kBlock, 0, s>>>(d_cnt, groups, g_offs.as<int64_t>(), run_start.as<int64_t>(), false);
       B2_LAUNCHED();
     }
     // right rows grouped by id (stable), rows with a null key last: the radix sort of the ids with the key validity as theirs
@@ -369,6 +383,13 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
     B2_RETURN_NOT_OK(b2_cast_numeric(ctx, &order.a, &narrow, &order32.a, s));
     build_rows.ptr = const_cast<void*>(order32.a.data);
     order32.a.data = nullptr;
+    B2_RETURN_NOT_OK(cnt32.alloc(sizeof(uint32_t) * (size_t)(groups ? groups : 1)));
+    B2_RETURN_NOT_OK(where32.alloc(sizeof(uint32_t) * (size_t)(groups ? groups : 1)));
+    if (groups) {
+      group_records_kernel<<<grid_for(groups, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_cnt, run_start.as<int64_t>(), build_rows.as<uint32_t>(), groups,
+                                                                               cnt32.as<uint32_t>(), where32.as<uint32_t>());
+      B2_LAUNCHED();
+    }
   }
 
   // ---- probe ----
@@ -412,12 +433,12 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
   B2_RETURN_NOT_OK(row_off.alloc(sizeof(int64_t) * (size_t)(nl ? nl : 1)));
   int64_t total = 0;
   if (nl > 0) {
-    probe_counts_kernel<<<(unsigned)l_tiles, kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, d_cnt, nl, outer, counts.as<uint32_t>(),
+    probe_counts_kernel<<<(unsigned)l_tiles, kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, cnt32.as<uint32_t>(), nl, outer, counts.as<uint32_t>(),
                                                             l_sums.as<int64_t>());
     B2_LAUNCHED();
     scan_tiles_kernel<<<1, 1024, 0, s>>>(l_sums.as<int64_t>(), l_tiles, l_offs.as<int64_t>(), slot.dev());
     B2_LAUNCHED();
-    tile_scan_kernel<uint32_t><<<(unsigned)l_tiles, kBlock, 0, s>>>(counts.as<uint32_t>(), nl, l_offs.as<int64_t>(), row_off.as<int64_t>());
+    tile_scan_kernel<uint32_t><<<(unsigned)l_tiles, kBlock, 0, s>>>(counts.as<uint32_t>(), nl, l_offs.as<int64_t>(), row_off.as<int64_t>(), outer);
     B2_LAUNCHED();
     B2_RETURN_NOT_OK(slot.fetch(s));
     total = slot.host()[0];
@@ -469,7 +490,7 @@ extern "C" int b2_hash_join(B2Context* ctx, const B2Array* left_keys, const B2Ar
     B2_CUDA(cudaMemsetAsync(lbits.ptr, 0, bitmap_alloc_bytes(total), s));
   }
   if (head > 0) {
-    emit_pairs_kernel<<<grid_for(nl, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_lids, lid_valid, lkey_valid, d_cnt, run_start.as<int64_t>(),
+    emit_pairs_kernel<<<grid_for(nl, kBlock * 4, kSMs * 8), kBlock, 0, s>>>(d_lids, counts.as<uint32_t>(), where32.as<uint32_t>(),
                                                                           build_rows.as<uint32_t>(), row_off.as<int64_t>(), nl,
                                                                           ol.as<uint32_t>(), orr.as<uint32_t>(), outer);
     B2_LAUNCHED();
