@@ -57,6 +57,15 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        # NVML is initialised HERE, before the timed region: nvmlInit can take longer than the whole ~150 ms region, which
+        # once left a run with a single sample
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self._nvml = None
 
     def run(self):
         # NVML in-process (same counters nvidia-smi prints, but every 10 ms: the device-resident timed region
@@ -67,9 +76,9 @@ class ClockSampler(threading.Thread):
             self._smi_loop()
 
     def _nvml_loop(self):
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        if self._nvml is None:
+            raise RuntimeError("NVML unavailable")
+        pynvml, h = self._nvml
         mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
         bits = [0x8, 0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap (nvml.h)
