@@ -775,6 +775,51 @@ int main(int argc, char** argv) {
                 << " groups; intermediate batches stayed on the device)" << std::endl;
     }
   }
+  // ---- (r2) aggregate plan with a utf8 key (+ an int64 second key) and hash_count_distinct of a utf8 column ----
+  {
+    namespace ac = arrow::acero;
+    const int64_t rows = 90000;
+    auto pick = RandomNumeric<arrow::Int32Type>(rows, 0.05, 401, 0, 199);
+    auto pick2 = RandomNumeric<arrow::Int32Type>(rows, 0.05, 402, 0, 30);
+    auto region = RandomNumeric<arrow::Int64Type>(rows, 0.02, 403, 0, 3);
+    auto val = RandomNumeric<arrow::Int64Type>(rows, 0.1, 404, -100, 100);
+    auto to_words = [&](const std::shared_ptr<arrow::Array>& ids, const std::string& prefix) {
+      arrow::StringBuilder sb;
+      const auto& iv = static_cast<const arrow::Int32Array&>(*ids);
+      for (int64_t i = 0; i < iv.length(); ++i) {
+        if (iv.IsNull(i)) (void)sb.AppendNull();
+        else (void)sb.Append(prefix + std::string(static_cast<size_t>(iv.Value(i) % 5), 'x') + std::to_string(iv.Value(i)));
+      }
+      return UNWRAP(sb.Finish());
+    };
+    auto city = to_words(pick, "city-"), tag = to_words(pick2, "t");
+    auto stab = arrow::Table::Make(arrow::schema({arrow::field("city", arrow::utf8()), arrow::field("region", arrow::int64()),
+                                                  arrow::field("tag", arrow::utf8()), arrow::field("v", arrow::int64())}),
+                                   {city, region, tag, val});
+    std::vector<cp::Aggregate> saggs = {{"hash_sum", nullptr, "v", "v_sum"}, {"hash_count", nullptr, "v", "v_count"},
+                                        {"hash_count_distinct", nullptr, "tag", "tags"}, {"hash_max", nullptr, "v", "v_max"}};
+    auto run_s = [&](const std::string& factory) {
+      ac::Declaration plan = ac::Declaration::Sequence({{"table_source", ac::TableSourceNodeOptions(stab, 1 << 15)},
+                                                        {factory, ac::AggregateNodeOptions(saggs, {"city", "region"})}});
+      auto t = UNWRAP(ac::DeclarationToTable(std::move(plan), /*use_threads=*/false));
+      auto idx = UNWRAP(cp::SortIndices(Datum(t), cp::SortOptions({cp::SortKey("city"), cp::SortKey("region")}), &h.cpu_ctx));
+      return UNWRAP(cp::Take(Datum(t), Datum(idx), cp::TakeOptions::Defaults(), &h.cpu_ctx)).table()->CombineChunks().ValueOrDie();
+    };
+    auto swant = run_s("aggregate"), sgot = run_s("b200_aggregate");
+    ++g_checks;
+    bool same = sgot->num_rows() == swant->num_rows();
+    for (const char* name : {"city", "region", "v_sum", "v_count", "tags", "v_max"}) {
+      auto a = sgot->GetColumnByName(name), b = swant->GetColumnByName(name);
+      same = same && a && b && a->Equals(*b);
+    }
+    if (!same) {
+      std::cout << "FAIL b200_aggregate with a (utf8, int64) key\n want " << swant->ToString().substr(0, 500) << "\n got " << sgot->ToString().substr(0, 500) << std::endl;
+      return 1;
+    }
+    std::cout << "OK   b200_aggregate == aggregate with a (utf8, int64) key: hash_sum / hash_count / hash_count_distinct(utf8) / hash_max, "
+              << sgot->num_rows() << " groups" << std::endl;
+  }
+
   // ---- (r2) hash join: stock "hashjoin" vs "b200_hashjoin" over the same two tables, rows compared sorted by every column
   //      (the join's output order is unspecified in the reference) ----
   {
