@@ -902,7 +902,7 @@ struct HashAggKernelData : public cp::KernelState {
 
 static std::shared_ptr<DataType> HashAggOutType(int kind, const DataType& in) {
   switch (kind) {
-    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: return arrow::int64();
+    case B2_HASH_COUNT: case B2_HASH_COUNT_ALL: case B2_HASH_COUNT_DISTINCT: return arrow::int64();
     case B2_HASH_MEAN: return arrow::float64();
     case B2_HASH_ANY: case B2_HASH_ALL: return arrow::boolean();
     case B2_HASH_SUM: case B2_HASH_PRODUCT:
