@@ -439,6 +439,16 @@ def sort_indices(arr: pa.Array, order: str = "ascending", null_placement: str = 
     return make_array(pa.uint64(), out)
 
 
+def select_k_unstable(arr: pa.Array, k: int, order: str = "ascending", null_placement: str = "at_end") -> pa.Array:
+    """select_k_unstable (ArraySelector, kernels/vector_select_k.cc:157-232): the first k rows of the sort order.  The
+    reference's selection is unstable (ties in any order); this restatement -- like the CUDA path -- returns the stable
+    sort's prefix, one of the permitted answers.  NaNs / nulls follow the values as in sort_indices (the installed
+    24.0.0 binary never selects them; /root/reference does, per null_placement)."""
+    if k < 0:
+        raise pa.ArrowInvalid(f"select_k_unstable requires a nonnegative `k`, got {k}")
+    return sort_indices(arr, order, null_placement).slice(0, min(k, len(arr)))
+
+
 def sort_indices_multi(columns, sort_keys, null_placement: str = "at_end") -> pa.Array:
     """SortIndices over a record batch (kernels/vector_sort.cc:386-600): lexicographic over sort_keys = [(name, order)],
     stable.  Restated as the reference's own fallback states it -- a stable sort per key from the least significant key

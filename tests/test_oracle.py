@@ -406,3 +406,19 @@ def test_hash_join_indices_vs_reference(join_type):
     assert mine == ref
     head = [x for x in l.to_pylist() if x is not None]
     assert head == sorted(head)  # left-row order
+
+
+@pytest.mark.parametrize("t", [pa.int64(), pa.float64(), pa.uint16()], ids=str)
+@pytest.mark.parametrize("order", ["ascending", "descending"])
+def test_select_k_vs_reference(t, order):
+    """oracle select_k_unstable against the reference binary: same selected VALUES while k stays inside the non-null,
+    non-NaN values (ties may be broken differently; the 24.0.0 binary stops at the last such value)."""
+    arr = random_array(t, 5000, 0.1, SEED + 21, lo=0, hi=300, offset=2)
+    n_values = len(arr) - arr.null_count
+    for k in (0, 1, 17, 999, n_values):
+        mine = ora.select_k_unstable(arr, k, order)
+        ref = pc.select_k_unstable(arr, k, [("x", order)])
+        assert len(mine) == len(ref) == k
+        assert pc.take(arr, mine).equals(pc.take(arr, ref))
+    with pytest.raises(pa.ArrowInvalid):
+        ora.select_k_unstable(arr, -1)
